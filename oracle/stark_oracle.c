@@ -1,0 +1,1094 @@
+/*
+ * stark_oracle.c -- CPU restatement of the stark-rs hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * This file is the parity oracle for the B200 back end.  It is NOT part of the product:
+ * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg
+ * may load it.  Nothing under stark-rs_b200/ links, imports or calls it.
+ *
+ * It follows the reference (0xSooki/stark-rs, /root/reference/src) function by function,
+ * keeping the reference's algorithms (u128 % p reduction, recursive xgcd, schoolbook
+ * multiply, Horner evaluation, O(n^3) Lagrange interpolation, byte-serial hash,
+ * Vec-of-levels Merkle tree, per-element exp + 2x div FRI fold).  Every function cites the
+ * reference file:line it restates.
+ *
+ * PINNING STATUS
+ *   - field + polynomial arithmetic: pinned by the reference's own known-answer tests
+ *     (ff.rs:359-724, univariate tests) -- see tests/test_oracle_kat.py.
+ *   - hash digests, Merkle roots, Fiat-Shamir challenges, FRI codewords, proof bytes:
+ *     PARITY UNPINNED by reference-emitted values.  The reference pins no digest/root/proof
+ *     byte anywhere (its hash/merkle/fri tests are property tests, hash.rs:104-149,
+ *     merkle.rs:99-133, fri.rs:527-693) and it cannot be compiled here (no rustc/cargo in
+ *     the image).  The oracle is instead pinned by (i) those property tests, including
+ *     Fri::verify == true on the four statements of fri.rs:532-693, and (ii) the
+ *     survey-derived vectors of SURVEY.md 8(c), produced by an independent Python
+ *     restatement (tests/golden/survey_vectors.json).
+ *
+ * Error convention: a reference panic/assert becomes a longjmp to the API entry, which
+ * returns 1 and leaves the panic message in oracle_last_error().
+ */
+#include <setjmp.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef uint64_t u64;
+typedef uint8_t u8;
+typedef unsigned __int128 u128;
+typedef __int128 i128;
+
+static __thread jmp_buf g_env;
+static __thread int g_env_set = 0;
+static __thread char g_err[256];
+
+static void panic_(const char *msg) {
+  snprintf(g_err, sizeof g_err, "%s", msg);
+  if (g_env_set) longjmp(g_env, 1);
+  fprintf(stderr, "oracle panic outside API: %s\n", msg);
+  abort();
+}
+const char *oracle_last_error(void) { return g_err; }
+
+#define API_ENTER()            \
+  g_err[0] = 0;                \
+  g_env_set = 1;               \
+  if (setjmp(g_env)) {         \
+    g_env_set = 0;             \
+    return 1;                  \
+  }
+#define API_LEAVE() \
+  g_env_set = 0;    \
+  return 0;
+
+static void *xmalloc(size_t n) {
+  void *p = malloc(n ? n : 1);
+  if (!p) panic_("oracle: out of memory");
+  return p;
+}
+
+/* ------------------------------------------------------------------ ff.rs */
+
+/* ff.rs:138-144 */
+static u64 ff_mul(u64 p, u64 l, u64 r) { return (u64)(((u128)l * (u128)r) % (u128)p); }
+/* ff.rs:146-152 */
+static u64 ff_add(u64 p, u64 l, u64 r) { return (u64)(((u128)l + (u128)r) % (u128)p); }
+/* ff.rs:154-160 ; p + l - r underflows (debug panic) when r > p + l */
+static u64 ff_sub(u64 p, u64 l, u64 r) {
+  u128 s = (u128)p + (u128)l;
+  if ((u128)r > s) panic_("attempt to subtract with overflow");
+  return (u64)((s - (u128)r) % (u128)p);
+}
+/* ff.rs:162-167 ; u64 p - v underflows when v > p */
+static u64 ff_neg(u64 p, u64 v) {
+  if (v > p) panic_("attempt to subtract with overflow");
+  return (p - v) % p;
+}
+/* utils.rs:3-13, recursive extended Euclid in i128 */
+static void xgcd(u64 x, u64 y, i128 *g, i128 *a, i128 *b) {
+  if (y == 0) {
+    *g = (i128)x;
+    *a = 1;
+    *b = 0;
+    return;
+  }
+  i128 g1, x1, y1;
+  xgcd(y, x % y, &g1, &x1, &y1);
+  *g = g1;
+  *a = y1;
+  *b = x1 - ((i128)x / (i128)y) * y1;
+}
+/* ff.rs:169-178 */
+static u64 ff_inv(u64 p, u64 v) {
+  i128 g, x, y;
+  xgcd(v, p, &g, &x, &y);
+  if (g != 1) panic_("no inverse");
+  i128 pp = (i128)p;
+  i128 inv = ((x % pp) + pp) % pp;
+  return (u64)inv;
+}
+/* ff.rs:181-189 */
+static u64 ff_div(u64 p, u64 l, u64 r) {
+  if (r == 0) panic_("no division by zero");
+  u64 rinv = ff_inv(p, r);
+  return (u64)(((u128)l * (u128)rinv) % (u128)p);
+}
+/* ff.rs:191-197 */
+static u64 ff_g(u64 p) {
+  if (p != 998244353ull) panic_("assertion failed: self.p == 998244353");
+  return 3;
+}
+/* ff.rs:200-213 */
+static u64 ff_exp(u64 p, u64 base, u64 e) {
+  u64 res = 1;
+  while (e > 0) {
+    if (e % 2 == 1) res = ff_mul(p, res, base);
+    base = ff_mul(p, base, base);
+    e >>= 1;
+  }
+  return res;
+}
+/* ff.rs:215-223 */
+static u64 ff_prim_nth_root(u64 p, u64 n) {
+  if (p != 998244353ull) panic_("assertion failed: self.p == 998244353");
+  if (n == 0) panic_("attempt to subtract with overflow");
+  if ((n & (n - 1)) != 0) panic_("n must be a power of two");
+  if (n > (1ull << 23)) panic_("n > 2^23 not supported by this modulus");
+  u64 g = ff_g(p);
+  return ff_exp(p, g, (p - 1) / n);
+}
+/* ff.rs:225-232 */
+static u64 ff_sample(u64 p, const u8 *salt, size_t n) {
+  u64 acc = 0;
+  for (size_t i = 0; i < n; i++) {
+    acc = (u64)((((u128)acc) << 8) % (u128)p);
+    acc = (u64)((((u128)acc) ^ (u128)salt[i]) % (u128)p);
+  }
+  return acc;
+}
+
+/* ------------------------------------------------------- univariate .rs files */
+
+typedef struct {
+  u64 *c;
+  size_t n;
+} Poly; /* coeffs low -> high, mod.rs:8-11 */
+
+static Poly poly_alloc(size_t n) {
+  Poly r;
+  r.c = (u64 *)xmalloc(n * sizeof(u64));
+  r.n = n;
+  memset(r.c, 0, n * sizeof(u64));
+  return r;
+}
+static Poly poly_clone(const Poly *a) {
+  Poly r = poly_alloc(a->n);
+  memcpy(r.c, a->c, a->n * sizeof(u64));
+  return r;
+}
+static void poly_free(Poly *a) {
+  free(a->c);
+  a->c = NULL;
+  a->n = 0;
+}
+/* mod.rs:54-68 */
+static i128 poly_deg(const Poly *a) {
+  if (a->n == 0) return -1;
+  int all0 = 1;
+  for (size_t i = 0; i < a->n; i++)
+    if (a->c[i] != 0) {
+      all0 = 0;
+      break;
+    }
+  if (all0) return -1;
+  size_t maxidx = 0;
+  for (size_t i = 0; i < a->n; i++)
+    if (a->c[i] != 0) maxidx = i;
+  return (i128)maxidx;
+}
+/* mod.rs:70-75 */
+static Poly poly_neg(u64 p, const Poly *a) {
+  Poly r = poly_alloc(a->n);
+  for (size_t i = 0; i < a->n; i++) r.c[i] = ff_neg(p, a->c[i]);
+  return r;
+}
+/* add.rs:6-32 */
+static Poly poly_add(u64 p, const Poly *l, const Poly *r) {
+  if (poly_deg(l) == -1) return poly_clone(r);
+  if (poly_deg(r) == -1) return poly_clone(l);
+  size_t n = l->n > r->n ? l->n : r->n;
+  Poly o = poly_alloc(n);
+  for (size_t i = 0; i < n; i++) {
+    u64 a = i < l->n ? l->c[i] : 0, b = i < r->n ? r->c[i] : 0;
+    o.c[i] = ff_add(p, a, b);
+  }
+  return o;
+}
+/* sub.rs:8-34 */
+static Poly poly_sub(u64 p, const Poly *l, const Poly *r) {
+  if (poly_deg(l) == -1) return poly_neg(p, r);
+  if (poly_deg(r) == -1) return poly_clone(l);
+  size_t n = l->n > r->n ? l->n : r->n;
+  Poly o = poly_alloc(n);
+  for (size_t i = 0; i < n; i++) {
+    u64 a = i < l->n ? l->c[i] : 0, b = i < r->n ? r->c[i] : 0;
+    o.c[i] = ff_sub(p, a, b);
+  }
+  return o;
+}
+/* mul.rs:6-29 : schoolbook; [] if either side is zero; length by vector length */
+static Poly poly_mul(u64 p, const Poly *l, const Poly *r) {
+  if (poly_deg(l) == -1 || poly_deg(r) == -1) return poly_alloc(0);
+  Poly o = poly_alloc(l->n + r->n - 1);
+  for (size_t i = 0; i < l->n; i++) {
+    u64 a = l->c[i];
+    if (a == 0) continue;
+    for (size_t j = 0; j < r->n; j++) o.c[i + j] = ff_add(p, o.c[i + j], ff_mul(p, a, r->c[j]));
+  }
+  return o;
+}
+/* mod.rs:126-131 */
+static u64 poly_leading_coeff(const Poly *a) {
+  i128 d = poly_deg(a);
+  if (d == -1) panic_("Zero polynomial has no leading coefficient");
+  return a->c[(size_t)d];
+}
+/* div.rs:6-42 : long division, each step a full mul + sub */
+static void poly_div(u64 p, const Poly *numer, const Poly *denom, Poly *q_out, Poly *r_out) {
+  if (poly_deg(denom) == -1) panic_("No division by zero");
+  if (poly_deg(numer) < poly_deg(denom)) {
+    *q_out = poly_alloc(0);
+    *r_out = poly_clone(numer);
+    return;
+  }
+  Poly q = poly_alloc((size_t)(poly_deg(numer) - poly_deg(denom) + 1));
+  Poly r = poly_clone(numer);
+  while (poly_deg(&r) >= poly_deg(denom)) {
+    u64 coeff = ff_div(p, poly_leading_coeff(&r), poly_leading_coeff(denom));
+    size_t shift = (size_t)(poly_deg(&r) - poly_deg(denom));
+    Poly sp = poly_alloc(shift + 1);
+    sp.c[shift] = coeff;
+    Poly subtractee = poly_mul(p, &sp, denom);
+    q.c[shift] = coeff;
+    Poly nr = poly_sub(p, &r, &subtractee);
+    poly_free(&sp);
+    poly_free(&subtractee);
+    poly_free(&r);
+    r = nr;
+  }
+  *q_out = q;
+  *r_out = r;
+}
+/* exp.rs:6-33 */
+static Poly poly_exp(u64 p, const Poly *base, u64 e) {
+  if (e == 0) {
+    Poly o = poly_alloc(1);
+    o.c[0] = 1;
+    return o;
+  }
+  if (poly_deg(base) == -1) return poly_alloc(0);
+  Poly result = poly_alloc(1);
+  result.c[0] = 1;
+  Poly bpower = poly_clone(base);
+  while (e != 0) {
+    if (e & 1) {
+      Poly t = poly_mul(p, &result, &bpower);
+      poly_free(&result);
+      result = t;
+    }
+    Poly t2 = poly_mul(p, &bpower, &bpower);
+    poly_free(&bpower);
+    bpower = t2;
+    e >>= 1;
+  }
+  poly_free(&bpower);
+  return result;
+}
+/* eval.rs:6-14 : forward-power Horner */
+static u64 poly_eval(u64 p, const Poly *a, u64 x) {
+  u64 xi = 1, val = 0;
+  for (size_t i = 0; i < a->n; i++) {
+    val = ff_add(p, val, ff_mul(p, a->c[i], xi));
+    xi = ff_mul(p, xi, x);
+  }
+  return val;
+}
+/* mod.rs:77-96 : sequential product of (x - d) */
+static Poly poly_zerofier(u64 p, const u64 *domain, size_t n) {
+  if (n == 0) panic_("index out of bounds: the len is 0 but the index is 0");
+  Poly x = poly_alloc(2);
+  x.c[1] = 1;
+  Poly acc = poly_alloc(1);
+  acc.c[0] = 1;
+  for (size_t i = 0; i < n; i++) {
+    Poly d = poly_alloc(1);
+    d.c[0] = domain[i];
+    Poly lin = poly_sub(p, &x, &d);
+    Poly t = poly_mul(p, &acc, &lin);
+    poly_free(&d);
+    poly_free(&lin);
+    poly_free(&acc);
+    acc = t;
+  }
+  poly_free(&x);
+  return acc;
+}
+/* mod.rs:99-113 : f(cX), a fresh exp per coefficient */
+static Poly poly_scale(u64 p, const Poly *a, u64 factor) {
+  Poly o = poly_alloc(a->n);
+  for (size_t i = 0; i < a->n; i++) o.c[i] = ff_mul(p, ff_exp(p, factor, (u64)i), a->c[i]);
+  return o;
+}
+/* interpolate.rs:6-44 : Lagrange, O(n^3) */
+static Poly poly_interpolate(u64 p, const u64 *domain, const u64 *values, size_t n) {
+  if (n == 0) panic_("assertion failed: domain.len() > 0");
+  Poly x = poly_alloc(2);
+  x.c[1] = 1;
+  Poly acc = poly_alloc(1); /* [0] */
+  for (size_t i = 0; i < n; i++) {
+    Poly prod = poly_alloc(1);
+    prod.c[0] = values[i];
+    for (size_t j = 0; j < n; j++) {
+      if (j == i) continue;
+      Poly xj = poly_alloc(1);
+      xj.c[0] = domain[j];
+      u64 denom = ff_inv(p, ff_sub(p, domain[i], domain[j]));
+      Poly lin = poly_sub(p, &x, &xj);
+      Poly t = poly_mul(p, &prod, &lin);
+      poly_free(&xj);
+      poly_free(&lin);
+      poly_free(&prod);
+      prod = t;
+      for (size_t k = 0; k < prod.n; k++) prod.c[k] = ff_mul(p, prod.c[k], denom);
+    }
+    Poly t = poly_add(p, &acc, &prod);
+    poly_free(&acc);
+    poly_free(&prod);
+    acc = t;
+  }
+  poly_free(&x);
+  return acc;
+}
+
+/* ---------------------------------------------------------------- hash.rs */
+
+static const u8 PRIMES[16] = {2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37, 41, 43, 47, 53}; /* hash.rs:53 */
+static const u8 ROUND_CONSTANTS[32] = {                                                   /* hash.rs:96-99 */
+    0x01, 0x02, 0x04, 0x08, 0x10, 0x20, 0x40, 0x80, 0x1b, 0x36, 0x6c, 0xd8, 0xab, 0x4d, 0x9a, 0x2f,
+    0x5e, 0xbc, 0x63, 0xc6, 0x97, 0x35, 0x6a, 0xd4, 0xb3, 0x7d, 0xfa, 0xef, 0xc5, 0x91, 0x39, 0x72};
+
+/* hash.rs:55-57 */
+static u8 rotate_left(u8 b, u8 n) { return (u8)((b << n) | (b >> (8 - n))); }
+/* hash.rs:88-94 */
+static u8 sbox(u8 b) {
+  u8 r = b;
+  r = (u8)(r * 251u);
+  r = rotate_left(r, 1);
+  r ^= 0x63;
+  return r;
+}
+/* hash.rs:59-86 */
+static void mix_state(u8 s[32]) {
+  for (int i = 0; i < 32; i++) s[i] = sbox(s[i]);
+  for (int i = 0; i < 8; i++) {
+    int b = i * 4;
+    u8 t0 = s[b], t1 = s[b + 1], t2 = s[b + 2], t3 = s[b + 3];
+    s[b] = t0 ^ t1 ^ t3;
+    s[b + 1] = t0 ^ t2 ^ t3;
+    s[b + 2] = t0 ^ t1 ^ t2;
+    s[b + 3] = t1 ^ t2 ^ t3;
+  }
+  for (int i = 0; i < 32; i++) {
+    int next = (i + 1) % 32;
+    int prev = i == 0 ? 31 : i - 1;
+    s[i] = (u8)(s[i] + s[next] + s[prev]);
+  }
+  for (int i = 0; i < 32; i++) s[i] = (u8)(s[i] + ROUND_CONSTANTS[i]);
+}
+/* hash.rs:7-30 */
+static void hash_from_bytes(const u8 *bytes, size_t n, u8 out[32]) {
+  u8 s[32];
+  for (int i = 0; i < 32; i++) s[i] = PRIMES[i % 16];
+  for (size_t off = 0, chunk_idx = 0; off < n; off += 32, chunk_idx++) {
+    size_t len = n - off < 32 ? n - off : 32;
+    for (size_t i = 0; i < len; i++) {
+      size_t pos = (i + chunk_idx * 32) % 32;
+      s[pos] = (u8)(s[pos] + bytes[off + i]);
+      s[pos] = rotate_left(s[pos], 3);
+      s[(pos + 7) % 32] ^= s[pos];
+    }
+    mix_state(s);
+  }
+  for (int k = 0; k < 8; k++) mix_state(s);
+  memcpy(out, s, 32);
+}
+/* hash.rs:32-35 : little-endian u64 bytes */
+static void hash_from_field_elements(const u64 *e, size_t n, u8 out[32]) {
+  u8 *buf = (u8 *)xmalloc(n * 8);
+  for (size_t i = 0; i < n; i++)
+    for (int b = 0; b < 8; b++) buf[i * 8 + b] = (u8)(e[i] >> (8 * b));
+  hash_from_bytes(buf, n * 8, out);
+  free(buf);
+}
+/* hash.rs:37-39 */
+static void hash_from_u64(u64 v, u8 out[32]) { hash_from_field_elements(&v, 1, out); }
+/* hash.rs:41-46 */
+static void hash_combine(const u8 l[32], const u8 r[32], u8 out[32]) {
+  u8 c[64];
+  memcpy(c, l, 32);
+  memcpy(c + 32, r, 32);
+  hash_from_bytes(c, 64, out);
+}
+
+/* -------------------------------------------------------------- merkle.rs */
+
+typedef struct {
+  size_t n_leaves;
+  size_t n_levels; /* nodes.len() = log2(n)+1 */
+  u8 **nodes;      /* nodes[level] = 32 * (n >> level) bytes ; nodes[0] = leaves */
+  u8 root[32];
+} Merkle;
+
+/* merkle.rs:11-38 */
+static Merkle merkle_new(const u8 *leaves, size_t n) {
+  if (n == 0) panic_("Cannot create tree from empty leaves");
+  if ((n & (n - 1)) != 0) panic_("Number of leaves must be power of 2");
+  Merkle t;
+  t.n_leaves = n;
+  size_t lv = 1;
+  for (size_t m = n; m > 1; m >>= 1) lv++;
+  t.n_levels = lv;
+  t.nodes = (u8 **)xmalloc(lv * sizeof(u8 *));
+  t.nodes[0] = (u8 *)xmalloc(n * 32);
+  memcpy(t.nodes[0], leaves, n * 32);
+  size_t cur = n;
+  for (size_t l = 1; l < lv; l++) {
+    size_t nxt = cur / 2;
+    t.nodes[l] = (u8 *)xmalloc(nxt * 32);
+    for (size_t i = 0; i < cur; i += 2)
+      hash_combine(t.nodes[l - 1] + 32 * i, t.nodes[l - 1] + 32 * (i + 1), t.nodes[l] + 32 * (i / 2));
+    cur = nxt;
+  }
+  memcpy(t.root, t.nodes[lv - 1], 32);
+  return t;
+}
+static void merkle_free(Merkle *t) {
+  for (size_t l = 0; l < t->n_levels; l++) free(t->nodes[l]);
+  free(t->nodes);
+  t->nodes = NULL;
+}
+/* merkle.rs:67-80 ; writes (n_levels-1) sibling hashes, returns the count */
+static size_t merkle_open(const Merkle *t, size_t index, u8 *out) {
+  if (index >= t->n_leaves) panic_("Index out of bounds");
+  size_t idx = index, k = 0;
+  for (size_t level = 0; level + 1 < t->n_levels; level++) {
+    size_t sib = (idx % 2 == 0) ? idx + 1 : idx - 1;
+    memcpy(out + 32 * k++, t->nodes[level] + 32 * sib, 32);
+    idx /= 2;
+  }
+  return k;
+}
+/* merkle.rs:82-96 */
+static int merkle_verify(const u8 leaf[32], size_t index, const u8 *proof, size_t n_proof, const u8 root[32]) {
+  u8 cur[32], nxt[32];
+  memcpy(cur, leaf, 32);
+  size_t idx = index;
+  for (size_t k = 0; k < n_proof; k++) {
+    if (idx % 2 == 0)
+      hash_combine(cur, proof + 32 * k, nxt);
+    else
+      hash_combine(proof + 32 * k, cur, nxt);
+    memcpy(cur, nxt, 32);
+    idx /= 2;
+  }
+  return memcmp(cur, root, 32) == 0;
+}
+
+/* --------------------------------------------------------- fiat_shamir.rs */
+
+typedef struct {
+  u8 *t;
+  size_t n, cap;
+} Transcript;
+static void fs_init(Transcript *f) { f->t = NULL, f->n = 0, f->cap = 0; }
+static void fs_free(Transcript *f) {
+  free(f->t);
+  fs_init(f);
+}
+/* fiat_shamir.rs:15-17 */
+static void fs_absorb(Transcript *f, const u8 *d, size_t n) {
+  if (f->n + n > f->cap) {
+    f->cap = (f->n + n) * 2 + 64;
+    f->t = (u8 *)realloc(f->t, f->cap);
+    if (!f->t) panic_("oracle: out of memory");
+  }
+  memcpy(f->t + f->n, d, n);
+  f->n += n;
+}
+/* fiat_shamir.rs:19-25 : first 8 hash bytes, LE, UNREDUCED */
+static u64 fs_challenge(const Transcript *f) {
+  u8 h[32];
+  hash_from_bytes(f->t, f->n, h);
+  u64 v = 0;
+  for (int b = 0; b < 8; b++) v |= (u64)h[b] << (8 * b);
+  return v;
+}
+
+/* -------------------------------------------------------------- stream.rs */
+
+enum { OBJ_ROOT = 0, OBJ_FE = 1, OBJ_FES = 2, OBJ_PATH = 3 }; /* tags: stream.rs:40,44,48,55 */
+typedef struct {
+  int tag;
+  size_t count; /* elements (FES) or hashes (PATH) */
+  u8 *data;     /* ROOT: 32 B ; FE: 8 B LE ; FES: 8*count LE ; PATH: 32*count */
+} ProofObj;
+typedef struct {
+  ProofObj *o;
+  size_t n, cap, head; /* head: pop() removes from the front, stream.rs:27-33 */
+} Stream;
+static void st_init(Stream *s) { s->o = NULL, s->n = s->cap = s->head = 0; }
+static void st_free(Stream *s) {
+  for (size_t i = 0; i < s->n; i++) free(s->o[i].data);
+  free(s->o);
+  st_init(s);
+}
+static void st_push(Stream *s, int tag, size_t count, const u8 *data, size_t bytes) {
+  if (s->n == s->cap) {
+    s->cap = s->cap * 2 + 16;
+    s->o = (ProofObj *)realloc(s->o, s->cap * sizeof(ProofObj));
+    if (!s->o) panic_("oracle: out of memory");
+  }
+  ProofObj *p = &s->o[s->n++];
+  p->tag = tag;
+  p->count = count;
+  p->data = (u8 *)xmalloc(bytes);
+  memcpy(p->data, data, bytes);
+}
+static void st_push_fes(Stream *s, const u64 *v, size_t n) {
+  u8 *b = (u8 *)xmalloc(8 * n);
+  for (size_t i = 0; i < n; i++)
+    for (int k = 0; k < 8; k++) b[8 * i + k] = (u8)(v[i] >> (8 * k));
+  st_push(s, OBJ_FES, n, b, 8 * n);
+  free(b);
+}
+static ProofObj *st_pop(Stream *s) { return s->head < s->n ? &s->o[s->head++] : NULL; }
+static void put_u64(u8 *d, u64 v) {
+  for (int k = 0; k < 8; k++) d[k] = (u8)(v >> (8 * k));
+}
+static u64 get_u64(const u8 *d) {
+  u64 v = 0;
+  for (int k = 0; k < 8; k++) v |= (u64)d[k] << (8 * k);
+  return v;
+}
+/* stream.rs:35-64 */
+static size_t st_serialize(const Stream *s, u8 *out, size_t cap) {
+  size_t w = 0;
+#define EMIT(ptr, len)                                \
+  do {                                                \
+    if (out && w + (len) <= cap) memcpy(out + w, (ptr), (len)); \
+    w += (len);                                       \
+  } while (0)
+  for (size_t i = 0; i < s->n; i++) {
+    const ProofObj *p = &s->o[i];
+    u8 tag = (u8)p->tag, cnt[8];
+    EMIT(&tag, 1);
+    switch (p->tag) {
+      case OBJ_ROOT: EMIT(p->data, 32); break;
+      case OBJ_FE: EMIT(p->data, 8); break;
+      case OBJ_FES:
+        put_u64(cnt, p->count);
+        EMIT(cnt, 8);
+        EMIT(p->data, 8 * p->count);
+        break;
+      case OBJ_PATH:
+        put_u64(cnt, p->count);
+        EMIT(cnt, 8);
+        EMIT(p->data, 32 * p->count);
+        break;
+    }
+  }
+#undef EMIT
+  return w;
+}
+/* stream.rs:66-168 : lenient parser (truncated items are dropped, unknown tag stops) */
+static void st_deserialize(Stream *s, const u8 *b, size_t n) {
+  st_init(s);
+  size_t i = 0;
+  while (i < n) {
+    u8 tag = b[i++];
+    if (tag == 0) {
+      if (i + 32 <= n) {
+        st_push(s, OBJ_ROOT, 1, b + i, 32);
+        i += 32;
+      }
+    } else if (tag == 1) {
+      if (i + 8 <= n) {
+        st_push(s, OBJ_FE, 1, b + i, 8);
+        i += 8;
+      }
+    } else if (tag == 2 || tag == 3) {
+      size_t w = tag == 2 ? 8 : 32;
+      if (i + 8 <= n) {
+        u64 len = get_u64(b + i);
+        i += 8;
+        size_t got = 0, start = i;
+        for (u64 k = 0; k < len; k++) {
+          if (i + w <= n) {
+            got++;
+            i += w;
+          }
+        }
+        st_push(s, tag, got, b + start, got * w);
+      }
+    } else
+      break;
+  }
+}
+
+/* ----------------------------------------------------------------- fri.rs */
+
+typedef struct {
+  u64 p, offset, omega;
+  size_t domain_length, expansion_factor, num_colinearity_tests;
+} Fri;
+
+static int is_pow2(size_t n) { return n != 0 && (n & (n - 1)) == 0; }
+/* fri.rs:30-55 */
+static Fri fri_new(u64 p, u64 omega, u64 offset, size_t n, size_t ef, size_t nq) {
+  if (!is_pow2(n)) panic_("Domain length must be power of 2");
+  if (!is_pow2(ef)) panic_("Expansion factor must be power of 2");
+  if (ef < 4) panic_("Expansion factor must be at least 4");
+  Fri f = {p, offset, omega, n, ef, nq};
+  return f;
+}
+/* fri.rs:57-91 */
+static u64 *fri_fold_codeword(const Fri *f, const u64 *cw, size_t n, u64 alpha, u64 offset, u64 omega) {
+  u64 p = f->p;
+  u64 one = 1;
+  u64 two_inv = ff_inv(p, 2);
+  size_t half = n / 2;
+  u64 *out = (u64 *)xmalloc(half * sizeof(u64));
+  for (size_t i = 0; i < half; i++) {
+    u64 x = ff_mul(p, offset, ff_exp(p, omega, (u64)i));
+    u64 a = ff_add(p, one, ff_div(p, alpha, x));
+    u64 b = ff_sub(p, one, ff_div(p, alpha, x));
+    u64 term = ff_add(p, ff_mul(p, a, cw[i]), ff_mul(p, b, cw[half + i]));
+    out[i] = ff_mul(p, two_inv, term);
+  }
+  return out;
+}
+/* fri.rs:93-103 */
+static u64 fri_num_rounds(const Fri *f) {
+  size_t len = f->domain_length;
+  u64 r = 0;
+  while (len > f->expansion_factor && 4 * f->num_colinearity_tests < len) {
+    len /= 2;
+    r++;
+  }
+  return r;
+}
+static void leaf_hashes(const u64 *cw, size_t n, u8 *out) { /* fri.rs:118-121 */
+  for (size_t i = 0; i < n; i++) hash_from_field_elements(&cw[i], 1, out + 32 * i);
+}
+typedef struct {
+  u64 **cw;
+  size_t *len;
+  size_t n;
+} Codewords;
+static void cws_free(Codewords *c) {
+  for (size_t i = 0; i < c->n; i++) free(c->cw[i]);
+  free(c->cw);
+  free(c->len);
+}
+/* fri.rs:105-156.  alphas_out (optional) receives the raw challenges drawn. */
+static Codewords fri_commit(const Fri *f, const u64 *initial, Stream *ps, Transcript *fs, u64 *alphas_out) {
+  size_t n = f->domain_length;
+  u64 *codeword = (u64 *)xmalloc(n * sizeof(u64));
+  memcpy(codeword, initial, n * sizeof(u64));
+  u64 omega = f->omega, offset = f->offset;
+  u64 R = fri_num_rounds(f);
+  Codewords cws;
+  cws.cw = (u64 **)xmalloc((R + 1) * sizeof(u64 *));
+  cws.len = (size_t *)xmalloc((R + 1) * sizeof(size_t));
+  cws.n = 0;
+  for (u64 r = 0; r < R; r++) {
+    u8 *hashes = (u8 *)xmalloc(n * 32);
+    leaf_hashes(codeword, n, hashes);
+    /* fri.rs:123-125 : pad to next power of two with Hash([0;32]) (no-op for 2^k) */
+    size_t padded = 1;
+    while (padded < n) padded <<= 1;
+    u8 *ph = (u8 *)xmalloc(padded * 32);
+    memset(ph, 0, padded * 32);
+    memcpy(ph, hashes, n * 32);
+    Merkle tree = merkle_new(ph, padded);
+    st_push(ps, OBJ_ROOT, 1, tree.root, 32);
+    fs_absorb(fs, tree.root, 32);
+    merkle_free(&tree);
+    free(ph);
+    free(hashes);
+    if (r == R - 1) break;
+    u64 alpha = fs_challenge(fs);
+    if (alphas_out) alphas_out[r] = alpha;
+    cws.cw[cws.n] = (u64 *)xmalloc(n * sizeof(u64));
+    memcpy(cws.cw[cws.n], codeword, n * sizeof(u64));
+    cws.len[cws.n++] = n;
+    u64 *folded = fri_fold_codeword(f, codeword, n, alpha, offset, omega);
+    free(codeword);
+    codeword = folded;
+    n /= 2;
+    omega = ff_mul(f->p, omega, omega);
+    offset = ff_mul(f->p, offset, offset);
+  }
+  st_push_fes(ps, codeword, n);
+  cws.cw[cws.n] = codeword;
+  cws.len[cws.n++] = n;
+  return cws;
+}
+/* fri.rs:168-174 */
+static size_t fri_sample_index(const u8 *bytes, size_t nbytes, size_t size) {
+  u128 acc = 0;
+  for (size_t i = 0; i < nbytes; i++) acc = (acc << 8) ^ (u128)bytes[i];
+  return (size_t)((u64)acc) % size;
+}
+/* fri.rs:176-213 */
+static void fri_sample_indices(const u8 *seed, size_t seed_len, size_t size, size_t reduced_size, size_t number,
+                               size_t *out) {
+  if (number > 2 * reduced_size) panic_("not enough entropy in indices wrt last codeword");
+  if (number > reduced_size) panic_("cannot sample more indices than available in last codeword");
+  size_t got = 0;
+  size_t *reduced = (size_t *)xmalloc(number * sizeof(size_t));
+  uint32_t counter = 0;
+  u8 *buf = (u8 *)xmalloc(seed_len + 4);
+  while (got < number) {
+    memcpy(buf, seed, seed_len);
+    for (int k = 0; k < 4; k++) buf[seed_len + k] = (u8)(counter >> (8 * k));
+    u8 h[32];
+    hash_from_bytes(buf, seed_len + 4, h);
+    size_t index = fri_sample_index(h, 32, size);
+    size_t ri = index % reduced_size;
+    counter++;
+    int seen = 0;
+    for (size_t k = 0; k < got; k++)
+      if (reduced[k] == ri) seen = 1;
+    if (!seen) {
+      out[got] = index;
+      reduced[got++] = ri;
+    }
+  }
+  free(buf);
+  free(reduced);
+}
+/* fri.rs:215-248 */
+static void fri_query(const Fri *f, const u64 *cur, size_t cur_len, const u64 *nxt, const size_t *c_idx, Stream *ps,
+                      const Merkle *cur_tree, const Merkle *nxt_tree) {
+  size_t half = cur_len / 2, nq = f->num_colinearity_tests;
+  for (size_t s = 0; s < nq; s++) {
+    u64 triple[3] = {cur[c_idx[s]], cur[c_idx[s] + half], nxt[c_idx[s]]};
+    st_push_fes(ps, triple, 3);
+  }
+  u8 *path = (u8 *)xmalloc(32 * 64);
+  for (size_t s = 0; s < nq; s++) {
+    size_t k = merkle_open(cur_tree, c_idx[s], path);
+    st_push(ps, OBJ_PATH, k, path, 32 * k);
+    k = merkle_open(cur_tree, c_idx[s] + half, path);
+    st_push(ps, OBJ_PATH, k, path, 32 * k);
+    k = merkle_open(nxt_tree, c_idx[s], path);
+    st_push(ps, OBJ_PATH, k, path, 32 * k);
+  }
+  free(path);
+}
+/* fri.rs:250-311 ; top_out receives num_colinearity_tests indices */
+static void fri_prove(const Fri *f, const u64 *initial, size_t n, Transcript *fs, Stream *ps, size_t *top_out,
+                      u64 *alphas_out, u64 *seed_challenge_out) {
+  if (f->domain_length != n) panic_("initial codeword length does not match domain length");
+  Codewords cws = fri_commit(f, initial, ps, fs, alphas_out);
+  size_t sample_size = cws.n > 1 ? cws.len[1] : cws.len[0];
+  u64 ch = fs_challenge(fs);
+  if (seed_challenge_out) *seed_challenge_out = ch;
+  u8 seed[32];
+  hash_from_u64(ch, seed);
+  size_t nq = f->num_colinearity_tests;
+  fri_sample_indices(seed, 32, sample_size, cws.len[cws.n - 1], nq, top_out);
+  size_t *idx = (size_t *)xmalloc(nq * sizeof(size_t));
+  memcpy(idx, top_out, nq * sizeof(size_t));
+  for (size_t i = 0; i + 1 < cws.n; i++) {
+    for (size_t s = 0; s < nq; s++) idx[s] %= cws.len[i] / 2;
+    /* fri.rs:288-298 : the reference REBUILDS both trees here */
+    u8 *h0 = (u8 *)xmalloc(32 * cws.len[i]);
+    u8 *h1 = (u8 *)xmalloc(32 * cws.len[i + 1]);
+    leaf_hashes(cws.cw[i], cws.len[i], h0);
+    leaf_hashes(cws.cw[i + 1], cws.len[i + 1], h1);
+    Merkle t0 = merkle_new(h0, cws.len[i]);
+    Merkle t1 = merkle_new(h1, cws.len[i + 1]);
+    fri_query(f, cws.cw[i], cws.len[i], cws.cw[i + 1], idx, ps, &t0, &t1);
+    merkle_free(&t0);
+    merkle_free(&t1);
+    free(h0);
+    free(h1);
+  }
+  free(idx);
+  cws_free(&cws);
+}
+/* fri.rs:507-525 */
+static int fri_test_colinearity(u64 p, const u64 xs[3], const u64 ys[3]) {
+  u64 dy1 = ff_sub(p, ys[1], ys[0]), dx1 = ff_sub(p, xs[1], xs[0]);
+  u64 dy2 = ff_sub(p, ys[2], ys[0]), dx2 = ff_sub(p, xs[2], xs[0]);
+  return ff_mul(p, dy1, dx2) == ff_mul(p, dy2, dx1);
+}
+/* fri.rs:313-505.  Returns 1 (true) / 0 (false); failure reason in *why. */
+static int fri_verify(const Fri *f, Stream *ps, Transcript *fs, const char **why) {
+  u64 p = f->p;
+  u64 omega = f->omega, offset = f->offset;
+  u64 R = fri_num_rounds(f);
+  size_t nq = f->num_colinearity_tests;
+  u8(*roots)[32] = (u8(*)[32])xmalloc((R + 1) * 32);
+  u64 *alphas = (u64 *)xmalloc((R + 1) * sizeof(u64));
+  for (u64 r = 0; r < R; r++) {
+    ProofObj *o = st_pop(ps);
+    if (!o || o->tag != OBJ_ROOT) { *why = "Failed to extract Merkle root"; return 0; }
+    memcpy(roots[r], o->data, 32);
+    fs_absorb(fs, o->data, 32);
+    alphas[r] = fs_challenge(fs);
+  }
+  ProofObj *lo = st_pop(ps);
+  if (!lo || lo->tag != OBJ_FES) { *why = "Failed to extract last codeword"; return 0; }
+  size_t ln = lo->count;
+  u64 *last = (u64 *)xmalloc(ln * sizeof(u64));
+  for (size_t i = 0; i < ln; i++) last[i] = get_u64(lo->data + 8 * i);
+  if (R == 0) { *why = "No FRI roots extracted"; return 0; }
+  u8 *lh = (u8 *)xmalloc(32 * ln);
+  leaf_hashes(last, ln, lh);
+  Merkle lt = merkle_new(lh, ln);
+  if (memcmp(roots[R - 1], lt.root, 32) != 0) { *why = "last codeword is not well formed"; return 0; }
+  merkle_free(&lt);
+  free(lh);
+  size_t degree_bound = ln / f->expansion_factor;
+  if (degree_bound == 0) { *why = "last codeword too small"; return 0; }
+  size_t degree = degree_bound - 1;
+  u64 last_omega = omega, last_offset = offset;
+  for (u64 k = 0; k + 1 < R; k++) {
+    last_omega = ff_mul(p, last_omega, last_omega);
+    last_offset = ff_mul(p, last_offset, last_offset);
+  }
+  u64 *dom = (u64 *)xmalloc(ln * sizeof(u64));
+  for (size_t i = 0; i < ln; i++) dom[i] = ff_mul(p, last_offset, ff_exp(p, last_omega, (u64)i));
+  Poly poly = poly_interpolate(p, dom, last, ln);
+  for (size_t i = 0; i < ln; i++)
+    if (poly_eval(p, &poly, dom[i]) != last[i]) { *why = "re-evaluated codeword does not match original!"; return 0; }
+  if (poly_deg(&poly) > (i128)degree) { *why = "last codeword does not correspond to polynomial of low enough degree"; return 0; }
+  poly_free(&poly);
+  free(dom);
+  u8 seed[32];
+  hash_from_u64(fs_challenge(fs), seed);
+  size_t *top = (size_t *)xmalloc(nq * sizeof(size_t));
+  fri_sample_indices(seed, 32, f->domain_length >> 1, f->domain_length >> (R - 1), nq, top);
+  u64 *aa = (u64 *)xmalloc(nq * 8), *bb = (u64 *)xmalloc(nq * 8), *cc = (u64 *)xmalloc(nq * 8);
+  for (size_t r = 0; r + 1 < R; r++) {
+    size_t half = f->domain_length >> (r + 1);
+    for (size_t s = 0; s < nq; s++) {
+      ProofObj *o = st_pop(ps);
+      if (!o || o->tag != OBJ_FES) { *why = "Failed to extract triple values"; return 0; }
+      if (o->count != 3) { *why = "Expected triple of values"; return 0; }
+      size_t ci = top[s] % half, ai = ci, bi = ci + half;
+      u64 ay = get_u64(o->data), by = get_u64(o->data + 8), cy = get_u64(o->data + 16);
+      aa[s] = ay, bb[s] = by, cc[s] = cy;
+      u64 xs[3] = {ff_mul(p, offset, ff_exp(p, omega, (u64)ai)), ff_mul(p, offset, ff_exp(p, omega, (u64)bi)), alphas[r]};
+      u64 ys[3] = {ay, by, cy};
+      if (!fri_test_colinearity(p, xs, ys)) { *why = "colinearity check failure"; return 0; }
+    }
+    for (size_t s = 0; s < nq; s++) {
+      size_t ci = top[s] % half, ai = ci, bi = ci + half;
+      u8 leaf[32];
+      ProofObj *o = st_pop(ps);
+      if (!o || o->tag != OBJ_PATH) { *why = "Failed to extract path for aa"; return 0; }
+      hash_from_field_elements(&aa[s], 1, leaf);
+      if (!merkle_verify(leaf, ai, o->data, o->count, roots[r])) { *why = "merkle authentication path verification fails for aa"; return 0; }
+      o = st_pop(ps);
+      if (!o || o->tag != OBJ_PATH) { *why = "Failed to extract path for bb"; return 0; }
+      hash_from_field_elements(&bb[s], 1, leaf);
+      if (!merkle_verify(leaf, bi, o->data, o->count, roots[r])) { *why = "merkle authentication path verification fails for bb"; return 0; }
+      o = st_pop(ps);
+      if (!o || o->tag != OBJ_PATH) { *why = "Failed to extract path for cc"; return 0; }
+      hash_from_field_elements(&cc[s], 1, leaf);
+      if (!merkle_verify(leaf, ci, o->data, o->count, roots[r + 1])) { *why = "merkle authentication path verification fails for cc"; return 0; }
+    }
+    omega = ff_mul(p, omega, omega);
+    offset = ff_mul(p, offset, offset);
+  }
+  free(aa), free(bb), free(cc), free(top), free(last), free(alphas), free(roots);
+  *why = "";
+  return 1;
+}
+
+/* =================================================================== C API
+ * Flat entry points for ctypes (tests/, bench.py).  Return 0 ok / 1 panic.   */
+
+int oracle_ff_mul(u64 p, u64 a, u64 b, u64 *out) { API_ENTER(); *out = ff_mul(p, a, b); API_LEAVE(); }
+int oracle_ff_add(u64 p, u64 a, u64 b, u64 *out) { API_ENTER(); *out = ff_add(p, a, b); API_LEAVE(); }
+int oracle_ff_sub(u64 p, u64 a, u64 b, u64 *out) { API_ENTER(); *out = ff_sub(p, a, b); API_LEAVE(); }
+int oracle_ff_neg(u64 p, u64 a, u64 *out) { API_ENTER(); *out = ff_neg(p, a); API_LEAVE(); }
+int oracle_ff_inv(u64 p, u64 a, u64 *out) { API_ENTER(); *out = ff_inv(p, a); API_LEAVE(); }
+int oracle_ff_div(u64 p, u64 a, u64 b, u64 *out) { API_ENTER(); *out = ff_div(p, a, b); API_LEAVE(); }
+int oracle_ff_exp(u64 p, u64 a, u64 e, u64 *out) { API_ENTER(); *out = ff_exp(p, a, e); API_LEAVE(); }
+int oracle_ff_g(u64 p, u64 *out) { API_ENTER(); *out = ff_g(p); API_LEAVE(); }
+int oracle_ff_prim_nth_root(u64 p, u64 n, u64 *out) { API_ENTER(); *out = ff_prim_nth_root(p, n); API_LEAVE(); }
+int oracle_ff_sample(u64 p, const u8 *salt, size_t n, u64 *out) { API_ENTER(); *out = ff_sample(p, salt, n); API_LEAVE(); }
+
+/* element-wise batch versions (used as the checker for stark_ff_vec_*) */
+int oracle_ff_vec(u64 p, int op, const u64 *a, const u64 *b, u64 e, u64 *out, size_t n) {
+  API_ENTER();
+  for (size_t i = 0; i < n; i++) {
+    switch (op) {
+      case 0: out[i] = ff_add(p, a[i], b[i]); break;
+      case 1: out[i] = ff_sub(p, a[i], b[i]); break;
+      case 2: out[i] = ff_mul(p, a[i], b[i]); break;
+      case 3: out[i] = ff_neg(p, a[i]); break;
+      case 4: out[i] = ff_inv(p, a[i]); break;
+      case 5: out[i] = ff_exp(p, a[i], e); break;
+      case 6: out[i] = ff_div(p, a[i], b[i]); break;
+      default: panic_("bad op");
+    }
+  }
+  API_LEAVE();
+}
+
+static void poly_out(Poly *r, u64 *out, size_t cap, size_t *out_len) {
+  *out_len = r->n;
+  if (r->n > cap) {
+    poly_free(r);
+    panic_("oracle: output buffer too small");
+  }
+  memcpy(out, r->c, r->n * sizeof(u64));
+  poly_free(r);
+}
+#define WRAP(name, ptr, len) Poly name = {(u64 *)(ptr), (len)}
+
+int oracle_poly_deg(const u64 *a, size_t na, int64_t *out) { API_ENTER(); WRAP(A, a, na); *out = (int64_t)poly_deg(&A); API_LEAVE(); }
+int oracle_poly_add(u64 p, const u64 *a, size_t na, const u64 *b, size_t nb, u64 *out, size_t cap, size_t *n) {
+  API_ENTER(); WRAP(A, a, na); WRAP(B, b, nb); Poly r = poly_add(p, &A, &B); poly_out(&r, out, cap, n); API_LEAVE(); }
+int oracle_poly_sub(u64 p, const u64 *a, size_t na, const u64 *b, size_t nb, u64 *out, size_t cap, size_t *n) {
+  API_ENTER(); WRAP(A, a, na); WRAP(B, b, nb); Poly r = poly_sub(p, &A, &B); poly_out(&r, out, cap, n); API_LEAVE(); }
+int oracle_poly_mul(u64 p, const u64 *a, size_t na, const u64 *b, size_t nb, u64 *out, size_t cap, size_t *n) {
+  API_ENTER(); WRAP(A, a, na); WRAP(B, b, nb); Poly r = poly_mul(p, &A, &B); poly_out(&r, out, cap, n); API_LEAVE(); }
+int oracle_poly_div(u64 p, const u64 *a, size_t na, const u64 *b, size_t nb, u64 *q, size_t qcap, size_t *nq, u64 *r,
+                    size_t rcap, size_t *nr) {
+  API_ENTER(); WRAP(A, a, na); WRAP(B, b, nb); Poly Q, Rm; poly_div(p, &A, &B, &Q, &Rm);
+  poly_out(&Q, q, qcap, nq); poly_out(&Rm, r, rcap, nr); API_LEAVE(); }
+int oracle_poly_exp(u64 p, const u64 *a, size_t na, u64 e, u64 *out, size_t cap, size_t *n) {
+  API_ENTER(); WRAP(A, a, na); Poly r = poly_exp(p, &A, e); poly_out(&r, out, cap, n); API_LEAVE(); }
+int oracle_poly_eval(u64 p, const u64 *a, size_t na, u64 x, u64 *out) { API_ENTER(); WRAP(A, a, na); *out = poly_eval(p, &A, x); API_LEAVE(); }
+/* eval.rs:16-21 */
+int oracle_poly_eval_domain(u64 p, const u64 *a, size_t na, const u64 *dom, size_t m, u64 *out) {
+  API_ENTER(); WRAP(A, a, na); for (size_t i = 0; i < m; i++) out[i] = poly_eval(p, &A, dom[i]); API_LEAVE(); }
+int oracle_poly_interpolate_domain(u64 p, const u64 *dom, const u64 *vals, size_t n, u64 *out, size_t cap, size_t *on) {
+  API_ENTER(); Poly r = poly_interpolate(p, dom, vals, n); poly_out(&r, out, cap, on); API_LEAVE(); }
+int oracle_poly_zerofier(u64 p, const u64 *dom, size_t n, u64 *out, size_t cap, size_t *on) {
+  API_ENTER(); Poly r = poly_zerofier(p, dom, n); poly_out(&r, out, cap, on); API_LEAVE(); }
+int oracle_poly_scale(u64 p, const u64 *a, size_t na, u64 factor, u64 *out) {
+  API_ENTER(); WRAP(A, a, na); Poly r = poly_scale(p, &A, factor); size_t n; poly_out(&r, out, na, &n); API_LEAVE(); }
+/* mod.rs:145-152 */
+int oracle_poly_test_colinearity(u64 p, const u64 *xs, const u64 *ys, size_t n, int *out) {
+  API_ENTER();
+  if (n < 2) panic_("At least 2 points to test colinearity");
+  Poly r = poly_interpolate(p, xs, ys, n);
+  *out = poly_deg(&r) <= 1;
+  poly_free(&r);
+  API_LEAVE();
+}
+/* LDE := eval_domain(interpolate_domain([w_n^i], col), [offset * w_{bn}^i]) with the
+ * reference's own slow algorithms (interpolate.rs:6-44, eval.rs:16-21, domain pattern fri.rs:575-578). */
+int oracle_lde(u64 p, const u64 *col, size_t n, size_t blowup, u64 offset, u64 *out) {
+  API_ENTER();
+  u64 wn = ff_prim_nth_root(p, n), wN = ff_prim_nth_root(p, n * blowup);
+  u64 *dom = (u64 *)xmalloc(n * sizeof(u64));
+  for (size_t i = 0; i < n; i++) dom[i] = ff_exp(p, wn, (u64)i);
+  Poly f = poly_interpolate(p, dom, col, n);
+  for (size_t i = 0; i < n * blowup; i++) out[i] = poly_eval(p, &f, ff_mul(p, offset, ff_exp(p, wN, (u64)i)));
+  poly_free(&f);
+  free(dom);
+  API_LEAVE();
+}
+
+int oracle_hash_from_bytes(const u8 *b, size_t n, u8 *out) { API_ENTER(); hash_from_bytes(b, n, out); API_LEAVE(); }
+int oracle_hash_from_field_elements(const u64 *e, size_t n, u8 *out) { API_ENTER(); hash_from_field_elements(e, n, out); API_LEAVE(); }
+int oracle_hash_combine(const u8 *l, const u8 *r, u8 *out) { API_ENTER(); hash_combine(l, r, out); API_LEAVE(); }
+int oracle_sbox(u8 b, u8 *out) { API_ENTER(); *out = sbox(b); API_LEAVE(); }
+/* leaf i = from_field_elements(vals[i*width .. (i+1)*width]) */
+int oracle_hash_leaves(const u64 *vals, size_t n_leaves, size_t width, u8 *out) {
+  API_ENTER(); for (size_t i = 0; i < n_leaves; i++) hash_from_field_elements(vals + i * width, width, out + 32 * i); API_LEAVE(); }
+
+/* all levels, concatenated: level 0 (n hashes), level 1 (n/2) ... root ; (2n-1)*32 bytes */
+int oracle_merkle_build(const u8 *leaves, size_t n, u8 *out_nodes) {
+  API_ENTER();
+  Merkle t = merkle_new(leaves, n);
+  size_t off = 0;
+  for (size_t l = 0; l < t.n_levels; l++) {
+    memcpy(out_nodes + off, t.nodes[l], 32 * (n >> l));
+    off += 32 * (n >> l);
+  }
+  merkle_free(&t);
+  API_LEAVE();
+}
+/* merkle.rs:44-65 (commit = same loop, root only) */
+int oracle_merkle_commit(const u8 *leaves, size_t n, u8 *root) {
+  API_ENTER(); Merkle t = merkle_new(leaves, n); memcpy(root, t.root, 32); merkle_free(&t); API_LEAVE(); }
+int oracle_merkle_open(const u8 *leaves, size_t n, size_t index, u8 *out, size_t *n_out) {
+  API_ENTER(); Merkle t = merkle_new(leaves, n); *n_out = merkle_open(&t, index, out); merkle_free(&t); API_LEAVE(); }
+int oracle_merkle_verify(const u8 *leaf, size_t index, const u8 *proof, size_t n_proof, const u8 *root, int *ok) {
+  API_ENTER(); *ok = merkle_verify(leaf, index, proof, n_proof, root); API_LEAVE(); }
+
+int oracle_fs_challenge(const u8 *transcript, size_t n, u64 *out) {
+  API_ENTER(); Transcript t = {(u8 *)transcript, n, n}; *out = fs_challenge(&t); API_LEAVE(); }
+
+int oracle_fri_num_rounds(u64 p, u64 omega, u64 offset, size_t n, size_t ef, size_t nq, u64 *out) {
+  API_ENTER(); Fri f = fri_new(p, omega, offset, n, ef, nq); *out = fri_num_rounds(&f); API_LEAVE(); }
+int oracle_fri_fold(u64 p, const u64 *cw, size_t n, u64 alpha, u64 offset, u64 omega, u64 *out) {
+  API_ENTER();
+  Fri f = {p, offset, omega, n, 4, 1};
+  u64 *r = fri_fold_codeword(&f, cw, n, alpha, offset, omega);
+  memcpy(out, r, (n / 2) * sizeof(u64));
+  free(r);
+  API_LEAVE();
+}
+int oracle_fri_sample_indices(const u8 *seed, size_t seed_len, size_t size, size_t reduced, size_t number, u64 *out) {
+  API_ENTER();
+  size_t *t = (size_t *)xmalloc(number * sizeof(size_t));
+  fri_sample_indices(seed, seed_len, size, reduced, number, t);
+  for (size_t i = 0; i < number; i++) out[i] = t[i];
+  free(t);
+  API_LEAVE();
+}
+/* Fri::prove with a fresh FiatShamir + ProofStream, then ProofStream::serialize.
+ * out may be NULL to query the length.  roots_out: R*32 B, alphas_out: R-1 raw u64,
+ * top_out: nq indices, seed_out: the raw index-seed challenge (all optional). */
+int oracle_fri_prove(u64 p, const u64 *cw, size_t n, size_t domain_length, u64 omega, u64 offset, size_t ef, size_t nq,
+                     u8 *out, size_t cap,
+                     size_t *out_len, u64 *top_out, u64 *alphas_out, u64 *seed_out) {
+  API_ENTER();
+  Fri f = fri_new(p, omega, offset, domain_length, ef, nq);
+  Transcript fs;
+  Stream ps;
+  fs_init(&fs);
+  st_init(&ps);
+  size_t *top = (size_t *)xmalloc((nq + 1) * sizeof(size_t));
+  fri_prove(&f, cw, n, &fs, &ps, top, alphas_out, seed_out);
+  if (top_out)
+    for (size_t i = 0; i < nq; i++) top_out[i] = top[i];
+  *out_len = st_serialize(&ps, out, cap);
+  free(top);
+  st_free(&ps);
+  fs_free(&fs);
+  API_LEAVE();
+}
+/* ProofStream::deserialize + Fri::verify with a fresh FiatShamir (fri.rs:549-558 pattern) */
+int oracle_fri_verify(u64 p, const u8 *proof, size_t len, u64 omega, u64 offset, size_t n, size_t ef, size_t nq,
+                      int *ok, char *why_out, size_t why_cap) {
+  API_ENTER();
+  Fri f = fri_new(p, omega, offset, n, ef, nq);
+  Stream ps;
+  Transcript fs;
+  st_deserialize(&ps, proof, len);
+  fs_init(&fs);
+  const char *why = "";
+  *ok = fri_verify(&f, &ps, &fs, &why);
+  if (why_out && why_cap) snprintf(why_out, why_cap, "%s", why);
+  st_free(&ps);
+  fs_free(&fs);
+  API_LEAVE();
+}
+/* number of objects in a serialized stream (SURVEY 8(c) cross-check) */
+int oracle_stream_count(const u8 *proof, size_t len, size_t *n_objects) {
+  API_ENTER(); Stream ps; st_deserialize(&ps, proof, len); *n_objects = ps.n; st_free(&ps); API_LEAVE(); }
+
+/* trace.rs:36-49 + 29-34 : fibonacci column as u64 (i128 as u64 cast, no reduction) */
+int oracle_trace_fibonacci(size_t length, u64 *out) {
+  API_ENTER();
+  i128 a = 1, b = 1;
+  for (size_t i = 0; i < length; i++) {
+    out[i] = (u64)a;
+    i128 next;
+    if (__builtin_add_overflow(a, b, &next)) panic_("attempt to add with overflow");
+    a = b;
+    b = next;
+  }
+  API_LEAVE();
+}
