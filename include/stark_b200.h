@@ -1,0 +1,193 @@
+/*
+ * stark_b200.h -- C ABI of libstark_b200.so, the B200 (sm_100a) back end for the data-parallel hot
+ * path of 0xSooki/stark-rs.  This is the drop-in boundary: the reference has no FFI of its own, so each
+ * entry point below names the reference function (file:line under the reference's src/) whose results
+ * it reproduces bit for bit.  The Rust shim in stark-rs_b200/rust/ and the C++ mirror in
+ * stark-rs_b200/host/ forward the reference's public methods to these symbols.
+ *
+ * Conventions
+ *   - Every function returns a stark_status (0 = ok) and never aborts; stark_last_error() gives the
+ *     thread-local message.  STARK_ERR_ARG mirrors a reference assert/panic and carries ITS message text
+ *     ("no inverse", "Number of leaves must be power of 2", ...) so the host shim can re-raise it.
+ *   - Field values cross the boundary as contiguous little-endian uint64_t (FieldElement.value, ff.rs:25-28)
+ *     and must be canonical (< p = 998244353, ff.rs:191-197) unless a parameter says "raw"; results are
+ *     canonical.  A non-canonical input is STARK_ERR_ARG, never silently reduced.
+ *   - Hashes are uint8_t[32] (hash.rs:2), contiguous.
+ *   - Host buffers are caller-owned.  Device objects are opaque handles created and freed by the library and
+ *     valid only on the context that made them.  A context owns one CUDA device + one stream and is not
+ *     thread-safe; use one per thread / per process (one process per GPU).
+ *   - On the device an element is ONE uint32_t (canonical).  stark_buf wraps such an array.
+ *   - There is no CPU fallback: every compute entry point fails with STARK_ERR_CUDA when no device is usable.
+ */
+#ifndef STARK_B200_H
+#define STARK_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STARK_P 998244353ull /* ff.rs:191-197, main.rs:6 */
+
+typedef enum {
+  STARK_OK = 0,
+  STARK_ERR_ARG = 1,  /* precondition = a reference assert!/panic! */
+  STARK_ERR_CUDA = 2,
+  STARK_ERR_NCCL = 3,
+  STARK_ERR_OOM = 4
+} stark_status;
+
+typedef struct stark_ctx stark_ctx;
+typedef struct stark_buf stark_buf;             /* device array of uint32_t field elements */
+typedef struct stark_tree stark_tree;           /* MerkleTree (merkle.rs:4-8): all levels on device */
+typedef struct stark_fri_state stark_fri_state; /* result of Fri::commit (fri.rs:105-156) kept on device */
+
+/* ---- context ------------------------------------------------------------------------------------------ */
+int stark_ctx_create(int device, stark_ctx **out);
+/* borrow an existing CUDA stream (e.g. torch.cuda.current_stream().cuda_stream) */
+int stark_ctx_create_on_stream(int device, void *cuda_stream, stark_ctx **out);
+void stark_ctx_destroy(stark_ctx *ctx);
+int stark_ctx_sync(stark_ctx *ctx);
+void *stark_ctx_stream(stark_ctx *ctx);
+uint64_t stark_ctx_launches(stark_ctx *ctx); /* kernels launched so far through this context */
+const char *stark_last_error(void);
+const char *stark_version(void);
+
+/* ---- device buffers ----------------------------------------------------------------------------------- */
+int stark_buf_alloc(stark_ctx *ctx, size_t n, stark_buf **out);
+int stark_buf_upload(stark_ctx *ctx, const uint64_t *host, size_t n, stark_buf **out); /* checks canonical */
+int stark_buf_upload_into(stark_ctx *ctx, const uint64_t *host, size_t n, stark_buf *dst, size_t dst_off);
+int stark_buf_download(stark_ctx *ctx, const stark_buf *buf, size_t off, size_t n, uint64_t *host);
+int stark_buf_wrap(stark_ctx *ctx, void *device_u32, size_t n, stark_buf **out); /* non-owning view */
+void *stark_buf_ptr(const stark_buf *buf);
+size_t stark_buf_len(const stark_buf *buf);
+void stark_buf_free(stark_buf *buf);
+
+/* ---- K0: ff.rs batch arithmetic (ff.rs:138-213) ------------------------------------------------------- */
+int stark_ff_vec_add(stark_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n); /* ff.rs:146 */
+int stark_ff_vec_sub(stark_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n); /* ff.rs:154 */
+int stark_ff_vec_mul(stark_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n); /* ff.rs:138 */
+int stark_ff_vec_neg(stark_ctx *ctx, const uint64_t *a, uint64_t *out, size_t n);                    /* ff.rs:162 */
+/* ff.rs:169-178; STARK_ERR_ARG "no inverse" if any a[i] == 0 (batch inversion on device) */
+int stark_ff_vec_inv(stark_ctx *ctx, const uint64_t *a, uint64_t *out, size_t n);
+int stark_ff_vec_pow(stark_ctx *ctx, const uint64_t *a, uint64_t e, uint64_t *out, size_t n);        /* ff.rs:200 */
+/* ff.rs:215-223; STARK_ERR_ARG "n must be a power of two" / "n > 2^23 not supported by this modulus" */
+int stark_ff_prim_nth_root(uint64_t n, uint64_t *out);
+
+/* ---- K1/K3: univariate (src/univariate) --------------------------------------------------------------- */
+/* Polynomial::mul (mul.rs:6-29).  *out_len = 0 if either side is the zero polynomial, else na+nb-1
+ * (vector length, not degree).  out must hold na+nb-1 values. */
+int stark_poly_mul(stark_ctx *ctx, const uint64_t *a, size_t na, const uint64_t *b, size_t nb, uint64_t *out,
+                   size_t *out_len);
+/* Polynomial::eval_domain (eval.rs:16-21) on domain[i] = offset * w_N^i, N = 2^log_n, w_N = prim_nth_root(N)
+ * (the pattern of fri.rs:575-578); nc <= N coefficients; natural order. */
+int stark_poly_eval_coset(stark_ctx *ctx, const uint64_t *coeffs, size_t nc, uint64_t offset, uint32_t log_n,
+                          uint64_t *out);
+/* Polynomial::interpolate_domain (interpolate.rs:6-44) on the same domain.  coeffs gets N values; *out_len
+ * follows the reference's shape rule: N if any value is non-zero, else 0 (N >= 2) or 1 (N == 1). */
+int stark_poly_interpolate_coset(stark_ctx *ctx, const uint64_t *vals, uint64_t offset, uint32_t log_n,
+                                 uint64_t *coeffs, size_t *out_len);
+/* eval_domain on an ARBITRARY domain (eval.rs:16-21), O(nc*m) on device */
+int stark_poly_eval_domain(stark_ctx *ctx, const uint64_t *coeffs, size_t nc, const uint64_t *domain, size_t m,
+                           uint64_t *out);
+/* interpolate_domain on an ARBITRARY domain (interpolate.rs:6-44), O(n^2) on device.
+ * STARK_ERR_ARG "no inverse" on duplicate points (mod.rs:613-625).  Same *out_len rule as above. */
+int stark_poly_interpolate_domain(stark_ctx *ctx, const uint64_t *domain, const uint64_t *vals, size_t n,
+                                  uint64_t *coeffs, size_t *out_len);
+/* Polynomial::scale, f(cX) (mod.rs:99-113) */
+int stark_poly_scale(stark_ctx *ctx, const uint64_t *coeffs, size_t n, uint64_t factor, uint64_t *out);
+/* Polynomial::zerofier (mod.rs:77-96) of the coset {offset * w_N^i}: X^N - offset^N, N+1 coefficients */
+int stark_poly_zerofier_coset(stark_ctx *ctx, uint64_t offset, uint32_t log_n, uint64_t *out);
+/* Polynomial::zerofier of an arbitrary domain (mod.rs:77-96), n+1 coefficients */
+int stark_poly_zerofier_domain(stark_ctx *ctx, const uint64_t *domain, size_t n, uint64_t *out);
+
+/* ---- K2: trace low-degree extension (trace.rs:21-34 columns, pattern fri.rs:575-578) ------
+ * out column c = eval_domain(interpolate_domain([w_n^i], col c), [offset * w_{bn}^i]); column-major in and
+ * out (column c at cols + c*n, out + c*n*b).  n = 2^log_n, b = 2^log_blowup, log_n + log_blowup <= 23. */
+int stark_lde(stark_ctx *ctx, const uint64_t *cols, uint32_t n_cols, uint32_t log_n, uint32_t log_blowup,
+              uint64_t offset, uint64_t *out);
+int stark_lde_dev(stark_ctx *ctx, const stark_buf *cols, uint32_t n_cols, uint32_t log_n, uint32_t log_blowup,
+                  uint64_t offset, stark_buf *out);
+/* device-resident transforms used by the pipelines above (natural order in and out) */
+int stark_ntt_dev(stark_ctx *ctx, const stark_buf *in, stark_buf *out, uint32_t log_n, uint32_t batch, int inverse);
+
+/* ---- K5: hash.rs / merkle.rs -------------------------------------------------------------------------- */
+/* Hash::from_bytes (hash.rs:7-30) of n_msgs messages of msg_len bytes each (contiguous) */
+int stark_hash_bytes(stark_ctx *ctx, const uint8_t *msgs, size_t n_msgs, size_t msg_len, uint8_t *out);
+/* leaf i = Hash::from_field_elements(&vals[i*width .. (i+1)*width]) (hash.rs:32-35; fri.rs:118-121 has width 1) */
+int stark_hash_leaves(stark_ctx *ctx, const uint64_t *vals, size_t n_leaves, uint32_t width, uint8_t *out);
+/* MerkleTree::new (merkle.rs:11-38).  STARK_ERR_ARG "Cannot create tree from empty leaves" /
+ * "Number of leaves must be power of 2". */
+int stark_merkle_build(stark_ctx *ctx, const uint8_t *leaves, size_t n, stark_tree **out);
+/* leaf hashing + MerkleTree::new in one go (fri.rs:118-127); row-major values, width per leaf */
+int stark_merkle_build_from_values(stark_ctx *ctx, const uint64_t *vals, size_t n_leaves, uint32_t width,
+                                   stark_tree **out);
+/* same, values already on device; column-major [width][n_leaves] when width > 1 (LDE output layout) */
+int stark_merkle_build_from_buf(stark_ctx *ctx, const stark_buf *vals, size_t n_leaves, uint32_t width,
+                                stark_tree **out);
+/* MerkleTree::commit (merkle.rs:44-65): root only */
+int stark_merkle_commit(stark_ctx *ctx, const uint8_t *leaves, size_t n, uint8_t root[32]);
+int stark_merkle_root(stark_tree *t, uint8_t root[32]);                          /* merkle.rs:40-42 */
+size_t stark_merkle_num_leaves(const stark_tree *t);
+uint32_t stark_merkle_num_levels(const stark_tree *t);                           /* nodes.len(), merkle.rs:18-29 */
+int stark_merkle_level(stark_tree *t, uint32_t level, uint8_t *out);             /* nodes[level] */
+/* MerkleTree::open (merkle.rs:67-80): log2(n) sibling hashes; STARK_ERR_ARG "Index out of bounds" */
+int stark_merkle_open(stark_tree *t, size_t index, uint8_t *out, size_t *n_hashes);
+void stark_merkle_free(stark_tree *t);
+
+/* ---- K4/K6/K7: fri.rs --------------------------------------------------------------------------------- */
+/* Fri::num_rounds (fri.rs:93-103); also checks the Fri::new asserts (fri.rs:37-45) */
+int stark_fri_num_rounds(size_t domain_length, uint32_t expansion_factor, uint32_t num_colinearity_tests,
+                         uint32_t *rounds);
+/* Fri::fold_codeword (fri.rs:57-91); alpha_raw may be unreduced (fiat_shamir.rs:21-24); n even */
+int stark_fri_fold(stark_ctx *ctx, const uint64_t *codeword, size_t n, uint64_t alpha_raw, uint64_t offset,
+                   uint64_t omega, uint64_t *out);
+int stark_fri_fold_dev(stark_ctx *ctx, const stark_buf *codeword, size_t n, uint64_t alpha_raw, uint64_t offset,
+                       uint64_t omega, stark_buf *out);
+/* Fri::commit (fri.rs:105-156) entirely on device, Fiat-Shamir included (fiat_shamir.rs:15-25); the
+ * transcript starts with `transcript` (may be NULL/0 = FiatShamir::new()).  Keeps every codeword and tree. */
+int stark_fri_commit(stark_ctx *ctx, const uint64_t *codeword, size_t n, uint64_t offset, uint64_t omega,
+                     uint32_t expansion_factor, uint32_t num_colinearity_tests, const uint8_t *transcript,
+                     size_t transcript_len, stark_fri_state **out);
+int stark_fri_commit_dev(stark_ctx *ctx, const stark_buf *codeword, size_t n, uint64_t offset, uint64_t omega,
+                         uint32_t expansion_factor, uint32_t num_colinearity_tests, const uint8_t *transcript,
+                         size_t transcript_len, stark_fri_state **out);
+uint32_t stark_fri_rounds(const stark_fri_state *s);
+int stark_fri_roots(stark_fri_state *s, uint8_t *out /* 32*rounds */);
+int stark_fri_alphas(stark_fri_state *s, uint64_t *out /* rounds-1 raw challenges */);
+int stark_fri_codeword_len(const stark_fri_state *s, uint32_t round, size_t *len);
+int stark_fri_codeword(stark_fri_state *s, uint32_t round, uint64_t *out);
+int stark_fri_open(stark_fri_state *s, uint32_t round, size_t index, uint8_t *out, size_t *n_hashes);
+void stark_fri_free(stark_fri_state *s);
+/* Fri::sample_indices (fri.rs:176-213); STARK_ERR_ARG with the reference's two messages */
+int stark_fri_sample_indices(const uint8_t *seed, size_t seed_len, size_t size, size_t reduced_size, size_t number,
+                             uint64_t *out);
+/* Fri::prove (fri.rs:250-311) + ProofStream::serialize (stream.rs:35-64): the exact proof bytes.
+ * top_indices (may be NULL) receives the num_colinearity_tests returned indices.  STARK_ERR_ARG
+ * "initial codeword length does not match domain length" when n != domain_length. */
+int stark_fri_proof_size(size_t domain_length, uint32_t expansion_factor, uint32_t num_colinearity_tests,
+                         size_t *bytes);
+int stark_fri_prove(stark_ctx *ctx, const uint64_t *codeword, size_t n, size_t domain_length, uint64_t offset,
+                    uint64_t omega, uint32_t expansion_factor, uint32_t num_colinearity_tests,
+                    const uint8_t *transcript, size_t transcript_len, uint8_t *proof, size_t proof_cap,
+                    size_t *proof_len, uint64_t *top_indices);
+int stark_fri_prove_dev(stark_ctx *ctx, const stark_buf *codeword, size_t n, size_t domain_length, uint64_t offset,
+                        uint64_t omega, uint32_t expansion_factor, uint32_t num_colinearity_tests,
+                        const uint8_t *transcript, size_t transcript_len, uint8_t *proof, size_t proof_cap,
+                        size_t *proof_len, uint64_t *top_indices);
+
+/* ---- pipeline: BASELINE config 3 ("2^20-row trace: coset LDE + Merkle commit + FRI") ------------------
+ * LDE of n_cols columns, one Merkle tree per column (leaf rule fri.rs:118-121), Fri::prove on column 0's
+ * codeword with omega = prim_nth_root(n*blowup).  column_roots gets 32*n_cols bytes. */
+int stark_prove_trace(stark_ctx *ctx, const uint64_t *cols, uint32_t n_cols, uint32_t log_n, uint32_t log_blowup,
+                      uint64_t offset, uint32_t num_colinearity_tests, uint8_t *column_roots, uint8_t *proof,
+                      size_t proof_cap, size_t *proof_len);
+int stark_prove_trace_dev(stark_ctx *ctx, const stark_buf *cols, uint32_t n_cols, uint32_t log_n,
+                          uint32_t log_blowup, uint64_t offset, uint32_t num_colinearity_tests,
+                          uint8_t *column_roots, uint8_t *proof, size_t proof_cap, size_t *proof_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STARK_B200_H */

@@ -1,0 +1,525 @@
+"""ctypes binding of libstark_b200.so (include/stark_b200.h) + a host-side mirror of the reference's types.
+
+This is the Python face of the drop-in boundary: thin wrappers over the C ABI, numpy in / numpy out, used by
+tests/ and bench.py.  There is NO CPU fallback here: if the CUDA library is missing or no device is usable
+every entry point raises.  The mirror classes (FiniteField, Polynomial, Hash, MerkleTree, FiatShamir, Fri)
+keep the names, argument meaning and panic messages of the reference (src/ff.rs, src/univariate, src/hash.rs,
+src/merkle.rs, src/fiat_shamir.rs, src/fri.rs) so parity tests read like the reference's own tests.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+__all__ = ["P", "StarkError", "StarkPanic", "Context", "Buffer", "MerkleTree", "FriState", "lib", "lib_path",
+           "build_library", "prim_nth_root", "fri_num_rounds", "fri_proof_size", "fri_sample_indices"]
+
+P = 998244353
+_HERE = os.path.dirname(os.path.abspath(__file__))
+lib_path = os.path.join(_HERE, "libstark_b200.so")
+
+U64, U32, SZ, U8P = C.c_uint64, C.c_uint32, C.c_size_t, C.POINTER(C.c_uint8)
+U64P = C.POINTER(C.c_uint64)
+
+
+class StarkError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__("stark_b200 status %d: %s" % (status, message))
+        self.status, self.message = status, message
+
+
+class StarkPanic(StarkError):
+    """STARK_ERR_ARG: a precondition that is an assert!/panic! in the reference (same message text)."""
+
+
+def build_library(force=False):
+    """Compile libstark_b200.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    import subprocess
+    args = ["make", "-C", _HERE, "-j8", "-s"] + (["-B"] if force else [])
+    subprocess.check_call(args)
+    return lib_path
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(lib_path):
+            raise StarkError(2, "libstark_b200.so not built (run `make -C stark-rs_b200` or __graft_entry__.build()); "
+                                "there is no CPU fallback")
+        _lib = C.CDLL(lib_path)
+        _lib.stark_last_error.restype = C.c_char_p
+        _lib.stark_version.restype = C.c_char_p
+        _lib.stark_ctx_launches.restype = C.c_uint64
+        _lib.stark_ctx_stream.restype = C.c_void_p
+        _lib.stark_buf_ptr.restype = C.c_void_p
+        _lib.stark_buf_len.restype = C.c_size_t
+        _lib.stark_merkle_num_leaves.restype = C.c_size_t
+        _lib.stark_merkle_num_levels.restype = C.c_uint32
+        _lib.stark_fri_rounds.restype = C.c_uint32
+    return _lib
+
+
+def _chk(rc):
+    if rc != 0:
+        msg = lib().stark_last_error().decode()
+        raise (StarkPanic if rc == 1 else StarkError)(rc, msg)
+
+
+def _u64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.uint64).reshape(-1))
+
+
+def _p64(a):
+    return a.ctypes.data_as(U64P)
+
+
+def _p8(a):
+    return a.ctypes.data_as(U8P)
+
+
+def _b(x):
+    if x is None:
+        return np.zeros(0, dtype=np.uint8)
+    if isinstance(x, np.ndarray):
+        return np.ascontiguousarray(x, dtype=np.uint8).reshape(-1)
+    return np.frombuffer(bytes(x), dtype=np.uint8).copy()
+
+
+def prim_nth_root(n):
+    """FiniteField::prim_nth_root (ff.rs:215-223)."""
+    out = U64()
+    _chk(lib().stark_ff_prim_nth_root(U64(n), C.byref(out)))
+    return out.value
+
+
+def fri_num_rounds(domain_length, expansion_factor, num_colinearity_tests):
+    out = U32()
+    _chk(lib().stark_fri_num_rounds(SZ(domain_length), U32(expansion_factor), U32(num_colinearity_tests), C.byref(out)))
+    return out.value
+
+
+def fri_proof_size(domain_length, expansion_factor, num_colinearity_tests):
+    out = SZ()
+    _chk(lib().stark_fri_proof_size(SZ(domain_length), U32(expansion_factor), U32(num_colinearity_tests), C.byref(out)))
+    return out.value
+
+
+def fri_sample_indices(seed, size, reduced_size, number):
+    seed = _b(seed)
+    out = np.zeros(max(number, 1), dtype=np.uint64)
+    _chk(lib().stark_fri_sample_indices(_p8(seed), SZ(len(seed)), SZ(size), SZ(reduced_size), SZ(number), _p64(out)))
+    return out[:number]
+
+
+class Buffer:
+    """stark_buf: a device array of uint32 field elements."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self.h = ctx, handle
+
+    def __len__(self):
+        return lib().stark_buf_len(self.h)
+
+    @property
+    def ptr(self):
+        return lib().stark_buf_ptr(self.h)
+
+    def download(self, off=0, n=None):
+        n = len(self) - off if n is None else n
+        out = np.empty(n, dtype=np.uint64)
+        _chk(lib().stark_buf_download(self.ctx.h, self.h, SZ(off), SZ(n), _p64(out)))
+        return out
+
+    def free(self):
+        if self.h:
+            lib().stark_buf_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class MerkleTree:
+    """MerkleTree (merkle.rs:4-97) with every level resident on the device."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self.h = ctx, handle
+
+    @property
+    def num_leaves(self):
+        return lib().stark_merkle_num_leaves(self.h)
+
+    @property
+    def num_levels(self):
+        return lib().stark_merkle_num_levels(self.h)
+
+    def get_root(self):
+        out = np.empty(32, dtype=np.uint8)
+        _chk(lib().stark_merkle_root(self.h, _p8(out)))
+        return out.tobytes()
+
+    def level(self, l):
+        out = np.empty((self.num_leaves >> l, 32), dtype=np.uint8)
+        _chk(lib().stark_merkle_level(self.h, U32(l), _p8(out)))
+        return out
+
+    def nodes(self):
+        return np.concatenate([self.level(l) for l in range(self.num_levels)])
+
+    def open(self, index):
+        out = np.empty((max(self.num_levels - 1, 1), 32), dtype=np.uint8)
+        n = SZ()
+        _chk(lib().stark_merkle_open(self.h, SZ(index), _p8(out), C.byref(n)))
+        return out[: n.value].copy()
+
+    def free(self):
+        if self.h:
+            lib().stark_merkle_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class FriState:
+    """What Fri::commit (fri.rs:105-156) returns and leaves behind: codewords, trees, roots, challenges."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self.h = ctx, handle
+
+    @property
+    def rounds(self):
+        return lib().stark_fri_rounds(self.h)
+
+    def roots(self):
+        out = np.empty((self.rounds, 32), dtype=np.uint8)
+        _chk(lib().stark_fri_roots(self.h, _p8(out)))
+        return out
+
+    def alphas(self):
+        out = np.zeros(max(self.rounds, 1), dtype=np.uint64)
+        _chk(lib().stark_fri_alphas(self.h, _p64(out)))
+        return [int(x) for x in out[: max(self.rounds - 1, 0)]]
+
+    def codeword(self, r):
+        n = SZ()
+        _chk(lib().stark_fri_codeword_len(self.h, U32(r), C.byref(n)))
+        out = np.empty(n.value, dtype=np.uint64)
+        _chk(lib().stark_fri_codeword(self.h, U32(r), _p64(out)))
+        return out
+
+    def open(self, r, index):
+        out = np.empty((64, 32), dtype=np.uint8)
+        n = SZ()
+        _chk(lib().stark_fri_open(self.h, U32(r), SZ(index), _p8(out), C.byref(n)))
+        return out[: n.value].copy()
+
+    def free(self):
+        if self.h:
+            lib().stark_fri_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """stark_ctx: one CUDA device + one stream.  `stream` may be a raw cudaStream_t (int) to borrow."""
+
+    def __init__(self, device=0, stream=None):
+        self.h = C.c_void_p()
+        if stream is None:
+            _chk(lib().stark_ctx_create(C.c_int(device), C.byref(self.h)))
+        else:
+            _chk(lib().stark_ctx_create_on_stream(C.c_int(device), C.c_void_p(stream), C.byref(self.h)))
+        self.device = device
+
+    def close(self):
+        if self.h:
+            lib().stark_ctx_destroy(self.h)
+            self.h = None
+
+    def sync(self):
+        _chk(lib().stark_ctx_sync(self.h))
+
+    @property
+    def launches(self):
+        return lib().stark_ctx_launches(self.h)
+
+    @property
+    def stream(self):
+        return lib().stark_ctx_stream(self.h)
+
+    # ---- buffers
+    def alloc(self, n):
+        h = C.c_void_p()
+        _chk(lib().stark_buf_alloc(self.h, SZ(n), C.byref(h)))
+        return Buffer(self, h)
+
+    def upload(self, values):
+        v = _u64(values)
+        h = C.c_void_p()
+        _chk(lib().stark_buf_upload(self.h, _p64(v), SZ(len(v)), C.byref(h)))
+        return Buffer(self, h)
+
+    def upload_ptr(self, host_ptr, n):
+        """upload n uint64 values from a raw (e.g. pinned) host pointer"""
+        h = C.c_void_p()
+        _chk(lib().stark_buf_upload(self.h, C.cast(host_ptr, U64P), SZ(n), C.byref(h)))
+        return Buffer(self, h)
+
+    def wrap(self, device_ptr, n):
+        h = C.c_void_p()
+        _chk(lib().stark_buf_wrap(self.h, C.c_void_p(device_ptr), SZ(n), C.byref(h)))
+        return Buffer(self, h)
+
+    # ---- ff.rs batch ops
+    def _vec2(self, name, a, b):
+        a, b = _u64(a), _u64(b)
+        assert len(a) == len(b)
+        out = np.empty_like(a)
+        _chk(getattr(lib(), name)(self.h, _p64(a), _p64(b), _p64(out), SZ(len(a))))
+        return out
+
+    def ff_vec_add(self, a, b):
+        return self._vec2("stark_ff_vec_add", a, b)
+
+    def ff_vec_sub(self, a, b):
+        return self._vec2("stark_ff_vec_sub", a, b)
+
+    def ff_vec_mul(self, a, b):
+        return self._vec2("stark_ff_vec_mul", a, b)
+
+    def ff_vec_neg(self, a):
+        a = _u64(a)
+        out = np.empty_like(a)
+        _chk(lib().stark_ff_vec_neg(self.h, _p64(a), _p64(out), SZ(len(a))))
+        return out
+
+    def ff_vec_inv(self, a):
+        a = _u64(a)
+        out = np.empty_like(a)
+        _chk(lib().stark_ff_vec_inv(self.h, _p64(a), _p64(out), SZ(len(a))))
+        return out
+
+    def ff_vec_pow(self, a, e):
+        a = _u64(a)
+        out = np.empty_like(a)
+        _chk(lib().stark_ff_vec_pow(self.h, _p64(a), U64(e), _p64(out), SZ(len(a))))
+        return out
+
+    # ---- univariate
+    def poly_mul(self, a, b):
+        """Polynomial::mul (mul.rs:6-29)"""
+        a, b = _u64(a), _u64(b)
+        out = np.zeros(max(len(a) + len(b), 1), dtype=np.uint64)
+        n = SZ()
+        _chk(lib().stark_poly_mul(self.h, _p64(a), SZ(len(a)), _p64(b), SZ(len(b)), _p64(out), C.byref(n)))
+        return out[: n.value].copy()
+
+    def poly_eval_coset(self, coeffs, offset, log_n):
+        c = _u64(coeffs)
+        out = np.empty(1 << log_n, dtype=np.uint64)
+        _chk(lib().stark_poly_eval_coset(self.h, _p64(c), SZ(len(c)), U64(offset), U32(log_n), _p64(out)))
+        return out
+
+    def poly_interpolate_coset(self, vals, offset, log_n):
+        v = _u64(vals)
+        assert len(v) == 1 << log_n
+        out = np.empty(1 << log_n, dtype=np.uint64)
+        n = SZ()
+        _chk(lib().stark_poly_interpolate_coset(self.h, _p64(v), U64(offset), U32(log_n), _p64(out), C.byref(n)))
+        return out[: n.value].copy()
+
+    def poly_eval_domain(self, coeffs, domain):
+        c, d = _u64(coeffs), _u64(domain)
+        out = np.empty(len(d), dtype=np.uint64)
+        _chk(lib().stark_poly_eval_domain(self.h, _p64(c), SZ(len(c)), _p64(d), SZ(len(d)), _p64(out)))
+        return out
+
+    def poly_interpolate_domain(self, domain, vals):
+        d, v = _u64(domain), _u64(vals)
+        assert len(d) == len(v)
+        out = np.empty(max(len(d), 1), dtype=np.uint64)
+        n = SZ()
+        _chk(lib().stark_poly_interpolate_domain(self.h, _p64(d), _p64(v), SZ(len(d)), _p64(out), C.byref(n)))
+        return out[: n.value].copy()
+
+    def poly_scale(self, coeffs, factor):
+        c = _u64(coeffs)
+        out = np.empty_like(c)
+        _chk(lib().stark_poly_scale(self.h, _p64(c), SZ(len(c)), U64(factor), _p64(out)))
+        return out
+
+    def poly_zerofier_coset(self, offset, log_n):
+        out = np.empty((1 << log_n) + 1, dtype=np.uint64)
+        _chk(lib().stark_poly_zerofier_coset(self.h, U64(offset), U32(log_n), _p64(out)))
+        return out
+
+    def poly_zerofier_domain(self, domain):
+        d = _u64(domain)
+        out = np.empty(len(d) + 1, dtype=np.uint64)
+        _chk(lib().stark_poly_zerofier_domain(self.h, _p64(d), SZ(len(d)), _p64(out)))
+        return out
+
+    # ---- LDE
+    def lde(self, cols, log_blowup, offset=3):
+        """cols: (n_cols, n) array, one trace column per row (column-major storage)."""
+        cols = np.ascontiguousarray(np.asarray(cols, dtype=np.uint64))
+        if cols.ndim == 1:
+            cols = cols[None, :]
+        n_cols, n = cols.shape
+        log_n = n.bit_length() - 1
+        assert 1 << log_n == n
+        out = np.empty((n_cols, n << log_blowup), dtype=np.uint64)
+        _chk(lib().stark_lde(self.h, _p64(cols), U32(n_cols), U32(log_n), U32(log_blowup), U64(offset), _p64(out)))
+        return out
+
+    def lde_dev(self, cols_buf, n_cols, log_n, log_blowup, offset=3, out=None):
+        out = out or self.alloc(n_cols << (log_n + log_blowup))
+        _chk(lib().stark_lde_dev(self.h, cols_buf.h, U32(n_cols), U32(log_n), U32(log_blowup), U64(offset), out.h))
+        return out
+
+    def ntt_dev(self, in_buf, out_buf, log_n, batch=1, inverse=False):
+        _chk(lib().stark_ntt_dev(self.h, in_buf.h, out_buf.h, U32(log_n), U32(batch), C.c_int(1 if inverse else 0)))
+        return out_buf
+
+    # ---- hash / merkle
+    def hash_bytes(self, msgs, msg_len):
+        m = _b(msgs)
+        n = len(m) // msg_len if msg_len else 0
+        out = np.empty((n, 32), dtype=np.uint8)
+        _chk(lib().stark_hash_bytes(self.h, _p8(m), SZ(n), SZ(msg_len), _p8(out)))
+        return out
+
+    def hash_empty(self, n):
+        out = np.empty((n, 32), dtype=np.uint8)
+        m = np.zeros(1, dtype=np.uint8)
+        _chk(lib().stark_hash_bytes(self.h, _p8(m), SZ(n), SZ(0), _p8(out)))
+        return out
+
+    def hash_leaves(self, vals, width=1):
+        v = _u64(vals)
+        n = len(v) // width
+        out = np.empty((n, 32), dtype=np.uint8)
+        _chk(lib().stark_hash_leaves(self.h, _p64(v), SZ(n), U32(width), _p8(out)))
+        return out
+
+    def merkle_build(self, leaves):
+        l = np.ascontiguousarray(leaves, dtype=np.uint8).reshape(-1, 32)
+        h = C.c_void_p()
+        _chk(lib().stark_merkle_build(self.h, _p8(l), SZ(len(l)), C.byref(h)))
+        return MerkleTree(self, h)
+
+    def merkle_build_from_values(self, vals, width=1):
+        v = _u64(vals)
+        h = C.c_void_p()
+        _chk(lib().stark_merkle_build_from_values(self.h, _p64(v), SZ(len(v) // width), U32(width), C.byref(h)))
+        return MerkleTree(self, h)
+
+    def merkle_build_from_buf(self, buf, n_leaves, width=1):
+        h = C.c_void_p()
+        _chk(lib().stark_merkle_build_from_buf(self.h, buf.h, SZ(n_leaves), U32(width), C.byref(h)))
+        return MerkleTree(self, h)
+
+    def merkle_commit(self, leaves):
+        l = np.ascontiguousarray(leaves, dtype=np.uint8).reshape(-1, 32)
+        out = np.empty(32, dtype=np.uint8)
+        _chk(lib().stark_merkle_commit(self.h, _p8(l), SZ(len(l)), _p8(out)))
+        return out.tobytes()
+
+    # ---- fri
+    def fri_fold(self, codeword, alpha_raw, offset, omega):
+        cw = _u64(codeword)
+        out = np.empty(len(cw) // 2, dtype=np.uint64)
+        _chk(lib().stark_fri_fold(self.h, _p64(cw), SZ(len(cw)), U64(alpha_raw), U64(offset), U64(omega), _p64(out)))
+        return out
+
+    def fri_fold_dev(self, cw_buf, n, alpha_raw, offset, omega, out=None):
+        out = out or self.alloc(n // 2)
+        _chk(lib().stark_fri_fold_dev(self.h, cw_buf.h, SZ(n), U64(alpha_raw), U64(offset), U64(omega), out.h))
+        return out
+
+    def fri_commit(self, codeword, offset, omega, expansion_factor, num_colinearity_tests, transcript=b""):
+        cw, t = _u64(codeword), _b(transcript)
+        h = C.c_void_p()
+        _chk(lib().stark_fri_commit(self.h, _p64(cw), SZ(len(cw)), U64(offset), U64(omega), U32(expansion_factor),
+                                    U32(num_colinearity_tests), _p8(t), SZ(len(t)), C.byref(h)))
+        return FriState(self, h)
+
+    def fri_commit_dev(self, cw_buf, n, offset, omega, expansion_factor, num_colinearity_tests, transcript=b""):
+        t = _b(transcript)
+        h = C.c_void_p()
+        _chk(lib().stark_fri_commit_dev(self.h, cw_buf.h, SZ(n), U64(offset), U64(omega), U32(expansion_factor),
+                                        U32(num_colinearity_tests), _p8(t), SZ(len(t)), C.byref(h)))
+        return FriState(self, h)
+
+    def fri_prove(self, codeword, offset, omega, expansion_factor, num_colinearity_tests, transcript=b"",
+                  domain_length=None):
+        """Fri::prove + ProofStream::serialize.  Returns (proof_bytes, top_level_indices)."""
+        cw, t = _u64(codeword), _b(transcript)
+        dl = len(cw) if domain_length is None else domain_length
+        ln = SZ()
+        cap = 0
+        try:
+            cap = fri_proof_size(dl, expansion_factor, num_colinearity_tests)
+        except StarkPanic:
+            pass
+        proof = np.empty(max(cap, 1), dtype=np.uint8)
+        top = np.zeros(max(num_colinearity_tests, 1), dtype=np.uint64)
+        _chk(lib().stark_fri_prove(self.h, _p64(cw), SZ(len(cw)), SZ(dl), U64(offset), U64(omega),
+                                   U32(expansion_factor), U32(num_colinearity_tests), _p8(t), SZ(len(t)), _p8(proof),
+                                   SZ(cap), C.byref(ln), _p64(top)))
+        return proof[: ln.value].tobytes(), [int(x) for x in top[:num_colinearity_tests]]
+
+    def fri_prove_dev(self, cw_buf, n, offset, omega, expansion_factor, num_colinearity_tests, proof_out=None,
+                      transcript=b""):
+        t = _b(transcript)
+        cap = fri_proof_size(n, expansion_factor, num_colinearity_tests)
+        proof = proof_out if proof_out is not None else np.empty(cap, dtype=np.uint8)
+        ln = SZ()
+        _chk(lib().stark_fri_prove_dev(self.h, cw_buf.h, SZ(n), SZ(n), U64(offset), U64(omega), U32(expansion_factor),
+                                       U32(num_colinearity_tests), _p8(t), SZ(len(t)), _p8(proof), SZ(len(proof)),
+                                       C.byref(ln), None))
+        return proof[: ln.value]
+
+    # ---- pipeline (BASELINE config 3)
+    def prove_trace(self, cols, log_blowup, offset=3, num_colinearity_tests=32):
+        """LDE + per-column Merkle commit + Fri::prove on column 0.  Returns (column_roots, proof_bytes)."""
+        cols = np.ascontiguousarray(np.asarray(cols, dtype=np.uint64))
+        if cols.ndim == 1:
+            cols = cols[None, :]
+        n_cols, n = cols.shape
+        log_n = n.bit_length() - 1
+        cap = fri_proof_size(n << log_blowup, 1 << log_blowup, num_colinearity_tests)
+        proof = np.empty(cap, dtype=np.uint8)
+        roots = np.empty((n_cols, 32), dtype=np.uint8)
+        ln = SZ()
+        _chk(lib().stark_prove_trace(self.h, _p64(cols), U32(n_cols), U32(log_n), U32(log_blowup), U64(offset),
+                                     U32(num_colinearity_tests), _p8(roots), _p8(proof), SZ(cap), C.byref(ln)))
+        return roots, proof[: ln.value].tobytes()
+
+    def prove_trace_ptr(self, host_ptr, n_cols, log_n, log_blowup, offset, nq, roots, proof):
+        """same, from a raw (pinned) host pointer into preallocated numpy outputs; returns proof length"""
+        ln = SZ()
+        _chk(lib().stark_prove_trace(self.h, C.cast(host_ptr, U64P), U32(n_cols), U32(log_n), U32(log_blowup),
+                                     U64(offset), U32(nq), _p8(roots), _p8(proof), SZ(len(proof)), C.byref(ln)))
+        return ln.value
+
+    def prove_trace_dev(self, cols_buf, n_cols, log_n, log_blowup, offset, nq, roots, proof):
+        ln = SZ()
+        _chk(lib().stark_prove_trace_dev(self.h, cols_buf.h, U32(n_cols), U32(log_n), U32(log_blowup), U64(offset),
+                                         U32(nq), _p8(roots), _p8(proof), SZ(len(proof)), C.byref(ln)))
+        return ln.value

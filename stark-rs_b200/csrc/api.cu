@@ -1,0 +1,275 @@
+// api.cu -- context, device buffers, host<->device value marshalling and the ff.rs batch entry points.
+//
+// Host values are uint64_t (FieldElement.value, reference src/ff.rs:25-28); device values are uint32_t.
+// upload_u64 narrows on the device and REJECTS non-canonical input (>= p) instead of reducing it: the
+// reference hashes and serialises raw values (hash.rs:32-35, stream.rs:45-51), so silently reducing would
+// break bit-exactness.
+#include "common.cuh"
+#include "merkle.h"
+
+thread_local char g_stark_err[512] = "";
+
+// ------------------------------------------------------------------------------------------- kernels
+
+__global__ void k_narrow(const u64 *__restrict__ in, u32 *__restrict__ out, size_t n, u32 *flag) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u64 v = in[i];
+  if (v >= ff::P) atomicOr(flag, 1u);
+  out[i] = (u32)v;
+}
+__global__ void k_widen(const u32 *__restrict__ in, u64 *__restrict__ out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
+}
+
+enum { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2, OP_NEG = 3, OP_POW = 4 };
+// element-wise ff.rs:138-167, 200-213 on canonical u32
+__global__ void k_ff_vec(int op, const u32 *__restrict__ a, const u32 *__restrict__ b, u64 e, u32 *__restrict__ out,
+                         size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const u32 x = a[i];
+    u32 r;
+    switch (op) {
+      case OP_ADD: r = ff::add(x, b[i]); break;
+      case OP_SUB: r = ff::sub(x, b[i]); break;
+      case OP_MUL: r = ff::mul(x, b[i]); break;
+      case OP_NEG: r = ff::neg(x); break;
+      default: r = ff::pow(x, e); break;
+    }
+    out[i] = r;
+  }
+}
+// ff.rs:169-178 for a whole vector: Montgomery batch inversion, 8 elements per thread (one Fermat
+// exponentiation per 8 inverses).  Sets *flag when an element is zero ("no inverse").
+__global__ void k_ff_vec_inv(const u32 *__restrict__ a, u32 *__restrict__ out, size_t n, u32 *flag) {
+  constexpr int K = 8;
+  const size_t T = (size_t)gridDim.x * blockDim.x;
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  u32 x[K], pre[K];
+  u32 acc = ff::R1;  // Montgomery one
+  bool zero = false;
+#pragma unroll
+  for (int j = 0; j < K; j++) {
+    const size_t i = t + (size_t)j * T;
+    u32 v = i < n ? a[i] : 1u;
+    if (v == 0) zero = true, v = 1u;
+    x[j] = ff::to_mont(v);
+    pre[j] = acc;
+    acc = ff::canon(ff::mont_mul(acc, x[j]));
+  }
+  if (zero) atomicOr(flag, 2u);
+  u32 inv = ff::mont_pow(acc, (u64)ff::P - 2);  // (prod)^-1, Montgomery form
+#pragma unroll
+  for (int j = K - 1; j >= 0; j--) {
+    const size_t i = t + (size_t)j * T;
+    const u32 r = ff::canon(ff::mont_mul(inv, pre[j]));  // x[j]^-1 (Montgomery)
+    inv = ff::canon(ff::mont_mul(inv, x[j]));
+    if (i < n) out[i] = ff::from_mont(r);
+  }
+}
+
+// ------------------------------------------------------------------------------------- marshalling
+
+static int read_flag(stark_ctx *ctx, u32 *value) {
+  CU_TRY(ctx, cudaMemcpyAsync(ctx->h_flag, ctx->flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  *value = *ctx->h_flag;
+  return STARK_OK;
+}
+
+int upload_u64(stark_ctx *ctx, const uint64_t *host, size_t n, u32 *dst) {
+  if (n == 0) return STARK_OK;
+  u64 *tmp = nullptr;
+  ST_TRY(dev_alloc(ctx, (void **)&tmp, n * 8));
+  CU_TRY(ctx, cudaMemsetAsync(ctx->flag, 0, 4, ctx->stream));
+  CU_TRY(ctx, cudaMemcpyAsync(tmp, host, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  k_narrow<<<(u32)((n + 255) / 256), 256, 0, ctx->stream>>>(tmp, dst, n, ctx->flag);
+  KERNEL_CHECK(ctx);
+  dev_free(ctx, tmp);
+  u32 f = 0;
+  ST_TRY(read_flag(ctx, &f));
+  if (f) return stark_fail(ctx, STARK_ERR_ARG, "non-canonical field element (value >= p) in input");
+  return STARK_OK;
+}
+
+int download_u64(stark_ctx *ctx, const u32 *src, size_t n, uint64_t *host) {
+  if (n == 0) return STARK_OK;
+  u64 *tmp = nullptr;
+  ST_TRY(dev_alloc(ctx, (void **)&tmp, n * 8));
+  k_widen<<<(u32)((n + 255) / 256), 256, 0, ctx->stream>>>(src, tmp, n);
+  KERNEL_CHECK(ctx);
+  CU_TRY(ctx, cudaMemcpyAsync(host, tmp, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  dev_free(ctx, tmp);
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return STARK_OK;
+}
+
+// ----------------------------------------------------------------------------------------------- C ABI
+
+extern "C" {
+
+const char *stark_last_error(void) { return g_stark_err; }
+const char *stark_version(void) { return "stark_b200 0.1 (sm_100a)"; }
+
+static int ctx_create(int device, cudaStream_t borrowed, bool borrow, stark_ctx **out) {
+  if (!out) return stark_fail(nullptr, STARK_ERR_ARG, "null argument");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return stark_fail(nullptr, STARK_ERR_CUDA, "no CUDA device available (%s); libstark_b200 has no CPU fallback",
+                      cudaGetErrorString(e));
+  if (device < 0 || device >= count) return stark_fail(nullptr, STARK_ERR_ARG, "device %d out of range", device);
+  CU_TRY(nullptr, cudaSetDevice(device));
+  stark_ctx *ctx = new stark_ctx();
+  memset(ctx, 0, sizeof *ctx);
+  ctx->device = device;
+  if (borrow) {
+    ctx->stream = borrowed, ctx->own_stream = false;
+  } else {
+    cudaError_t se = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (se != cudaSuccess) {
+      delete ctx;
+      return stark_fail(nullptr, STARK_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(se));
+    }
+    ctx->own_stream = true;
+  }
+  cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  // keep freed scratch memory in the stream-ordered pool instead of returning it to the driver
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  int rc = STARK_OK;
+  if (cudaMalloc(&ctx->flag, 16) != cudaSuccess || cudaMallocHost(&ctx->h_flag, 16) != cudaSuccess)
+    rc = stark_fail(nullptr, STARK_ERR_OOM, "context allocation failed");
+  if (rc == STARK_OK) rc = ntt_init(ctx);
+  if (rc == STARK_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+    rc = stark_fail(nullptr, STARK_ERR_CUDA, "context initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (rc != STARK_OK) {
+    delete ctx;
+    return rc;
+  }
+  ctx->launches = 0;
+  *out = ctx;
+  return STARK_OK;
+}
+int stark_ctx_create(int device, stark_ctx **out) { return ctx_create(device, nullptr, false, out); }
+int stark_ctx_create_on_stream(int device, void *cuda_stream, stark_ctx **out) {
+  return ctx_create(device, (cudaStream_t)cuda_stream, true, out);
+}
+void stark_ctx_destroy(stark_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  ntt_destroy(ctx);
+  cudaFree(ctx->flag);
+  cudaFreeHost(ctx->h_flag);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+int stark_ctx_sync(stark_ctx *ctx) {
+  if (!ctx) return stark_fail(nullptr, STARK_ERR_ARG, "null context");
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return STARK_OK;
+}
+void *stark_ctx_stream(stark_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+uint64_t stark_ctx_launches(stark_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- buffers
+int stark_buf_alloc(stark_ctx *ctx, size_t n, stark_buf **out) {
+  if (!ctx || !out) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+  stark_buf *b = new stark_buf{ctx, nullptr, n, true};
+  int rc = dev_alloc(ctx, (void **)&b->ptr, n * 4);
+  if (rc != STARK_OK) {
+    delete b;
+    return rc;
+  }
+  *out = b;
+  return STARK_OK;
+}
+int stark_buf_upload(stark_ctx *ctx, const uint64_t *host, size_t n, stark_buf **out) {
+  if (!ctx || !out || (!host && n)) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+  stark_buf *b = nullptr;
+  ST_TRY(stark_buf_alloc(ctx, n, &b));
+  int rc = upload_u64(ctx, host, n, b->ptr);
+  if (rc != STARK_OK) {
+    stark_buf_free(b);
+    return rc;
+  }
+  *out = b;
+  return STARK_OK;
+}
+int stark_buf_upload_into(stark_ctx *ctx, const uint64_t *host, size_t n, stark_buf *dst, size_t dst_off) {
+  if (!ctx || !dst || (!host && n)) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+  if (dst_off + n > dst->n) return stark_fail(ctx, STARK_ERR_ARG, "buffer too small");
+  return upload_u64(ctx, host, n, dst->ptr + dst_off);
+}
+int stark_buf_download(stark_ctx *ctx, const stark_buf *buf, size_t off, size_t n, uint64_t *host) {
+  if (!ctx || !buf || (!host && n)) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+  if (off + n > buf->n) return stark_fail(ctx, STARK_ERR_ARG, "range out of bounds");
+  return download_u64(ctx, buf->ptr + off, n, host);
+}
+int stark_buf_wrap(stark_ctx *ctx, void *device_u32, size_t n, stark_buf **out) {
+  if (!ctx || !out || (!device_u32 && n)) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+  *out = new stark_buf{ctx, (u32 *)device_u32, n, false};
+  return STARK_OK;
+}
+void *stark_buf_ptr(const stark_buf *buf) { return buf ? buf->ptr : nullptr; }
+size_t stark_buf_len(const stark_buf *buf) { return buf ? buf->n : 0; }
+void stark_buf_free(stark_buf *buf) {
+  if (!buf) return;
+  if (buf->owns && buf->ptr) dev_free(buf->ctx, buf->ptr);
+  delete buf;
+}
+
+// ---- ff.rs batch ops
+static int ff_vec(stark_ctx *ctx, int op, const uint64_t *a, const uint64_t *b, u64 e, uint64_t *out, size_t n) {
+  if (!ctx || (n && (!a || !out)) || (n && op <= OP_MUL && !b)) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+  if (n == 0) return STARK_OK;
+  u32 *da = nullptr, *db = nullptr, *dout = nullptr;
+  ST_TRY(dev_alloc(ctx, (void **)&da, n * 4));
+  ST_TRY(dev_alloc(ctx, (void **)&dout, n * 4));
+  int rc = upload_u64(ctx, a, n, da);
+  if (rc == STARK_OK && op <= OP_MUL) {
+    rc = dev_alloc(ctx, (void **)&db, n * 4);
+    if (rc == STARK_OK) rc = upload_u64(ctx, b, n, db);
+  }
+  if (rc == STARK_OK) {
+    if (op == 5) {
+      cudaMemsetAsync(ctx->flag, 0, 4, ctx->stream);
+      const size_t threads = (n + 7) / 8;
+      k_ff_vec_inv<<<(u32)((threads + 127) / 128), 128, 0, ctx->stream>>>(da, dout, n, ctx->flag);
+      ctx->launches++;
+      u32 f = 0;
+      rc = read_flag(ctx, &f);
+      if (rc == STARK_OK && f) rc = stark_fail(ctx, STARK_ERR_ARG, "no inverse");  // ff.rs:171
+    } else {
+      const u32 blocks = (u32)((n + 255) / 256 < (size_t)ctx->sm_count * 16 ? (n + 255) / 256 : (size_t)ctx->sm_count * 16);
+      k_ff_vec<<<blocks, 256, 0, ctx->stream>>>(op, da, db, e, dout, n);
+      ctx->launches++;
+    }
+    if (rc == STARK_OK && cudaGetLastError() != cudaSuccess) rc = stark_fail(ctx, STARK_ERR_CUDA, "kernel launch failed");
+  }
+  if (rc == STARK_OK) rc = download_u64(ctx, dout, n, out);
+  dev_free(ctx, da), dev_free(ctx, db), dev_free(ctx, dout);
+  return rc;
+}
+int stark_ff_vec_add(stark_ctx *c, const uint64_t *a, const uint64_t *b, uint64_t *o, size_t n) { return ff_vec(c, OP_ADD, a, b, 0, o, n); }
+int stark_ff_vec_sub(stark_ctx *c, const uint64_t *a, const uint64_t *b, uint64_t *o, size_t n) { return ff_vec(c, OP_SUB, a, b, 0, o, n); }
+int stark_ff_vec_mul(stark_ctx *c, const uint64_t *a, const uint64_t *b, uint64_t *o, size_t n) { return ff_vec(c, OP_MUL, a, b, 0, o, n); }
+int stark_ff_vec_neg(stark_ctx *c, const uint64_t *a, uint64_t *o, size_t n) { return ff_vec(c, OP_NEG, a, nullptr, 0, o, n); }
+int stark_ff_vec_pow(stark_ctx *c, const uint64_t *a, uint64_t e, uint64_t *o, size_t n) { return ff_vec(c, OP_POW, a, nullptr, e, o, n); }
+int stark_ff_vec_inv(stark_ctx *c, const uint64_t *a, uint64_t *o, size_t n) { return ff_vec(c, 5, a, nullptr, 0, o, n); }
+
+int stark_ff_prim_nth_root(uint64_t n, uint64_t *out) {
+  if (!out) return stark_fail(nullptr, STARK_ERR_ARG, "null argument");
+  if (n == 0 || (n & (n - 1))) return stark_fail(nullptr, STARK_ERR_ARG, "n must be a power of two");       // ff.rs:217
+  if (n > (1ull << 23)) return stark_fail(nullptr, STARK_ERR_ARG, "n > 2^23 not supported by this modulus");  // ff.rs:218
+  *out = ff::pow(ff::GEN, (ff::P - 1) / n);
+  return STARK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,94 @@
+// common.cuh -- context, status codes and error plumbing shared by the .cu files of libstark_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/stark_b200.h"
+#include "field.cuh"
+#include "ntt_core.cuh"
+
+typedef uint8_t u8;
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+struct GeoCacheEntry {
+  u32 g, c;        // canonical base and constant
+  u32 *lo, *hi;    // device tables (4096 + hi_len entries)
+  u32 hi_len;
+  u64 stamp;
+};
+
+struct stark_ctx {
+  int device;
+  cudaStream_t stream;
+  bool own_stream;
+  int sm_count;
+  // w23 power tables (forward), Montgomery form
+  u32 *root_lo, *root_hi;
+  // per-length sub-transform twiddles: tw_sub[dir][(1 << logL) + e] = w_L^(+-e), logL <= 12
+  u32 *tw_sub[2];
+  u32 w8[2][4];
+  GeoCacheEntry geo[8];
+  u64 geo_stamp;
+  u32 *flag;       // device int used by validation kernels
+  u32 *h_flag;     // pinned host mirror
+  u64 launches;    // kernels launched through this context (bench.py "gpu_launches")
+  char err[512];
+};
+
+extern thread_local char g_stark_err[512];
+
+static inline int stark_fail(stark_ctx *ctx, int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_stark_err, sizeof g_stark_err, fmt, ap);
+  va_end(ap);
+  if (ctx) snprintf(ctx->err, sizeof ctx->err, "%s", g_stark_err);
+  return code;
+}
+
+#define CU_TRY(ctx, expr)                                                                            \
+  do {                                                                                               \
+    cudaError_t e__ = (expr);                                                                        \
+    if (e__ != cudaSuccess)                                                                          \
+      return stark_fail((ctx), e__ == cudaErrorMemoryAllocation ? STARK_ERR_OOM : STARK_ERR_CUDA,    \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+#define ST_TRY(expr)            \
+  do {                          \
+    int s__ = (expr);           \
+    if (s__ != STARK_OK) return s__; \
+  } while (0)
+
+#define KERNEL_CHECK(ctx)                \
+  do {                                   \
+    (ctx)->launches++;                   \
+    CU_TRY((ctx), cudaGetLastError());   \
+  } while (0)
+
+// stream-ordered scratch allocation (no device-wide sync on the hot path)
+static inline int dev_alloc(stark_ctx *ctx, void **p, size_t bytes) {
+  CU_TRY(ctx, cudaMallocAsync(p, bytes ? bytes : 16, ctx->stream));
+  return STARK_OK;
+}
+static inline void dev_free(stark_ctx *ctx, void *p) {
+  if (p) cudaFreeAsync(p, ctx->stream);
+}
+
+// ---- internal device-pointer entry points (implemented in ntt.cu / poly.cu / merkle.cu / fri.cu)
+struct ScaleSpec {
+  int mode;   // ntt::ScaleMode
+  u32 c;      // canonical constant (SCALE_CONST, SCALE_GEO)
+  u32 g;      // canonical base (SCALE_GEO)
+};
+int ntt_init(stark_ctx *ctx);
+void ntt_destroy(stark_ctx *ctx);
+int geo_tables(stark_ctx *ctx, u32 g, u32 c, u64 max_index, ntt::GeoTables *out);
+// batched transform of length 2^log_n: in/out device u32 (canonical), n_valid = leading input elements that are
+// read (the rest are zero), batch strides in elements.  in == out is allowed.
+int ntt_transform(stark_ctx *ctx, const u32 *in, u32 *out, int log_n, bool inverse, u32 batch, u64 in_batch,
+                  u64 out_batch, u64 n_valid, ScaleSpec pre, ScaleSpec post);

@@ -1,0 +1,652 @@
+// fri.cu -- FRI prover on the device (reference src/fri.rs:29-311, src/fiat_shamir.rs, src/stream.rs:35-64).
+//
+// Fri::prove runs as ONE stream of kernel launches with no host round trip: per round leaf hashes + tree
+// (merkle.cu), a one-thread transcript kernel that absorbs the root and draws alpha (fiat_shamir.rs:15-25),
+// and the fused fold kernel; then index sampling (fri.rs:176-213), and kernels that gather the revealed
+// values and authentication paths straight into ProofStream::serialize's byte layout (stream.rs:35-64).  The
+// host makes a single D2H copy of the finished proof.  Every tree is built once and kept (the reference
+// rebuilds each tree 2-3x, fri.rs:127, 288-298); results are identical because a tree is a pure function of
+// its codeword.
+//
+// fold_codeword (fri.rs:57-91) in closed form:
+//   out[i] = (c[i] + c[i+h]) / 2  +  (alpha mod p) / (2 offset) * w^-i * (c[i] - c[i+h])
+// The per-element exp + two xgcd inversions of the reference become one geometric twiddle: w^-i comes from a
+// two-level table of (w0^-1)^e shared by all rounds (round r uses e = i * 2^r), i.e. the inverted domain
+// constants are produced by ONE host inversion, not one per element.  12 bytes of HBM traffic per output.
+#include <vector>
+
+#include "common.cuh"
+#include "hash.cuh"
+#include "merkle.h"
+
+using hs::State;
+using ntt::GeoTables;
+
+// ---------------------------------------------------------------------------------------- transcript
+
+// streaming form of Hash::from_bytes over an append-only transcript (fiat_shamir.rs:4-25): `s` is the sponge
+// after all complete 32-byte chunks (each followed by its mix, round constants settled), `pend` the bytes of
+// the incomplete last chunk.
+struct TranscriptDev {
+  u32 s[32];
+  u8 pend[32];
+  u32 npend;
+};
+
+HS_HD void tr_init(TranscriptDev &T) {
+  for (int i = 0; i < 32; i++) T.s[i] = hs::prime_at(i), T.pend[i] = 0;
+  T.npend = 0;
+}
+HS_HD void tr_absorb(TranscriptDev &T, const u8 *data, size_t n) {
+  for (size_t k = 0; k < n; k++) {
+    T.pend[T.npend++] = data[k];
+    if (T.npend == 32) {
+      State st;
+      for (int i = 0; i < 32; i++) st.s[i] = T.s[i];
+      for (int i = 0; i < 32; i++) hs::absorb_byte(st, i, T.pend[i]);
+      hs::mix_lazy<false>(st);
+      hs::settle(st);
+      for (int i = 0; i < 32; i++) T.s[i] = st.s[i] & 0xffu;
+      T.npend = 0;
+    }
+  }
+}
+// FiatShamir::challenge (fiat_shamir.rs:19-25): first 8 bytes of Hash(transcript), little-endian, UNREDUCED
+HS_HD u64 tr_challenge(const TranscriptDev &T) {
+  State st;
+  for (int i = 0; i < 32; i++) st.s[i] = T.s[i];
+  if (T.npend) {
+    for (u32 i = 0; i < T.npend; i++) {
+      const u32 v = hs::rotl_lazy(st.s[i] + T.pend[i], 3);
+      st.s[i] = v;
+      st.s[(i + 7) & 31] ^= v;
+    }
+    hs::mix_lazy<false>(st);
+    hs::finalize<true>(st);
+  } else {
+    hs::finalize<false>(st);
+  }
+  u64 v = 0;
+  for (int b = 0; b < 8; b++) v |= (u64)(st.s[b] & 0xffu) << (8 * b);
+  return v;
+}
+
+// absorb one Merkle root (fri.rs:129-131) and, unless it is the last round (fri.rs:133-135), draw alpha
+// (fri.rs:138).  One thread; the root is read from the tree, also copied to roots_out.
+__global__ void k_transcript_round(TranscriptDev *T, const u8 *root, u8 *roots_out, int draw, u64 *alpha_raw,
+                                   u32 *alpha_m) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  u8 r[32];
+  for (int i = 0; i < 32; i++) r[i] = root[i], roots_out[i] = r[i];
+  TranscriptDev t = *T;
+  tr_absorb(t, r, 32);
+  *T = t;
+  if (draw) {
+    const u64 a = tr_challenge(t);
+    *alpha_raw = a;
+    *alpha_m = ff::to_mont(ff::reduce64(a));
+  }
+}
+__global__ void k_transcript_challenge(const TranscriptDev *T, u64 *out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  *out = tr_challenge(*T);
+}
+
+// ---------------------------------------------------------------------------------------------- fold
+
+// V outputs per thread (128-bit accesses for V = 4).  tw(i) = K * g_r^i, g_r^i = g0^(i << r).
+template <int V>
+__global__ void __launch_bounds__(256) k_fri_fold(const u32 *__restrict__ cw, u32 *__restrict__ out, size_t h, int r,
+                                                  GeoTables G, u32 g_r_m, const u32 *__restrict__ alpha_m,
+                                                  u32 inv2off_m) {
+  const u32 K = ff::canon(ff::mont_mul(*alpha_m, inv2off_m));
+  const size_t stride = (size_t)gridDim.x * blockDim.x * V;
+  for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * V; i < h; i += stride) {
+    u32 a[V], b[V], o[V];
+    if constexpr (V == 4) {
+      const uint4 x = *reinterpret_cast<const uint4 *>(cw + i), y = *reinterpret_cast<const uint4 *>(cw + h + i);
+      a[0] = x.x, a[1] = x.y, a[2] = x.z, a[3] = x.w;
+      b[0] = y.x, b[1] = y.y, b[2] = y.z, b[3] = y.w;
+    } else {
+      a[0] = cw[i], b[0] = cw[h + i];
+    }
+    u32 tw = ff::canon(ff::mont_mul(ntt::geo_pow(G, (u64)i << r), K));
+#pragma unroll
+    for (int k = 0; k < V; k++) {
+      const u32 s = a[k] + b[k];           // < 2p
+      const u32 d = a[k] + ff::P - b[k];   // < 2p
+      o[k] = ff::canon4(ff::half(s) + ff::mont_mul(d, tw));
+      if (k + 1 < V) tw = ff::canon(ff::mont_mul(tw, g_r_m));
+    }
+    if constexpr (V == 4)
+      *reinterpret_cast<uint4 *>(out + i) = make_uint4(o[0], o[1], o[2], o[3]);
+    else
+      out[i] = o[0];
+  }
+}
+
+// ------------------------------------------------------------------------------------ index sampling
+
+// Fri::sample_indices (fri.rs:176-213) with seed = Hash::from_u64(challenge) (fri.rs:272): candidates for a
+// batch of counters are hashed in parallel, thread 0 then applies the sequential reject rule.
+__global__ void __launch_bounds__(256) k_sample_indices(const u64 *challenge, u64 size, u64 reduced, u32 number,
+                                                        u64 *out) {
+  __shared__ u64 cand[256];
+  __shared__ u8 seed[32];
+  __shared__ u32 got;
+  if (threadIdx.x == 0) {
+    const u64 c = *challenge;
+    u8 m[8];
+    for (int b = 0; b < 8; b++) m[b] = (u8)(c >> (8 * b));
+    hs::from_bytes(m, 8, seed);
+    got = 0;
+  }
+  __syncthreads();
+  for (u32 base = 0;; base += 256) {
+    u8 msg[36], h[32];
+    for (int i = 0; i < 32; i++) msg[i] = seed[i];
+    const u32 counter = base + threadIdx.x;
+    for (int b = 0; b < 4; b++) msg[32 + b] = (u8)(counter >> (8 * b));  // fri.rs:199-200
+    hs::from_bytes(msg, 36, h);
+    u64 v = 0;
+    for (int b = 24; b < 32; b++) v = (v << 8) | h[b];  // fri.rs:168-174: low 64 bits of the big-endian value
+    cand[threadIdx.x] = v % size;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      u32 g = got;
+      for (u32 k = 0; k < 256 && g < number; k++) {
+        const u64 idx = cand[k], ri = idx % reduced;
+        bool seen = false;
+        for (u32 j = 0; j < g; j++)
+          if (out[j] % reduced == ri) seen = true;
+        if (!seen) out[g++] = idx;
+      }
+      got = g;
+    }
+    __syncthreads();
+    if (got >= number) break;
+  }
+}
+
+// ------------------------------------------------------------------------------------ proof assembly
+
+__device__ __forceinline__ void put_u64(u8 *d, u64 v) {
+#pragma unroll
+  for (int b = 0; b < 8; b++) d[b] = (u8)(v >> (8 * b));
+}
+// R x [0x00, root]  then  [0x02, len u64, values u64...]   (fri.rs:129, 151; stream.rs:39-53)
+__global__ void k_proof_header(u8 *out, const u8 *roots, u32 R, const u32 *last, u64 last_len) {
+  const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < R) {
+    u8 *d = out + 33 * t;
+    d[0] = 0;
+    for (int i = 0; i < 32; i++) d[1 + i] = roots[32 * t + i];
+  }
+  u8 *base = out + 33 * (u64)R;
+  if (t == 0) {
+    base[0] = 2;
+    put_u64(base + 1, last_len);
+  }
+  if (t < last_len) put_u64(base + 9 + 8 * t, last[t]);
+}
+// one query round (fri.rs:215-248): nq x [0x02, 3, a, b, c]  then  nq x (path a, path b, path c), each path
+// [0x03, depth u64, depth hashes] (stream.rs:54-60); indices folded as fri.rs:282-285.
+__global__ void k_proof_round(u8 *out, const u32 *cur, const u32 *nxt, u64 cur_len, const u8 *cur_nodes,
+                              const u8 *nxt_nodes, const u64 *top, u32 nq, u32 depth_cur) {
+  const u64 half = cur_len >> 1;
+  const u32 depth_nxt = depth_cur - 1;
+  const u64 triples = 33ull * nq;
+  const u64 path_cur = 9 + 32ull * depth_cur, path_nxt = 9 + 32ull * depth_nxt;
+  const u64 per_q = 2 * path_cur + path_nxt;
+  const u32 hashes_per_q = 2 * depth_cur + depth_nxt;
+  const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nq) {
+    const u64 c = top[t] % half;
+    u8 *d = out + 33 * t;
+    d[0] = 2;
+    put_u64(d + 1, 3);
+    put_u64(d + 9, cur[c]);
+    put_u64(d + 17, cur[c + half]);
+    put_u64(d + 25, nxt[c]);
+    u8 *p = out + triples + per_q * t;
+    p[0] = 3, put_u64(p + 1, depth_cur);
+    p += path_cur;
+    p[0] = 3, put_u64(p + 1, depth_cur);
+    p += path_cur;
+    p[0] = 3, put_u64(p + 1, depth_nxt);
+  }
+  if (t >= (u64)nq * hashes_per_q) return;
+  const u32 q = (u32)(t / hashes_per_q), k = (u32)(t % hashes_per_q);
+  const u64 c = top[q] % half;
+  u64 leaf, n_tree;
+  const u8 *nodes;
+  u32 level;
+  u8 *dst = out + triples + per_q * q;
+  if (k < depth_cur) {
+    leaf = c, nodes = cur_nodes, n_tree = cur_len, level = k, dst += 9 + 32ull * level;
+  } else if (k < 2 * depth_cur) {
+    leaf = c + half, nodes = cur_nodes, n_tree = cur_len, level = k - depth_cur, dst += path_cur + 9 + 32ull * level;
+  } else {
+    leaf = c, nodes = nxt_nodes, n_tree = half, level = k - 2 * depth_cur, dst += 2 * path_cur + 9 + 32ull * level;
+  }
+  const u64 sib = (leaf >> level) ^ 1;  // merkle.rs:73-77
+  const uint4 *src = reinterpret_cast<const uint4 *>(nodes + 32 * ((2 * n_tree - 2 * (n_tree >> level)) + sib));
+  const uint4 x = src[0], y = src[1];
+  const u32 w[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+#pragma unroll
+  for (int i = 0; i < 32; i++) dst[i] = (u8)(w[i >> 2] >> (8 * (i & 3)));
+}
+
+// ---------------------------------------------------------------------------------------- host logic
+
+struct stark_fri_state {
+  stark_ctx *ctx;
+  u32 rounds;                 // Fri::num_rounds()
+  std::vector<u32 *> cw;      // codewords[i] (fri.rs:110,140,153); cw[0] borrowed if !own0
+  std::vector<size_t> len;
+  std::vector<stark_tree *> trees;  // tree of codewords[i] for i < rounds
+  bool own0;
+  u8 *d_roots;        // rounds * 32
+  u64 *d_alpha_raw;   // rounds entries (last unused)
+  u32 *d_alpha_m;
+  TranscriptDev *d_tr;
+  u32 nq, ef;
+};
+
+static int fri_check(stark_ctx *ctx, size_t n, u32 ef, u32 *rounds, u32 nq) {
+  if (n == 0 || (n & (n - 1))) return stark_fail(ctx, STARK_ERR_ARG, "Domain length must be power of 2");    // fri.rs:37-40
+  if (ef == 0 || (ef & (ef - 1))) return stark_fail(ctx, STARK_ERR_ARG, "Expansion factor must be power of 2");  // fri.rs:41-44
+  if (ef < 4) return stark_fail(ctx, STARK_ERR_ARG, "Expansion factor must be at least 4");                  // fri.rs:45
+  size_t len = n;
+  u32 r = 0;
+  while (len > ef && 4 * (size_t)nq < len) len >>= 1, r++;  // fri.rs:93-103
+  *rounds = r;
+  return STARK_OK;
+}
+
+static void fri_state_free(stark_fri_state *s) {
+  if (!s) return;
+  stark_ctx *ctx = s->ctx;
+  for (size_t i = 0; i < s->cw.size(); i++)
+    if (i > 0 || s->own0) dev_free(ctx, s->cw[i]);
+  for (stark_tree *t : s->trees) stark_merkle_free(t);
+  dev_free(ctx, s->d_roots), dev_free(ctx, s->d_alpha_raw), dev_free(ctx, s->d_alpha_m), dev_free(ctx, s->d_tr);
+  delete s;
+}
+
+static int fold_launch(stark_ctx *ctx, const u32 *cw, u32 *out, size_t h, int r, GeoTables G, u32 g_r_m,
+                       const u32 *alpha_m, u32 inv2off_m) {
+  if (h == 0) return STARK_OK;
+  if (h % 4 == 0) {
+    size_t blocks = (h / 4 + 255) / 256, cap = (size_t)ctx->sm_count * 8;
+    k_fri_fold<4><<<(u32)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(cw, out, h, r, G, g_r_m, alpha_m, inv2off_m);
+  } else {
+    k_fri_fold<1><<<(u32)((h + 255) / 256), 256, 0, ctx->stream>>>(cw, out, h, r, G, g_r_m, alpha_m, inv2off_m);
+  }
+  KERNEL_CHECK(ctx);
+  return STARK_OK;
+}
+
+// Fri::commit (fri.rs:105-156) on device.  cw0 is borrowed unless copy0.
+static int fri_commit_dev(stark_ctx *ctx, const u32 *cw0, size_t n, u32 offset, u32 omega, u32 ef, u32 nq,
+                          const u8 *transcript, size_t transcript_len, bool copy0, stark_fri_state **out) {
+  u32 R = 0;
+  ST_TRY(fri_check(ctx, n, ef, &R, nq));
+  // fold_codeword divides by x = offset * w^i (fri.rs:72-78 -> ff.rs:182)
+  if (R > 1 && (offset == 0 || (omega == 0 && n > 2))) return stark_fail(ctx, STARK_ERR_ARG, "no division by zero");
+  stark_fri_state *s = new stark_fri_state();
+  s->ctx = ctx, s->rounds = R, s->own0 = copy0, s->nq = nq, s->ef = ef;
+  s->d_roots = nullptr, s->d_alpha_raw = nullptr, s->d_alpha_m = nullptr, s->d_tr = nullptr;
+  int rc = STARK_OK;
+#define TRY_(e)                      \
+  if (rc == STARK_OK) rc = (e);
+  TRY_(dev_alloc(ctx, (void **)&s->d_roots, (size_t)(R ? R : 1) * 32));
+  TRY_(dev_alloc(ctx, (void **)&s->d_alpha_raw, (size_t)(R ? R : 1) * 8));
+  TRY_(dev_alloc(ctx, (void **)&s->d_alpha_m, (size_t)(R ? R : 1) * 4));
+  TRY_(dev_alloc(ctx, (void **)&s->d_tr, sizeof(TranscriptDev)));
+  if (rc == STARK_OK) {
+    TranscriptDev t;
+    tr_init(t);
+    if (transcript_len) tr_absorb(t, transcript, transcript_len);  // host side: FiatShamir prefix
+    if (cudaMemcpyAsync(s->d_tr, &t, sizeof t, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+      rc = stark_fail(ctx, STARK_ERR_CUDA, "H2D copy failed");
+  }
+  u32 *cur = const_cast<u32 *>(cw0);
+  if (rc == STARK_OK && copy0) {
+    u32 *c = nullptr;
+    rc = dev_alloc(ctx, (void **)&c, n * 4);
+    if (rc == STARK_OK && cudaMemcpyAsync(c, cw0, n * 4, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess)
+      rc = stark_fail(ctx, STARK_ERR_CUDA, "D2D copy failed");
+    cur = c;
+  }
+  if (rc == STARK_OK) s->cw.push_back(cur), s->len.push_back(n);
+  GeoTables G = {nullptr, nullptr};
+  u32 g0 = 1;
+  if (rc == STARK_OK && R > 1) {
+    g0 = ff::inv(omega);
+    rc = geo_tables(ctx, g0, 1, n / 2, &G);
+  }
+  u32 off_r = offset, g_r = g0;
+  size_t len = n;
+  for (u32 r = 0; r < R && rc == STARK_OK; r++) {
+    stark_tree *tree = nullptr;
+    rc = merkle_build_from_dev_values(ctx, s->cw[r], len, 1, 1, 0, &tree);  // fri.rs:118-127
+    if (rc != STARK_OK) break;
+    s->trees.push_back(tree);
+    const bool last = r == R - 1;
+    k_transcript_round<<<1, 32, 0, ctx->stream>>>(s->d_tr, tree->nodes + 32 * (2 * len - 2), s->d_roots + 32 * r,
+                                                  last ? 0 : 1, s->d_alpha_raw + r, s->d_alpha_m + r);
+    ctx->launches++;
+    if (last) break;  // fri.rs:133-135
+    u32 *nxt = nullptr;
+    rc = dev_alloc(ctx, (void **)&nxt, (len / 2) * 4);
+    if (rc != STARK_OK) break;
+    const u32 inv2off_m = ff::to_mont(ff::inv(ff::mul(2, off_r)));
+    rc = fold_launch(ctx, s->cw[r], nxt, len / 2, (int)r, G, ff::to_mont(g_r), s->d_alpha_m + r, inv2off_m);
+    s->cw.push_back(nxt), s->len.push_back(len / 2);
+    len /= 2;
+    off_r = ff::mul(off_r, off_r), g_r = ff::mul(g_r, g_r);  // fri.rs:146-147
+  }
+#undef TRY_
+  if (rc == STARK_OK && cudaGetLastError() != cudaSuccess) rc = stark_fail(ctx, STARK_ERR_CUDA, "kernel launch failed");
+  if (rc != STARK_OK) {
+    fri_state_free(s);
+    return rc;
+  }
+  *out = s;
+  return STARK_OK;
+}
+
+struct ProofLayout {
+  u32 R, n_cw;              // rounds, number of codewords (max(R,1))
+  size_t last_len, header;  // bytes of roots + last codeword object
+  std::vector<size_t> round_off;
+  size_t total;
+};
+static void proof_layout(size_t n, u32 R, u32 nq, ProofLayout *L) {
+  L->R = R, L->n_cw = R ? R : 1;
+  L->last_len = n >> (L->n_cw - 1);
+  L->header = 33 * (size_t)R + 9 + 8 * L->last_len;
+  size_t off = L->header;
+  L->round_off.clear();
+  for (u32 i = 0; i + 1 < L->n_cw; i++) {
+    L->round_off.push_back(off);
+    size_t len = n >> i;
+    u32 d = 0;
+    for (size_t m = len; m > 1; m >>= 1) d++;
+    off += (size_t)nq * (33 + 2 * (9 + 32 * (size_t)d) + (9 + 32 * (size_t)(d - 1)));
+  }
+  L->total = off;
+}
+
+// Fri::prove (fri.rs:250-311) + ProofStream::serialize: proof bytes to host in one D2H copy
+static int fri_prove_dev(stark_ctx *ctx, const u32 *cw0, size_t n, size_t domain_length, u32 offset, u32 omega, u32 ef,
+                         u32 nq, const u8 *transcript, size_t transcript_len, u8 *proof, size_t proof_cap,
+                         size_t *proof_len, u64 *top_indices) {
+  if (n != domain_length)
+    return stark_fail(ctx, STARK_ERR_ARG, "initial codeword length does not match domain length");  // fri.rs:256-260
+  u32 R = 0;
+  ST_TRY(fri_check(ctx, n, ef, &R, nq));
+  ProofLayout L;
+  proof_layout(n, R, nq, &L);
+  if (proof_len) *proof_len = L.total;
+  // fri.rs:183-192
+  if ((size_t)nq > 2 * L.last_len) return stark_fail(ctx, STARK_ERR_ARG, "not enough entropy in indices wrt last codeword");
+  if ((size_t)nq > L.last_len)
+    return stark_fail(ctx, STARK_ERR_ARG, "cannot sample more indices than available in last codeword; requested: %u, available: %zu", nq, L.last_len);
+  if (!proof || proof_cap < L.total) return stark_fail(ctx, STARK_ERR_ARG, "proof buffer too small: need %zu bytes", L.total);
+  stark_fri_state *s = nullptr;
+  ST_TRY(fri_commit_dev(ctx, cw0, n, offset, omega, ef, nq, transcript, transcript_len, false, &s));
+  int rc = STARK_OK;
+  u8 *d_proof = nullptr;
+  u64 *d_top = nullptr, *d_seed = nullptr;
+  rc = dev_alloc(ctx, (void **)&d_proof, L.total + 8 * (size_t)nq + 16);
+  if (rc == STARK_OK) rc = dev_alloc(ctx, (void **)&d_seed, 8);
+  if (rc == STARK_OK) {
+    d_top = reinterpret_cast<u64 *>(d_proof + ((L.total + 7) & ~(size_t)7));
+    k_transcript_challenge<<<1, 32, 0, ctx->stream>>>(s->d_tr, d_seed);  // fri.rs:272
+    const size_t sample_size = L.n_cw > 1 ? s->len[1] : s->len[0];       // fri.rs:266-270
+    if (nq) k_sample_indices<<<1, 256, 0, ctx->stream>>>(d_seed, sample_size, L.last_len, nq, d_top);
+    const size_t hdr_threads = L.last_len > R ? L.last_len : R;
+    k_proof_header<<<(u32)((hdr_threads + 255) / 256), 256, 0, ctx->stream>>>(d_proof, s->d_roots, R, s->cw[L.n_cw - 1],
+                                                                             L.last_len);
+    ctx->launches += 3;
+    for (u32 i = 0; i + 1 < L.n_cw && nq; i++) {
+      u32 d = 0;
+      for (size_t m = s->len[i]; m > 1; m >>= 1) d++;
+      const size_t threads = (size_t)nq * (3 * d - 1);
+      k_proof_round<<<(u32)((threads + 127) / 128), 128, 0, ctx->stream>>>(d_proof + L.round_off[i], s->cw[i], s->cw[i + 1],
+                                                                         s->len[i], s->trees[i]->nodes,
+                                                                         s->trees[i + 1]->nodes, d_top, nq, d);
+      ctx->launches++;
+    }
+    if (cudaGetLastError() != cudaSuccess) rc = stark_fail(ctx, STARK_ERR_CUDA, "kernel launch failed");
+  }
+  if (rc == STARK_OK && cudaMemcpyAsync(proof, d_proof, L.total, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+    rc = stark_fail(ctx, STARK_ERR_CUDA, "D2H copy failed");
+  if (rc == STARK_OK && top_indices && nq &&
+      cudaMemcpyAsync(top_indices, d_top, 8 * (size_t)nq, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+    rc = stark_fail(ctx, STARK_ERR_CUDA, "D2H copy failed");
+  dev_free(ctx, d_proof), dev_free(ctx, d_seed);
+  fri_state_free(s);
+  if (rc == STARK_OK) {
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = stark_fail(ctx, STARK_ERR_CUDA, "prove failed: %s", cudaGetErrorString(e));
+  }
+  return rc;
+}
+
+static int reduce_params(stark_ctx *ctx, uint64_t offset, uint64_t omega, u32 *off, u32 *om) {
+  // FiniteField::mul reduces with u128 % p (ff.rs:138-144), so unreduced offset / omega act as their residues
+  *off = ff::reduce64(offset), *om = ff::reduce64(omega);
+  (void)ctx;
+  return STARK_OK;
+}
+
+// ----------------------------------------------------------------------------------------------- C ABI
+
+extern "C" {
+
+int stark_fri_num_rounds(size_t domain_length, uint32_t ef, uint32_t nq, uint32_t *rounds) {
+  if (!rounds) return stark_fail(nullptr, STARK_ERR_ARG, "null argument");
+  return fri_check(nullptr, domain_length, ef, rounds, nq);
+}
+
+int stark_fri_fold_dev(stark_ctx *ctx, const stark_buf *codeword, size_t n, uint64_t alpha_raw, uint64_t offset,
+                       uint64_t omega, stark_buf *out) {
+  if (!ctx || !codeword || !out) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+  const size_t h = n / 2;
+  if (codeword->n < n || out->n < h) return stark_fail(ctx, STARK_ERR_ARG, "buffer too small");
+  if (h == 0) return STARK_OK;
+  u32 off, om;
+  reduce_params(ctx, offset, omega, &off, &om);
+  if (off == 0 || (om == 0 && h > 1)) return stark_fail(ctx, STARK_ERR_ARG, "no division by zero");  // ff.rs:182
+  const u32 g0 = om ? ff::inv(om) : 1u;
+  GeoTables G;
+  ST_TRY(geo_tables(ctx, g0, 1, h, &G));
+  u32 *d_alpha = nullptr;
+  ST_TRY(dev_alloc(ctx, (void **)&d_alpha, 4));
+  const u32 am = ff::to_mont(ff::reduce64(alpha_raw));
+  CU_TRY(ctx, cudaMemcpyAsync(d_alpha, &am, 4, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = fold_launch(ctx, codeword->ptr, out->ptr, h, 0, G, ff::to_mont(g0), d_alpha,
+                       ff::to_mont(ff::inv(ff::mul(2, off))));
+  dev_free(ctx, d_alpha);
+  return rc;
+}
+
+int stark_fri_fold(stark_ctx *ctx, const uint64_t *codeword, size_t n, uint64_t alpha_raw, uint64_t offset,
+                   uint64_t omega, uint64_t *out) {
+  if (!ctx || (n && !codeword) || (n / 2 && !out)) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+  stark_buf *in = nullptr, *o = nullptr;
+  ST_TRY(stark_buf_upload(ctx, codeword, n, &in));
+  int rc = stark_buf_alloc(ctx, n / 2, &o);
+  if (rc == STARK_OK) rc = stark_fri_fold_dev(ctx, in, n, alpha_raw, offset, omega, o);
+  if (rc == STARK_OK) rc = download_u64(ctx, o->ptr, n / 2, out);
+  stark_buf_free(in), stark_buf_free(o);
+  return rc;
+}
+
+int stark_fri_commit_dev(stark_ctx *ctx, const stark_buf *codeword, size_t n, uint64_t offset, uint64_t omega,
+                         uint32_t ef, uint32_t nq, const uint8_t *transcript, size_t transcript_len,
+                         stark_fri_state **out) {
+  if (!ctx || !codeword || !out) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+  if (codeword->n < n) return stark_fail(ctx, STARK_ERR_ARG, "buffer too small");
+  u32 off, om;
+  reduce_params(ctx, offset, omega, &off, &om);
+  return fri_commit_dev(ctx, codeword->ptr, n, off, om, ef, nq, transcript, transcript_len, true, out);
+}
+int stark_fri_commit(stark_ctx *ctx, const uint64_t *codeword, size_t n, uint64_t offset, uint64_t omega, uint32_t ef,
+                     uint32_t nq, const uint8_t *transcript, size_t transcript_len, stark_fri_state **out) {
+  if (!ctx || !codeword || !out) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+  u32 R;
+  ST_TRY(fri_check(ctx, n, ef, &R, nq));
+  stark_buf *in = nullptr;
+  ST_TRY(stark_buf_upload(ctx, codeword, n, &in));
+  int rc = stark_fri_commit_dev(ctx, in, n, offset, omega, ef, nq, transcript, transcript_len, out);
+  stark_buf_free(in);
+  return rc;
+}
+uint32_t stark_fri_rounds(const stark_fri_state *s) { return s ? s->rounds : 0; }
+int stark_fri_roots(stark_fri_state *s, uint8_t *out) {
+  if (!s || !out) return stark_fail(nullptr, STARK_ERR_ARG, "null argument");
+  if (!s->rounds) return STARK_OK;
+  CU_TRY(s->ctx, cudaMemcpyAsync(out, s->d_roots, 32 * (size_t)s->rounds, cudaMemcpyDeviceToHost, s->ctx->stream));
+  CU_TRY(s->ctx, cudaStreamSynchronize(s->ctx->stream));
+  return STARK_OK;
+}
+int stark_fri_alphas(stark_fri_state *s, uint64_t *out) {
+  if (!s || !out) return stark_fail(nullptr, STARK_ERR_ARG, "null argument");
+  if (s->rounds < 2) return STARK_OK;
+  CU_TRY(s->ctx, cudaMemcpyAsync(out, s->d_alpha_raw, 8 * (size_t)(s->rounds - 1), cudaMemcpyDeviceToHost, s->ctx->stream));
+  CU_TRY(s->ctx, cudaStreamSynchronize(s->ctx->stream));
+  return STARK_OK;
+}
+int stark_fri_codeword_len(const stark_fri_state *s, uint32_t round, size_t *len) {
+  if (!s || !len || round >= s->cw.size()) return stark_fail(nullptr, STARK_ERR_ARG, "round out of range");
+  *len = s->len[round];
+  return STARK_OK;
+}
+int stark_fri_codeword(stark_fri_state *s, uint32_t round, uint64_t *out) {
+  if (!s || !out || round >= s->cw.size()) return stark_fail(nullptr, STARK_ERR_ARG, "round out of range");
+  return download_u64(s->ctx, s->cw[round], s->len[round], out);
+}
+int stark_fri_open(stark_fri_state *s, uint32_t round, size_t index, uint8_t *out, size_t *n_hashes) {
+  if (!s || round >= s->trees.size()) return stark_fail(nullptr, STARK_ERR_ARG, "round out of range");
+  return stark_merkle_open(s->trees[round], index, out, n_hashes);
+}
+void stark_fri_free(stark_fri_state *s) { fri_state_free(s); }
+
+int stark_fri_sample_indices(const uint8_t *seed, size_t seed_len, size_t size, size_t reduced_size, size_t number,
+                             uint64_t *out) {
+  // host-side mirror of fri.rs:176-213 for callers that hold their own seed (tiny: `number` 36-byte hashes)
+  if ((!seed && seed_len) || (!out && number)) return stark_fail(nullptr, STARK_ERR_ARG, "null argument");
+  if (number > 2 * reduced_size) return stark_fail(nullptr, STARK_ERR_ARG, "not enough entropy in indices wrt last codeword");
+  if (number > reduced_size)
+    return stark_fail(nullptr, STARK_ERR_ARG, "cannot sample more indices than available in last codeword; requested: %zu, available: %zu", number, reduced_size);
+  std::vector<u8> msg(seed_len + 4);
+  for (size_t i = 0; i < seed_len; i++) msg[i] = seed[i];
+  size_t got = 0;
+  for (u32 counter = 0; got < number; counter++) {
+    for (int b = 0; b < 4; b++) msg[seed_len + b] = (u8)(counter >> (8 * b));
+    u8 h[32];
+    hs::from_bytes(msg.data(), msg.size(), h);
+    u64 v = 0;
+    for (int b = 24; b < 32; b++) v = (v << 8) | h[b];
+    const u64 idx = v % size, ri = idx % reduced_size;
+    bool seen = false;
+    for (size_t j = 0; j < got; j++)
+      if (out[j] % reduced_size == ri) seen = true;
+    if (!seen) out[got++] = idx;
+  }
+  return STARK_OK;
+}
+
+int stark_fri_proof_size(size_t domain_length, uint32_t ef, uint32_t nq, size_t *bytes) {
+  if (!bytes) return stark_fail(nullptr, STARK_ERR_ARG, "null argument");
+  u32 R;
+  ST_TRY(fri_check(nullptr, domain_length, ef, &R, nq));
+  ProofLayout L;
+  proof_layout(domain_length, R, nq, &L);
+  *bytes = L.total;
+  return STARK_OK;
+}
+
+int stark_fri_prove_dev(stark_ctx *ctx, const stark_buf *codeword, size_t n, size_t domain_length, uint64_t offset,
+                        uint64_t omega, uint32_t ef, uint32_t nq, const uint8_t *transcript, size_t transcript_len,
+                        uint8_t *proof, size_t proof_cap, size_t *proof_len, uint64_t *top_indices) {
+  if (!ctx || !codeword) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+  if (codeword->n < n) return stark_fail(ctx, STARK_ERR_ARG, "buffer too small");
+  u32 off, om;
+  reduce_params(ctx, offset, omega, &off, &om);
+  return fri_prove_dev(ctx, codeword->ptr, n, domain_length, off, om, ef, nq, transcript, transcript_len, proof,
+                       proof_cap, proof_len, top_indices);
+}
+int stark_fri_prove(stark_ctx *ctx, const uint64_t *codeword, size_t n, size_t domain_length, uint64_t offset,
+                    uint64_t omega, uint32_t ef, uint32_t nq, const uint8_t *transcript, size_t transcript_len,
+                    uint8_t *proof, size_t proof_cap, size_t *proof_len, uint64_t *top_indices) {
+  if (!ctx || (n && !codeword)) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+  if (n != domain_length)
+    return stark_fail(ctx, STARK_ERR_ARG, "initial codeword length does not match domain length");
+  stark_buf *in = nullptr;
+  ST_TRY(stark_buf_upload(ctx, codeword, n, &in));
+  int rc = stark_fri_prove_dev(ctx, in, n, domain_length, offset, omega, ef, nq, transcript, transcript_len, proof,
+                               proof_cap, proof_len, top_indices);
+  stark_buf_free(in);
+  return rc;
+}
+
+// BASELINE config 3: LDE of every column, one Merkle tree per column, FRI on column 0
+int stark_prove_trace_dev(stark_ctx *ctx, const stark_buf *cols, uint32_t n_cols, uint32_t log_n, uint32_t log_blowup,
+                          uint64_t offset, uint32_t nq, uint8_t *column_roots, uint8_t *proof, size_t proof_cap,
+                          size_t *proof_len) {
+  if (!ctx || !cols || n_cols == 0) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+  if (log_n + log_blowup > (u32)ff::TWO_ADICITY)
+    return stark_fail(ctx, STARK_ERR_ARG, "n > 2^23 not supported by this modulus");
+  if (offset == 0 || offset >= ff::P) return stark_fail(ctx, STARK_ERR_ARG, "offset must be a non-zero canonical element");
+  const size_t n = (size_t)1 << log_n, N = n << log_blowup;
+  if (cols->n < n * n_cols) return stark_fail(ctx, STARK_ERR_ARG, "buffer too small");
+  u32 *lde = nullptr;
+  u8 *d_roots = nullptr;
+  ST_TRY(dev_alloc(ctx, (void **)&lde, N * n_cols * 4));
+  int rc = lde_dev(ctx, cols->ptr, n_cols, log_n, log_blowup, (u32)offset, lde);
+  // commitments of columns 1.. (column 0's tree is built inside Fri::commit, fri.rs:118-127, and its root is
+  // the first proof object)
+  std::vector<stark_tree *> trees;
+  if (rc == STARK_OK && n_cols > 1) rc = dev_alloc(ctx, (void **)&d_roots, 32 * (size_t)n_cols);
+  for (u32 c = 1; c < n_cols && rc == STARK_OK; c++) {
+    stark_tree *t = nullptr;
+    rc = merkle_build_from_dev_values(ctx, lde + (size_t)c * N, N, 1, 1, 0, &t);
+    if (rc == STARK_OK) {
+      trees.push_back(t);
+      if (cudaMemcpyAsync(d_roots + 32 * (size_t)c, t->nodes + 32 * (2 * N - 2), 32, cudaMemcpyDeviceToDevice,
+                          ctx->stream) != cudaSuccess)
+        rc = stark_fail(ctx, STARK_ERR_CUDA, "D2D copy failed");
+    }
+  }
+  if (rc == STARK_OK && n_cols > 1 && column_roots &&
+      cudaMemcpyAsync(column_roots + 32, d_roots + 32, 32 * (size_t)(n_cols - 1), cudaMemcpyDeviceToHost, ctx->stream) !=
+          cudaSuccess)
+    rc = stark_fail(ctx, STARK_ERR_CUDA, "D2H copy failed");
+  const u32 omega = ff::pow(ff::GEN, (ff::P - 1) >> (log_n + log_blowup));  // prim_nth_root(N), ff.rs:215-223
+  if (rc == STARK_OK)
+    rc = fri_prove_dev(ctx, lde, N, N, (u32)offset, omega, 1u << log_blowup, nq, nullptr, 0, proof, proof_cap, proof_len,
+                       nullptr);
+  if (rc == STARK_OK && column_roots) memcpy(column_roots, proof + 1, 32);  // first object = root of column 0
+  for (stark_tree *t : trees) stark_merkle_free(t);
+  dev_free(ctx, lde), dev_free(ctx, d_roots);
+  return rc;
+}
+
+int stark_prove_trace(stark_ctx *ctx, const uint64_t *cols, uint32_t n_cols, uint32_t log_n, uint32_t log_blowup,
+                      uint64_t offset, uint32_t nq, uint8_t *column_roots, uint8_t *proof, size_t proof_cap,
+                      size_t *proof_len) {
+  if (!ctx || !cols) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+  if (log_n > (u32)ff::TWO_ADICITY) return stark_fail(ctx, STARK_ERR_ARG, "n > 2^23 not supported by this modulus");
+  stark_buf *in = nullptr;
+  ST_TRY(stark_buf_upload(ctx, cols, ((size_t)1 << log_n) * n_cols, &in));
+  int rc = stark_prove_trace_dev(ctx, in, n_cols, log_n, log_blowup, offset, nq, column_roots, proof, proof_cap, proof_len);
+  stark_buf_free(in);
+  return rc;
+}
+
+}  // extern "C"

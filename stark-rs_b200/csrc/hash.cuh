@@ -1,0 +1,190 @@
+// hash.cuh -- the stark-rs 32-byte hash (reference src/hash.rs:7-99) as integer-pipe code.
+//
+// One hash per thread.  The 32-byte state lives in 32 registers, one byte per register, and the HIGH 24
+// bits of each register are allowed to hold garbage: wrapping adds, multiplies and xors only ever
+// propagate information upwards, so the low 8 bits stay exact.  A byte is cleaned only where a right
+// shift needs it (the two rotations), and there the clean-up is free:
+//     rotl8(z, k) = ((z * 0x0101) >> (8 - k)) & 0xff      and   z * 0x0101 = PRMT(z: byte0, byte0, 0, 0)
+// i.e. one PRMT both masks the byte and duplicates it, one SHF finishes the rotate (bits >= 8 are garbage
+// again, which is fine).  Per mix_state: sbox 3 ops/byte (IMAD, PRMT, SHF), linear layer 6 ops/4 bytes
+// (LOP3), the serial neighbour add 1 IADD3/byte; the round-constant add is folded into the NEXT
+// consumer's IMAD / IADD3.  The byte chain s[i] += s[i+1] + s[i-1] (hash.rs:77-81) is inherently serial
+// (32 dependent adds); occupancy, not ILP, hides it.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define HS_HD __host__ __device__ __forceinline__
+#else
+#define HS_HD inline
+#endif
+
+namespace hs {
+typedef uint32_t u32;
+typedef uint8_t u8;
+
+// hash.rs:53
+#define HS_PRIMES \
+  { 2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37, 41, 43, 47, 53 }
+// hash.rs:96-99
+#define HS_RC                                                                                                 \
+  {                                                                                                           \
+    0x01, 0x02, 0x04, 0x08, 0x10, 0x20, 0x40, 0x80, 0x1b, 0x36, 0x6c, 0xd8, 0xab, 0x4d, 0x9a, 0x2f, 0x5e,     \
+        0xbc, 0x63, 0xc6, 0x97, 0x35, 0x6a, 0xd4, 0xb3, 0x7d, 0xfa, 0xef, 0xc5, 0x91, 0x39, 0x72              \
+  }
+
+HS_HD u32 prime_at(int i) {
+  constexpr u32 t[16] = HS_PRIMES;
+  return t[i & 15];
+}
+HS_HD u32 rc_at(int i) {
+  constexpr u32 t[32] = HS_RC;
+  return t[i];
+}
+
+// low byte of z duplicated into bytes 0 and 1, bytes 2-3 zero  (= (z & 0xff) * 0x0101)
+HS_HD u32 dup_byte(u32 z) {
+#if defined(__CUDA_ARCH__)
+  return __byte_perm(z, 0u, 0x4400);
+#else
+  return (z & 0xffu) * 0x0101u;
+#endif
+}
+// rotate_left (hash.rs:55-57) of the low byte; result exact in bits 0-7, garbage above
+HS_HD u32 rotl_lazy(u32 z, int k) { return dup_byte(z) >> (8 - k); }
+
+struct State {
+  u32 s[32];  // low 8 bits exact, high bits garbage; round constants possibly pending (see `pending`)
+};
+
+// hash.rs:10-12
+HS_HD void init(State &st) {
+#pragma unroll
+  for (int i = 0; i < 32; i++) st.s[i] = prime_at(i);
+}
+
+// mix_state (hash.rs:59-86) WITHOUT its final round-constant add (left pending for the next consumer).
+// If PENDING, the round constants of the previous mix are still owed and are folded into the sbox multiply:
+// sbox(x + rc) = rotl1(251 x + 251 rc) ^ 0x63.
+template <bool PENDING>
+HS_HD void mix_lazy(State &st) {
+  u32 *s = st.s;
+  // sbox (hash.rs:88-94), without the ^0x63 (it cancels or is re-applied in the linear layer below)
+#pragma unroll
+  for (int i = 0; i < 32; i++) {
+    const u32 c = PENDING ? (rc_at(i) * 251u) & 0xffu : 0u;
+    s[i] = rotl_lazy(s[i] * 251u + c, 1);
+  }
+  // linear layer (hash.rs:64-75): out = X ^ t[2,1,3,0], X = t0^t1^t2^t3.  With the pending ^0x63 on all four
+  // inputs X is unchanged and each output owes exactly one ^0x63.
+#pragma unroll
+  for (int g = 0; g < 8; g++) {
+    const u32 t0 = s[4 * g], t1 = s[4 * g + 1], t2 = s[4 * g + 2], t3 = s[4 * g + 3];
+    const u32 x = t0 ^ t1 ^ t2 ^ t3;
+    s[4 * g] = x ^ t2 ^ 0x63u;
+    s[4 * g + 1] = x ^ t1 ^ 0x63u;
+    s[4 * g + 2] = x ^ t3 ^ 0x63u;
+    s[4 * g + 3] = x ^ t0 ^ 0x63u;
+  }
+  // serial in-place neighbour add (hash.rs:77-81): prev is already updated, next is old; s[31] sees NEW s[0]
+  s[0] = s[0] + s[1] + s[31];
+#pragma unroll
+  for (int i = 1; i < 31; i++) s[i] = s[i] + s[i + 1] + s[i - 1];
+  s[31] = s[31] + s[0] + s[30];
+}
+
+// absorb one message byte at position i (hash.rs:15-20); no round constants may be pending
+HS_HD void absorb_byte(State &st, int i, u32 b) {
+  u32 *s = st.s;
+  const u32 v = rotl_lazy(s[i] + b, 3);
+  s[i] = v;
+  s[(i + 7) & 31] ^= v;
+}
+
+HS_HD void settle(State &st) {
+#pragma unroll
+  for (int i = 0; i < 32; i++) st.s[i] += rc_at(i);
+}
+
+// 8 finalisation mixes (hash.rs:25-27) + settle.  PENDING as for mix_lazy.
+template <bool PENDING>
+HS_HD void finalize(State &st) {
+  mix_lazy<PENDING>(st);
+#pragma unroll 1
+  for (int k = 0; k < 7; k++) mix_lazy<true>(st);
+  settle(st);
+}
+
+// pack the 32 state bytes into 8 little-endian words
+HS_HD void pack_words(const State &st, u32 *w) {
+#pragma unroll
+  for (int g = 0; g < 8; g++) {
+#if defined(__CUDA_ARCH__)
+    const u32 lo = __byte_perm(st.s[4 * g], st.s[4 * g + 1], 0x0040);
+    const u32 hi = __byte_perm(st.s[4 * g + 2], st.s[4 * g + 3], 0x0040);
+    w[g] = __byte_perm(lo, hi, 0x5410);
+#else
+    w[g] = (st.s[4 * g] & 0xff) | ((st.s[4 * g + 1] & 0xff) << 8) | ((st.s[4 * g + 2] & 0xff) << 16) |
+           ((st.s[4 * g + 3] & 0xff) << 24);
+#endif
+  }
+}
+
+// absorb a full 32-byte chunk given as 8 LE words, then mix (hash.rs:14-23).  PENDING: constants owed on entry.
+template <bool PENDING>
+HS_HD void absorb_words_mix(State &st, const u32 *w) {
+  if (PENDING) settle(st);
+#pragma unroll
+  for (int i = 0; i < 32; i++) absorb_byte(st, i, w[i >> 2] >> (8 * (i & 3)));
+  mix_lazy<false>(st);
+}
+
+// Hash::combine (hash.rs:41-46): 64-byte message = two chunks, then 8 mixes
+HS_HD void combine(const u32 *left, const u32 *right, u32 *out) {
+  State st;
+  init(st);
+  absorb_words_mix<false>(st, left);
+  absorb_words_mix<true>(st, right);
+  finalize<true>(st);
+  pack_words(st, out);
+}
+
+// Hash::from_field_elements(&[v]) (hash.rs:32-35) for a canonical value (< 2^32): 8-byte LE message
+HS_HD void leaf1(u32 v, u32 *out) {
+  State st;
+  init(st);
+#pragma unroll
+  for (int i = 0; i < 8; i++) absorb_byte(st, i, i < 4 ? (v >> (8 * i)) : 0u);
+  mix_lazy<false>(st);
+  finalize<true>(st);
+  pack_words(st, out);
+}
+
+// generic Hash::from_bytes (hash.rs:7-30) -- byte-serial loop form, used for short host/transcript messages
+// and for ragged message lengths on the device.
+HS_HD void from_bytes(const u8 *msg, size_t n, u8 *out) {
+  State st;
+  init(st);
+  bool pending = false;
+  for (size_t off = 0; off < n; off += 32) {
+    const int len = (n - off) < 32 ? (int)(n - off) : 32;
+    if (pending) settle(st);
+#pragma unroll 1
+    for (int i = 0; i < len; i++) {
+      // runtime-indexed variant of absorb_byte (the State lives in local memory here; not the hot path)
+      u32 v = rotl_lazy(st.s[i] + msg[off + i], 3);
+      st.s[i] = v;
+      st.s[(i + 7) & 31] ^= v;
+    }
+    mix_lazy<false>(st);
+    pending = true;
+  }
+  if (pending)
+    finalize<true>(st);
+  else
+    finalize<false>(st);
+  for (int i = 0; i < 32; i++) out[i] = (u8)st.s[i];
+}
+
+}  // namespace hs

@@ -1,0 +1,357 @@
+// merkle.cu -- leaf hashing and Merkle commitment kernels (reference src/hash.rs:7-46, src/merkle.rs:11-80,
+// and the leaf rule of src/fri.rs:118-121).
+//
+// Tree storage: ONE device array of (2n-1) hashes, level l (n >> l nodes) at hash offset 2n - 2(n >> l):
+// level 0 = leaves ... last = root.  That is MerkleTree.nodes (merkle.rs:18-29) flattened, so open()
+// (merkle.rs:67-80) is a gather and nothing is ever rebuilt (the reference rebuilds every tree in the
+// query phase, fri.rs:288-298).
+//
+// Kernels: one hash per thread (hash.cuh).  Levels with > 1024 parents get one launch each; the last <= 11
+// levels are climbed by a single CTA through shared memory.  All of this is integer-pipe bound
+// (~1.9k thread-instructions per node hash against 96 bytes of traffic).
+#include "common.cuh"
+#include "hash.cuh"
+#include "merkle.h"
+
+using hs::State;
+
+__device__ __forceinline__ void load_hash(const u8 *p, u32 *w) {
+  const uint4 a = reinterpret_cast<const uint4 *>(p)[0], b = reinterpret_cast<const uint4 *>(p)[1];
+  w[0] = a.x, w[1] = a.y, w[2] = a.z, w[3] = a.w, w[4] = b.x, w[5] = b.y, w[6] = b.z, w[7] = b.w;
+}
+__device__ __forceinline__ void store_hash(u8 *p, const u32 *w) {
+  reinterpret_cast<uint4 *>(p)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+  reinterpret_cast<uint4 *>(p)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+// leaf i = Hash::from_field_elements(&[vals[i]])  (fri.rs:118-121, hash.rs:32-35)
+__global__ void __launch_bounds__(256) k_leaf_hash1(const u32 *__restrict__ vals, size_t n, u8 *__restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u32 w[8];
+  hs::leaf1(vals[i], w);
+  store_hash(out + 32 * i, w);
+}
+
+// leaf i = Hash::from_field_elements(&[vals[i*row_stride + c*col_stride] for c < width])  (hash.rs:32-35)
+__global__ void __launch_bounds__(256) k_leaf_hashw(const u32 *__restrict__ vals, size_t n, u32 width, size_t row_stride,
+                                                    size_t col_stride, u8 *__restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  State st;
+  hs::init(st);
+  bool pending = false;
+  const u32 *base = vals + i * row_stride;
+  for (u32 c0 = 0; c0 < width; c0 += 4) {  // one 32-byte chunk = 4 values (LE u64 each, high word zero)
+    const int nv = (width - c0) < 4 ? (int)(width - c0) : 4;
+    u32 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) v[k] = k < nv ? base[(size_t)(c0 + k) * col_stride] : 0u;
+    if (pending) hs::settle(st);
+#pragma unroll
+    for (int b = 0; b < 32; b++)
+      if (b < 8 * nv) hs::absorb_byte(st, b, (b & 4) ? 0u : v[b >> 3] >> (8 * (b & 3)));
+    hs::mix_lazy<false>(st);
+    pending = true;
+  }
+  if (pending)
+    hs::finalize<true>(st);
+  else
+    hs::finalize<false>(st);
+  u32 w[8];
+  hs::pack_words(st, w);
+  store_hash(out + 32 * i, w);
+}
+
+// generic Hash::from_bytes of n messages of msg_len bytes (hash.rs:7-30); state stays in registers
+__global__ void __launch_bounds__(128) k_hash_bytes(const u8 *__restrict__ msgs, size_t n, size_t msg_len,
+                                                    u8 *__restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u8 *m = msgs + i * msg_len;
+  State st;
+  hs::init(st);
+  bool pending = false;
+  for (size_t off = 0; off < msg_len; off += 32) {
+    const int len = (msg_len - off) < 32 ? (int)(msg_len - off) : 32;
+    if (pending) hs::settle(st);
+#pragma unroll
+    for (int b = 0; b < 32; b++)
+      if (b < len) hs::absorb_byte(st, b, m[off + b]);
+    hs::mix_lazy<false>(st);
+    pending = true;
+  }
+  if (pending)
+    hs::finalize<true>(st);
+  else
+    hs::finalize<false>(st);
+  u32 w[8];
+  hs::pack_words(st, w);
+  u8 *o = out + 32 * i;
+#pragma unroll
+  for (int g = 0; g < 8; g++) reinterpret_cast<u32 *>(o)[g] = w[g];
+}
+
+// one tree level: parent i = Hash::combine(child 2i, child 2i+1)  (merkle.rs:21-27)
+__global__ void __launch_bounds__(256) k_merkle_level(const u8 *__restrict__ in, u8 *__restrict__ out, size_t n_out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  u32 l[8], r[8], w[8];
+  load_hash(in + 64 * i, l);
+  load_hash(in + 64 * i + 32, r);
+  hs::combine(l, r, w);
+  store_hash(out + 32 * i, w);
+}
+
+// the last levels: one CTA climbs from a level with m <= 2048 nodes to the root through shared memory,
+// writing every level to the tree array.  nodes = tree base, n = leaf count, level = input level.
+__global__ void __launch_bounds__(1024) k_merkle_top(u8 *nodes, size_t n, u32 level) {
+  __shared__ __align__(16) u8 sm[1024 * 32];
+  size_t m = n >> level;
+  const u32 t = threadIdx.x;
+  bool first = true;
+  while (m > 1) {
+    const size_t half = m >> 1;
+    u32 w[8];
+    if (t < half) {
+      u32 l[8], r[8];
+      if (first) {
+        const u8 *src = nodes + 32 * (2 * n - 2 * m);
+        load_hash(src + 64 * t, l);
+        load_hash(src + 64 * t + 32, r);
+      } else {
+        load_hash(sm + 64 * t, l);
+        load_hash(sm + 64 * t + 32, r);
+      }
+      hs::combine(l, r, w);
+    }
+    __syncthreads();
+    if (t < half) {
+      store_hash(sm + 32 * t, w);
+      store_hash(nodes + 32 * (2 * n - 2 * half) + 32 * t, w);
+    }
+    __syncthreads();
+    first = false;
+    m = half;
+  }
+}
+
+// gather authentication paths (merkle.rs:67-80): out[(q*depth + l)*32 ..] = nodes[level l][(idx[q] >> l) ^ 1]
+__global__ void k_merkle_open(const u8 *__restrict__ nodes, size_t n, u32 depth, const u64 *__restrict__ idx, u32 n_idx,
+                              u8 *__restrict__ out) {
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 16-byte half hash
+  const u32 item = t >> 1, half = t & 1;
+  if (item >= n_idx * depth) return;
+  const u32 q = item / depth, l = item % depth;
+  const size_t sib = (size_t)(idx[q] >> l) ^ 1;
+  const uint4 *src = reinterpret_cast<const uint4 *>(nodes + 32 * ((2 * n - 2 * (n >> l)) + sib));
+  reinterpret_cast<uint4 *>(out + 32 * (size_t)item)[half] = src[half];
+}
+
+// ------------------------------------------------------------------------------------------ device API
+
+int merkle_check_n(stark_ctx *ctx, size_t n) {
+  if (n == 0) return stark_fail(ctx, STARK_ERR_ARG, "Cannot create tree from empty leaves");     // merkle.rs:12
+  if (n & (n - 1)) return stark_fail(ctx, STARK_ERR_ARG, "Number of leaves must be power of 2");  // merkle.rs:13-16
+  return STARK_OK;
+}
+
+int merkle_leaves_dev(stark_ctx *ctx, const u32 *vals, size_t n, u32 width, size_t row_stride, size_t col_stride,
+                      u8 *out) {
+  if (n == 0) return STARK_OK;
+  const u32 blocks = (u32)((n + 255) / 256);
+  if (width == 1)
+    k_leaf_hash1<<<blocks, 256, 0, ctx->stream>>>(vals, n, out);
+  else
+    k_leaf_hashw<<<blocks, 256, 0, ctx->stream>>>(vals, n, width, row_stride, col_stride, out);
+  KERNEL_CHECK(ctx);
+  return STARK_OK;
+}
+
+// nodes[0 .. n) already holds the leaves; fill the upper levels
+int merkle_climb_dev(stark_ctx *ctx, u8 *nodes, size_t n) {
+  u32 level = 0;
+  size_t m = n;
+  while (m > 2048) {
+    const size_t half = m >> 1;
+    k_merkle_level<<<(u32)((half + 255) / 256), 256, 0, ctx->stream>>>(nodes + 32 * (2 * n - 2 * m),
+                                                                       nodes + 32 * (2 * n - 2 * half), half);
+    KERNEL_CHECK(ctx);
+    m = half;
+    level++;
+  }
+  if (m > 1) {
+    k_merkle_top<<<1, 1024, 0, ctx->stream>>>(nodes, n, level);
+    KERNEL_CHECK(ctx);
+  }
+  return STARK_OK;
+}
+
+int merkle_tree_alloc(stark_ctx *ctx, size_t n, stark_tree **out) {
+  ST_TRY(merkle_check_n(ctx, n));
+  stark_tree *t = new stark_tree();
+  t->ctx = ctx, t->n = n, t->levels = 1;
+  for (size_t m = n; m > 1; m >>= 1) t->levels++;
+  t->nodes = nullptr;
+  int rc = dev_alloc(ctx, (void **)&t->nodes, (2 * n - 1) * 32);
+  if (rc != STARK_OK) {
+    delete t;
+    return rc;
+  }
+  *out = t;
+  return STARK_OK;
+}
+
+int merkle_open_dev(stark_ctx *ctx, const u8 *nodes, size_t n, const u64 *idx_dev, u32 n_idx, u8 *out_dev) {
+  u32 depth = 0;
+  for (size_t m = n; m > 1; m >>= 1) depth++;
+  if (depth == 0 || n_idx == 0) return STARK_OK;
+  const u32 threads = n_idx * depth * 2;
+  k_merkle_open<<<(threads + 127) / 128, 128, 0, ctx->stream>>>(nodes, n, depth, idx_dev, n_idx, out_dev);
+  KERNEL_CHECK(ctx);
+  return STARK_OK;
+}
+
+// ----------------------------------------------------------------------------------------------- C ABI
+
+extern "C" {
+
+int stark_hash_bytes(stark_ctx *ctx, const uint8_t *msgs, size_t n_msgs, size_t msg_len, uint8_t *out) {
+  if (!ctx || (!msgs && n_msgs * msg_len) || !out) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+  if (n_msgs == 0) return STARK_OK;
+  u8 *d_in = nullptr, *d_out = nullptr;
+  ST_TRY(dev_alloc(ctx, (void **)&d_in, n_msgs * msg_len));
+  ST_TRY(dev_alloc(ctx, (void **)&d_out, n_msgs * 32));
+  if (msg_len) CU_TRY(ctx, cudaMemcpyAsync(d_in, msgs, n_msgs * msg_len, cudaMemcpyHostToDevice, ctx->stream));
+  k_hash_bytes<<<(u32)((n_msgs + 127) / 128), 128, 0, ctx->stream>>>(d_in, n_msgs, msg_len, d_out);
+  KERNEL_CHECK(ctx);
+  CU_TRY(ctx, cudaMemcpyAsync(out, d_out, n_msgs * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  dev_free(ctx, d_in), dev_free(ctx, d_out);
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return STARK_OK;
+}
+
+int stark_hash_leaves(stark_ctx *ctx, const uint64_t *vals, size_t n_leaves, uint32_t width, uint8_t *out) {
+  if (!ctx || !out || (!vals && n_leaves)) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+  if (n_leaves == 0) return STARK_OK;
+  stark_buf *b = nullptr;
+  ST_TRY(stark_buf_upload(ctx, vals, n_leaves * (size_t)width, &b));
+  u8 *d_out = nullptr;
+  int rc = dev_alloc(ctx, (void **)&d_out, n_leaves * 32);
+  if (rc == STARK_OK) rc = merkle_leaves_dev(ctx, (const u32 *)stark_buf_ptr(b), n_leaves, width, width, 1, d_out);
+  if (rc == STARK_OK && cudaMemcpyAsync(out, d_out, n_leaves * 32, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+    rc = stark_fail(ctx, STARK_ERR_CUDA, "D2H copy failed");
+  dev_free(ctx, d_out);
+  stark_buf_free(b);
+  if (rc == STARK_OK) CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return rc;
+}
+
+int stark_merkle_build(stark_ctx *ctx, const uint8_t *leaves, size_t n, stark_tree **out) {
+  if (!ctx || !out) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+  stark_tree *t = nullptr;
+  ST_TRY(merkle_tree_alloc(ctx, n, &t));
+  int rc = STARK_OK;
+  if (cudaMemcpyAsync(t->nodes, leaves, n * 32, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+    rc = stark_fail(ctx, STARK_ERR_CUDA, "H2D copy failed");
+  if (rc == STARK_OK) rc = merkle_climb_dev(ctx, t->nodes, n);
+  if (rc != STARK_OK) {
+    stark_merkle_free(t);
+    return rc;
+  }
+  *out = t;
+  return STARK_OK;
+}
+
+}  // extern "C"
+int merkle_build_from_dev_values(stark_ctx *ctx, const u32 *vals, size_t n, u32 width, size_t row_stride,
+                                 size_t col_stride, stark_tree **out) {
+  stark_tree *t = nullptr;
+  ST_TRY(merkle_tree_alloc(ctx, n, &t));
+  int rc = merkle_leaves_dev(ctx, vals, n, width, row_stride, col_stride, t->nodes);
+  if (rc == STARK_OK) rc = merkle_climb_dev(ctx, t->nodes, n);
+  if (rc != STARK_OK) {
+    stark_merkle_free(t);
+    return rc;
+  }
+  *out = t;
+  return STARK_OK;
+}
+
+extern "C" {
+int stark_merkle_build_from_values(stark_ctx *ctx, const uint64_t *vals, size_t n_leaves, uint32_t width,
+                                   stark_tree **out) {
+  if (!ctx || !out || width == 0) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+  ST_TRY(merkle_check_n(ctx, n_leaves));
+  stark_buf *b = nullptr;
+  ST_TRY(stark_buf_upload(ctx, vals, n_leaves * (size_t)width, &b));
+  int rc = merkle_build_from_dev_values(ctx, (const u32 *)stark_buf_ptr(b), n_leaves, width, width, 1, out);
+  stark_buf_free(b);
+  return rc;
+}
+
+int stark_merkle_build_from_buf(stark_ctx *ctx, const stark_buf *vals, size_t n_leaves, uint32_t width,
+                                stark_tree **out) {
+  if (!ctx || !out || !vals || width == 0) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+  ST_TRY(merkle_check_n(ctx, n_leaves));
+  if (stark_buf_len(vals) < n_leaves * (size_t)width) return stark_fail(ctx, STARK_ERR_ARG, "buffer too small");
+  // column-major [width][n_leaves]
+  return merkle_build_from_dev_values(ctx, (const u32 *)stark_buf_ptr(vals), n_leaves, width, 1, n_leaves, out);
+}
+
+int stark_merkle_commit(stark_ctx *ctx, const uint8_t *leaves, size_t n, uint8_t root[32]) {
+  stark_tree *t = nullptr;
+  ST_TRY(stark_merkle_build(ctx, leaves, n, &t));
+  int rc = stark_merkle_root(t, root);
+  stark_merkle_free(t);
+  return rc;
+}
+
+int stark_merkle_root(stark_tree *t, uint8_t root[32]) {
+  if (!t || !root) return stark_fail(nullptr, STARK_ERR_ARG, "null argument");
+  stark_ctx *ctx = t->ctx;
+  CU_TRY(ctx, cudaMemcpyAsync(root, t->nodes + 32 * (2 * t->n - 2), 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return STARK_OK;
+}
+
+size_t stark_merkle_num_leaves(const stark_tree *t) { return t ? t->n : 0; }
+uint32_t stark_merkle_num_levels(const stark_tree *t) { return t ? t->levels : 0; }
+
+int stark_merkle_level(stark_tree *t, uint32_t level, uint8_t *out) {
+  if (!t || !out) return stark_fail(nullptr, STARK_ERR_ARG, "null argument");
+  stark_ctx *ctx = t->ctx;
+  if (level >= t->levels) return stark_fail(ctx, STARK_ERR_ARG, "level out of range");
+  const size_t m = t->n >> level;
+  CU_TRY(ctx, cudaMemcpyAsync(out, t->nodes + 32 * (2 * t->n - 2 * m), 32 * m, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return STARK_OK;
+}
+
+int stark_merkle_open(stark_tree *t, size_t index, uint8_t *out, size_t *n_hashes) {
+  if (!t || !out) return stark_fail(nullptr, STARK_ERR_ARG, "null argument");
+  stark_ctx *ctx = t->ctx;
+  if (index >= t->n) return stark_fail(ctx, STARK_ERR_ARG, "Index out of bounds");  // merkle.rs:68
+  const u32 depth = t->levels - 1;
+  if (n_hashes) *n_hashes = depth;
+  if (depth == 0) return STARK_OK;
+  u64 *d_idx = nullptr;
+  u8 *d_out = nullptr;
+  ST_TRY(dev_alloc(ctx, (void **)&d_idx, 8));
+  ST_TRY(dev_alloc(ctx, (void **)&d_out, 32 * depth));
+  u64 idx = index;
+  CU_TRY(ctx, cudaMemcpyAsync(d_idx, &idx, 8, cudaMemcpyHostToDevice, ctx->stream));
+  ST_TRY(merkle_open_dev(ctx, t->nodes, t->n, d_idx, 1, d_out));
+  CU_TRY(ctx, cudaMemcpyAsync(out, d_out, 32 * depth, cudaMemcpyDeviceToHost, ctx->stream));
+  dev_free(ctx, d_idx), dev_free(ctx, d_out);
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return STARK_OK;
+}
+
+void stark_merkle_free(stark_tree *t) {
+  if (!t) return;
+  if (t->nodes) dev_free(t->ctx, t->nodes);
+  delete t;
+}
+
+}  // extern "C"

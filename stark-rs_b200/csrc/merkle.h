@@ -1,0 +1,31 @@
+// merkle.h -- internal handle layouts and device-pointer entry points shared by the .cu files.
+#pragma once
+#include "common.cuh"
+
+struct stark_buf {
+  stark_ctx *ctx;
+  u32 *ptr;
+  size_t n;
+  bool owns;
+};
+
+struct stark_tree {
+  stark_ctx *ctx;
+  size_t n;      // leaves
+  u32 levels;    // nodes.len() of merkle.rs:18-29 = log2(n) + 1
+  u8 *nodes;     // device, (2n-1) hashes, level l at hash offset 2n - 2(n >> l)
+};
+
+int merkle_check_n(stark_ctx *ctx, size_t n);
+int merkle_tree_alloc(stark_ctx *ctx, size_t n, stark_tree **out);
+int merkle_leaves_dev(stark_ctx *ctx, const u32 *vals, size_t n, u32 width, size_t row_stride, size_t col_stride,
+                      u8 *out);
+int merkle_climb_dev(stark_ctx *ctx, u8 *nodes, size_t n);
+int merkle_build_from_dev_values(stark_ctx *ctx, const u32 *vals, size_t n, u32 width, size_t row_stride,
+                                 size_t col_stride, stark_tree **out);
+int merkle_open_dev(stark_ctx *ctx, const u8 *nodes, size_t n, const u64 *idx_dev, u32 n_idx, u8 *out_dev);
+
+// poly.cu / api.cu helpers
+int upload_u64(stark_ctx *ctx, const uint64_t *host, size_t n, u32 *dst);     // H2D + canonical check + narrow
+int download_u64(stark_ctx *ctx, const u32 *src, size_t n, uint64_t *host);   // widen + D2H (synchronises)
+int lde_dev(stark_ctx *ctx, const u32 *cols, u32 n_cols, u32 log_n, u32 log_blowup, u32 offset, u32 *out);

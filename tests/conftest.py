@@ -17,3 +17,19 @@ def oracle():
     import oracle as O
     O.build()
     return O
+
+
+@pytest.fixture(scope="session")
+def ctx():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import stark_rs_b200 as S
+    c = S.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="session")
+def S():
+    import stark_rs_b200 as S
+    return S

@@ -1,0 +1,164 @@
+"""GPU parity: FRI fold / commit / prove (fri.rs) + Fiat-Shamir + proof bytes through the C ABI vs the oracle."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+P = 998244353
+G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "survey_vectors.json")))
+
+
+def rf(seed, n):
+    return np.random.default_rng(seed).integers(0, P, n, dtype=np.uint64)
+
+
+@pytest.mark.parametrize("n", [2, 4, 8, 16, 64, 512, 2048])
+def test_fold_vs_reference_algorithm(ctx, oracle, n):
+    """fri.rs:57-91 with per-element exp + 2 xgcd divisions"""
+    w = oracle.ff_prim_nth_root(n)
+    cw = rf(n, n)
+    for alpha in (0, 1, P - 1, P, 15764728482632548394, (1 << 64) - 1):     # unreduced challenges, fiat_shamir.rs:21-24
+        for offset in (3, 7):
+            assert np.array_equal(ctx.fri_fold(cw, alpha, offset, w), oracle.fri_fold(cw, alpha, offset, w)), (n, alpha)
+
+
+@pytest.mark.parametrize("log_n", [13, 16, 20, 22, 23])
+def test_fold_large_vs_closed_form(ctx, oracle, log_n):
+    n = 1 << log_n
+    w = oracle.ff_prim_nth_root(n)
+    cw = rf(log_n, n)
+    alpha = 0xDEADBEEFCAFEBABE
+    assert np.array_equal(ctx.fri_fold(cw, alpha, 3, w), oracle.fast_fri_fold(cw, alpha, 3, w))
+
+
+def test_fold_degenerate_domain(ctx, oracle, S):
+    """Fri::new never checks omega's order (fri.rs:30-55): the fold is a pure function of its inputs"""
+    cw = rf(1, 256)
+    for omega in (1, 5, oracle.ff_prim_nth_root(8)):
+        assert np.array_equal(ctx.fri_fold(cw, 99, 3, omega), oracle.fri_fold(cw, 99, 3, omega))
+    with pytest.raises(S.StarkPanic, match="no division by zero"):          # ff.rs:182 via fri.rs:75
+        ctx.fri_fold(cw, 99, 0, 5)
+    big = rf(2, 1 << 24)                                                    # > 2^23: throughput-only domain (SURVEY 8d cfg 5)
+    w23 = oracle.ff_prim_nth_root(1 << 23)
+    assert np.array_equal(ctx.fri_fold(big, 7, 3, w23), oracle.fast_fri_fold(big, 7, 3, w23))
+
+
+def _statement(O, n, offset, coeffs):
+    w = O.ff_prim_nth_root(n)
+    dom = [O.ff_mul(offset, O.ff_exp(w, i)) for i in range(n)]
+    return w, O.poly_eval_domain(coeffs, dom)
+
+
+@pytest.mark.parametrize("case", G["fri_proofs"], ids=lambda c: "n%d" % c["n"])
+def test_prove_reference_statements(ctx, oracle, case):
+    """the four statements of fri.rs:532-693: identical proof bytes, and Fri::verify accepts them"""
+    n, off, ef, nq = case["n"], case["offset"], case["ef"], case["nq"]
+    w, cw = _statement(oracle, n, off, case["coeffs"])
+    proof, top = ctx.fri_prove(cw, off, w, ef, nq)
+    ref = oracle.fri_prove(cw, w, off, ef, nq)
+    assert proof == ref["proof"]
+    assert top == ref["top_indices"] == case["top"]
+    assert hashlib.sha256(proof).hexdigest() == case["sha256"] and len(proof) == case["bytes"]
+    ok, why = oracle.fri_verify(proof, w, off, n, ef, nq)
+    assert ok, why
+
+
+@pytest.mark.parametrize("log_n,ef,nq", [(5, 4, 2), (6, 4, 3), (8, 8, 5), (10, 4, 8), (12, 4, 16), (14, 4, 32), (16, 16, 20)])
+def test_commit_and_prove_random_low_degree(ctx, oracle, log_n, ef, nq):
+    n = 1 << log_n
+    w = oracle.ff_prim_nth_root(n)
+    coeffs = rf(log_n, n // ef)
+    cw = oracle.fast_eval_coset(coeffs, 3, log_n)
+    ref = oracle.fri_prove(cw, w, 3, ef, nq)
+    st = ctx.fri_commit(cw, 3, w, ef, nq)                                   # fri.rs:105-156
+    assert st.rounds == ref["rounds"]
+    assert st.alphas() == ref["alphas"]                                     # raw u64 challenges
+    roots = st.roots()
+    for r in range(st.rounds):
+        assert roots[r].tobytes() == ref["proof"][33 * r + 1: 33 * r + 33]
+    a0 = ref["alphas"][0]
+    assert np.array_equal(st.codeword(1), oracle.fast_fri_fold(cw, a0, 3, w))
+    assert np.array_equal(st.open(0, 5), oracle.merkle_open(oracle.hash_leaves(cw), 5))
+    proof, top = ctx.fri_prove(cw, 3, w, ef, nq)                            # fri.rs:250-311 + stream.rs:35-64
+    assert proof == ref["proof"] and top == ref["top_indices"]
+    ok, why = oracle.fri_verify(proof, w, 3, n, ef, nq)
+    assert ok, why
+
+
+def test_prove_non_low_degree_and_transcript_prefix(ctx, oracle):
+    n, ef, nq = 256, 4, 8
+    w = oracle.ff_prim_nth_root(n)
+    cw = rf(9, n)                                                           # random codeword: still must match byte for byte
+    proof, _ = ctx.fri_prove(cw, 3, w, ef, nq)
+    assert proof == oracle.fri_prove(cw, w, 3, ef, nq)["proof"]
+    assert not oracle.fri_verify(proof, w, 3, n, ef, nq)[0]
+    # a transcript that already holds data (FiatShamir::absorb before prove): roots must differ from the empty one
+    for prefix in (b"x", b"0123456789abcdef0123456789abcdef", bytes(range(45))):
+        st = ctx.fri_commit(cw, 3, w, ef, nq, transcript=prefix)
+        roots = st.roots()
+        tr = prefix + roots[0].tobytes()
+        assert st.alphas()[0] == oracle.fs_challenge(tr)                    # fiat_shamir.rs:19-25
+        tr += roots[1].tobytes()
+        assert st.alphas()[1] == oracle.fs_challenge(tr)
+
+
+def test_prove_edge_parameters(ctx, oracle, S):
+    w = oracle.ff_prim_nth_root(16)
+    cw = rf(3, 16)
+    for ef, nq in [(4, 1), (4, 2), (4, 3), (8, 2), (16, 2), (4, 4)]:       # includes num_rounds 0 and 1
+        ref = oracle.fri_prove(cw, w, 3, ef, nq)
+        proof, top = ctx.fri_prove(cw, 3, w, ef, nq)
+        assert proof == ref["proof"] and top == ref["top_indices"], (ef, nq)
+    with pytest.raises(S.StarkPanic, match="initial codeword length does not match domain length"):   # fri.rs:256-260
+        ctx.fri_prove(cw, 3, w, 4, 2, domain_length=32)
+    with pytest.raises(S.StarkPanic, match="Expansion factor must be at least 4"):
+        ctx.fri_prove(cw, 3, w, 2, 2)
+    with pytest.raises(S.StarkPanic, match="cannot sample more indices|not enough entropy"):          # fri.rs:183-192
+        ctx.fri_prove(cw, 3, w, 4, 40)
+
+
+def test_prove_full_size_2_22(ctx, oracle):
+    """BASELINE config 3 size: N = 2^22, ef 4, 32 queries, 15 rounds.  The oracle's Fri::verify must accept the
+    GPU proof (any wrong fold / index / transcript / path order fails it) and round 0 is cross-checked against
+    values recomputed on the CPU."""
+    log_n = 22
+    n = 1 << log_n
+    w = oracle.ff_prim_nth_root(n)
+    assert w == 267099868
+    coeffs = rf(22, n // 4)
+    cw = oracle.fast_eval_coset(coeffs, 3, log_n)
+    proof, top = ctx.fri_prove(cw, 3, w, 4, 32)
+    assert len(proof) == ctx_size(n) and len(set(t % 256 for t in top)) == 32
+    ok, why = oracle.fri_verify(proof, w, 3, n, 4, 32)
+    assert ok, why
+    alpha0 = oracle.fs_challenge(proof[1:33])
+    fold1 = oracle.fast_fri_fold(cw, alpha0, 3, w)
+    # first revealed triple of round 0: (cw[a], cw[a + n/2], fold1[a]) with a = top[0] % (n/2)
+    base = 33 * 15 + 9 + 8 * 256
+    a = top[0] % (n // 2)
+    trip = np.frombuffer(proof[base + 9: base + 33], dtype="<u8")
+    assert list(trip) == [int(cw[a]), int(cw[a + n // 2]), int(fold1[a])]
+
+
+def ctx_size(n):
+    import stark_rs_b200 as S
+    return S.fri_proof_size(n, 4, 32)
+
+
+@pytest.mark.parametrize("log_n,n_cols", [(6, 1), (8, 3), (12, 2)])
+def test_prove_trace_pipeline(ctx, oracle, log_n, n_cols):
+    """BASELINE config 3 pipeline at oracle-checkable sizes: LDE (b=4, offset 3) + per-column Merkle + FRI"""
+    cols = rf(log_n, n_cols << log_n).reshape(n_cols, -1)
+    nq = 4 if log_n < 10 else 32
+    roots, proof = ctx.prove_trace(cols, 2, 3, nq)
+    N = 4 << log_n
+    w = oracle.ff_prim_nth_root(N)
+    for c in range(n_cols):
+        lde = oracle.fast_lde(cols[c], log_n, 2, 3)
+        assert roots[c].tobytes() == oracle.merkle_commit(oracle.hash_leaves(lde))
+        if c == 0:
+            assert proof == oracle.fri_prove(lde, w, 3, 4, nq)["proof"]
+    assert oracle.fri_verify(proof, w, 3, N, 4, nq)[0]
