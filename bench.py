@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json metric: "prove time and NTT/LDE field elems/s at 2^20-row trace, 1/2/4/8 B200".
+
+One STEP = one pass of the hot path over one synthetic trace (BASELINE config 3):
+    n_cols x 2^20-row column(s)  ->  coset LDE (blowup 4, offset 3, N = 2^22)  ->  one Merkle tree per column
+    (leaf rule fri.rs:118-121)  ->  Fri::prove on column 0 (omega = prim_nth_root(2^22), ef 4, 32 queries, 15 rounds)
+    ->  ProofStream::serialize bytes on the host.
+`value`  = LDE-output field elements proved per second, whole job (all ranks), trace already resident in HBM.
+`e2e`    = the same through the reference-facing C-ABI call with HOST buffers: the uint64 trace is copied from pinned
+           host memory inside the timed region and the proof bytes come back to the host.
+Multi-GPU (torchrun, one process per GPU): every rank proves its own trace (independent objects, no data-path
+collective) -> "weak" scaling; NCCL is used for the barrier and the max-over-ranks reduction only.
+
+`--impl reference` times the CPU restatement of the reference (oracle/, "port": no rustc in the image, so the Rust
+crate itself cannot be built) on the host cores, one independent pipeline per core, on a bounded sample of the same
+workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+P = 998244353
+METRIC = "prove time and NTT/LDE field elems/s at 2^20-row trace"
+UNIT = "field elems/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log-n", type=int, default=20)
+    ap.add_argument("--log-blowup", type=int, default=2)
+    ap.add_argument("--cols", type=int, default=1)
+    ap.add_argument("--nq", type=int, default=32)
+    ap.add_argument("--seed", type=lambda s: int(s, 0), default=0x5354524B)
+    ap.add_argument("--cpu-sample-log-n", type=int, default=9, help="trace rows (log2) of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return ("cfg3: %d col x 2^%d rows, coset LDE blowup %d offset 3 -> N=2^%d, Merkle per column, Fri::prove(ef %d, "
+            "%d queries) -> proof bytes" % (a.cols, a.log_n, 1 << a.log_blowup, a.log_n + a.log_blowup,
+                                          1 << a.log_blowup, a.nq))
+
+
+# ----------------------------------------------------------------------------------------------------- CPU arm
+
+def cpu_pipeline(a, mode, log_n, steps, warmup, threads):
+    import oracle as O
+    O.build()
+    for _ in range(warmup):
+        O.bench_pipeline(mode, log_n, a.log_blowup, min(a.nq, 1 << max(log_n - 2, 0)), a.seed, threads)
+    t = 0.0
+    for s in range(steps):
+        sec, _ = O.bench_pipeline(mode, log_n, a.log_blowup, min(a.nq, 1 << max(log_n - 2, 0)), a.seed + 1000 * s, threads)
+        t += sec
+    elems = threads * a.cols * (1 << (log_n + a.log_blowup)) * steps
+    return elems / t, t / steps
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    val, sec = cpu_pipeline(a, 0, a.cpu_sample_log_n, a.steps, min(a.warmup, 1), threads)
+    sample = ("%d independent pipelines (one per host thread) on a 2^%d-row trace each: LDE by the reference's own "
+              "interpolate_domain O(n^3) + eval_domain O(n*m), Merkle commit, Fri::prove, serialize"
+              % (threads, a.cpu_sample_log_n))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": min(a.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64 (u128 % p)", "data": "synthetic (splitmix64, seed 0x%X)" % a.seed,
+        "config": {"workload": workload_name(a), "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------- GPU arm
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 8]
+        os.unlink(self.f.name)
+        sm, reasons = [], set()
+        for r in rows:
+            r = [x.strip() for x in r]
+            try:
+                sm.append(float(r[1]))
+                out["sm_max_mhz"] = float(r[2])
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            busy = sorted(sm)[len(sm) // 2:]  # upper half = samples under load
+            out["sm_mhz"] = float(np.median(busy))
+        out["reasons"], out["samples"] = sorted(reasons), len(sm)
+        return out
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback")
+    import stark_rs_b200 as S
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    stream = torch.cuda.Stream(device=local)
+    ctx = S.Context(local, stream=stream.cuda_stream)
+    n, N = 1 << a.log_n, 1 << (a.log_n + a.log_blowup)
+    ef = 1 << a.log_blowup
+
+    # synthetic trace (SURVEY 8(d) generator), column-major, in PINNED host memory as uint64 (the ABI's layout)
+    from stark_rs_b200 import synthetic as G
+    host = torch.empty(a.cols * n, dtype=torch.int64).pin_memory()
+    hv = host.numpy().view(np.uint64)
+    for c in range(a.cols):
+        hv[c * n:(c + 1) * n] = G.splitmix64(a.seed + c + 1000003 * rank, n)
+    proof_cap = S.fri_proof_size(N, ef, a.nq)
+    proof = torch.empty(proof_cap, dtype=torch.uint8).pin_memory().numpy()
+    roots = torch.empty(a.cols * 32, dtype=torch.uint8).pin_memory().numpy().reshape(a.cols, 32)
+    dev_cols = ctx.upload_ptr(host.data_ptr(), a.cols * n)      # resident copy for the `value` measurement
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        with torch.cuda.stream(stream):
+            for e0, e1 in ev:
+                flush.zero_()               # evict L2 between timed iterations (outside the event pair)
+                e0.record(stream)
+                fn()
+                e1.record(stream)
+        barrier()
+        ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    step_dev = lambda: ctx.prove_trace_dev(dev_cols, a.cols, a.log_n, a.log_blowup, 3, a.nq, roots, proof)
+    step_e2e = lambda: ctx.prove_trace_ptr(host.data_ptr(), a.cols, a.log_n, a.log_blowup, 3, a.nq, roots, proof)
+
+    for _ in range(max(a.warmup, 3)):
+        step_dev()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = ctx.launches
+    ms_dev = timed(step_dev, a.steps)
+    launches = ctx.launches - l0
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, a.steps)
+    clocks = sampler.stop() if sampler else None
+    proof_len = step_dev()
+    proof_bytes = bytes(proof[:proof_len])
+
+    # per-kernel device times (CUDA events on the launching stream) over a further timed pass with profiling on
+    ctx.profile_begin()
+    ms_prof = timed(step_dev, a.steps)
+    prof = ctx.profile_end()
+
+    elems = world * a.cols * N * a.steps
+    value = elems / (ms_dev * 1e-3)
+    e2e_value = elems / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    ipk = ctx.int_peak()
+
+    kernels = {}
+    for k in prof:
+        per_step_ms = k["ms"] / a.steps
+        kernels[k["kernel"]] = {
+            "launches_per_step": k["launches"] / a.steps, "ms_per_step": per_step_ms,
+            "share": k["ms"] / ms_prof if ms_prof else None,
+            "algorithmic_bytes_per_step": k["bytes"] / a.steps,
+            "achieved_gbs": (k["bytes"] / (k["ms"] * 1e-3) / 1e9) if k["ms"] > 0 and k["bytes"] else None,
+        }
+        if kernels[k["kernel"]]["achieved_gbs"]:
+            kernels[k["kernel"]]["hbm_frac"] = kernels[k["kernel"]]["achieved_gbs"] / hbm_peak
+    dom = max(prof, key=lambda k: k["ms"])
+    dk = kernels[dom["kernel"]]
+    # integer-pipe view of the hash kernels: thread-instructions per hash from the shipped SASS
+    INSTR = {"merkle_level": 2316.0, "leaf_hash": 1868.0}
+    int_pipe = None
+    if dom["kernel"] in INSTR:
+        hashes = dom["bytes"] / (96.0 if dom["kernel"] == "merkle_level" else 36.0)
+        ips = hashes * INSTR[dom["kernel"]] / (dom["ms"] * 1e-3)
+        int_pipe = {"hashes_per_s": hashes / (dom["ms"] * 1e-3), "thread_instr_per_hash_sass": INSTR[dom["kernel"]],
+                    "achieved_thread_instr_per_s": ips, "peak_thread_instr_per_s_mixed": ipk["mixed_per_s"],
+                    "peak_alu_only": ipk["alu_per_s"], "peak_imad_only": ipk["imad_per_s"],
+                    "frac_of_mixed_peak": ips / ipk["mixed_per_s"]}
+    roofline = {
+        "kernel": dom["kernel"], "bound": "hbm", "achieved": dk["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
+        "frac": (dk["achieved_gbs"] / hbm_peak) if dk["achieved_gbs"] else None, "traffic": None,
+        "peak_source": peak_src, "launches_per_step": dk["launches_per_step"], "avg_launch_ms":
+            dom["ms"] / dom["launches"], "share_of_step": dk["share"],
+        "note": "the dominant kernel hashes (integer-pipe bound, SURVEY 8(d)); its HBM fraction is low by "
+                "construction -- see int_pipe; HBM-bound kernels (ntt_pass*, fri_fold) are listed under kernels",
+        "int_pipe": int_pipe,
+    }
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": ms_dev / a.steps, "prove_ms": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32 (Montgomery, p = 998244353)", "data": "synthetic (splitmix64, seed 0x%X)" % a.seed,
+        "config": {"workload": workload_name(a), "l2": "256 MiB buffer written between timed iterations",
+                   "timing": "CUDA events per step on the launching stream, summed, max over ranks",
+                   "proof_bytes": proof_len, "parallelism": "1 trace per GPU (no data-path collective)"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
+                "h2d_bytes_per_step": a.cols * n * 8, "d2h_bytes_per_step": proof_len + 32 * max(a.cols - 1, 0)},
+        "gpu_launches": launches, "gpu_launches_per_step": launches / a.steps,
+        "clocks": clocks, "roofline": roofline, "kernels": kernels,
+        "ms_per_step_profiled": ms_prof / a.steps, "int_peak": ipk,
+    }
+
+    if world == 1 and not a.no_cpu_baseline:
+        import oracle as O
+        threads = os.cpu_count() or 1
+        v0, s0 = cpu_pipeline(a, 0, a.cpu_sample_log_n, 2, 0, threads)
+        v1, s1 = cpu_pipeline(a, 1, 14, 2, 0, threads)
+        line["cpu_baseline"] = {
+            "value": v0, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d parallel pipelines on 2^%d-row traces, reference algorithms end to end (O(n^3) interpolate + "
+                      "Horner eval LDE, Merkle, Fri::prove), %.2f s per sample" % (threads, a.cpu_sample_log_n, s0)}
+        line["cpu_baseline_matched"] = {
+            "value": v1, "unit": UNIT, "cores": threads, "kind": "port+fast-ntt",
+            "sample": "%d parallel pipelines on 2^14-row traces, O(n log n) CPU NTT for the LDE (not in the reference), "
+                      "reference hash/Merkle/Fri::prove, %.2f s per sample" % (threads, s1)}
+        if not a.no_verify:
+            w = O.ff_prim_nth_root(N)
+            ok, why = O.fri_verify(proof_bytes, w, 3, N, ef, a.nq)
+            line["proof_verified_by_oracle"] = bool(ok)
+            if not ok:
+                line["verify_error"] = why
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

@@ -51,6 +51,12 @@ void stark_ctx_destroy(stark_ctx *ctx);
 int stark_ctx_sync(stark_ctx *ctx);
 void *stark_ctx_stream(stark_ctx *ctx);
 uint64_t stark_ctx_launches(stark_ctx *ctx); /* kernels launched so far through this context */
+/* per-kernel device timing with CUDA events on the context's stream (measurement only; bench.py roofline) */
+int stark_ctx_profile_begin(stark_ctx *ctx);
+int stark_ctx_profile_end(stark_ctx *ctx, char *json, size_t cap);
+/* register-only integer issue-rate microbenchmark: thread-instructions per second of IMAD, LOP3/IADD3 and a
+ * 1:1 mix, measured with CUDA events (no integer peak is recorded in MEASURED_PEAKS.json) */
+int stark_bench_int_peak(stark_ctx *ctx, double *imad_per_s, double *alu_per_s, double *mixed_per_s);
 const char *stark_last_error(void);
 const char *stark_version(void);
 

@@ -22,7 +22,7 @@ class OraclePanic(Exception):
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, f) for f in ("stark_oracle.c", "fast_cpu.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("stark_oracle.c", "fast_cpu.c", "bench_cpu.c")]
     if (not force and os.path.exists(_LIB)
             and all(not os.path.exists(s) or os.path.getmtime(_LIB) >= os.path.getmtime(s) for s in srcs)):
         return _LIB
@@ -426,3 +426,15 @@ def splitmix64(seed, n, p=P):
         z = z ^ (z >> np.uint64(31))
     out[:] = z % np.uint64(p)
     return out
+
+
+def bench_pipeline(mode, log_n, log_blowup, nq, seed, threads):
+    """bench_cpu.c: `threads` independent config-3 pipelines; returns (seconds, sha-less digest of thread 0's proof).
+    mode 0 = reference algorithms end to end ("port"), mode 1 = O(n log n) LDE + reference hash/Merkle/FRI."""
+    sec = C.c_double()
+    dig = np.zeros(32, dtype=np.uint8)
+    rc = lib().oracle_bench_pipeline(C.c_int(mode), C.c_uint32(log_n), C.c_uint32(log_blowup), C.c_uint32(nq), U64(seed),
+                                     C.c_int(threads), C.byref(sec), _p8(dig))
+    if rc != 0:
+        raise OraclePanic("bench pipeline failed: " + lib().oracle_last_error().decode())
+    return sec.value, dig.tobytes()

@@ -262,6 +262,22 @@ class Context:
     def stream(self):
         return lib().stark_ctx_stream(self.h)
 
+    # ---- measurement hooks
+    def profile_begin(self):
+        _chk(lib().stark_ctx_profile_begin(self.h))
+
+    def profile_end(self):
+        """per-kernel CUDA-event timings since profile_begin: [{kernel, launches, ms, bytes}]"""
+        import json
+        buf = C.create_string_buffer(1 << 16)
+        _chk(lib().stark_ctx_profile_end(self.h, buf, SZ(len(buf))))
+        return json.loads(buf.value.decode())
+
+    def int_peak(self):
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        _chk(lib().stark_bench_int_peak(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"imad_per_s": a.value, "alu_per_s": b.value, "mixed_per_s": c.value}
+
     # ---- buffers
     def alloc(self, n):
         h = C.c_void_p()

@@ -5,6 +5,8 @@
 // reference hashes and serialises raw values (hash.rs:32-35, stream.rs:45-51), so silently reducing would
 // break bit-exactness.
 #include "common.cuh"
+#include <stdlib.h>
+
 #include "merkle.h"
 
 thread_local char g_stark_err[512] = "";
@@ -70,6 +72,20 @@ __global__ void k_ff_vec_inv(const u32 *__restrict__ a, u32 *__restrict__ out, s
   }
 }
 
+// --------------------------------------------------------------------------------------- profiling
+
+void prof_begin(stark_ctx *ctx, const char *tag, u64 bytes) {
+  if (ctx->prof_n == ctx->prof_cap) {
+    ctx->prof_cap = ctx->prof_cap ? ctx->prof_cap * 2 : 1024;
+    ctx->prof = (ProfRec *)realloc(ctx->prof, ctx->prof_cap * sizeof(ProfRec));
+  }
+  ProfRec &r = ctx->prof[ctx->prof_n];
+  r.tag = tag, r.bytes = bytes;
+  cudaEventCreate(&r.e0), cudaEventCreate(&r.e1);
+  cudaEventRecord(r.e0, ctx->stream);
+}
+void prof_end(stark_ctx *ctx) { cudaEventRecord(ctx->prof[ctx->prof_n++].e1, ctx->stream); }
+
 // ------------------------------------------------------------------------------------- marshalling
 
 static int read_flag(stark_ctx *ctx, u32 *value) {
@@ -85,8 +101,7 @@ int upload_u64(stark_ctx *ctx, const uint64_t *host, size_t n, u32 *dst) {
   ST_TRY(dev_alloc(ctx, (void **)&tmp, n * 8));
   CU_TRY(ctx, cudaMemsetAsync(ctx->flag, 0, 4, ctx->stream));
   CU_TRY(ctx, cudaMemcpyAsync(tmp, host, n * 8, cudaMemcpyHostToDevice, ctx->stream));
-  k_narrow<<<(u32)((n + 255) / 256), 256, 0, ctx->stream>>>(tmp, dst, n, ctx->flag);
-  KERNEL_CHECK(ctx);
+  LAUNCH(ctx, "narrow_u64", 12ull * n, k_narrow<<<(u32)((n + 255) / 256), 256, 0, ctx->stream>>>(tmp, dst, n, ctx->flag));
   dev_free(ctx, tmp);
   u32 f = 0;
   ST_TRY(read_flag(ctx, &f));
@@ -98,8 +113,7 @@ int download_u64(stark_ctx *ctx, const u32 *src, size_t n, uint64_t *host) {
   if (n == 0) return STARK_OK;
   u64 *tmp = nullptr;
   ST_TRY(dev_alloc(ctx, (void **)&tmp, n * 8));
-  k_widen<<<(u32)((n + 255) / 256), 256, 0, ctx->stream>>>(src, tmp, n);
-  KERNEL_CHECK(ctx);
+  LAUNCH(ctx, "widen_u64", 12ull * n, k_widen<<<(u32)((n + 255) / 256), 256, 0, ctx->stream>>>(src, tmp, n));
   CU_TRY(ctx, cudaMemcpyAsync(host, tmp, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
   dev_free(ctx, tmp);
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -177,6 +191,38 @@ int stark_ctx_sync(stark_ctx *ctx) {
 }
 void *stark_ctx_stream(stark_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 uint64_t stark_ctx_launches(stark_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int stark_ctx_profile_begin(stark_ctx *ctx) {
+  if (!ctx) return stark_fail(nullptr, STARK_ERR_ARG, "null context");
+  ctx->prof_on = true;
+  return STARK_OK;
+}
+// writes a JSON array [{"kernel": tag, "launches": n, "ms": total, "bytes": total algorithmic}, ...]
+int stark_ctx_profile_end(stark_ctx *ctx, char *json, size_t cap) {
+  if (!ctx || !json || cap < 3) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+  ctx->prof_on = false;
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  struct Agg { const char *tag; u64 n, bytes; double ms; } agg[64];
+  int na = 0;
+  for (size_t i = 0; i < ctx->prof_n; i++) {
+    ProfRec &r = ctx->prof[i];
+    float ms = 0;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    cudaEventDestroy(r.e0), cudaEventDestroy(r.e1);
+    int k = 0;
+    while (k < na && strcmp(agg[k].tag, r.tag)) k++;
+    if (k == na && na < 64) agg[na++] = Agg{r.tag, 0, 0, 0.0};
+    if (k < 64) agg[k].n++, agg[k].bytes += r.bytes, agg[k].ms += ms;
+  }
+  ctx->prof_n = 0;
+  size_t w = 0;
+  w += snprintf(json + w, cap - w, "[");
+  for (int k = 0; k < na && w + 160 < cap; k++)
+    w += snprintf(json + w, cap - w, "%s{\"kernel\": \"%s\", \"launches\": %llu, \"ms\": %.6f, \"bytes\": %llu}", k ? ", " : "",
+                  agg[k].tag, (unsigned long long)agg[k].n, agg[k].ms, (unsigned long long)agg[k].bytes);
+  snprintf(json + w, cap - w, "]");
+  return STARK_OK;
+}
 
 // ---- buffers
 int stark_buf_alloc(stark_ctx *ctx, size_t n, stark_buf **out) {

@@ -37,7 +37,18 @@ struct stark_ctx {
   u32 *h_flag;     // pinned host mirror
   u64 launches;    // kernels launched through this context (bench.py "gpu_launches")
   char err[512];
+  // optional per-kernel timing (stark_ctx_profile_begin/end): CUDA events around every launch, on ctx->stream
+  bool prof_on;
+  struct ProfRec *prof;   // growing array
+  size_t prof_n, prof_cap;
 };
+struct ProfRec {
+  const char *tag;
+  u64 bytes;              // algorithmic HBM bytes of this launch, 0 if not meaningful
+  cudaEvent_t e0, e1;
+};
+void prof_begin(stark_ctx *ctx, const char *tag, u64 bytes);
+void prof_end(stark_ctx *ctx);
 
 extern thread_local char g_stark_err[512];
 
@@ -68,6 +79,15 @@ static inline int stark_fail(stark_ctx *ctx, int code, const char *fmt, ...) {
   do {                                   \
     (ctx)->launches++;                   \
     CU_TRY((ctx), cudaGetLastError());   \
+  } while (0)
+
+// LAUNCH(ctx, "tag", algorithmic_bytes, kernel<<<grid, block, smem, ctx->stream>>>(args...));
+#define LAUNCH(ctx, tag, bytes, ...)                       \
+  do {                                                     \
+    if ((ctx)->prof_on) prof_begin((ctx), (tag), (bytes)); \
+    __VA_ARGS__;                                           \
+    if ((ctx)->prof_on) prof_end((ctx));                   \
+    KERNEL_CHECK(ctx);                                     \
   } while (0)
 
 // stream-ordered scratch allocation (no device-wide sync on the hot path)

@@ -279,11 +279,12 @@ static int fold_launch(stark_ctx *ctx, const u32 *cw, u32 *out, size_t h, int r,
   if (h == 0) return STARK_OK;
   if (h % 4 == 0) {
     size_t blocks = (h / 4 + 255) / 256, cap = (size_t)ctx->sm_count * 8;
-    k_fri_fold<4><<<(u32)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(cw, out, h, r, G, g_r_m, alpha_m, inv2off_m);
+    LAUNCH(ctx, "fri_fold", 12ull * h,
+           k_fri_fold<4><<<(u32)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(cw, out, h, r, G, g_r_m, alpha_m, inv2off_m));
   } else {
-    k_fri_fold<1><<<(u32)((h + 255) / 256), 256, 0, ctx->stream>>>(cw, out, h, r, G, g_r_m, alpha_m, inv2off_m);
+    LAUNCH(ctx, "fri_fold", 12ull * h,
+           k_fri_fold<1><<<(u32)((h + 255) / 256), 256, 0, ctx->stream>>>(cw, out, h, r, G, g_r_m, alpha_m, inv2off_m));
   }
-  KERNEL_CHECK(ctx);
   return STARK_OK;
 }
 
@@ -334,8 +335,10 @@ static int fri_commit_dev(stark_ctx *ctx, const u32 *cw0, size_t n, u32 offset, 
     if (rc != STARK_OK) break;
     s->trees.push_back(tree);
     const bool last = r == R - 1;
+    if (ctx->prof_on) prof_begin(ctx, "transcript", 0);
     k_transcript_round<<<1, 32, 0, ctx->stream>>>(s->d_tr, tree->nodes + 32 * (2 * len - 2), s->d_roots + 32 * r,
                                                   last ? 0 : 1, s->d_alpha_raw + r, s->d_alpha_m + r);
+    if (ctx->prof_on) prof_end(ctx);
     ctx->launches++;
     if (last) break;  // fri.rs:133-135
     u32 *nxt = nullptr;
@@ -404,13 +407,14 @@ static int fri_prove_dev(stark_ctx *ctx, const u32 *cw0, size_t n, size_t domain
   if (rc == STARK_OK) rc = dev_alloc(ctx, (void **)&d_seed, 8);
   if (rc == STARK_OK) {
     d_top = reinterpret_cast<u64 *>(d_proof + ((L.total + 7) & ~(size_t)7));
+    if (ctx->prof_on) prof_begin(ctx, "query_phase", 0);
     k_transcript_challenge<<<1, 32, 0, ctx->stream>>>(s->d_tr, d_seed);  // fri.rs:272
     const size_t sample_size = L.n_cw > 1 ? s->len[1] : s->len[0];       // fri.rs:266-270
     if (nq) k_sample_indices<<<1, 256, 0, ctx->stream>>>(d_seed, sample_size, L.last_len, nq, d_top);
     const size_t hdr_threads = L.last_len > R ? L.last_len : R;
     k_proof_header<<<(u32)((hdr_threads + 255) / 256), 256, 0, ctx->stream>>>(d_proof, s->d_roots, R, s->cw[L.n_cw - 1],
                                                                              L.last_len);
-    ctx->launches += 3;
+    ctx->launches += nq ? 3 : 2;
     for (u32 i = 0; i + 1 < L.n_cw && nq; i++) {
       u32 d = 0;
       for (size_t m = s->len[i]; m > 1; m >>= 1) d++;
@@ -420,6 +424,7 @@ static int fri_prove_dev(stark_ctx *ctx, const u32 *cw0, size_t n, size_t domain
                                                                          s->trees[i + 1]->nodes, d_top, nq, d);
       ctx->launches++;
     }
+    if (ctx->prof_on) prof_end(ctx);
     if (cudaGetLastError() != cudaSuccess) rc = stark_fail(ctx, STARK_ERR_CUDA, "kernel launch failed");
   }
   if (rc == STARK_OK && cudaMemcpyAsync(proof, d_proof, L.total, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)

@@ -161,10 +161,10 @@ int merkle_leaves_dev(stark_ctx *ctx, const u32 *vals, size_t n, u32 width, size
   if (n == 0) return STARK_OK;
   const u32 blocks = (u32)((n + 255) / 256);
   if (width == 1)
-    k_leaf_hash1<<<blocks, 256, 0, ctx->stream>>>(vals, n, out);
+    LAUNCH(ctx, "leaf_hash", 36ull * n, k_leaf_hash1<<<blocks, 256, 0, ctx->stream>>>(vals, n, out));
   else
-    k_leaf_hashw<<<blocks, 256, 0, ctx->stream>>>(vals, n, width, row_stride, col_stride, out);
-  KERNEL_CHECK(ctx);
+    LAUNCH(ctx, "leaf_hash_w", (4ull * width + 32) * n,
+           k_leaf_hashw<<<blocks, 256, 0, ctx->stream>>>(vals, n, width, row_stride, col_stride, out));
   return STARK_OK;
 }
 
@@ -174,15 +174,14 @@ int merkle_climb_dev(stark_ctx *ctx, u8 *nodes, size_t n) {
   size_t m = n;
   while (m > 2048) {
     const size_t half = m >> 1;
-    k_merkle_level<<<(u32)((half + 255) / 256), 256, 0, ctx->stream>>>(nodes + 32 * (2 * n - 2 * m),
-                                                                       nodes + 32 * (2 * n - 2 * half), half);
-    KERNEL_CHECK(ctx);
+    LAUNCH(ctx, "merkle_level", 96ull * half,
+           k_merkle_level<<<(u32)((half + 255) / 256), 256, 0, ctx->stream>>>(nodes + 32 * (2 * n - 2 * m),
+                                                                              nodes + 32 * (2 * n - 2 * half), half));
     m = half;
     level++;
   }
   if (m > 1) {
-    k_merkle_top<<<1, 1024, 0, ctx->stream>>>(nodes, n, level);
-    KERNEL_CHECK(ctx);
+    LAUNCH(ctx, "merkle_top", 96ull * (m - 1), k_merkle_top<<<1, 1024, 0, ctx->stream>>>(nodes, n, level));
   }
   return STARK_OK;
 }
@@ -207,8 +206,7 @@ int merkle_open_dev(stark_ctx *ctx, const u8 *nodes, size_t n, const u64 *idx_de
   for (size_t m = n; m > 1; m >>= 1) depth++;
   if (depth == 0 || n_idx == 0) return STARK_OK;
   const u32 threads = n_idx * depth * 2;
-  k_merkle_open<<<(threads + 127) / 128, 128, 0, ctx->stream>>>(nodes, n, depth, idx_dev, n_idx, out_dev);
-  KERNEL_CHECK(ctx);
+  LAUNCH(ctx, "merkle_open", 0, k_merkle_open<<<(threads + 127) / 128, 128, 0, ctx->stream>>>(nodes, n, depth, idx_dev, n_idx, out_dev));
   return STARK_OK;
 }
 
@@ -223,8 +221,8 @@ int stark_hash_bytes(stark_ctx *ctx, const uint8_t *msgs, size_t n_msgs, size_t 
   ST_TRY(dev_alloc(ctx, (void **)&d_in, n_msgs * msg_len));
   ST_TRY(dev_alloc(ctx, (void **)&d_out, n_msgs * 32));
   if (msg_len) CU_TRY(ctx, cudaMemcpyAsync(d_in, msgs, n_msgs * msg_len, cudaMemcpyHostToDevice, ctx->stream));
-  k_hash_bytes<<<(u32)((n_msgs + 127) / 128), 128, 0, ctx->stream>>>(d_in, n_msgs, msg_len, d_out);
-  KERNEL_CHECK(ctx);
+  LAUNCH(ctx, "hash_bytes", (msg_len + 32) * n_msgs,
+         k_hash_bytes<<<(u32)((n_msgs + 127) / 128), 128, 0, ctx->stream>>>(d_in, n_msgs, msg_len, d_out));
   CU_TRY(ctx, cudaMemcpyAsync(out, d_out, n_msgs * 32, cudaMemcpyDeviceToHost, ctx->stream));
   dev_free(ctx, d_in), dev_free(ctx, d_out);
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));

@@ -1,0 +1,70 @@
+// microbench.cu -- register-only integer issue-rate microbenchmark (measurement infrastructure).
+// The roofline of the hash kernels is the integer pipe, for which MEASURED_PEAKS.json has no number
+// (SURVEY 8(d)).  Three kernels with 8 independent chains per thread: IMAD only (fma pipe), LOP3/IADD3 only
+// (alu pipe), and a 1:1 mix (both pipes, the issue-slot limit).
+#include "common.cuh"
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_int_peak(u32 *out, u32 seed, int iters) {
+  u32 a[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) a[k] = seed + threadIdx.x * 8 + k;
+  const u32 m = seed | 1u, c = seed ^ 0x9e3779b9u;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        if (MODE == 0) {
+          a[k] = a[k] * m + c;  // IMAD
+        } else if (MODE == 1) {
+          a[k] = (a[k] ^ c) + m;  // LOP3 + IADD3
+          a[k] = (a[k] & m) ^ c;  // LOP3
+        } else {
+          a[k] = a[k] * m + c;    // IMAD
+          a[k] = (a[k] ^ m) + c;  // LOP3 (xor) + IADD3 ... see SASS
+        }
+      }
+    }
+  }
+  u32 r = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) r ^= a[k];
+  if (r == 0x12345678u) out[0] = r;  // keep the chains alive
+}
+
+template <int MODE>
+static int run_mode(stark_ctx *ctx, u32 *d_out, double ops_per_inner, double *per_s) {
+  const int iters = 2048, blocks = ctx->sm_count * 8, threads = 256;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0), cudaEventCreate(&e1);
+  k_int_peak<MODE><<<blocks, threads, 0, ctx->stream>>>(d_out, 12345u, 64);  // warm-up
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {
+    cudaEventRecord(e0, ctx->stream);
+    k_int_peak<MODE><<<blocks, threads, 0, ctx->stream>>>(d_out, 12345u + rep, iters);
+    cudaEventRecord(e1, ctx->stream);
+    CU_TRY(ctx, cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+  }
+  cudaEventDestroy(e0), cudaEventDestroy(e1);
+  ctx->launches += 6;
+  const double instr = (double)blocks * threads * iters * 64.0 * ops_per_inner;
+  *per_s = instr / (best * 1e-3);
+  return STARK_OK;
+}
+
+extern "C" int stark_bench_int_peak(stark_ctx *ctx, double *imad_per_s, double *alu_per_s, double *mixed_per_s) {
+  if (!ctx || !imad_per_s || !alu_per_s || !mixed_per_s) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+  u32 *d_out = nullptr;
+  ST_TRY(dev_alloc(ctx, (void **)&d_out, 16));
+  // instruction counts per innermost statement group, from the SASS of this file (cuobjdump -sass):
+  // MODE 0: 1 IMAD; MODE 1: 3 (LOP3, IADD3, LOP3); MODE 2: 3 (IMAD, LOP3, IADD3)
+  int rc = run_mode<0>(ctx, d_out, 1.0, imad_per_s);
+  if (rc == STARK_OK) rc = run_mode<1>(ctx, d_out, 3.0, alu_per_s);
+  if (rc == STARK_OK) rc = run_mode<2>(ctx, d_out, 3.0, mixed_per_s);
+  dev_free(ctx, d_out);
+  return rc;
+}

@@ -91,9 +91,8 @@ int geo_tables(stark_ctx *ctx, u32 g, u32 c, u64 max_index, GeoTables *out) {
   CU_TRY(ctx, cudaMalloc(&e.lo, (size_t)(4096 + alloc_hi) * 4));
   e.hi = e.lo + 4096;
   e.g = g, e.c = c, e.hi_len = alloc_hi, e.stamp = ++ctx->geo_stamp;
-  k_geo_tables<<<(alloc_hi + 4095 + 255) / 256, 256, 0, ctx->stream>>>(e.lo, e.hi, ff::to_mont(g), ff::to_mont(c),
-                                                                       alloc_hi);
-  KERNEL_CHECK(ctx);
+  LAUNCH(ctx, "geo_tables", 0, k_geo_tables<<<(alloc_hi + 4095 + 255) / 256, 256, 0, ctx->stream>>>(
+                                   e.lo, e.hi, ff::to_mont(g), ff::to_mont(c), alloc_hi));
   out->lo = e.lo, out->hi = e.hi;
   return STARK_OK;
 }
@@ -193,7 +192,7 @@ static int resolve_scale(stark_ctx *ctx, const ScaleSpec &s, u64 max_index, int 
 }
 
 template <int V, bool ROWOUT>
-static int launch_pass(stark_ctx *ctx, const PassArgs &A, u32 tiles) {
+static int launch_pass(stark_ctx *ctx, const PassArgs &A, u32 tiles, const char *tag, u64 bytes) {
   const u32 nt = (1u << (A.logL - 3)) << A.logC4;
   const size_t smem = ((size_t)V * 4) << (A.logL + A.logC4);
   static bool configured = false;  // per instantiation
@@ -201,8 +200,7 @@ static int launch_pass(stark_ctx *ctx, const PassArgs &A, u32 tiles) {
     CU_TRY(ctx, cudaFuncSetAttribute(k_ntt_pass<V, ROWOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     configured = true;
   }
-  k_ntt_pass<V, ROWOUT><<<tiles, nt, smem, ctx->stream>>>(A);
-  KERNEL_CHECK(ctx);
+  LAUNCH(ctx, tag, bytes, k_ntt_pass<V, ROWOUT><<<tiles, nt, smem, ctx->stream>>>(A));
   return STARK_OK;
 }
 
@@ -238,8 +236,7 @@ int ntt_transform(stark_ctx *ctx, const u32 *in, u32 *out, int log_n, bool inver
     TinyArgs A = {in, out, log_n, batch, in_batch, out_batch, n_valid, ff::to_mont(w), pre_mode, post_mode,
                   pre_geo, post_geo, post_c};
     // in == out is fine: each thread reads its whole transform before writing
-    k_ntt_tiny<<<(batch + 127) / 128, 128, 0, ctx->stream>>>(A);
-    KERNEL_CHECK(ctx);
+    LAUNCH(ctx, "ntt_tiny", 8ull * N * batch, k_ntt_tiny<<<(batch + 127) / 128, 128, 0, ctx->stream>>>(A));
     return STARK_OK;
   }
 
@@ -260,7 +257,7 @@ int ntt_transform(stark_ctx *ctx, const u32 *in, u32 *out, int log_n, bool inver
     A.out_batch = out_batch, A.out_stride = 1;
     A.tiles_per_batch = 1;
     A.tw = ctx->tw_sub[d] + (1u << log_n);
-    return launch_pass<1, false>(ctx, A, batch);
+    return launch_pass<1, false>(ctx, A, batch, "ntt_single", 4ull * batch * (n_valid + N));
   }
 
   // two passes.  pass 1 cannot run in place (it transposes), so in == out goes through a scratch copy.
@@ -285,7 +282,7 @@ int ntt_transform(stark_ctx *ctx, const u32 *in, u32 *out, int log_n, bool inver
     B.tiles_per_batch = (int)(N2 >> logC);
     B.tw = ctx->tw_sub[d] + (1u << log_n1);
     B.post_mode = SCALE_NONE;
-    ST_TRY((launch_pass<4, true>(ctx, B, batch * (u32)B.tiles_per_batch)));
+    ST_TRY((launch_pass<4, true>(ctx, B, batch * (u32)B.tiles_per_batch, "ntt_pass1", 4ull * batch * (n_valid + N))));
   }
   {  // pass 2: L = N2, columns k1 (stride N1), in place on out
     PassArgs B = A;
@@ -298,7 +295,7 @@ int ntt_transform(stark_ctx *ctx, const u32 *in, u32 *out, int log_n, bool inver
     B.tiles_per_batch = (int)(N1 >> logC);
     B.tw = ctx->tw_sub[d] + (1u << log_n2);
     B.pre_mode = SCALE_NONE;
-    ST_TRY((launch_pass<4, false>(ctx, B, batch * (u32)B.tiles_per_batch)));
+    ST_TRY((launch_pass<4, false>(ctx, B, batch * (u32)B.tiles_per_batch, "ntt_pass2", 8ull * batch * N)));
   }
   dev_free(ctx, tmp);
   return STARK_OK;
