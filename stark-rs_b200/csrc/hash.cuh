@@ -188,3 +188,130 @@ HS_HD void from_bytes(const u8 *msg, size_t n, u8 *out) {
 }
 
 }  // namespace hs
+
+// =====================================================================================================
+// hs2 -- TWO hashes per thread, one per 16-bit lane of every state register (lane 0 = bits 0-15, lane 1 =
+// bits 16-31).  ncu on the one-hash-per-thread kernel above shows the ALU pipe (LOP3/PRMT/SHF/IADD3) at 92 %
+// with the FMA pipe at 10 %: the kernel is bound by ALU-pipe instruction count.  Packing two hashes per
+// register halves every per-register instruction, and the formulation below moves the shifts and adds to the
+// FMA pipe (IMAD) so both pipes carry about the same load:
+//   lanes "clean" (< 256) on entry to the sbox:  y = v*251 + c   (one IMAD; each lane <= 64260 < 2^16)
+//   rotl8(z,k) of both lanes:  d = PRMT(y: b0,b0,b2,b2)  (masks + duplicates),  e = d << k as IMAD d*2^k,
+//                              r = PRMT(e: b1,0,b3,0)  -> clean lanes again
+//   linear layer: 6 LOP3 per 4 registers, lanes stay clean
+//   neighbour chain: plain 32-bit adds; a lane grows to at most 255 + 31*510 + 1020 < 2^16, so lanes never
+//                    spill into each other; the next sbox masks.
+// Per hash and mix: ~72 ALU-pipe + ~64 FMA-pipe instructions instead of 144 + 32.
+namespace hs2 {
+using hs::prime_at;
+using hs::rc_at;
+using hs::u32;
+
+HS_HD u32 prmt(u32 a, u32 b, u32 sel) {
+#if defined(__CUDA_ARCH__)
+  return __byte_perm(a, b, sel);
+#else
+  const uint64_t src = ((uint64_t)b << 32) | a;
+  u32 r = 0;
+  for (int i = 0; i < 4; i++) r |= (u32)((src >> (8 * ((sel >> (4 * i)) & 7))) & 0xff) << (8 * i);
+  return r;
+#endif
+}
+// a + b on the FMA pipe: a * one + b with `one` a RUNTIME 1 (ptxas folds a literal 1 back into IADD3, which
+// lands on the already saturated ALU pipe)
+HS_HD u32 add_fma(u32 a, u32 b, u32 one) { return a * one + b; }
+constexpr u32 M2 = 0x00ff00ffu;
+// rotl8 of both (8-bit, possibly dirty above bit 7) lanes by k; result lanes clean
+HS_HD u32 rotl2(u32 y, u32 k) { return prmt(prmt(y, 0u, 0x2200) * (1u << k), 0u, 0x4341); }
+
+struct State2 {
+  u32 s[32];
+  u32 one;  // runtime constant 1 (see add_fma)
+};
+HS_HD void init(State2 &st, u32 one) {
+  st.one = one;
+#pragma unroll
+  for (int i = 0; i < 32; i++) st.s[i] = prime_at(i) * 0x10001u;
+}
+// mix_state (hash.rs:59-86) for both lanes, round constants left pending (see hs::mix_lazy)
+template <bool PENDING>
+HS_HD void mix_lazy(State2 &st) {
+  u32 *s = st.s;
+#pragma unroll
+  for (int i = 0; i < 32; i++) {
+    const u32 c = PENDING ? ((rc_at(i) * 251u) & 0xffu) * 0x10001u : 0u;
+    s[i] = rotl2((s[i] & M2) * 251u + c, 1);
+  }
+#pragma unroll
+  for (int g = 0; g < 8; g++) {
+    const u32 t0 = s[4 * g], t1 = s[4 * g + 1], t2 = s[4 * g + 2], t3 = s[4 * g + 3];
+    const u32 x = t0 ^ t1 ^ t2 ^ t3;
+    s[4 * g] = x ^ t2 ^ 0x00630063u;
+    s[4 * g + 1] = x ^ t1 ^ 0x00630063u;
+    s[4 * g + 2] = x ^ t3 ^ 0x00630063u;
+    s[4 * g + 3] = x ^ t0 ^ 0x00630063u;
+  }
+  // s[i] += s[i+1] + s[i-1]' : the pair sums are independent (FMA pipe), only the running add is serial
+  u32 t[32];
+#pragma unroll
+  for (int i = 0; i < 31; i++) t[i] = add_fma(s[i], s[i + 1], st.one);
+  s[0] = add_fma(t[0], s[31], st.one);
+#pragma unroll
+  for (int i = 1; i < 31; i++) s[i] = add_fma(t[i], s[i - 1], st.one);
+  s[31] = s[31] + s[0] + s[30];
+}
+HS_HD void settle(State2 &st) {
+#pragma unroll
+  for (int i = 0; i < 32; i++) st.s[i] += rc_at(i) * 0x10001u;
+}
+template <bool PENDING>
+HS_HD void finalize(State2 &st) {
+  mix_lazy<PENDING>(st);
+#pragma unroll 1
+  for (int k = 0; k < 7; k++) mix_lazy<true>(st);
+  settle(st);
+}
+// absorb the byte pair b (clean lanes) at position i (hash.rs:15-20); constants must be settled
+HS_HD void absorb_pair(State2 &st, int i, u32 b) {
+  const u32 v = rotl2(add_fma(st.s[i], b, st.one), 3);
+  st.s[i] = v;
+  st.s[(i + 7) & 31] ^= v;
+}
+// byte k (0..3) of word a -> lane 0, of word b -> lane 1, clean
+HS_HD u32 pair_bytes(u32 a, u32 b, int k) { return prmt(a, b, 0x0400u + (u32)k * 0x0101u) & M2; }
+
+template <bool PENDING>
+HS_HD void absorb_words_mix(State2 &st, const u32 *wa, const u32 *wb) {
+  if (PENDING) settle(st);
+#pragma unroll
+  for (int i = 0; i < 32; i++) absorb_pair(st, i, pair_bytes(wa[i >> 2], wb[i >> 2], i & 3));
+  mix_lazy<false>(st);
+}
+HS_HD void pack_words(const State2 &st, u32 *wa, u32 *wb) {
+#pragma unroll
+  for (int g = 0; g < 8; g++) {
+    const u32 *s = st.s + 4 * g;
+    wa[g] = prmt(prmt(s[0], s[1], 0x0040), prmt(s[2], s[3], 0x0040), 0x5410);
+    wb[g] = prmt(prmt(s[0], s[1], 0x0062), prmt(s[2], s[3], 0x0062), 0x5410);
+  }
+}
+// two Hash::combine (hash.rs:41-46) at once
+HS_HD void combine2(const u32 *la, const u32 *ra, const u32 *lb, const u32 *rb, u32 *oa, u32 *ob, u32 one) {
+  State2 st;
+  init(st, one);
+  absorb_words_mix<false>(st, la, lb);
+  absorb_words_mix<true>(st, ra, rb);
+  finalize<true>(st);
+  pack_words(st, oa, ob);
+}
+// two Hash::from_field_elements(&[v]) (hash.rs:32-35) at once
+HS_HD void leaf2(u32 va, u32 vb, u32 *oa, u32 *ob, u32 one) {
+  State2 st;
+  init(st, one);
+#pragma unroll
+  for (int i = 0; i < 8; i++) absorb_pair(st, i, i < 4 ? pair_bytes(va, vb, i) : 0u);
+  mix_lazy<false>(st);
+  finalize<true>(st);
+  pack_words(st, oa, ob);
+}
+}  // namespace hs2

@@ -24,13 +24,22 @@ __device__ __forceinline__ void store_hash(u8 *p, const u32 *w) {
   reinterpret_cast<uint4 *>(p)[1] = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
-// leaf i = Hash::from_field_elements(&[vals[i]])  (fri.rs:118-121, hash.rs:32-35)
+// leaf i = Hash::from_field_elements(&[vals[i]])  (fri.rs:118-121, hash.rs:32-35); two leaves per thread (hs2)
 __global__ void __launch_bounds__(256) k_leaf_hash1(const u32 *__restrict__ vals, size_t n, u8 *__restrict__ out) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t i = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
   if (i >= n) return;
-  u32 w[8];
-  hs::leaf1(vals[i], w);
-  store_hash(out + 32 * i, w);
+  const bool two = i + 1 < n;
+  u32 va, vb = 0;
+  if (two) {
+    const uint2 v = *reinterpret_cast<const uint2 *>(vals + i);
+    va = v.x, vb = v.y;
+  } else {
+    va = vals[i];
+  }
+  u32 wa[8], wb[8];
+  hs2::leaf2(va, vb, wa, wb, blockDim.y);
+  store_hash(out + 32 * i, wa);
+  if (two) store_hash(out + 32 * i + 32, wb);
 }
 
 // leaf i = Hash::from_field_elements(&[vals[i*row_stride + c*col_stride] for c < width])  (hash.rs:32-35)
@@ -92,43 +101,51 @@ __global__ void __launch_bounds__(128) k_hash_bytes(const u8 *__restrict__ msgs,
   for (int g = 0; g < 8; g++) reinterpret_cast<u32 *>(o)[g] = w[g];
 }
 
-// one tree level: parent i = Hash::combine(child 2i, child 2i+1)  (merkle.rs:21-27)
+// one tree level: parent i = Hash::combine(child 2i, child 2i+1)  (merkle.rs:21-27); two parents per thread
 __global__ void __launch_bounds__(256) k_merkle_level(const u8 *__restrict__ in, u8 *__restrict__ out, size_t n_out) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t i = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
   if (i >= n_out) return;
-  u32 l[8], r[8], w[8];
-  load_hash(in + 64 * i, l);
-  load_hash(in + 64 * i + 32, r);
-  hs::combine(l, r, w);
-  store_hash(out + 32 * i, w);
+  const bool two = i + 1 < n_out;
+  u32 la[8], ra[8], lb[8], rb[8], wa[8], wb[8];
+  load_hash(in + 64 * i, la);
+  load_hash(in + 64 * i + 32, ra);
+  load_hash(in + 64 * (two ? i + 1 : i), lb);
+  load_hash(in + 64 * (two ? i + 1 : i) + 32, rb);
+  hs2::combine2(la, ra, lb, rb, wa, wb, blockDim.y);
+  store_hash(out + 32 * i, wa);
+  if (two) store_hash(out + 32 * i + 32, wb);
 }
 
 // the last levels: one CTA climbs from a level with m <= 2048 nodes to the root through shared memory,
 // writing every level to the tree array.  nodes = tree base, n = leaf count, level = input level.
-__global__ void __launch_bounds__(1024) k_merkle_top(u8 *nodes, size_t n, u32 level) {
+__global__ void __launch_bounds__(512) k_merkle_top(u8 *nodes, size_t n, u32 level) {
   __shared__ __align__(16) u8 sm[1024 * 32];
   size_t m = n >> level;
-  const u32 t = threadIdx.x;
+  const u32 t = 2 * threadIdx.x;
   bool first = true;
   while (m > 1) {
     const size_t half = m >> 1;
-    u32 w[8];
-    if (t < half) {
-      u32 l[8], r[8];
-      if (first) {
-        const u8 *src = nodes + 32 * (2 * n - 2 * m);
-        load_hash(src + 64 * t, l);
-        load_hash(src + 64 * t + 32, r);
-      } else {
-        load_hash(sm + 64 * t, l);
-        load_hash(sm + 64 * t + 32, r);
-      }
-      hs::combine(l, r, w);
+    u32 wa[8], wb[8];
+    const bool act = t < half, two = t + 1 < half;
+    if (act) {
+      u32 la[8], ra[8], lb[8], rb[8];
+      const u8 *src = first ? nodes + 32 * (2 * n - 2 * m) : sm;
+      const u32 tb = two ? t + 1 : t;
+      load_hash(src + 64 * t, la);
+      load_hash(src + 64 * t + 32, ra);
+      load_hash(src + 64 * tb, lb);
+      load_hash(src + 64 * tb + 32, rb);
+      hs2::combine2(la, ra, lb, rb, wa, wb, blockDim.y);
     }
     __syncthreads();
-    if (t < half) {
-      store_hash(sm + 32 * t, w);
-      store_hash(nodes + 32 * (2 * n - 2 * half) + 32 * t, w);
+    if (act) {
+      u8 *dst = nodes + 32 * (2 * n - 2 * half);
+      store_hash(sm + 32 * t, wa);
+      store_hash(dst + 32 * t, wa);
+      if (two) {
+        store_hash(sm + 32 * t + 32, wb);
+        store_hash(dst + 32 * t + 32, wb);
+      }
     }
     __syncthreads();
     first = false;
@@ -161,7 +178,7 @@ int merkle_leaves_dev(stark_ctx *ctx, const u32 *vals, size_t n, u32 width, size
   if (n == 0) return STARK_OK;
   const u32 blocks = (u32)((n + 255) / 256);
   if (width == 1)
-    LAUNCH(ctx, "leaf_hash", 36ull * n, k_leaf_hash1<<<blocks, 256, 0, ctx->stream>>>(vals, n, out));
+    LAUNCH(ctx, "leaf_hash", 36ull * n, k_leaf_hash1<<<(u32)((n + 511) / 512), 256, 0, ctx->stream>>>(vals, n, out));
   else
     LAUNCH(ctx, "leaf_hash_w", (4ull * width + 32) * n,
            k_leaf_hashw<<<blocks, 256, 0, ctx->stream>>>(vals, n, width, row_stride, col_stride, out));
@@ -175,13 +192,13 @@ int merkle_climb_dev(stark_ctx *ctx, u8 *nodes, size_t n) {
   while (m > 2048) {
     const size_t half = m >> 1;
     LAUNCH(ctx, "merkle_level", 96ull * half,
-           k_merkle_level<<<(u32)((half + 255) / 256), 256, 0, ctx->stream>>>(nodes + 32 * (2 * n - 2 * m),
+           k_merkle_level<<<(u32)((half + 511) / 512), 256, 0, ctx->stream>>>(nodes + 32 * (2 * n - 2 * m),
                                                                               nodes + 32 * (2 * n - 2 * half), half));
     m = half;
     level++;
   }
   if (m > 1) {
-    LAUNCH(ctx, "merkle_top", 96ull * (m - 1), k_merkle_top<<<1, 1024, 0, ctx->stream>>>(nodes, n, level));
+    LAUNCH(ctx, "merkle_top", 96ull * (m - 1), k_merkle_top<<<1, 512, 0, ctx->stream>>>(nodes, n, level));
   }
   return STARK_OK;
 }

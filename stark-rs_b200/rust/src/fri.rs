@@ -1,0 +1,52 @@
+//! Fri (reference fri.rs:8-311): the prover runs on the GPU (stark_fri_prove), the verifier stays with the reference.
+#![allow(dead_code)]
+use crate::ff::{FieldElement, FiniteField};
+use crate::ffi;
+use crate::fiat_shamir::FiatShamir;
+use crate::stream::{ProofObject, ProofStream};
+
+pub struct Fri {
+    pub offset: FieldElement, pub omega: FieldElement, pub domain_length: usize, pub field: FiniteField,
+    pub expansion_factor: usize, pub num_colinearity_tests: usize,
+}
+
+impl Fri {
+    pub fn new(omega: FieldElement, offset: FieldElement, domain_length: usize, expansion_factor: usize, num_colinearity_tests: usize) -> Self {
+        assert!(domain_length.is_power_of_two(), "Domain length must be power of 2");
+        assert!(expansion_factor.is_power_of_two(), "Expansion factor must be power of 2");
+        assert!(expansion_factor >= 4, "Expansion factor must be at least 4");
+        Fri { omega, offset, domain_length, field: omega.field, expansion_factor, num_colinearity_tests }
+    }
+    pub fn num_rounds(&self) -> u64 {
+        let mut r = 0u32;
+        ffi::check(unsafe { ffi::stark_fri_num_rounds(self.domain_length, self.expansion_factor as u32, self.num_colinearity_tests as u32, &mut r) });
+        r as u64
+    }
+    /// fri.rs:57-91 for a whole codeword; alpha may be unreduced
+    pub fn fold_codeword(&self, codeword: &[FieldElement], alpha: &FieldElement, offset: &FieldElement, omega: &FieldElement) -> Vec<FieldElement> {
+        let vals: Vec<u64> = codeword.iter().map(|e| e.value).collect();
+        let mut out = vec![0u64; vals.len() / 2];
+        ffi::check(unsafe { ffi::stark_fri_fold(ffi::ctx(), vals.as_ptr(), vals.len(), alpha.value, offset.value, omega.value, out.as_mut_ptr()) });
+        out.into_iter().map(|v| self.field.new_element(v)).collect()
+    }
+    /// fri.rs:250-311.  The GPU returns ProofStream::serialize's bytes; they are parsed back into `proof_stream`
+    /// and the roots are absorbed into `fiat_shamir`, so both end in the state the reference leaves them in.
+    pub fn prove(&self, initial_codeword: Vec<FieldElement>, fiat_shamir: &mut FiatShamir, proof_stream: &mut ProofStream) -> Vec<usize> {
+        let vals: Vec<u64> = initial_codeword.iter().map(|e| e.value).collect();
+        let mut cap = 0usize;
+        ffi::check(unsafe { ffi::stark_fri_proof_size(self.domain_length, self.expansion_factor as u32, self.num_colinearity_tests as u32, &mut cap) });
+        let (mut proof, mut len) = (vec![0u8; cap], 0usize);
+        let mut top = vec![0u64; self.num_colinearity_tests.max(1)];
+        ffi::check(unsafe {
+            ffi::stark_fri_prove(ffi::ctx(), vals.as_ptr(), vals.len(), self.domain_length, self.offset.value, self.omega.value,
+                                 self.expansion_factor as u32, self.num_colinearity_tests as u32, fiat_shamir.transcript.as_ptr(),
+                                 fiat_shamir.transcript.len(), proof.as_mut_ptr(), cap, &mut len, top.as_mut_ptr())
+        });
+        for obj in ProofStream::deserialize(&proof[..len], self.field).objects {
+            if let ProofObject::MerkleRoot(r) = &obj { fiat_shamir.absorb(&r.0); }
+            proof_stream.push(obj);
+        }
+        top.truncate(self.num_colinearity_tests);
+        top.into_iter().map(|i| i as usize).collect()
+    }
+}

@@ -33,3 +33,26 @@ int main() {
   printf(fails ? "FAIL %d\n" : "OK\n", fails);
   return fails != 0;
 }
+// ---- hs2 (two hashes per thread) appended check
+static int check_hs2() {
+  int fails = 0;
+  uint64_t s = 7;
+  auto rnd = [&]() { s = s * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)(s >> 32); };
+  for (int it = 0; it < 300; it++) {
+    uint32_t la[8], ra[8], lb[8], rb[8], oa[8], ob[8]; uint8_t ea[32], eb[32];
+    for (int i = 0; i < 8; i++) la[i] = rnd(), ra[i] = rnd(), lb[i] = rnd(), rb[i] = rnd();
+    if (it == 0) for (int i = 0; i < 8; i++) la[i] = ra[i] = 0xffffffffu, lb[i] = rb[i] = 0;
+    hs2::combine2(la, ra, lb, rb, oa, ob, 1);
+    oracle_hash_combine((uint8_t *)la, (uint8_t *)ra, ea);
+    oracle_hash_combine((uint8_t *)lb, (uint8_t *)rb, eb);
+    if (memcmp(oa, ea, 32) || memcmp(ob, eb, 32)) { fails++; if (fails < 3) printf("combine2 mismatch it=%d\n", it); }
+    uint32_t va = rnd() % 998244353u, vb = rnd() % 998244353u; uint64_t a64 = va, b64 = vb;
+    hs2::leaf2(va, vb, oa, ob, 1);
+    oracle_hash_from_bytes((uint8_t *)&a64, 8, ea);
+    oracle_hash_from_bytes((uint8_t *)&b64, 8, eb);
+    if (memcmp(oa, ea, 32) || memcmp(ob, eb, 32)) { fails++; if (fails < 3) printf("leaf2 mismatch it=%d\n", it); }
+  }
+  printf(fails ? "hs2 FAIL %d\n" : "hs2 OK\n", fails);
+  return fails;
+}
+static int dummy_hs2 = check_hs2();
