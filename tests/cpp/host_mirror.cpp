@@ -1,0 +1,63 @@
+// host_mirror.cpp -- the reference's own tests (fri.rs:532-693, merkle.rs:99-133, mul.rs / interpolate.rs KATs)
+// re-stated against the C++ host mirror (stark-rs_b200/host/stark.hpp) -> C ABI -> B200.  The oracle's Fri::verify
+// (oracle/liboracle.so) is the acceptance check for the proofs.  TEST CODE.
+#include <cstdio>
+#include "../../stark-rs_b200/host/stark.hpp"
+using namespace stark;
+extern "C" int oracle_fri_verify(uint64_t p, const uint8_t *proof, size_t len, uint64_t omega, uint64_t offset, size_t n,
+                                 size_t ef, size_t nq, int *ok, char *why, size_t cap);
+static int fails = 0;
+#define EXPECT(c) do { if (!(c)) { printf("FAIL %s:%d %s\n", __FILE__, __LINE__, #c); fails++; } } while (0)
+static const uint64_t P = 998244353;
+
+static void fri_case(size_t n, uint64_t off, size_t ef, size_t nq, std::vector<uint64_t> coeffs) {
+  FiniteField field(P);
+  FieldElement omega = field.prim_nth_root(n), offset = field.new_element(off);
+  Fri fri(omega, offset, n, ef, nq);
+  Polynomial poly(wrap(coeffs, field), field);
+  std::vector<FieldElement> domain;
+  for (size_t i = 0; i < n; i++) domain.push_back(field.mul(offset, field.exp(omega, i)));
+  auto codeword = poly.eval_domain(domain);   // takes the coset-NTT path
+  for (size_t i = 0; i < n; i += n / 8) EXPECT(codeword[i] == poly.eval(domain[i]));
+  ProofStream ps;
+  FiatShamir fs;
+  auto top = fri.prove(codeword, fs, ps);
+  EXPECT(top.size() == nq);
+  auto bytes = ps.serialize();
+  EXPECT(fs.transcript.size() == 32 * fri.num_rounds());
+  int ok = 0;
+  char why[128] = "";
+  oracle_fri_verify(P, bytes.data(), bytes.size(), omega.value, off, n, ef, nq, &ok, why, sizeof why);
+  if (!ok) printf("verify: %s\n", why);
+  EXPECT(ok == 1);
+}
+
+int main() {
+  FiniteField field(P);
+  // fri.rs:532-693
+  fri_case(32, 3, 4, 2, std::vector<uint64_t>(1, 5));
+  fri_case(64, 7, 4, 3, {5, 3});
+  fri_case(128, 13, 4, 4, {1, 3, 2});
+  fri_case(256, 17, 8, 5, {1, 2, 5, 3, 7, 4, 1, 2});
+  // merkle.rs:111-122
+  std::vector<Hash> leaves;
+  for (uint8_t i = 0; i < 8; i++) leaves.push_back(Hash::from_bytes(&i, 1));
+  MerkleTree tree(leaves);
+  for (size_t i = 0; i < 8; i++) EXPECT(MerkleTree::verify(leaves[i], i, tree.open(i), tree.get_root()));
+  EXPECT(tree.get_root().to_hex() == "d86d7c3c1368c029ff23248875ffb2fb673459897e3dcbd67ac0e09ca4cdd738");
+  EXPECT(Hash::leaves({1})[0] == Hash::from_field_elements({1}));
+  // mul.rs:104-119, interpolate.rs:57-77, mod.rs:427-440
+  Polynomial a(wrap({1, 0, 2}, field), field), b(wrap({3, 0, 4}, field), field);
+  EXPECT(raw(Polynomial::mul(a, b).coeffs) == (std::vector<uint64_t>{3, 0, 10, 0, 8}));
+  auto ip = Polynomial::interpolate_domain(wrap({1, 2, 3}, field), wrap({1, 4, 9}, field));
+  EXPECT(raw(ip.coeffs) == (std::vector<uint64_t>{0, 0, 1}));
+  EXPECT(raw(Polynomial(wrap({2, 3}, field), field).scale(field.new_element(5)).coeffs) == (std::vector<uint64_t>{2, 15}));
+  // panics keep the reference's text
+  try { field.inv(field.zero()); EXPECT(false); } catch (const Panic &e) { EXPECT(std::string(e.what()) == "no inverse"); }
+  try { MerkleTree t3(std::vector<Hash>(3)); EXPECT(false); } catch (const Panic &e) { EXPECT(std::string(e.what()) == "Number of leaves must be power of 2"); }
+  try { Fri f(field.prim_nth_root(64), field.new_element(3), 64, 2, 2); EXPECT(false); } catch (const Panic &e) { EXPECT(std::string(e.what()) == "Expansion factor must be at least 4"); }
+  auto cols = lde({std::vector<uint64_t>{1, 1, 2, 3, 5, 8, 13, 21}}, 2, 3);
+  EXPECT(cols[0].size() == 32);
+  printf(fails ? "host_mirror: %d FAILED\n" : "host_mirror: all ok\n", fails);
+  return fails != 0;
+}
