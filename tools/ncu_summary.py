@@ -1,0 +1,42 @@
+#!/usr/bin/env python3
+"""Summarise an .ncu-rep (read here, no GPU needed) into a small CSV kept under profiles/.
+
+usage: tools/ncu_summary.py gpurun_out/prof_x.ncu-rep profiles/r1_x.csv
+One row per profiled launch with the counters DESIGN.md / bench.py quote: duration, DRAM bytes, DRAM %, integer
+pipe utilisation (ALU / FMA), issue utilisation, occupancy, registers, instruction counts, bank conflicts."""
+import csv
+import subprocess
+import sys
+
+WANT = [
+    "Kernel Name", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "smsp__inst_executed.sum", "smsp__thread_inst_executed.sum", "sm__inst_executed.avg.per_cycle_elapsed",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__cycles_active.avg", "sm__cycles_elapsed.max",
+]
+
+
+def main():
+    rep, out = sys.argv[1], sys.argv[2]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    cols = [(w, hdr.index(w)) for w in WANT if w in hdr]
+    with open(out, "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["%s [%s]" % (n, units[i]) if units[i] else n for n, i in cols])
+        for r in rows[2:]:
+            w.writerow([r[i] for _, i in cols])
+    print("wrote %s: %d launches, %d counters" % (out, len(rows) - 2, len(cols)))
+
+
+if __name__ == "__main__":
+    main()
