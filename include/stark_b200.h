@@ -132,6 +132,12 @@ int stark_merkle_build_from_values(stark_ctx *ctx, const uint64_t *vals, size_t 
 /* same, values already on device; column-major [width][n_leaves] when width > 1 (LDE output layout) */
 int stark_merkle_build_from_buf(stark_ctx *ctx, const stark_buf *vals, size_t n_leaves, uint32_t width,
                                 stark_tree **out);
+/* MerkleTree::new over leaf hashes already on the device (sharded prover: the gathered subtree roots) */
+int stark_merkle_build_dev(stark_ctx *ctx, const void *leaves_dev, size_t n, stark_tree **out);
+/* device address of the flattened MerkleTree.nodes (merkle.rs:18-29): level l starts at hash 2n - 2(n >> l) */
+void *stark_merkle_nodes_ptr(const stark_tree *t);
+/* MerkleTree::open (merkle.rs:67-80) for n_idx leaves in one call: out[(q*log2(n) + l)*32 ..] */
+int stark_merkle_open_batch(stark_tree *t, const uint64_t *idx, size_t n_idx, uint8_t *out);
 /* MerkleTree::commit (merkle.rs:44-65): root only */
 int stark_merkle_commit(stark_ctx *ctx, const uint8_t *leaves, size_t n, uint8_t root[32]);
 int stark_merkle_root(stark_tree *t, uint8_t root[32]);                          /* merkle.rs:40-42 */
@@ -151,6 +157,13 @@ int stark_fri_fold(stark_ctx *ctx, const uint64_t *codeword, size_t n, uint64_t 
                    uint64_t omega, uint64_t *out);
 int stark_fri_fold_dev(stark_ctx *ctx, const stark_buf *codeword, size_t n, uint64_t alpha_raw, uint64_t offset,
                        uint64_t omega, stark_buf *out);
+/* one rank's share of Fri::fold_codeword (fri.rs:57-91), SURVEY 8(e): outputs [i0, i0+count) -> out[out_off ..] */
+int stark_fri_fold_range_dev(stark_ctx *ctx, const stark_buf *codeword, size_t n, uint64_t alpha_raw, uint64_t offset,
+                             uint64_t omega, size_t i0, size_t count, stark_buf *out, size_t out_off);
+/* host-side transcript helpers of the sharded prover: FiatShamir::challenge (fiat_shamir.rs:19-25, raw u64) of a
+ * host-held transcript and Hash::from_u64 (hash.rs:37-39, the index seed of fri.rs:272) */
+int stark_fiat_shamir_challenge(const uint8_t *transcript, size_t len, uint64_t *challenge_raw);
+int stark_hash_from_u64(uint64_t value, uint8_t out[32]);
 /* Fri::commit (fri.rs:105-156) entirely on device, Fiat-Shamir included (fiat_shamir.rs:15-25); the
  * transcript starts with `transcript` (may be NULL/0 = FiatShamir::new()).  Keeps every codeword and tree. */
 int stark_fri_commit(stark_ctx *ctx, const uint64_t *codeword, size_t n, uint64_t offset, uint64_t omega,

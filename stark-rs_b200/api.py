@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 __all__ = ["P", "StarkError", "StarkPanic", "Context", "Buffer", "MerkleTree", "FriState", "lib", "lib_path",
-           "build_library", "prim_nth_root", "fri_num_rounds", "fri_proof_size", "fri_sample_indices"]
+           "build_library", "prim_nth_root", "fri_num_rounds", "fri_proof_size", "fri_sample_indices",
+           "fiat_shamir_challenge", "hash_from_u64"]
 
 P = 998244353
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -59,6 +60,7 @@ def lib():
         _lib.stark_merkle_num_leaves.restype = C.c_size_t
         _lib.stark_merkle_num_levels.restype = C.c_uint32
         _lib.stark_fri_rounds.restype = C.c_uint32
+        _lib.stark_merkle_nodes_ptr.restype = C.c_void_p
     return _lib
 
 
@@ -112,6 +114,21 @@ def fri_sample_indices(seed, size, reduced_size, number):
     out = np.zeros(max(number, 1), dtype=np.uint64)
     _chk(lib().stark_fri_sample_indices(_p8(seed), SZ(len(seed)), SZ(size), SZ(reduced_size), SZ(number), _p64(out)))
     return out[:number]
+
+
+def fiat_shamir_challenge(transcript):
+    """FiatShamir::challenge (fiat_shamir.rs:19-25): raw, unreduced u64 of a host-held transcript."""
+    t = _b(transcript)
+    out = U64()
+    _chk(lib().stark_fiat_shamir_challenge(_p8(t), SZ(len(t)), C.byref(out)))
+    return out.value
+
+
+def hash_from_u64(value):
+    """Hash::from_u64 (hash.rs:37-39), host side (the index seed of fri.rs:272)."""
+    out = np.empty(32, dtype=np.uint8)
+    _chk(lib().stark_hash_from_u64(U64(value), _p8(out)))
+    return out.tobytes()
 
 
 class Buffer:
@@ -177,6 +194,23 @@ class MerkleTree:
         n = SZ()
         _chk(lib().stark_merkle_open(self.h, SZ(index), _p8(out), C.byref(n)))
         return out[: n.value].copy()
+
+    def open_batch(self, indices):
+        """MerkleTree::open for many leaves: (len(indices), log2 n, 32) uint8"""
+        idx = _u64(indices)
+        depth = self.num_levels - 1
+        out = np.zeros((len(idx), depth, 32), dtype=np.uint8)
+        _chk(lib().stark_merkle_open_batch(self.h, _p64(idx), SZ(len(idx)), _p8(out)))
+        return out
+
+    @property
+    def nodes_ptr(self):
+        """device address of the flattened node array (level l at hash offset 2n - 2(n >> l))"""
+        return lib().stark_merkle_nodes_ptr(self.h)
+
+    @property
+    def root_ptr(self):
+        return self.nodes_ptr + 32 * (2 * self.num_leaves - 2)
 
     def free(self):
         if self.h:
@@ -450,6 +484,12 @@ class Context:
         _chk(lib().stark_merkle_build_from_buf(self.h, buf.h, SZ(n_leaves), U32(width), C.byref(h)))
         return MerkleTree(self, h)
 
+    def merkle_build_dev(self, leaves_dev_ptr, n):
+        """MerkleTree::new over n leaf hashes already on the device"""
+        h = C.c_void_p()
+        _chk(lib().stark_merkle_build_dev(self.h, C.c_void_p(leaves_dev_ptr), SZ(n), C.byref(h)))
+        return MerkleTree(self, h)
+
     def merkle_commit(self, leaves):
         l = np.ascontiguousarray(leaves, dtype=np.uint8).reshape(-1, 32)
         out = np.empty(32, dtype=np.uint8)
@@ -467,6 +507,12 @@ class Context:
         out = out or self.alloc(n // 2)
         _chk(lib().stark_fri_fold_dev(self.h, cw_buf.h, SZ(n), U64(alpha_raw), U64(offset), U64(omega), out.h))
         return out
+
+    def fri_fold_range_dev(self, cw_buf, n, alpha_raw, offset, omega, i0, count, out_buf, out_off=0):
+        """outputs [i0, i0+count) of fold_codeword into out_buf[out_off:]"""
+        _chk(lib().stark_fri_fold_range_dev(self.h, cw_buf.h, SZ(n), U64(alpha_raw), U64(offset), U64(omega), SZ(i0),
+                                            SZ(count), out_buf.h, SZ(out_off)))
+        return out_buf
 
     def fri_commit(self, codeword, offset, omega, expansion_factor, num_colinearity_tests, transcript=b""):
         cw, t = _u64(codeword), _b(transcript)

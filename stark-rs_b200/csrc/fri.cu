@@ -95,13 +95,15 @@ __global__ void k_transcript_challenge(const TranscriptDev *T, u64 *out) {
 // ---------------------------------------------------------------------------------------------- fold
 
 // V outputs per thread (128-bit accesses for V = 4).  tw(i) = K * g_r^i, g_r^i = g0^(i << r).
+// Outputs [i0, i1) of the fold of a codeword of length 2h (the whole fold is i0 = 0, i1 = h; a rank of the sharded
+// prover folds only its own output range); out is indexed by the GLOBAL output index i.
 template <int V>
-__global__ void __launch_bounds__(256) k_fri_fold(const u32 *__restrict__ cw, u32 *__restrict__ out, size_t h, int r,
-                                                  GeoTables G, u32 g_r_m, const u32 *__restrict__ alpha_m,
-                                                  u32 inv2off_m) {
+__global__ void __launch_bounds__(256) k_fri_fold(const u32 *__restrict__ cw, u32 *__restrict__ out, size_t h, size_t i0,
+                                                  size_t i1, int r, GeoTables G, u32 g_r_m,
+                                                  const u32 *__restrict__ alpha_m, u32 inv2off_m) {
   const u32 K = ff::canon(ff::mont_mul(*alpha_m, inv2off_m));
   const size_t stride = (size_t)gridDim.x * blockDim.x * V;
-  for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * V; i < h; i += stride) {
+  for (size_t i = i0 + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * V; i < i1; i += stride) {
     u32 a[V], b[V], o[V];
     if constexpr (V == 4) {
       const uint4 x = *reinterpret_cast<const uint4 *>(cw + i), y = *reinterpret_cast<const uint4 *>(cw + h + i);
@@ -274,18 +276,24 @@ static void fri_state_free(stark_fri_state *s) {
   delete s;
 }
 
-static int fold_launch(stark_ctx *ctx, const u32 *cw, u32 *out, size_t h, int r, GeoTables G, u32 g_r_m,
-                       const u32 *alpha_m, u32 inv2off_m) {
-  if (h == 0) return STARK_OK;
-  if (h % 4 == 0) {
-    size_t blocks = (h / 4 + 255) / 256, cap = (size_t)ctx->sm_count * 8;
-    LAUNCH(ctx, "fri_fold", 12ull * h,
-           k_fri_fold<4><<<(u32)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(cw, out, h, r, G, g_r_m, alpha_m, inv2off_m));
+// out is indexed by the global output index (out[i] for i in [i0, i1))
+static int fold_launch_range(stark_ctx *ctx, const u32 *cw, u32 *out, size_t h, size_t i0, size_t i1, int r, GeoTables G,
+                             u32 g_r_m, const u32 *alpha_m, u32 inv2off_m) {
+  if (i1 <= i0) return STARK_OK;
+  const size_t cnt = i1 - i0;
+  if (h % 4 == 0 && i0 % 4 == 0 && cnt % 4 == 0) {
+    size_t blocks = (cnt / 4 + 255) / 256, cap = (size_t)ctx->sm_count * 8;
+    LAUNCH(ctx, "fri_fold", 12ull * cnt,
+           k_fri_fold<4><<<(u32)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(cw, out, h, i0, i1, r, G, g_r_m, alpha_m, inv2off_m));
   } else {
-    LAUNCH(ctx, "fri_fold", 12ull * h,
-           k_fri_fold<1><<<(u32)((h + 255) / 256), 256, 0, ctx->stream>>>(cw, out, h, r, G, g_r_m, alpha_m, inv2off_m));
+    LAUNCH(ctx, "fri_fold", 12ull * cnt,
+           k_fri_fold<1><<<(u32)((cnt + 255) / 256), 256, 0, ctx->stream>>>(cw, out, h, i0, i1, r, G, g_r_m, alpha_m, inv2off_m));
   }
   return STARK_OK;
+}
+static int fold_launch(stark_ctx *ctx, const u32 *cw, u32 *out, size_t h, int r, GeoTables G, u32 g_r_m,
+                       const u32 *alpha_m, u32 inv2off_m) {
+  return fold_launch_range(ctx, cw, out, h, 0, h, r, G, g_r_m, alpha_m, inv2off_m);
 }
 
 // Fri::commit (fri.rs:105-156) on device.  cw0 is borrowed unless copy0.
@@ -477,6 +485,51 @@ int stark_fri_fold_dev(stark_ctx *ctx, const stark_buf *codeword, size_t n, uint
                        ff::to_mont(ff::inv(ff::mul(2, off))));
   dev_free(ctx, d_alpha);
   return rc;
+}
+
+// one rank's share of fold_codeword (fri.rs:57-91): outputs [i0, i0 + count) written to out[out_off ..]
+int stark_fri_fold_range_dev(stark_ctx *ctx, const stark_buf *codeword, size_t n, uint64_t alpha_raw, uint64_t offset,
+                             uint64_t omega, size_t i0, size_t count, stark_buf *out, size_t out_off) {
+  if (!ctx || !codeword || !out) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+  const size_t h = n / 2;
+  if (codeword->n < n || i0 + count > h || out->n < out_off + count) return stark_fail(ctx, STARK_ERR_ARG, "range out of bounds");
+  if (count == 0) return STARK_OK;
+  u32 off, om;
+  reduce_params(ctx, offset, omega, &off, &om);
+  if (off == 0 || (om == 0 && h > 1)) return stark_fail(ctx, STARK_ERR_ARG, "no division by zero");  // ff.rs:182
+  const u32 g0 = om ? ff::inv(om) : 1u;
+  GeoTables G;
+  ST_TRY(geo_tables(ctx, g0, 1, h, &G));
+  u32 *d_alpha = nullptr;
+  ST_TRY(dev_alloc(ctx, (void **)&d_alpha, 4));
+  const u32 am = ff::to_mont(ff::reduce64(alpha_raw));
+  CU_TRY(ctx, cudaMemcpyAsync(d_alpha, &am, 4, cudaMemcpyHostToDevice, ctx->stream));
+  // the kernel indexes out by the global output index
+  u32 *base = out->ptr + out_off;
+  int rc = fold_launch_range(ctx, codeword->ptr, base - i0, h, i0, i0 + count, 0, G, ff::to_mont(g0), d_alpha,
+                             ff::to_mont(ff::inv(ff::mul(2, off))));
+  dev_free(ctx, d_alpha);
+  return rc;
+}
+
+// FiatShamir::challenge (fiat_shamir.rs:19-25) for a host-held transcript: first 8 bytes, little-endian, of
+// Hash::from_bytes(transcript), UNREDUCED.  Host logic of the sharded prover (32 R bytes per proof).
+int stark_fiat_shamir_challenge(const uint8_t *transcript, size_t len, uint64_t *challenge_raw) {
+  if ((!transcript && len) || !challenge_raw) return stark_fail(nullptr, STARK_ERR_ARG, "null argument");
+  u8 h[32];
+  hs::from_bytes(transcript, len, h);
+  u64 v = 0;
+  for (int b = 0; b < 8; b++) v |= (u64)h[b] << (8 * b);
+  *challenge_raw = v;
+  return STARK_OK;
+}
+// Hash::from_u64 (hash.rs:37-39) on the host: the index seed of fri.rs:272
+int stark_hash_from_u64(uint64_t value, uint8_t out[32]) {
+  if (!out) return stark_fail(nullptr, STARK_ERR_ARG, "null argument");
+  u8 m[8];
+  for (int b = 0; b < 8; b++) m[b] = (u8)(value >> (8 * b));
+  hs::from_bytes(m, 8, out);
+  return STARK_OK;
 }
 
 int stark_fri_fold(stark_ctx *ctx, const uint64_t *codeword, size_t n, uint64_t alpha_raw, uint64_t offset,

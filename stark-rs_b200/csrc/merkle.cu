@@ -314,6 +314,47 @@ int stark_merkle_build_from_buf(stark_ctx *ctx, const stark_buf *vals, size_t n_
   return merkle_build_from_dev_values(ctx, (const u32 *)stark_buf_ptr(vals), n_leaves, width, 1, n_leaves, out);
 }
 
+// MerkleTree::new (merkle.rs:11-38) over leaves that are already on the device (e.g. the gathered subtree roots of
+// the sharded prover)
+int stark_merkle_build_dev(stark_ctx *ctx, const void *leaves_dev, size_t n, stark_tree **out) {
+  if (!ctx || !out || !leaves_dev) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+  stark_tree *t = nullptr;
+  ST_TRY(merkle_tree_alloc(ctx, n, &t));
+  int rc = STARK_OK;
+  if (cudaMemcpyAsync(t->nodes, leaves_dev, n * 32, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess)
+    rc = stark_fail(ctx, STARK_ERR_CUDA, "D2D copy failed");
+  if (rc == STARK_OK) rc = merkle_climb_dev(ctx, t->nodes, n);
+  if (rc != STARK_OK) {
+    stark_merkle_free(t);
+    return rc;
+  }
+  *out = t;
+  return STARK_OK;
+}
+
+// device address of the flattened node array: level l (n >> l hashes) starts at hash offset 2n - 2(n >> l)
+void *stark_merkle_nodes_ptr(const stark_tree *t) { return t ? (void *)t->nodes : nullptr; }
+
+// MerkleTree::open (merkle.rs:67-80) for n_idx leaves at once: out[(q*depth + l)*32 ..] = sibling at level l
+int stark_merkle_open_batch(stark_tree *t, const uint64_t *idx, size_t n_idx, uint8_t *out) {
+  if (!t || (n_idx && (!idx || !out))) return stark_fail(nullptr, STARK_ERR_ARG, "null argument");
+  stark_ctx *ctx = t->ctx;
+  for (size_t i = 0; i < n_idx; i++)
+    if (idx[i] >= t->n) return stark_fail(ctx, STARK_ERR_ARG, "Index out of bounds");  // merkle.rs:68
+  const u32 depth = t->levels - 1;
+  if (depth == 0 || n_idx == 0) return STARK_OK;
+  u64 *d_idx = nullptr;
+  u8 *d_out = nullptr;
+  ST_TRY(dev_alloc(ctx, (void **)&d_idx, 8 * n_idx));
+  ST_TRY(dev_alloc(ctx, (void **)&d_out, 32 * (size_t)depth * n_idx));
+  CU_TRY(ctx, cudaMemcpyAsync(d_idx, idx, 8 * n_idx, cudaMemcpyHostToDevice, ctx->stream));
+  ST_TRY(merkle_open_dev(ctx, t->nodes, t->n, d_idx, (u32)n_idx, d_out));
+  CU_TRY(ctx, cudaMemcpyAsync(out, d_out, 32 * (size_t)depth * n_idx, cudaMemcpyDeviceToHost, ctx->stream));
+  dev_free(ctx, d_idx), dev_free(ctx, d_out);
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return STARK_OK;
+}
+
 int stark_merkle_commit(stark_ctx *ctx, const uint8_t *leaves, size_t n, uint8_t root[32]) {
   stark_tree *t = nullptr;
   ST_TRY(stark_merkle_build(ctx, leaves, n, &t));

@@ -11,6 +11,7 @@
 //        pass 2: N2-point transforms over n2 at stride N1, in place, X[k2*N1 + k1] -- natural order.
 //   HBM traffic: 8N bytes per pass (4 read + 4 written), nothing else (twiddle tables are <= 48 KB, L1/L2).
 #include "common.cuh"
+#include "ntt_pass.cuh"
 
 using namespace ntt;
 
@@ -172,6 +173,30 @@ __global__ void __launch_bounds__(1024, 1) k_ntt_pass(const __grid_constant__ Pa
   }
 }
 
+// N >= 2^13: one multi-pass Stockham pass (ntt_pass.cuh).  8192-element tile, 256 threads, 32 KB of shared memory.
+template <int LOGR, int KIND>
+__global__ void __launch_bounds__(ntt2::NT, 4) k_ntt2_pass(const __grid_constant__ ntt2::PassParams A) {
+  using namespace ntt2;
+  typedef Plan<LOGR> PL;
+  __shared__ __align__(16) q4 tile[1 << (TILE_LOG - 2)];
+  __shared__ u32 otw[KIND == MIDDLE ? (1 << LOGR) : 1];
+  const u32 tid = threadIdx.x;
+  const TileCtx T = tile_ctx<LOGR>(A, blockIdx.x);
+  if (KIND == MIDDLE) fill_outer_table<LOGR>(tid, A, T, otw);
+  u32 regs[32];
+  round_compute<LOGR, KIND, 0>(tid, A, T, tile, otw, regs);
+  round_store<LOGR, KIND, 0>(tid, A, T, tile, regs);
+  __syncthreads();
+  if constexpr (PL::NR == 3) {
+    round_compute<LOGR, KIND, 1>(tid, A, T, tile, otw, regs);
+    __syncthreads();
+    round_store<LOGR, KIND, 1>(tid, A, T, tile, regs);
+    __syncthreads();
+  }
+  round_compute<LOGR, KIND, PL::NR - 1>(tid, A, T, tile, otw, regs);
+  round_store<LOGR, KIND, PL::NR - 1>(tid, A, T, tile, regs);
+}
+
 // ----------------------------------------------------------------------------------------- launcher
 
 static int resolve_scale(stark_ctx *ctx, const ScaleSpec &s, u64 max_index, int *mode, u32 *c_m, GeoTables *geo) {
@@ -260,43 +285,54 @@ int ntt_transform(stark_ctx *ctx, const u32 *in, u32 *out, int log_n, bool inver
     return launch_pass<1, false>(ctx, A, batch, "ntt_single", 4ull * batch * (n_valid + N));
   }
 
-  // two passes.  pass 1 cannot run in place (it transposes), so in == out goes through a scratch copy.
-  const int log_n1 = log_n / 2, log_n2 = log_n - log_n1;
-  const u64 N1 = 1ull << log_n1, N2 = 1ull << log_n2;
+  // N >= 2^13: 2 or 3 Stockham passes with radices 2^6 .. 2^9 (ntt_pass.cuh)
+  int plan[3];
+  const int n_pass = ntt2::pass_plan(log_n, plan);
+  // FIRST and MIDDLE passes are out of place, the LAST pass may run in place:
+  //   2 passes: in -> out -> out           (in == out: in -> tmp -> out)
+  //   3 passes: in -> tmp -> out -> out
   u32 *tmp = nullptr;
+  const bool need_tmp = n_pass == 3 || in == out;
+  if (need_tmp) ST_TRY(dev_alloc(ctx, (void **)&tmp, (size_t)batch * N * 4));
+  ntt2::PassParams B;
+  memset(&B, 0, sizeof B);
+  B.logN = log_n, B.log_tiles = log_n - ntt2::TILE_LOG;
+  B.roots = roots, B.inverse = d;
+  for (int k = 0; k < 4; k++) B.w8[k] = ctx->w8[d][k];
+  const u32 grid = batch << B.log_tiles;
   const u32 *src = in;
-  if (in == out) {
-    ST_TRY(dev_alloc(ctx, (void **)&tmp, (size_t)batch * N * 4));
-    CU_TRY(ctx, cudaMemcpy2DAsync(tmp, N * 4, in, in_batch * 4, N * 4, batch, cudaMemcpyDeviceToDevice, ctx->stream));
-    src = tmp;
-    in_batch = N;
-  }
-  {  // pass 1: L = N1, columns n2 (stride N2), row-mode (transposed) store + four-step twiddle
-    PassArgs B = A;
-    B.in = src, B.out = out;
-    B.logL = log_n1;
-    int logC = log_n2 < (15 - log_n1) ? log_n2 : (15 - log_n1);  // tile <= 32K elements
-    B.logC4 = logC - 2;
-    B.in_batch = in_batch, B.in_stride = N2, B.n_valid = n_valid;
-    B.out_batch = out_batch, B.out_stride = 0;
-    B.tiles_per_batch = (int)(N2 >> logC);
-    B.tw = ctx->tw_sub[d] + (1u << log_n1);
-    B.post_mode = SCALE_NONE;
-    ST_TRY((launch_pass<4, true>(ctx, B, batch * (u32)B.tiles_per_batch, "ntt_pass1", 4ull * batch * (n_valid + N))));
-  }
-  {  // pass 2: L = N2, columns k1 (stride N1), in place on out
-    PassArgs B = A;
-    B.in = out, B.out = out;
-    B.logL = log_n2;
-    int logC = log_n1 < (15 - log_n2) ? log_n1 : (15 - log_n2);
-    B.logC4 = logC - 2;
-    B.in_batch = out_batch, B.in_stride = N1, B.n_valid = N;
-    B.out_batch = out_batch, B.out_stride = N1;
-    B.tiles_per_batch = (int)(N1 >> logC);
-    B.tw = ctx->tw_sub[d] + (1u << log_n2);
-    B.pre_mode = SCALE_NONE;
-    ST_TRY((launch_pass<4, false>(ctx, B, batch * (u32)B.tiles_per_batch, "ntt_pass2", 8ull * batch * N)));
+  u64 src_batch = in_batch;
+  int logS = 0, rc = STARK_OK;
+  for (int i = 0; i < n_pass && rc == STARK_OK; i++) {
+    const int r = plan[i];
+    const int kind = i == 0 ? ntt2::FIRST : (i == n_pass - 1 ? ntt2::LAST : ntt2::MIDDLE);
+    u32 *dst;
+    u64 dst_batch;
+    if (kind == ntt2::LAST || (kind == ntt2::MIDDLE) || (n_pass == 2 && !need_tmp))
+      dst = out, dst_batch = out_batch;
+    else
+      dst = tmp, dst_batch = N;
+    B.in = src, B.out = dst, B.in_batch = src_batch, B.out_batch = dst_batch;
+    B.n_valid = kind == ntt2::FIRST ? n_valid : N;
+    B.logS = logS;
+    B.tw_in = ctx->tw_sub[d] + (1u << r);
+    if (kind == ntt2::FIRST) ntt2::fill_first_pass_constants(B, r);
+    B.pre_mode = kind == ntt2::FIRST ? pre_mode : (int)SCALE_NONE, B.pre_geo = pre_geo;
+    B.post_mode = kind == ntt2::LAST ? post_mode : (int)SCALE_NONE, B.post_const = post_c, B.post_geo = post_geo;
+    const u64 bytes = kind == ntt2::FIRST ? 4ull * batch * (n_valid + N) : 8ull * batch * N;
+    const char *tag = kind == ntt2::FIRST ? "ntt_pass1" : (kind == ntt2::LAST ? "ntt_pass_last" : "ntt_pass_mid");
+#define NTT2_CASE(R_, K_)                                                                                        \
+  if (r == R_ && kind == K_) {                                                                                   \
+    LAUNCH(ctx, tag, bytes, (k_ntt2_pass<R_, K_><<<grid, ntt2::NT, 0, ctx->stream>>>(B)));                       \
+  } else
+    NTT2_CASE(6, ntt2::FIRST) NTT2_CASE(7, ntt2::FIRST) NTT2_CASE(8, ntt2::FIRST) NTT2_CASE(9, ntt2::FIRST)
+    NTT2_CASE(6, ntt2::MIDDLE) NTT2_CASE(7, ntt2::MIDDLE) NTT2_CASE(8, ntt2::MIDDLE) NTT2_CASE(9, ntt2::MIDDLE)
+    NTT2_CASE(6, ntt2::LAST) NTT2_CASE(7, ntt2::LAST) NTT2_CASE(8, ntt2::LAST) NTT2_CASE(9, ntt2::LAST)
+    rc = stark_fail(ctx, STARK_ERR_ARG, "no NTT pass kernel for radix 2^%d", r);
+#undef NTT2_CASE
+    src = dst, src_batch = dst_batch;
+    logS += r;
   }
   dev_free(ctx, tmp);
-  return STARK_OK;
+  return rc;
 }

@@ -1,0 +1,303 @@
+// ntt_pass.cuh -- multi-pass Stockham NTT for N >= 2^13 (host+device inline, so tests/emul can run it on the CPU).
+//
+// Replaces Polynomial::eval_domain / interpolate_domain on structured domains (reference
+// src/univariate/eval.rs:16-21, interpolate.rs:6-44), natural order in and out.
+//
+// The transform is a radix-R_1, R_2(, R_3) decimation-in-frequency Stockham (autosort) FFT, one HBM/L2 PASS per
+// factor, R_i = 2^6 .. 2^9.  Pass i (s = R_1..R_{i-1}, M = N/R_i, u = q + s p with q < s):
+//     in_j  = X[u + j M]                          j < R_i
+//     out_k = Y[q + s (R_i p + k)] = (sum_j in_j w_R^(jk)) * w_N^(s p k)
+// A CTA owns a TILE of R rows x C = 2^13/R adjacent columns u (8192 elements, 32 KB of shared memory, 256 threads,
+// 32 elements per thread), so 4-6 CTAs are resident per SM and one CTA's barriers hide behind the others' work.
+// Inside the tile the R-point column DFTs are again Stockham rounds (radix 8, plus one radix-2/4 round when
+// log2 R is not a multiple of 3) on registers: a thread holds an 8-row x 4-column block, does the butterflies there
+// and exchanges through shared memory between rounds.  The first round reads HBM directly (128-bit, coalesced along
+// the columns), the last round writes HBM directly.
+//   FIRST  pass (s = 1):    every column has its own p = u, so the outer twiddle w_N^(u k) is per element (the
+//                           "four-step" twiddle); the tile's output Y[R u + k] is one contiguous R*C block.
+//   MIDDLE pass:            the C columns share p, the outer twiddle is a per-row table in shared memory.
+//   LAST   pass (s = N/R):  no outer twiddle; fused post-scale (n^-1, or n^-1 * g^i for the coset); runs in place.
+// All shapes are template parameters: the index arithmetic folds to shifts and constants.
+#pragma once
+#include "ntt_core.cuh"
+
+namespace ntt2 {
+using ff::u32;
+using ff::u64;
+using ntt::GeoTables;
+using ntt::q4;
+using ntt::RootTables;
+
+enum Kind { FIRST = 0, MIDDLE = 1, LAST = 2 };
+constexpr int TILE_LOG = 13;   // elements per tile
+constexpr int NT = 256;        // threads per CTA
+
+struct PassParams {
+  const u32 *in;
+  u32 *out;
+  u64 in_batch, out_batch;   // element stride between the transforms of a batch
+  u64 n_valid;               // FIRST: inputs at coefficient index >= n_valid are zero and are not read
+  int logN;                  // transform length
+  int logS;                  // s = product of the previous passes' radices
+  int log_tiles;             // tiles per transform = 2^(logN - 13)
+  const u32 *tw_in;          // tw_in[e] = w_R^(+-e), e < R, Montgomery form, canonical
+  u32 w8[4];                 // 1, w_8, w_8^2, w_8^3 in the pass direction (Montgomery form)
+  RootTables roots;          // w_{2^23}^e two-level table
+  int inverse;
+  int pre_mode;              // FIRST: ntt::ScaleMode on loaded elements (index = coefficient index)
+  GeoTables pre_geo;
+  int post_mode;             // LAST: ntt::ScaleMode on stored elements (index = output index)
+  u32 post_const;            // Montgomery form
+  GeoTables post_geo;
+  u32 dpow[8];               // FIRST: w_N^(+-(R/8) k), k < 8, Montgomery form (see round_compute)
+};
+
+// pass radices (log2) for a transform of length 2^log_n, 13 <= log_n <= 23, largest first: its narrow 64-byte row
+// segments then only affect loads (the FIRST pass stores one contiguous block per tile).  Returns the pass count.
+inline int pass_plan(int log_n, int *r) {
+  static const int PLAN[11][3] = {{7, 6, 0}, {8, 6, 0}, {9, 6, 0}, {9, 7, 0}, {9, 8, 0}, {9, 9, 0},
+                                  {7, 6, 6}, {8, 6, 6}, {9, 6, 6}, {9, 7, 6}, {9, 8, 6}};
+  for (int i = 0; i < 3; i++) r[i] = PLAN[log_n - 13][i];
+  return r[2] ? 3 : 2;
+}
+
+// host side: the pass constants that depend on (log N, radix, direction)
+inline void fill_first_pass_constants(PassParams &A, int log_r) {
+  u32 w = ff::pow(ff::GEN, (ff::P - 1) >> (A.logN - log_r + 3));   // w_N^(R/8), ff.rs:215-223
+  if (A.inverse) w = ff::inv(w);
+  const u32 wm = ff::to_mont(w);
+  A.dpow[0] = ff::R1;
+  for (int k = 1; k < 8; k++) A.dpow[k] = ff::canon(ff::mont_mul(A.dpow[k - 1], wm));
+}
+
+template <int LOGR>
+struct Plan {
+  static constexpr int B0 = LOGR % 3;
+  static constexpr int NR = LOGR / 3 + (B0 ? 1 : 0);
+  FF_HD static constexpr int lr(int r) { return (r == 0 && B0) ? B0 : 3; }
+  FF_HD static constexpr int logs(int r) {
+    int s = 0;
+    for (int i = 0; i < r; i++) s += lr(i);
+    return s;
+  }
+};
+
+// shared-memory slot (16 bytes = 4 adjacent columns of one row) of (row l, column quad c4).  A 128-bit access is
+// served per quarter-warp, conflict-free when its 8 lanes hit 8 distinct slots mod 8; the XOR keeps that true for the
+// column-fastest (same row) and the row-fastest (8 adjacent rows, same quad) lane mappings used below.
+template <int LOGC4>
+FF_HD u32 slot(u32 l, u32 c4) {
+  if (LOGC4 >= 3) return (l << LOGC4) + (c4 ^ (l & 7u));
+  const u32 sr = l >> 1, pos = ((l & 1u) << 2) | c4;   // LOGC4 == 2: two rows form one 8-slot group
+  return (sr << 3) + (pos ^ (sr & 7u));
+}
+
+// radix-2^LR DIF on a[0 .. 2^LR) in [0, 2p); a[pos] ends up holding output bitrev(pos).  The outputs are LAZY, in
+// [0, 4p): the caller either multiplies them by a canonical twiddle (-> [0, 2p)) or reduces them.
+template <int LR>
+FF_HD void dif_lazy(u32 *a, const u32 *w8) {
+  constexpr int R = 1 << LR;
+#pragma unroll
+  for (int len = R; len >= 2; len >>= 1) {
+    const int h = len >> 1;
+    const bool final_stage = len == 2;
+#pragma unroll
+    for (int blk = 0; blk < R; blk += len) {
+#pragma unroll
+      for (int j = 0; j < h; j++) {
+        const u32 u = a[blk + j], v = a[blk + j + h];
+        const u32 s = u + v, d = u + ff::P2 - v;
+        if (final_stage) {
+          a[blk + j] = s, a[blk + j + h] = d;
+        } else {
+          a[blk + j] = ff::red2p(s);
+          a[blk + j + h] = (j == 0) ? ff::red2p(d) : ff::mont_mul(d, w8[j * (8 / len)]);
+        }
+      }
+    }
+  }
+}
+template <int LR>
+FF_HD constexpr int bitrev(int i) {
+  int r = 0;
+  for (int b = 0; b < LR; b++) r |= ((i >> b) & 1) << (LR - 1 - b);
+  return r;
+}
+
+struct TileCtx {
+  const u32 *in;   // + batch offset
+  u32 *out;        // + batch offset
+  u32 col0;        // first column u of the tile
+  u32 q0, p;       // col0 = q0 + s p
+};
+
+template <int LOGR>
+FF_HD TileCtx tile_ctx(const PassParams &A, u32 tile) {
+  constexpr int LOGC = TILE_LOG - LOGR;
+  TileCtx T;
+  const u32 b = tile >> A.log_tiles, ct = tile & ((1u << A.log_tiles) - 1u);
+  T.in = A.in + (u64)b * A.in_batch;
+  T.out = A.out + (u64)b * A.out_batch;
+  T.col0 = ct << LOGC;
+  T.q0 = T.col0 & ((1u << A.logS) - 1u);
+  T.p = T.col0 >> A.logS;
+  return T;
+}
+
+// w_N^(+-e) for e < N
+FF_HD u32 root_n(const PassParams &A, u32 e) {
+  u32 e23 = e << (23 - A.logN);
+  if (A.inverse) e23 = ((1u << 23) - e23) & ((1u << 23) - 1u);
+  return ntt::root_pow(A.roots, e23);
+}
+
+// MIDDLE: otw[k] = w_N^(+-(s p k)), k < R  (per-tile table in shared memory; s p k < N)
+template <int LOGR>
+FF_HD void fill_outer_table(u32 tid, const PassParams &A, const TileCtx &T, u32 *otw) {
+  for (u32 k = tid; k < (1u << LOGR); k += NT) otw[k] = root_n(A, (T.p * k) << A.logS);
+}
+
+// task -> (row group u', column quad c4).  Column-fastest: adjacent lanes touch adjacent 16-byte slots of one row.
+// Row-fastest (only the last round of a FIRST pass): adjacent lanes own adjacent output rows, which are adjacent
+// addresses of the transposed store.
+template <int LOGR, int LR, bool ROWFAST>
+FF_HD void decode(u32 t, u32 &up, u32 &c4) {
+  constexpr int LOGC4 = TILE_LOG - LOGR - 2;
+  if (ROWFAST) {
+    up = t & ((1u << (LOGR - LR)) - 1u);
+    c4 = t >> (LOGR - LR);
+  } else {
+    c4 = t & ((1u << LOGC4) - 1u);
+    up = t >> LOGC4;
+  }
+}
+
+// Phase A of round ROUND: gather the inputs (HBM in round 0, shared memory afterwards), butterflies, twiddles.
+// regs[(i*4 + x)*RAD + k] = output k of column x of task i.
+template <int LOGR, int KIND, int ROUND>
+FF_HD void round_compute(u32 tid, const PassParams &A, const TileCtx &T, const q4 *smem, const u32 *otw, u32 *regs) {
+  typedef Plan<LOGR> PL;
+  constexpr int LR = PL::lr(ROUND), LOGS = PL::logs(ROUND), RAD = 1 << LR, NTASK = 8 >> LR;
+  constexpr int LOGC4 = TILE_LOG - LOGR - 2;
+  constexpr bool LASTR = ROUND == PL::NR - 1;
+  constexpr bool ROWFAST = LASTR && KIND == FIRST;
+  const int logM = A.logN - LOGR;
+#pragma unroll
+  for (int i = 0; i < NTASK; i++) {
+    u32 up, c4;
+    decode<LOGR, LR, ROWFAST>(tid + (u32)i * NT, up, c4);
+    u32 a[4][RAD];
+#pragma unroll
+    for (int j = 0; j < RAD; j++) {
+      const u32 l = up + ((u32)j << (LOGR - LR));
+      q4 v;
+      if (ROUND == 0) {
+        const u64 cidx = ((u64)l << logM) + T.col0 + 4u * c4;   // coefficient index of the quad's first element
+        if (KIND != FIRST || cidx + 4 <= A.n_valid) {
+          v = *reinterpret_cast<const q4 *>(T.in + cidx);
+        } else if (cidx >= A.n_valid) {
+          v.x = v.y = v.z = v.w = 0u;   // zero padding is never read
+        } else {
+          v.x = T.in[cidx];
+          v.y = cidx + 1 < A.n_valid ? T.in[cidx + 1] : 0u;
+          v.z = cidx + 2 < A.n_valid ? T.in[cidx + 2] : 0u;
+          v.w = 0u;
+        }
+        if (KIND == FIRST && A.pre_mode == ntt::SCALE_GEO) {
+          v.x = ff::mont_mul(v.x, ntt::geo_pow(A.pre_geo, cidx + 0));
+          v.y = ff::mont_mul(v.y, ntt::geo_pow(A.pre_geo, cidx + 1));
+          v.z = ff::mont_mul(v.z, ntt::geo_pow(A.pre_geo, cidx + 2));
+          v.w = ff::mont_mul(v.w, ntt::geo_pow(A.pre_geo, cidx + 3));
+        }
+      } else {
+        v = smem[slot<LOGC4>(l, c4)];
+      }
+      a[0][j] = v.x, a[1][j] = v.y, a[2][j] = v.z, a[3][j] = v.w;
+    }
+    // inner twiddles w_R^(s' p' k), shared by the four columns (the last round has p' = 0: none)
+    u32 tw[RAD], step[RAD];
+    if (!LASTR) {
+      const u32 pp = up >> LOGS;
+#pragma unroll
+      for (int k = 1; k < RAD; k++) tw[k] = A.tw_in[(pp * (u32)k) << LOGS];
+    } else if (KIND == FIRST) {
+      // outer ("four-step") twiddle of element (column cb + x, row up + S' k), S' = R/8:
+      //   w^((cb + x)(up + S' k)) = [w^(cb up) (w^(cb S'))^k] * [w^up (w^S')^k]^x
+      // three table look-ups per thread, then geometric steps: tw[k] walks along x with ratio step[k].
+      const u32 cb = T.col0 + 4u * c4;
+      const u32 wa = root_n(A, cb * up), wc = root_n(A, cb << LOGS), wb = root_n(A, up);
+      tw[0] = wa, step[0] = wb;
+#pragma unroll
+      for (int k = 1; k < RAD; k++) {
+        tw[k] = ff::canon(ff::mont_mul(tw[k - 1], wc));
+        step[k] = ff::canon(ff::mont_mul(wb, A.dpow[k]));
+      }
+    }
+#pragma unroll
+    for (int x = 0; x < 4; x++) {
+      dif_lazy<LR>(a[x], A.w8);
+#pragma unroll
+      for (int pos = 0; pos < RAD; pos++) {
+        const int k = bitrev<LR>(pos);
+        u32 val = a[x][pos];
+        if (!LASTR) {
+          val = k ? ff::mont_mul(val, tw[k]) : ff::red2p(val);
+        } else {
+          const u32 row = up + ((u32)k << LOGS);   // output row of the R-point DFT (p' = 0, q' = u')
+          if (KIND == FIRST) {
+            val = ff::mont_mul(val, tw[k]);
+            if (x < 3) tw[k] = ff::canon(ff::mont_mul(tw[k], step[k]));
+          } else if (KIND == MIDDLE) {
+            val = ff::mont_mul(val, otw[row]);
+          } else {
+            if (A.post_mode == ntt::SCALE_CONST) {
+              val = ff::canon(ff::mont_mul(val, A.post_const));
+            } else if (A.post_mode == ntt::SCALE_GEO) {
+              const u64 oidx = (u64)T.col0 + 4u * c4 + (u32)x + ((u64)row << A.logS);
+              val = ff::canon(ff::mont_mul(val, ntt::geo_pow(A.post_geo, oidx)));
+            } else {
+              val = ff::canon4(val);
+            }
+          }
+        }
+        regs[(i * 4 + x) * RAD + k] = val;
+      }
+    }
+  }
+}
+
+// Phase B of round ROUND: scatter the register block (shared memory, or HBM in the last round)
+template <int LOGR, int KIND, int ROUND>
+FF_HD void round_store(u32 tid, const PassParams &A, const TileCtx &T, q4 *smem, const u32 *regs) {
+  typedef Plan<LOGR> PL;
+  constexpr int LR = PL::lr(ROUND), LOGS = PL::logs(ROUND), RAD = 1 << LR, NTASK = 8 >> LR;
+  constexpr int LOGC4 = TILE_LOG - LOGR - 2;
+  constexpr bool LASTR = ROUND == PL::NR - 1;
+  constexpr bool ROWFAST = LASTR && KIND == FIRST;
+#pragma unroll
+  for (int i = 0; i < NTASK; i++) {
+    u32 up, c4;
+    decode<LOGR, LR, ROWFAST>(tid + (u32)i * NT, up, c4);
+    const u32 qp = up & ((1u << LOGS) - 1u), pp = up >> LOGS;
+#pragma unroll
+    for (int k = 0; k < RAD; k++) {
+      const u32 l = qp + (((pp << LR) + (u32)k) << LOGS);
+      const u32 *r = regs + i * 4 * RAD + k;
+      if (!LASTR) {
+        q4 v = {r[0], r[RAD], r[2 * RAD], r[3 * RAD]};
+        smem[slot<LOGC4>(l, c4)] = v;
+      } else if (KIND == FIRST) {
+        // Y[R u + k]: the tile's output is one contiguous block; scalar stores, coalesced along the rows
+        u32 *dst = T.out + (((u64)T.col0 + 4u * c4) << LOGR) + l;
+#pragma unroll
+        for (int x = 0; x < 4; x++) dst[(u64)x << LOGR] = r[x * RAD];
+      } else {
+        // Y[q + s (R p + k)]
+        q4 v = {r[0], r[RAD], r[2 * RAD], r[3 * RAD]};
+        *reinterpret_cast<q4 *>(T.out + T.q0 + 4u * c4 + ((((u64)T.p << LOGR) + l) << A.logS)) = v;
+      }
+    }
+  }
+}
+
+}  // namespace ntt2

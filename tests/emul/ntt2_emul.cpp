@@ -1,0 +1,176 @@
+// CPU emulation of k_ntt2_pass (index-math and range check only; TEST INFRASTRUCTURE, never shipped).
+// Runs the host+device inline round functions of ntt_pass.cuh thread by thread, phase by phase (a phase boundary
+// is a __syncthreads in the kernel), mirrors the pass sequencing of ntt_transform() in ntt.cu, and compares with an
+// O(n log n) reference NTT done with u64 %.  Also counts shared-memory bank conflicts of every 128-bit access pattern.
+// Build: g++ -O2 -std=c++17 -I stark-rs_b200/csrc tests/emul/ntt2_emul.cpp
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "ntt_pass.cuh"
+using namespace ntt2;
+
+static std::vector<u32> g_lo(4096), g_hi(2048), g_tw[2];
+static u32 g_w8[2][4];
+static void init() {
+  u32 w23 = ff::to_mont(ff::pow(3, (ff::P - 1) >> 23));
+  for (u32 i = 0; i < 4096; i++) g_lo[i] = ff::mont_pow(w23, i);
+  for (u32 i = 0; i < 2048; i++) g_hi[i] = ff::mont_pow(w23, (u64)i << 12);
+  RootTables T = {g_lo.data(), g_hi.data()};
+  for (int d = 0; d < 2; d++) {
+    g_tw[d].assign(8192, ff::R1);
+    for (u32 i = 1; i < 8192; i++) {
+      int logL = 31 - __builtin_clz(i);
+      u32 e = i - (1u << logL), idx = e << (23 - logL);
+      if (d) idx = ((1u << 23) - idx) & ((1u << 23) - 1u);
+      g_tw[d][i] = ntt::root_pow(T, idx);
+    }
+    u32 w8 = ff::pow(3, (ff::P - 1) >> 3);
+    if (d) w8 = ff::inv(w8);
+    g_w8[d][0] = ff::R1;
+    for (int k = 1; k < 4; k++) g_w8[d][k] = ff::to_mont(ff::pow(w8, k));
+  }
+}
+
+static long g_range_viol = 0;
+
+template <int LOGR, int KIND>
+static void run_pass(const PassParams &A, u32 grid) {
+  typedef Plan<LOGR> PL;
+  std::vector<q4> tile(1 << (TILE_LOG - 2));
+  std::vector<u32> otw(1 << LOGR), regs((size_t)NT * 32);
+  for (u32 blk = 0; blk < grid; blk++) {
+    const TileCtx T = tile_ctx<LOGR>(A, blk);
+    if (KIND == MIDDLE) for (u32 tid = 0; tid < NT; tid++) fill_outer_table<LOGR>(tid, A, T, otw.data());
+    for (u32 tid = 0; tid < NT; tid++) round_compute<LOGR, KIND, 0>(tid, A, T, tile.data(), otw.data(), &regs[tid * 32]);
+    for (u32 tid = 0; tid < NT; tid++) round_store<LOGR, KIND, 0>(tid, A, T, tile.data(), &regs[tid * 32]);
+    if (PL::NR == 3) {
+      for (u32 tid = 0; tid < NT; tid++) round_compute<LOGR, KIND, 1>(tid, A, T, tile.data(), otw.data(), &regs[tid * 32]);
+      for (u32 tid = 0; tid < NT; tid++) round_store<LOGR, KIND, 1>(tid, A, T, tile.data(), &regs[tid * 32]);
+    }
+    for (auto &v : tile) if (v.x >= ff::P2 || v.y >= ff::P2 || v.z >= ff::P2 || v.w >= ff::P2) g_range_viol++;
+    for (u32 tid = 0; tid < NT; tid++) round_compute<LOGR, KIND, PL::NR - 1>(tid, A, T, tile.data(), otw.data(), &regs[tid * 32]);
+    for (u32 tid = 0; tid < NT; tid++) round_store<LOGR, KIND, PL::NR - 1>(tid, A, T, tile.data(), &regs[tid * 32]);
+  }
+}
+
+// mirrors the N >= 2^13 branch of ntt_transform() in ntt.cu
+static void transform(const u32 *in, u32 *out, int log_n, int d, u32 batch, u64 n_valid, int post_mode, u32 post_c,
+                      GeoTables post_geo, int pre_mode, GeoTables pre_geo) {
+  const u64 N = 1ull << log_n;
+  int plan[3];
+  const int n_pass = pass_plan(log_n, plan);
+  std::vector<u32> tmp((size_t)batch * N);
+  const bool need_tmp = n_pass == 3 || in == out;
+  PassParams B;
+  memset(&B, 0, sizeof B);
+  B.logN = log_n, B.log_tiles = log_n - TILE_LOG;
+  B.roots = {g_lo.data(), g_hi.data()}, B.inverse = d;
+  for (int k = 0; k < 4; k++) B.w8[k] = g_w8[d][k];
+  const u32 grid = batch << B.log_tiles;
+  const u32 *src = in;
+  int logS = 0;
+  for (int i = 0; i < n_pass; i++) {
+    const int r = plan[i];
+    const int kind = i == 0 ? FIRST : (i == n_pass - 1 ? LAST : MIDDLE);
+    u32 *dst = (kind == LAST || kind == MIDDLE || (n_pass == 2 && !need_tmp)) ? out : tmp.data();
+    B.in = src, B.out = dst, B.in_batch = N, B.out_batch = N;
+    B.n_valid = kind == FIRST ? n_valid : N;
+    B.logS = logS;
+    B.tw_in = g_tw[d].data() + (1u << r);
+    if (kind == FIRST) fill_first_pass_constants(B, r);
+    B.pre_mode = kind == FIRST ? pre_mode : 0, B.pre_geo = pre_geo;
+    B.post_mode = kind == LAST ? post_mode : 0, B.post_const = post_c, B.post_geo = post_geo;
+#define CASE(R_, K_) if (r == R_ && kind == K_) run_pass<R_, K_>(B, grid); else
+    CASE(6, FIRST) CASE(7, FIRST) CASE(8, FIRST) CASE(9, FIRST) CASE(6, MIDDLE) CASE(7, MIDDLE) CASE(8, MIDDLE)
+    CASE(9, MIDDLE) CASE(6, LAST) CASE(7, LAST) CASE(8, LAST) CASE(9, LAST) abort();
+    src = dst;
+    logS += r;
+  }
+}
+
+static void ref_ntt(std::vector<u64> &a, u64 root) {
+  size_t n = a.size();
+  for (size_t i = 1, j = 0; i < n; i++) { size_t bit = n >> 1; for (; j & bit; bit >>= 1) j ^= bit; j ^= bit; if (i < j) std::swap(a[i], a[j]); }
+  for (size_t len = 2; len <= n; len <<= 1) {
+    u64 wl = ff::pow((u32)root, n / len);
+    for (size_t i = 0; i < n; i += len) { u64 w = 1;
+      for (size_t k = 0; k < len / 2; k++) { u64 u = a[i + k], v = a[i + k + len / 2] * w % ff::P;
+        a[i + k] = (u + v) % ff::P; a[i + k + len / 2] = (u + ff::P - v) % ff::P; w = w * wl % ff::P; } }
+  }
+}
+
+// bank conflicts: for every round's load / store pattern, per quarter-warp the 8 slots must be distinct mod 8
+template <int LOGR, int KIND, int ROUND>
+static long conflicts() {
+  typedef Plan<LOGR> PL;
+  constexpr int LR = PL::lr(ROUND), LOGS = PL::logs(ROUND), RAD = 1 << LR, NTASK = 8 >> LR, LOGC4 = TILE_LOG - LOGR - 2;
+  constexpr bool LASTR = ROUND == PL::NR - 1, ROWFAST = LASTR && KIND == FIRST;
+  long bad = 0;
+  for (int i = 0; i < NTASK; i++) for (u32 qw = 0; qw < NT / 8; qw++) for (int j = 0; j < RAD; j++) {
+    u32 seenL = 0, seenS = 0;
+    for (u32 lane = 0; lane < 8; lane++) {
+      u32 up, c4; decode<LOGR, LR, ROWFAST>(qw * 8 + lane + i * NT, up, c4);
+      if (ROUND > 0) seenL |= 1u << (slot<LOGC4>(up + ((u32)j << (LOGR - LR)), c4) & 7);
+      if (!LASTR) { u32 qp = up & ((1u << LOGS) - 1), pp = up >> LOGS; seenS |= 1u << (slot<LOGC4>(qp + (((pp << LR) + j) << LOGS), c4) & 7); }
+    }
+    if (ROUND > 0 && seenL != 0xff) bad++;
+    if (!LASTR && seenS != 0xff) bad++;
+  }
+  return bad;
+}
+template <int LOGR, int KIND> static long conflicts_all() {
+  long b = conflicts<LOGR, KIND, 0>() + conflicts<LOGR, KIND, Plan<LOGR>::NR - 1>();
+  if (Plan<LOGR>::NR == 3) b += conflicts<LOGR, KIND, 1>();
+  return b;
+}
+
+int main(int argc, char **argv) {
+  init();
+  int max_log = argc > 1 ? atoi(argv[1]) : 19;
+  int fails = 0;
+  long bc = conflicts_all<6, FIRST>() + conflicts_all<7, FIRST>() + conflicts_all<8, FIRST>() + conflicts_all<9, FIRST>() +
+            conflicts_all<6, LAST>() + conflicts_all<7, LAST>() + conflicts_all<8, LAST>() + conflicts_all<9, LAST>();
+  printf("bank-conflicted quarter-warp accesses: %ld\n", bc);
+  if (bc) fails++;
+  // geometric table for scale tests: c * g^i
+  const u32 g = 3, c = ff::inv(1u << 10);
+  std::vector<u32> glo(4096), ghi(4096);
+  for (u32 i = 0; i < 4096; i++) glo[i] = ff::canon(ff::mont_mul(ff::mont_pow(ff::to_mont(g), i), ff::to_mont(c)));
+  for (u32 i = 0; i < 4096; i++) ghi[i] = ff::mont_pow(ff::to_mont(g), (u64)i << 12);
+  GeoTables G = {glo.data(), ghi.data()};
+  for (int log_n = 13; log_n <= max_log; log_n++) for (int d = 0; d < 2; d++) for (int mode = 0; mode < 4; mode++) {
+    if (mode >= 2 && log_n > 16 && log_n != max_log) continue;
+    const u64 N = 1ull << log_n; const u32 batch = log_n <= 15 ? 2 : 1;
+    std::vector<u32> in(batch * N), out(batch * N);
+    u64 s = 12345 + log_n;
+    for (auto &x : in) { s = s * 6364136223846793005ull + 1442695040888963407ull; x = (u32)((s >> 33) % ff::P); }
+    u64 n_valid = mode == 1 ? (N / 4 + 3) : (mode == 3 ? N / 4 : N);
+    const bool inplace = mode == 3;
+    int post_mode = mode == 2 ? ntt::SCALE_GEO : (mode == 3 ? ntt::SCALE_CONST : ntt::SCALE_NONE);
+    int pre_mode = mode == 1 ? ntt::SCALE_GEO : ntt::SCALE_NONE;
+    std::vector<u32> keep = in;
+    if (inplace) { transform(in.data(), in.data(), log_n, d, batch, n_valid, post_mode, ff::to_mont(c), G, pre_mode, G); out = in; in = keep; }
+    else transform(in.data(), out.data(), log_n, d, batch, n_valid, post_mode, ff::to_mont(c), G, pre_mode, G);
+    u64 root = ff::pow(3, (ff::P - 1) >> log_n); if (d) root = ff::inv((u32)root);
+    for (u32 b = 0; b < batch; b++) {
+      std::vector<u64> r(N);
+      for (u64 i = 0; i < N; i++) {
+        u64 v = i < n_valid ? in[b * N + i] : 0;
+        if (pre_mode) v = v * ff::mul(c, ff::pow(g, i)) % ff::P;
+        r[i] = v;
+      }
+      ref_ntt(r, root);
+      for (u64 i = 0; i < N; i++) {
+        u64 want = r[i];
+        if (post_mode == ntt::SCALE_CONST) want = want * c % ff::P;
+        if (post_mode == ntt::SCALE_GEO) want = want * ff::mul(c, ff::pow(g, i)) % ff::P;
+        if (want != out[b * N + i]) { if (fails < 8) printf("MISMATCH log_n=%d d=%d mode=%d b=%u i=%llu got %u want %llu\n", log_n, d, mode, b, (unsigned long long)i, out[b * N + i], (unsigned long long)want); fails++; break; }
+      }
+    }
+  }
+  printf("smem range violations (>= 2p): %ld\n", g_range_viol);
+  if (g_range_viol) fails++;
+  printf(fails ? "FAIL %d\n" : "OK %d\n", fails ? fails : max_log);
+  return fails != 0;
+}
