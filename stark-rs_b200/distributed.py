@@ -157,7 +157,7 @@ class Comm:
         """every rank has written full[lo:lo+cnt] (its own slice, rank-major); make `full` replicated"""
         if self.world == 1:
             return
-        self.all_gather_rows(full.view(self.world, cnt), full[lo:lo + cnt].clone() if not self.nccl else full[lo:lo + cnt])
+        self.all_gather_rows(full.view(self.world, cnt), full[lo:lo + cnt].clone())
 
     def sum_uint8(self, arr, device):
         """element-wise sum over ranks of a host uint8 array (exactly one rank holds each non-zero byte)"""
@@ -188,7 +188,8 @@ class ShardedTree:
         owns, zeros for the others"""
         out = np.zeros((len(idx), self.depth_sub, 32), dtype=np.uint8)
         if self.top is None:
-            mine = list(range(len(idx)))
+            # replicated tree: every rank has it; rank 0 alone contributes to the all-reduce
+            mine = list(range(len(idx))) if self.comm.rank == 0 else []
         else:
             mine = [k for k, i in enumerate(idx) if i // self.per == self.comm.rank]
         if mine and self.depth_sub:
@@ -209,9 +210,9 @@ class ShardedTree:
 def build_tree(backend, comm, values, n, shard_min=1 << 14, width=1):
     """leaf hashing + MerkleTree::new (fri.rs:118-127) over a replicated codeword, sharded by leaf range"""
     G = comm.world
-    if G > 1 and n >= shard_min and n % G == 0 and (n // G) >= 2:
+    if G > 1 and width == 1 and n >= shard_min and n % G == 0 and (n // G) >= 2:
         per = n // G
-        sub = backend.subtree(values, comm.rank * per * width, per, width)
+        sub = backend.subtree(values, comm.rank * per, per, 1)
         roots = backend.new_hashes(G)
         comm.all_gather_rows(roots, sub.root)
         return ShardedTree(n, sub, backend.tree_from_hashes(roots), comm)

@@ -1,0 +1,84 @@
+"""CudaBackend of the sharded prover on one B200: the per-rank pieces (leaf-range subtrees, output-range folds) must
+reassemble to exactly the single-GPU / oracle results for G = 2, 4, 8, and ShardedFri at world size 1 must emit the
+oracle's proof bytes.  (The collectives themselves are covered on CPU by tests/test_distributed_gloo.py and on
+2-8 GPUs by benchmarks/sharded_sweep.py, which asserts the same equalities.)"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def backend(S):
+    from stark_rs_b200 import distributed as D
+    stream = torch.cuda.Stream()
+    ctx = S.Context(0, stream=stream.cuda_stream)
+    with torch.cuda.stream(stream):
+        yield D.CudaBackend(ctx, "cuda:0")
+    ctx.close()
+
+
+@pytest.mark.parametrize("G", [2, 4, 8])
+def test_subtrees_and_top_tree_equal_full_tree(backend, oracle, G):
+    n = 1 << 12
+    vals = oracle.splitmix64(11, n)
+    cw = backend.upload(vals)
+    full = oracle.merkle_build(oracle.hash_leaves(vals))
+    roots = backend.new_hashes(G)
+    per = n // G
+    subs = []
+    for g in range(G):
+        t = backend.subtree(cw, g * per, per)
+        roots[g].copy_(t.root)
+        subs.append(t)
+    top = backend.tree_from_hashes(roots)
+    assert top.root_bytes() == full[-1].tobytes()
+    # a sharded authentication path = owner's subtree path + top-tree path (merkle.rs:67-80)
+    for idx in [0, 1, per - 1, per, n - 1, 1234]:
+        g = idx // per
+        lower = subs[g].open_batch([idx % per])[0]
+        upper = top.open_batch([g])[0]
+        want = oracle.merkle_open(full[:n], idx)
+        assert np.array_equal(np.concatenate([lower, upper]), want)
+    for t in subs + [top]:
+        t.free()
+
+
+@pytest.mark.parametrize("G", [2, 4, 8])
+def test_fold_ranges_equal_full_fold(backend, oracle, G):
+    n = 1 << 14
+    vals = oracle.splitmix64(5, n)
+    w = oracle.ff_prim_nth_root(n)
+    alpha = 15764728482632548394          # raw, unreduced (fiat_shamir.rs:21-24)
+    cw = backend.upload(vals)
+    out = backend.new_codeword(n // 2)
+    per = (n // 2) // G
+    for g in range(G):
+        backend.fold_range(cw, n, alpha, 3, w, g * per, per, out)
+    assert np.array_equal(backend.download(out), oracle.fast_fri_fold(vals, alpha, 3, w))
+
+
+def test_sharded_fri_world1_equals_oracle_and_single_gpu(backend, oracle, ctx):
+    from stark_rs_b200 import distributed as D
+    n, ef, nq = 1 << 12, 4, 16
+    cw = oracle.fast_lde(oracle.splitmix64(9, n // ef), 10, 2, 3)
+    w = oracle.ff_prim_nth_root(n)
+    proof, top = D.ShardedFri(backend, w, 3, n, ef, nq).prove(backend.upload(cw))
+    ref = oracle.fri_prove(cw, w, 3, ef, nq)
+    assert proof == ref["proof"] and top == ref["top_indices"]
+    single, top1 = ctx.fri_prove(cw, 3, w, ef, nq)
+    assert single == proof and top1 == top
+
+
+def test_lde_commit_world1(backend, oracle):
+    from stark_rs_b200 import distributed as D
+    log_n, lb, ng, gw = 8, 1, 2, 8
+    cols = lambda k: backend.upload(np.concatenate([oracle.splitmix64(1000 * k + c, 1 << log_n) for c in range(gw)]))
+    commitment, roots, _ = D.lde_commit_sharded(backend, D.Comm(), cols, ng, gw, log_n, lb, 3)
+    want = []
+    for k in range(ng):
+        ldes = [oracle.fast_lde(oracle.splitmix64(1000 * k + c, 1 << log_n), log_n, lb, 3) for c in range(gw)]
+        want.append(oracle.merkle_commit(oracle.hash_leaves(np.stack(ldes, axis=1).reshape(-1), gw)))
+    assert roots.tobytes() == b"".join(want)
+    assert commitment == oracle.merkle_commit(np.frombuffer(b"".join(want), dtype=np.uint8).reshape(ng, 32))
