@@ -8,7 +8,7 @@
         would need a 2^24 domain), rank g owns groups {g, g+G, ...}.
 
 usage: python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 --master-port P \
-           benchmarks/sharded_sweep.py [--logs 16,18,...] [--cfg4-log-n 22] [--check]
+           benchmarks/sharded_sweep.py [--sizes 16,18,...] [--cfg4-log-n 22] [--check]
 Rank 0 prints one JSON line per measurement; times are CUDA events on the device, max over ranks.  With --check the
 results are compared with a single-GPU run of the same input on rank 0 (roots and folded codewords must be identical)."""
 import argparse
@@ -27,7 +27,7 @@ from stark_rs_b200 import distributed as D  # noqa: E402
 from stark_rs_b200 import synthetic as G_  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--logs", default="16,18,20,22,24,26")
+ap.add_argument("--sizes", default="16,18,20,22,24,26")
 ap.add_argument("--cfg4-log-n", type=int, default=0, help="rows (log2) of the config-4 trace; 0 = skip")
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--check", action="store_true")
@@ -84,7 +84,7 @@ def one_round(cw, n, omega, transcript=b""):
 
 
 with torch.cuda.stream(stream):
-    for k in [int(x) for x in a.logs.split(",")]:
+    for k in [int(x) for x in a.sizes.split(",")]:
         n = 1 << k
         omega = S.prim_nth_root(1 << min(k, 23))
         gen = torch.Generator(device="cuda").manual_seed(1234 + k)      # same replica on every rank
