@@ -57,6 +57,9 @@ int stark_ctx_profile_end(stark_ctx *ctx, char *json, size_t cap);
 /* register-only integer issue-rate microbenchmark: thread-instructions per second of IMAD, LOP3/IADD3 and a
  * 1:1 mix, measured with CUDA events (no integer peak is recorded in MEASURED_PEAKS.json) */
 int stark_bench_int_peak(stark_ctx *ctx, double *imad_per_s, double *alu_per_s, double *mixed_per_s);
+/* dependent-hash latency (clock cycles per Hash::combine) of one warp alone on an SM, for the one-hash-per-thread,
+ * two-per-thread and four-lanes-per-hash kernels forms (measurement only) */
+int stark_bench_hash_latency(stark_ctx *ctx, double *hs_cycles, double *hs2_cycles, double *hsq_cycles);
 const char *stark_last_error(void);
 const char *stark_version(void);
 

@@ -312,6 +312,11 @@ class Context:
         _chk(lib().stark_bench_int_peak(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return {"imad_per_s": a.value, "alu_per_s": b.value, "mixed_per_s": c.value}
 
+    def hash_latency(self):
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        _chk(lib().stark_bench_hash_latency(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"hs_cycles": a.value, "hs2_cycles": b.value, "hsq_cycles": c.value}
+
     # ---- buffers
     def alloc(self, n):
         h = C.c_void_p()

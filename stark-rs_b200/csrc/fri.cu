@@ -18,75 +18,13 @@
 #include "common.cuh"
 #include "hash.cuh"
 #include "merkle.h"
+#include "merkle_dev.cuh"
 
 using hs::State;
 using ntt::GeoTables;
 
 // ---------------------------------------------------------------------------------------- transcript
 
-// streaming form of Hash::from_bytes over an append-only transcript (fiat_shamir.rs:4-25): `s` is the sponge
-// after all complete 32-byte chunks (each followed by its mix, round constants settled), `pend` the bytes of
-// the incomplete last chunk.
-struct TranscriptDev {
-  u32 s[32];
-  u8 pend[32];
-  u32 npend;
-};
-
-HS_HD void tr_init(TranscriptDev &T) {
-  for (int i = 0; i < 32; i++) T.s[i] = hs::prime_at(i), T.pend[i] = 0;
-  T.npend = 0;
-}
-HS_HD void tr_absorb(TranscriptDev &T, const u8 *data, size_t n) {
-  for (size_t k = 0; k < n; k++) {
-    T.pend[T.npend++] = data[k];
-    if (T.npend == 32) {
-      State st;
-      for (int i = 0; i < 32; i++) st.s[i] = T.s[i];
-      for (int i = 0; i < 32; i++) hs::absorb_byte(st, i, T.pend[i]);
-      hs::mix_lazy<false>(st);
-      hs::settle(st);
-      for (int i = 0; i < 32; i++) T.s[i] = st.s[i] & 0xffu;
-      T.npend = 0;
-    }
-  }
-}
-// FiatShamir::challenge (fiat_shamir.rs:19-25): first 8 bytes of Hash(transcript), little-endian, UNREDUCED
-HS_HD u64 tr_challenge(const TranscriptDev &T) {
-  State st;
-  for (int i = 0; i < 32; i++) st.s[i] = T.s[i];
-  if (T.npend) {
-    for (u32 i = 0; i < T.npend; i++) {
-      const u32 v = hs::rotl_lazy(st.s[i] + T.pend[i], 3);
-      st.s[i] = v;
-      st.s[(i + 7) & 31] ^= v;
-    }
-    hs::mix_lazy<false>(st);
-    hs::finalize<true>(st);
-  } else {
-    hs::finalize<false>(st);
-  }
-  u64 v = 0;
-  for (int b = 0; b < 8; b++) v |= (u64)(st.s[b] & 0xffu) << (8 * b);
-  return v;
-}
-
-// absorb one Merkle root (fri.rs:129-131) and, unless it is the last round (fri.rs:133-135), draw alpha
-// (fri.rs:138).  One thread; the root is read from the tree, also copied to roots_out.
-__global__ void k_transcript_round(TranscriptDev *T, const u8 *root, u8 *roots_out, int draw, u64 *alpha_raw,
-                                   u32 *alpha_m) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  u8 r[32];
-  for (int i = 0; i < 32; i++) r[i] = root[i], roots_out[i] = r[i];
-  TranscriptDev t = *T;
-  tr_absorb(t, r, 32);
-  *T = t;
-  if (draw) {
-    const u64 a = tr_challenge(t);
-    *alpha_raw = a;
-    *alpha_m = ff::to_mont(ff::reduce64(a));
-  }
-}
 __global__ void k_transcript_challenge(const TranscriptDev *T, u64 *out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   *out = tr_challenge(*T);
@@ -127,31 +65,135 @@ __global__ void __launch_bounds__(256) k_fri_fold(const u32 *__restrict__ cw, u3
   }
 }
 
+// -------------------------------------------------------------------------------------------- FRI tail
+
+// The last rounds of Fri::commit (fri.rs:116-147), codeword <= 2^11, as ONE single-CTA kernel: per round leaf hashes,
+// the whole tree, the transcript round and the fold, back to back through shared memory.  These rounds are a pure
+// dependency chain (root -> alpha -> fold -> next leaves) of ~log2(n)+3 hash latencies each; run as separate launches
+// they cost a launch + drain per link.
+constexpr int TAIL_LOG = 9, TAIL_NT = 512, TAIL_MAX_ROUNDS = 12;
+struct TailArgs {
+  u32 n_rounds, first_round, len0;
+  u32 *cw[TAIL_MAX_ROUNDS + 1];   // cw[i] = codeword of tail round i; cw[i + 1] receives its fold
+  u8 *nodes[TAIL_MAX_ROUNDS];     // tree of cw[i]
+  u32 inv2off_m[TAIL_MAX_ROUNDS]; // (2 offset_r)^-1, Montgomery
+  GeoTables G;                    // (w0^-1)^e table shared by all rounds (round r uses e = i << r)
+  TranscriptDev *T;
+  u8 *roots;                      // entries of the first tail round onwards
+  u64 *alpha_raw;
+  u32 *alpha_m;
+};
+__global__ void __launch_bounds__(TAIL_NT, 1) k_fri_tail(const __grid_constant__ TailArgs A) {
+  __shared__ __align__(16) u8 sm[(1 << TAIL_LOG) * 16];
+  const u32 t = threadIdx.x, one = blockDim.y;
+  u32 len = A.len0;
+  for (u32 i = 0; i < A.n_rounds; i++) {
+    const u32 *cw = A.cw[i];
+    u8 *nodes = A.nodes[i];
+    // leaves (fri.rs:118-121), two per thread
+    if (2 * t < len) {
+      u32 wa[8], wb[8];
+      if (2 * t + 1 < len) {
+        const uint2 v = *reinterpret_cast<const uint2 *>(cw + 2 * t);
+        hs2::leaf2(v.x, v.y, wa, wb, one);
+        store_hash(nodes + 64 * (size_t)t + 32, wb);
+      } else {
+        hs2::leaf2(cw[2 * t], 0u, wa, wb, one);
+      }
+      store_hash(nodes + 64 * (size_t)t, wa);
+    }
+    __syncthreads();
+    u32 levels = 0;
+    for (u32 c = len; c > 1; c >>= 1) levels++;
+    cta_climb<TAIL_NT>(nodes, len, 0, 0, len, levels, nodes, sm, one);
+    const bool last = i + 1 == A.n_rounds;
+    if (t == 0) {
+      u32 root[8];
+      load_hash(len > 1 ? sm : nodes, root);
+      const TranscriptArgs tr = {A.T, A.roots + 32 * i, last ? 0 : 1, A.alpha_raw + i, A.alpha_m + i};
+      transcript_round(tr, root);   // fri.rs:129-138
+    }
+    __syncthreads();
+    if (last) break;   // fri.rs:133-135
+    // fold_codeword (fri.rs:57-91), same closed form as k_fri_fold
+    const u32 K = ff::canon(ff::mont_mul(A.alpha_m[i], A.inv2off_m[i]));
+    const u32 h = len >> 1, r = A.first_round + i;
+    u32 *out = A.cw[i + 1];
+    for (u32 j = t; j < h; j += TAIL_NT) {
+      const u32 a = cw[j], b = cw[h + j];
+      const u32 tw = ff::canon(ff::mont_mul(ntt::geo_pow(A.G, (u64)j << r), K));
+      out[j] = ff::canon4(ff::half(a + b) + ff::mont_mul(a + ff::P - b, tw));
+    }
+    __syncthreads();
+    len = h;
+  }
+}
+
+// fold_codeword (fri.rs:57-91) fused with the leaf hashing of the NEXT round (fri.rs:118-121): writes the folded
+// codeword and its leaf hashes in one pass, two outputs per thread (hs2).  h even.
+__global__ void __launch_bounds__(256) k_fold_leaf1(const u32 *__restrict__ cw, u32 *__restrict__ out, size_t h, int r,
+                                                    GeoTables G, u32 g_r_m, const u32 *__restrict__ alpha_m,
+                                                    u32 inv2off_m, u8 *__restrict__ leaves) {
+  const size_t i = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
+  if (i >= h) return;
+  const u32 K = ff::canon(ff::mont_mul(*alpha_m, inv2off_m));
+  const uint2 x = *reinterpret_cast<const uint2 *>(cw + i), y = *reinterpret_cast<const uint2 *>(cw + h + i);
+  const u32 tw0 = ff::canon(ff::mont_mul(ntt::geo_pow(G, (u64)i << r), K));
+  const u32 tw1 = ff::canon(ff::mont_mul(tw0, g_r_m));
+  const u32 o0 = ff::canon4(ff::half(x.x + y.x) + ff::mont_mul(x.x + ff::P - y.x, tw0));
+  const u32 o1 = ff::canon4(ff::half(x.y + y.y) + ff::mont_mul(x.y + ff::P - y.y, tw1));
+  *reinterpret_cast<uint2 *>(out + i) = make_uint2(o0, o1);
+  u32 wa[8], wb[8];
+  hs2::leaf2(o0, o1, wa, wb, blockDim.y);
+  store_hash(leaves + 32 * i, wa);
+  store_hash(leaves + 32 * i + 32, wb);
+}
+
 // ------------------------------------------------------------------------------------ index sampling
 
-// Fri::sample_indices (fri.rs:176-213) with seed = Hash::from_u64(challenge) (fri.rs:272): candidates for a
-// batch of counters are hashed in parallel, thread 0 then applies the sequential reject rule.
-__global__ void __launch_bounds__(256) k_sample_indices(const u64 *challenge, u64 size, u64 reduced, u32 number,
-                                                        u64 *out) {
+// Fri::sample_indices (fri.rs:176-213) with seed = Hash::from_u64(FiatShamir::challenge) (fri.rs:272, hash.rs:37-39).
+// Thread 0 draws the challenge from the transcript and hashes it into the seed; every candidate message is
+// seed || counter (36 bytes, fri.rs:198-200), so the sponge after the first chunk (the seed) is computed once and shared;
+// candidates for a batch of 256 counters are then hashed in parallel (4 absorbed bytes + 9 mixes each, registers only)
+// and thread 0 applies the sequential reject rule.
+__global__ void __launch_bounds__(256) k_sample_indices(const TranscriptDev *T, u64 *challenge_out, u64 size, u64 reduced,
+                                                        u32 number, u64 *out) {
   __shared__ u64 cand[256];
-  __shared__ u8 seed[32];
+  __shared__ u32 pre[32];
   __shared__ u32 got;
   if (threadIdx.x == 0) {
-    const u64 c = *challenge;
-    u8 m[8];
-    for (int b = 0; b < 8; b++) m[b] = (u8)(c >> (8 * b));
-    hs::from_bytes(m, 8, seed);
+    const u64 c = tr_challenge(*T);
+    *challenge_out = c;
+    State st;
+    hs::init(st);
+#pragma unroll
+    for (int i = 0; i < 8; i++) hs::absorb_byte(st, i, (u32)(c >> (8 * i)) & 0xffu);
+    hs::mix_lazy<false>(st);
+    hs::finalize<true>(st);
+    u32 seed[8];
+    hs::pack_words(st, seed);
+    State s2;
+    hs::init(s2);
+    hs::absorb_words_mix<false>(s2, seed);   // round constants of this mix still pending
+#pragma unroll
+    for (int i = 0; i < 32; i++) pre[i] = s2.s[i];
     got = 0;
   }
   __syncthreads();
+  if (number == 0) return;
   for (u32 base = 0;; base += 256) {
-    u8 msg[36], h[32];
-    for (int i = 0; i < 32; i++) msg[i] = seed[i];
     const u32 counter = base + threadIdx.x;
-    for (int b = 0; b < 4; b++) msg[32 + b] = (u8)(counter >> (8 * b));  // fri.rs:199-200
-    hs::from_bytes(msg, 36, h);
+    State st;
+#pragma unroll
+    for (int i = 0; i < 32; i++) st.s[i] = pre[i];
+    hs::settle(st);
+#pragma unroll
+    for (int i = 0; i < 4; i++) hs::absorb_byte(st, i, (counter >> (8 * i)) & 0xffu);   // u32 LE, fri.rs:199-200
+    hs::mix_lazy<false>(st);
+    hs::finalize<true>(st);
     u64 v = 0;
-    for (int b = 24; b < 32; b++) v = (v << 8) | h[b];  // fri.rs:168-174: low 64 bits of the big-endian value
+#pragma unroll
+    for (int b = 24; b < 32; b++) v = (v << 8) | (u64)(st.s[b] & 0xffu);   // fri.rs:168-174: low 64 bits, big-endian
     cand[threadIdx.x] = v % size;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -191,10 +233,24 @@ __global__ void k_proof_header(u8 *out, const u8 *roots, u32 R, const u32 *last,
   }
   if (t < last_len) put_u64(base + 9 + 8 * t, last[t]);
 }
-// one query round (fri.rs:215-248): nq x [0x02, 3, a, b, c]  then  nq x (path a, path b, path c), each path
-// [0x03, depth u64, depth hashes] (stream.rs:54-60); indices folded as fri.rs:282-285.
-__global__ void k_proof_round(u8 *out, const u32 *cur, const u32 *nxt, u64 cur_len, const u8 *cur_nodes,
-                              const u8 *nxt_nodes, const u64 *top, u32 nq, u32 depth_cur) {
+// the query rounds (fri.rs:215-248, 280-307), all in one launch (blockIdx.y = round i): nq x [0x02, 3, a, b, c]  then
+// nq x (path a, path b, path c), each path [0x03, depth u64, depth hashes] (stream.rs:54-60); indices folded as
+// fri.rs:282-285 (top % (len_i / 2), which equals the reference's cumulative reduction because the lengths halve).
+constexpr int MAX_FRI_ROUNDS = 24;
+struct ProofRoundsArgs {
+  const u32 *cw[MAX_FRI_ROUNDS];
+  const u8 *nodes[MAX_FRI_ROUNDS];
+  u64 out_off[MAX_FRI_ROUNDS];
+  u64 len0;
+  u32 nq, depth0;
+};
+__global__ void k_proof_rounds(u8 *proof, const __grid_constant__ ProofRoundsArgs A, const u64 *top) {
+  const u32 i = blockIdx.y, nq = A.nq;
+  u8 *out = proof + A.out_off[i];
+  const u32 *cur = A.cw[i], *nxt = A.cw[i + 1];
+  const u8 *cur_nodes = A.nodes[i], *nxt_nodes = A.nodes[i + 1];
+  const u64 cur_len = A.len0 >> i;
+  const u32 depth_cur = A.depth0 - i;
   const u64 half = cur_len >> 1;
   const u32 depth_nxt = depth_cur - 1;
   const u64 triples = 33ull * nq;
@@ -236,7 +292,7 @@ __global__ void k_proof_round(u8 *out, const u32 *cur, const u32 *nxt, u64 cur_l
   const uint4 x = src[0], y = src[1];
   const u32 w[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
 #pragma unroll
-  for (int i = 0; i < 32; i++) dst[i] = (u8)(w[i >> 2] >> (8 * (i & 3)));
+  for (int b = 0; b < 32; b++) dst[b] = (u8)(w[b >> 2] >> (8 * (b & 3)));
 }
 
 // ---------------------------------------------------------------------------------------- host logic
@@ -335,28 +391,80 @@ static int fri_commit_dev(stark_ctx *ctx, const u32 *cw0, size_t n, u32 offset, 
     g0 = ff::inv(omega);
     rc = geo_tables(ctx, g0, 1, n / 2, &G);
   }
-  u32 off_r = offset, g_r = g0;
+  // Round r:  [r > 0: fold of round r-1 fused with this round's leaf hashes]  ->  tree  ->  root + transcript (alpha_r).
+  // off_r / g_r are the domain constants of round r (fri.rs:146-147); the fold INTO round r uses those of round r-1.
+  u32 off_r = offset, g_r = g0, off_prev = offset, g_prev = g0;
   size_t len = n;
   for (u32 r = 0; r < R && rc == STARK_OK; r++) {
+    const bool tail = len >= 2 && len <= ((size_t)1 << TAIL_LOG) && R - r <= (u32)TAIL_MAX_ROUNDS;
+    if (r > 0) {
+      u32 *nxt = nullptr;
+      rc = dev_alloc(ctx, (void **)&nxt, len * 4);
+      if (rc != STARK_OK) break;
+      s->cw.push_back(nxt), s->len.push_back(len);
+    }
+    if (tail) {
+      // the remaining rounds in one single-CTA launch (its input codeword still has to be folded)
+      if (r > 0) {
+        const u32 inv2off_m = ff::to_mont(ff::inv(ff::mul(2, off_prev)));
+        rc = fold_launch(ctx, s->cw[r - 1], s->cw[r], len, (int)(r - 1), G, ff::to_mont(g_prev), s->d_alpha_m + (r - 1), inv2off_m);
+        if (rc != STARK_OK) break;
+      }
+      TailArgs A;
+      memset(&A, 0, sizeof A);
+      A.n_rounds = R - r, A.first_round = r, A.len0 = (u32)len;
+      A.G = G, A.T = s->d_tr, A.roots = s->d_roots + 32 * r, A.alpha_raw = s->d_alpha_raw + r, A.alpha_m = s->d_alpha_m + r;
+      A.cw[0] = s->cw[r];
+      size_t l = len;
+      u64 hashes = 0;
+      for (u32 i = 0; i < A.n_rounds && rc == STARK_OK; i++) {
+        stark_tree *tree = nullptr;
+        rc = merkle_tree_alloc(ctx, l, &tree);
+        if (rc != STARK_OK) break;
+        s->trees.push_back(tree);
+        A.nodes[i] = tree->nodes;
+        A.inv2off_m[i] = ff::to_mont(ff::inv(ff::mul(2, off_r)));
+        hashes += 2 * l - 1;
+        if (i + 1 < A.n_rounds) {
+          u32 *nxt = nullptr;
+          rc = dev_alloc(ctx, (void **)&nxt, (l / 2) * 4);
+          if (rc != STARK_OK) break;
+          A.cw[i + 1] = nxt;
+          s->cw.push_back(nxt), s->len.push_back(l / 2);
+          l /= 2;
+          off_r = ff::mul(off_r, off_r);
+        }
+      }
+      if (rc == STARK_OK) LAUNCH(ctx, "fri_tail", 64 * hashes, k_fri_tail<<<1, TAIL_NT, 0, ctx->stream>>>(A));
+      break;
+    }
     stark_tree *tree = nullptr;
-    rc = merkle_build_from_dev_values(ctx, s->cw[r], len, 1, 1, 0, &tree);  // fri.rs:118-127
+    rc = merkle_tree_alloc(ctx, len, &tree);
     if (rc != STARK_OK) break;
     s->trees.push_back(tree);
-    const bool last = r == R - 1;
-    if (ctx->prof_on) prof_begin(ctx, "transcript", 0);
-    k_transcript_round<<<1, 32, 0, ctx->stream>>>(s->d_tr, tree->nodes + 32 * (2 * len - 2), s->d_roots + 32 * r,
-                                                  last ? 0 : 1, s->d_alpha_raw + r, s->d_alpha_m + r);
-    if (ctx->prof_on) prof_end(ctx);
-    ctx->launches++;
-    if (last) break;  // fri.rs:133-135
-    u32 *nxt = nullptr;
-    rc = dev_alloc(ctx, (void **)&nxt, (len / 2) * 4);
+    if (r == 0) {
+      rc = merkle_leaves_dev(ctx, s->cw[0], len, 1, 1, 0, tree->nodes);   // fri.rs:118-121
+    } else if (len % 2 == 0) {
+      const u32 inv2off_m = ff::to_mont(ff::inv(ff::mul(2, off_prev)));
+      LAUNCH(ctx, "fold_leaf", 12ull * len + 32ull * len,
+             k_fold_leaf1<<<(u32)((len / 2 + 255) / 256), 256, 0, ctx->stream>>>(s->cw[r - 1], s->cw[r], len, (int)(r - 1), G,
+                                                                              ff::to_mont(g_prev), s->d_alpha_m + (r - 1),
+                                                                              inv2off_m, tree->nodes));
+    } else {
+      const u32 inv2off_m = ff::to_mont(ff::inv(ff::mul(2, off_prev)));
+      rc = fold_launch(ctx, s->cw[r - 1], s->cw[r], len, (int)(r - 1), G, ff::to_mont(g_prev), s->d_alpha_m + (r - 1), inv2off_m);
+      if (rc == STARK_OK) rc = merkle_leaves_dev(ctx, s->cw[r], len, 1, 1, 0, tree->nodes);
+    }
     if (rc != STARK_OK) break;
-    const u32 inv2off_m = ff::to_mont(ff::inv(ff::mul(2, off_r)));
-    rc = fold_launch(ctx, s->cw[r], nxt, len / 2, (int)r, G, ff::to_mont(g_r), s->d_alpha_m + r, inv2off_m);
-    s->cw.push_back(nxt), s->len.push_back(len / 2);
-    len /= 2;
+    // tree (fri.rs:127); the kernel that produces the root also pushes it, absorbs it and, unless this is the last
+    // round (fri.rs:133-135), draws alpha (fri.rs:129-138)
+    const bool last = r == R - 1;
+    const TranscriptArgs tr = {s->d_tr, s->d_roots + 32 * r, last ? 0 : 1, s->d_alpha_raw + r, s->d_alpha_m + r};
+    rc = merkle_climb_dev(ctx, tree->nodes, len, &tr);
+    if (rc != STARK_OK) break;
+    off_prev = off_r, g_prev = g_r;
     off_r = ff::mul(off_r, off_r), g_r = ff::mul(g_r, g_r);  // fri.rs:146-147
+    len /= 2;
   }
 #undef TRY_
   if (rc == STARK_OK && cudaGetLastError() != cudaSuccess) rc = stark_fail(ctx, STARK_ERR_CUDA, "kernel launch failed");
@@ -406,6 +514,7 @@ static int fri_prove_dev(stark_ctx *ctx, const u32 *cw0, size_t n, size_t domain
   if ((size_t)nq > L.last_len)
     return stark_fail(ctx, STARK_ERR_ARG, "cannot sample more indices than available in last codeword; requested: %u, available: %zu", nq, L.last_len);
   if (!proof || proof_cap < L.total) return stark_fail(ctx, STARK_ERR_ARG, "proof buffer too small: need %zu bytes", L.total);
+  if (L.n_cw > (u32)MAX_FRI_ROUNDS) return stark_fail(ctx, STARK_ERR_ARG, "more than %d FRI rounds are not supported", MAX_FRI_ROUNDS);
   stark_fri_state *s = nullptr;
   ST_TRY(fri_commit_dev(ctx, cw0, n, offset, omega, ef, nq, transcript, transcript_len, false, &s));
   int rc = STARK_OK;
@@ -416,20 +525,22 @@ static int fri_prove_dev(stark_ctx *ctx, const u32 *cw0, size_t n, size_t domain
   if (rc == STARK_OK) {
     d_top = reinterpret_cast<u64 *>(d_proof + ((L.total + 7) & ~(size_t)7));
     if (ctx->prof_on) prof_begin(ctx, "query_phase", 0);
-    k_transcript_challenge<<<1, 32, 0, ctx->stream>>>(s->d_tr, d_seed);  // fri.rs:272
     const size_t sample_size = L.n_cw > 1 ? s->len[1] : s->len[0];       // fri.rs:266-270
-    if (nq) k_sample_indices<<<1, 256, 0, ctx->stream>>>(d_seed, sample_size, L.last_len, nq, d_top);
+    k_sample_indices<<<1, 256, 0, ctx->stream>>>(s->d_tr, d_seed, sample_size, L.last_len, nq, d_top);  // fri.rs:272-276
     const size_t hdr_threads = L.last_len > R ? L.last_len : R;
     k_proof_header<<<(u32)((hdr_threads + 255) / 256), 256, 0, ctx->stream>>>(d_proof, s->d_roots, R, s->cw[L.n_cw - 1],
                                                                              L.last_len);
-    ctx->launches += nq ? 3 : 2;
-    for (u32 i = 0; i + 1 < L.n_cw && nq; i++) {
-      u32 d = 0;
-      for (size_t m = s->len[i]; m > 1; m >>= 1) d++;
-      const size_t threads = (size_t)nq * (3 * d - 1);
-      k_proof_round<<<(u32)((threads + 127) / 128), 128, 0, ctx->stream>>>(d_proof + L.round_off[i], s->cw[i], s->cw[i + 1],
-                                                                         s->len[i], s->trees[i]->nodes,
-                                                                         s->trees[i + 1]->nodes, d_top, nq, d);
+    ctx->launches += 2;
+    if (L.n_cw > 1 && nq) {
+      ProofRoundsArgs PA;
+      memset(&PA, 0, sizeof PA);
+      u32 d0 = 0;
+      for (size_t m = s->len[0]; m > 1; m >>= 1) d0++;
+      PA.len0 = s->len[0], PA.nq = nq, PA.depth0 = d0;
+      for (u32 i = 0; i < L.n_cw; i++) PA.cw[i] = s->cw[i], PA.nodes[i] = s->trees[i]->nodes;
+      for (u32 i = 0; i + 1 < L.n_cw; i++) PA.out_off[i] = L.round_off[i];
+      const size_t threads = (size_t)nq * (3 * d0 - 1);
+      k_proof_rounds<<<dim3((u32)((threads + 127) / 128), L.n_cw - 1), 128, 0, ctx->stream>>>(d_proof, PA, d_top);
       ctx->launches++;
     }
     if (ctx->prof_on) prof_end(ctx);

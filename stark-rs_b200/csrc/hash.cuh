@@ -107,12 +107,19 @@ HS_HD void settle(State &st) {
   for (int i = 0; i < 32; i++) st.s[i] += rc_at(i);
 }
 
-// 8 finalisation mixes (hash.rs:25-27) + settle.  PENDING as for mix_lazy.
-template <bool PENDING>
+// 8 finalisation mixes (hash.rs:25-27) + settle.  PENDING as for mix_lazy.  UNROLL: straight-line code, so the
+// scheduler can start the next mix's sbox on bytes whose neighbour-add chain has already finished (the latency-bound
+// narrow tree levels); the rolled form keeps the throughput kernels' code small.
+template <bool PENDING, bool UNROLL = false>
 HS_HD void finalize(State &st) {
   mix_lazy<PENDING>(st);
+  if (UNROLL) {
+#pragma unroll
+    for (int k = 0; k < 7; k++) mix_lazy<true>(st);
+  } else {
 #pragma unroll 1
-  for (int k = 0; k < 7; k++) mix_lazy<true>(st);
+    for (int k = 0; k < 7; k++) mix_lazy<true>(st);
+  }
   settle(st);
 }
 
@@ -141,12 +148,24 @@ HS_HD void absorb_words_mix(State &st, const u32 *w) {
 }
 
 // Hash::combine (hash.rs:41-46): 64-byte message = two chunks, then 8 mixes
+// Code size matters as much as instruction count for the latency-bound callers (a narrow tree level runs this code
+// once per launch, from a cold instruction cache): the two chunks share ONE copy of absorb + mix and the eight
+// finalisation mixes ONE copy of the pending-constants mix.
+template <bool UNROLL = false>
 HS_HD void combine(const u32 *left, const u32 *right, u32 *out) {
   State st;
   init(st);
-  absorb_words_mix<false>(st, left);
-  absorb_words_mix<true>(st, right);
-  finalize<true>(st);
+#pragma unroll 1
+  for (int c = 0; c < 2; c++) {
+    if (c) settle(st);
+    u32 w[8];
+#pragma unroll
+    for (int g = 0; g < 8; g++) w[g] = c ? right[g] : left[g];
+    absorb_words_mix<false>(st, w);
+  }
+#pragma unroll 1
+  for (int k = 0; k < 8; k++) mix_lazy<true>(st);
+  settle(st);
   pack_words(st, out);
 }
 
@@ -299,9 +318,17 @@ HS_HD void pack_words(const State2 &st, u32 *wa, u32 *wb) {
 HS_HD void combine2(const u32 *la, const u32 *ra, const u32 *lb, const u32 *rb, u32 *oa, u32 *ob, u32 one) {
   State2 st;
   init(st, one);
-  absorb_words_mix<false>(st, la, lb);
-  absorb_words_mix<true>(st, ra, rb);
-  finalize<true>(st);
+#pragma unroll 1
+  for (int c = 0; c < 2; c++) {   // one copy of absorb + mix for both chunks (code size, see hs::combine)
+    if (c) settle(st);
+    u32 wa[8], wb[8];
+#pragma unroll
+    for (int g = 0; g < 8; g++) wa[g] = c ? ra[g] : la[g], wb[g] = c ? rb[g] : lb[g];
+    absorb_words_mix<false>(st, wa, wb);
+  }
+#pragma unroll 1
+  for (int k = 0; k < 8; k++) mix_lazy<true>(st);
+  settle(st);
   pack_words(st, oa, ob);
 }
 // two Hash::from_field_elements(&[v]) (hash.rs:32-35) at once
@@ -315,3 +342,136 @@ HS_HD void leaf2(u32 va, u32 vb, u32 *oa, u32 *ob, u32 one) {
   pack_words(st, oa, ob);
 }
 }  // namespace hs2
+
+// =====================================================================================================
+// hsq -- ONE hash on FOUR adjacent lanes (lane q = lane & 3 holds state bytes 8q .. 8q+7), for the narrow tree levels
+// and the FRI tail, where there are fewer hashes than lanes and the only thing that matters is the LATENCY of one hash.
+// A lone warp runs the one-hash-per-thread form (2.3 k dependent-ish instructions) in ~2.7 us; split over four lanes
+// every lane executes ~1.1 k instructions and the per-mix critical path is three shuffle hops + an 8-long add chain.
+//   mix_state (hash.rs:59-86): sbox and the 4-byte linear groups are lane-local.  The neighbour-add chain is the closed
+//   form  s'[i] = s[31] + sum_{k<=i} (s[k] + s[k+1])  (i <= 30),  s'[31] = s[31] + s'[0] + s'[30]:
+//   a local 8-element prefix, the three lower lanes' totals fetched with three independent shuffles, one more hop for s'[0].
+//   absorb (hash.rs:15-20): byte i xors into byte i+7, i.e. lane q's byte j depends on lane q-1's byte j+1 (and byte 7 on
+//   the lane's own byte 0), so the four lanes absorb in four phases; lane 3's bytes 1..7 wrap into lane 0's bytes 0..6.
+// Bytes are lazy as in hs (garbage above bit 7).  All 32 lanes of a warp must call these functions together.
+#if defined(__CUDACC__)
+namespace hsq {
+using hs::u32;
+static __constant__ u32 PRIMES_C[16] = HS_PRIMES;
+static __constant__ u32 RC_C[32] = HS_RC;
+
+struct Quad {
+  u32 s[8];
+  u32 rc[8];      // round constants of this lane's bytes
+  u32 rc251[8];   // (rc * 251) & 0xff: the pending constants folded into the next sbox multiply (see hs::mix_lazy)
+  u32 q, base;    // lane within the quad, warp lane of the quad's lane 0
+};
+__device__ __forceinline__ u32 shfl(u32 v, u32 lane) { return __shfl_sync(0xffffffffu, v, lane); }
+
+__device__ __forceinline__ void init(Quad &st) {
+  const u32 lane = threadIdx.x & 31u;
+  st.q = lane & 3u, st.base = lane & ~3u;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    st.s[j] = PRIMES_C[(8 * st.q + j) & 15];
+    st.rc[j] = RC_C[8 * st.q + j];
+    st.rc251[j] = (st.rc[j] * 251u) & 0xffu;
+  }
+}
+// mix_state without its final round-constant add (left pending, as hs::mix_lazy)
+template <bool PENDING>
+__device__ __forceinline__ void mix_lazy(Quad &st) {
+  u32 *s = st.s;
+#pragma unroll
+  for (int j = 0; j < 8; j++) s[j] = hs::rotl_lazy(s[j] * 251u + (PENDING ? st.rc251[j] : 0u), 1);
+#pragma unroll
+  for (int g = 0; g < 2; g++) {
+    const u32 t0 = s[4 * g], t1 = s[4 * g + 1], t2 = s[4 * g + 2], t3 = s[4 * g + 3];
+    const u32 x = t0 ^ t1 ^ t2 ^ t3;
+    s[4 * g] = x ^ t2 ^ 0x63u;
+    s[4 * g + 1] = x ^ t1 ^ 0x63u;
+    s[4 * g + 2] = x ^ t3 ^ 0x63u;
+    s[4 * g + 3] = x ^ t0 ^ 0x63u;
+  }
+  // neighbour add, closed form.  With t[k] = s[k] + s[k+1]:  s'[i] = s[31] + sum_{k<=i} t[k]  (i <= 30).
+  // Lane q's local inclusive prefix P[j] covers k = 8q .. 8q+j; its last term needs s[8q+8] = the next lane's s[0].
+  // Everything a lane needs from the others -- s[31], the lower lanes' partial totals (without that last s[0]) and the
+  // three s[0] values -- is fetched with INDEPENDENT shuffles, so a mix costs two shuffle hops, not a scan.
+  const u32 e0 = s[0] + s[1];
+  const u32 s31 = shfl(s[7], st.base + 3u);                                       // old s[31]
+  const u32 z1 = shfl(s[0], st.base + 1u), z2 = shfl(s[0], st.base + 2u), z3 = shfl(s[0], st.base + 3u);
+  const u32 n0 = s31 + shfl(e0, st.base);                                         // s'[0] = s[31] + s[0] + s[1]
+  u32 P[8];
+  P[0] = e0;
+#pragma unroll
+  for (int j = 1; j < 7; j++) P[j] = P[j - 1] + (s[j] + s[j + 1]);
+  const u32 Lp = P[6] + s[7];                                                     // lane total without s[8q+8]
+  const u32 a = shfl(Lp, st.base), b = shfl(Lp, st.base + 1u), c = shfl(Lp, st.base + 2u);
+  u32 O = s31;
+  if (st.q > 0) O += a + z1;
+  if (st.q > 1) O += b + z2;
+  if (st.q > 2) O += c + z3;
+  const u32 nxt0 = st.q == 0 ? z1 : (st.q == 1 ? z2 : z3);                        // s[8q+8] for lanes 0..2
+  const u32 last = (st.q == 3u) ? (s31 + n0 + (O + P[6])) : (O + Lp + nxt0);      // lane 3: s'[31] = s[31]+s'[0]+s'[30]
+#pragma unroll
+  for (int j = 0; j < 7; j++) s[j] = O + P[j];
+  s[7] = last;
+}
+__device__ __forceinline__ void settle(Quad &st) {
+#pragma unroll
+  for (int j = 0; j < 8; j++) st.s[j] += st.rc[j];
+}
+template <bool PENDING>
+__device__ __forceinline__ void finalize(Quad &st) {
+  mix_lazy<PENDING>(st);
+#pragma unroll 1
+  for (int k = 0; k < 7; k++) mix_lazy<true>(st);
+  settle(st);
+}
+// absorb a full 32-byte chunk, of which this lane holds bytes 8q .. 8q+7 as the little-endian words w0, w1, then mix
+template <bool PENDING>
+__device__ __forceinline__ void absorb_mix(Quad &st, u32 w0, u32 w1) {
+  if (PENDING) settle(st);
+  u32 *s = st.s;
+  u32 b[8], v[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) b[j] = ((j < 4 ? w0 : w1) >> (8 * (j & 3))) & 0xffu, v[j] = 0u;
+#pragma unroll
+  for (int p = 0; p < 4; p++) {
+    u32 in[7];
+#pragma unroll
+    for (int j = 0; j < 7; j++) in[j] = shfl(v[j + 1], st.base + ((p + 3) & 3));   // lane p-1's v[j+1]
+    if (st.q == (u32)p) {
+#pragma unroll
+      for (int j = 0; j < 7; j++) v[j] = hs::rotl_lazy((p ? (s[j] ^ in[j]) : s[j]) + b[j], 3);
+      v[7] = hs::rotl_lazy((s[7] ^ v[0]) + b[7], 3);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 7; j++) {
+    const u32 w = shfl(v[j + 1], st.base + 3u);   // bytes 25..31 wrap into bytes 0..6
+    s[j] = st.q == 0u ? (v[j] ^ w) : v[j];
+  }
+  s[7] = v[7];
+  mix_lazy<false>(st);
+}
+// Hash::combine (hash.rs:41-46) of the 32-byte hashes at `left` and `right`; every lane of the quad returns its own
+// 8 output bytes as two little-endian words (lane q: bytes 8q .. 8q+7)
+__device__ __forceinline__ void combine(const uint8_t *left, const uint8_t *right, u32 &o0, u32 &o1) {
+  Quad st;
+  init(st);
+  const uint2 l = *reinterpret_cast<const uint2 *>(left + 8 * st.q), r = *reinterpret_cast<const uint2 *>(right + 8 * st.q);
+#pragma unroll 1
+  for (int c = 0; c < 2; c++) {   // one copy of absorb + mix for both chunks (code size, see hs::combine)
+    if (c) settle(st);
+    absorb_mix<false>(st, c ? r.x : l.x, c ? r.y : l.y);
+  }
+#pragma unroll 1
+  for (int k = 0; k < 8; k++) mix_lazy<true>(st);
+  settle(st);
+  const u32 *s = st.s;
+  o0 = __byte_perm(__byte_perm(s[0], s[1], 0x0040), __byte_perm(s[2], s[3], 0x0040), 0x5410);
+  o1 = __byte_perm(__byte_perm(s[4], s[5], 0x0040), __byte_perm(s[6], s[7], 0x0040), 0x5410);
+}
+}  // namespace hsq
+#endif

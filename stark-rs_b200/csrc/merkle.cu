@@ -6,23 +6,17 @@
 // (merkle.rs:67-80) is a gather and nothing is ever rebuilt (the reference rebuilds every tree in the
 // query phase, fri.rs:288-298).
 //
-// Kernels: one hash per thread (hash.cuh).  Levels with > 1024 parents get one launch each; the last <= 11
-// levels are climbed by a single CTA through shared memory.  All of this is integer-pipe bound
-// (~1.9k thread-instructions per node hash against 96 bytes of traffic).
+// Kernels (hash.cuh): wide levels hash two nodes per thread (hs2, bound by the ALU pipe); levels with fewer than
+// 2^17 parents are latency-bound -- a node hash is a ~2 k-instruction dependency chain -- so there one CTA climbs up to
+// 10 levels of its 1024-node chunk through shared memory (k_merkle_climb), one hash per thread in the narrow steps.
+// The kernel that produces the root can also absorb it into the Fiat-Shamir transcript and draw alpha (transcript.cuh),
+// so a FRI round has no separate transcript launch.
 #include "common.cuh"
 #include "hash.cuh"
 #include "merkle.h"
+#include "merkle_dev.cuh"
 
 using hs::State;
-
-__device__ __forceinline__ void load_hash(const u8 *p, u32 *w) {
-  const uint4 a = reinterpret_cast<const uint4 *>(p)[0], b = reinterpret_cast<const uint4 *>(p)[1];
-  w[0] = a.x, w[1] = a.y, w[2] = a.z, w[3] = a.w, w[4] = b.x, w[5] = b.y, w[6] = b.z, w[7] = b.w;
-}
-__device__ __forceinline__ void store_hash(u8 *p, const u32 *w) {
-  reinterpret_cast<uint4 *>(p)[0] = make_uint4(w[0], w[1], w[2], w[3]);
-  reinterpret_cast<uint4 *>(p)[1] = make_uint4(w[4], w[5], w[6], w[7]);
-}
 
 // leaf i = Hash::from_field_elements(&[vals[i]])  (fri.rs:118-121, hash.rs:32-35); two leaves per thread (hs2)
 __global__ void __launch_bounds__(256) k_leaf_hash1(const u32 *__restrict__ vals, size_t n, u8 *__restrict__ out) {
@@ -116,41 +110,50 @@ __global__ void __launch_bounds__(256) k_merkle_level(const u8 *__restrict__ in,
   if (two) store_hash(out + 32 * i + 32, wb);
 }
 
-// the last levels: one CTA climbs from a level with m <= 2048 nodes to the root through shared memory,
-// writing every level to the tree array.  nodes = tree base, n = leaf count, level = input level.
-__global__ void __launch_bounds__(512) k_merkle_top(u8 *nodes, size_t n, u32 level) {
-  __shared__ __align__(16) u8 sm[1024 * 32];
-  size_t m = n >> level;
-  const u32 t = 2 * threadIdx.x;
-  bool first = true;
-  while (m > 1) {
-    const size_t half = m >> 1;
-    u32 wa[8], wb[8];
-    const bool act = t < half, two = t + 1 < half;
-    if (act) {
-      u32 la[8], ra[8], lb[8], rb[8];
-      const u8 *src = first ? nodes + 32 * (2 * n - 2 * m) : sm;
-      const u32 tb = two ? t + 1 : t;
-      load_hash(src + 64 * t, la);
-      load_hash(src + 64 * t + 32, ra);
-      load_hash(src + 64 * tb, lb);
-      load_hash(src + 64 * tb + 32, rb);
-      hs2::combine2(la, ra, lb, rb, wa, wb, blockDim.y);
-    }
+// CTA b climbs `levels` levels from the `cnt` nodes [b cnt, (b+1) cnt) of level `level_in` (cta_climb).  When the
+// climb ends at the root and tr.T is set, thread 0 runs the transcript round (fri.rs:129-138) on it.
+//   <256>: many CTAs, chunks of 512 nodes, 9 levels per launch (two hs2 steps, then seven 4-lanes-per-hash steps)
+//   <512>: the single top CTA, up to 1024 nodes
+template <int NT>
+__global__ void __launch_bounds__(NT) k_merkle_climb(u8 *nodes, size_t n, u32 level_in, u32 cnt, u32 levels,
+                                                     TranscriptArgs tr, u32 *counter) {
+  __shared__ __align__(16) u8 sm[2 * NT * 32];
+  __shared__ u32 ticket;
+  const u32 t = threadIdx.x;
+  const size_t first = (size_t)blockIdx.x * cnt;
+  cta_climb<NT>(nodes, n, level_in, first, cnt, levels, nodes + 32 * (level_off(n, level_in) + first), sm, blockDim.y);
+  u32 level = level_in + levels;
+  if (counter != nullptr && gridDim.x > 1) {
+    // Fused top: the LAST CTA to finish its chunk climbs the gridDim.x chunk roots to the tree root in this same launch
+    // (no second launch, and the hash code is already in this SM's instruction cache).
+    __threadfence();
     __syncthreads();
-    if (act) {
-      u8 *dst = nodes + 32 * (2 * n - 2 * half);
-      store_hash(sm + 32 * t, wa);
-      store_hash(dst + 32 * t, wa);
-      if (two) {
-        store_hash(sm + 32 * t + 32, wb);
-        store_hash(dst + 32 * t + 32, wb);
-      }
-    }
+    if (t == 0) ticket = atomicAdd(counter, 1u);
     __syncthreads();
-    first = false;
-    m = half;
+    if (ticket != gridDim.x - 1) return;
+    if (t == 0) *counter = 0u;   // ready for the next launch on this stream
+    __threadfence();
+    const u32 m = gridDim.x;     // <= NT nodes: 32 m bytes fit in sm
+    const uint4 *src = reinterpret_cast<const uint4 *>(nodes + 32 * level_off(n, level));
+    for (u32 i = t; i < 2 * m; i += NT) reinterpret_cast<uint4 *>(sm)[i] = __ldcg(src + i);   // written by other SMs
+    __syncthreads();
+    u32 top_levels = 0;
+    for (u32 c = m; c > 1; c >>= 1) top_levels++;
+    cta_climb<NT>(nodes, n, level, 0, m, top_levels, sm, sm, blockDim.y);
+    level += top_levels;
   }
+  if (tr.T != nullptr && t == 0 && (n >> level) == 1) {
+    u32 root[8];
+    load_hash(sm, root);
+    transcript_round(tr, root);
+  }
+}
+// the root of a one-leaf tree is the leaf itself (merkle.rs:11-38 with n = 1)
+__global__ void k_transcript_only(const u8 *root_hash, TranscriptArgs tr) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  u32 root[8];
+  load_hash(root_hash, root);
+  transcript_round(tr, root);
 }
 
 // gather authentication paths (merkle.rs:67-80): out[(q*depth + l)*32 ..] = nodes[level l][(idx[q] >> l) ^ 1]
@@ -185,11 +188,13 @@ int merkle_leaves_dev(stark_ctx *ctx, const u32 *vals, size_t n, u32 width, size
   return STARK_OK;
 }
 
-// nodes[0 .. n) already holds the leaves; fill the upper levels
-int merkle_climb_dev(stark_ctx *ctx, u8 *nodes, size_t n) {
+// nodes[0 .. n) already holds the leaves; fill the upper levels.  tr (optional): transcript round on the root.
+int merkle_climb_dev(stark_ctx *ctx, u8 *nodes, size_t n, const TranscriptArgs *tr) {
+  const TranscriptArgs none = {nullptr, nullptr, 0, nullptr, nullptr};
   u32 level = 0;
   size_t m = n;
-  while (m > 2048) {
+  // throughput-bound levels: one launch each
+  while ((m >> 1) >= ((size_t)1 << 17)) {
     const size_t half = m >> 1;
     LAUNCH(ctx, "merkle_level", 96ull * half,
            k_merkle_level<<<(u32)((half + 511) / 512), 256, 0, ctx->stream>>>(nodes + 32 * (2 * n - 2 * m),
@@ -197,9 +202,19 @@ int merkle_climb_dev(stark_ctx *ctx, u8 *nodes, size_t n) {
     m = half;
     level++;
   }
-  if (m > 1) {
-    LAUNCH(ctx, "merkle_top", 96ull * (m - 1), k_merkle_top<<<1, 512, 0, ctx->stream>>>(nodes, n, level));
+  // latency-bound levels (m <= 2^17 nodes left): chunks of 512 nodes climb 9 levels each and the last CTA to finish
+  // climbs the <= 256 chunk roots to the root; small trees are a single CTA
+  if (m > 1024) {
+    const size_t ctas = m / 512;
+    LAUNCH(ctx, "merkle_climb", 96ull * (m - 1),
+           k_merkle_climb<256><<<(u32)ctas, 256, 0, ctx->stream>>>(nodes, n, level, 512u, 9u, tr ? *tr : none, ctx->flag + 1));
+  } else if (m > 1) {
+    u32 levels = 0;
+    for (size_t c = m; c > 1; c >>= 1) levels++;
+    LAUNCH(ctx, "merkle_top", 96ull * (m - 1),
+           k_merkle_climb<512><<<1, 512, 0, ctx->stream>>>(nodes, n, level, (u32)m, levels, tr ? *tr : none, nullptr));
   }
+  if (n == 1 && tr) LAUNCH(ctx, "transcript", 0, k_transcript_only<<<1, 32, 0, ctx->stream>>>(nodes, *tr));
   return STARK_OK;
 }
 
@@ -280,11 +295,11 @@ int stark_merkle_build(stark_ctx *ctx, const uint8_t *leaves, size_t n, stark_tr
 
 }  // extern "C"
 int merkle_build_from_dev_values(stark_ctx *ctx, const u32 *vals, size_t n, u32 width, size_t row_stride,
-                                 size_t col_stride, stark_tree **out) {
+                                 size_t col_stride, stark_tree **out, const TranscriptArgs *tr) {
   stark_tree *t = nullptr;
   ST_TRY(merkle_tree_alloc(ctx, n, &t));
   int rc = merkle_leaves_dev(ctx, vals, n, width, row_stride, col_stride, t->nodes);
-  if (rc == STARK_OK) rc = merkle_climb_dev(ctx, t->nodes, n);
+  if (rc == STARK_OK) rc = merkle_climb_dev(ctx, t->nodes, n, tr);
   if (rc != STARK_OK) {
     stark_merkle_free(t);
     return rc;

@@ -68,3 +68,54 @@ extern "C" int stark_bench_int_peak(stark_ctx *ctx, double *imad_per_s, double *
   dev_free(ctx, d_out);
   return rc;
 }
+
+// ---- dependent-hash latency of ONE warp alone on an SM (the narrow Merkle levels and the FRI tail are chains of such
+// hashes): K chained Hash::combine(x, x) with the one-hash-per-thread (hs), two-per-thread (hs2) and four-lanes-per-hash
+// (hsq) forms; clock64 cycles per hash.
+#include "hash.cuh"
+__global__ void k_hash_latency(int mode, int K, unsigned long long *cycles, u32 *sink) {
+  __shared__ __align__(16) u8 buf[8 * 32];   // hsq reads its children from memory: per-quad scratch
+  u32 x[8], y[8];
+  for (int i = 0; i < 8; i++) x[i] = threadIdx.x * 8 + i, y[i] = ~x[i];
+  u8 *mine = buf + 32 * (threadIdx.x >> 2);
+  const u32 q = threadIdx.x & 3u;
+  *reinterpret_cast<uint2 *>(mine + 8 * q) = make_uint2(x[0], x[1]);
+  __syncwarp();
+  const unsigned long long t0 = clock64();
+  for (int k = 0; k < K; k++) {
+    if (mode == 0) {
+      u32 o[8];
+      hs::combine<false>(x, x, o);
+      for (int i = 0; i < 8; i++) x[i] = o[i];
+    } else if (mode == 1) {
+      u32 oa[8], ob[8];
+      hs2::combine2(x, x, y, y, oa, ob, blockDim.y);
+      for (int i = 0; i < 8; i++) x[i] = oa[i], y[i] = ob[i];
+    } else {
+      u32 o0, o1;
+      hsq::combine(mine, mine, o0, o1);
+      __syncwarp();
+      *reinterpret_cast<uint2 *>(mine + 8 * q) = make_uint2(o0, o1);
+      __syncwarp();
+      x[0] = o0;
+    }
+  }
+  const unsigned long long t1 = clock64();
+  if (threadIdx.x == 0) *cycles = (t1 - t0) / (unsigned long long)K;
+  if (x[0] == 0x12345678u && y[0] == 1u) *sink = x[1];
+}
+extern "C" int stark_bench_hash_latency(stark_ctx *ctx, double *hs_cycles, double *hs2_cycles, double *hsq_cycles) {
+  if (!ctx || !hs_cycles || !hs2_cycles || !hsq_cycles) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+  unsigned long long *d = nullptr, h[3];
+  ST_TRY(dev_alloc(ctx, (void **)&d, 64));
+  for (int mode = 0; mode < 3; mode++) {
+    k_hash_latency<<<1, 32, 0, ctx->stream>>>(mode, 4, d + mode, (u32 *)(d + 4));    // warm-up (instruction cache)
+    k_hash_latency<<<1, 32, 0, ctx->stream>>>(mode, 64, d + mode, (u32 *)(d + 4));
+    ctx->launches += 2;
+  }
+  CU_TRY(ctx, cudaMemcpyAsync(h, d, 24, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  dev_free(ctx, d);
+  *hs_cycles = (double)h[0], *hs2_cycles = (double)h[1], *hsq_cycles = (double)h[2];
+  return STARK_OK;
+}
