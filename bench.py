@@ -225,7 +225,6 @@ def run_ours(a):
     except Exception:
         pass
     hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
-    ipk = ctx.int_peak()
 
     kernels = {}
     for k in prof:
@@ -240,23 +239,41 @@ def run_ours(a):
             kernels[k["kernel"]]["hbm_frac"] = kernels[k["kernel"]]["achieved_gbs"] / hbm_peak
     dom = max(prof, key=lambda k: k["ms"])
     dk = kernels[dom["kernel"]]
-    # integer-pipe view of the hash kernels: thread-instructions per hash from the shipped SASS
-    INSTR = {"merkle_level": 2316.0, "leaf_hash": 1868.0}
-    int_pipe = None
-    if dom["kernel"] in INSTR:
-        hashes = dom["bytes"] / (96.0 if dom["kernel"] == "merkle_level" else 36.0)
-        ips = hashes * INSTR[dom["kernel"]] / (dom["ms"] * 1e-3)
-        int_pipe = {"hashes_per_s": hashes / (dom["ms"] * 1e-3), "thread_instr_per_hash_sass": INSTR[dom["kernel"]],
-                    "achieved_thread_instr_per_s": ips, "peak_thread_instr_per_s_mixed": ipk["mixed_per_s"],
-                    "peak_alu_only": ipk["alu_per_s"], "peak_imad_only": ipk["imad_per_s"],
-                    "frac_of_mixed_peak": ips / ipk["mixed_per_s"]}
+    # Integer-pipe view of the hash kernels ("integer-pipe utilisation for ... hashing").  B200 issues 64
+    # lanes/clk/SM on each of the ALU and FMA pipes (B300_MICROARCH.md: both rt_SMSP = 2), so a pipe's peak is
+    # sm_count * 64 * clock thread-instructions/s.  Per-hash instruction counts come from the ncu captures under
+    # profiles/ (smsp__inst_executed / hashes; ALU share from sm__inst_executed_pipe_alu): see DESIGN.md 3.4.
+    HASH = {"merkle_level": {"bytes": 96.0, "instr": 1796.0, "alu_instr": 1010.0},
+            "leaf_hash": {"bytes": 36.0, "instr": 1367.0, "alu_instr": 790.0},
+            "fold_leaf": {"bytes": 44.0, "instr": 1401.0, "alu_instr": 800.0}}
+    sm_count = torch.cuda.get_device_properties(local).multi_processor_count
+    sm_hz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0
+    pipe_peak = sm_count * 64.0 * sm_hz * 1e6
+    int_pipe = {}
+    for name, h in HASH.items():
+        k = next((x for x in prof if x["kernel"] == name), None)
+        if not k or not k["ms"]:
+            continue
+        hashes = k["bytes"] / h["bytes"]
+        rate = hashes / (k["ms"] * 1e-3)
+        int_pipe[name] = {"hashes_per_s": rate, "thread_instr_per_hash": h["instr"], "alu_instr_per_hash": h["alu_instr"],
+                          "alu_pipe_peak_thread_instr_per_s": pipe_peak,
+                          "frac_of_alu_pipe_peak": rate * h["alu_instr"] / pipe_peak,
+                          "frac_of_issue_peak": rate * h["instr"] / (2 * pipe_peak)}
+    # DRAM traffic of the dominant throughput kernel from the ncu --set full capture of this same command
+    # (profiles/r1k_bench_kernels_ncu_full.csv, k_merkle_level with 2^19 parents: 33.6 MB read + 5.4 MB written while the
+    # algorithmic bytes of that launch are 96 * 2^19 = 50.3 MB; the written level is still in L2 when the kernel ends)
+    NCU_TRAFFIC = {"merkle_level": {"launch": "2^19 parents", "traffic": 33573120 + 5376000, "algorithmic": 96 * (1 << 19)}}
     roofline = {
         "kernel": dom["kernel"], "bound": "hbm", "achieved": dk["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
-        "frac": (dk["achieved_gbs"] / hbm_peak) if dk["achieved_gbs"] else None, "traffic": None,
+        "frac": (dk["achieved_gbs"] / hbm_peak) if dk["achieved_gbs"] else None,
+        "traffic": NCU_TRAFFIC.get(dom["kernel"], {}).get("traffic"),
+        "traffic_note": NCU_TRAFFIC.get(dom["kernel"]),
         "peak_source": peak_src, "launches_per_step": dk["launches_per_step"], "avg_launch_ms":
             dom["ms"] / dom["launches"], "share_of_step": dk["share"],
-        "note": "the dominant kernel hashes (integer-pipe bound, SURVEY 8(d)); its HBM fraction is low by "
-                "construction -- see int_pipe; HBM-bound kernels (ntt_pass*, fri_fold) are listed under kernels",
+        "note": "the dominant kernels hash: they are integer-pipe bound (wide tree levels, leaves) or latency bound "
+                "(merkle_climb: a chain of ~2 us dependent hashes), so their HBM fraction is low by construction -- see "
+                "int_pipe; the HBM-bound kernels (ntt_pass*, fri_fold) are listed under kernels with their own fractions",
         "int_pipe": int_pipe,
     }
 
@@ -271,7 +288,7 @@ def run_ours(a):
                 "h2d_bytes_per_step": a.cols * n * 8, "d2h_bytes_per_step": proof_len + 32 * max(a.cols - 1, 0)},
         "gpu_launches": launches, "gpu_launches_per_step": launches / a.steps,
         "clocks": clocks, "roofline": roofline, "kernels": kernels,
-        "ms_per_step_profiled": ms_prof / a.steps, "int_peak": ipk,
+        "ms_per_step_profiled": ms_prof / a.steps, "hash_latency_cycles": ctx.hash_latency(),
     }
 
     if world == 1 and not a.no_cpu_baseline:

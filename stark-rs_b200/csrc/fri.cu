@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(TAIL_NT, 1) k_fri_tail(const __grid_constant__
 
 // fold_codeword (fri.rs:57-91) fused with the leaf hashing of the NEXT round (fri.rs:118-121): writes the folded
 // codeword and its leaf hashes in one pass, two outputs per thread (hs2).  h even.
-__global__ void __launch_bounds__(256) k_fold_leaf1(const u32 *__restrict__ cw, u32 *__restrict__ out, size_t h, int r,
+__global__ void __launch_bounds__(64) k_fold_leaf1(const u32 *__restrict__ cw, u32 *__restrict__ out, size_t h, int r,
                                                     GeoTables G, u32 g_r_m, const u32 *__restrict__ alpha_m,
                                                     u32 inv2off_m, u8 *__restrict__ leaves) {
   const size_t i = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
@@ -159,17 +159,34 @@ __global__ void __launch_bounds__(256) k_fold_leaf1(const u32 *__restrict__ cw, 
 __global__ void __launch_bounds__(256) k_sample_indices(const TranscriptDev *T, u64 *challenge_out, u64 size, u64 reduced,
                                                         u32 number, u64 *out) {
   __shared__ u64 cand[256];
+  __shared__ u64 seen_red[256];   // idx % reduced of the accepted indices
   __shared__ u32 pre[32];
   __shared__ u32 got;
   if (threadIdx.x == 0) {
-    const u64 c = tr_challenge(*T);
+    u64 c;
+    if (T->npend == 0) {
+      // FiatShamir::challenge on a chunk-aligned transcript: 8 finalisation mixes of the stored sponge
+      State st;
+#pragma unroll
+      for (int i = 0; i < 32; i++) st.s[i] = T->s[i];
+      hs::mix_lazy<false>(st);
+#pragma unroll 1
+      for (int k = 0; k < 7; k++) hs::mix_lazy<true>(st);
+      c = 0;
+#pragma unroll
+      for (int b = 0; b < 8; b++) c |= (u64)((st.s[b] + hs::rc_at(b)) & 0xffu) << (8 * b);
+    } else {
+      c = tr_challenge(*T);
+    }
     *challenge_out = c;
     State st;
     hs::init(st);
 #pragma unroll
     for (int i = 0; i < 8; i++) hs::absorb_byte(st, i, (u32)(c >> (8 * i)) & 0xffu);
     hs::mix_lazy<false>(st);
-    hs::finalize<true>(st);
+#pragma unroll 1
+    for (int k = 0; k < 8; k++) hs::mix_lazy<true>(st);
+    hs::settle(st);
     u32 seed[8];
     hs::pack_words(st, seed);
     State s2;
@@ -181,6 +198,8 @@ __global__ void __launch_bounds__(256) k_sample_indices(const TranscriptDev *T, 
   }
   __syncthreads();
   if (number == 0) return;
+  // size and reduced are powers of two for every Fri::new-accepted domain (fri.rs:37-44): % is a mask then
+  const bool pow2 = (size & (size - 1)) == 0 && (reduced & (reduced - 1)) == 0;
   for (u32 base = 0;; base += 256) {
     const u32 counter = base + threadIdx.x;
     State st;
@@ -190,20 +209,26 @@ __global__ void __launch_bounds__(256) k_sample_indices(const TranscriptDev *T, 
 #pragma unroll
     for (int i = 0; i < 4; i++) hs::absorb_byte(st, i, (counter >> (8 * i)) & 0xffu);   // u32 LE, fri.rs:199-200
     hs::mix_lazy<false>(st);
-    hs::finalize<true>(st);
+#pragma unroll 1
+    for (int k = 0; k < 8; k++) hs::mix_lazy<true>(st);
+    hs::settle(st);
     u64 v = 0;
 #pragma unroll
     for (int b = 24; b < 32; b++) v = (v << 8) | (u64)(st.s[b] & 0xffu);   // fri.rs:168-174: low 64 bits, big-endian
-    cand[threadIdx.x] = v % size;
+    cand[threadIdx.x] = pow2 ? (v & (size - 1)) : (v % size);
     __syncthreads();
     if (threadIdx.x == 0) {
       u32 g = got;
       for (u32 k = 0; k < 256 && g < number; k++) {
-        const u64 idx = cand[k], ri = idx % reduced;
+        const u64 idx = cand[k], ri = pow2 ? (idx & (reduced - 1)) : (idx % reduced);
         bool seen = false;
-        for (u32 j = 0; j < g; j++)
-          if (out[j] % reduced == ri) seen = true;
-        if (!seen) out[g++] = idx;
+        for (u32 j = 0; j < g; j++) seen |= seen_red[j & 255u] == ri && j < 256;
+        if (g >= 256)   // more accepted indices than the cache holds: fall back to the stored list
+          for (u32 j = 256; j < g; j++) seen |= (out[j] % reduced) == ri;
+        if (!seen) {
+          if (g < 256) seen_red[g] = ri;
+          out[g++] = idx;
+        }
       }
       got = g;
     }
@@ -447,7 +472,7 @@ static int fri_commit_dev(stark_ctx *ctx, const u32 *cw0, size_t n, u32 offset, 
     } else if (len % 2 == 0) {
       const u32 inv2off_m = ff::to_mont(ff::inv(ff::mul(2, off_prev)));
       LAUNCH(ctx, "fold_leaf", 12ull * len + 32ull * len,
-             k_fold_leaf1<<<(u32)((len / 2 + 255) / 256), 256, 0, ctx->stream>>>(s->cw[r - 1], s->cw[r], len, (int)(r - 1), G,
+             k_fold_leaf1<<<(u32)((len / 2 + 63) / 64), 64, 0, ctx->stream>>>(s->cw[r - 1], s->cw[r], len, (int)(r - 1), G,
                                                                               ff::to_mont(g_prev), s->d_alpha_m + (r - 1),
                                                                               inv2off_m, tree->nodes));
     } else {

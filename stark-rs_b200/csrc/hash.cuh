@@ -357,8 +357,6 @@ HS_HD void leaf2(u32 va, u32 vb, u32 *oa, u32 *ob, u32 one) {
 #if defined(__CUDACC__)
 namespace hsq {
 using hs::u32;
-static __constant__ u32 PRIMES_C[16] = HS_PRIMES;
-static __constant__ u32 RC_C[32] = HS_RC;
 
 struct Quad {
   u32 s[8];
@@ -368,14 +366,39 @@ struct Quad {
 };
 __device__ __forceinline__ u32 shfl(u32 v, u32 lane) { return __shfl_sync(0xffffffffu, v, lane); }
 
+// lane-dependent constants without lane-indexed constant-memory loads (those serialise per distinct address):
+// the four lanes' byte rows are packed into words and picked with selects
+__device__ __forceinline__ u32 pick4(u32 q, u32 a, u32 b, u32 c, u32 d) { return q < 2 ? (q == 0 ? a : b) : (q == 2 ? c : d); }
 __device__ __forceinline__ void init(Quad &st) {
   const u32 lane = threadIdx.x & 31u;
-  st.q = lane & 3u, st.base = lane & ~3u;
+  const u32 q = lane & 3u;
+  st.q = q, st.base = lane & ~3u;
+  constexpr u32 pr[16] = HS_PRIMES;
+  constexpr u32 rc[32] = HS_RC;
 #pragma unroll
-  for (int j = 0; j < 8; j++) {
-    st.s[j] = PRIMES_C[(8 * st.q + j) & 15];
-    st.rc[j] = RC_C[8 * st.q + j];
-    st.rc251[j] = (st.rc[j] * 251u) & 0xffu;
+  for (int w = 0; w < 2; w++) {
+    // bytes 4w .. 4w+3 of each lane's row, packed little-endian
+    u32 pk[4], rk[4], mk[4];
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+      pk[l] = rk[l] = mk[l] = 0;
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        const int i = 8 * l + 4 * w + b;
+        pk[l] |= pr[i & 15] << (8 * b);
+        rk[l] |= rc[i] << (8 * b);
+        mk[l] |= ((rc[i] * 251u) & 0xffu) << (8 * b);
+      }
+    }
+    const u32 pw = (q & 1u) ? pk[1] : pk[0];   // PRIMES repeat with period 16: lanes 0,2 / 1,3
+    const u32 rw = pick4(q, rk[0], rk[1], rk[2], rk[3]);
+    const u32 mw = pick4(q, mk[0], mk[1], mk[2], mk[3]);
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      st.s[4 * w + b] = (pw >> (8 * b)) & 0xffu;
+      st.rc[4 * w + b] = (rw >> (8 * b)) & 0xffu;
+      st.rc251[4 * w + b] = (mw >> (8 * b)) & 0xffu;
+    }
   }
 }
 // mix_state without its final round-constant add (left pending, as hs::mix_lazy)
@@ -428,31 +451,33 @@ __device__ __forceinline__ void finalize(Quad &st) {
   for (int k = 0; k < 7; k++) mix_lazy<true>(st);
   settle(st);
 }
-// absorb a full 32-byte chunk, of which this lane holds bytes 8q .. 8q+7 as the little-endian words w0, w1, then mix
+// absorb a full 32-byte chunk m[0..8) (little-endian words; EVERY lane holds the whole chunk), then mix.
+// The absorb loop (hash.rs:15-20: byte i xors into byte i+7) is a serial pass over all 32 state bytes, cheap in one
+// thread (7 independent chains of <= 5 links, ~130 cycles) and slow across lanes (each link would be a shuffle hop:
+// measured 560-620 cycles per chunk for lane-phased and Jacobi-sweep variants).  So the quad all-gathers its state
+// (two packed words per lane, 8 shuffles), every lane runs the same serial absorb on the full state, and keeps its own
+// eight bytes.
 template <bool PENDING>
-__device__ __forceinline__ void absorb_mix(Quad &st, u32 w0, u32 w1) {
+__device__ __forceinline__ void absorb_mix(Quad &st, const u32 *m) {
   if (PENDING) settle(st);
   u32 *s = st.s;
-  u32 b[8], v[8];
+  const u32 w0 = __byte_perm(__byte_perm(s[0], s[1], 0x0040), __byte_perm(s[2], s[3], 0x0040), 0x5410);
+  const u32 w1 = __byte_perm(__byte_perm(s[4], s[5], 0x0040), __byte_perm(s[6], s[7], 0x0040), 0x5410);
+  u32 S[32];
 #pragma unroll
-  for (int j = 0; j < 8; j++) b[j] = ((j < 4 ? w0 : w1) >> (8 * (j & 3))) & 0xffu, v[j] = 0u;
+  for (int l = 0; l < 4; l++) {
+    const u32 a = shfl(w0, st.base + l), b = shfl(w1, st.base + l);
 #pragma unroll
-  for (int p = 0; p < 4; p++) {
-    u32 in[7];
-#pragma unroll
-    for (int j = 0; j < 7; j++) in[j] = shfl(v[j + 1], st.base + ((p + 3) & 3));   // lane p-1's v[j+1]
-    if (st.q == (u32)p) {
-#pragma unroll
-      for (int j = 0; j < 7; j++) v[j] = hs::rotl_lazy((p ? (s[j] ^ in[j]) : s[j]) + b[j], 3);
-      v[7] = hs::rotl_lazy((s[7] ^ v[0]) + b[7], 3);
-    }
+    for (int j = 0; j < 4; j++) S[8 * l + j] = a >> (8 * j), S[8 * l + 4 + j] = b >> (8 * j);   // lazy bytes
   }
 #pragma unroll
-  for (int j = 0; j < 7; j++) {
-    const u32 w = shfl(v[j + 1], st.base + 3u);   // bytes 25..31 wrap into bytes 0..6
-    s[j] = st.q == 0u ? (v[j] ^ w) : v[j];
+  for (int i = 0; i < 32; i++) {
+    const u32 v = hs::rotl_lazy(S[i] + (m[i >> 2] >> (8 * (i & 3))), 3);
+    S[i] = v;
+    S[(i + 7) & 31] ^= v;
   }
-  s[7] = v[7];
+#pragma unroll
+  for (int j = 0; j < 8; j++) s[j] = pick4(st.q, S[j], S[8 + j], S[16 + j], S[24 + j]);
   mix_lazy<false>(st);
 }
 // Hash::combine (hash.rs:41-46) of the 32-byte hashes at `left` and `right`; every lane of the quad returns its own
@@ -460,11 +485,12 @@ __device__ __forceinline__ void absorb_mix(Quad &st, u32 w0, u32 w1) {
 __device__ __forceinline__ void combine(const uint8_t *left, const uint8_t *right, u32 &o0, u32 &o1) {
   Quad st;
   init(st);
-  const uint2 l = *reinterpret_cast<const uint2 *>(left + 8 * st.q), r = *reinterpret_cast<const uint2 *>(right + 8 * st.q);
 #pragma unroll 1
   for (int c = 0; c < 2; c++) {   // one copy of absorb + mix for both chunks (code size, see hs::combine)
     if (c) settle(st);
-    absorb_mix<false>(st, c ? r.x : l.x, c ? r.y : l.y);
+    const uint4 x = reinterpret_cast<const uint4 *>(c ? right : left)[0], y = reinterpret_cast<const uint4 *>(c ? right : left)[1];
+    const u32 m[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+    absorb_mix<false>(st, m);
   }
 #pragma unroll 1
   for (int k = 0; k < 8; k++) mix_lazy<true>(st);

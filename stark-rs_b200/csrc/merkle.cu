@@ -18,8 +18,12 @@
 
 using hs::State;
 
+// The hs2 kernels have no shared memory and no barrier, so small CTAs cost nothing and spread a mid-sized level
+// (a few hundred thousand hashes) evenly over the 148 SMs: 64 threads = 128 hashes per CTA.
+constexpr int HASH_NT = 64;
+
 // leaf i = Hash::from_field_elements(&[vals[i]])  (fri.rs:118-121, hash.rs:32-35); two leaves per thread (hs2)
-__global__ void __launch_bounds__(256) k_leaf_hash1(const u32 *__restrict__ vals, size_t n, u8 *__restrict__ out) {
+__global__ void __launch_bounds__(HASH_NT) k_leaf_hash1(const u32 *__restrict__ vals, size_t n, u8 *__restrict__ out) {
   const size_t i = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
   if (i >= n) return;
   const bool two = i + 1 < n;
@@ -96,7 +100,7 @@ __global__ void __launch_bounds__(128) k_hash_bytes(const u8 *__restrict__ msgs,
 }
 
 // one tree level: parent i = Hash::combine(child 2i, child 2i+1)  (merkle.rs:21-27); two parents per thread
-__global__ void __launch_bounds__(256) k_merkle_level(const u8 *__restrict__ in, u8 *__restrict__ out, size_t n_out) {
+__global__ void __launch_bounds__(HASH_NT) k_merkle_level(const u8 *__restrict__ in, u8 *__restrict__ out, size_t n_out) {
   const size_t i = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
   if (i >= n_out) return;
   const bool two = i + 1 < n_out;
@@ -181,7 +185,7 @@ int merkle_leaves_dev(stark_ctx *ctx, const u32 *vals, size_t n, u32 width, size
   if (n == 0) return STARK_OK;
   const u32 blocks = (u32)((n + 255) / 256);
   if (width == 1)
-    LAUNCH(ctx, "leaf_hash", 36ull * n, k_leaf_hash1<<<(u32)((n + 511) / 512), 256, 0, ctx->stream>>>(vals, n, out));
+    LAUNCH(ctx, "leaf_hash", 36ull * n, k_leaf_hash1<<<(u32)((n + 2 * HASH_NT - 1) / (2 * HASH_NT)), HASH_NT, 0, ctx->stream>>>(vals, n, out));
   else
     LAUNCH(ctx, "leaf_hash_w", (4ull * width + 32) * n,
            k_leaf_hashw<<<blocks, 256, 0, ctx->stream>>>(vals, n, width, row_stride, col_stride, out));
@@ -197,7 +201,7 @@ int merkle_climb_dev(stark_ctx *ctx, u8 *nodes, size_t n, const TranscriptArgs *
   while ((m >> 1) >= ((size_t)1 << 17)) {
     const size_t half = m >> 1;
     LAUNCH(ctx, "merkle_level", 96ull * half,
-           k_merkle_level<<<(u32)((half + 511) / 512), 256, 0, ctx->stream>>>(nodes + 32 * (2 * n - 2 * m),
+           k_merkle_level<<<(u32)((half + 2 * HASH_NT - 1) / (2 * HASH_NT)), HASH_NT, 0, ctx->stream>>>(nodes + 32 * (2 * n - 2 * m),
                                                                               nodes + 32 * (2 * n - 2 * half), half));
     m = half;
     level++;

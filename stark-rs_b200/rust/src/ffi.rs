@@ -56,7 +56,14 @@ extern "C" {
     pub fn stark_merkle_num_levels(t: *const StarkTree) -> u32;
     pub fn stark_merkle_level(t: *mut StarkTree, level: u32, out: *mut u8) -> i32;
     pub fn stark_merkle_open(t: *mut StarkTree, index: usize, out: *mut u8, n_hashes: *mut usize) -> i32;
+    pub fn stark_merkle_build_dev(ctx: *mut StarkCtx, leaves_dev: *const std::ffi::c_void, n: usize, out: *mut *mut StarkTree) -> i32;
+    pub fn stark_merkle_nodes_ptr(t: *const StarkTree) -> *mut std::ffi::c_void;
+    pub fn stark_merkle_open_batch(t: *mut StarkTree, idx: *const u64, n_idx: usize, out: *mut u8) -> i32;
     pub fn stark_merkle_free(t: *mut StarkTree);
+    pub fn stark_fri_fold_range_dev(ctx: *mut StarkCtx, codeword: *const StarkBuf, n: usize, alpha_raw: u64, offset: u64, omega: u64, i0: usize, count: usize, out: *mut StarkBuf, out_off: usize) -> i32;
+    pub fn stark_fiat_shamir_challenge(transcript: *const u8, len: usize, challenge_raw: *mut u64) -> i32;
+    pub fn stark_hash_from_u64(value: u64, out: *mut u8) -> i32;
+    pub fn stark_bench_hash_latency(ctx: *mut StarkCtx, hs_cycles: *mut f64, hs2_cycles: *mut f64, hsq_cycles: *mut f64) -> i32;
     pub fn stark_fri_num_rounds(domain_length: usize, expansion_factor: u32, num_colinearity_tests: u32, rounds: *mut u32) -> i32;
     pub fn stark_fri_fold(ctx: *mut StarkCtx, codeword: *const u64, n: usize, alpha_raw: u64, offset: u64, omega: u64, out: *mut u64) -> i32;
     pub fn stark_fri_fold_dev(ctx: *mut StarkCtx, codeword: *const StarkBuf, n: usize, alpha_raw: u64, offset: u64, omega: u64, out: *mut StarkBuf) -> i32;
