@@ -173,9 +173,9 @@ __global__ void __launch_bounds__(1024, 1) k_ntt_pass(const __grid_constant__ Pa
   }
 }
 
-// N >= 2^13: one multi-pass Stockham pass (ntt_pass.cuh).  8192-element tile, 256 threads, 32 KB of shared memory.
+// N >= 2^13: one multi-pass Stockham pass (ntt_pass.cuh).  4096-element tile, 128 threads, 16 KB of shared memory.
 template <int LOGR, int KIND>
-__global__ void __launch_bounds__(ntt2::NT, 4) k_ntt2_pass(const __grid_constant__ ntt2::PassParams A) {
+__global__ void __launch_bounds__(ntt2::NT, 8) k_ntt2_pass(const __grid_constant__ ntt2::PassParams A) {
   using namespace ntt2;
   typedef Plan<LOGR> PL;
   __shared__ __align__(16) q4 tile[1 << (TILE_LOG - 2)];
@@ -285,7 +285,7 @@ int ntt_transform(stark_ctx *ctx, const u32 *in, u32 *out, int log_n, bool inver
     return launch_pass<1, false>(ctx, A, batch, "ntt_single", 4ull * batch * (n_valid + N));
   }
 
-  // N >= 2^13: 2 or 3 Stockham passes with radices 2^6 .. 2^9 (ntt_pass.cuh)
+  // N >= 2^13: 2 or 3 Stockham passes with radices 2^5 .. 2^8 (ntt_pass.cuh)
   int plan[3];
   const int n_pass = ntt2::pass_plan(log_n, plan);
   // FIRST and MIDDLE passes are out of place, the LAST pass may run in place:
@@ -325,9 +325,9 @@ int ntt_transform(stark_ctx *ctx, const u32 *in, u32 *out, int log_n, bool inver
   if (r == R_ && kind == K_) {                                                                                   \
     LAUNCH(ctx, tag, bytes, (k_ntt2_pass<R_, K_><<<grid, ntt2::NT, 0, ctx->stream>>>(B)));                       \
   } else
-    NTT2_CASE(6, ntt2::FIRST) NTT2_CASE(7, ntt2::FIRST) NTT2_CASE(8, ntt2::FIRST) NTT2_CASE(9, ntt2::FIRST)
-    NTT2_CASE(6, ntt2::MIDDLE) NTT2_CASE(7, ntt2::MIDDLE) NTT2_CASE(8, ntt2::MIDDLE) NTT2_CASE(9, ntt2::MIDDLE)
-    NTT2_CASE(6, ntt2::LAST) NTT2_CASE(7, ntt2::LAST) NTT2_CASE(8, ntt2::LAST) NTT2_CASE(9, ntt2::LAST)
+    NTT2_CASE(6, ntt2::FIRST) NTT2_CASE(7, ntt2::FIRST) NTT2_CASE(8, ntt2::FIRST)
+    NTT2_CASE(6, ntt2::MIDDLE) NTT2_CASE(7, ntt2::MIDDLE) NTT2_CASE(8, ntt2::MIDDLE)
+    NTT2_CASE(5, ntt2::LAST) NTT2_CASE(6, ntt2::LAST) NTT2_CASE(7, ntt2::LAST) NTT2_CASE(8, ntt2::LAST)
     rc = stark_fail(ctx, STARK_ERR_ARG, "no NTT pass kernel for radix 2^%d", r);
 #undef NTT2_CASE
     src = dst, src_batch = dst_batch;

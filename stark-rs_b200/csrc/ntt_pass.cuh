@@ -4,11 +4,13 @@
 // src/univariate/eval.rs:16-21, interpolate.rs:6-44), natural order in and out.
 //
 // The transform is a radix-R_1, R_2(, R_3) decimation-in-frequency Stockham (autosort) FFT, one HBM/L2 PASS per
-// factor, R_i = 2^6 .. 2^9.  Pass i (s = R_1..R_{i-1}, M = N/R_i, u = q + s p with q < s):
+// factor, R_i = 2^5 .. 2^8.  Pass i (s = R_1..R_{i-1}, M = N/R_i, u = q + s p with q < s):
 //     in_j  = X[u + j M]                          j < R_i
 //     out_k = Y[q + s (R_i p + k)] = (sum_j in_j w_R^(jk)) * w_N^(s p k)
-// A CTA owns a TILE of R rows x C = 2^13/R adjacent columns u (8192 elements, 32 KB of shared memory, 256 threads,
-// 32 elements per thread), so 4-6 CTAs are resident per SM and one CTA's barriers hide behind the others' work.
+// A CTA owns a TILE of R rows x C = 2^12/R adjacent columns u (4096 elements, 16 KB of shared memory, 128 threads,
+// 32 elements per thread), so 8 CTAs are resident per SM and one CTA's barriers hide behind the others' work (8192-
+// element / 256-thread tiles measured 4-9 % slower: coarser barriers, and 512 tiles of a 2^22 transform balance worse
+// over 148 SMs than 1024).
 // Inside the tile the R-point column DFTs are again Stockham rounds (radix 8, plus one radix-2/4 round when
 // log2 R is not a multiple of 3) on registers: a thread holds an 8-row x 4-column block, does the butterflies there
 // and exchanges through shared memory between rounds.  The first round reads HBM directly (128-bit, coalesced along
@@ -29,8 +31,8 @@ using ntt::q4;
 using ntt::RootTables;
 
 enum Kind { FIRST = 0, MIDDLE = 1, LAST = 2 };
-constexpr int TILE_LOG = 13;   // elements per tile
-constexpr int NT = 256;        // threads per CTA
+constexpr int TILE_LOG = 12;   // elements per tile
+constexpr int NT = 128;        // threads per CTA
 
 struct PassParams {
   const u32 *in;
@@ -52,11 +54,12 @@ struct PassParams {
   u32 dpow[8];               // FIRST: w_N^(+-(R/8) k), k < 8, Montgomery form (see round_compute)
 };
 
-// pass radices (log2) for a transform of length 2^log_n, 13 <= log_n <= 23, largest first: its narrow 64-byte row
-// segments then only affect loads (the FIRST pass stores one contiguous block per tile).  Returns the pass count.
+// pass radices (log2) for a transform of length 2^log_n, 13 <= log_n <= 23, largest first (the FIRST pass stores one
+// contiguous block per tile, so its narrower row segments only affect loads).  Radix 2^9 would leave 32-byte rows in
+// a 4096-element tile and is not used.  Returns the pass count.
 inline int pass_plan(int log_n, int *r) {
-  static const int PLAN[11][3] = {{7, 6, 0}, {8, 6, 0}, {9, 6, 0}, {9, 7, 0}, {9, 8, 0}, {9, 9, 0},
-                                  {7, 6, 6}, {8, 6, 6}, {9, 6, 6}, {9, 7, 6}, {9, 8, 6}};
+  static const int PLAN[11][3] = {{7, 6, 0}, {7, 7, 0}, {8, 7, 0}, {8, 8, 0}, {6, 6, 5}, {6, 6, 6},
+                                  {7, 6, 6}, {7, 7, 6}, {7, 7, 7}, {8, 7, 7}, {8, 8, 7}};
   for (int i = 0; i < 3; i++) r[i] = PLAN[log_n - 13][i];
   return r[2] ? 3 : 2;
 }
@@ -88,8 +91,11 @@ struct Plan {
 template <int LOGC4>
 FF_HD u32 slot(u32 l, u32 c4) {
   if (LOGC4 >= 3) return (l << LOGC4) + (c4 ^ (l & 7u));
-  const u32 sr = l >> 1, pos = ((l & 1u) << 2) | c4;   // LOGC4 == 2: two rows form one 8-slot group
-  return (sr << 3) + (pos ^ (sr & 7u));
+  // LOGC4 == 2: two rows form one 8-slot group.  Quarter-warps touch two rows that differ in exactly one of the row
+  // bits 0, 2 or 3 (column-fastest) or eight consecutive rows (row-fastest): the low two slot bits rotate with the
+  // row pair, the half (bit 2) flips with row bits 2 and 3.
+  const u32 sr = l >> 1, pos = ((l & 1u) << 2) | c4;
+  return (sr << 3) + (pos ^ ((sr & 3u) | ((((sr >> 1) ^ (sr >> 2)) & 1u) << 2)));
 }
 
 // radix-2^LR DIF on a[0 .. 2^LR) in [0, 2p); a[pos] ends up holding output bitrev(pos).  The outputs are LAZY, in

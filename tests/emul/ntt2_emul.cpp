@@ -82,8 +82,8 @@ static void transform(const u32 *in, u32 *out, int log_n, int d, u32 batch, u64 
     B.pre_mode = kind == FIRST ? pre_mode : 0, B.pre_geo = pre_geo;
     B.post_mode = kind == LAST ? post_mode : 0, B.post_const = post_c, B.post_geo = post_geo;
 #define CASE(R_, K_) if (r == R_ && kind == K_) run_pass<R_, K_>(B, grid); else
-    CASE(6, FIRST) CASE(7, FIRST) CASE(8, FIRST) CASE(9, FIRST) CASE(6, MIDDLE) CASE(7, MIDDLE) CASE(8, MIDDLE)
-    CASE(9, MIDDLE) CASE(6, LAST) CASE(7, LAST) CASE(8, LAST) CASE(9, LAST) abort();
+    CASE(6, FIRST) CASE(7, FIRST) CASE(8, FIRST) CASE(6, MIDDLE) CASE(7, MIDDLE) CASE(8, MIDDLE)
+    CASE(5, LAST) CASE(6, LAST) CASE(7, LAST) CASE(8, LAST) abort();
     src = dst;
     logS += r;
   }
@@ -129,8 +129,8 @@ int main(int argc, char **argv) {
   init();
   int max_log = argc > 1 ? atoi(argv[1]) : 19;
   int fails = 0;
-  long bc = conflicts_all<6, FIRST>() + conflicts_all<7, FIRST>() + conflicts_all<8, FIRST>() + conflicts_all<9, FIRST>() +
-            conflicts_all<6, LAST>() + conflicts_all<7, LAST>() + conflicts_all<8, LAST>() + conflicts_all<9, LAST>();
+  long bc = conflicts_all<6, FIRST>() + conflicts_all<7, FIRST>() + conflicts_all<8, FIRST>() + conflicts_all<5, LAST>() +
+            conflicts_all<6, LAST>() + conflicts_all<7, LAST>() + conflicts_all<8, LAST>();
   printf("bank-conflicted quarter-warp accesses: %ld\n", bc);
   if (bc) fails++;
   // geometric table for scale tests: c * g^i
