@@ -31,6 +31,10 @@ ap.add_argument("--sizes", default="16,18,20,22,24,26")
 ap.add_argument("--cfg4-log-n", type=int, default=0, help="rows (log2) of the config-4 trace; 0 = skip")
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--check", action="store_true")
+ap.add_argument("--fused", action="store_true",
+                help="fold kernel stores straight into every rank's replica (symmetric memory: multicast / P2P) "
+                     "instead of fold + all-gather")
+ap.add_argument("--prove-log-n", type=int, default=0, help="also run a full sharded Fri::prove of this size; 0 = skip")
 a = ap.parse_args()
 
 world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -66,18 +70,35 @@ def timed(fn, reps):
     return sorted(ms)[len(ms) // 2], out
 
 
+arena = None
+if a.fused and world > 1:
+    try:
+        arena = D.SymmetricArena(1 << (max(int(x) for x in a.sizes.split(",")) - 1), "cuda:%d" % local)
+    except Exception as e:
+        if rank == 0:
+            print(json.dumps({"fused": "unavailable", "why": repr(e)}), flush=True)
+
+
 def one_round(cw, n, omega, transcript=b""):
     """one Fri::commit round (fri.rs:116-147) on G ranks: returns (root bytes, folded codeword)"""
     tree = D.build_tree(b, comm, cw, n, shard_min=1 << 14)
     root = tree.root_bytes()
     alpha = S.fiat_shamir_challenge(transcript + root)
     h = n // 2
-    nxt = b.new_codeword(h)
-    if world > 1 and h % world == 0:
+    if arena is not None and h % (4 * world) == 0:
+        per = h // world
+        arena.reset()
+        arena.barrier()                       # peers are done reading the previous round's replica
+        nxt, peers, mc = arena.carve(h)
+        b.fold_bcast(cw, n, alpha, 3, omega, rank * per, per, peers, mc)
+        arena.barrier()
+    elif world > 1 and h % world == 0:
+        nxt = b.new_codeword(h)
         per = h // world
         b.fold_range(cw, n, alpha, 3, omega, rank * per, per, nxt)
         comm.all_gather_inplace(nxt, rank * per, per)
     else:
+        nxt = b.new_codeword(h)
         b.fold_range(cw, n, alpha, 3, omega, 0, h, nxt)
     tree.free()
     return root, nxt
@@ -93,7 +114,9 @@ with torch.cuda.stream(stream):
         line = {"config": "cfg5 fold+commit round", "log_n": k, "n_gpus": world, "ms": ms,
                 "leaf_plus_node_hashes_per_s": (2 * n - 1) / (ms * 1e-3), "elements_per_s": n / (ms * 1e-3),
                 "domain": "genuine" if k <= 23 else "degenerate (omega = w_2^23), throughput-only",
-                "bytes_gathered_per_round": 32 * world + 4 * (n // 2) if world > 1 else 0}
+                "bytes_gathered_per_round": 32 * world + 4 * (n // 2) if world > 1 else 0,
+                "fold_exchange": ("fused (multicast)" if arena.mc else "fused (P2P stores)") if arena is not None
+                else ("nccl all_gather" if world > 1 else "none")}
         if a.check and rank == 0:
             solo = D.ShardedTree(n, b.subtree(cw, 0, n), None, D.Comm.__new__(D.Comm))
             ref_root = solo.sub.root_bytes()
@@ -104,6 +127,24 @@ with torch.cuda.stream(stream):
         if rank == 0:
             print(json.dumps(line), flush=True)
         del cw, nxt
+
+    if a.prove_log_n:
+        import oracle as O
+        O.build()
+        k = a.prove_log_n
+        col = O.splitmix64(4242, 1 << (k - 2))
+        lde = O.fast_lde(col, k - 2, 2, 3)
+        fri = D.ShardedFri(b, S.prim_nth_root(1 << k), 3, 1 << k, 4, 32)
+        fused = fri.enable_fused_fold() if a.fused else False
+        ms, (proof, top) = timed(lambda: fri.prove(b.upload(lde)), 2)
+        line = {"config": "sharded Fri::prove (host-orchestrated)", "log_n": k, "n_gpus": world, "ms": ms,
+                "fused_fold": bool(fused), "fused_rounds_per_proof": fri.fused_rounds // 4 if fused else 0,
+                "proof_bytes": len(proof)}
+        if a.check and rank == 0:
+            ref = O.fri_prove(lde, S.prim_nth_root(1 << k), 3, 4, 32)
+            line["identical_to_oracle"] = bool(proof == ref["proof"] and top == ref["top_indices"])
+        if rank == 0:
+            print(json.dumps(line), flush=True)
 
     if a.cfg4_log_n:
         log_n, lb, ng, gw = a.cfg4_log_n, 1, 8, 8

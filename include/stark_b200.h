@@ -163,6 +163,10 @@ int stark_fri_fold_dev(stark_ctx *ctx, const stark_buf *codeword, size_t n, uint
 /* one rank's share of Fri::fold_codeword (fri.rs:57-91), SURVEY 8(e): outputs [i0, i0+count) -> out[out_off ..] */
 int stark_fri_fold_range_dev(stark_ctx *ctx, const stark_buf *codeword, size_t n, uint64_t alpha_raw, uint64_t offset,
                              uint64_t omega, size_t i0, size_t count, stark_buf *out, size_t out_off);
+/* the same fused with the replication of the result: every output is stored straight into all ranks' replicas of the
+ * next codeword (peers[g], device addresses mapped on this device) or once through the NVSwitch multicast address */
+int stark_fri_fold_bcast_dev(stark_ctx *ctx, const stark_buf *codeword, size_t n, uint64_t alpha_raw, uint64_t offset,
+                             uint64_t omega, size_t i0, size_t count, void *const *peers, int n_peers, void *multicast);
 /* host-side transcript helpers of the sharded prover: FiatShamir::challenge (fiat_shamir.rs:19-25, raw u64) of a
  * host-held transcript and Hash::from_u64 (hash.rs:37-39, the index seed of fri.rs:272) */
 int stark_fiat_shamir_challenge(const uint8_t *transcript, size_t len, uint64_t *challenge_raw);

@@ -519,6 +519,13 @@ class Context:
                                             SZ(count), out_buf.h, SZ(out_off)))
         return out_buf
 
+    def fri_fold_bcast_dev(self, cw_buf, n, alpha_raw, offset, omega, i0, count, peer_ptrs, multicast_ptr=0):
+        """outputs [i0, i0+count) of fold_codeword stored straight into every rank's replica (peer device addresses)"""
+        arr = (C.c_void_p * max(len(peer_ptrs), 1))(*[C.c_void_p(int(p)) for p in peer_ptrs])
+        _chk(lib().stark_fri_fold_bcast_dev(self.h, cw_buf.h, SZ(n), U64(alpha_raw), U64(offset), U64(omega), SZ(i0),
+                                            SZ(count), arr, C.c_int(len(peer_ptrs)),
+                                            C.c_void_p(int(multicast_ptr)) if multicast_ptr else None))
+
     def fri_commit(self, codeword, offset, omega, expansion_factor, num_colinearity_tests, transcript=b""):
         cw, t = _u64(codeword), _b(transcript)
         h = C.c_void_p()

@@ -65,6 +65,43 @@ __global__ void __launch_bounds__(256) k_fri_fold(const u32 *__restrict__ cw, u3
   }
 }
 
+// fold fused with its all-gather (SURVEY 8(e), K8 "fused variant"): the rank computes its output range and stores every
+// result straight into ALL ranks' replicas of the next codeword -- one multimem.st through the NVSwitch multicast
+// address when there is one (the switch replicates the 16-byte store to every GPU), else one store per peer over
+// NVLink P2P -- so the transfer overlaps the arithmetic and no separate collective runs.  The caller brackets the
+// launch with the symmetric-memory barrier.
+struct FoldPeers {
+  u32 *out[8];   // every rank's replica of the next codeword (own included), indexed by the global output index
+  u32 *mc;       // multicast address of the same buffer, or nullptr
+  int n;
+};
+__global__ void __launch_bounds__(256) k_fri_fold_bcast(const u32 *__restrict__ cw, const __grid_constant__ FoldPeers P, size_t h, size_t i0,
+                                                        size_t i1, int r, GeoTables G, u32 g_r_m,
+                                                        const u32 *__restrict__ alpha_m, u32 inv2off_m) {
+  const u32 K = ff::canon(ff::mont_mul(*alpha_m, inv2off_m));
+  const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
+  for (size_t i = i0 + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < i1; i += stride) {
+    const uint4 x = *reinterpret_cast<const uint4 *>(cw + i), y = *reinterpret_cast<const uint4 *>(cw + h + i);
+    const u32 a[4] = {x.x, x.y, x.z, x.w}, b[4] = {y.x, y.y, y.z, y.w};
+    u32 o[4];
+    u32 tw = ff::canon(ff::mont_mul(ntt::geo_pow(G, (u64)i << r), K));
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      o[k] = ff::canon4(ff::half(a[k] + b[k]) + ff::mont_mul(a[k] + ff::P - b[k], tw));
+      if (k < 3) tw = ff::canon(ff::mont_mul(tw, g_r_m));
+    }
+    if (P.mc != nullptr) {
+      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(P.mc + i), "r"(o[0]), "r"(o[1]),
+                   "r"(o[2]), "r"(o[3])
+                   : "memory");
+    } else {
+      const uint4 v = make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll 1
+      for (int g = 0; g < P.n; g++) *reinterpret_cast<uint4 *>(P.out[g] + i) = v;
+    }
+  }
+}
+
 // -------------------------------------------------------------------------------------------- FRI tail
 
 // The last rounds of Fri::commit (fri.rs:116-147), codeword <= 2^11, as ONE single-CTA kernel: per round leaf hashes,
@@ -646,6 +683,39 @@ int stark_fri_fold_range_dev(stark_ctx *ctx, const stark_buf *codeword, size_t n
                              ff::to_mont(ff::inv(ff::mul(2, off))));
   dev_free(ctx, d_alpha);
   return rc;
+}
+
+// fold_codeword range fused with the replication of the result (k_fri_fold_bcast).  peers[g] = rank g's replica of the
+// next codeword (device addresses valid on THIS device: CUDA IPC / symmetric memory), multicast = NVSwitch multicast
+// address of the same buffer or NULL; all indexed from output 0.  i0, count multiples of 4.
+int stark_fri_fold_bcast_dev(stark_ctx *ctx, const stark_buf *codeword, size_t n, uint64_t alpha_raw, uint64_t offset,
+                             uint64_t omega, size_t i0, size_t count, void *const *peers, int n_peers, void *multicast) {
+  if (!ctx || !codeword || (!peers && !multicast)) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+  const size_t h = n / 2;
+  if (codeword->n < n || i0 + count > h) return stark_fail(ctx, STARK_ERR_ARG, "range out of bounds");
+  if (n_peers < 0 || n_peers > 8) return stark_fail(ctx, STARK_ERR_ARG, "at most 8 peers");
+  if ((h % 4) || (i0 % 4) || (count % 4)) return stark_fail(ctx, STARK_ERR_ARG, "fold range must be a multiple of 4");
+  if (count == 0) return STARK_OK;
+  u32 off, om;
+  reduce_params(ctx, offset, omega, &off, &om);
+  if (off == 0 || (om == 0 && h > 1)) return stark_fail(ctx, STARK_ERR_ARG, "no division by zero");  // ff.rs:182
+  const u32 g0 = om ? ff::inv(om) : 1u;
+  GeoTables G;
+  ST_TRY(geo_tables(ctx, g0, 1, h, &G));
+  u32 *d_alpha = nullptr;
+  ST_TRY(dev_alloc(ctx, (void **)&d_alpha, 4));
+  const u32 am = ff::to_mont(ff::reduce64(alpha_raw));
+  CU_TRY(ctx, cudaMemcpyAsync(d_alpha, &am, 4, cudaMemcpyHostToDevice, ctx->stream));
+  FoldPeers P;
+  memset(&P, 0, sizeof P);
+  P.n = n_peers, P.mc = (u32 *)multicast;
+  for (int g = 0; g < n_peers; g++) P.out[g] = (u32 *)peers[g];
+  size_t blocks = (count / 4 + 255) / 256, cap = (size_t)ctx->sm_count * 8;
+  LAUNCH(ctx, "fri_fold_bcast", 12ull * count,
+         k_fri_fold_bcast<<<(u32)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(
+             codeword->ptr, P, h, i0, i0 + count, 0, G, ff::to_mont(g0), d_alpha, ff::to_mont(ff::inv(ff::mul(2, off)))));
+  dev_free(ctx, d_alpha);
+  return STARK_OK;
 }
 
 // FiatShamir::challenge (fiat_shamir.rs:19-25) for a host-held transcript: first 8 bytes, little-endian, of

@@ -94,6 +94,11 @@ class CudaBackend:
         self.ctx.fri_fold_range_dev(a, n, alpha_raw, offset, omega, lo, cnt, o, lo)
         a.free(), o.free()
 
+    def fold_bcast(self, cw, n, alpha_raw, offset, omega, lo, cnt, peer_ptrs, multicast_ptr):
+        a = self._buf(cw, 0, n)
+        self.ctx.fri_fold_bcast_dev(a, n, alpha_raw, offset, omega, lo, cnt, peer_ptrs, multicast_ptr)
+        a.free()
+
     def gather_values(self, cw, idx):
         if not len(idx):
             return []
@@ -168,6 +173,39 @@ class Comm:
         return t.cpu().numpy()
 
 
+class SymmetricArena:
+    """One symmetric-memory allocation (torch.distributed._symmetric_memory: every rank's copy is mapped into every other
+    rank's address space over NVLink, plus an NVSwitch multicast address when the fabric supports it) from which the
+    folded codewords of all FRI rounds are carved, so that the fold kernel can store its results straight into every
+    replica (stark_fri_fold_bcast_dev) instead of running a separate all-gather.  NCCL process groups only."""
+
+    def __init__(self, n_elems, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.buf = symm.empty(n_elems, dtype=torch.int32, device=device)
+        self.h = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.ptrs = [int(p) for p in self.h.buffer_ptrs]
+        mc = 0
+        try:
+            mc = int(self.h.multicast_ptr or 0)
+        except Exception:
+            mc = 0
+        self.mc = mc
+        self.off = 0
+
+    def reset(self):
+        self.off = 0
+
+    def carve(self, n):
+        """-> (local tensor view, peer addresses, multicast address) of the next n elements"""
+        off = self.off
+        self.off += (n + 3) & ~3
+        assert self.off <= self.buf.numel()
+        return (self.buf[off:off + n], [p + 4 * off for p in self.ptrs], (self.mc + 4 * off) if self.mc else 0)
+
+    def barrier(self):
+        self.h.barrier(channel=0)
+
+
 # ------------------------------------------------------------------------------------------------- Merkle
 
 class ShardedTree:
@@ -230,6 +268,20 @@ class ShardedFri:
         self.omega, self.offset, self.n = int(omega), int(offset), int(domain_length)
         self.ef, self.nq, self.shard_min = int(expansion_factor), int(num_colinearity_tests), shard_min
         self.rounds = backend.num_rounds(self.n, self.ef, self.nq)      # raises the Fri::new panics
+        self.arena = None            # SymmetricArena: enables the fused fold + replicate path (enable_fused_fold)
+        self.fused_rounds = 0
+
+    def enable_fused_fold(self):
+        """Carve the folded codewords from symmetric memory and let the fold kernel write every replica itself.
+        Returns False (and keeps the all-gather path) when symmetric memory cannot be set up."""
+        if not (self.comm.nccl and self.comm.world > 1 and hasattr(self.b, "fold_bcast")):
+            return False
+        try:
+            self.arena = SymmetricArena(self.n, self.b.device, self.comm.group)
+        except Exception as e:       # no peer access / fabric handles in this environment
+            self.arena, self.fused_error = None, repr(e)
+            return False
+        return True
 
     def num_rounds(self):
         return self.rounds
@@ -240,6 +292,9 @@ class ShardedFri:
         G, g = comm.world, comm.rank
         om, off = self.omega % P, self.offset % P
         cw, codewords, trees = codeword, [], []
+        if self.arena is not None:
+            self.arena.reset()
+            self.arena.barrier()          # every rank is done with the previous proof's replicas
         for r in range(self.rounds):
             n = cw.numel()
             tree = build_tree(b, comm, cw, n, self.shard_min)
@@ -252,12 +307,20 @@ class ShardedFri:
             alpha = fs.challenge()                            # raw u64, fiat_shamir.rs:19-25
             codewords.append(cw)
             h = n // 2
-            nxt = b.new_codeword(h)
-            if G > 1 and n >= self.shard_min and h % G == 0:
+            if self.arena is not None and n >= self.shard_min and h % (4 * G) == 0:
+                # fused: the fold kernel stores its slice into every rank's replica (multicast or P2P), then a barrier
+                per = h // G
+                nxt, peers, mc = self.arena.carve(h)
+                b.fold_bcast(cw, n, alpha, off, om, g * per, per, peers, mc)
+                self.arena.barrier()
+                self.fused_rounds += 1
+            elif G > 1 and n >= self.shard_min and h % G == 0:
+                nxt = b.new_codeword(h)
                 per = h // G
                 b.fold_range(cw, n, alpha, off, om, g * per, per, nxt)
                 comm.all_gather_inplace(nxt, g * per, per)
             else:
+                nxt = b.new_codeword(h)
                 b.fold_range(cw, n, alpha, off, om, 0, h, nxt)
             cw = nxt
             om, off = om * om % P, off * off % P              # fri.rs:146-147

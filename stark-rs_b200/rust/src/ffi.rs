@@ -61,6 +61,7 @@ extern "C" {
     pub fn stark_merkle_open_batch(t: *mut StarkTree, idx: *const u64, n_idx: usize, out: *mut u8) -> i32;
     pub fn stark_merkle_free(t: *mut StarkTree);
     pub fn stark_fri_fold_range_dev(ctx: *mut StarkCtx, codeword: *const StarkBuf, n: usize, alpha_raw: u64, offset: u64, omega: u64, i0: usize, count: usize, out: *mut StarkBuf, out_off: usize) -> i32;
+    pub fn stark_fri_fold_bcast_dev(ctx: *mut StarkCtx, codeword: *const StarkBuf, n: usize, alpha_raw: u64, offset: u64, omega: u64, i0: usize, count: usize, peers: *const *mut std::ffi::c_void, n_peers: i32, multicast: *mut std::ffi::c_void) -> i32;
     pub fn stark_fiat_shamir_challenge(transcript: *const u8, len: usize, challenge_raw: *mut u64) -> i32;
     pub fn stark_hash_from_u64(value: u64, out: *mut u8) -> i32;
     pub fn stark_bench_hash_latency(ctx: *mut StarkCtx, hs_cycles: *mut f64, hs2_cycles: *mut f64, hsq_cycles: *mut f64) -> i32;
