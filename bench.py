@@ -102,7 +102,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -192,16 +192,18 @@ def run_ours(a):
     step_dev = lambda: ctx.prove_trace_dev(dev_cols, a.cols, a.log_n, a.log_blowup, 3, a.nq, roots, proof)
     step_e2e = lambda: ctx.prove_trace_ptr(host.data_ptr(), a.cols, a.log_n, a.log_blowup, 3, a.nq, roots, proof)
 
+    # clocks are sampled (nvidia-smi, 20 ms period) from before the warm-up to the end of the last timed pass: the timed
+    # region itself is a few tens of milliseconds, too short for more than a sample or two on its own
+    sampler = ClockSampler(local) if rank == 0 else None
+    time.sleep(0.3 if rank == 0 else 0.0)       # let nvidia-smi start before the GPU gets busy
     for _ in range(max(a.warmup, 3)):
         step_dev()
-    sampler = ClockSampler(local) if rank == 0 else None
     l0 = ctx.launches
     ms_dev = timed(step_dev, a.steps)
     launches = ctx.launches - l0
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, a.steps)
-    clocks = sampler.stop() if sampler else None
     proof_len = step_dev()
     proof_bytes = bytes(proof[:proof_len])
 
@@ -209,6 +211,7 @@ def run_ours(a):
     ctx.profile_begin()
     ms_prof = timed(step_dev, a.steps)
     prof = ctx.profile_end()
+    clocks = sampler.stop() if sampler else None
 
     elems = world * a.cols * N * a.steps
     value = elems / (ms_dev * 1e-3)

@@ -38,8 +38,10 @@ __global__ void k_transcript_challenge(const TranscriptDev *T, u64 *out) {
 template <int V>
 __global__ void __launch_bounds__(256) k_fri_fold(const u32 *__restrict__ cw, u32 *__restrict__ out, size_t h, size_t i0,
                                                   size_t i1, int r, GeoTables G, u32 g_r_m,
-                                                  const u32 *__restrict__ alpha_m, u32 inv2off_m) {
-  const u32 K = ff::canon(ff::mont_mul(*alpha_m, inv2off_m));
+                                                  const u32 *__restrict__ alpha_m, u32 alpha_val, u32 inv2off_m) {
+  // alpha (Montgomery form) comes from device memory inside Fri::commit (written by the transcript step) and by value
+  // from the stand-alone entry points
+  const u32 K = ff::canon(ff::mont_mul(alpha_m ? *alpha_m : alpha_val, inv2off_m));
   const size_t stride = (size_t)gridDim.x * blockDim.x * V;
   for (size_t i = i0 + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * V; i < i1; i += stride) {
     u32 a[V], b[V], o[V];
@@ -77,8 +79,8 @@ struct FoldPeers {
 };
 __global__ void __launch_bounds__(256) k_fri_fold_bcast(const u32 *__restrict__ cw, const __grid_constant__ FoldPeers P, size_t h, size_t i0,
                                                         size_t i1, int r, GeoTables G, u32 g_r_m,
-                                                        const u32 *__restrict__ alpha_m, u32 inv2off_m) {
-  const u32 K = ff::canon(ff::mont_mul(*alpha_m, inv2off_m));
+                                                        const u32 *__restrict__ alpha_m, u32 alpha_val, u32 inv2off_m) {
+  const u32 K = ff::canon(ff::mont_mul(alpha_m ? *alpha_m : alpha_val, inv2off_m));
   const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
   for (size_t i = i0 + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < i1; i += stride) {
     const uint4 x = *reinterpret_cast<const uint4 *>(cw + i), y = *reinterpret_cast<const uint4 *>(cw + h + i);
@@ -396,16 +398,16 @@ static void fri_state_free(stark_fri_state *s) {
 
 // out is indexed by the global output index (out[i] for i in [i0, i1))
 static int fold_launch_range(stark_ctx *ctx, const u32 *cw, u32 *out, size_t h, size_t i0, size_t i1, int r, GeoTables G,
-                             u32 g_r_m, const u32 *alpha_m, u32 inv2off_m) {
+                             u32 g_r_m, const u32 *alpha_m, u32 inv2off_m, u32 alpha_val = 0) {
   if (i1 <= i0) return STARK_OK;
   const size_t cnt = i1 - i0;
   if (h % 4 == 0 && i0 % 4 == 0 && cnt % 4 == 0) {
     size_t blocks = (cnt / 4 + 255) / 256, cap = (size_t)ctx->sm_count * 8;
     LAUNCH(ctx, "fri_fold", 12ull * cnt,
-           k_fri_fold<4><<<(u32)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(cw, out, h, i0, i1, r, G, g_r_m, alpha_m, inv2off_m));
+           k_fri_fold<4><<<(u32)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(cw, out, h, i0, i1, r, G, g_r_m, alpha_m, alpha_val, inv2off_m));
   } else {
     LAUNCH(ctx, "fri_fold", 12ull * cnt,
-           k_fri_fold<1><<<(u32)((cnt + 255) / 256), 256, 0, ctx->stream>>>(cw, out, h, i0, i1, r, G, g_r_m, alpha_m, inv2off_m));
+           k_fri_fold<1><<<(u32)((cnt + 255) / 256), 256, 0, ctx->stream>>>(cw, out, h, i0, i1, r, G, g_r_m, alpha_m, alpha_val, inv2off_m));
   }
   return STARK_OK;
 }
@@ -650,14 +652,9 @@ int stark_fri_fold_dev(stark_ctx *ctx, const stark_buf *codeword, size_t n, uint
   const u32 g0 = om ? ff::inv(om) : 1u;
   GeoTables G;
   ST_TRY(geo_tables(ctx, g0, 1, h, &G));
-  u32 *d_alpha = nullptr;
-  ST_TRY(dev_alloc(ctx, (void **)&d_alpha, 4));
-  const u32 am = ff::to_mont(ff::reduce64(alpha_raw));
-  CU_TRY(ctx, cudaMemcpyAsync(d_alpha, &am, 4, cudaMemcpyHostToDevice, ctx->stream));
-  int rc = fold_launch(ctx, codeword->ptr, out->ptr, h, 0, G, ff::to_mont(g0), d_alpha,
-                       ff::to_mont(ff::inv(ff::mul(2, off))));
-  dev_free(ctx, d_alpha);
-  return rc;
+  const u32 am = ff::to_mont(ff::reduce64(alpha_raw));   // alpha travels as a kernel argument: no allocation, no copy
+  return fold_launch_range(ctx, codeword->ptr, out->ptr, h, 0, h, 0, G, ff::to_mont(g0), nullptr,
+                           ff::to_mont(ff::inv(ff::mul(2, off))), am);
 }
 
 // one rank's share of fold_codeword (fri.rs:57-91): outputs [i0, i0 + count) written to out[out_off ..]
@@ -673,16 +670,11 @@ int stark_fri_fold_range_dev(stark_ctx *ctx, const stark_buf *codeword, size_t n
   const u32 g0 = om ? ff::inv(om) : 1u;
   GeoTables G;
   ST_TRY(geo_tables(ctx, g0, 1, h, &G));
-  u32 *d_alpha = nullptr;
-  ST_TRY(dev_alloc(ctx, (void **)&d_alpha, 4));
   const u32 am = ff::to_mont(ff::reduce64(alpha_raw));
-  CU_TRY(ctx, cudaMemcpyAsync(d_alpha, &am, 4, cudaMemcpyHostToDevice, ctx->stream));
   // the kernel indexes out by the global output index
   u32 *base = out->ptr + out_off;
-  int rc = fold_launch_range(ctx, codeword->ptr, base - i0, h, i0, i0 + count, 0, G, ff::to_mont(g0), d_alpha,
-                             ff::to_mont(ff::inv(ff::mul(2, off))));
-  dev_free(ctx, d_alpha);
-  return rc;
+  return fold_launch_range(ctx, codeword->ptr, base - i0, h, i0, i0 + count, 0, G, ff::to_mont(g0), nullptr,
+                           ff::to_mont(ff::inv(ff::mul(2, off))), am);
 }
 
 // fold_codeword range fused with the replication of the result (k_fri_fold_bcast).  peers[g] = rank g's replica of the
@@ -702,10 +694,7 @@ int stark_fri_fold_bcast_dev(stark_ctx *ctx, const stark_buf *codeword, size_t n
   const u32 g0 = om ? ff::inv(om) : 1u;
   GeoTables G;
   ST_TRY(geo_tables(ctx, g0, 1, h, &G));
-  u32 *d_alpha = nullptr;
-  ST_TRY(dev_alloc(ctx, (void **)&d_alpha, 4));
   const u32 am = ff::to_mont(ff::reduce64(alpha_raw));
-  CU_TRY(ctx, cudaMemcpyAsync(d_alpha, &am, 4, cudaMemcpyHostToDevice, ctx->stream));
   FoldPeers P;
   memset(&P, 0, sizeof P);
   P.n = n_peers, P.mc = (u32 *)multicast;
@@ -713,8 +702,7 @@ int stark_fri_fold_bcast_dev(stark_ctx *ctx, const stark_buf *codeword, size_t n
   size_t blocks = (count / 4 + 255) / 256, cap = (size_t)ctx->sm_count * 8;
   LAUNCH(ctx, "fri_fold_bcast", 12ull * count,
          k_fri_fold_bcast<<<(u32)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(
-             codeword->ptr, P, h, i0, i0 + count, 0, G, ff::to_mont(g0), d_alpha, ff::to_mont(ff::inv(ff::mul(2, off)))));
-  dev_free(ctx, d_alpha);
+             codeword->ptr, P, h, i0, i0 + count, 0, G, ff::to_mont(g0), nullptr, am, ff::to_mont(ff::inv(ff::mul(2, off)))));
   return STARK_OK;
 }
 
