@@ -209,18 +209,21 @@ HS_HD void from_bytes(const u8 *msg, size_t n, u8 *out) {
 }  // namespace hs
 
 // =====================================================================================================
-// hs2 -- TWO hashes per thread, one per 16-bit lane of every state register (lane 0 = bits 0-15, lane 1 =
-// bits 16-31).  ncu on the one-hash-per-thread kernel above shows the ALU pipe (LOP3/PRMT/SHF/IADD3) at 92 %
-// with the FMA pipe at 10 %: the kernel is bound by ALU-pipe instruction count.  Packing two hashes per
-// register halves every per-register instruction, and the formulation below moves the shifts and adds to the
-// FMA pipe (IMAD) so both pipes carry about the same load:
-//   lanes "clean" (< 256) on entry to the sbox:  y = v*251 + c   (one IMAD; each lane <= 64260 < 2^16)
-//   rotl8(z,k) of both lanes:  d = PRMT(y: b0,b0,b2,b2)  (masks + duplicates),  e = d << k as IMAD d*2^k,
-//                              r = PRMT(e: b1,0,b3,0)  -> clean lanes again
+// hs2 -- TWO hashes per thread.  Lane 0 lives in bits 0-7 of every state register and may carry garbage up to bit 23;
+// lane 1 lives in bits 24-31 (its carries fall off the top of the register).  ncu on the one-hash-per-thread kernel
+// shows the ALU pipe (LOP3/PRMT/SHF/IADD3) at 92 % with the FMA pipe at 10 %: the kernel is bound by ALU-pipe instruction
+// count.  Packing two hashes per register halves every per-register instruction, and the formulation below splits the
+// work evenly between the two 64-lane/clk pipes:
+//   sbox multiply on the raw register:  y = s*251 + c  (one IMAD).  Lane 0 needs no mask: its value stays below 2^15
+//                    (clean byte + at most 62 byte sums), so the product stays below 2^24 and never reaches lane 1;
+//                    lane 1's product overflows out of the register.  (A 16-bit lane layout needed an AND per register
+//                    per mix here: 16 % of all ALU-pipe instructions.)
+//   rotl8(z,k) of both lanes:  d = PRMT(y: b0,b0,b3,b3)  (selects the two exact bytes, duplicates them),
+//                              e = d << k as IMAD d*2^k,  r = PRMT(e: b1,0,0,b3)  -> clean lanes
 //   linear layer: 6 LOP3 per 4 registers, lanes stay clean
-//   neighbour chain: plain 32-bit adds; a lane grows to at most 255 + 31*510 + 1020 < 2^16, so lanes never
-//                    spill into each other; the next sbox masks.
-// Per hash and mix: ~72 ALU-pipe + ~64 FMA-pipe instructions instead of 144 + 32.
+//   neighbour chain: s[i] += s[i+1] + s[i-1]' is either one IADD3 (ALU pipe) or two IMAD adds (FMA pipe); the first
+//                    CHAIN_ALU bytes take the IADD3 form so that both pipes carry ~117 instructions per mix
+// Per hash pair and mix: ~117 ALU-pipe + ~116 FMA-pipe instructions (was 144 + 126 with 16-bit lanes).
 namespace hs2 {
 using hs::prime_at;
 using hs::rc_at;
@@ -237,20 +240,33 @@ HS_HD u32 prmt(u32 a, u32 b, u32 sel) {
 #endif
 }
 // a + b on the FMA pipe: a * one + b with `one` a RUNTIME 1 (ptxas folds a literal 1 back into IADD3, which
-// lands on the already saturated ALU pipe)
+// lands on the ALU pipe)
 HS_HD u32 add_fma(u32 a, u32 b, u32 one) { return a * one + b; }
-constexpr u32 M2 = 0x00ff00ffu;
-// rotl8 of both (8-bit, possibly dirty above bit 7) lanes by k; result lanes clean
-HS_HD u32 rotl2(u32 y, u32 k) { return prmt(prmt(y, 0u, 0x2200) * (1u << k), 0u, 0x4341); }
+HS_HD u32 xor3(u32 a, u32 b, u32 c) {
+#if defined(__CUDA_ARCH__)
+  u32 d;
+  asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+#else
+  return a ^ b ^ c;
+#endif
+}
+constexpr u32 BOTH = 0x01000001u;   // x * BOTH = the byte x in lane 0 (bits 0-7) and lane 1 (bits 24-31)
+constexpr u32 M2 = 0xff0000ffu;
+constexpr int CHAIN_ALU = 5;        // neighbour-chain bytes done as one IADD3 instead of two IMAD adds (pipe balance)
+// rotl8 of both lanes by k (lane 0 possibly dirty above bit 7); result lanes clean.  `pow2k` = 2^k as a RUNTIME value
+// (State2::one << k): with a literal the compiler strength-reduces the multiply to a shift/add on the ALU pipe, which is
+// the saturated one (ncu: ALU 92 %, FMA 38 % before this change).
+HS_HD u32 rotl2(u32 y, u32 pow2k) { return prmt(prmt(y, 0u, 0x3300) * pow2k, 0u, 0x3441); }
 
 struct State2 {
   u32 s[32];
-  u32 one;  // runtime constant 1 (see add_fma)
+  u32 one, two, eight;  // runtime constants 1, 2, 8 (see add_fma, rotl2)
 };
 HS_HD void init(State2 &st, u32 one) {
-  st.one = one;
+  st.one = one, st.two = one << 1, st.eight = one << 3;
 #pragma unroll
-  for (int i = 0; i < 32; i++) st.s[i] = prime_at(i) * 0x10001u;
+  for (int i = 0; i < 32; i++) st.s[i] = prime_at(i) * BOTH;
 }
 // mix_state (hash.rs:59-86) for both lanes, round constants left pending (see hs::mix_lazy)
 template <bool PENDING>
@@ -258,30 +274,34 @@ HS_HD void mix_lazy(State2 &st) {
   u32 *s = st.s;
 #pragma unroll
   for (int i = 0; i < 32; i++) {
-    const u32 c = PENDING ? ((rc_at(i) * 251u) & 0xffu) * 0x10001u : 0u;
-    s[i] = rotl2((s[i] & M2) * 251u + c, 1);
+    const u32 c = PENDING ? ((rc_at(i) * 251u) & 0xffu) * BOTH : 0u;
+    s[i] = rotl2(s[i] * 251u + c, st.two);   // lane 0 < 2^15 here, so lane 0's product stays below bit 24
   }
 #pragma unroll
   for (int g = 0; g < 8; g++) {
+    // 6 LOP3 per group, pinned with lop3.b32 (left to itself the compiler emits 8): x = t0^t1^t2^t3 in two, then
+    // each output = x ^ t_j ^ 0x63 in one three-input XOR
     const u32 t0 = s[4 * g], t1 = s[4 * g + 1], t2 = s[4 * g + 2], t3 = s[4 * g + 3];
-    const u32 x = t0 ^ t1 ^ t2 ^ t3;
-    s[4 * g] = x ^ t2 ^ 0x00630063u;
-    s[4 * g + 1] = x ^ t1 ^ 0x00630063u;
-    s[4 * g + 2] = x ^ t3 ^ 0x00630063u;
-    s[4 * g + 3] = x ^ t0 ^ 0x00630063u;
+    const u32 x = xor3(t0, t1, t2) ^ t3;
+    s[4 * g] = xor3(x, t2, 0x63u * BOTH);
+    s[4 * g + 1] = xor3(x, t1, 0x63u * BOTH);
+    s[4 * g + 2] = xor3(x, t3, 0x63u * BOTH);
+    s[4 * g + 3] = xor3(x, t0, 0x63u * BOTH);
   }
-  // s[i] += s[i+1] + s[i-1]' : the pair sums are independent (FMA pipe), only the running add is serial
+  // s[i] += s[i+1] + s[i-1]' (hash.rs:77-81).  Lane 0 grows to at most 255 + 31*510 + 1020 < 2^15, lane 1 wraps.
+  s[0] = s[0] + s[1] + s[31];
+#pragma unroll
+  for (int i = 1; i < CHAIN_ALU; i++) s[i] = s[i] + s[i + 1] + s[i - 1];
   u32 t[32];
 #pragma unroll
-  for (int i = 0; i < 31; i++) t[i] = add_fma(s[i], s[i + 1], st.one);
-  s[0] = add_fma(t[0], s[31], st.one);
+  for (int i = CHAIN_ALU; i < 31; i++) t[i] = add_fma(s[i], s[i + 1], st.one);   // independent pair sums (FMA pipe)
 #pragma unroll
-  for (int i = 1; i < 31; i++) s[i] = add_fma(t[i], s[i - 1], st.one);
+  for (int i = CHAIN_ALU; i < 31; i++) s[i] = add_fma(t[i], s[i - 1], st.one);    // the serial running add
   s[31] = s[31] + s[0] + s[30];
 }
 HS_HD void settle(State2 &st) {
 #pragma unroll
-  for (int i = 0; i < 32; i++) st.s[i] += rc_at(i) * 0x10001u;
+  for (int i = 0; i < 32; i++) st.s[i] += rc_at(i) * BOTH;
 }
 template <bool PENDING>
 HS_HD void finalize(State2 &st) {
@@ -292,12 +312,12 @@ HS_HD void finalize(State2 &st) {
 }
 // absorb the byte pair b (clean lanes) at position i (hash.rs:15-20); constants must be settled
 HS_HD void absorb_pair(State2 &st, int i, u32 b) {
-  const u32 v = rotl2(add_fma(st.s[i], b, st.one), 3);
+  const u32 v = rotl2(add_fma(st.s[i], b, st.one), st.eight);
   st.s[i] = v;
   st.s[(i + 7) & 31] ^= v;
 }
 // byte k (0..3) of word a -> lane 0, of word b -> lane 1, clean
-HS_HD u32 pair_bytes(u32 a, u32 b, int k) { return prmt(a, b, 0x0400u + (u32)k * 0x0101u) & M2; }
+HS_HD u32 pair_bytes(u32 a, u32 b, int k) { return prmt(a, b, ((4u + (u32)k) << 12) | (u32)k) & M2; }
 
 template <bool PENDING>
 HS_HD void absorb_words_mix(State2 &st, const u32 *wa, const u32 *wb) {
@@ -311,7 +331,7 @@ HS_HD void pack_words(const State2 &st, u32 *wa, u32 *wb) {
   for (int g = 0; g < 8; g++) {
     const u32 *s = st.s + 4 * g;
     wa[g] = prmt(prmt(s[0], s[1], 0x0040), prmt(s[2], s[3], 0x0040), 0x5410);
-    wb[g] = prmt(prmt(s[0], s[1], 0x0062), prmt(s[2], s[3], 0x0062), 0x5410);
+    wb[g] = prmt(prmt(s[0], s[1], 0x0073), prmt(s[2], s[3], 0x0073), 0x5410);
   }
 }
 // two Hash::combine (hash.rs:41-46) at once
