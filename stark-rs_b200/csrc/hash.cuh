@@ -437,25 +437,26 @@ __device__ __forceinline__ void mix_lazy(Quad &st) {
     s[4 * g + 3] = x ^ t0 ^ 0x63u;
   }
   // neighbour add, closed form.  With t[k] = s[k] + s[k+1]:  s'[i] = s[31] + sum_{k<=i} t[k]  (i <= 30).
-  // Lane q's local inclusive prefix P[j] covers k = 8q .. 8q+j; its last term needs s[8q+8] = the next lane's s[0].
-  // Everything a lane needs from the others -- s[31], the lower lanes' partial totals (without that last s[0]) and the
-  // three s[0] values -- is fetched with INDEPENDENT shuffles, so a mix costs two shuffle hops, not a scan.
+  // A lane's total telescopes: sum_{k=8q}^{8q+7} t[k] = 2 T_q - s[8q] + s[8q+8] with T_q the lane's byte sum, so the
+  // offset of lane q is  O_q = s[31] + 2 (T_0 + .. + T_{q-1}) - s[0] + s[8q]  and needs only T of the lower lanes,
+  // s[0] and s[31]: ONE hop of independent shuffles per mix (the local prefix runs underneath it).
   const u32 e0 = s[0] + s[1];
+  const u32 T = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
   const u32 s31 = shfl(s[7], st.base + 3u);                                       // old s[31]
-  const u32 z1 = shfl(s[0], st.base + 1u), z2 = shfl(s[0], st.base + 2u), z3 = shfl(s[0], st.base + 3u);
+  const u32 z0 = shfl(s[0], st.base);                                             // s[0]
   const u32 n0 = s31 + shfl(e0, st.base);                                         // s'[0] = s[31] + s[0] + s[1]
-  u32 P[8];
+  const u32 a = shfl(T, st.base), b = shfl(T, st.base + 1u), c = shfl(T, st.base + 2u);
+  const u32 nxt0 = shfl(s[0], st.base + ((st.q + 1u) & 3u));                      // s[8q+8] (lanes 0..2)
+  u32 P[7];
   P[0] = e0;
 #pragma unroll
   for (int j = 1; j < 7; j++) P[j] = P[j - 1] + (s[j] + s[j + 1]);
-  const u32 Lp = P[6] + s[7];                                                     // lane total without s[8q+8]
-  const u32 a = shfl(Lp, st.base), b = shfl(Lp, st.base + 1u), c = shfl(Lp, st.base + 2u);
-  u32 O = s31;
-  if (st.q > 0) O += a + z1;
-  if (st.q > 1) O += b + z2;
-  if (st.q > 2) O += c + z3;
-  const u32 nxt0 = st.q == 0 ? z1 : (st.q == 1 ? z2 : z3);                        // s[8q+8] for lanes 0..2
-  const u32 last = (st.q == 3u) ? (s31 + n0 + (O + P[6])) : (O + Lp + nxt0);      // lane 3: s'[31] = s[31]+s'[0]+s'[30]
+  u32 lower = 0;
+  if (st.q > 0) lower += a;
+  if (st.q > 1) lower += b;
+  if (st.q > 2) lower += c;
+  const u32 O = s31 + 2u * lower - z0 + s[0];
+  const u32 last = (st.q == 3u) ? (s31 + n0 + (O + P[6])) : (O + P[6] + s[7] + nxt0);   // lane 3: s'[31]
 #pragma unroll
   for (int j = 0; j < 7; j++) s[j] = O + P[j];
   s[7] = last;

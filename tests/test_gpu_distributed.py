@@ -82,3 +82,22 @@ def test_lde_commit_world1(backend, oracle):
         want.append(oracle.merkle_commit(oracle.hash_leaves(np.stack(ldes, axis=1).reshape(-1), gw)))
     assert roots.tobytes() == b"".join(want)
     assert commitment == oracle.merkle_commit(np.frombuffer(b"".join(want), dtype=np.uint8).reshape(ng, 32))
+
+
+def test_fold_bcast_writes_every_replica(backend, oracle):
+    """k_fri_fold_bcast with the P2P store path on one GPU: three 'replicas' (plain device buffers standing in for the
+    peers' mapped memory) must all receive the folded range, equal to the oracle's fold."""
+    n = 1 << 14
+    vals = oracle.splitmix64(21, n)
+    w = oracle.ff_prim_nth_root(n)
+    alpha = (1 << 64) - 59
+    cw = backend.upload(vals)
+    reps = [torch.zeros(n // 2, dtype=torch.int32, device="cuda:0") for _ in range(3)]
+    per = (n // 2) // 4
+    for g in range(4):                                  # four ranks' ranges, each stored into all replicas
+        backend.fold_bcast(cw, n, alpha, 3, w, g * per, per, [r.data_ptr() for r in reps], 0)
+    want = oracle.fast_fri_fold(vals, alpha, 3, w)
+    for r in reps:
+        assert np.array_equal(backend.download(r), want)
+    with pytest.raises(Exception):
+        backend.fold_bcast(cw, n, alpha, 3, w, 2, per, [reps[0].data_ptr()], 0)      # range not a multiple of 4
