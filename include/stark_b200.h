@@ -89,6 +89,11 @@ int stark_ff_prim_nth_root(uint64_t n, uint64_t *out);
  * (vector length, not degree).  out must hold na+nb-1 values. */
 int stark_poly_mul(stark_ctx *ctx, const uint64_t *a, size_t na, const uint64_t *b, size_t nb, uint64_t *out,
                    size_t *out_len);
+/* Polynomial::div (div.rs:6-53): quotient and remainder with the reference's vector lengths (intdiv = q with a zero
+ * remainder, modulo = r).  STARK_ERR_ARG "No division by zero" when the divisor is the zero polynomial.  q must hold
+ * na values, r must hold na + nb values.  O(n log n): Newton inversion of the reversed divisor over the NTT. */
+int stark_poly_div(stark_ctx *ctx, const uint64_t *a, size_t na, const uint64_t *b, size_t nb, uint64_t *q,
+                   size_t *q_len, uint64_t *r, size_t *r_len);
 /* Polynomial::eval_domain (eval.rs:16-21) on domain[i] = offset * w_N^i, N = 2^log_n, w_N = prim_nth_root(N)
  * (the pattern of fri.rs:575-578); nc <= N coefficients; natural order. */
 int stark_poly_eval_coset(stark_ctx *ctx, const uint64_t *coeffs, size_t nc, uint64_t offset, uint32_t log_n,

@@ -384,6 +384,16 @@ class Context:
         _chk(lib().stark_poly_mul(self.h, _p64(a), SZ(len(a)), _p64(b), SZ(len(b)), _p64(out), C.byref(n)))
         return out[: n.value].copy()
 
+    def poly_div(self, a, b):
+        """Polynomial::div (div.rs:6-53) -> (quotient, remainder)"""
+        a, b = _u64(a), _u64(b)
+        q = np.zeros(max(len(a), 1), dtype=np.uint64)
+        r = np.zeros(max(len(a) + len(b), 1), dtype=np.uint64)
+        nq, nr = SZ(), SZ()
+        _chk(lib().stark_poly_div(self.h, _p64(a), SZ(len(a)), _p64(b), SZ(len(b)), _p64(q), C.byref(nq), _p64(r),
+                                  C.byref(nr)))
+        return q[: nq.value].copy(), r[: nr.value].copy()
+
     def poly_eval_coset(self, coeffs, offset, log_n):
         c = _u64(coeffs)
         out = np.empty(1 << log_n, dtype=np.uint64)

@@ -139,6 +139,35 @@ __global__ void k_reduce_rows(const u32 *__restrict__ partial, u32 rows, u32 n, 
   out[k] = s;
 }
 
+// ---- Polynomial::div helpers (div.rs:6-53 by Newton inversion of the reversed divisor)
+// dst[i] = src[hi - i] for i < cnt (i <= hi), zero beyond: the first cnt coefficients of the reversed polynomial
+__global__ void k_reverse_copy(const u32 *__restrict__ src, size_t hi, u32 *__restrict__ dst, size_t cnt) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += stride) dst[i] = i <= hi ? src[hi - i] : 0u;
+}
+// t = 2 - t  (mod x^n)
+__global__ void k_two_minus(u32 *__restrict__ t, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    t[i] = i == 0 ? ff::sub(2u, t[0]) : ff::neg(t[i]);
+}
+// r[i] = a[i] - qb[i] for i < n_low (a beyond na and qb beyond nqb count as zero), r[i] = 0 for n_low <= i < len;
+// flag |= 4 when a coefficient at or above n_low of a - qb is non-zero (cannot happen for a correct quotient)
+__global__ void k_remainder(const u32 *__restrict__ a, size_t na, const u32 *__restrict__ qb, size_t nqb, size_t n_low,
+                            u32 *__restrict__ r, size_t len, u32 *flag) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
+    const u32 x = i < na ? a[i] : 0u, y = i < nqb ? qb[i] : 0u;
+    const u32 d = ff::sub(x, y);
+    if (i < n_low) {
+      r[i] = d;
+    } else {
+      r[i] = 0u;
+      if (d) atomicOr(flag, 4u);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------- device-level
 
 static u32 grid_for(stark_ctx *ctx, size_t n, u32 block) {
@@ -175,9 +204,127 @@ static int log2_exact(size_t n) {
   return l;
 }
 
+// out[0 .. keep) = the low `keep` coefficients of a * b (device, canonical); na, nb >= 1
+static int poly_mul_dev(stark_ctx *ctx, const u32 *a, size_t na, const u32 *b, size_t nb, u32 *out, size_t keep) {
+  const size_t m = na + nb - 1;
+  const int lg = log2_exact(m) < 3 ? 3 : log2_exact(m);
+  if (lg > ff::TWO_ADICITY) return stark_fail(ctx, STARK_ERR_ARG, "n > 2^23 not supported by this modulus");
+  const size_t M = (size_t)1 << lg;
+  u32 *fa = nullptr, *fb = nullptr;
+  ST_TRY(dev_alloc(ctx, (void **)&fa, M * 4));
+  ST_TRY(dev_alloc(ctx, (void **)&fb, M * 4));
+  ScaleSpec none = {ntt::SCALE_NONE, 1, 1};
+  int rc = ntt_transform(ctx, a, fa, lg, false, 1, M, M, na, none, none);
+  if (rc == STARK_OK) rc = ntt_transform(ctx, b, fb, lg, false, 1, M, M, nb, none, none);
+  if (rc == STARK_OK) {
+    k_pointwise<<<grid_for(ctx, M, 256), 256, 0, ctx->stream>>>(fa, fb, M);
+    ctx->launches++;
+    ScaleSpec post = {ntt::SCALE_CONST, ff::mul(ff::inv((u32)(M % ff::P)), ff::R1), 1};
+    rc = ntt_transform(ctx, fa, fb, lg, true, 1, M, M, M, none, post);
+  }
+  if (rc == STARK_OK) {
+    const size_t n = keep < m ? keep : m;
+    CU_TRY(ctx, cudaMemcpyAsync(out, fb, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (keep > m) CU_TRY(ctx, cudaMemsetAsync(out + m, 0, (keep - m) * 4, ctx->stream));
+  }
+  dev_free(ctx, fa), dev_free(ctx, fb);
+  return rc;
+}
+
+// Polynomial::div (div.rs:6-53) for deg a = da >= deg b = db >= 0 on device data: q gets k = da - db + 1 coefficients,
+// r gets r_len coefficients (zeros above db - 1).  Quotient by Newton inversion of the reversed divisor:
+//   rev(q) = rev(a) * rev(b)^-1 mod x^k,   g <- g (2 - rev(b) g) doubling the precision each step.
+static int poly_div_dev(stark_ctx *ctx, const u32 *a, size_t na, size_t da, const u32 *b, size_t db, u32 *q, u32 *r,
+                        size_t r_len) {
+  const size_t k = da - db + 1;
+  u32 *ra = nullptr, *rb = nullptr, *g = nullptr, *t = nullptr, *qb = nullptr;
+  ST_TRY(dev_alloc(ctx, (void **)&ra, k * 4));
+  ST_TRY(dev_alloc(ctx, (void **)&rb, k * 4));
+  ST_TRY(dev_alloc(ctx, (void **)&g, k * 4));
+  ST_TRY(dev_alloc(ctx, (void **)&t, k * 4));
+  ST_TRY(dev_alloc(ctx, (void **)&qb, (k + db) * 4));
+  k_reverse_copy<<<grid_for(ctx, k, 256), 256, 0, ctx->stream>>>(a, da, ra, k);
+  k_reverse_copy<<<grid_for(ctx, k, 256), 256, 0, ctx->stream>>>(b, db, rb, k);
+  ctx->launches += 2;
+  // g0 = lead(b)^-1 (div.rs:25 divides by the leading coefficient; it is non-zero by definition of the degree)
+  u32 lead = 0;
+  CU_TRY(ctx, cudaMemcpyAsync(&lead, b + db, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  const u32 g0 = ff::inv(lead);
+  CU_TRY(ctx, cudaMemcpyAsync(g, &g0, 4, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = STARK_OK;
+  for (size_t prec = 1; prec < k && rc == STARK_OK; prec *= 2) {
+    const size_t np = 2 * prec < k ? 2 * prec : k;
+    rc = poly_mul_dev(ctx, rb, np, g, prec, t, np);                         // t = rev(b) g mod x^np
+    if (rc != STARK_OK) break;
+    k_two_minus<<<grid_for(ctx, np, 256), 256, 0, ctx->stream>>>(t, np);    // t = 2 - t
+    ctx->launches++;
+    rc = poly_mul_dev(ctx, g, prec, t, np, g, np);                          // g = g t mod x^np
+  }
+  if (rc == STARK_OK) rc = poly_mul_dev(ctx, ra, k, g, k, t, k);            // rev(q) = rev(a) g mod x^k
+  if (rc == STARK_OK) {
+    k_reverse_copy<<<grid_for(ctx, k, 256), 256, 0, ctx->stream>>>(t, k - 1, q, k);
+    ctx->launches++;
+    rc = poly_mul_dev(ctx, q, k, b, db + 1, qb, k + db);                    // q b, da + 1 coefficients
+  }
+  if (rc == STARK_OK) {
+    CU_TRY(ctx, cudaMemsetAsync(ctx->flag, 0, 4, ctx->stream));
+    k_remainder<<<grid_for(ctx, r_len, 256), 256, 0, ctx->stream>>>(a, na, qb, k + db, db, r, r_len, ctx->flag);
+    ctx->launches++;
+  }
+  dev_free(ctx, ra), dev_free(ctx, rb), dev_free(ctx, g), dev_free(ctx, t), dev_free(ctx, qb);
+  return rc;
+}
+
 // ----------------------------------------------------------------------------------------------- C ABI
 
 extern "C" {
+
+// Polynomial::div (div.rs:6-53): (quotient, remainder) with the reference's vector lengths:
+//   deg b = -1 -> STARK_ERR_ARG "No division by zero";  deg a < deg b -> q = [], r = a (na coefficients);
+//   else q has deg a - deg b + 1 coefficients and r has max(na, deg a + 1 + (nb - 1 - deg b)) (the length the
+//   reference's repeated Polynomial::sub leaves behind), zeros above deg b - 1.
+int stark_poly_div(stark_ctx *ctx, const uint64_t *a, size_t na, const uint64_t *b, size_t nb, uint64_t *q,
+                   size_t *q_len, uint64_t *r, size_t *r_len) {
+  if (!ctx || !q_len || !r_len || (na && !a) || (nb && !b)) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+  long da = -1, db = -1;
+  for (size_t i = 0; i < na; i++)
+    if (a[i]) da = (long)i;
+  for (size_t i = 0; i < nb; i++)
+    if (b[i]) db = (long)i;
+  if (db < 0) return stark_fail(ctx, STARK_ERR_ARG, "No division by zero");   // div.rs:7-9
+  if (da < db) {                                                               // div.rs:10-18
+    *q_len = 0, *r_len = na;
+    if (na && !r) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+    for (size_t i = 0; i < na; i++) {
+      if (a[i] >= ff::P) return stark_fail(ctx, STARK_ERR_ARG, "non-canonical field element (value >= p) in input");
+      r[i] = a[i];
+    }
+    return STARK_OK;
+  }
+  const size_t k = (size_t)(da - db) + 1;
+  const size_t tz = nb - 1 - (size_t)db;
+  const size_t rl = na > (size_t)da + 1 + tz ? na : (size_t)da + 1 + tz;
+  if (!q || !r) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+  u32 *d_a = nullptr, *d_b = nullptr, *d_q = nullptr, *d_r = nullptr;
+  ST_TRY(dev_alloc(ctx, (void **)&d_a, na * 4));
+  ST_TRY(dev_alloc(ctx, (void **)&d_b, nb * 4));
+  ST_TRY(dev_alloc(ctx, (void **)&d_q, k * 4));
+  ST_TRY(dev_alloc(ctx, (void **)&d_r, rl * 4));
+  int rc = upload_u64(ctx, a, na, d_a);
+  if (rc == STARK_OK) rc = upload_u64(ctx, b, nb, d_b);
+  if (rc == STARK_OK) rc = poly_div_dev(ctx, d_a, na, (size_t)da, d_b, (size_t)db, d_q, d_r, rl);
+  if (rc == STARK_OK) rc = download_u64(ctx, d_q, k, q);
+  if (rc == STARK_OK) rc = download_u64(ctx, d_r, rl, r);
+  if (rc == STARK_OK) {
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->h_flag, ctx->flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (*ctx->h_flag & 4u) rc = stark_fail(ctx, STARK_ERR_CUDA, "internal error: quotient check failed");
+  }
+  dev_free(ctx, d_a), dev_free(ctx, d_b), dev_free(ctx, d_q), dev_free(ctx, d_r);
+  if (rc == STARK_OK) *q_len = k, *r_len = rl;
+  return rc;
+}
 
 int stark_poly_mul(stark_ctx *ctx, const uint64_t *a, size_t na, const uint64_t *b, size_t nb, uint64_t *out,
                    size_t *out_len) {

@@ -207,6 +207,22 @@ struct Polynomial {
     out.resize(n);
     return Polynomial(wrap(out, f), f);
   }
+  // div.rs:6-53: (quotient, remainder); panics "No division by zero"
+  static std::pair<Polynomial, Polynomial> div(const Polynomial &numer, const Polynomial &denom) {
+    const auto a = raw(numer.coeffs), b = raw(denom.coeffs);
+    std::vector<uint64_t> q(a.size() + 1), r(a.size() + b.size() + 1);
+    size_t nq = 0, nr = 0;
+    check(stark_poly_div(ctx(), a.data(), a.size(), b.data(), b.size(), q.data(), &nq, r.data(), &nr));
+    q.resize(nq), r.resize(nr);
+    return {Polynomial(wrap(q, numer.field), numer.field), Polynomial(wrap(r, numer.field), numer.field)};
+  }
+  static Polynomial intdiv(const Polynomial &numer, const Polynomial &denom) {  // div.rs:43-47
+    auto qr = div(numer, denom);
+    for (const auto &c : qr.second.coeffs)
+      if (c.value != 0) throw Panic("assertion failed: r.is_zero()");
+    return qr.first;
+  }
+  static Polynomial modulo(const Polynomial &numer, const Polynomial &denom) { return div(numer, denom).second; }  // div.rs:49-52
   static Polynomial zerofier(const std::vector<FieldElement> &domain) {  // mod.rs:77-96
     const auto d = raw(domain);
     std::vector<uint64_t> out(d.size() + 1);

@@ -35,6 +35,7 @@ extern "C" {
     pub fn stark_ff_vec_pow(ctx: *mut StarkCtx, a: *const u64, e: u64, out: *mut u64, n: usize) -> i32;
     pub fn stark_ff_prim_nth_root(n: u64, out: *mut u64) -> i32;
     pub fn stark_poly_mul(ctx: *mut StarkCtx, a: *const u64, na: usize, b: *const u64, nb: usize, out: *mut u64, out_len: *mut usize) -> i32;
+    pub fn stark_poly_div(ctx: *mut StarkCtx, a: *const u64, na: usize, b: *const u64, nb: usize, q: *mut u64, q_len: *mut usize, r: *mut u64, r_len: *mut usize) -> i32;
     pub fn stark_poly_eval_coset(ctx: *mut StarkCtx, coeffs: *const u64, nc: usize, offset: u64, log_n: u32, out: *mut u64) -> i32;
     pub fn stark_poly_interpolate_coset(ctx: *mut StarkCtx, vals: *const u64, offset: u64, log_n: u32, coeffs: *mut u64, out_len: *mut usize) -> i32;
     pub fn stark_poly_eval_domain(ctx: *mut StarkCtx, coeffs: *const u64, nc: usize, domain: *const u64, m: usize, out: *mut u64) -> i32;

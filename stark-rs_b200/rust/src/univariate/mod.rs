@@ -94,6 +94,18 @@ impl Polynomial {
         ffi::check(unsafe { ffi::stark_poly_zerofier_domain(ffi::ctx(), d.as_ptr(), d.len(), out.as_mut_ptr()) });
         Self::from_raw(out, field)
     }
+    /// div.rs:6-53 (quotient, remainder); panics "No division by zero"
+    pub fn div(numer: &Polynomial, denom: &Polynomial) -> (Polynomial, Polynomial) {
+        let (a, b) = (raw(&numer.coeffs), raw(&denom.coeffs));
+        let (mut q, mut r) = (vec![0u64; a.len() + 1], vec![0u64; a.len() + b.len() + 1]);
+        let (mut nq, mut nr) = (0usize, 0usize);
+        ffi::check(unsafe { ffi::stark_poly_div(ffi::ctx(), a.as_ptr(), a.len(), b.as_ptr(), b.len(), q.as_mut_ptr(), &mut nq, r.as_mut_ptr(), &mut nr) });
+        q.truncate(nq);
+        r.truncate(nr);
+        (Self::from_raw(q, numer.field), Self::from_raw(r, numer.field))
+    }
+    pub fn intdiv(numer: &Polynomial, denom: &Polynomial) -> Polynomial { let (q, r) = Self::div(numer, denom); assert!(r.is_zero()); q }
+    pub fn modulo(numer: &Polynomial, denom: &Polynomial) -> Polynomial { Self::div(numer, denom).1 }
     pub fn scale(&self, factor: &FieldElement) -> Polynomial {
         let (c, mut out) = (raw(&self.coeffs), vec![0u64; self.coeffs.len()]);
         ffi::check(unsafe { ffi::stark_poly_scale(ffi::ctx(), c.as_ptr(), c.len(), factor.value, out.as_mut_ptr()) });
@@ -107,3 +119,5 @@ impl Polynomial {
 impl std::ops::Add<&Polynomial> for &Polynomial { type Output = Polynomial; fn add(self, r: &Polynomial) -> Polynomial { Polynomial::add(self, r) } }
 impl std::ops::Sub<&Polynomial> for &Polynomial { type Output = Polynomial; fn sub(self, r: &Polynomial) -> Polynomial { Polynomial::sub(self, r) } }
 impl std::ops::Mul<&Polynomial> for &Polynomial { type Output = Polynomial; fn mul(self, r: &Polynomial) -> Polynomial { Polynomial::mul(self, r) } }
+impl std::ops::Div<&Polynomial> for &Polynomial { type Output = (Polynomial, Polynomial); fn div(self, r: &Polynomial) -> (Polynomial, Polynomial) { Polynomial::div(self, r) } }
+impl std::ops::Rem<&Polynomial> for &Polynomial { type Output = Polynomial; fn rem(self, r: &Polynomial) -> Polynomial { Polynomial::modulo(self, r) } }

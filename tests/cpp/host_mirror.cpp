@@ -52,6 +52,11 @@ int main() {
   auto ip = Polynomial::interpolate_domain(wrap({1, 2, 3}, field), wrap({1, 4, 9}, field));
   EXPECT(raw(ip.coeffs) == (std::vector<uint64_t>{0, 0, 1}));
   EXPECT(raw(Polynomial(wrap({2, 3}, field), field).scale(field.new_element(5)).coeffs) == (std::vector<uint64_t>{2, 15}));
+  // div.rs:83-123
+  auto qr = Polynomial::div(Polynomial(wrap({2, 3, 1}, field), field), Polynomial(wrap({1, 1}, field), field));
+  EXPECT(raw(qr.first.coeffs) == (std::vector<uint64_t>{2, 1}));
+  EXPECT(raw(Polynomial::modulo(Polynomial(wrap({1, 0, 1}, field), field), Polynomial(wrap({1, 1}, field), field)).coeffs)[0] == 2);
+  try { Polynomial::div(a, Polynomial(wrap({0}, field), field)); EXPECT(false); } catch (const Panic &e) { EXPECT(std::string(e.what()) == "No division by zero"); }
   // panics keep the reference's text
   try { field.inv(field.zero()); EXPECT(false); } catch (const Panic &e) { EXPECT(std::string(e.what()) == "no inverse"); }
   try { MerkleTree t3(std::vector<Hash>(3)); EXPECT(false); } catch (const Panic &e) { EXPECT(std::string(e.what()) == "Number of leaves must be power of 2"); }

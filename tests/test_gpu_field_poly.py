@@ -196,3 +196,48 @@ def test_lde_dev_and_ntt_dev(ctx, oracle):
     assert np.array_equal(tmp.download()[: 1 << log_n], oracle.fast_eval_coset(cols[: 1 << log_n], 1, log_n))
     ctx.ntt_dev(tmp, tmp, log_n, batch=n_cols, inverse=True)       # in place
     assert np.array_equal(tmp.download(), cols)
+
+
+def test_poly_div_vs_reference_algorithm(ctx, oracle, S):
+    """Polynomial::div / intdiv / modulo (div.rs:6-53): quotient, remainder AND their vector lengths"""
+    def chk(a, b):
+        q, r = ctx.poly_div(a, b)
+        qo, ro = oracle.poly_div(a, b)
+        assert np.array_equal(q, qo) and np.array_equal(r, ro), (len(a), len(b), len(q), len(qo), len(r), len(ro))
+    # the reference's own cases (div.rs:83-123): (2+3x+x^2)/(1+x) = 2+x r 0 ; (1+x^2)/(1+x) r 2
+    q, r = ctx.poly_div([2, 3, 1], [1, 1])
+    assert list(q) == [2, 1] and not r.any()
+    q, r = ctx.poly_div([1, 0, 1], [1, 1])
+    assert list(q) == [P - 1, 1] and list(r[:1]) == [2] and not r[1:].any()
+    rng = np.random.default_rng(5)
+    for na, nb in [(1, 1), (2, 1), (5, 3), (8, 8), (9, 8), (64, 1), (100, 37), (257, 129), (1000, 999), (4096, 17),
+                   (5000, 2500), (1 << 13, 1 << 12)]:
+        a = rng.integers(0, P, na, dtype=np.uint64)
+        b = rng.integers(0, P, nb, dtype=np.uint64)
+        b[-1] = max(int(b[-1]), 1)
+        chk(a, b)
+    chk([5, 4, 3], [1, 2, 3, 4])                         # deg a < deg b: ([], a)
+    chk([1, 2, 3, 0, 0], [4, 5, 0, 0, 0])                # trailing zeros on both sides (length rules)
+    chk([0, 0, 0], [7])                                  # zero numerator
+    chk([3, 1, 4, 1, 5, 9, 2, 6], [2])                   # constant divisor
+    a = rng.integers(0, P, 300, dtype=np.uint64)
+    b = rng.integers(1, P, 120, dtype=np.uint64)
+    prod = oracle.poly_mul(a, b)
+    q, r = ctx.poly_div(prod, b)                         # intdiv: exact division, zero remainder
+    assert np.array_equal(q, a) and not r.any()
+    with pytest.raises(S.StarkPanic, match="No division by zero"):
+        ctx.poly_div([1, 2, 3], [0, 0])
+    with pytest.raises(S.StarkPanic, match="No division by zero"):
+        ctx.poly_div([1, 2, 3], [])
+
+
+def test_poly_div_large(ctx, oracle):
+    """2^18 / 2^17: checked through a = q b + r with the NTT multiply (the reference's long division is O(n m))"""
+    rng = np.random.default_rng(6)
+    a = rng.integers(0, P, 1 << 18, dtype=np.uint64)
+    b = rng.integers(1, P, 1 << 17, dtype=np.uint64)
+    q, r = ctx.poly_div(a, b)
+    assert len(q) == (1 << 18) - (1 << 17) + 1 and len(r) == 1 << 18 and not r[(1 << 17) - 1:].any()
+    back = oracle.fast_poly_mul(q, b)
+    back = (back[: 1 << 18] + r) % P
+    assert np.array_equal(back, a)
