@@ -50,6 +50,7 @@ __device__ __forceinline__ void cta_climb(uint8_t *nodes, size_t n, uint32_t lev
         const uint32_t pc = act ? p : 0;   // idle quads of a live warp hash parent 0 again (shuffles need all lanes)
         hsq::combine(src + 64 * pc, src + 64 * pc + 32, o0, o1);
       }
+      CLIMB_TICK();
       __syncthreads();
       if (act) {
         *reinterpret_cast<uint2 *>(sm + 32 * p + 8 * q) = make_uint2(o0, o1);
