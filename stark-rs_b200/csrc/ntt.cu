@@ -10,6 +10,8 @@
 //                T[n2*N1 + k1]  (column tile in, contiguous rows out)
 //        pass 2: N2-point transforms over n2 at stride N1, in place, X[k2*N1 + k1] -- natural order.
 //   HBM traffic: 8N bytes per pass (4 read + 4 written), nothing else (twiddle tables are <= 48 KB, L1/L2).
+#include <algorithm>
+
 #include "common.cuh"
 #include "ntt_pass.cuh"
 
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(1024, 1) k_ntt_pass(const __grid_constant__ Pa
 }
 
 // N >= 2^13: one multi-pass Stockham pass (ntt_pass.cuh).  4096-element tile, 128 threads, 16 KB of shared memory.
-template <int LOGR, int KIND>
+template <int LOGR, int KIND, int MODE>
 __global__ void __launch_bounds__(ntt2::NT, 8) k_ntt2_pass(const __grid_constant__ ntt2::PassParams A) {
   using namespace ntt2;
   typedef Plan<LOGR> PL;
@@ -184,16 +186,16 @@ __global__ void __launch_bounds__(ntt2::NT, 8) k_ntt2_pass(const __grid_constant
   const TileCtx T = tile_ctx<LOGR>(A, blockIdx.x);
   if (KIND == MIDDLE) fill_outer_table<LOGR>(tid, A, T, otw);
   u32 regs[32];
-  round_compute<LOGR, KIND, 0>(tid, A, T, tile, otw, regs);
+  round_compute<LOGR, KIND, 0, MODE>(tid, A, T, tile, otw, regs);
   round_store<LOGR, KIND, 0>(tid, A, T, tile, regs);
   __syncthreads();
   if constexpr (PL::NR == 3) {
-    round_compute<LOGR, KIND, 1>(tid, A, T, tile, otw, regs);
+    round_compute<LOGR, KIND, 1, MODE>(tid, A, T, tile, otw, regs);
     __syncthreads();
     round_store<LOGR, KIND, 1>(tid, A, T, tile, regs);
     __syncthreads();
   }
-  round_compute<LOGR, KIND, PL::NR - 1>(tid, A, T, tile, otw, regs);
+  round_compute<LOGR, KIND, PL::NR - 1, MODE>(tid, A, T, tile, otw, regs);
   round_store<LOGR, KIND, PL::NR - 1>(tid, A, T, tile, regs);
 }
 
@@ -291,18 +293,31 @@ int ntt_transform(stark_ctx *ctx, const u32 *in, u32 *out, int log_n, bool inver
   // FIRST and MIDDLE passes are out of place, the LAST pass may run in place:
   //   2 passes: in -> out -> out           (in == out: in -> tmp -> out)
   //   3 passes: in -> tmp -> out -> out
+  // The whole batch goes through each pass in one launch.  (Processing it in L2-sized groups, all passes of a group
+  // back to back so that intermediates never reach HBM, was measured SLOWER for 16 x 2^22 -- 468 vs 406 us: a launch of
+  // two transforms is only 1.7 waves of CTAs and the launch tails cost more than the DRAM traffic saved.  The loop is
+  // kept so the group size can be revisited.)
+  const u32 group = batch;
+  const u32 batch_total = batch;
+  const u32 *in_all = in;
+  u32 *out_all = out;
+  const u64 in_batch_all = in_batch;
   u32 *tmp = nullptr;
   const bool need_tmp = n_pass == 3 || in == out;
-  if (need_tmp) ST_TRY(dev_alloc(ctx, (void **)&tmp, (size_t)batch * N * 4));
+  if (need_tmp) ST_TRY(dev_alloc(ctx, (void **)&tmp, (size_t)std::min(batch_total, group) * N * 4));
   ntt2::PassParams B;
   memset(&B, 0, sizeof B);
   B.logN = log_n, B.log_tiles = log_n - ntt2::TILE_LOG;
   B.roots = roots, B.inverse = d;
   for (int k = 0; k < 4; k++) B.w8[k] = ctx->w8[d][k];
+  int rc = STARK_OK;
+  for (u32 b0 = 0; b0 < batch_total && rc == STARK_OK; b0 += group) {
+  batch = std::min(group, batch_total - b0);
+  in = in_all + (u64)b0 * in_batch_all, out = out_all + (u64)b0 * out_batch, in_batch = in_batch_all;
   const u32 grid = batch << B.log_tiles;
   const u32 *src = in;
   u64 src_batch = in_batch;
-  int logS = 0, rc = STARK_OK;
+  int logS = 0;
   for (int i = 0; i < n_pass && rc == STARK_OK; i++) {
     const int r = plan[i];
     const int kind = i == 0 ? ntt2::FIRST : (i == n_pass - 1 ? ntt2::LAST : ntt2::MIDDLE);
@@ -321,17 +336,31 @@ int ntt_transform(stark_ctx *ctx, const u32 *in, u32 *out, int log_n, bool inver
     B.post_mode = kind == ntt2::LAST ? post_mode : (int)SCALE_NONE, B.post_const = post_c, B.post_geo = post_geo;
     const u64 bytes = kind == ntt2::FIRST ? 4ull * batch * (n_valid + N) : 8ull * batch * N;
     const char *tag = kind == ntt2::FIRST ? "ntt_pass1" : (kind == ntt2::LAST ? "ntt_pass_last" : "ntt_pass_mid");
+    // compile-time specialisation of the per-element options (see round_compute)
+    const int mode = kind == ntt2::FIRST ? ((B.n_valid < N ? 1 : 0) | (B.pre_mode == SCALE_GEO ? 2 : 0))
+                                         : (kind == ntt2::LAST ? B.post_mode : 0);
+#define NTT2_LAUNCH(R_, K_, M_) LAUNCH(ctx, tag, bytes, (k_ntt2_pass<R_, K_, M_><<<grid, ntt2::NT, 0, ctx->stream>>>(B)))
 #define NTT2_CASE(R_, K_)                                                                                        \
   if (r == R_ && kind == K_) {                                                                                   \
-    LAUNCH(ctx, tag, bytes, (k_ntt2_pass<R_, K_><<<grid, ntt2::NT, 0, ctx->stream>>>(B)));                       \
+    if (K_ == ntt2::MIDDLE || mode == 0) {                                                                       \
+      NTT2_LAUNCH(R_, K_, 0);                                                                                    \
+    } else if (mode == 1) {                                                                                      \
+      NTT2_LAUNCH(R_, K_, 1);   /* FIRST: zero padding only; LAST: constant post-scale */                        \
+    } else if (K_ == ntt2::FIRST) {                                                                              \
+      NTT2_LAUNCH(R_, K_, 3);   /* FIRST: pre-scale (with or without zero padding) */                            \
+    } else {                                                                                                     \
+      NTT2_LAUNCH(R_, K_, 2);   /* LAST: geometric post-scale */                                                 \
+    }                                                                                                            \
   } else
     NTT2_CASE(6, ntt2::FIRST) NTT2_CASE(7, ntt2::FIRST) NTT2_CASE(8, ntt2::FIRST)
     NTT2_CASE(6, ntt2::MIDDLE) NTT2_CASE(7, ntt2::MIDDLE) NTT2_CASE(8, ntt2::MIDDLE)
     NTT2_CASE(5, ntt2::LAST) NTT2_CASE(6, ntt2::LAST) NTT2_CASE(7, ntt2::LAST) NTT2_CASE(8, ntt2::LAST)
     rc = stark_fail(ctx, STARK_ERR_ARG, "no NTT pass kernel for radix 2^%d", r);
+#undef NTT2_LAUNCH
 #undef NTT2_CASE
     src = dst, src_batch = dst_batch;
     logS += r;
+  }
   }
   dev_free(ctx, tmp);
   return rc;

@@ -180,7 +180,11 @@ FF_HD void decode(u32 t, u32 &up, u32 &c4) {
 
 // Phase A of round ROUND: gather the inputs (HBM in round 0, shared memory afterwards), butterflies, twiddles.
 // regs[(i*4 + x)*RAD + k] = output k of column x of task i.
-template <int LOGR, int KIND, int ROUND>
+// MODE specialises the per-element options at compile time (a run-time test per element costs more than it looks: the
+// LAST pass spent 64 of its ~1000 instructions per thread on the post-scale switch):
+//   FIRST:  bit 0 = some inputs are zero padding (n_valid < N), bit 1 = geometric pre-scale
+//   LAST:   the ntt::ScaleMode of the post-scale
+template <int LOGR, int KIND, int ROUND, int MODE>
 FF_HD void round_compute(u32 tid, const PassParams &A, const TileCtx &T, const q4 *smem, const u32 *otw, u32 *regs) {
   typedef Plan<LOGR> PL;
   constexpr int LR = PL::lr(ROUND), LOGS = PL::logs(ROUND), RAD = 1 << LR, NTASK = 8 >> LR;
@@ -199,7 +203,7 @@ FF_HD void round_compute(u32 tid, const PassParams &A, const TileCtx &T, const q
       q4 v;
       if (ROUND == 0) {
         const u64 cidx = ((u64)l << logM) + T.col0 + 4u * c4;   // coefficient index of the quad's first element
-        if (KIND != FIRST || cidx + 4 <= A.n_valid) {
+        if (KIND != FIRST || !(MODE & 1) || cidx + 4 <= A.n_valid) {
           v = *reinterpret_cast<const q4 *>(T.in + cidx);
         } else if (cidx >= A.n_valid) {
           v.x = v.y = v.z = v.w = 0u;   // zero padding is never read
@@ -209,7 +213,7 @@ FF_HD void round_compute(u32 tid, const PassParams &A, const TileCtx &T, const q
           v.z = cidx + 2 < A.n_valid ? T.in[cidx + 2] : 0u;
           v.w = 0u;
         }
-        if (KIND == FIRST && A.pre_mode == ntt::SCALE_GEO) {
+        if (KIND == FIRST && (MODE & 2)) {
           v.x = ff::mont_mul(v.x, ntt::geo_pow(A.pre_geo, cidx + 0));
           v.y = ff::mont_mul(v.y, ntt::geo_pow(A.pre_geo, cidx + 1));
           v.z = ff::mont_mul(v.z, ntt::geo_pow(A.pre_geo, cidx + 2));
@@ -256,9 +260,9 @@ FF_HD void round_compute(u32 tid, const PassParams &A, const TileCtx &T, const q
           } else if (KIND == MIDDLE) {
             val = ff::mont_mul(val, otw[row]);
           } else {
-            if (A.post_mode == ntt::SCALE_CONST) {
+            if (MODE == ntt::SCALE_CONST) {
               val = ff::canon(ff::mont_mul(val, A.post_const));
-            } else if (A.post_mode == ntt::SCALE_GEO) {
+            } else if (MODE == ntt::SCALE_GEO) {
               const u64 oidx = (u64)T.col0 + 4u * c4 + (u32)x + ((u64)row << A.logS);
               val = ff::canon(ff::mont_mul(val, ntt::geo_pow(A.post_geo, oidx)));
             } else {

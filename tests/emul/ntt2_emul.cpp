@@ -34,7 +34,7 @@ static void init() {
 
 static long g_range_viol = 0;
 
-template <int LOGR, int KIND>
+template <int LOGR, int KIND, int MODE>
 static void run_pass(const PassParams &A, u32 grid) {
   typedef Plan<LOGR> PL;
   std::vector<q4> tile(1 << (TILE_LOG - 2));
@@ -42,14 +42,14 @@ static void run_pass(const PassParams &A, u32 grid) {
   for (u32 blk = 0; blk < grid; blk++) {
     const TileCtx T = tile_ctx<LOGR>(A, blk);
     if (KIND == MIDDLE) for (u32 tid = 0; tid < NT; tid++) fill_outer_table<LOGR>(tid, A, T, otw.data());
-    for (u32 tid = 0; tid < NT; tid++) round_compute<LOGR, KIND, 0>(tid, A, T, tile.data(), otw.data(), &regs[tid * 32]);
+    for (u32 tid = 0; tid < NT; tid++) round_compute<LOGR, KIND, 0, MODE>(tid, A, T, tile.data(), otw.data(), &regs[tid * 32]);
     for (u32 tid = 0; tid < NT; tid++) round_store<LOGR, KIND, 0>(tid, A, T, tile.data(), &regs[tid * 32]);
     if (PL::NR == 3) {
-      for (u32 tid = 0; tid < NT; tid++) round_compute<LOGR, KIND, 1>(tid, A, T, tile.data(), otw.data(), &regs[tid * 32]);
+      for (u32 tid = 0; tid < NT; tid++) round_compute<LOGR, KIND, 1, MODE>(tid, A, T, tile.data(), otw.data(), &regs[tid * 32]);
       for (u32 tid = 0; tid < NT; tid++) round_store<LOGR, KIND, 1>(tid, A, T, tile.data(), &regs[tid * 32]);
     }
     for (auto &v : tile) if (v.x >= ff::P2 || v.y >= ff::P2 || v.z >= ff::P2 || v.w >= ff::P2) g_range_viol++;
-    for (u32 tid = 0; tid < NT; tid++) round_compute<LOGR, KIND, PL::NR - 1>(tid, A, T, tile.data(), otw.data(), &regs[tid * 32]);
+    for (u32 tid = 0; tid < NT; tid++) round_compute<LOGR, KIND, PL::NR - 1, MODE>(tid, A, T, tile.data(), otw.data(), &regs[tid * 32]);
     for (u32 tid = 0; tid < NT; tid++) round_store<LOGR, KIND, PL::NR - 1>(tid, A, T, tile.data(), &regs[tid * 32]);
   }
 }
@@ -81,7 +81,8 @@ static void transform(const u32 *in, u32 *out, int log_n, int d, u32 batch, u64 
     if (kind == FIRST) fill_first_pass_constants(B, r);
     B.pre_mode = kind == FIRST ? pre_mode : 0, B.pre_geo = pre_geo;
     B.post_mode = kind == LAST ? post_mode : 0, B.post_const = post_c, B.post_geo = post_geo;
-#define CASE(R_, K_) if (r == R_ && kind == K_) run_pass<R_, K_>(B, grid); else
+    const int mode = kind == FIRST ? ((B.n_valid < N ? 1 : 0) | (B.pre_mode == ntt::SCALE_GEO ? 2 : 0)) : (kind == LAST ? B.post_mode : 0);
+#define CASE(R_, K_) if (r == R_ && kind == K_) { if (K_ == MIDDLE || mode == 0) run_pass<R_, K_, 0>(B, grid); else if (mode == 1) run_pass<R_, K_, 1>(B, grid); else if (K_ == FIRST) run_pass<R_, K_, 3>(B, grid); else run_pass<R_, K_, 2>(B, grid); } else
     CASE(6, FIRST) CASE(7, FIRST) CASE(8, FIRST) CASE(6, MIDDLE) CASE(7, MIDDLE) CASE(8, MIDDLE)
     CASE(5, LAST) CASE(6, LAST) CASE(7, LAST) CASE(8, LAST) abort();
     src = dst;
