@@ -246,9 +246,11 @@ def run_ours(a):
     # lanes/clk/SM on each of the ALU and FMA pipes (B300_MICROARCH.md: both rt_SMSP = 2), so a pipe's peak is
     # sm_count * 64 * clock thread-instructions/s.  Per-hash instruction counts come from the ncu captures under
     # profiles/ (smsp__inst_executed / hashes; ALU share from sm__inst_executed_pipe_alu): see DESIGN.md 3.4.
-    HASH = {"merkle_level": {"bytes": 96.0, "instr": 1796.0, "alu_instr": 1010.0},
-            "leaf_hash": {"bytes": 36.0, "instr": 1367.0, "alu_instr": 790.0},
-            "fold_leaf": {"bytes": 44.0, "instr": 1401.0, "alu_instr": 800.0}}
+    # (round 1, final hs2 form: SASS of k_merkle_level / k_leaf_hash1 / k_fold_leaf1 -- two 528-instruction chunk
+    # iterations + eight 238-instruction mixes + ~180 per thread of two hashes; ALU = PRMT/LOP3/IADD3/..., FMA = IMAD)
+    HASH = {"merkle_level": {"bytes": 96.0, "instr": 1569.0, "alu_instr": 832.0},
+            "leaf_hash": {"bytes": 36.0, "instr": 1151.0, "alu_instr": 578.0},
+            "fold_leaf": {"bytes": 44.0, "instr": 1187.0, "alu_instr": 600.0}}
     sm_count = torch.cuda.get_device_properties(local).multi_processor_count
     sm_hz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0
     pipe_peak = sm_count * 64.0 * sm_hz * 1e6
@@ -263,10 +265,12 @@ def run_ours(a):
                           "alu_pipe_peak_thread_instr_per_s": pipe_peak,
                           "frac_of_alu_pipe_peak": rate * h["alu_instr"] / pipe_peak,
                           "frac_of_issue_peak": rate * h["instr"] / (2 * pipe_peak)}
-    # DRAM traffic of the dominant throughput kernel from the ncu --set full capture of this same command
-    # (profiles/r1k_bench_kernels_ncu_full.csv, k_merkle_level with 2^19 parents: 33.6 MB read + 5.4 MB written while the
-    # algorithmic bytes of that launch are 96 * 2^19 = 50.3 MB; the written level is still in L2 when the kernel ends)
-    NCU_TRAFFIC = {"merkle_level": {"launch": "2^19 parents", "traffic": 33573120 + 5376000, "algorithmic": 96 * (1 << 19)}}
+    # DRAM traffic per launch from ncu --set full captures of this same command (profiles/r1k_bench_kernels_ncu_full.csv,
+    # profiles/r1u_bench_kernels_ncu_full.csv), quoted with the algorithmic bytes of the SAME launch: the written level /
+    # tree is still in L2 when a kernel ends, so the measured write traffic is below the algorithmic figure
+    NCU_TRAFFIC = {"merkle_level": {"launch": "2^19 parents", "traffic": 33573120 + 5376000, "algorithmic": 96 * (1 << 19)},
+                   "merkle_climb": {"launch": "128 CTAs: 2^16 nodes -> root", "traffic": 2162944,
+                                    "algorithmic": 96 * ((1 << 16) - 1)}}
     roofline = {
         "kernel": dom["kernel"], "bound": "hbm", "achieved": dk["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
         "frac": (dk["achieved_gbs"] / hbm_peak) if dk["achieved_gbs"] else None,
@@ -274,9 +278,10 @@ def run_ours(a):
         "traffic_note": NCU_TRAFFIC.get(dom["kernel"]),
         "peak_source": peak_src, "launches_per_step": dk["launches_per_step"], "avg_launch_ms":
             dom["ms"] / dom["launches"], "share_of_step": dk["share"],
-        "note": "the dominant kernels hash: they are integer-pipe bound (wide tree levels, leaves) or latency bound "
-                "(merkle_climb: a chain of ~2 us dependent hashes), so their HBM fraction is low by construction -- see "
-                "int_pipe; the HBM-bound kernels (ntt_pass*, fri_fold) are listed under kernels with their own fractions",
+        "note": "the dominant kernels hash: merkle_level / leaf_hash / fold_leaf are integer-pipe bound (see int_pipe: "
+                "fraction of the 64 lanes/clk/SM ALU pipe), merkle_climb is latency bound (per tree a chain of ~17 dependent "
+                "node hashes of 1.5-3 us each on a handful of SMs, DESIGN.md section 4), so their HBM fraction is low by "
+                "construction; the HBM-bound kernels (ntt_pass*, fri_fold) are listed under kernels with their own fractions",
         "int_pipe": int_pipe,
     }
 

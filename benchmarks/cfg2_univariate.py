@@ -105,4 +105,5 @@ for logm in (k, k + 1, k + 2):
         print(json.dumps({"op": "device-resident %s" % ("iNTT" if inverse else "NTT"), "log_n": logm,
                           "us_kernels_only": ms * 1e3, "elems_per_s": (1 << logm) / (ms * 1e-3),
                           "kernels": {p["kernel"]: round(p["ms"] / a.reps * 1e3, 2) for p in prof}}))
+src.free(), dst.free()
 ctx.close()

@@ -151,7 +151,7 @@ class Buffer:
         return out
 
     def free(self):
-        if self.h:
+        if self.h and self.ctx.h:      # a handle must not outlive its context (the library frees through it)
             lib().stark_buf_free(self.h)
             self.h = None
 
@@ -213,7 +213,7 @@ class MerkleTree:
         return self.nodes_ptr + 32 * (2 * self.num_leaves - 2)
 
     def free(self):
-        if self.h:
+        if self.h and self.ctx.h:      # a handle must not outlive its context (the library frees through it)
             lib().stark_merkle_free(self.h)
             self.h = None
 
@@ -258,7 +258,7 @@ class FriState:
         return out[: n.value].copy()
 
     def free(self):
-        if self.h:
+        if self.h and self.ctx.h:      # a handle must not outlive its context (the library frees through it)
             lib().stark_fri_free(self.h)
             self.h = None
 
