@@ -106,11 +106,11 @@ __global__ void __launch_bounds__(256) k_fri_fold_bcast(const u32 *__restrict__ 
 
 // -------------------------------------------------------------------------------------------- FRI tail
 
-// The last rounds of Fri::commit (fri.rs:116-147), codeword <= 2^11, as ONE single-CTA kernel: per round leaf hashes,
+// The last rounds of Fri::commit (fri.rs:116-147), codeword <= 2^10, as ONE single-CTA kernel: per round leaf hashes,
 // the whole tree, the transcript round and the fold, back to back through shared memory.  These rounds are a pure
 // dependency chain (root -> alpha -> fold -> next leaves) of ~log2(n)+3 hash latencies each; run as separate launches
 // they cost a launch + drain per link.
-constexpr int TAIL_LOG = 9, TAIL_NT = 512, TAIL_MAX_ROUNDS = 12;
+constexpr int TAIL_LOG = 10, TAIL_NT = 512, TAIL_MAX_ROUNDS = 12;
 struct TailArgs {
   u32 n_rounds, first_round, len0;
   u32 *cw[TAIL_MAX_ROUNDS + 1];   // cw[i] = codeword of tail round i; cw[i + 1] receives its fold
@@ -146,11 +146,9 @@ __global__ void __launch_bounds__(TAIL_NT, 1) k_fri_tail(const __grid_constant__
     for (u32 c = len; c > 1; c >>= 1) levels++;
     cta_climb<TAIL_NT>(nodes, len, 0, 0, len, levels, nodes, sm, one);
     const bool last = i + 1 == A.n_rounds;
-    if (t == 0) {
-      u32 root[8];
-      load_hash(len > 1 ? sm : nodes, root);
+    if (t < 32) {
       const TranscriptArgs tr = {A.T, A.roots + 32 * i, last ? 0 : 1, A.alpha_raw + i, A.alpha_m + i};
-      transcript_round(tr, root);   // fri.rs:129-138
+      transcript_round_warp(tr, len > 1 ? sm : nodes);   // fri.rs:129-138
     }
     __syncthreads();
     if (last) break;   // fri.rs:133-135

@@ -146,11 +146,7 @@ __global__ void __launch_bounds__(NT) k_merkle_climb(u8 *nodes, size_t n, u32 le
     cta_climb<NT>(nodes, n, level, 0, m, top_levels, sm, sm, blockDim.y);
     level += top_levels;
   }
-  if (tr.T != nullptr && t == 0 && (n >> level) == 1) {
-    u32 root[8];
-    load_hash(sm, root);
-    transcript_round(tr, root);
-  }
+  if (tr.T != nullptr && t < 32 && (n >> level) == 1) transcript_round_warp(tr, sm);
 }
 // the root of a one-leaf tree is the leaf itself (merkle.rs:11-38 with n = 1)
 __global__ void k_transcript_only(const u8 *root_hash, TranscriptArgs tr) {

@@ -72,6 +72,43 @@ static __device__ __noinline__ uint64_t transcript_round_slow(TranscriptDev *T, 
   *T = t;
   return draw ? tr_challenge(t) : 0;
 }
+// The same round on ONE WARP (all 32 lanes must call it; every quad computes the same thing, lane 0 writes): the
+// 4-lanes-per-hash form (hsq) is ~2x shorter in latency than one thread, and this round sits on the critical path of
+// every FRI round.  root_bytes: the 32-byte root (shared or global memory).  Falls back to the one-thread form when
+// the transcript is not chunk-aligned.
+__device__ __forceinline__ void transcript_round(const TranscriptArgs &A, const uint32_t *root);
+__device__ __forceinline__ void transcript_round_warp(const TranscriptArgs &A, const uint8_t *root_bytes) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint4 x = reinterpret_cast<const uint4 *>(root_bytes)[0], y = reinterpret_cast<const uint4 *>(root_bytes)[1];
+  const uint32_t m[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+  TranscriptDev *T = A.T;
+  if (T->npend != 0) {      // warp-uniform
+    if (lane == 0) transcript_round(A, m);
+    return;
+  }
+  if (lane < 8) reinterpret_cast<uint32_t *>(A.root_out)[lane] = m[lane];
+  hsq::Quad st;
+  hsq::init(st);
+#pragma unroll
+  for (int j = 0; j < 8; j++) st.s[j] = T->s[8 * st.q + j];
+  __syncwarp();             // every lane has read the sponge before lane group 0 overwrites it
+  hsq::absorb_mix<false>(st, m);          // round constants of this mix pending
+  if (lane < 4) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) T->s[8 * st.q + j] = (st.s[j] + st.rc[j]) & 0xffu;
+  }
+  if (!A.draw) return;
+#pragma unroll 1
+  for (int k = 0; k < 8; k++) hsq::mix_lazy<true>(st);
+  if (lane == 0) {
+    uint64_t a = 0;
+#pragma unroll
+    for (int b = 0; b < 8; b++) a |= (uint64_t)((st.s[b] + st.rc[b]) & 0xffu) << (8 * b);
+    *A.alpha_raw = a;
+    *A.alpha_m = ff::to_mont(ff::reduce64(a));
+  }
+}
+
 // One thread.  root = 8 little-endian words.  Fast path (transcript length a multiple of 32, the FRI case): the sponge
 // stays in registers with static indexing, one copy of each mix form (code size: this runs once per launch).
 __device__ __forceinline__ void transcript_round(const TranscriptArgs &A, const uint32_t *root) {
