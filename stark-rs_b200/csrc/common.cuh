@@ -90,6 +90,39 @@ static inline int stark_fail(stark_ctx *ctx, int code, const char *fmt, ...) {
     KERNEL_CHECK(ctx);                                     \
   } while (0)
 
+// ---- programmatic dependent launch (sm_90+): a kernel launched with LAUNCH_PDL may be SCHEDULED while its predecessor
+// in the stream is still running; it must begin with pdl_entry(), which (1) lets ITS successor be scheduled early and
+// (2) blocks until every predecessor grid has completed and its memory is visible.  The prove pipeline is a chain of
+// ~50 short dependent kernels, so the ~2 us launch + ramp between two of them is worth hiding.  Kernels launched the
+// classic way before or after a PDL kernel keep full stream ordering.
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_entry() {
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at, cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+// LAUNCH_PDL(ctx, "tag", algorithmic_bytes, kernel, grid, block, args...)
+#define LAUNCH_PDL(ctx, tag, bytes, kernel, grid, block, ...)                                      \
+  do {                                                                                             \
+    if ((ctx)->prof_on) prof_begin((ctx), (tag), (bytes));                                         \
+    cudaError_t le__ = launch_pdl(kernel, dim3(grid), dim3(block), 0, (ctx)->stream, __VA_ARGS__); \
+    if ((ctx)->prof_on) prof_end((ctx));                                                           \
+    (ctx)->launches++;                                                                             \
+    CU_TRY((ctx), le__);                                                                           \
+  } while (0)
+
 // stream-ordered scratch allocation (no device-wide sync on the hot path)
 static inline int dev_alloc(stark_ctx *ctx, void **p, size_t bytes) {
   CU_TRY(ctx, cudaMallocAsync(p, bytes ? bytes : 16, ctx->stream));

@@ -39,6 +39,7 @@ template <int V>
 __global__ void __launch_bounds__(256) k_fri_fold(const u32 *__restrict__ cw, u32 *__restrict__ out, size_t h, size_t i0,
                                                   size_t i1, int r, GeoTables G, u32 g_r_m,
                                                   const u32 *__restrict__ alpha_m, u32 alpha_val, u32 inv2off_m) {
+  pdl_entry();
   // alpha (Montgomery form) comes from device memory inside Fri::commit (written by the transcript step) and by value
   // from the stand-alone entry points
   const u32 K = ff::canon(ff::mont_mul(alpha_m ? *alpha_m : alpha_val, inv2off_m));
@@ -124,6 +125,7 @@ struct TailArgs {
 };
 __global__ void __launch_bounds__(TAIL_NT, 1) k_fri_tail(const __grid_constant__ TailArgs A) {
   __shared__ __align__(16) u8 sm[(1 << TAIL_LOG) * 16];
+  pdl_entry();
   const u32 t = threadIdx.x, one = blockDim.y;
   u32 len = A.len0;
   for (u32 i = 0; i < A.n_rounds; i++) {
@@ -171,6 +173,7 @@ __global__ void __launch_bounds__(TAIL_NT, 1) k_fri_tail(const __grid_constant__
 __global__ void __launch_bounds__(64) k_fold_leaf1(const u32 *__restrict__ cw, u32 *__restrict__ out, size_t h, int r,
                                                     GeoTables G, u32 g_r_m, const u32 *__restrict__ alpha_m,
                                                     u32 inv2off_m, u8 *__restrict__ leaves) {
+  pdl_entry();
   const size_t i = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
   if (i >= h) return;
   const u32 K = ff::canon(ff::mont_mul(*alpha_m, inv2off_m));
@@ -199,6 +202,7 @@ __global__ void __launch_bounds__(256) k_sample_indices(const TranscriptDev *T, 
   __shared__ u64 seen_red[256];   // idx % reduced of the accepted indices
   __shared__ u32 pre[32];
   __shared__ u32 got;
+  pdl_entry();
   if (threadIdx.x == 0) {
     u64 c;
     if (T->npend == 0) {
@@ -282,6 +286,7 @@ __device__ __forceinline__ void put_u64(u8 *d, u64 v) {
 }
 // R x [0x00, root]  then  [0x02, len u64, values u64...]   (fri.rs:129, 151; stream.rs:39-53)
 __global__ void k_proof_header(u8 *out, const u8 *roots, u32 R, const u32 *last, u64 last_len) {
+  pdl_entry();
   const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < R) {
     u8 *d = out + 33 * t;
@@ -307,6 +312,7 @@ struct ProofRoundsArgs {
   u32 nq, depth0;
 };
 __global__ void k_proof_rounds(u8 *proof, const __grid_constant__ ProofRoundsArgs A, const u64 *top) {
+  pdl_entry();
   const u32 i = blockIdx.y, nq = A.nq;
   u8 *out = proof + A.out_off[i];
   const u32 *cur = A.cw[i], *nxt = A.cw[i + 1];
@@ -401,11 +407,11 @@ static int fold_launch_range(stark_ctx *ctx, const u32 *cw, u32 *out, size_t h, 
   const size_t cnt = i1 - i0;
   if (h % 4 == 0 && i0 % 4 == 0 && cnt % 4 == 0) {
     size_t blocks = (cnt / 4 + 255) / 256, cap = (size_t)ctx->sm_count * 8;
-    LAUNCH(ctx, "fri_fold", 12ull * cnt,
-           k_fri_fold<4><<<(u32)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(cw, out, h, i0, i1, r, G, g_r_m, alpha_m, alpha_val, inv2off_m));
+    LAUNCH_PDL(ctx, "fri_fold", 12ull * cnt, k_fri_fold<4>, (u32)(blocks < cap ? blocks : cap), 256, cw, out, h, i0, i1, r, G,
+               g_r_m, alpha_m, alpha_val, inv2off_m);
   } else {
-    LAUNCH(ctx, "fri_fold", 12ull * cnt,
-           k_fri_fold<1><<<(u32)((cnt + 255) / 256), 256, 0, ctx->stream>>>(cw, out, h, i0, i1, r, G, g_r_m, alpha_m, alpha_val, inv2off_m));
+    LAUNCH_PDL(ctx, "fri_fold", 12ull * cnt, k_fri_fold<1>, (u32)((cnt + 255) / 256), 256, cw, out, h, i0, i1, r, G, g_r_m,
+               alpha_m, alpha_val, inv2off_m);
   }
   return STARK_OK;
 }
@@ -497,7 +503,7 @@ static int fri_commit_dev(stark_ctx *ctx, const u32 *cw0, size_t n, u32 offset, 
           off_r = ff::mul(off_r, off_r);
         }
       }
-      if (rc == STARK_OK) LAUNCH(ctx, "fri_tail", 64 * hashes, k_fri_tail<<<1, TAIL_NT, 0, ctx->stream>>>(A));
+      if (rc == STARK_OK) LAUNCH_PDL(ctx, "fri_tail", 64 * hashes, k_fri_tail, 1u, TAIL_NT, A);
       break;
     }
     stark_tree *tree = nullptr;
@@ -508,10 +514,9 @@ static int fri_commit_dev(stark_ctx *ctx, const u32 *cw0, size_t n, u32 offset, 
       rc = merkle_leaves_dev(ctx, s->cw[0], len, 1, 1, 0, tree->nodes);   // fri.rs:118-121
     } else if (len % 2 == 0) {
       const u32 inv2off_m = ff::to_mont(ff::inv(ff::mul(2, off_prev)));
-      LAUNCH(ctx, "fold_leaf", 12ull * len + 32ull * len,
-             k_fold_leaf1<<<(u32)((len / 2 + 63) / 64), 64, 0, ctx->stream>>>(s->cw[r - 1], s->cw[r], len, (int)(r - 1), G,
-                                                                              ff::to_mont(g_prev), s->d_alpha_m + (r - 1),
-                                                                              inv2off_m, tree->nodes));
+      LAUNCH_PDL(ctx, "fold_leaf", 12ull * len + 32ull * len, k_fold_leaf1, (u32)((len / 2 + 63) / 64), 64,
+                 (const u32 *)s->cw[r - 1], s->cw[r], len, (int)(r - 1), G, ff::to_mont(g_prev),
+                 (const u32 *)(s->d_alpha_m + (r - 1)), inv2off_m, tree->nodes);
     } else {
       const u32 inv2off_m = ff::to_mont(ff::inv(ff::mul(2, off_prev)));
       rc = fold_launch(ctx, s->cw[r - 1], s->cw[r], len, (int)(r - 1), G, ff::to_mont(g_prev), s->d_alpha_m + (r - 1), inv2off_m);
@@ -588,10 +593,12 @@ static int fri_prove_dev(stark_ctx *ctx, const u32 *cw0, size_t n, size_t domain
     d_top = reinterpret_cast<u64 *>(d_proof + ((L.total + 7) & ~(size_t)7));
     if (ctx->prof_on) prof_begin(ctx, "query_phase", 0);
     const size_t sample_size = L.n_cw > 1 ? s->len[1] : s->len[0];       // fri.rs:266-270
-    k_sample_indices<<<1, 256, 0, ctx->stream>>>(s->d_tr, d_seed, sample_size, L.last_len, nq, d_top);  // fri.rs:272-276
+    cudaError_t qe = launch_pdl(k_sample_indices, dim3(1), dim3(256), 0, ctx->stream, (const TranscriptDev *)s->d_tr, d_seed,
+                                (u64)sample_size, (u64)L.last_len, nq, d_top);  // fri.rs:272-276
     const size_t hdr_threads = L.last_len > R ? L.last_len : R;
-    k_proof_header<<<(u32)((hdr_threads + 255) / 256), 256, 0, ctx->stream>>>(d_proof, s->d_roots, R, s->cw[L.n_cw - 1],
-                                                                             L.last_len);
+    if (qe == cudaSuccess)
+      qe = launch_pdl(k_proof_header, dim3((u32)((hdr_threads + 255) / 256)), dim3(256), 0, ctx->stream, d_proof,
+                      (const u8 *)s->d_roots, R, (const u32 *)s->cw[L.n_cw - 1], (u64)L.last_len);
     ctx->launches += 2;
     if (L.n_cw > 1 && nq) {
       ProofRoundsArgs PA;
@@ -602,9 +609,12 @@ static int fri_prove_dev(stark_ctx *ctx, const u32 *cw0, size_t n, size_t domain
       for (u32 i = 0; i < L.n_cw; i++) PA.cw[i] = s->cw[i], PA.nodes[i] = s->trees[i]->nodes;
       for (u32 i = 0; i + 1 < L.n_cw; i++) PA.out_off[i] = L.round_off[i];
       const size_t threads = (size_t)nq * (3 * d0 - 1);
-      k_proof_rounds<<<dim3((u32)((threads + 127) / 128), L.n_cw - 1), 128, 0, ctx->stream>>>(d_proof, PA, d_top);
+      if (qe == cudaSuccess)
+        qe = launch_pdl(k_proof_rounds, dim3((u32)((threads + 127) / 128), L.n_cw - 1), dim3(128), 0, ctx->stream, d_proof, PA,
+                        (const u64 *)d_top);
       ctx->launches++;
     }
+    if (qe != cudaSuccess) rc = stark_fail(ctx, STARK_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(qe));
     if (ctx->prof_on) prof_end(ctx);
     if (cudaGetLastError() != cudaSuccess) rc = stark_fail(ctx, STARK_ERR_CUDA, "kernel launch failed");
   }

@@ -24,6 +24,7 @@ constexpr int HASH_NT = 64;
 
 // leaf i = Hash::from_field_elements(&[vals[i]])  (fri.rs:118-121, hash.rs:32-35); two leaves per thread (hs2)
 __global__ void __launch_bounds__(HASH_NT) k_leaf_hash1(const u32 *__restrict__ vals, size_t n, u8 *__restrict__ out) {
+  pdl_entry();
   const size_t i = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
   if (i >= n) return;
   const bool two = i + 1 < n;
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(128) k_hash_bytes(const u8 *__restrict__ msgs,
 
 // one tree level: parent i = Hash::combine(child 2i, child 2i+1)  (merkle.rs:21-27); two parents per thread
 __global__ void __launch_bounds__(HASH_NT) k_merkle_level(const u8 *__restrict__ in, u8 *__restrict__ out, size_t n_out) {
+  pdl_entry();
   const size_t i = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
   if (i >= n_out) return;
   const bool two = i + 1 < n_out;
@@ -123,6 +125,7 @@ __global__ void __launch_bounds__(NT) k_merkle_climb(u8 *nodes, size_t n, u32 le
                                                      TranscriptArgs tr, u32 *counter) {
   __shared__ __align__(16) u8 sm[2 * NT * 32];
   __shared__ u32 ticket;
+  pdl_entry();
   const u32 t = threadIdx.x;
   const size_t first = (size_t)blockIdx.x * cnt;
   cta_climb<NT>(nodes, n, level_in, first, cnt, levels, nodes + 32 * (level_off(n, level_in) + first), sm, blockDim.y);
@@ -181,7 +184,7 @@ int merkle_leaves_dev(stark_ctx *ctx, const u32 *vals, size_t n, u32 width, size
   if (n == 0) return STARK_OK;
   const u32 blocks = (u32)((n + 255) / 256);
   if (width == 1)
-    LAUNCH(ctx, "leaf_hash", 36ull * n, k_leaf_hash1<<<(u32)((n + 2 * HASH_NT - 1) / (2 * HASH_NT)), HASH_NT, 0, ctx->stream>>>(vals, n, out));
+    LAUNCH_PDL(ctx, "leaf_hash", 36ull * n, k_leaf_hash1, (u32)((n + 2 * HASH_NT - 1) / (2 * HASH_NT)), HASH_NT, vals, n, out);
   else
     LAUNCH(ctx, "leaf_hash_w", (4ull * width + 32) * n,
            k_leaf_hashw<<<blocks, 256, 0, ctx->stream>>>(vals, n, width, row_stride, col_stride, out));
@@ -196,9 +199,8 @@ int merkle_climb_dev(stark_ctx *ctx, u8 *nodes, size_t n, const TranscriptArgs *
   // throughput-bound levels: one launch each
   while ((m >> 1) >= ((size_t)1 << 17)) {
     const size_t half = m >> 1;
-    LAUNCH(ctx, "merkle_level", 96ull * half,
-           k_merkle_level<<<(u32)((half + 2 * HASH_NT - 1) / (2 * HASH_NT)), HASH_NT, 0, ctx->stream>>>(nodes + 32 * (2 * n - 2 * m),
-                                                                              nodes + 32 * (2 * n - 2 * half), half));
+    LAUNCH_PDL(ctx, "merkle_level", 96ull * half, k_merkle_level, (u32)((half + 2 * HASH_NT - 1) / (2 * HASH_NT)), HASH_NT,
+               (const u8 *)(nodes + 32 * (2 * n - 2 * m)), nodes + 32 * (2 * n - 2 * half), half);
     m = half;
     level++;
   }
@@ -206,13 +208,13 @@ int merkle_climb_dev(stark_ctx *ctx, u8 *nodes, size_t n, const TranscriptArgs *
   // climbs the <= 256 chunk roots to the root; small trees are a single CTA
   if (m > 1024) {
     const size_t ctas = m / 512;
-    LAUNCH(ctx, "merkle_climb", 96ull * (m - 1),
-           k_merkle_climb<256><<<(u32)ctas, 256, 0, ctx->stream>>>(nodes, n, level, 512u, 9u, tr ? *tr : none, ctx->flag + 1));
+    LAUNCH_PDL(ctx, "merkle_climb", 96ull * (m - 1), k_merkle_climb<256>, (u32)ctas, 256, nodes, n, level, 512u, 9u,
+               tr ? *tr : none, ctx->flag + 1);
   } else if (m > 1) {
     u32 levels = 0;
     for (size_t c = m; c > 1; c >>= 1) levels++;
-    LAUNCH(ctx, "merkle_top", 96ull * (m - 1),
-           k_merkle_climb<512><<<1, 512, 0, ctx->stream>>>(nodes, n, level, (u32)m, levels, tr ? *tr : none, nullptr));
+    LAUNCH_PDL(ctx, "merkle_top", 96ull * (m - 1), k_merkle_climb<512>, 1u, 512, nodes, n, level, (u32)m, levels,
+               tr ? *tr : none, (u32 *)nullptr);
   }
   if (n == 1 && tr) LAUNCH(ctx, "transcript", 0, k_transcript_only<<<1, 32, 0, ctx->stream>>>(nodes, *tr));
   return STARK_OK;

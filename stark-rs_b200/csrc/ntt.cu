@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(ntt2::NT, 8) k_ntt2_pass(const __grid_constant
   typedef Plan<LOGR> PL;
   __shared__ __align__(16) q4 tile[1 << (TILE_LOG - 2)];
   __shared__ u32 otw[KIND == MIDDLE ? (1 << LOGR) : 1];
+  pdl_entry();
   const u32 tid = threadIdx.x;
   const TileCtx T = tile_ctx<LOGR>(A, blockIdx.x);
   if (KIND == MIDDLE) fill_outer_table<LOGR>(tid, A, T, otw);
@@ -339,7 +340,7 @@ int ntt_transform(stark_ctx *ctx, const u32 *in, u32 *out, int log_n, bool inver
     // compile-time specialisation of the per-element options (see round_compute)
     const int mode = kind == ntt2::FIRST ? ((B.n_valid < N ? 1 : 0) | (B.pre_mode == SCALE_GEO ? 2 : 0))
                                          : (kind == ntt2::LAST ? B.post_mode : 0);
-#define NTT2_LAUNCH(R_, K_, M_) LAUNCH(ctx, tag, bytes, (k_ntt2_pass<R_, K_, M_><<<grid, ntt2::NT, 0, ctx->stream>>>(B)))
+#define NTT2_LAUNCH(R_, K_, M_) LAUNCH_PDL(ctx, tag, bytes, (k_ntt2_pass<R_, K_, M_>), grid, ntt2::NT, B)
 #define NTT2_CASE(R_, K_)                                                                                        \
   if (r == R_ && kind == K_) {                                                                                   \
     if (K_ == ntt2::MIDDLE || mode == 0) {                                                                       \
