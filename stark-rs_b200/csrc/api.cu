@@ -109,6 +109,26 @@ int upload_u64(stark_ctx *ctx, const uint64_t *host, size_t n, u32 *dst) {
   return STARK_OK;
 }
 
+// the same without the host round trip: the canonical-input flag is copied to pinned host memory behind the narrowing
+// kernel and inspected by upload_u64_check() after the caller's final synchronisation (pipelines that end with a sync
+// anyway, e.g. stark_prove_trace, save one host-device bubble)
+int upload_u64_nosync(stark_ctx *ctx, const uint64_t *host, size_t n, u32 *dst) {
+  ctx->h_flag[2] = 0;
+  if (n == 0) return STARK_OK;
+  u64 *tmp = nullptr;
+  ST_TRY(dev_alloc(ctx, (void **)&tmp, n * 8));
+  CU_TRY(ctx, cudaMemsetAsync(ctx->flag + 2, 0, 4, ctx->stream));
+  CU_TRY(ctx, cudaMemcpyAsync(tmp, host, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(ctx, "narrow_u64", 12ull * n, k_narrow<<<(u32)((n + 255) / 256), 256, 0, ctx->stream>>>(tmp, dst, n, ctx->flag + 2));
+  dev_free(ctx, tmp);
+  CU_TRY(ctx, cudaMemcpyAsync(ctx->h_flag + 2, ctx->flag + 2, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  return STARK_OK;
+}
+int upload_u64_check(stark_ctx *ctx) {   // call after the stream has been synchronised
+  if (ctx->h_flag[2]) return stark_fail(ctx, STARK_ERR_ARG, "non-canonical field element (value >= p) in input");
+  return STARK_OK;
+}
+
 int download_u64(stark_ctx *ctx, const u32 *src, size_t n, uint64_t *host) {
   if (n == 0) return STARK_OK;
   u64 *tmp = nullptr;

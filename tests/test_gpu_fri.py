@@ -162,3 +162,13 @@ def test_prove_trace_pipeline(ctx, oracle, log_n, n_cols):
         if c == 0:
             assert proof == oracle.fri_prove(lde, w, 3, 4, nq)["proof"]
     assert oracle.fri_verify(proof, w, 3, N, 4, nq)[0]
+
+
+def test_prove_trace_rejects_non_canonical_input(ctx, S):
+    """stark_prove_trace checks canonical input without a mid-pipeline host round trip: the error must still surface"""
+    col = np.arange(1 << 8, dtype=np.uint64)
+    col[77] = P            # >= p: never silently reduced (the reference would hash / serialise the raw value)
+    with pytest.raises(S.StarkPanic, match="non-canonical"):
+        ctx.prove_trace(col, 2, 3, 8)
+    ok_roots, ok_proof = ctx.prove_trace(np.arange(1 << 8, dtype=np.uint64), 2, 3, 8)   # the context is still usable
+    assert len(ok_proof) > 0
