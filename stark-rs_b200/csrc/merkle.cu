@@ -71,6 +71,43 @@ __global__ void __launch_bounds__(256) k_leaf_hashw(const u32 *__restrict__ vals
   store_hash(out + 32 * i, w);
 }
 
+// the same, two rows per thread (hs2): rows i, i+1 of the `width` columns.  One 32-byte chunk = 4 values (LE u64 each,
+// high word zero).  This is the leaf rule of BASELINE config 4 (8 trace columns per Merkle leaf).
+__global__ void __launch_bounds__(HASH_NT) k_leaf_hashw2(const u32 *__restrict__ vals, size_t n, u32 width, size_t row_stride,
+                                                         size_t col_stride, u8 *__restrict__ out) {
+  pdl_entry();
+  const size_t i = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
+  if (i >= n) return;
+  const bool two = i + 1 < n;
+  const u32 *ba = vals + i * row_stride, *bb = vals + (two ? i + 1 : i) * row_stride;
+  hs2::State2 st;
+  hs2::init(st, blockDim.y);
+  bool pending = false;
+  for (u32 c0 = 0; c0 < width; c0 += 4) {
+    const int nv = (width - c0) < 4 ? (int)(width - c0) : 4;
+    u32 va[4], vb[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      va[k] = k < nv ? ba[(size_t)(c0 + k) * col_stride] : 0u;
+      vb[k] = k < nv ? bb[(size_t)(c0 + k) * col_stride] : 0u;
+    }
+    if (pending) hs2::settle(st);
+#pragma unroll
+    for (int b = 0; b < 32; b++)
+      if (b < 8 * nv) hs2::absorb_pair(st, b, (b & 4) ? 0u : hs2::pair_bytes(va[b >> 3], vb[b >> 3], b & 3));
+    hs2::mix_lazy<false>(st);
+    pending = true;
+  }
+  if (pending)
+    hs2::finalize<true>(st);
+  else
+    hs2::finalize<false>(st);
+  u32 wa[8], wb[8];
+  hs2::pack_words(st, wa, wb);
+  store_hash(out + 32 * i, wa);
+  if (two) store_hash(out + 32 * i + 32, wb);
+}
+
 // generic Hash::from_bytes of n messages of msg_len bytes (hash.rs:7-30); state stays in registers
 __global__ void __launch_bounds__(128) k_hash_bytes(const u8 *__restrict__ msgs, size_t n, size_t msg_len,
                                                     u8 *__restrict__ out) {
@@ -182,12 +219,11 @@ int merkle_check_n(stark_ctx *ctx, size_t n) {
 int merkle_leaves_dev(stark_ctx *ctx, const u32 *vals, size_t n, u32 width, size_t row_stride, size_t col_stride,
                       u8 *out) {
   if (n == 0) return STARK_OK;
-  const u32 blocks = (u32)((n + 255) / 256);
   if (width == 1)
     LAUNCH_PDL(ctx, "leaf_hash", 36ull * n, k_leaf_hash1, (u32)((n + 2 * HASH_NT - 1) / (2 * HASH_NT)), HASH_NT, vals, n, out);
   else
-    LAUNCH(ctx, "leaf_hash_w", (4ull * width + 32) * n,
-           k_leaf_hashw<<<blocks, 256, 0, ctx->stream>>>(vals, n, width, row_stride, col_stride, out));
+    LAUNCH_PDL(ctx, "leaf_hash_w", (4ull * width + 32) * n, k_leaf_hashw2, (u32)((n + 2 * HASH_NT - 1) / (2 * HASH_NT)), HASH_NT,
+               vals, n, width, row_stride, col_stride, out);
   return STARK_OK;
 }
 
