@@ -362,7 +362,8 @@ class ShardedFri:
                 stream.push_field_elements([va[q], vb[q], vc[q]])
             for q in range(len(a)):                                                      # fri.rs:236-243
                 for w in range(3):
-                    stream.push_merkle_path([bytes(hh) for hh in lower[w][q]] + [bytes(hh) for hh in upper[w][q]])
+                    lo_, up_ = lower[w][q], upper[w][q]
+                    stream.push_merkle_path_raw(lo_.shape[0] + up_.shape[0], lo_.tobytes() + up_.tobytes())
         for t in trees:
             t.free()
         return stream.serialize(), top

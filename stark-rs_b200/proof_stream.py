@@ -27,6 +27,11 @@ class ProofStream:
     def push_merkle_path(self, hashes):
         self.objects.append((3, [bytes(h) for h in hashes]))
 
+    def push_merkle_path_raw(self, count, raw):
+        """a path given as `count` concatenated 32-byte hashes (one bytes object: no per-hash Python objects)"""
+        assert len(raw) == 32 * count
+        self.objects.append((4, (int(count), bytes(raw))))
+
     def serialize(self):
         out = bytearray()
         for tag, x in self.objects:
@@ -38,10 +43,14 @@ class ProofStream:
             elif tag == 2:
                 out += struct.pack("<Q", len(x))
                 out += struct.pack("<%dQ" % len(x), *x)
-            else:
+            elif tag == 3:
                 out += struct.pack("<Q", len(x))
                 for h in x:
                     out += h
+            else:                      # raw MerklePath: serialised exactly like tag 3
+                out[-1] = 3
+                out += struct.pack("<Q", x[0])
+                out += x[1]
         return bytes(out)
 
 
