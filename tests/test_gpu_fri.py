@@ -172,3 +172,32 @@ def test_prove_trace_rejects_non_canonical_input(ctx, S):
         ctx.prove_trace(col, 2, 3, 8)
     ok_roots, ok_proof = ctx.prove_trace(np.arange(1 << 8, dtype=np.uint64), 2, 3, 8)   # the context is still usable
     assert len(ok_proof) > 0
+
+
+def test_prove_randomised_parameters(ctx, oracle):
+    """40 seeded random statements: size 2^4..2^13, expansion factor, query count, offset, codeword kind; every proof
+    byte and every returned index must equal the oracle's.  Exercises the single-CTA tail alone (small n), tail + fused
+    fold/leaf rounds, the multi-CTA climb (n >= 2^11) and the index-sampling reject rule with many queries."""
+    rng = np.random.default_rng(20261018)
+    for case in range(40):
+        log_n = int(rng.integers(4, 14))
+        n = 1 << log_n
+        ef = int(rng.choice([4, 8, 16]))
+        if ef >= n:
+            ef = 4
+        w = oracle.ff_prim_nth_root(n)
+        offset = int(rng.integers(1, P))
+        rounds_ok = [q for q in (1, 2, 3, 5, 8, 13, 21, 32, 40) if q <= n // ef // 2 or q <= 2]
+        nq = int(rng.choice(rounds_ok))
+        if rng.random() < 0.5:
+            base = rng.integers(0, P, n // ef, dtype=np.uint64)
+            cw = oracle.fast_eval_coset(base, offset, log_n)               # genuine low-degree codeword
+        else:
+            cw = rng.integers(0, P, n, dtype=np.uint64)
+        try:
+            ref = oracle.fri_prove(cw, w, offset, ef, nq)
+        except oracle.OraclePanic:
+            continue                                                        # parameters the reference rejects too
+        proof, top = ctx.fri_prove(cw, offset, w, ef, nq)
+        assert proof == ref["proof"], (case, log_n, ef, nq, offset)
+        assert top == ref["top_indices"], (case, log_n, ef, nq)
