@@ -57,6 +57,26 @@ int main() {
   EXPECT(raw(qr.first.coeffs) == (std::vector<uint64_t>{2, 1}));
   EXPECT(raw(Polynomial::modulo(Polynomial(wrap({1, 0, 1}, field), field), Polynomial(wrap({1, 1}, field), field)).coeffs)[0] == 2);
   try { Polynomial::div(a, Polynomial(wrap({0}, field), field)); EXPECT(false); } catch (const Panic &e) { EXPECT(std::string(e.what()) == "No division by zero"); }
+  // ff.rs:359-365, 406-438, 467-473, 525-672 (the reference's own known answers, through the mirror's scalar field)
+  EXPECT((field.new_element(P - 1) + field.new_element(5)).value == 4);
+  EXPECT((field.new_element(5) - field.new_element(10)).value == P - 5);
+  EXPECT((field.new_element(123) * field.new_element(456)).value == 123 * 456);
+  EXPECT((-field.new_element(100)).value == P - 100 && (-field.zero()).value == 0);
+  EXPECT((field.inv(field.new_element(123)) * field.new_element(123)).value == 1);
+  EXPECT((field.new_element(2) ^ 10).value == 1024 && field.g().value == 3);
+  EXPECT((field.prim_nth_root(8) ^ 8).value == 1 && (field.prim_nth_root(8) ^ 4).value != 1);
+  EXPECT(field.prim_nth_root(1 << 22).value == 267099868);
+  EXPECT(field.sample({}).value == 0 && field.sample({42}).value == 42);
+  // mod.rs:320-402 zerofier, eval.rs:83-118, interpolate.rs:57-163 (GPU paths behind the same methods)
+  EXPECT(raw(Polynomial::zerofier(wrap({5}, field)).coeffs) == (std::vector<uint64_t>{P - 5, 1}));
+  EXPECT(raw(Polynomial::zerofier(wrap({1, 2, 3}, field)).coeffs) == (std::vector<uint64_t>{P - 6, 11, P - 6, 1}));
+  EXPECT(Polynomial(wrap({1, 2, 3, 4}, field), field).eval(field.new_element(2)).value == 49);
+  auto ev = Polynomial(wrap({1, 1}, field), field).eval_domain(wrap({0, 1, 2, 3}, field));
+  EXPECT(raw(ev) == (std::vector<uint64_t>{1, 2, 3, 4}));
+  EXPECT(raw(Polynomial::interpolate_domain(wrap({0, 1, P - 5}, field), wrap({P - 2, 6, 48}, field)).coeffs) == (std::vector<uint64_t>{P - 2, 5, 3}));
+  EXPECT(raw(Polynomial(wrap({1, 2, 3}, field), field).scale(field.new_element(2)).coeffs) == (std::vector<uint64_t>{1, 4, 12}));
+  try { field.prim_nth_root(6); EXPECT(false); } catch (const Panic &e) { EXPECT(std::string(e.what()) == "n must be a power of two"); }
+  try { field.div(field.one(), field.zero()); EXPECT(false); } catch (const Panic &e) { EXPECT(std::string(e.what()) == "no division by zero"); }
   // panics keep the reference's text
   try { field.inv(field.zero()); EXPECT(false); } catch (const Panic &e) { EXPECT(std::string(e.what()) == "no inverse"); }
   try { MerkleTree t3(std::vector<Hash>(3)); EXPECT(false); } catch (const Panic &e) { EXPECT(std::string(e.what()) == "Number of leaves must be power of 2"); }
