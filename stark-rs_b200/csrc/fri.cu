@@ -25,10 +25,6 @@ using ntt::GeoTables;
 
 // ---------------------------------------------------------------------------------------- transcript
 
-__global__ void k_transcript_challenge(const TranscriptDev *T, u64 *out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  *out = tr_challenge(*T);
-}
 
 // ---------------------------------------------------------------------------------------------- fold
 

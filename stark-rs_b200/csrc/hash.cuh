@@ -107,19 +107,13 @@ HS_HD void settle(State &st) {
   for (int i = 0; i < 32; i++) st.s[i] += rc_at(i);
 }
 
-// 8 finalisation mixes (hash.rs:25-27) + settle.  PENDING as for mix_lazy.  UNROLL: straight-line code, so the
-// scheduler can start the next mix's sbox on bytes whose neighbour-add chain has already finished (the latency-bound
-// narrow tree levels); the rolled form keeps the throughput kernels' code small.
-template <bool PENDING, bool UNROLL = false>
+// 8 finalisation mixes (hash.rs:25-27) + settle.  PENDING as for mix_lazy.  The seven pending-form mixes stay a rolled
+// loop: straight-line code was measured 15 % SLOWER in the latency-bound callers (instruction-cache misses).
+template <bool PENDING>
 HS_HD void finalize(State &st) {
   mix_lazy<PENDING>(st);
-  if (UNROLL) {
-#pragma unroll
-    for (int k = 0; k < 7; k++) mix_lazy<true>(st);
-  } else {
 #pragma unroll 1
-    for (int k = 0; k < 7; k++) mix_lazy<true>(st);
-  }
+  for (int k = 0; k < 7; k++) mix_lazy<true>(st);
   settle(st);
 }
 
@@ -151,7 +145,6 @@ HS_HD void absorb_words_mix(State &st, const u32 *w) {
 // Code size matters as much as instruction count for the latency-bound callers (a narrow tree level runs this code
 // once per launch, from a cold instruction cache): the two chunks share ONE copy of absorb + mix and the eight
 // finalisation mixes ONE copy of the pending-constants mix.
-template <bool UNROLL = false>
 HS_HD void combine(const u32 *left, const u32 *right, u32 *out) {
   State st;
   init(st);

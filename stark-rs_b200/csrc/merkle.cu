@@ -41,37 +41,8 @@ __global__ void __launch_bounds__(HASH_NT) k_leaf_hash1(const u32 *__restrict__ 
   if (two) store_hash(out + 32 * i + 32, wb);
 }
 
-// leaf i = Hash::from_field_elements(&[vals[i*row_stride + c*col_stride] for c < width])  (hash.rs:32-35)
-__global__ void __launch_bounds__(256) k_leaf_hashw(const u32 *__restrict__ vals, size_t n, u32 width, size_t row_stride,
-                                                    size_t col_stride, u8 *__restrict__ out) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  State st;
-  hs::init(st);
-  bool pending = false;
-  const u32 *base = vals + i * row_stride;
-  for (u32 c0 = 0; c0 < width; c0 += 4) {  // one 32-byte chunk = 4 values (LE u64 each, high word zero)
-    const int nv = (width - c0) < 4 ? (int)(width - c0) : 4;
-    u32 v[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) v[k] = k < nv ? base[(size_t)(c0 + k) * col_stride] : 0u;
-    if (pending) hs::settle(st);
-#pragma unroll
-    for (int b = 0; b < 32; b++)
-      if (b < 8 * nv) hs::absorb_byte(st, b, (b & 4) ? 0u : v[b >> 3] >> (8 * (b & 3)));
-    hs::mix_lazy<false>(st);
-    pending = true;
-  }
-  if (pending)
-    hs::finalize<true>(st);
-  else
-    hs::finalize<false>(st);
-  u32 w[8];
-  hs::pack_words(st, w);
-  store_hash(out + 32 * i, w);
-}
-
-// the same, two rows per thread (hs2): rows i, i+1 of the `width` columns.  One 32-byte chunk = 4 values (LE u64 each,
+// leaves i, i+1 = Hash::from_field_elements(&[vals[i*row_stride + c*col_stride] for c < width])  (hash.rs:32-35),
+// two rows per thread (hs2).  One 32-byte chunk = 4 values (LE u64 each,
 // high word zero).  This is the leaf rule of BASELINE config 4 (8 trace columns per Merkle leaf).
 __global__ void __launch_bounds__(HASH_NT) k_leaf_hashw2(const u32 *__restrict__ vals, size_t n, u32 width, size_t row_stride,
                                                          size_t col_stride, u8 *__restrict__ out) {

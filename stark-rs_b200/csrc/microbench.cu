@@ -85,7 +85,7 @@ __global__ void k_hash_latency(int mode, int K, unsigned long long *cycles, u32 
   for (int k = 0; k < K; k++) {
     if (mode == 0) {
       u32 o[8];
-      hs::combine<false>(x, x, o);
+      hs::combine(x, x, o);
       for (int i = 0; i < 8; i++) x[i] = o[i];
     } else if (mode == 1) {
       u32 oa[8], ob[8];

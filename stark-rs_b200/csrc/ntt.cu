@@ -137,40 +137,37 @@ __global__ void k_ntt_tiny(TinyArgs A) {
   }
 }
 
-template <int LOGR, int V, bool ROWOUT>
-__device__ __forceinline__ void first_round(const PassArgs &A, u32 tid, u32 nt, u32 tile, bool only,
-                                            typename Slot<V>::type *smem, u32 *regs) {
-  round_load_compute<LOGR, V, true>(tid, nt, tile, A, 0, smem, only && ROWOUT, regs);
+template <int LOGR>
+__device__ __forceinline__ void first_round(const PassArgs &A, u32 tid, u32 nt, u32 b, bool only, u32 *smem, u32 *regs) {
+  round_load_compute<LOGR, true>(tid, nt, b, A, 0, smem, regs);
   if (only)
-    round_store<LOGR, V, true, ROWOUT>(tid, nt, tile, A, 0, smem, regs);
+    round_store<LOGR, true>(tid, nt, b, A, 0, smem, regs);
   else
-    round_store<LOGR, V, false, ROWOUT>(tid, nt, tile, A, 0, smem, regs);
+    round_store<LOGR, false>(tid, nt, b, A, 0, smem, regs);
 }
 
-template <int V, bool ROWOUT>
-__global__ void __launch_bounds__(1024, 1) k_ntt_pass(const __grid_constant__ PassArgs A) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  typedef typename Slot<V>::type slot_t;
-  slot_t *smem = reinterpret_cast<slot_t *>(smem_raw);
-  const u32 tid = threadIdx.x, nt = blockDim.x, tile = blockIdx.x;
+// 8 <= N <= 4096: one CTA of N/8 threads per transform (ntt_core.cuh)
+__global__ void __launch_bounds__(512) k_ntt_single(const __grid_constant__ PassArgs A) {
+  __shared__ u32 smem[4096];
+  const u32 tid = threadIdx.x, nt = blockDim.x, b = blockIdx.x;
   int logr[4];
   const int nr = plan_rounds(A.logL, logr);
-  u32 regs[32];
+  u32 regs[8];
   switch (logr[0]) {
-    case 1: first_round<1, V, ROWOUT>(A, tid, nt, tile, nr == 1, smem, regs); break;
-    case 2: first_round<2, V, ROWOUT>(A, tid, nt, tile, nr == 1, smem, regs); break;
-    default: first_round<3, V, ROWOUT>(A, tid, nt, tile, nr == 1, smem, regs); break;
+    case 1: first_round<1>(A, tid, nt, b, nr == 1, smem, regs); break;
+    case 2: first_round<2>(A, tid, nt, b, nr == 1, smem, regs); break;
+    default: first_round<3>(A, tid, nt, b, nr == 1, smem, regs); break;
   }
   int logS = logr[0];
   for (int r = 1; r < nr; r++) {
     const bool last = r == nr - 1;
     __syncthreads();
-    round_load_compute<3, V, false>(tid, nt, tile, A, logS, smem, last && ROWOUT, regs);
+    round_load_compute<3, false>(tid, nt, b, A, logS, smem, regs);
     __syncthreads();
     if (last)
-      round_store<3, V, true, ROWOUT>(tid, nt, tile, A, logS, smem, regs);
+      round_store<3, true>(tid, nt, b, A, logS, smem, regs);
     else
-      round_store<3, V, false, ROWOUT>(tid, nt, tile, A, logS, smem, regs);
+      round_store<3, false>(tid, nt, b, A, logS, smem, regs);
     logS += 3;
   }
 }
@@ -219,19 +216,6 @@ static int resolve_scale(stark_ctx *ctx, const ScaleSpec &s, u64 max_index, int 
   return STARK_OK;
 }
 
-template <int V, bool ROWOUT>
-static int launch_pass(stark_ctx *ctx, const PassArgs &A, u32 tiles, const char *tag, u64 bytes) {
-  const u32 nt = (1u << (A.logL - 3)) << A.logC4;
-  const size_t smem = ((size_t)V * 4) << (A.logL + A.logC4);
-  static bool configured = false;  // per instantiation
-  if (!configured) {
-    CU_TRY(ctx, cudaFuncSetAttribute(k_ntt_pass<V, ROWOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    configured = true;
-  }
-  LAUNCH(ctx, tag, bytes, k_ntt_pass<V, ROWOUT><<<tiles, nt, smem, ctx->stream>>>(A));
-  return STARK_OK;
-}
-
 int ntt_transform(stark_ctx *ctx, const u32 *in, u32 *out, int log_n, bool inverse, u32 batch, u64 in_batch,
                   u64 out_batch, u64 n_valid, ScaleSpec pre, ScaleSpec post) {
   if (log_n < 0 || log_n > ff::TWO_ADICITY)
@@ -268,24 +252,18 @@ int ntt_transform(stark_ctx *ctx, const u32 *in, u32 *out, int log_n, bool inver
     return STARK_OK;
   }
 
-  PassArgs A;
-  memset(&A, 0, sizeof A);
-  A.roots = roots;
-  A.shiftN = 23 - log_n;
-  A.inverse = d;
-  for (int k = 0; k < 4; k++) A.w8[k] = ctx->w8[d][k];
-  A.pre_mode = pre_mode, A.pre_geo = pre_geo;
-  A.post_mode = post_mode, A.post_const = post_c, A.post_geo = post_geo;
-
   if (log_n <= 12) {
-    // one pass, one transform per CTA, scalar columns (V = 1)
-    A.in = in, A.out = out;
-    A.logL = log_n, A.logC4 = 0;
-    A.in_batch = in_batch, A.in_stride = 1, A.n_valid = n_valid;
-    A.out_batch = out_batch, A.out_stride = 1;
-    A.tiles_per_batch = 1;
+    // one pass, one transform per CTA
+    PassArgs A;
+    memset(&A, 0, sizeof A);
+    for (int k = 0; k < 4; k++) A.w8[k] = ctx->w8[d][k];
+    A.pre_mode = pre_mode, A.pre_geo = pre_geo;
+    A.post_mode = post_mode, A.post_const = post_c, A.post_geo = post_geo;
+    A.in = in, A.out = out, A.logL = log_n;
+    A.in_batch = in_batch, A.out_batch = out_batch, A.n_valid = n_valid;
     A.tw = ctx->tw_sub[d] + (1u << log_n);
-    return launch_pass<1, false>(ctx, A, batch, "ntt_single", 4ull * batch * (n_valid + N));
+    LAUNCH(ctx, "ntt_single", 4ull * batch * (n_valid + N), k_ntt_single<<<batch, (u32)(N >> 3), 0, ctx->stream>>>(A));
+    return STARK_OK;
   }
 
   // N >= 2^13: 2 or 3 Stockham passes with radices 2^5 .. 2^8 (ntt_pass.cuh)

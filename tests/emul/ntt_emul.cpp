@@ -1,6 +1,6 @@
-// CPU emulation of k_ntt_pass (index-math check only; TEST INFRASTRUCTURE, never shipped).
+// CPU emulation of k_ntt_single (index-math check only; TEST INFRASTRUCTURE, never shipped).
 // Runs the host+device inline round functions of ntt_core.cuh thread by thread and compares with a
-// direct O(n^2) DFT.  Build: g++ -O2 -std=c++17 -I stark-rs_b200/csrc tests/emul/ntt_emul.cpp
+// reference O(n log n) NTT done with u64 %.  Build: g++ -O2 -std=c++17 -I stark-rs_b200/csrc tests/emul/ntt_emul.cpp
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -31,64 +31,33 @@ static void init() {
   }
 }
 
-template <int V, bool ROWOUT>
-static void run_pass(const PassArgs &A, u32 tiles) {
-  typedef typename Slot<V>::type slot_t;
-  const u32 nt = (1u << (A.logL - 3)) << A.logC4;
-  std::vector<slot_t> smem((size_t)1 << (A.logL + A.logC4));
-  std::vector<u32> regs((size_t)nt * 32);
+// mirrors k_ntt_single in ntt.cu
+static void run_single(const PassArgs &A, u32 batch) {
+  const u32 nt = 1u << (A.logL - 3);
+  std::vector<u32> smem((size_t)1 << A.logL), regs((size_t)nt * 8);
   int logr[4];
   const int nr = plan_rounds(A.logL, logr);
-  for (u32 tile = 0; tile < tiles; tile++) {
+  for (u32 b = 0; b < batch; b++) {
     int logS = 0;
     for (int r = 0; r < nr; r++) {
       const bool first = r == 0, last = r == nr - 1;
       for (u32 tid = 0; tid < nt; tid++) {
-        u32 *rg = &regs[(size_t)tid * 32];
+        u32 *rg = &regs[(size_t)tid * 8];
         if (first) {
-          if (logr[0] == 1) round_load_compute<1, V, true>(tid, nt, tile, A, 0, smem.data(), last && ROWOUT, rg);
-          else if (logr[0] == 2) round_load_compute<2, V, true>(tid, nt, tile, A, 0, smem.data(), last && ROWOUT, rg);
-          else round_load_compute<3, V, true>(tid, nt, tile, A, 0, smem.data(), last && ROWOUT, rg);
-        } else round_load_compute<3, V, false>(tid, nt, tile, A, logS, smem.data(), last && ROWOUT, rg);
+          if (logr[0] == 1) round_load_compute<1, true>(tid, nt, b, A, 0, smem.data(), rg);
+          else if (logr[0] == 2) round_load_compute<2, true>(tid, nt, b, A, 0, smem.data(), rg);
+          else round_load_compute<3, true>(tid, nt, b, A, 0, smem.data(), rg);
+        } else round_load_compute<3, false>(tid, nt, b, A, logS, smem.data(), rg);
       }
       for (u32 tid = 0; tid < nt; tid++) {
-        u32 *rg = &regs[(size_t)tid * 32];
+        u32 *rg = &regs[(size_t)tid * 8];
         const int lr = first ? logr[0] : 3;
-#define ST(LR) (last ? round_store<LR, V, true, ROWOUT>(tid, nt, tile, A, logS, smem.data(), rg) \
-                     : round_store<LR, V, false, ROWOUT>(tid, nt, tile, A, logS, smem.data(), rg))
+#define ST(LR) (last ? round_store<LR, true>(tid, nt, b, A, logS, smem.data(), rg) : round_store<LR, false>(tid, nt, b, A, logS, smem.data(), rg))
         if (lr == 1) ST(1); else if (lr == 2) ST(2); else ST(3);
       }
       logS += first ? logr[0] : 3;
     }
   }
-}
-
-// mirrors ntt_transform() in ntt.cu for log_n >= 3 (no scaling)
-static void transform(const u32 *in, u32 *out, int log_n, int d, u32 batch, u64 n_valid) {
-  const u64 N = 1ull << log_n;
-  PassArgs A; memset(&A, 0, sizeof A);
-  A.roots = {g_lo.data(), g_hi.data()};
-  A.shiftN = 23 - log_n; A.inverse = d;
-  for (int k = 0; k < 4; k++) A.w8[k] = g_w8[d][k];
-  if (log_n <= 12) {
-    A.in = in, A.out = out, A.logL = log_n, A.logC4 = 0;
-    A.in_batch = N, A.in_stride = 1, A.n_valid = n_valid, A.out_batch = N, A.out_stride = 1, A.tiles_per_batch = 1;
-    A.tw = g_tw[d].data() + (1u << log_n);
-    run_pass<1, false>(A, batch);
-    return;
-  }
-  const int l1 = log_n / 2, l2 = log_n - l1;
-  const u64 N1 = 1ull << l1, N2 = 1ull << l2;
-  { PassArgs B = A; B.in = in, B.out = out, B.logL = l1;
-    int logC = l2 < (15 - l1) ? l2 : (15 - l1); B.logC4 = logC - 2;
-    B.in_batch = N, B.in_stride = N2, B.n_valid = n_valid, B.out_batch = N; B.tiles_per_batch = (int)(N2 >> logC);
-    B.tw = g_tw[d].data() + (1u << l1);
-    run_pass<4, true>(B, batch * B.tiles_per_batch); }
-  { PassArgs B = A; B.in = out, B.out = out, B.logL = l2;
-    int logC = l1 < (15 - l2) ? l1 : (15 - l2); B.logC4 = logC - 2;
-    B.in_batch = N, B.in_stride = N1, B.n_valid = N, B.out_batch = N, B.out_stride = N1; B.tiles_per_batch = (int)(N1 >> logC);
-    B.tw = g_tw[d].data() + (1u << l2);
-    run_pass<4, false>(B, batch * B.tiles_per_batch); }
 }
 
 // reference: in-place iterative NTT (bit reversal + DIT) with u64 %
@@ -105,21 +74,31 @@ static void ref_ntt(std::vector<u64> &a, u64 root) {
 
 int main(int argc, char **argv) {
   init();
-  int max_log = argc > 1 ? atoi(argv[1]) : 16;
+  int max_log = argc > 1 ? atoi(argv[1]) : 12;
+  if (max_log > 12) max_log = 12;
   int fails = 0;
-  for (int log_n = 3; log_n <= max_log; log_n++) for (int d = 0; d < 2; d++) {
-    const u64 N = 1ull << log_n; const u32 batch = log_n <= 12 ? 3 : 2;
+  for (int log_n = 3; log_n <= max_log; log_n++) for (int d = 0; d < 2; d++) for (int mode = 0; mode < 2; mode++) {
+    const u64 N = 1ull << log_n; const u32 batch = 3;
     std::vector<u32> in(batch * N), out(batch * N);
     u64 s = 12345 + log_n;
     for (auto &x : in) { s = s * 6364136223846793005ull + 1442695040888963407ull; x = (u32)((s >> 33) % ff::P); }
-    u64 n_valid = (log_n % 2) ? N : (N / 4 + 3);
-    transform(in.data(), out.data(), log_n, d, batch, n_valid);
+    const u64 n_valid = (log_n % 2) ? N : (N / 4 + 3);
+    const u32 c = ff::inv((u32)N);
+    PassArgs A; memset(&A, 0, sizeof A);
+    for (int k = 0; k < 4; k++) A.w8[k] = g_w8[d][k];
+    A.in = in.data(), A.out = out.data(), A.logL = log_n, A.in_batch = N, A.out_batch = N, A.n_valid = n_valid;
+    A.tw = g_tw[d].data() + (1u << log_n);
+    A.post_mode = mode ? SCALE_CONST : SCALE_NONE, A.post_const = ff::to_mont(c);
+    run_single(A, batch);
     u64 root = ff::pow(3, (ff::P - 1) >> log_n); if (d) root = ff::inv((u32)root);
     for (u32 b = 0; b < batch; b++) {
       std::vector<u64> r(N);
       for (u64 i = 0; i < N; i++) r[i] = i < n_valid ? in[b * N + i] : 0;
       ref_ntt(r, root);
-      for (u64 i = 0; i < N; i++) if (r[i] != out[b * N + i]) { if (fails < 5) printf("MISMATCH log_n=%d d=%d b=%u i=%llu got %u want %llu\n", log_n, d, b, (unsigned long long)i, out[b * N + i], (unsigned long long)r[i]); fails++; break; }
+      for (u64 i = 0; i < N; i++) {
+        const u64 want = mode ? r[i] * c % ff::P : r[i];
+        if (want != out[b * N + i]) { if (fails < 5) printf("MISMATCH log_n=%d d=%d mode=%d b=%u i=%llu got %u want %llu\n", log_n, d, mode, b, (unsigned long long)i, out[b * N + i], (unsigned long long)want); fails++; break; }
+      }
     }
   }
   printf(fails ? "FAIL %d\n" : "OK %d\n", fails ? fails : max_log);
