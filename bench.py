@@ -256,9 +256,10 @@ def run_ours(a):
     HASH = {"merkle_level": {"bytes": 96.0, "instr": 1569.0, "alu_instr": 832.0},
             "leaf_hash": {"bytes": 36.0, "instr": 1151.0, "alu_instr": 578.0},
             "fold_leaf": {"bytes": 44.0, "instr": 1187.0, "alu_instr": 600.0}}
-    sm_count = torch.cuda.get_device_properties(local).multi_processor_count
-    sm_hz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0
-    pipe_peak = sm_count * 64.0 * sm_hz * 1e6
+    # measured live: register-only LOP3 / IMAD / mixed issue rates (stark_bench_int_peak: 18.55 T, 18.56 T and 35.5 T
+    # thread-instructions/s on this B200, i.e. 64 lanes/clk/SM per pipe and both pipes at once)
+    ipk = ctx.int_peak()
+    pipe_peak = ipk["alu_per_s"]
     int_pipe = {}
     for name, h in HASH.items():
         k = next((x for x in prof if x["kernel"] == name), None)
@@ -269,7 +270,7 @@ def run_ours(a):
         int_pipe[name] = {"hashes_per_s": rate, "thread_instr_per_hash": h["instr"], "alu_instr_per_hash": h["alu_instr"],
                           "alu_pipe_peak_thread_instr_per_s": pipe_peak,
                           "frac_of_alu_pipe_peak": rate * h["alu_instr"] / pipe_peak,
-                          "frac_of_issue_peak": rate * h["instr"] / (2 * pipe_peak)}
+                          "frac_of_issue_peak": rate * h["instr"] / ipk["mixed_per_s"]}
     # DRAM traffic per launch from ncu --set full captures of this same command (profiles/r1k_bench_kernels_ncu_full.csv,
     # profiles/r1u_bench_kernels_ncu_full.csv), quoted with the algorithmic bytes of the SAME launch: the written level /
     # tree is still in L2 when a kernel ends, so the measured write traffic is below the algorithmic figure
@@ -302,7 +303,7 @@ def run_ours(a):
         "gpu_launches": launches, "gpu_launches_per_step": launches / a.steps,
         "clocks": clocks, "roofline": roofline, "kernels": kernels,
         "ms_per_rank_device_pass": (per_rank[0] if per_rank else None),
-        "ms_per_step_profiled": ms_prof / a.steps, "hash_latency_cycles": ctx.hash_latency(),
+        "ms_per_step_profiled": ms_prof / a.steps, "hash_latency_cycles": ctx.hash_latency(), "int_peak": ipk,
     }
 
     if world == 1 and not a.no_cpu_baseline:

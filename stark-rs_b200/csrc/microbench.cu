@@ -1,9 +1,26 @@
 // microbench.cu -- register-only integer issue-rate microbenchmark (measurement infrastructure).
 // The roofline of the hash kernels is the integer pipe, for which MEASURED_PEAKS.json has no number
-// (SURVEY 8(d)).  Three kernels with 8 independent chains per thread: IMAD only (fma pipe), LOP3/IADD3 only
+// (SURVEY 8(d)).  Three kernels with 8 independent chains per thread: IMAD only (fma pipe), LOP3 only
 // (alu pipe), and a 1:1 mix (both pipes, the issue-slot limit).
 #include "common.cuh"
 
+// one dependent step of each flavour, pinned with inline PTX so that ptxas can neither fuse nor strength-reduce it
+__device__ __forceinline__ u32 op_imad(u32 a, u32 m, u32 c) {
+  u32 d;
+  asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(m), "r"(c));
+  return d;
+}
+__device__ __forceinline__ u32 op_lop3(u32 a, u32 m, u32 c) {
+  u32 d;
+  asm volatile("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(m), "r"(c));
+  return d;
+}
+__device__ __forceinline__ u32 op_iadd3(u32 a, u32 m, u32 c) {
+  u32 d;
+  asm volatile("{ .reg .u32 t; add.u32 t, %1, %2; add.u32 %0, t, %3; }" : "=r"(d) : "r"(a), "r"(m), "r"(c));
+  return d;
+}
+// MODE 0: IMAD only (FMA pipe); MODE 1: LOP3 only (ALU pipe); MODE 2: IMAD + LOP3 alternating (both pipes)
 template <int MODE>
 __global__ void __launch_bounds__(256) k_int_peak(u32 *out, u32 seed, int iters) {
   u32 a[8];
@@ -16,13 +33,12 @@ __global__ void __launch_bounds__(256) k_int_peak(u32 *out, u32 seed, int iters)
 #pragma unroll
       for (int k = 0; k < 8; k++) {
         if (MODE == 0) {
-          a[k] = a[k] * m + c;  // IMAD
+          a[k] = op_imad(a[k], m, c);
         } else if (MODE == 1) {
-          a[k] = (a[k] ^ c) + m;  // LOP3 + IADD3
-          a[k] = (a[k] & m) ^ c;  // LOP3
+          a[k] = op_lop3(a[k], m, c);
         } else {
-          a[k] = a[k] * m + c;    // IMAD
-          a[k] = (a[k] ^ m) + c;  // LOP3 (xor) + IADD3 ... see SASS
+          a[k] = op_imad(a[k], m, c);
+          a[k] = op_lop3(a[k], m, c);
         }
       }
     }
@@ -60,11 +76,10 @@ extern "C" int stark_bench_int_peak(stark_ctx *ctx, double *imad_per_s, double *
   if (!ctx || !imad_per_s || !alu_per_s || !mixed_per_s) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
   u32 *d_out = nullptr;
   ST_TRY(dev_alloc(ctx, (void **)&d_out, 16));
-  // instruction counts per innermost statement group, from the SASS of this file (cuobjdump -sass):
-  // MODE 0: 1 IMAD; MODE 1: 3 (LOP3, IADD3, LOP3); MODE 2: 3 (IMAD, LOP3, IADD3)
+  // instructions per innermost statement (pinned with inline PTX): MODE 0: 1 IMAD; MODE 1: 1 LOP3; MODE 2: IMAD + LOP3
   int rc = run_mode<0>(ctx, d_out, 1.0, imad_per_s);
-  if (rc == STARK_OK) rc = run_mode<1>(ctx, d_out, 3.0, alu_per_s);
-  if (rc == STARK_OK) rc = run_mode<2>(ctx, d_out, 3.0, mixed_per_s);
+  if (rc == STARK_OK) rc = run_mode<1>(ctx, d_out, 1.0, alu_per_s);
+  if (rc == STARK_OK) rc = run_mode<2>(ctx, d_out, 2.0, mixed_per_s);
   dev_free(ctx, d_out);
   return rc;
 }
