@@ -112,12 +112,15 @@ int upload_u64(stark_ctx *ctx, const uint64_t *host, size_t n, u32 *dst) {
 // the same without the host round trip: the canonical-input flag is copied to pinned host memory behind the narrowing
 // kernel and inspected by upload_u64_check() after the caller's final synchronisation (pipelines that end with a sync
 // anyway, e.g. stark_prove_trace, save one host-device bubble)
-int upload_u64_nosync(stark_ctx *ctx, const uint64_t *host, size_t n, u32 *dst) {
+int upload_flag_reset(stark_ctx *ctx) {   // once before a group of upload_u64_nosync calls
   ctx->h_flag[2] = 0;
+  CU_TRY(ctx, cudaMemsetAsync(ctx->flag + 2, 0, 4, ctx->stream));
+  return STARK_OK;
+}
+int upload_u64_nosync(stark_ctx *ctx, const uint64_t *host, size_t n, u32 *dst) {
   if (n == 0) return STARK_OK;
   u64 *tmp = nullptr;
   ST_TRY(dev_alloc(ctx, (void **)&tmp, n * 8));
-  CU_TRY(ctx, cudaMemsetAsync(ctx->flag + 2, 0, 4, ctx->stream));
   CU_TRY(ctx, cudaMemcpyAsync(tmp, host, n * 8, cudaMemcpyHostToDevice, ctx->stream));
   LAUNCH(ctx, "narrow_u64", 12ull * n, k_narrow<<<(u32)((n + 255) / 256), 256, 0, ctx->stream>>>(tmp, dst, n, ctx->flag + 2));
   dev_free(ctx, tmp);

@@ -902,7 +902,8 @@ int stark_prove_trace(stark_ctx *ctx, const uint64_t *cols, uint32_t n_cols, uin
   const size_t total = ((size_t)1 << log_n) * n_cols;
   ST_TRY(stark_buf_alloc(ctx, total, &in));
   // H2D + narrowing without a host round trip: the canonical check is read after the pipeline's final sync
-  int rc = upload_u64_nosync(ctx, cols, total, in->ptr);
+  int rc = upload_flag_reset(ctx);
+  if (rc == STARK_OK) rc = upload_u64_nosync(ctx, cols, total, in->ptr);
   if (rc == STARK_OK)
     rc = stark_prove_trace_dev(ctx, in, n_cols, log_n, log_blowup, offset, nq, column_roots, proof, proof_cap, proof_len);
   stark_buf_free(in);

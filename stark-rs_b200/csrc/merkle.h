@@ -28,6 +28,7 @@ int merkle_open_dev(stark_ctx *ctx, const u8 *nodes, size_t n, const u64 *idx_de
 
 // poly.cu / api.cu helpers
 int upload_u64(stark_ctx *ctx, const uint64_t *host, size_t n, u32 *dst);     // H2D + canonical check + narrow
+int upload_flag_reset(stark_ctx *ctx);                                         // before a group of nosync uploads
 int upload_u64_nosync(stark_ctx *ctx, const uint64_t *host, size_t n, u32 *dst);  // no host round trip ...
 int upload_u64_check(stark_ctx *ctx);                                          // ... flag read after the final sync
 int download_u64(stark_ctx *ctx, const u32 *src, size_t n, uint64_t *host);   // widen + D2H (synchronises)

@@ -344,8 +344,10 @@ int stark_poly_mul(stark_ctx *ctx, const uint64_t *a, size_t na, const uint64_t 
   ST_TRY(dev_alloc(ctx, (void **)&db, nb * 4));
   ST_TRY(dev_alloc(ctx, (void **)&fa, M * 4));
   ST_TRY(dev_alloc(ctx, (void **)&fb, M * 4));
-  int rc = upload_u64(ctx, a, na, da);
-  if (rc == STARK_OK) rc = upload_u64(ctx, b, nb, db);
+  // uploads without a host round trip; the canonical-input flag is inspected after the download's sync
+  int rc = upload_flag_reset(ctx);
+  if (rc == STARK_OK) rc = upload_u64_nosync(ctx, a, na, da);
+  if (rc == STARK_OK) rc = upload_u64_nosync(ctx, b, nb, db);
   ScaleSpec none = {ntt::SCALE_NONE, 1, 1};
   if (rc == STARK_OK) rc = ntt_transform(ctx, da, fa, lg, false, 1, M, M, na, none, none);
   if (rc == STARK_OK) rc = ntt_transform(ctx, db, fb, lg, false, 1, M, M, nb, none, none);
@@ -358,6 +360,7 @@ int stark_poly_mul(stark_ctx *ctx, const uint64_t *a, size_t na, const uint64_t 
   }
   if (rc == STARK_OK) rc = download_u64(ctx, fb, m, out);
   dev_free(ctx, da), dev_free(ctx, db), dev_free(ctx, fa), dev_free(ctx, fb);
+  if (rc == STARK_OK) rc = upload_u64_check(ctx);
   if (rc == STARK_OK) *out_len = m;
   return rc;
 }
@@ -372,12 +375,14 @@ int stark_poly_eval_coset(stark_ctx *ctx, const uint64_t *coeffs, size_t nc, uin
   u32 *dc = nullptr, *dv = nullptr;
   ST_TRY(dev_alloc(ctx, (void **)&dc, (nc ? nc : 1) * 4));
   ST_TRY(dev_alloc(ctx, (void **)&dv, N * 4));
-  int rc = upload_u64(ctx, coeffs, nc, dc);
+  int rc = upload_flag_reset(ctx);
+  if (rc == STARK_OK) rc = upload_u64_nosync(ctx, coeffs, nc, dc);
   ScaleSpec none = {ntt::SCALE_NONE, 1, 1};
   ScaleSpec pre = {ntt::SCALE_GEO, 1, (u32)offset};
   if (rc == STARK_OK) rc = ntt_transform(ctx, dc, dv, (int)log_n, false, 1, N, N, nc, pre, none);
   if (rc == STARK_OK) rc = download_u64(ctx, dv, N, out);
   dev_free(ctx, dc), dev_free(ctx, dv);
+  if (rc == STARK_OK) rc = upload_u64_check(ctx);
   return rc;
 }
 
@@ -391,12 +396,14 @@ int stark_poly_interpolate_coset(stark_ctx *ctx, const uint64_t *vals, uint64_t 
   u32 *dv = nullptr, *dc = nullptr;
   ST_TRY(dev_alloc(ctx, (void **)&dv, N * 4));
   ST_TRY(dev_alloc(ctx, (void **)&dc, N * 4));
-  int rc = upload_u64(ctx, vals, N, dv);
+  int rc = upload_flag_reset(ctx);
+  if (rc == STARK_OK) rc = upload_u64_nosync(ctx, vals, N, dv);
   ScaleSpec none = {ntt::SCALE_NONE, 1, 1};
   ScaleSpec post = {ntt::SCALE_GEO, ff::inv((u32)(N % ff::P)), ff::inv((u32)offset)};
   if (rc == STARK_OK) rc = ntt_transform(ctx, dv, dc, (int)log_n, true, 1, N, N, N, none, post);
   if (rc == STARK_OK) rc = download_u64(ctx, dc, N, coeffs);
   dev_free(ctx, dv), dev_free(ctx, dc);
+  if (rc == STARK_OK) rc = upload_u64_check(ctx);
   // shape rule (add.rs:7-12, mul.rs:7-12): all-zero values -> [] for N >= 2, [0] for N == 1
   if (rc == STARK_OK) *out_len = all_zero(vals, N) ? (N == 1 ? 1 : 0) : N;
   return rc;
