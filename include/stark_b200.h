@@ -217,6 +217,32 @@ int stark_prove_trace(stark_ctx *ctx, const uint64_t *cols, uint32_t n_cols, uin
 int stark_prove_trace_dev(stark_ctx *ctx, const stark_buf *cols, uint32_t n_cols, uint32_t log_n,
                           uint32_t log_blowup, uint64_t offset, uint32_t num_colinearity_tests,
                           uint8_t *column_roots, uint8_t *proof, size_t proof_cap, size_t *proof_len);
+/* Fri::verify (fri.rs:313-505) with test_colinearity (fri.rs:507-525) and MerkleTree::verify (merkle.rs:82-97) as a
+ * batch verifier on the device: `proof` is ProofStream::serialize's bytes (stream.rs:35-64), `transcript` the
+ * caller's FiatShamir state before the call (fiat_shamir.rs:4-13; empty for a fresh one).  *ok = the reference's
+ * return value; *reason (optional) = 0 or the index of the reference's `println!` text, see stark_fri_verify_reason.
+ * Optional outputs: roots_out = the num_rounds() Merkle roots popped from the stream (the shim absorbs them into its
+ * FiatShamir like fri.rs:327), top_indices = the num_colinearity_tests sampled indices (fri.rs:401-407), poly_indices /
+ * poly_values = the 2 * num_colinearity_tests (index, value) pairs of `polynomial_values` (fri.rs:437-441); the last
+ * three are written only when *ok.  Status 1 mirrors the reference's panics: Fri::new asserts (fri.rs:37-45),
+ * MerkleTree::new on an empty / non-power-of-two last codeword (merkle.rs:12-16), the sample_indices asserts
+ * (fri.rs:183-192), u128 underflow in FiniteField::sub on non-canonical stream values (ff.rs:154-160).  omega must be
+ * FiniteField::prim_nth_root(domain_length) (what every Fri in the reference is built with). */
+int stark_fri_verify(stark_ctx *ctx, const uint8_t *proof, size_t proof_len, size_t domain_length, uint64_t offset,
+                     uint64_t omega, uint32_t expansion_factor, uint32_t num_colinearity_tests,
+                     const uint8_t *transcript, size_t transcript_len, int *ok, uint32_t *reason, uint8_t *roots_out,
+                     uint64_t *top_indices, uint64_t *poly_indices, uint64_t *poly_values);
+const char *stark_fri_verify_reason(uint32_t reason);
+
+/* Trace ingestion (trace.rs:4-34: Trace { trace: Vec<Vec<i128>> }, get_col, to_field_elements): `rows_i128` is the
+ * row-major matrix, n_rows x n_cols values of 16 little-endian bytes each.  Every value is cast `as u64` like the
+ * reference (trace.rs:29-34) and taken mod p -- the reference's FieldElement keeps the raw cast, but the trace only
+ * enters the LDE through FiniteField::mul/add, which reduce (ff.rs:138-152).  Result: the column-major device matrix
+ * stark_lde_dev / stark_prove_trace_dev take (column c at c * n_rows). */
+int stark_trace_to_columns(stark_ctx *ctx, const void *rows_i128, size_t n_rows, uint32_t n_cols, stark_buf **out);
+int stark_prove_trace_rows(stark_ctx *ctx, const void *rows_i128, uint32_t n_cols, uint32_t log_n, uint32_t log_blowup,
+                           uint64_t offset, uint32_t num_colinearity_tests, uint8_t *column_roots, uint8_t *proof,
+                           size_t proof_cap, size_t *proof_len);
 
 #ifdef __cplusplus
 }

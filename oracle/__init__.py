@@ -374,6 +374,16 @@ def trace_fibonacci(length):
     _chk(lib().oracle_trace_fibonacci(SZ(length), _p64(out)))
     return out
 
+
+def trace_columns(rows):
+    """Trace::to_field_elements + get_col (trace.rs:21-34): rows of Python ints (i128) -> (n_cols, n_rows) raw u64 casts"""
+    n_rows, n_cols = len(rows), len(rows[0])
+    raw = b"".join((int(v) & ((1 << 128) - 1)).to_bytes(16, "little") for r in rows for v in r)
+    buf = np.frombuffer(raw, dtype=np.uint8)
+    out = np.empty((n_cols, n_rows), dtype=np.uint64)
+    _chk(lib().oracle_trace_columns(_p8(buf), SZ(n_rows), SZ(n_cols), _p64(out)))
+    return out
+
 # --------------------------------------------- fast_cpu.c (algorithm-matched, not the reference)
 
 

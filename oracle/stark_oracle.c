@@ -1079,6 +1079,22 @@ int oracle_fri_verify(u64 p, const u8 *proof, size_t len, u64 omega, u64 offset,
 int oracle_stream_count(const u8 *proof, size_t len, size_t *n_objects) {
   API_ENTER(); Stream ps; st_deserialize(&ps, proof, len); *n_objects = ps.n; st_free(&ps); API_LEAVE(); }
 
+/* trace.rs:29-34 (to_field_elements: `e as u64`, new_element keeps the raw value, ff.rs:113-118) composed with
+ * trace.rs:21-23 (get_col) for every column: rows is the row-major i128 matrix (16 little-endian bytes per value);
+ * out is column-major, column c at out + c*n_rows, RAW u64 casts (no reduction -- callers that need residues reduce) */
+int oracle_trace_columns(const u8 *rows, size_t n_rows, size_t n_cols, u64 *out) {
+  API_ENTER();
+  for (size_t r = 0; r < n_rows; r++)
+    for (size_t c = 0; c < n_cols; c++) {
+      const u8 *v = rows + 16 * (r * n_cols + c);
+      unsigned __int128 x = 0;
+      for (int k = 15; k >= 0; k--) x = (x << 8) | v[k];
+      i128 e = (i128)x;           /* the i128 the Rust side holds */
+      out[c * n_rows + r] = (u64)e; /* `e as u64`: truncation to the low 64 bits */
+    }
+  API_LEAVE();
+}
+
 /* trace.rs:36-49 + 29-34 : fibonacci column as u64 (i128 as u64 cast, no reduction) */
 int oracle_trace_fibonacci(size_t length, u64 *out) {
   API_ENTER();

@@ -53,6 +53,7 @@ def lib():
         _lib = C.CDLL(lib_path)
         _lib.stark_last_error.restype = C.c_char_p
         _lib.stark_version.restype = C.c_char_p
+        _lib.stark_fri_verify_reason.restype = C.c_char_p
         _lib.stark_ctx_launches.restype = C.c_uint64
         _lib.stark_ctx_stream.restype = C.c_void_p
         _lib.stark_buf_ptr.restype = C.c_void_p
@@ -579,6 +580,27 @@ class Context:
                                        C.byref(ln), None))
         return proof[: ln.value]
 
+    def fri_verify(self, proof, omega, offset, domain_length, expansion_factor, num_colinearity_tests, transcript=b"",
+                   details=False):
+        """Fri::verify (fri.rs:313-505) on the device.  Returns (ok, reason_text); with details=True also a dict with
+        the roots popped from the stream, the sampled top-level indices and polynomial_values (fri.rs:437-441)."""
+        b = np.frombuffer(bytes(proof), dtype=np.uint8) if len(proof) else np.zeros(0, dtype=np.uint8)
+        t = _b(transcript)
+        ok, why = C.c_int(0), U32(0)
+        nq = num_colinearity_tests
+        roots = np.zeros((64, 32), dtype=np.uint8)
+        top = np.zeros(max(nq, 1), dtype=np.uint64)
+        pidx = np.zeros(max(2 * nq, 1), dtype=np.uint64)
+        pval = np.zeros(max(2 * nq, 1), dtype=np.uint64)
+        _chk(lib().stark_fri_verify(self.h, _p8(b), SZ(len(b)), SZ(domain_length), U64(offset), U64(omega),
+                                    U32(expansion_factor), U32(nq), _p8(t), SZ(len(t)), C.byref(ok), C.byref(why),
+                                    _p8(roots), _p64(top), _p64(pidx), _p64(pval)))
+        text = lib().stark_fri_verify_reason(why).decode()
+        if not details:
+            return bool(ok.value), text
+        return bool(ok.value), text, {"roots": roots, "top": [int(x) for x in top[:nq]],
+                                      "polynomial_values": [(int(i), int(v)) for i, v in zip(pidx[:2 * nq], pval[:2 * nq])]}
+
     # ---- pipeline (BASELINE config 3)
     def prove_trace(self, cols, log_blowup, offset=3, num_colinearity_tests=32):
         """LDE + per-column Merkle commit + Fri::prove on column 0.  Returns (column_roots, proof_bytes)."""
@@ -593,6 +615,39 @@ class Context:
         ln = SZ()
         _chk(lib().stark_prove_trace(self.h, _p64(cols), U32(n_cols), U32(log_n), U32(log_blowup), U64(offset),
                                      U32(num_colinearity_tests), _p8(roots), _p8(proof), SZ(cap), C.byref(ln)))
+        return roots, proof[: ln.value].tobytes()
+
+    @staticmethod
+    def _i128_rows(rows):
+        """rows: sequence of rows of Python ints (i128 range) -> contiguous little-endian 16-byte values"""
+        n_rows, n_cols = len(rows), len(rows[0])
+        raw = bytearray(16 * n_rows * n_cols)
+        k = 0
+        for r in rows:
+            assert len(r) == n_cols
+            for v in r:
+                raw[k:k + 16] = (int(v) & ((1 << 128) - 1)).to_bytes(16, "little")
+                k += 16
+        return np.frombuffer(bytes(raw), dtype=np.uint8), n_rows, n_cols
+
+    def trace_to_columns(self, rows):
+        """Trace::to_field_elements + get_col for every column (trace.rs:21-34) -> device Buffer, column-major"""
+        raw, n_rows, n_cols = self._i128_rows(rows)
+        h = C.c_void_p()
+        _chk(lib().stark_trace_to_columns(self.h, raw.ctypes.data_as(C.c_void_p), SZ(n_rows), U32(n_cols), C.byref(h)))
+        return Buffer(self, h)
+
+    def prove_trace_rows(self, rows, log_blowup, offset=3, num_colinearity_tests=32):
+        raw, n_rows, n_cols = self._i128_rows(rows)
+        log_n = n_rows.bit_length() - 1
+        assert 1 << log_n == n_rows
+        cap = fri_proof_size(n_rows << log_blowup, 1 << log_blowup, num_colinearity_tests)
+        proof = np.empty(cap, dtype=np.uint8)
+        roots = np.empty((n_cols, 32), dtype=np.uint8)
+        ln = SZ()
+        _chk(lib().stark_prove_trace_rows(self.h, raw.ctypes.data_as(C.c_void_p), U32(n_cols), U32(log_n), U32(log_blowup),
+                                          U64(offset), U32(num_colinearity_tests), _p8(roots), _p8(proof), SZ(cap),
+                                          C.byref(ln)))
         return roots, proof[: ln.value].tobytes()
 
     def prove_trace_ptr(self, host_ptr, n_cols, log_n, log_blowup, offset, nq, roots, proof):

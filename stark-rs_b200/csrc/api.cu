@@ -25,6 +25,33 @@ __global__ void k_widen(const u32 *__restrict__ in, u64 *__restrict__ out, size_
   if (i < n) out[i] = in[i];
 }
 
+// Trace ingestion (trace.rs:21-34): rows[r][c] is an i128 (16 bytes, little-endian); the reference casts it `as u64`
+// (low 64 bits, no reduction) into a FieldElement whose value then only ever enters FiniteField::mul / add, which
+// reduce (ff.rs:138-152), so the column handed to the LDE is the residue mod p.  32 x 32 tiles through shared memory:
+// coalesced 16-byte reads along the row, coalesced 4-byte writes along the column.
+__global__ void __launch_bounds__(256) k_trace_ingest(const uint4 *__restrict__ rows, size_t n_rows, u32 n_cols,
+                                                      u32 *__restrict__ cols) {
+  __shared__ u32 tile[32][33];
+  const size_t r0 = (size_t)blockIdx.x * 32;
+  const u32 c0 = blockIdx.y * 32;
+  for (u32 i = threadIdx.y; i < 32; i += blockDim.y) {
+    const size_t r = r0 + i;
+    const u32 c = c0 + threadIdx.x;
+    u32 v = 0;
+    if (r < n_rows && c < n_cols) {
+      const uint4 x = rows[r * n_cols + c];
+      v = (u32)((((u64)x.y << 32) | x.x) % ff::P);   // i128 as u64, then the residue
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (u32 i = threadIdx.y; i < 32; i += blockDim.y) {
+    const u32 c = c0 + i;
+    const size_t r = r0 + threadIdx.x;
+    if (r < n_rows && c < n_cols) cols[(size_t)c * n_rows + r] = tile[threadIdx.x][i];
+  }
+}
+
 enum { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2, OP_NEG = 3, OP_POW = 4 };
 // element-wise ff.rs:138-167, 200-213 on canonical u32
 __global__ void k_ff_vec(int op, const u32 *__restrict__ a, const u32 *__restrict__ b, u64 e, u32 *__restrict__ out,
@@ -140,6 +167,19 @@ int download_u64(stark_ctx *ctx, const u32 *src, size_t n, uint64_t *host) {
   CU_TRY(ctx, cudaMemcpyAsync(host, tmp, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
   dev_free(ctx, tmp);
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return STARK_OK;
+}
+
+// trace ingestion: H2D of the row-major i128 matrix + k_trace_ingest (no synchronisation)
+int trace_to_columns_dev(stark_ctx *ctx, const void *rows_i128, size_t n_rows, u32 n_cols, u32 *cols) {
+  const size_t bytes = n_rows * (size_t)n_cols * 16;
+  if (bytes == 0) return STARK_OK;
+  uint4 *tmp = nullptr;
+  ST_TRY(dev_alloc(ctx, (void **)&tmp, bytes));
+  CU_TRY(ctx, cudaMemcpyAsync(tmp, rows_i128, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(ctx, "trace_ingest", bytes + 4 * n_rows * (size_t)n_cols,
+         k_trace_ingest<<<dim3((u32)((n_rows + 31) / 32), (n_cols + 31) / 32), dim3(32, 8), 0, ctx->stream>>>(tmp, n_rows, n_cols, cols));
+  dev_free(ctx, tmp);
   return STARK_OK;
 }
 
@@ -293,6 +333,21 @@ void stark_buf_free(stark_buf *buf) {
   if (!buf) return;
   if (buf->owns && buf->ptr) dev_free(buf->ctx, buf->ptr);
   delete buf;
+}
+
+// ---- trace ingestion
+int stark_trace_to_columns(stark_ctx *ctx, const void *rows_i128, size_t n_rows, uint32_t n_cols, stark_buf **out) {
+  if (!ctx || !out || (!rows_i128 && n_rows * (size_t)n_cols)) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+  stark_buf *b = nullptr;
+  ST_TRY(stark_buf_alloc(ctx, n_rows * (size_t)n_cols, &b));
+  int rc = trace_to_columns_dev(ctx, rows_i128, n_rows, n_cols, b->ptr);
+  if (rc == STARK_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = stark_fail(ctx, STARK_ERR_CUDA, "trace ingestion failed");
+  if (rc != STARK_OK) {
+    stark_buf_free(b);
+    return rc;
+  }
+  *out = b;
+  return STARK_OK;
 }
 
 // ---- ff.rs batch ops

@@ -274,6 +274,13 @@ __global__ void __launch_bounds__(256) k_sample_indices(const TranscriptDev *T, 
   }
 }
 
+// host wrapper for the verifier (verify.cu): the same index sampling on a transcript the verifier rebuilt
+int fri_sample_indices_dev(stark_ctx *ctx, const TranscriptDev *T, u64 *d_challenge, u64 size, u64 reduced, u32 number,
+                           u64 *d_out) {
+  LAUNCH_PDL(ctx, "sample_indices", 0, k_sample_indices, 1, 256, T, d_challenge, size, reduced, number, d_out);
+  return STARK_OK;
+}
+
 // ------------------------------------------------------------------------------------ proof assembly
 
 __device__ __forceinline__ void put_u64(u8 *d, u64 v) {
@@ -908,6 +915,22 @@ int stark_prove_trace(stark_ctx *ctx, const uint64_t *cols, uint32_t n_cols, uin
     rc = stark_prove_trace_dev(ctx, in, n_cols, log_n, log_blowup, offset, nq, column_roots, proof, proof_cap, proof_len);
   stark_buf_free(in);
   if (rc == STARK_OK) rc = upload_u64_check(ctx);
+  return rc;
+}
+
+// the same from the reference's own trace layout (trace.rs:4-34): row-major i128 values, 16 bytes each
+int stark_prove_trace_rows(stark_ctx *ctx, const void *rows_i128, uint32_t n_cols, uint32_t log_n, uint32_t log_blowup,
+                           uint64_t offset, uint32_t nq, uint8_t *column_roots, uint8_t *proof, size_t proof_cap,
+                           size_t *proof_len) {
+  if (!ctx || !rows_i128 || n_cols == 0) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+  if (log_n > (u32)ff::TWO_ADICITY) return stark_fail(ctx, STARK_ERR_ARG, "n > 2^23 not supported by this modulus");
+  const size_t n = (size_t)1 << log_n;
+  stark_buf *in = nullptr;
+  ST_TRY(stark_buf_alloc(ctx, n * n_cols, &in));
+  int rc = trace_to_columns_dev(ctx, rows_i128, n, n_cols, in->ptr);
+  if (rc == STARK_OK)
+    rc = stark_prove_trace_dev(ctx, in, n_cols, log_n, log_blowup, offset, nq, column_roots, proof, proof_cap, proof_len);
+  stark_buf_free(in);
   return rc;
 }
 

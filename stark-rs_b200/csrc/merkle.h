@@ -32,4 +32,5 @@ int upload_flag_reset(stark_ctx *ctx);                                         /
 int upload_u64_nosync(stark_ctx *ctx, const uint64_t *host, size_t n, u32 *dst);  // no host round trip ...
 int upload_u64_check(stark_ctx *ctx);                                          // ... flag read after the final sync
 int download_u64(stark_ctx *ctx, const u32 *src, size_t n, uint64_t *host);   // widen + D2H (synchronises)
+int trace_to_columns_dev(stark_ctx *ctx, const void *rows_i128, size_t n_rows, u32 n_cols, u32 *cols);
 int lde_dev(stark_ctx *ctx, const u32 *cols, u32 n_cols, u32 log_n, u32 log_blowup, u32 offset, u32 *out);

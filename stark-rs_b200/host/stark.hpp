@@ -417,6 +417,30 @@ struct Fri {
     }
     return std::vector<size_t>(top.begin(), top.begin() + num_colinearity_tests);
   }
+  // fri.rs:313-505 on the device (stark_fri_verify).  On success the stream objects the reference pops are consumed, the
+  // roots are absorbed into fiat_shamir (fri.rs:327) and polynomial_values receives the top-layer pairs (fri.rs:437-441);
+  // on failure the reference's println! line is printed and false returned.
+  bool verify(ProofStream &proof_stream, FiatShamir &fiat_shamir,
+              std::vector<std::pair<size_t, FieldElement>> &polynomial_values) const {
+    const std::vector<uint8_t> bytes = proof_stream.serialize();
+    const size_t nq = num_colinearity_tests, R = (size_t)num_rounds();
+    int ok = 0;
+    uint32_t why = 0;
+    std::vector<uint8_t> roots(32 * (R ? R : 1));
+    std::vector<uint64_t> top(nq ? nq : 1), pi(2 * nq + 1), pv(2 * nq + 1);
+    check(stark_fri_verify(ctx(), bytes.data(), bytes.size(), domain_length, offset.value, omega.value,
+                           (uint32_t)expansion_factor, (uint32_t)nq, fiat_shamir.transcript.data(),
+                           fiat_shamir.transcript.size(), &ok, &why, roots.data(), top.data(), pi.data(), pv.data()));
+    if (!ok) {
+      printf("%s\n", stark_fri_verify_reason(why));
+      return false;
+    }
+    for (size_t r = 0; r < R; r++) fiat_shamir.absorb(&roots[32 * r], 32);
+    for (size_t i = 0; R > 1 && i < 2 * nq; i++) polynomial_values.push_back({(size_t)pi[i], field.new_element(pv[i])});
+    const size_t consumed = R + 1 + (R - 1) * 4 * nq;
+    proof_stream.objects.erase(proof_stream.objects.begin(), proof_stream.objects.begin() + consumed);
+    return true;
+  }
 };
 
 // trace.rs:21-34 columns -> low-degree extension, column-major
@@ -430,5 +454,55 @@ inline std::vector<std::vector<uint64_t>> lde(const std::vector<std::vector<uint
   for (size_t c = 0; c < cols.size(); c++) r.emplace_back(out.begin() + c * N, out.begin() + (c + 1) * N);
   return r;
 }
+
+// trace.rs:4-49: the trace container (row-major i128) with ingestion + prove on the device
+struct Trace {
+  std::vector<std::vector<__int128>> trace;
+  size_t num_columns;
+  explicit Trace(const std::vector<std::vector<__int128>> &rows) : trace(rows), num_columns(rows.at(0).size()) {}
+  const std::vector<__int128> *get_row(size_t i) const { return i < trace.size() ? &trace[i] : nullptr; }
+  std::vector<__int128> get_col(size_t j) const {
+    std::vector<__int128> c;
+    for (const auto &r : trace) c.push_back(r.at(j));
+    return c;
+  }
+  std::vector<std::vector<FieldElement>> to_field_elements(FiniteField field) const {   // `e as u64`, not reduced
+    std::vector<std::vector<FieldElement>> out;
+    for (const auto &r : trace) {
+      out.emplace_back();
+      for (__int128 e : r) out.back().push_back(field.new_element((uint64_t)e));
+    }
+    return out;
+  }
+  static Trace fibonacci(size_t length) {
+    std::vector<std::vector<__int128>> rows;
+    __int128 a = 1, b = 1;
+    for (size_t i = 0; i < length; i++) {
+      rows.push_back({a});
+      __int128 next;
+      if (__builtin_add_overflow(a, b, &next)) throw Panic("attempt to add with overflow");
+      a = b, b = next;
+    }
+    return Trace(rows);
+  }
+  // LDE + per-column Merkle roots + Fri::prove of column 0 from the rows as they lie: stark_prove_trace_rows
+  std::pair<std::vector<Hash>, std::vector<uint8_t>> prove(uint32_t log_blowup, uint64_t offset, uint32_t num_colinearity_tests) const {
+    const size_t n = trace.size();
+    if (n == 0 || (n & (n - 1))) throw Panic("n must be a power of two");
+    std::vector<__int128> flat;
+    for (const auto &r : trace) {
+      if (r.size() != num_columns) throw Panic("ragged trace");
+      flat.insert(flat.end(), r.begin(), r.end());
+    }
+    size_t cap = 0, len = 0;
+    check(stark_fri_proof_size(n << log_blowup, 1u << log_blowup, num_colinearity_tests, &cap));
+    std::vector<Hash> roots(num_columns);
+    std::vector<uint8_t> proof(cap);
+    check(stark_prove_trace_rows(ctx(), flat.data(), (uint32_t)num_columns, (uint32_t)__builtin_ctzll(n), log_blowup, offset,
+                                 num_colinearity_tests, roots.data()->b, proof.data(), cap, &len));
+    proof.resize(len);
+    return {roots, proof};
+  }
+};
 
 }  // namespace stark

@@ -1,4 +1,4 @@
-//! Fri (reference fri.rs:8-311): the prover runs on the GPU (stark_fri_prove), the verifier stays with the reference.
+//! Fri (reference fri.rs:8-311): prover (stark_fri_prove) and verifier (stark_fri_verify) run on the GPU.
 #![allow(dead_code)]
 use crate::ff::{FieldElement, FiniteField};
 use crate::ffi;
@@ -48,5 +48,28 @@ impl Fri {
         }
         top.truncate(self.num_colinearity_tests);
         top.into_iter().map(|i| i as usize).collect()
+    }
+    /// fri.rs:313-505 on the device.  On success the objects the reference pops are consumed, the roots are absorbed into
+    /// `fiat_shamir` (fri.rs:327) and `polynomial_values` receives the top-layer pairs (fri.rs:437-441); on failure the
+    /// reference's println! line is printed and false returned.
+    pub fn verify(&self, proof_stream: &mut ProofStream, fiat_shamir: &mut FiatShamir, polynomial_values: &mut Vec<(usize, FieldElement)>) -> bool {
+        let bytes = proof_stream.serialize();
+        let (nq, rounds) = (self.num_colinearity_tests, self.num_rounds() as usize);
+        let (mut ok, mut why) = (0i32, 0u32);
+        let mut roots = vec![0u8; 32 * rounds.max(1)];
+        let (mut top, mut pi, mut pv) = (vec![0u64; nq.max(1)], vec![0u64; 2 * nq + 1], vec![0u64; 2 * nq + 1]);
+        ffi::check(unsafe {
+            ffi::stark_fri_verify(ffi::ctx(), bytes.as_ptr(), bytes.len(), self.domain_length, self.offset.value, self.omega.value,
+                                  self.expansion_factor as u32, nq as u32, fiat_shamir.transcript.as_ptr(), fiat_shamir.transcript.len(),
+                                  &mut ok, &mut why, roots.as_mut_ptr(), top.as_mut_ptr(), pi.as_mut_ptr(), pv.as_mut_ptr())
+        });
+        if ok == 0 {
+            println!("{}", unsafe { std::ffi::CStr::from_ptr(ffi::stark_fri_verify_reason(why)) }.to_string_lossy());
+            return false;
+        }
+        for r in 0..rounds { fiat_shamir.absorb(&roots[32 * r..32 * r + 32]); }
+        if rounds > 1 { for i in 0..2 * nq { polynomial_values.push((pi[i] as usize, self.field.new_element(pv[i]))); } }
+        for _ in 0..rounds + 1 + (rounds - 1) * 4 * nq { proof_stream.pop(); }
+        true
     }
 }

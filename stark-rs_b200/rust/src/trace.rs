@@ -13,6 +13,26 @@ impl Trace {
     pub fn to_field_elements(&self, field: FiniteField) -> Vec<Vec<FieldElement>> {
         self.trace.iter().map(|r| r.iter().map(|&e| field.new_element(e as u64)).collect()).collect()
     }
+    /// Every column as canonical residues on the device (`e as u64` like to_field_elements, then mod p as
+    /// FiniteField::mul/add see it), column-major: stark_trace_to_columns.  Rows must all have num_columns entries.
+    fn flat(&self) -> Vec<i128> {
+        assert!(self.trace.iter().all(|r| r.len() == self.num_columns));
+        self.trace.iter().flatten().copied().collect()
+    }
+    /// LDE (blowup 2^log_blowup, coset offset) + per-column Merkle roots + Fri::prove of column 0, straight from the
+    /// row-major i128 rows: stark_prove_trace_rows.  Returns (column roots, ProofStream::serialize bytes).
+    pub fn prove(&self, log_blowup: u32, offset: u64, num_colinearity_tests: u32) -> (Vec<[u8; 32]>, Vec<u8>) {
+        let n = self.trace.len();
+        assert!(n.is_power_of_two(), "n must be a power of two");
+        let flat = self.flat();   // i128 is 16 little-endian bytes on every target this library runs on
+        let mut cap = 0usize;
+        ffi::check(unsafe { ffi::stark_fri_proof_size(n << log_blowup, 1 << log_blowup, num_colinearity_tests, &mut cap) });
+        let (mut roots, mut proof, mut len) = (vec![[0u8; 32]; self.num_columns], vec![0u8; cap], 0usize);
+        ffi::check(unsafe { ffi::stark_prove_trace_rows(ffi::ctx(), flat.as_ptr() as *const std::ffi::c_void, self.num_columns as u32,
+            n.trailing_zeros(), log_blowup, offset, num_colinearity_tests, roots.as_mut_ptr() as *mut u8, proof.as_mut_ptr(), cap, &mut len) });
+        proof.truncate(len);
+        (roots, proof)
+    }
     pub fn fibonacci(length: usize) -> Trace {
         let (mut a, mut b) = (1i128, 1i128);
         let rows: Vec<Vec<i128>> = (0..length).map(|_| { let r = vec![a]; (a, b) = (b, a + b); r }).collect();

@@ -30,6 +30,19 @@ static void fri_case(size_t n, uint64_t off, size_t ef, size_t nq, std::vector<u
   oracle_fri_verify(P, bytes.data(), bytes.size(), omega.value, off, n, ef, nq, &ok, why, sizeof why);
   if (!ok) printf("verify: %s\n", why);
   EXPECT(ok == 1);
+  // the reference's own test body (fri.rs:563-570): a fresh FiatShamir, verify, and the returned points lie on the codeword
+  FiatShamir fs2;
+  std::vector<std::pair<size_t, FieldElement>> points;
+  const size_t n_obj = ps.objects.size();
+  EXPECT(fri.verify(ps, fs2, points));
+  EXPECT(fs2.transcript == fs.transcript && ps.objects.size() < n_obj);
+  EXPECT(points.size() == 2 * nq);
+  for (auto &pt : points) EXPECT(codeword[pt.first] == pt.second);
+  // a tampered stream is rejected (fri.rs has no negative test; the oracle's verdict is the reference here)
+  ProofStream bad = ProofStream::deserialize(bytes);
+  bad.objects[fri.num_rounds()].values[0] ^= 1;
+  FiatShamir fs3;
+  EXPECT(!fri.verify(bad, fs3, points));
 }
 
 int main() {
@@ -83,6 +96,17 @@ int main() {
   try { Fri f(field.prim_nth_root(64), field.new_element(3), 64, 2, 2); EXPECT(false); } catch (const Panic &e) { EXPECT(std::string(e.what()) == "Expansion factor must be at least 4"); }
   auto cols = lde({std::vector<uint64_t>{1, 1, 2, 3, 5, 8, 13, 21}}, 2, 3);
   EXPECT(cols[0].size() == 32);
+  // trace.rs:36-49 through the row-major entry point: Fibonacci column -> LDE x4 -> Fri::prove, checked by the oracle's verifier
+  {
+    Trace t = Trace::fibonacci(64);
+    EXPECT(t.num_columns == 1 && t.get_col(0)[5] == 8 && t.to_field_elements(field)[63][0].value == 10610209857723ull);
+    auto [roots, proof] = t.prove(2, 3, 8);
+    int ok = 0;
+    char why[128];
+    oracle_fri_verify(P, proof.data(), proof.size(), field.prim_nth_root(256).value, 3, 256, 4, 8, &ok, why, sizeof why);
+    EXPECT(ok && roots.size() == 1);
+    try { Trace::fibonacci(200); EXPECT(false); } catch (const Panic &e) { EXPECT(std::string(e.what()) == "attempt to add with overflow"); }
+  }
   printf(fails ? "host_mirror: %d FAILED\n" : "host_mirror: all ok\n", fails);
   return fails != 0;
 }

@@ -164,6 +164,51 @@ def test_prove_trace_pipeline(ctx, oracle, log_n, n_cols):
     assert oracle.fri_verify(proof, w, 3, N, 4, nq)[0]
 
 
+def _i128_rows(seed, n_rows, n_cols):
+    """random i128 rows: small values, negatives, values above 2^64 and the extremes (trace.rs:4-7 holds Vec<Vec<i128>>)"""
+    rng = np.random.default_rng(seed)
+    lo = rng.integers(0, 1 << 63, (n_rows, n_cols), dtype=np.uint64).astype(object) * 2 + rng.integers(0, 2, (n_rows, n_cols)).astype(object)
+    hi = rng.integers(-(1 << 62), 1 << 62, (n_rows, n_cols)).astype(object) * 2
+    kind = rng.integers(0, 4, (n_rows, n_cols))
+    rows = [[int(lo[r, c]) % 1000 if kind[r, c] == 0 else int(lo[r, c]) if kind[r, c] == 1 else
+             -int(lo[r, c]) if kind[r, c] == 2 else (int(hi[r, c]) << 64) + int(lo[r, c]) for c in range(n_cols)]
+            for r in range(n_rows)]
+    rows[0][0], rows[-1][-1] = (1 << 127) - 1, -(1 << 127)
+    return rows
+
+
+@pytest.mark.parametrize("n_rows,n_cols", [(1, 1), (5, 3), (33, 31), (64, 1), (100, 40), (1 << 12, 2)])
+def test_trace_to_columns(ctx, oracle, n_rows, n_cols):
+    """trace ingestion: row-major i128 -> column-major residues, ragged tile edges included"""
+    rows = _i128_rows(n_rows * 131 + n_cols, n_rows, n_cols)
+    got = ctx.trace_to_columns(rows).download().reshape(n_cols, n_rows)
+    want = oracle.trace_columns(rows) % np.uint64(P)     # raw `as u64` casts (trace.rs:29-34), residue as ff.rs:138-152 sees them
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("log_n,n_cols", [(6, 1), (9, 3), (12, 2)])
+def test_prove_trace_rows(ctx, oracle, log_n, n_cols):
+    """the prove pipeline fed with the reference's own trace container layout gives the bytes of the column-major path"""
+    rows = _i128_rows(log_n, 1 << log_n, n_cols)
+    nq = 4 if log_n < 10 else 32
+    cols = oracle.trace_columns(rows) % np.uint64(P)
+    roots, proof = ctx.prove_trace_rows(rows, 2, 3, nq)
+    roots2, proof2 = ctx.prove_trace(cols, 2, 3, nq)
+    assert proof == proof2 and np.array_equal(roots, roots2)
+    lde = oracle.fast_lde(cols[0], log_n, 2, 3)
+    assert proof == oracle.fri_prove(lde, oracle.ff_prim_nth_root(4 << log_n), 3, 4, nq)["proof"]
+
+
+def test_prove_trace_rows_fibonacci(ctx, oracle):
+    """BASELINE config 1's Trace::fibonacci(64) column through the row-major entry point (trace.rs:36-49)"""
+    fib = oracle.trace_fibonacci(64)
+    rows = [[int(v)] for v in fib]
+    roots, proof = ctx.prove_trace_rows(rows, 2, 3, 8)
+    lde = oracle.lde(fib % np.uint64(P), 4, 3)
+    assert proof == oracle.fri_prove(lde, oracle.ff_prim_nth_root(256), 3, 4, 8)["proof"]
+    assert roots[0].tobytes() == oracle.merkle_commit(oracle.hash_leaves(lde))
+
+
 def test_prove_trace_rejects_non_canonical_input(ctx, S):
     """stark_prove_trace checks canonical input without a mid-pipeline host round trip: the error must still surface"""
     col = np.arange(1 << 8, dtype=np.uint64)

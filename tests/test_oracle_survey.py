@@ -171,3 +171,17 @@ def test_trace_fibonacci(oracle):
     assert list(col[:6]) == [1, 1, 2, 3, 5, 8] and int(col[63]) == 10610209857723
     with pytest.raises(oracle.OraclePanic):
         oracle.trace_fibonacci(200)                                         # i128 overflow (debug panic)
+
+
+def test_trace_columns(oracle):
+    """trace.rs:21-34: `e as u64` keeps the low 64 bits of the two's-complement i128; get_col transposes"""
+    rows = [[1, -1, 1 << 64], [(1 << 127) - 1, -(1 << 127), 998244353], [7, (1 << 64) + 5, -998244353]]
+    cols = oracle.trace_columns(rows)
+    assert cols.shape == (3, 3)
+    m = (1 << 64) - 1
+    assert [int(x) for x in cols[0]] == [1, m, 7]
+    assert [int(x) for x in cols[1]] == [m, 0, 5]
+    assert [int(x) for x in cols[2]] == [0, 998244353, (-998244353) & m]
+    fib = [[int(v)] for v in oracle.trace_fibonacci(64)]                    # Trace::fibonacci(64).get_col(0)
+    assert np.array_equal(oracle.trace_columns(fib)[0], oracle.trace_fibonacci(64))
+
