@@ -306,6 +306,14 @@ def run_ours(a):
         "ms_per_step_profiled": ms_prof / a.steps, "hash_latency_cycles": ctx.hash_latency(), "int_peak": ipk,
     }
 
+    # Fri::verify of the timed proof on the device (stark_fri_verify; outside the timed region)
+    try:
+        t0 = time.perf_counter()
+        okd, whyd = ctx.fri_verify(proof_bytes, pow(3, (998244353 - 1) // N, 998244353), 3, N, ef, a.nq)
+        line["proof_verified_on_device"] = {"ok": bool(okd), "reason": whyd, "ms_host_to_verdict": 1e3 * (time.perf_counter() - t0)}
+    except Exception as e:  # noqa: BLE001
+        line["proof_verified_on_device"] = {"ok": False, "reason": "error: %s" % e}
+
     if world == 1 and not a.no_cpu_baseline:
         import oracle as O
         threads = os.cpu_count() or 1
