@@ -26,6 +26,15 @@ col = O.splitmix64(2, 1 << 11)
 roots, proof = ctx.prove_trace(col, 2, 3, 16)
 lde = O.fast_lde(col, 11, 2, 3)
 assert proof == O.fri_prove(lde, O.ff_prim_nth_root(1 << 13), 3, 4, 16)["proof"]
+# verifier (transcript replay, last-codeword tree + iNTT, rounds kernel) and trace ingestion (ragged 32 x 32 tiles)
+w13 = O.ff_prim_nth_root(1 << 13)
+assert ctx.fri_verify(proof, w13, 3, 1 << 13, 4, 16) == (True, "")
+assert ctx.fri_verify(proof[:-7], w13, 3, 1 << 13, 4, 16)[0] is False
+rows = [[(r * 7 + c) * (-1) ** r for c in range(5)] for r in range(1 << 7)]
+got = ctx.trace_to_columns(rows).download().reshape(5, -1)
+assert np.array_equal(got, O.trace_columns(rows) % np.uint64(998244353))
+roots2, proof2 = ctx.prove_trace_rows(rows, 2, 3, 8)
+assert ctx.fri_verify(proof2, O.ff_prim_nth_root(1 << 9), 3, 1 << 9, 4, 8)[0]
 big = O.splitmix64(3, 1 << 18)
 t = ctx.merkle_build_from_values(big)      # one throughput level launch + climb
 assert t.get_root() == O.merkle_commit(O.hash_leaves(big))
