@@ -37,9 +37,24 @@ constexpr int TWO_ADICITY = 23;     // ff.rs:218
 
 // a: any u32, b < p  ->  a*b*2^-32 mod p, in [0, 2p)
 FF_HD u32 mont_mul(u32 a, u32 b) {
+#if defined(__CUDA_ARCH__)
+  // Exactly three FMA-pipe instructions: IMAD.WIDE.U32 (ab), IMAD (m), IMAD.HI.U32 with the 64-bit addend ab.  The C
+  // form below reaches ptxas as 64-bit multiplies; it emits the same three plus an add of the zero cross term
+  // (IADD3 Rd, Rhi, UR(=0)) per product on the ALU pipe -- 8 % of an NTT pass, 15 % of its ALU-pipe load.
+  u32 r;
+  asm("{\n\t.reg .u32 lo, hi, m, tl;\n\t"
+      "mul.lo.u32 lo, %1, %2;\n\t"
+      "mul.hi.u32 hi, %1, %2;\n\t"
+      "mul.lo.u32 m, lo, %3;\n\t"
+      "mad.lo.cc.u32 tl, m, %4, lo;\n\t"
+      "madc.hi.u32 %0, m, %4, hi;\n\t}"
+      : "=r"(r) : "r"(a), "r"(b), "r"(NPINV), "r"(P));
+  return r;
+#else
   u64 ab = (u64)a * b;
   u32 m = (u32)ab * NPINV;
   return (u32)((ab + (u64)m * P) >> 32);
+#endif
 }
 // [0, 4p) -> [0, 2p)
 FF_HD u32 red2p(u32 x) {
