@@ -57,6 +57,10 @@ int stark_ctx_profile_end(stark_ctx *ctx, char *json, size_t cap);
 /* register-only integer issue-rate microbenchmark: thread-instructions per second of IMAD, LOP3/IADD3 and a
  * 1:1 mix, measured with CUDA events (no integer peak is recorded in MEASURED_PEAKS.json) */
 int stark_bench_int_peak(stark_ctx *ctx, double *imad_per_s, double *alu_per_s, double *mixed_per_s);
+/* rates of the pieces of a Montgomery product (ff.rs:138-144 replacement), thread-operations per second: out[0]
+ * IMAD.WIDE.U32 (32 x 32 -> 64, both halves consumed), out[1] IMAD.HI.U32, out[2] Montgomery products (3 multiplies each), out[3] NTT
+ * butterfly steps (product + lazy add + range reduction) */
+int stark_bench_mul_peak(stark_ctx *ctx, double *out4);
 /* dependent-hash latency (clock cycles per Hash::combine) of one warp alone on an SM, for the one-hash-per-thread,
  * two-per-thread and four-lanes-per-hash kernels forms (measurement only) */
 int stark_bench_hash_latency(stark_ctx *ctx, double *hs_cycles, double *hs2_cycles, double *hsq_cycles);

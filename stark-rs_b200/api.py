@@ -313,6 +313,12 @@ class Context:
         _chk(lib().stark_bench_int_peak(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return {"imad_per_s": a.value, "alu_per_s": b.value, "mixed_per_s": c.value}
 
+    def mul_peak(self):
+        """rates of the pieces of a Montgomery product (thread-operations/s), stark_bench_mul_peak"""
+        out = (C.c_double * 4)()
+        _chk(lib().stark_bench_mul_peak(self.h, out))
+        return {"imad_wide_per_s": out[0], "imad_hi_per_s": out[1], "mont_mul_per_s": out[2], "butterfly_step_per_s": out[3]}
+
     def hash_latency(self):
         a, b, c = C.c_double(), C.c_double(), C.c_double()
         _chk(lib().stark_bench_hash_latency(self.h, C.byref(a), C.byref(b), C.byref(c)))

@@ -31,11 +31,21 @@ struct stark_ctx {
   // per-length sub-transform twiddles: tw_sub[dir][(1 << logL) + e] = w_L^(+-e), logL <= 12
   u32 *tw_sub[2];
   u32 w8[2][4];
+  // the same sub-transform twiddles and w_8 powers in Shoup form (plain value + floor(w 2^32 / p)) for ntt_pass.cuh
+  ntt::wpair *tw_sh[2];
+  ntt::wpair w8_sh[2][4];
   GeoCacheEntry geo[8];
   u64 geo_stamp;
   u32 *flag;       // device int used by validation kernels
   u32 *h_flag;     // pinned host mirror
   u64 launches;    // kernels launched through this context (bench.py "gpu_launches")
+  // side streams for batched transforms larger than L2 (ntt.cu: column groups run all passes back to back, a few groups
+  // in flight): created on first use
+  cudaStream_t side[4];
+  cudaEvent_t side_done[4], fork_ev;
+  int n_side;            // streams created so far
+  int ntt_streams;       // groups in flight (STARK_NTT_STREAMS, default 2; 1 = whole batch per pass)
+  int ntt_group_mb;      // bytes of one group's column slice (STARK_NTT_GROUP_MB, default 16)
   char err[512];
   // optional per-kernel timing (stark_ctx_profile_begin/end): CUDA events around every launch, on ctx->stream
   bool prof_on;

@@ -56,6 +56,20 @@ FF_HD u32 mont_mul(u32 a, u32 b) {
   return (u32)((ab + (u64)m * P) >> 32);
 #endif
 }
+// Multiplication by a CONSTANT w < p whose companion ws = floor(w * 2^32 / p) is known (Shoup): x any u32 ->
+// x*w mod p in [0, 2p), with w in plain (not Montgomery) form.  IMAD.HI + 2 IMAD.  On B200 the 64-bit-result multiplies
+// (IMAD.WIDE, IMAD.HI) issue at HALF the rate of a 32-bit IMAD (stark_bench_mul_peak: 9.1 / 9.3 T vs 18.5 T thread-
+// instructions/s), so a Montgomery product occupies the FMA-heavy pipe for 2+1+2 = 5 slots and this one for 2+1+1 = 4:
+// every product with a table twiddle takes this form; Montgomery stays for products of two run-time values.
+FF_HD u32 shoup_mul(u32 x, u32 w, u32 ws) {
+#if defined(__CUDA_ARCH__)
+  const u32 q = __umulhi(x, ws);
+#else
+  const u32 q = (u32)(((u64)x * ws) >> 32);
+#endif
+  return x * w - q * P;
+}
+FF_HD u32 shoup_of(u32 w) { return (u32)(((u64)w << 32) / P); }
 // [0, 4p) -> [0, 2p)
 FF_HD u32 red2p(u32 x) {
   u32 y = x - P2;
@@ -67,6 +81,10 @@ FF_HD u32 canon(u32 x) {
   return y < x ? y : x;
 }
 FF_HD u32 canon4(u32 x) { return canon(red2p(x)); }
+// a + b pinned to the ALU pipe: ptxas turns a plain 32-bit add into IMAD.IADD on the FMA-heavy pipe where it believes
+// that pipe has room, but it counts IMAD.WIDE / IMAD.HI as one slot.  A third addend that is zero only at RUN time
+// (a kernel parameter) keeps the add a three-input IADD3, which the FMA pipe cannot execute, at no extra instruction.
+FF_HD u32 add_alu(u32 a, u32 b, u32 zero) { return a + b + zero; }
 // lazy add/sub on [0, 2p) operands -> [0, 4p)
 FF_HD u32 add_lazy(u32 a, u32 b) { return a + b; }
 FF_HD u32 sub_lazy(u32 a, u32 b) { return a + P2 - b; }

@@ -20,19 +20,41 @@ __device__ __forceinline__ u32 op_iadd3(u32 a, u32 m, u32 c) {
   asm volatile("{ .reg .u32 t; add.u32 t, %1, %2; add.u32 %0, t, %3; }" : "=r"(d) : "r"(a), "r"(m), "r"(c));
   return d;
 }
+__device__ __forceinline__ u32 op_imad_hi(u32 a, u32 m, u32 c) {
+  u32 d;
+  asm volatile("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(m), "r"(c));
+  return d;
+}
+// a 32 x 32 -> 64 multiply whose two halves are both consumed (by one LOP3 on the other pipe)
+__device__ __forceinline__ u32 op_imad_wide(u32 a, u32 m) {
+  u32 d;
+  asm volatile("{ .reg .u64 w; .reg .u32 lo, hi; mul.wide.u32 w, %1, %2; mov.b64 {lo, hi}, w; xor.b32 %0, lo, hi; }" : "=r"(d) : "r"(a), "r"(m));
+  return d;
+}
 // MODE 0: IMAD only (FMA pipe); MODE 1: LOP3 only (ALU pipe); MODE 2: IMAD + LOP3 alternating (both pipes)
+// MODE 3: IMAD.WIDE.U32 (+ one LOP3 on the other pipe); MODE 4: IMAD.HI.U32; MODE 5: Montgomery products (field.cuh: IMAD.WIDE +
+// IMAD + IMAD.HI each); MODE 6: the NTT butterfly mix -- one Montgomery product, one lazy add, one range reduction
 template <int MODE>
 __global__ void __launch_bounds__(256) k_int_peak(u32 *out, u32 seed, int iters) {
   u32 a[8];
 #pragma unroll
   for (int k = 0; k < 8; k++) a[k] = seed + threadIdx.x * 8 + k;
   const u32 m = seed | 1u, c = seed ^ 0x9e3779b9u;
+  const u32 tw = (seed * 2654435761u) % ff::P;   // a canonical twiddle for the Montgomery modes
   for (int i = 0; i < iters; i++) {
 #pragma unroll
     for (int u = 0; u < 8; u++) {
 #pragma unroll
       for (int k = 0; k < 8; k++) {
-        if (MODE == 0) {
+        if (MODE == 3) {
+          a[k] = op_imad_wide(a[k], m);
+        } else if (MODE == 4) {
+          a[k] = op_imad_hi(a[k], m, c);
+        } else if (MODE == 5) {
+          a[k] = ff::mont_mul(a[k], tw);
+        } else if (MODE == 6) {
+          a[k] = ff::red2p(a[(k + 1) & 7] + ff::mont_mul(a[k], tw));
+        } else if (MODE == 0) {
           a[k] = op_imad(a[k], m, c);
         } else if (MODE == 1) {
           a[k] = op_lop3(a[k], m, c);
@@ -80,6 +102,20 @@ extern "C" int stark_bench_int_peak(stark_ctx *ctx, double *imad_per_s, double *
   int rc = run_mode<0>(ctx, d_out, 1.0, imad_per_s);
   if (rc == STARK_OK) rc = run_mode<1>(ctx, d_out, 1.0, alu_per_s);
   if (rc == STARK_OK) rc = run_mode<2>(ctx, d_out, 2.0, mixed_per_s);
+  dev_free(ctx, d_out);
+  return rc;
+}
+
+// rates of the multiply forms a Montgomery product is made of (thread-operations per second): out[0] IMAD.WIDE.U32 (each with one LOP3 beside it),
+// out[1] IMAD.HI.U32, out[2] Montgomery products, out[3] butterfly steps (product + add + reduction)
+extern "C" int stark_bench_mul_peak(stark_ctx *ctx, double *out) {
+  if (!ctx || !out) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+  u32 *d_out = nullptr;
+  ST_TRY(dev_alloc(ctx, (void **)&d_out, 16));
+  int rc = run_mode<3>(ctx, d_out, 1.0, out + 0);
+  if (rc == STARK_OK) rc = run_mode<4>(ctx, d_out, 1.0, out + 1);
+  if (rc == STARK_OK) rc = run_mode<5>(ctx, d_out, 1.0, out + 2);
+  if (rc == STARK_OK) rc = run_mode<6>(ctx, d_out, 1.0, out + 3);
   dev_free(ctx, d_out);
   return rc;
 }

@@ -37,6 +37,13 @@ __global__ void k_sub_tables(u32 *tw, RootTables T, int inverse) {
   if (inverse) idx = ((1u << 23) - idx) & ((1u << 23) - 1u);
   tw[i] = root_pow(T, idx);
 }
+// Shoup form of a Montgomery-form table: out[i] = (w, floor(w 2^32 / p)), w = in[i] / R
+__global__ void k_shoup_table(const u32 *in, wpair *out, u32 n) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u32 w = ff::from_mont(in[i]);
+  out[i] = wpair{w, ff::shoup_of(w)};
+}
 // lo[i] = c * g^i (i < 4096), hi[j] = g^(4096 j) (j < hi_len); Montgomery form
 __global__ void k_geo_tables(u32 *lo, u32 *hi, u32 g_m, u32 c_m, u32 hi_len) {
   u32 i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -49,6 +56,8 @@ int ntt_init(stark_ctx *ctx) {
   CU_TRY(ctx, cudaMalloc(&ctx->root_hi, 2048 * 4));
   CU_TRY(ctx, cudaMalloc(&ctx->tw_sub[0], 8192 * 4));
   CU_TRY(ctx, cudaMalloc(&ctx->tw_sub[1], 8192 * 4));
+  CU_TRY(ctx, cudaMalloc(&ctx->tw_sh[0], 8192 * sizeof(wpair)));
+  CU_TRY(ctx, cudaMalloc(&ctx->tw_sh[1], 8192 * sizeof(wpair)));
   const u32 w23 = ff::pow(ff::GEN, (ff::P - 1) >> 23);  // ff.rs:215-223
   k_root_tables<<<16, 256, 0, ctx->stream>>>(ctx->root_lo, ctx->root_hi, ff::to_mont(w23));
   KERNEL_CHECK(ctx);
@@ -56,17 +65,40 @@ int ntt_init(stark_ctx *ctx) {
   for (int d = 0; d < 2; d++) {
     k_sub_tables<<<32, 256, 0, ctx->stream>>>(ctx->tw_sub[d], T, d);
     KERNEL_CHECK(ctx);
+    k_shoup_table<<<32, 256, 0, ctx->stream>>>(ctx->tw_sub[d], ctx->tw_sh[d], 8192);
+    KERNEL_CHECK(ctx);
     u32 w8 = ff::pow(ff::GEN, (ff::P - 1) >> 3);
     if (d) w8 = ff::inv(w8);
     ctx->w8[d][0] = ff::R1;
     for (int k = 1; k < 4; k++) ctx->w8[d][k] = ff::to_mont(ff::pow(w8, k));
+    for (int k = 0; k < 4; k++) ctx->w8_sh[d][k] = wpair{ff::pow(w8, k), ff::shoup_of(ff::pow(w8, k))};
   }
   for (int i = 0; i < 8; i++) ctx->geo[i] = GeoCacheEntry{0, 0, nullptr, nullptr, 0, 0};
   ctx->geo_stamp = 0;
+  const char *e = getenv("STARK_NTT_STREAMS");
+  ctx->ntt_streams = e ? atoi(e) : 2;
+  if (ctx->ntt_streams < 1 || ctx->ntt_streams > 4) ctx->ntt_streams = 2;
+  e = getenv("STARK_NTT_GROUP_MB");
+  ctx->ntt_group_mb = e ? atoi(e) : 16;
+  if (ctx->ntt_group_mb < 1) ctx->ntt_group_mb = 16;
+  ctx->n_side = 0;
+  return STARK_OK;
+}
+// lazily created side streams + events
+static int side_streams(stark_ctx *ctx, int n) {
+  if (!ctx->fork_ev) CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+  while (ctx->n_side < n) {
+    CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->side[ctx->n_side], cudaStreamNonBlocking));
+    CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->side_done[ctx->n_side], cudaEventDisableTiming));
+    ctx->n_side++;
+  }
   return STARK_OK;
 }
 void ntt_destroy(stark_ctx *ctx) {
+  for (int i = 0; i < ctx->n_side; i++) cudaStreamDestroy(ctx->side[i]), cudaEventDestroy(ctx->side_done[i]);
+  if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
   cudaFree(ctx->root_lo), cudaFree(ctx->root_hi), cudaFree(ctx->tw_sub[0]), cudaFree(ctx->tw_sub[1]);
+  cudaFree(ctx->tw_sh[0]), cudaFree(ctx->tw_sh[1]);
   for (int i = 0; i < 8; i++) cudaFree(ctx->geo[i].lo);
 }
 
@@ -272,26 +304,57 @@ int ntt_transform(stark_ctx *ctx, const u32 *in, u32 *out, int log_n, bool inver
   // FIRST and MIDDLE passes are out of place, the LAST pass may run in place:
   //   2 passes: in -> out -> out           (in == out: in -> tmp -> out)
   //   3 passes: in -> tmp -> out -> out
-  // The whole batch goes through each pass in one launch.  (Processing it in L2-sized groups, all passes of a group
-  // back to back so that intermediates never reach HBM, was measured SLOWER for 16 x 2^22 -- 468 vs 406 us: a launch of
-  // two transforms is only 1.7 waves of CTAs and the launch tails cost more than the DRAM traffic saved.  The loop is
-  // kept so the group size can be revisited.)
-  const u32 group = batch;
+  // A batch that fits in L2 goes through each pass in one launch.  A batch much larger than L2 is cut into column
+  // GROUPS of ~16 MB whose passes run back to back, so a group's intermediates are still in the 126 MB L2 when the
+  // next pass reads them (HBM traffic ~8N per transform instead of 8N per pass); one group alone is less than a wave
+  // of CTAs and its launch tails would cost more than the traffic saved (measured: 468 vs 406 us for 16 x 2^22), so
+  // ctx->ntt_streams groups are in flight on side streams, forked from / joined to the context's stream by events.
   const u32 batch_total = batch;
   const u32 *in_all = in;
   u32 *out_all = out;
   const u64 in_batch_all = in_batch;
-  u32 *tmp = nullptr;
   const bool need_tmp = n_pass == 3 || in == out;
-  if (need_tmp) ST_TRY(dev_alloc(ctx, (void **)&tmp, (size_t)std::min(batch_total, group) * N * 4));
+  u32 group = batch;
+  int n_streams = 1;
+  if (ctx->ntt_streams > 1 && (u64)batch * N * 4 >= (48ull << 20)) {
+    const u64 per_group = ((u64)ctx->ntt_group_mb << 20) / (N * 4);
+    group = (u32)(per_group ? per_group : 1);
+    n_streams = ctx->ntt_streams;
+    if ((batch + group - 1) / group < 2u * n_streams) group = batch, n_streams = 1;   // too few groups to pipeline
+  }
+  u32 *tmp_all = nullptr;
+  if (need_tmp) ST_TRY(dev_alloc(ctx, (void **)&tmp_all, (size_t)std::min(batch_total, group) * N * 4 * n_streams));
+  cudaStream_t main_stream = ctx->stream;
+  struct RestoreStream {   // the launch macros return on a failed launch: never leave a side stream in the context
+    stark_ctx *c;
+    cudaStream_t s;
+    ~RestoreStream() { c->stream = s; }
+  } restore_stream{ctx, main_stream};
+  if (n_streams > 1) {
+    int src_ = side_streams(ctx, n_streams);
+    if (src_ != STARK_OK) {
+      dev_free(ctx, tmp_all);
+      return src_;
+    }
+    cudaEventRecord(ctx->fork_ev, main_stream);
+    for (int i = 0; i < n_streams; i++) cudaStreamWaitEvent(ctx->side[i], ctx->fork_ev, 0);
+  }
   ntt2::PassParams B;
   memset(&B, 0, sizeof B);
   B.logN = log_n, B.log_tiles = log_n - ntt2::TILE_LOG;
-  B.roots = roots, B.inverse = d;
-  for (int k = 0; k < 4; k++) B.w8[k] = ctx->w8[d][k];
+  B.roots = roots, B.inverse = d, B.zero = 0;
+  for (int k = 0; k < 4; k++) B.w8[k] = ctx->w8_sh[d][k];
+  const u32 post_plain = ff::from_mont(post_c);
+  const wpair post_sh = {post_plain, ff::shoup_of(post_plain)};
   int rc = STARK_OK;
-  for (u32 b0 = 0; b0 < batch_total && rc == STARK_OK; b0 += group) {
+  u32 gi = 0;
+  for (u32 b0 = 0; b0 < batch_total && rc == STARK_OK; b0 += group, gi++) {
   batch = std::min(group, batch_total - b0);
+  u32 *tmp = tmp_all;
+  if (n_streams > 1) {
+    ctx->stream = ctx->side[gi % n_streams];   // the LAUNCH macros launch on ctx->stream
+    if (tmp_all) tmp = tmp_all + (size_t)(gi % n_streams) * group * N;
+  }
   in = in_all + (u64)b0 * in_batch_all, out = out_all + (u64)b0 * out_batch, in_batch = in_batch_all;
   const u32 grid = batch << B.log_tiles;
   const u32 *src = in;
@@ -309,10 +372,10 @@ int ntt_transform(stark_ctx *ctx, const u32 *in, u32 *out, int log_n, bool inver
     B.in = src, B.out = dst, B.in_batch = src_batch, B.out_batch = dst_batch;
     B.n_valid = kind == ntt2::FIRST ? n_valid : N;
     B.logS = logS;
-    B.tw_in = ctx->tw_sub[d] + (1u << r);
+    B.tw_in = ctx->tw_sh[d] + (1u << r);
     if (kind == ntt2::FIRST) ntt2::fill_first_pass_constants(B, r);
     B.pre_mode = kind == ntt2::FIRST ? pre_mode : (int)SCALE_NONE, B.pre_geo = pre_geo;
-    B.post_mode = kind == ntt2::LAST ? post_mode : (int)SCALE_NONE, B.post_const = post_c, B.post_geo = post_geo;
+    B.post_mode = kind == ntt2::LAST ? post_mode : (int)SCALE_NONE, B.post_const = post_sh, B.post_geo = post_geo;
     const u64 bytes = kind == ntt2::FIRST ? 4ull * batch * (n_valid + N) : 8ull * batch * N;
     const char *tag = kind == ntt2::FIRST ? "ntt_pass1" : (kind == ntt2::LAST ? "ntt_pass_last" : "ntt_pass_mid");
     // compile-time specialisation of the per-element options (see round_compute)
@@ -341,6 +404,13 @@ int ntt_transform(stark_ctx *ctx, const u32 *in, u32 *out, int log_n, bool inver
     logS += r;
   }
   }
-  dev_free(ctx, tmp);
+  if (n_streams > 1) {
+    ctx->stream = main_stream;
+    for (int i = 0; i < n_streams; i++) {
+      cudaEventRecord(ctx->side_done[i], ctx->side[i]);
+      cudaStreamWaitEvent(main_stream, ctx->side_done[i], 0);
+    }
+  }
+  dev_free(ctx, tmp_all);
   return rc;
 }

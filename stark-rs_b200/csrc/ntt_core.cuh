@@ -27,6 +27,11 @@ struct alignas(16) q4 {
   u32 x, y, z, w;
 };
 
+// a constant multiplier in Shoup form (field.cuh shoup_mul): w plain, s = floor(w * 2^32 / p)
+struct alignas(8) wpair {
+  u32 w, s;
+};
+
 // w23^e tables (Montgomery form): lo[i] = w23^i (i < 4096), hi[j] = w23^(4096 j) (j < 2048),
 // w23 = 3^((p-1)/2^23)  (ff.rs:215-223 prim_nth_root).
 struct RootTables {

@@ -29,10 +29,16 @@ using ff::u64;
 using ntt::GeoTables;
 using ntt::q4;
 using ntt::RootTables;
+using ntt::wpair;
 
 enum Kind { FIRST = 0, MIDDLE = 1, LAST = 2 };
 constexpr int TILE_LOG = 12;   // elements per tile
 constexpr int NT = 128;        // threads per CTA
+#ifndef NTT2_PIN_LAST
+#define NTT2_PIN_LAST 5
+#define NTT2_PIN_OTHER 7
+#endif
+constexpr int PIN_LAST = NTT2_PIN_LAST, PIN_OTHER = NTT2_PIN_OTHER;   // dif_lazy: stages whose sums go to the ALU pipe
 
 struct PassParams {
   const u32 *in;
@@ -42,15 +48,16 @@ struct PassParams {
   int logN;                  // transform length
   int logS;                  // s = product of the previous passes' radices
   int log_tiles;             // tiles per transform = 2^(logN - 13)
-  const u32 *tw_in;          // tw_in[e] = w_R^(+-e), e < R, Montgomery form, canonical
-  u32 w8[4];                 // 1, w_8, w_8^2, w_8^3 in the pass direction (Montgomery form)
+  const wpair *tw_in;        // tw_in[e] = w_R^(+-e), e < R, Shoup form (plain value + companion)
+  wpair w8[4];               // 1, w_8, w_8^2, w_8^3 in the pass direction, Shoup form
   RootTables roots;          // w_{2^23}^e two-level table
   int inverse;
   int pre_mode;              // FIRST: ntt::ScaleMode on loaded elements (index = coefficient index)
   GeoTables pre_geo;
   int post_mode;             // LAST: ntt::ScaleMode on stored elements (index = output index)
-  u32 post_const;            // Montgomery form
+  wpair post_const;          // Shoup form
   GeoTables post_geo;
+  u32 zero;                  // 0, known only at run time (ff::add_alu)
   u32 dpow[8];               // FIRST: w_N^(+-(R/8) k), k < 8, Montgomery form (see round_compute)
 };
 
@@ -100,24 +107,29 @@ FF_HD u32 slot(u32 l, u32 c4) {
 
 // radix-2^LR DIF on a[0 .. 2^LR) in [0, 2p); a[pos] ends up holding output bitrev(pos).  The outputs are LAZY, in
 // [0, 4p): the caller either multiplies them by a canonical twiddle (-> [0, 2p)) or reduces them.
-template <int LR>
-FF_HD void dif_lazy(u32 *a, const u32 *w8) {
+// PIN: bit i set = the sums of stage i (0 = the first, widest stage) are pinned to the ALU pipe (ff::add_alu); the
+// differences are three-input IADD3 anyway.  Chosen per pass kind from the SASS pipe counts (tools/sass_hist.py).
+template <int LR, int PIN>
+FF_HD void dif_lazy(u32 *a, const wpair *w8, u32 zero) {
   constexpr int R = 1 << LR;
 #pragma unroll
-  for (int len = R; len >= 2; len >>= 1) {
+  int stage = 0;
+#pragma unroll
+  for (int len = R; len >= 2; len >>= 1, stage++) {
     const int h = len >> 1;
     const bool final_stage = len == 2;
+    const bool pin = (PIN >> stage) & 1;
 #pragma unroll
     for (int blk = 0; blk < R; blk += len) {
 #pragma unroll
       for (int j = 0; j < h; j++) {
         const u32 u = a[blk + j], v = a[blk + j + h];
-        const u32 s = u + v, d = u + ff::P2 - v;
+        const u32 s = pin ? ff::add_alu(u, v, zero) : u + v, d = u + ff::P2 - v;
         if (final_stage) {
           a[blk + j] = s, a[blk + j + h] = d;
         } else {
           a[blk + j] = ff::red2p(s);
-          a[blk + j + h] = (j == 0) ? ff::red2p(d) : ff::mont_mul(d, w8[j * (8 / len)]);
+          a[blk + j + h] = (j == 0) ? ff::red2p(d) : ff::shoup_mul(d, w8[j * (8 / len)].w, w8[j * (8 / len)].s);
         }
       }
     }
@@ -225,11 +237,14 @@ FF_HD void round_compute(u32 tid, const PassParams &A, const TileCtx &T, const q
       a[0][j] = v.x, a[1][j] = v.y, a[2][j] = v.z, a[3][j] = v.w;
     }
     // inner twiddles w_R^(s' p' k), shared by the four columns (the last round has p' = 0: none)
-    u32 tw[RAD], step[RAD];
+    u32 tw[RAD], step[RAD];   // !LASTR: tw = plain twiddle, step = its Shoup companion
     if (!LASTR) {
       const u32 pp = up >> LOGS;
 #pragma unroll
-      for (int k = 1; k < RAD; k++) tw[k] = A.tw_in[(pp * (u32)k) << LOGS];
+      for (int k = 1; k < RAD; k++) {
+        const wpair t = A.tw_in[(pp * (u32)k) << LOGS];
+        tw[k] = t.w, step[k] = t.s;
+      }
     } else if (KIND == FIRST) {
       // outer ("four-step") twiddle of element (column cb + x, row up + S' k), S' = R/8:
       //   w^((cb + x)(up + S' k)) = [w^(cb up) (w^(cb S'))^k] * [w^up (w^S')^k]^x
@@ -245,13 +260,13 @@ FF_HD void round_compute(u32 tid, const PassParams &A, const TileCtx &T, const q
     }
 #pragma unroll
     for (int x = 0; x < 4; x++) {
-      dif_lazy<LR>(a[x], A.w8);
+      dif_lazy<LR, (KIND == LAST ? PIN_LAST : PIN_OTHER)>(a[x], A.w8, A.zero);
 #pragma unroll
       for (int pos = 0; pos < RAD; pos++) {
         const int k = bitrev<LR>(pos);
         u32 val = a[x][pos];
         if (!LASTR) {
-          val = k ? ff::mont_mul(val, tw[k]) : ff::red2p(val);
+          val = k ? ff::shoup_mul(val, tw[k], step[k]) : ff::red2p(val);
         } else {
           const u32 row = up + ((u32)k << LOGS);   // output row of the R-point DFT (p' = 0, q' = u')
           if (KIND == FIRST) {
@@ -261,7 +276,7 @@ FF_HD void round_compute(u32 tid, const PassParams &A, const TileCtx &T, const q
             val = ff::mont_mul(val, otw[row]);
           } else {
             if (MODE == ntt::SCALE_CONST) {
-              val = ff::canon(ff::mont_mul(val, A.post_const));
+              val = ff::canon(ff::shoup_mul(val, A.post_const.w, A.post_const.s));
             } else if (MODE == ntt::SCALE_GEO) {
               const u64 oidx = (u64)T.col0 + 4u * c4 + (u32)x + ((u64)row << A.logS);
               val = ff::canon(ff::mont_mul(val, ntt::geo_pow(A.post_geo, oidx)));

@@ -65,6 +65,7 @@ extern "C" {
     pub fn stark_fri_fold_bcast_dev(ctx: *mut StarkCtx, codeword: *const StarkBuf, n: usize, alpha_raw: u64, offset: u64, omega: u64, i0: usize, count: usize, peers: *const *mut std::ffi::c_void, n_peers: i32, multicast: *mut std::ffi::c_void) -> i32;
     pub fn stark_fiat_shamir_challenge(transcript: *const u8, len: usize, challenge_raw: *mut u64) -> i32;
     pub fn stark_hash_from_u64(value: u64, out: *mut u8) -> i32;
+    pub fn stark_bench_mul_peak(ctx: *mut StarkCtx, out4: *mut f64) -> i32;
     pub fn stark_bench_hash_latency(ctx: *mut StarkCtx, hs_cycles: *mut f64, hs2_cycles: *mut f64, hsq_cycles: *mut f64) -> i32;
     pub fn stark_fri_verify(ctx: *mut StarkCtx, proof: *const u8, proof_len: usize, domain_length: usize, offset: u64, omega: u64, expansion_factor: u32, num_colinearity_tests: u32, transcript: *const u8, transcript_len: usize, ok: *mut i32, reason: *mut u32, roots_out: *mut u8, top_indices: *mut u64, poly_indices: *mut u64, poly_values: *mut u64) -> i32;
     pub fn stark_fri_verify_reason(reason: u32) -> *const std::os::raw::c_char;

@@ -10,25 +10,26 @@
 #include "ntt_pass.cuh"
 using namespace ntt2;
 
-static std::vector<u32> g_lo(4096), g_hi(2048), g_tw[2];
-static u32 g_w8[2][4];
+static std::vector<u32> g_lo(4096), g_hi(2048);
+static std::vector<wpair> g_tw[2];
+static wpair g_w8[2][4];
 static void init() {
   u32 w23 = ff::to_mont(ff::pow(3, (ff::P - 1) >> 23));
   for (u32 i = 0; i < 4096; i++) g_lo[i] = ff::mont_pow(w23, i);
   for (u32 i = 0; i < 2048; i++) g_hi[i] = ff::mont_pow(w23, (u64)i << 12);
   RootTables T = {g_lo.data(), g_hi.data()};
   for (int d = 0; d < 2; d++) {
-    g_tw[d].assign(8192, ff::R1);
+    g_tw[d].assign(8192, wpair{1, ff::shoup_of(1)});
     for (u32 i = 1; i < 8192; i++) {
       int logL = 31 - __builtin_clz(i);
       u32 e = i - (1u << logL), idx = e << (23 - logL);
       if (d) idx = ((1u << 23) - idx) & ((1u << 23) - 1u);
-      g_tw[d][i] = ntt::root_pow(T, idx);
+      const u32 w = ff::from_mont(ntt::root_pow(T, idx));
+      g_tw[d][i] = wpair{w, ff::shoup_of(w)};
     }
     u32 w8 = ff::pow(3, (ff::P - 1) >> 3);
     if (d) w8 = ff::inv(w8);
-    g_w8[d][0] = ff::R1;
-    for (int k = 1; k < 4; k++) g_w8[d][k] = ff::to_mont(ff::pow(w8, k));
+    for (int k = 0; k < 4; k++) g_w8[d][k] = wpair{ff::pow(w8, k), ff::shoup_of(ff::pow(w8, k))};
   }
 }
 
@@ -80,7 +81,7 @@ static void transform(const u32 *in, u32 *out, int log_n, int d, u32 batch, u64 
     B.tw_in = g_tw[d].data() + (1u << r);
     if (kind == FIRST) fill_first_pass_constants(B, r);
     B.pre_mode = kind == FIRST ? pre_mode : 0, B.pre_geo = pre_geo;
-    B.post_mode = kind == LAST ? post_mode : 0, B.post_const = post_c, B.post_geo = post_geo;
+    B.post_mode = kind == LAST ? post_mode : 0, B.post_const = wpair{ff::from_mont(post_c), ff::shoup_of(ff::from_mont(post_c))}, B.post_geo = post_geo;
     const int mode = kind == FIRST ? ((B.n_valid < N ? 1 : 0) | (B.pre_mode == ntt::SCALE_GEO ? 2 : 0)) : (kind == LAST ? B.post_mode : 0);
 #define CASE(R_, K_) if (r == R_ && kind == K_) { if (K_ == MIDDLE || mode == 0) run_pass<R_, K_, 0>(B, grid); else if (mode == 1) run_pass<R_, K_, 1>(B, grid); else if (K_ == FIRST) run_pass<R_, K_, 3>(B, grid); else run_pass<R_, K_, 2>(B, grid); } else
     CASE(6, FIRST) CASE(7, FIRST) CASE(8, FIRST) CASE(6, MIDDLE) CASE(7, MIDDLE) CASE(8, MIDDLE)
