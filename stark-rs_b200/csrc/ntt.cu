@@ -44,6 +44,15 @@ __global__ void k_shoup_table(const u32 *in, wpair *out, u32 n) {
   const u32 w = ff::from_mont(in[i]);
   out[i] = wpair{w, ff::shoup_of(w)};
 }
+// out[i] = w23^(+-(e(i))) in Shoup form: otw table e = i << 8 (i < 2^15); row table i = (logN - 13) * 256 + row, e = row << (23 - logN)
+__global__ void k_shoup_roots(wpair *out, RootTables T, int inverse, int row_table, u32 n) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u32 idx = row_table ? (i & 255u) << (10 - (i >> 8)) : i << 8;
+  if (inverse) idx = ((1u << 23) - idx) & ((1u << 23) - 1u);
+  const u32 w = ff::from_mont(root_pow(T, idx));
+  out[i] = wpair{w, ff::shoup_of(w)};
+}
 // lo[i] = c * g^i (i < 4096), hi[j] = g^(4096 j) (j < hi_len); Montgomery form
 __global__ void k_geo_tables(u32 *lo, u32 *hi, u32 g_m, u32 c_m, u32 hi_len) {
   u32 i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -66,6 +75,12 @@ int ntt_init(stark_ctx *ctx) {
     k_sub_tables<<<32, 256, 0, ctx->stream>>>(ctx->tw_sub[d], T, d);
     KERNEL_CHECK(ctx);
     k_shoup_table<<<32, 256, 0, ctx->stream>>>(ctx->tw_sub[d], ctx->tw_sh[d], 8192);
+    KERNEL_CHECK(ctx);
+    CU_TRY(ctx, cudaMalloc(&ctx->otw_sh[d], (1u << 15) * sizeof(wpair)));
+    CU_TRY(ctx, cudaMalloc(&ctx->row_sh[d], 11 * 256 * sizeof(wpair)));
+    k_shoup_roots<<<(1u << 15) / 256, 256, 0, ctx->stream>>>(ctx->otw_sh[d], T, d, 0, 1u << 15);
+    KERNEL_CHECK(ctx);
+    k_shoup_roots<<<11, 256, 0, ctx->stream>>>(ctx->row_sh[d], T, d, 1, 11 * 256);
     KERNEL_CHECK(ctx);
     u32 w8 = ff::pow(ff::GEN, (ff::P - 1) >> 3);
     if (d) w8 = ff::inv(w8);
@@ -99,6 +114,7 @@ void ntt_destroy(stark_ctx *ctx) {
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
   cudaFree(ctx->root_lo), cudaFree(ctx->root_hi), cudaFree(ctx->tw_sub[0]), cudaFree(ctx->tw_sub[1]);
   cudaFree(ctx->tw_sh[0]), cudaFree(ctx->tw_sh[1]);
+  cudaFree(ctx->otw_sh[0]), cudaFree(ctx->otw_sh[1]), cudaFree(ctx->row_sh[0]), cudaFree(ctx->row_sh[1]);
   for (int i = 0; i < 8; i++) cudaFree(ctx->geo[i].lo);
 }
 
@@ -210,7 +226,7 @@ __global__ void __launch_bounds__(ntt2::NT, 8) k_ntt2_pass(const __grid_constant
   using namespace ntt2;
   typedef Plan<LOGR> PL;
   __shared__ __align__(16) q4 tile[1 << (TILE_LOG - 2)];
-  __shared__ u32 otw[KIND == MIDDLE ? (1 << LOGR) : 1];
+  __shared__ wpair otw[KIND == MIDDLE ? (1 << LOGR) : 1];
   pdl_entry();
   const u32 tid = threadIdx.x;
   const TileCtx T = tile_ctx<LOGR>(A, blockIdx.x);
@@ -373,6 +389,8 @@ int ntt_transform(stark_ctx *ctx, const u32 *in, u32 *out, int log_n, bool inver
     B.n_valid = kind == ntt2::FIRST ? n_valid : N;
     B.logS = logS;
     B.tw_in = ctx->tw_sh[d] + (1u << r);
+    B.otw_tab = ctx->otw_sh[d], B.otw_shift = 15 - (log_n - logS);
+    B.row_tab = ctx->row_sh[d] + (log_n - 13) * 256;
     if (kind == ntt2::FIRST) ntt2::fill_first_pass_constants(B, r);
     B.pre_mode = kind == ntt2::FIRST ? pre_mode : (int)SCALE_NONE, B.pre_geo = pre_geo;
     B.post_mode = kind == ntt2::LAST ? post_mode : (int)SCALE_NONE, B.post_const = post_sh, B.post_geo = post_geo;

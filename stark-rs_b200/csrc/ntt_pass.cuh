@@ -58,6 +58,9 @@ struct PassParams {
   wpair post_const;          // Shoup form
   GeoTables post_geo;
   u32 zero;                  // 0, known only at run time (ff::add_alu)
+  const wpair *otw_tab;      // MIDDLE: w_{2^15}^(+-e), e < 2^15, Shoup form; w_N^(s e) = otw_tab[e << otw_shift]
+  int otw_shift;             //         15 - (logN - logS)
+  const wpair *row_tab;      // FIRST: w_N^(+-row), row < 256, Shoup form
   u32 dpow[8];               // FIRST: w_N^(+-(R/8) k), k < 8, Montgomery form (see round_compute)
 };
 
@@ -169,10 +172,11 @@ FF_HD u32 root_n(const PassParams &A, u32 e) {
   return ntt::root_pow(A.roots, e23);
 }
 
-// MIDDLE: otw[k] = w_N^(+-(s p k)), k < R  (per-tile table in shared memory; s p k < N)
+// MIDDLE: otw[k] = w_N^(+-(s p k)) = w_{N/s}^(+-(p k)), k < R, in Shoup form (per-tile table in shared memory).
+// N/s <= 2^15 for every plan (the first radix is >= 2^(logN - 15)), so the pairs come straight from one table.
 template <int LOGR>
-FF_HD void fill_outer_table(u32 tid, const PassParams &A, const TileCtx &T, u32 *otw) {
-  for (u32 k = tid; k < (1u << LOGR); k += NT) otw[k] = root_n(A, (T.p * k) << A.logS);
+FF_HD void fill_outer_table(u32 tid, const PassParams &A, const TileCtx &T, wpair *otw) {
+  for (u32 k = tid; k < (1u << LOGR); k += NT) otw[k] = A.otw_tab[(T.p * k) << A.otw_shift];
 }
 
 // task -> (row group u', column quad c4).  Column-fastest: adjacent lanes touch adjacent 16-byte slots of one row.
@@ -197,7 +201,7 @@ FF_HD void decode(u32 t, u32 &up, u32 &c4) {
 //   FIRST:  bit 0 = some inputs are zero padding (n_valid < N), bit 1 = geometric pre-scale
 //   LAST:   the ntt::ScaleMode of the post-scale
 template <int LOGR, int KIND, int ROUND, int MODE>
-FF_HD void round_compute(u32 tid, const PassParams &A, const TileCtx &T, const q4 *smem, const u32 *otw, u32 *regs) {
+FF_HD void round_compute(u32 tid, const PassParams &A, const TileCtx &T, const q4 *smem, const wpair *otw, u32 *regs) {
   typedef Plan<LOGR> PL;
   constexpr int LR = PL::lr(ROUND), LOGS = PL::logs(ROUND), RAD = 1 << LR, NTASK = 8 >> LR;
   constexpr int LOGC4 = TILE_LOG - LOGR - 2;
@@ -225,7 +229,7 @@ FF_HD void round_compute(u32 tid, const PassParams &A, const TileCtx &T, const q
           v.z = cidx + 2 < A.n_valid ? T.in[cidx + 2] : 0u;
           v.w = 0u;
         }
-        if (KIND == FIRST && (MODE & 2)) {
+        if (KIND == FIRST && (MODE & 2) && (!(MODE & 1) || cidx < A.n_valid)) {   // zero padding needs no scaling
           v.x = ff::mont_mul(v.x, ntt::geo_pow(A.pre_geo, cidx + 0));
           v.y = ff::mont_mul(v.y, ntt::geo_pow(A.pre_geo, cidx + 1));
           v.z = ff::mont_mul(v.z, ntt::geo_pow(A.pre_geo, cidx + 2));
@@ -245,18 +249,29 @@ FF_HD void round_compute(u32 tid, const PassParams &A, const TileCtx &T, const q
         const wpair t = A.tw_in[(pp * (u32)k) << LOGS];
         tw[k] = t.w, step[k] = t.s;
       }
-    } else if (KIND == FIRST) {
-      // outer ("four-step") twiddle of element (column cb + x, row up + S' k), S' = R/8:
-      //   w^((cb + x)(up + S' k)) = [w^(cb up) (w^(cb S'))^k] * [w^up (w^S')^k]^x
-      // three table look-ups per thread, then geometric steps: tw[k] walks along x with ratio step[k].
-      const u32 cb = T.col0 + 4u * c4;
-      const u32 wa = root_n(A, cb * up), wc = root_n(A, cb << LOGS), wb = root_n(A, up);
-      tw[0] = wa, step[0] = wb;
+    }
+    if (LASTR && KIND == FIRST) {
+      // The R-point DFTs of the four columns, then the outer ("four-step") twiddle of element (column cb + x, row_k =
+      // up + S' k), S' = R/8:   w^((cb + x) row_k) = [w^(cb up) (w^(cb S'))^k] * (w^row_k)^x.
+      // The bracket walks along k with a run-time ratio (Montgomery products); along x the ratio w^row_k comes from a
+      // 256-entry table in Shoup form, so the walk t <- t * w^row_k is a Shoup product (4 FMA-pipe slots, not 5).
 #pragma unroll
-      for (int k = 1; k < RAD; k++) {
-        tw[k] = ff::canon(ff::mont_mul(tw[k - 1], wc));
-        step[k] = ff::canon(ff::mont_mul(wb, A.dpow[k]));
+      for (int x = 0; x < 4; x++) dif_lazy<LR, PIN_OTHER>(a[x], A.w8, A.zero);
+      const u32 cb = T.col0 + 4u * c4;
+      const u32 wc = root_n(A, cb << LOGS);
+      u32 base = root_n(A, cb * up);   // Montgomery form
+#pragma unroll
+      for (int k = 0; k < RAD; k++) {
+        const wpair st = A.row_tab[up + ((u32)k << LOGS)];
+        u32 t = base;
+#pragma unroll
+        for (int x = 0; x < 4; x++) {
+          regs[(i * 4 + x) * RAD + k] = ff::mont_mul(a[x][bitrev<LR>(k)], t);
+          if (x < 3) t = ff::canon(ff::shoup_mul(t, st.w, st.s));
+        }
+        if (k + 1 < RAD) base = ff::canon(ff::mont_mul(base, wc));
       }
+      continue;
     }
 #pragma unroll
     for (int x = 0; x < 4; x++) {
@@ -269,11 +284,9 @@ FF_HD void round_compute(u32 tid, const PassParams &A, const TileCtx &T, const q
           val = k ? ff::shoup_mul(val, tw[k], step[k]) : ff::red2p(val);
         } else {
           const u32 row = up + ((u32)k << LOGS);   // output row of the R-point DFT (p' = 0, q' = u')
-          if (KIND == FIRST) {
-            val = ff::mont_mul(val, tw[k]);
-            if (x < 3) tw[k] = ff::canon(ff::mont_mul(tw[k], step[k]));
-          } else if (KIND == MIDDLE) {
-            val = ff::mont_mul(val, otw[row]);
+          if (KIND == MIDDLE) {
+            const wpair o = otw[row];
+            val = ff::shoup_mul(val, o.w, o.s);
           } else {
             if (MODE == ntt::SCALE_CONST) {
               val = ff::canon(ff::shoup_mul(val, A.post_const.w, A.post_const.s));

@@ -13,6 +13,7 @@ using namespace ntt2;
 static std::vector<u32> g_lo(4096), g_hi(2048);
 static std::vector<wpair> g_tw[2];
 static wpair g_w8[2][4];
+static std::vector<wpair> g_otw[2], g_row[2];
 static void init() {
   u32 w23 = ff::to_mont(ff::pow(3, (ff::P - 1) >> 23));
   for (u32 i = 0; i < 4096; i++) g_lo[i] = ff::mont_pow(w23, i);
@@ -27,6 +28,15 @@ static void init() {
       const u32 w = ff::from_mont(ntt::root_pow(T, idx));
       g_tw[d][i] = wpair{w, ff::shoup_of(w)};
     }
+    // mirrors k_shoup_roots in ntt.cu
+    g_otw[d].resize(1u << 15), g_row[d].resize(11 * 256);
+    for (int tab = 0; tab < 2; tab++)
+      for (u32 i = 0; i < (tab ? 11u * 256 : 1u << 15); i++) {
+        u32 idx = tab ? (i & 255u) << (10 - (i >> 8)) : i << 8;
+        if (d) idx = ((1u << 23) - idx) & ((1u << 23) - 1u);
+        const u32 w = ff::from_mont(ntt::root_pow(T, idx));
+        (tab ? g_row[d] : g_otw[d])[i] = wpair{w, ff::shoup_of(w)};
+      }
     u32 w8 = ff::pow(3, (ff::P - 1) >> 3);
     if (d) w8 = ff::inv(w8);
     for (int k = 0; k < 4; k++) g_w8[d][k] = wpair{ff::pow(w8, k), ff::shoup_of(ff::pow(w8, k))};
@@ -39,7 +49,8 @@ template <int LOGR, int KIND, int MODE>
 static void run_pass(const PassParams &A, u32 grid) {
   typedef Plan<LOGR> PL;
   std::vector<q4> tile(1 << (TILE_LOG - 2));
-  std::vector<u32> otw(1 << LOGR), regs((size_t)NT * 32);
+  std::vector<wpair> otw(1 << LOGR);
+  std::vector<u32> regs((size_t)NT * 32);
   for (u32 blk = 0; blk < grid; blk++) {
     const TileCtx T = tile_ctx<LOGR>(A, blk);
     if (KIND == MIDDLE) for (u32 tid = 0; tid < NT; tid++) fill_outer_table<LOGR>(tid, A, T, otw.data());
@@ -79,6 +90,8 @@ static void transform(const u32 *in, u32 *out, int log_n, int d, u32 batch, u64 
     B.n_valid = kind == FIRST ? n_valid : N;
     B.logS = logS;
     B.tw_in = g_tw[d].data() + (1u << r);
+    B.otw_tab = g_otw[d].data(), B.otw_shift = 15 - (log_n - logS);
+    B.row_tab = g_row[d].data() + (log_n - 13) * 256;
     if (kind == FIRST) fill_first_pass_constants(B, r);
     B.pre_mode = kind == FIRST ? pre_mode : 0, B.pre_geo = pre_geo;
     B.post_mode = kind == LAST ? post_mode : 0, B.post_const = wpair{ff::from_mont(post_c), ff::shoup_of(ff::from_mont(post_c))}, B.post_geo = post_geo;
