@@ -11,6 +11,7 @@
 //        pass 2: N2-point transforms over n2 at stride N1, in place, X[k2*N1 + k1] -- natural order.
 //   HBM traffic: 8N bytes per pass (4 read + 4 written), nothing else (twiddle tables are <= 48 KB, L1/L2).
 #include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 #include "ntt_pass.cuh"
@@ -76,6 +77,12 @@ int ntt_init(stark_ctx *ctx) {
     KERNEL_CHECK(ctx);
     k_shoup_table<<<32, 256, 0, ctx->stream>>>(ctx->tw_sub[d], ctx->tw_sh[d], 8192);
     KERNEL_CHECK(ctx);
+    {
+      std::vector<wpair> h(4 * 512);
+      ntt2::fill_inner_twiddles(h.data(), d);
+      CU_TRY(ctx, cudaMalloc(&ctx->tw_in_sh[d], h.size() * sizeof(wpair)));
+      CU_TRY(ctx, cudaMemcpy(ctx->tw_in_sh[d], h.data(), h.size() * sizeof(wpair), cudaMemcpyHostToDevice));
+    }
     CU_TRY(ctx, cudaMalloc(&ctx->otw_sh[d], (1u << 15) * sizeof(wpair)));
     CU_TRY(ctx, cudaMalloc(&ctx->row_sh[d], 11 * 256 * sizeof(wpair)));
     k_shoup_roots<<<(1u << 15) / 256, 256, 0, ctx->stream>>>(ctx->otw_sh[d], T, d, 0, 1u << 15);
@@ -114,6 +121,7 @@ void ntt_destroy(stark_ctx *ctx) {
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
   cudaFree(ctx->root_lo), cudaFree(ctx->root_hi), cudaFree(ctx->tw_sub[0]), cudaFree(ctx->tw_sub[1]);
   cudaFree(ctx->tw_sh[0]), cudaFree(ctx->tw_sh[1]);
+  cudaFree(ctx->tw_in_sh[0]), cudaFree(ctx->tw_in_sh[1]);
   cudaFree(ctx->otw_sh[0]), cudaFree(ctx->otw_sh[1]), cudaFree(ctx->row_sh[0]), cudaFree(ctx->row_sh[1]);
   for (int i = 0; i < 8; i++) cudaFree(ctx->geo[i].lo);
 }
@@ -362,6 +370,21 @@ int ntt_transform(stark_ctx *ctx, const u32 *in, u32 *out, int log_n, bool inver
   for (int k = 0; k < 4; k++) B.w8[k] = ctx->w8_sh[d][k];
   const u32 post_plain = ff::from_mont(post_c);
   const wpair post_sh = {post_plain, ff::shoup_of(post_plain)};
+  // geometric pre-scale walks: g and g^(N / radix of the FIRST pass's first round)
+  wpair pre_g1 = {1, ff::shoup_of(1)}, pre_gj = pre_g1;
+  if (pre_mode == SCALE_GEO && log_n >= 13) {
+    int pl[3];
+    ntt2::pass_plan(log_n, pl);
+    const int lr0 = pl[0] % 3 ? pl[0] % 3 : 3;
+    const u32 gj = ff::pow(pre.g, N >> lr0);
+    pre_g1 = wpair{pre.g, ff::shoup_of(pre.g)}, pre_gj = wpair{gj, ff::shoup_of(gj)};
+  }
+  // geometric post-scale walks (ntt_pass.cuh): g and g^(N/8), the distance between the outputs of the last radix-8 round
+  wpair post_g1 = {1, ff::shoup_of(1)}, post_gk = post_g1;
+  if (post_mode == SCALE_GEO) {
+    const u32 gk = ff::pow(post.g, N >> 3);
+    post_g1 = wpair{post.g, ff::shoup_of(post.g)}, post_gk = wpair{gk, ff::shoup_of(gk)};
+  }
   int rc = STARK_OK;
   u32 gi = 0;
   for (u32 b0 = 0; b0 < batch_total && rc == STARK_OK; b0 += group, gi++) {
@@ -388,12 +411,13 @@ int ntt_transform(stark_ctx *ctx, const u32 *in, u32 *out, int log_n, bool inver
     B.in = src, B.out = dst, B.in_batch = src_batch, B.out_batch = dst_batch;
     B.n_valid = kind == ntt2::FIRST ? n_valid : N;
     B.logS = logS;
-    B.tw_in = ctx->tw_sh[d] + (1u << r);
+    B.tw_in = ctx->tw_in_sh[d] + (r - 5) * 512;
     B.otw_tab = ctx->otw_sh[d], B.otw_shift = 15 - (log_n - logS);
     B.row_tab = ctx->row_sh[d] + (log_n - 13) * 256;
     if (kind == ntt2::FIRST) ntt2::fill_first_pass_constants(B, r);
     B.pre_mode = kind == ntt2::FIRST ? pre_mode : (int)SCALE_NONE, B.pre_geo = pre_geo;
-    B.post_mode = kind == ntt2::LAST ? post_mode : (int)SCALE_NONE, B.post_const = post_sh, B.post_geo = post_geo;
+    B.post_mode = kind == ntt2::LAST ? post_mode : (int)SCALE_NONE, B.post_const = post_sh, B.post_geo = post_geo, B.post_g1 = post_g1, B.post_gk = post_gk;
+    B.pre_g1 = pre_g1, B.pre_gj = pre_gj;
     const u64 bytes = kind == ntt2::FIRST ? 4ull * batch * (n_valid + N) : 8ull * batch * N;
     const char *tag = kind == ntt2::FIRST ? "ntt_pass1" : (kind == ntt2::LAST ? "ntt_pass_last" : "ntt_pass_mid");
     // compile-time specialisation of the per-element options (see round_compute)

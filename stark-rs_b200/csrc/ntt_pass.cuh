@@ -48,7 +48,7 @@ struct PassParams {
   int logN;                  // transform length
   int logS;                  // s = product of the previous passes' radices
   int log_tiles;             // tiles per transform = 2^(logN - 13)
-  const wpair *tw_in;        // tw_in[e] = w_R^(+-e), e < R, Shoup form (plain value + companion)
+  const wpair *tw_in;        // inner twiddles of this pass's radix in Shoup form, laid out per round (fill_inner_twiddles)
   wpair w8[4];               // 1, w_8, w_8^2, w_8^3 in the pass direction, Shoup form
   RootTables roots;          // w_{2^23}^e two-level table
   int inverse;
@@ -58,6 +58,8 @@ struct PassParams {
   wpair post_const;          // Shoup form
   GeoTables post_geo;
   u32 zero;                  // 0, known only at run time (ff::add_alu)
+  wpair pre_g1, pre_gj;      // FIRST, geometric pre-scale c g^i: g and g^(N / first-round radix) in Shoup form
+  wpair post_g1, post_gk;    // LAST, geometric post-scale c g^i: g and g^(N/8) in Shoup form (the walks along a row / down a column block)
   const wpair *otw_tab;      // MIDDLE: w_{2^15}^(+-e), e < 2^15, Shoup form; w_N^(s e) = otw_tab[e << otw_shift]
   int otw_shift;             //         15 - (logN - logS)
   const wpair *row_tab;      // FIRST: w_N^(+-row), row < 256, Shoup form
@@ -94,6 +96,31 @@ struct Plan {
     return s;
   }
 };
+
+// Inner twiddles of the R-point column DFTs, one block of 512 pairs per radix R = 2^5 .. 2^8 (out + (LOGR - 5) * 512):
+// round 0 at +0, round 1 at +256, each as [p'][k], k < RAD = the round's radix: entry = w_R^(+-(s' p' k)).  A task needs
+// the RAD - 1 twiddles of ONE p', which are adjacent here: one address computation and RAD/2 128-bit loads instead of
+// RAD - 1 indexed 64-bit loads (each of which cost an IMAD + a 64-bit IMAD.WIDE on the saturated FMA pipe).
+inline void fill_inner_twiddles(wpair *out, int inverse) {
+  for (int logr = 5; logr <= 8; logr++) {
+    u32 w = ff::pow(ff::GEN, (ff::P - 1) >> logr);   // ff.rs:215-223
+    if (inverse) w = ff::inv(w);
+    const int b0 = logr % 3, nr = logr / 3 + (b0 ? 1 : 0);
+    wpair *blk = out + (logr - 5) * 512;
+    for (int i = 0; i < 512; i++) blk[i] = wpair{1, ff::shoup_of(1)};
+    int logs = 0;
+    for (int round = 0; round + 1 < nr; round++) {
+      const int lr = (round == 0 && b0) ? b0 : 3;
+      const u32 n_pp = 1u << (logr - lr - logs);
+      for (u32 pp = 0; pp < n_pp; pp++)
+        for (u32 k = 0; k < (1u << lr); k++) {
+          const u32 v = ff::pow(w, (u64)(pp * k) << logs);
+          blk[256 * round + (pp << lr) + k] = wpair{v, ff::shoup_of(v)};
+        }
+      logs += lr;
+    }
+  }
+}
 
 // shared-memory slot (16 bytes = 4 adjacent columns of one row) of (row l, column quad c4).  A 128-bit access is
 // served per quarter-warp, conflict-free when its 8 lanes hit 8 distinct slots mod 8; the XOR keeps that true for the
@@ -213,6 +240,10 @@ FF_HD void round_compute(u32 tid, const PassParams &A, const TileCtx &T, const q
     u32 up, c4;
     decode<LOGR, LR, ROWFAST>(tid + (u32)i * NT, up, c4);
     u32 a[4][RAD];
+    // FIRST, geometric pre-scale c g^cidx: one table look-up per task, then Shoup walks by g^(N/RAD) from row to row
+    // (the RAD inputs of a butterfly are N/RAD apart) and by g along the quad
+    u32 Gj = 0;
+    if (ROUND == 0 && KIND == FIRST && (MODE & 2)) Gj = ntt::geo_pow(A.pre_geo, ((u64)up << logM) + T.col0 + 4u * c4);
 #pragma unroll
     for (int j = 0; j < RAD; j++) {
       const u32 l = up + ((u32)j << (LOGR - LR));
@@ -229,11 +260,15 @@ FF_HD void round_compute(u32 tid, const PassParams &A, const TileCtx &T, const q
           v.z = cidx + 2 < A.n_valid ? T.in[cidx + 2] : 0u;
           v.w = 0u;
         }
-        if (KIND == FIRST && (MODE & 2) && (!(MODE & 1) || cidx < A.n_valid)) {   // zero padding needs no scaling
-          v.x = ff::mont_mul(v.x, ntt::geo_pow(A.pre_geo, cidx + 0));
-          v.y = ff::mont_mul(v.y, ntt::geo_pow(A.pre_geo, cidx + 1));
-          v.z = ff::mont_mul(v.z, ntt::geo_pow(A.pre_geo, cidx + 2));
-          v.w = ff::mont_mul(v.w, ntt::geo_pow(A.pre_geo, cidx + 3));
+        if (KIND == FIRST && (MODE & 2)) {
+          if (!(MODE & 1) || cidx < A.n_valid) {   // zero padding needs no scaling
+            u32 t = Gj;
+            v.x = ff::mont_mul(v.x, t), t = ff::canon(ff::shoup_mul(t, A.pre_g1.w, A.pre_g1.s));
+            v.y = ff::mont_mul(v.y, t), t = ff::canon(ff::shoup_mul(t, A.pre_g1.w, A.pre_g1.s));
+            v.z = ff::mont_mul(v.z, t), t = ff::canon(ff::shoup_mul(t, A.pre_g1.w, A.pre_g1.s));
+            v.w = ff::mont_mul(v.w, t);
+          }
+          if (j + 1 < RAD) Gj = ff::canon(ff::shoup_mul(Gj, A.pre_gj.w, A.pre_gj.s));
         }
       } else {
         v = smem[slot<LOGC4>(l, c4)];
@@ -244,10 +279,12 @@ FF_HD void round_compute(u32 tid, const PassParams &A, const TileCtx &T, const q
     u32 tw[RAD], step[RAD];   // !LASTR: tw = plain twiddle, step = its Shoup companion
     if (!LASTR) {
       const u32 pp = up >> LOGS;
+      const q4 *tp = reinterpret_cast<const q4 *>(A.tw_in + 256 * ROUND + (pp << LR));   // pairs (2h, 2h + 1)
 #pragma unroll
-      for (int k = 1; k < RAD; k++) {
-        const wpair t = A.tw_in[(pp * (u32)k) << LOGS];
-        tw[k] = t.w, step[k] = t.s;
+      for (int h = 0; h < RAD / 2; h++) {
+        const q4 t = tp[h];
+        if (h) tw[2 * h] = t.x, step[2 * h] = t.y;
+        tw[2 * h + 1] = t.z, step[2 * h + 1] = t.w;
       }
     }
     if (LASTR && KIND == FIRST) {
@@ -270,6 +307,25 @@ FF_HD void round_compute(u32 tid, const PassParams &A, const TileCtx &T, const q
           if (x < 3) t = ff::canon(ff::shoup_mul(t, st.w, st.s));
         }
         if (k + 1 < RAD) base = ff::canon(ff::mont_mul(base, wc));
+      }
+      continue;
+    }
+    if (LASTR && KIND == LAST && MODE == ntt::SCALE_GEO) {
+      // Fused geometric post-scale c g^oidx, oidx = O + x + k N/8 (the eight outputs of a column are N/8 apart): one
+      // table look-up per task, then Shoup walks by g^(N/8) down the column block and by g along the four columns
+      // (was: two table look-ups and two Montgomery products per element).
+#pragma unroll
+      for (int x = 0; x < 4; x++) dif_lazy<LR, PIN_LAST>(a[x], A.w8, A.zero);
+      u32 G = ntt::geo_pow(A.post_geo, (u64)T.col0 + 4u * c4 + ((u64)up << A.logS));   // Montgomery form
+#pragma unroll
+      for (int k = 0; k < RAD; k++) {
+        u32 t = G;
+#pragma unroll
+        for (int x = 0; x < 4; x++) {
+          regs[(i * 4 + x) * RAD + k] = ff::canon(ff::mont_mul(a[x][bitrev<LR>(k)], t));
+          if (x < 3) t = ff::canon(ff::shoup_mul(t, A.post_g1.w, A.post_g1.s));
+        }
+        if (k + 1 < RAD) G = ff::canon(ff::shoup_mul(G, A.post_gk.w, A.post_gk.s));
       }
       continue;
     }

@@ -13,7 +13,7 @@ using namespace ntt2;
 static std::vector<u32> g_lo(4096), g_hi(2048);
 static std::vector<wpair> g_tw[2];
 static wpair g_w8[2][4];
-static std::vector<wpair> g_otw[2], g_row[2];
+static std::vector<wpair> g_otw[2], g_row[2], g_twin[2];
 static void init() {
   u32 w23 = ff::to_mont(ff::pow(3, (ff::P - 1) >> 23));
   for (u32 i = 0; i < 4096; i++) g_lo[i] = ff::mont_pow(w23, i);
@@ -28,6 +28,8 @@ static void init() {
       const u32 w = ff::from_mont(ntt::root_pow(T, idx));
       g_tw[d][i] = wpair{w, ff::shoup_of(w)};
     }
+    g_twin[d].resize(4 * 512);
+    fill_inner_twiddles(g_twin[d].data(), d);
     // mirrors k_shoup_roots in ntt.cu
     g_otw[d].resize(1u << 15), g_row[d].resize(11 * 256);
     for (int tab = 0; tab < 2; tab++)
@@ -89,12 +91,17 @@ static void transform(const u32 *in, u32 *out, int log_n, int d, u32 batch, u64 
     B.in = src, B.out = dst, B.in_batch = N, B.out_batch = N;
     B.n_valid = kind == FIRST ? n_valid : N;
     B.logS = logS;
-    B.tw_in = g_tw[d].data() + (1u << r);
+    B.tw_in = g_twin[d].data() + (r - 5) * 512;
     B.otw_tab = g_otw[d].data(), B.otw_shift = 15 - (log_n - logS);
     B.row_tab = g_row[d].data() + (log_n - 13) * 256;
     if (kind == FIRST) fill_first_pass_constants(B, r);
     B.pre_mode = kind == FIRST ? pre_mode : 0, B.pre_geo = pre_geo;
     B.post_mode = kind == LAST ? post_mode : 0, B.post_const = wpair{ff::from_mont(post_c), ff::shoup_of(ff::from_mont(post_c))}, B.post_geo = post_geo;
+    { const u32 g = 3, gk = ff::pow(g, N >> 3);   // the geometric scale of main(): c * 3^i
+      B.post_g1 = wpair{g, ff::shoup_of(g)}, B.post_gk = wpair{gk, ff::shoup_of(gk)};
+      const int lr0 = plan[0] % 3 ? plan[0] % 3 : 3;
+      const u32 gj = ff::pow(g, N >> lr0);
+      B.pre_g1 = B.post_g1, B.pre_gj = wpair{gj, ff::shoup_of(gj)}; }
     const int mode = kind == FIRST ? ((B.n_valid < N ? 1 : 0) | (B.pre_mode == ntt::SCALE_GEO ? 2 : 0)) : (kind == LAST ? B.post_mode : 0);
 #define CASE(R_, K_) if (r == R_ && kind == K_) { if (K_ == MIDDLE || mode == 0) run_pass<R_, K_, 0>(B, grid); else if (mode == 1) run_pass<R_, K_, 1>(B, grid); else if (K_ == FIRST) run_pass<R_, K_, 3>(B, grid); else run_pass<R_, K_, 2>(B, grid); } else
     CASE(6, FIRST) CASE(7, FIRST) CASE(8, FIRST) CASE(6, MIDDLE) CASE(7, MIDDLE) CASE(8, MIDDLE)
