@@ -1,4 +1,5 @@
-for cfg in "1 16" "2 16" "3 16" "4 16" "2 8" "3 8" "2 32" "3 32"; do set -- $cfg; echo "== streams $1 group_mb $2"; STARK_NTT_STREAMS=$1 STARK_NTT_GROUP_MB=$2 python benchmarks/ntt_micro.py --logs 20,22 --batch 16 --lde 2>&1 | python -c "
+# sweep of the batched-NTT grouping knobs (ntt.cu): groups in flight x bytes per group
+for cfg in ${SWEEP:-"1 16" "2 16" "3 16" "2 32" "3 32" "4 32"}; do set -- $cfg; echo "== streams $1 group_mb $2"; STARK_NTT_STREAMS=$1 STARK_NTT_GROUP_MB=$2 python benchmarks/ntt_micro.py --logs 20,22 --batch 16 --lde 2>&1 | python -c "
 import sys, json
 for l in sys.stdin:
     try: d=json.loads(l)

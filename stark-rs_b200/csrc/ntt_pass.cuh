@@ -35,8 +35,8 @@ enum Kind { FIRST = 0, MIDDLE = 1, LAST = 2 };
 constexpr int TILE_LOG = 12;   // elements per tile
 constexpr int NT = 128;        // threads per CTA
 #ifndef NTT2_PIN_LAST
-#define NTT2_PIN_LAST 5
-#define NTT2_PIN_OTHER 7
+#define NTT2_PIN_LAST 0x05
+#define NTT2_PIN_OTHER 0x77
 #endif
 constexpr int PIN_LAST = NTT2_PIN_LAST, PIN_OTHER = NTT2_PIN_OTHER;   // dif_lazy: stages whose sums go to the ALU pipe
 
@@ -137,8 +137,8 @@ FF_HD u32 slot(u32 l, u32 c4) {
 
 // radix-2^LR DIF on a[0 .. 2^LR) in [0, 2p); a[pos] ends up holding output bitrev(pos).  The outputs are LAZY, in
 // [0, 4p): the caller either multiplies them by a canonical twiddle (-> [0, 2p)) or reduces them.
-// PIN: bit i set = the sums of stage i (0 = the first, widest stage) are pinned to the ALU pipe (ff::add_alu); the
-// differences are three-input IADD3 anyway.  Chosen per pass kind from the SASS pipe counts (tools/sass_hist.py).
+// PIN: bit i set = the sums of stage i (0 = the first, widest stage) are pinned to the ALU pipe (ff::add_alu); bit 4 + i
+// = so are the two-input differences of stage i (the other differences are three-input IADD3 anyway).  Chosen per pass kind from the SASS pipe counts (tools/sass_hist.py).
 template <int LR, int PIN>
 FF_HD void dif_lazy(u32 *a, const wpair *w8, u32 zero) {
   constexpr int R = 1 << LR;
@@ -154,7 +154,10 @@ FF_HD void dif_lazy(u32 *a, const wpair *w8, u32 zero) {
 #pragma unroll
       for (int j = 0; j < h; j++) {
         const u32 u = a[blk + j], v = a[blk + j + h];
-        const u32 s = pin ? ff::add_alu(u, v, zero) : u + v, d = u + ff::P2 - v;
+        const u32 s = pin ? ff::add_alu(u, v, zero) : u + v;
+        // the difference is a three-input IADD3 except where ptxas folds the + 2p into the range reduction that follows
+        // (j == 0) and is left with a two-input u - v, which it may move to the FMA pipe: pin that one as well
+        const u32 d = (((PIN >> (4 + stage)) & 1) && j == 0 && !final_stage) ? ff::add_alu(u, 0u - v, zero) + ff::P2 : u + ff::P2 - v;
         if (final_stage) {
           a[blk + j] = s, a[blk + j + h] = d;
         } else {
@@ -315,7 +318,7 @@ FF_HD void round_compute(u32 tid, const PassParams &A, const TileCtx &T, const q
       // table look-up per task, then Shoup walks by g^(N/8) down the column block and by g along the four columns
       // (was: two table look-ups and two Montgomery products per element).
 #pragma unroll
-      for (int x = 0; x < 4; x++) dif_lazy<LR, PIN_LAST>(a[x], A.w8, A.zero);
+      for (int x = 0; x < 4; x++) dif_lazy<LR, PIN_OTHER>(a[x], A.w8, A.zero);
       u32 G = ntt::geo_pow(A.post_geo, (u64)T.col0 + 4u * c4 + ((u64)up << A.logS));   // Montgomery form
 #pragma unroll
       for (int k = 0; k < RAD; k++) {
@@ -331,7 +334,7 @@ FF_HD void round_compute(u32 tid, const PassParams &A, const TileCtx &T, const q
     }
 #pragma unroll
     for (int x = 0; x < 4; x++) {
-      dif_lazy<LR, (KIND == LAST ? PIN_LAST : PIN_OTHER)>(a[x], A.w8, A.zero);
+      dif_lazy<LR, ((KIND == LAST && MODE == ntt::SCALE_NONE) ? PIN_LAST : PIN_OTHER)>(a[x], A.w8, A.zero);
 #pragma unroll
       for (int pos = 0; pos < RAD; pos++) {
         const int k = bitrev<LR>(pos);
@@ -373,6 +376,11 @@ FF_HD void round_store(u32 tid, const PassParams &A, const TileCtx &T, q4 *smem,
     u32 up, c4;
     decode<LOGR, LR, ROWFAST>(tid + (u32)i * NT, up, c4);
     const u32 qp = up & ((1u << LOGS) - 1u), pp = up >> LOGS;
+    // MIDDLE / LAST output rows of one task are 2^(LOGS + logS) elements apart: a running 64-bit pointer (two ALU adds per
+    // store) instead of an address product per store on the FMA pipe
+    u32 *run = nullptr;
+    if (LASTR && KIND != FIRST) run = T.out + T.q0 + 4u * c4 + ((((u64)T.p << LOGR) + qp + ((pp << LR) << LOGS)) << A.logS);
+    const u64 run_step = 1ull << (LOGS + A.logS);
 #pragma unroll
     for (int k = 0; k < RAD; k++) {
       const u32 l = qp + (((pp << LR) + (u32)k) << LOGS);
@@ -388,7 +396,8 @@ FF_HD void round_store(u32 tid, const PassParams &A, const TileCtx &T, q4 *smem,
       } else {
         // Y[q + s (R p + k)]
         q4 v = {r[0], r[RAD], r[2 * RAD], r[3 * RAD]};
-        *reinterpret_cast<q4 *>(T.out + T.q0 + 4u * c4 + ((((u64)T.p << LOGR) + l) << A.logS)) = v;
+        *reinterpret_cast<q4 *>(run) = v;
+        run += run_step;
       }
     }
   }
