@@ -35,7 +35,7 @@ struct stark_ctx {
   ntt::wpair *tw_sh[2];
   ntt::wpair w8_sh[2][4];
   ntt::wpair *tw_in_sh[2]; // inner twiddles per radix and round (ntt_pass.cuh fill_inner_twiddles), 4 x 512 pairs
-  ntt::wpair *otw_sh[2];   // w_{2^15}^(+-e), e < 2^15 (outer twiddles of the MIDDLE pass)
+  ntt::wpair *otw_sh[2];   // w_{2^16}^(+-e), e < 2^16 (outer twiddles of the MIDDLE pass)
   ntt::wpair *row_sh[2];   // w_{2^logN}^(+-row), row < 256, at [(logN - 13) * 256 + row], logN = 13..23 (FIRST pass)
   GeoCacheEntry geo[8];
   u64 geo_stamp;

@@ -45,11 +45,11 @@ __global__ void k_shoup_table(const u32 *in, wpair *out, u32 n) {
   const u32 w = ff::from_mont(in[i]);
   out[i] = wpair{w, ff::shoup_of(w)};
 }
-// out[i] = w23^(+-(e(i))) in Shoup form: otw table e = i << 8 (i < 2^15); row table i = (logN - 13) * 256 + row, e = row << (23 - logN)
+// out[i] = w23^(+-(e(i))) in Shoup form: otw table e = i << 7 (i < 2^16); row table i = (logN - 13) * 256 + row, e = row << (23 - logN)
 __global__ void k_shoup_roots(wpair *out, RootTables T, int inverse, int row_table, u32 n) {
   u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  u32 idx = row_table ? (i & 255u) << (10 - (i >> 8)) : i << 8;
+  u32 idx = row_table ? (i & 255u) << (10 - (i >> 8)) : i << 7;
   if (inverse) idx = ((1u << 23) - idx) & ((1u << 23) - 1u);
   const u32 w = ff::from_mont(root_pow(T, idx));
   out[i] = wpair{w, ff::shoup_of(w)};
@@ -83,9 +83,9 @@ int ntt_init(stark_ctx *ctx) {
       CU_TRY(ctx, cudaMalloc(&ctx->tw_in_sh[d], h.size() * sizeof(wpair)));
       CU_TRY(ctx, cudaMemcpy(ctx->tw_in_sh[d], h.data(), h.size() * sizeof(wpair), cudaMemcpyHostToDevice));
     }
-    CU_TRY(ctx, cudaMalloc(&ctx->otw_sh[d], (1u << 15) * sizeof(wpair)));
+    CU_TRY(ctx, cudaMalloc(&ctx->otw_sh[d], (1u << 16) * sizeof(wpair)));
     CU_TRY(ctx, cudaMalloc(&ctx->row_sh[d], 11 * 256 * sizeof(wpair)));
-    k_shoup_roots<<<(1u << 15) / 256, 256, 0, ctx->stream>>>(ctx->otw_sh[d], T, d, 0, 1u << 15);
+    k_shoup_roots<<<(1u << 16) / 256, 256, 0, ctx->stream>>>(ctx->otw_sh[d], T, d, 0, 1u << 16);
     KERNEL_CHECK(ctx);
     k_shoup_roots<<<11, 256, 0, ctx->stream>>>(ctx->row_sh[d], T, d, 1, 11 * 256);
     KERNEL_CHECK(ctx);
@@ -412,7 +412,7 @@ int ntt_transform(stark_ctx *ctx, const u32 *in, u32 *out, int log_n, bool inver
     B.n_valid = kind == ntt2::FIRST ? n_valid : N;
     B.logS = logS;
     B.tw_in = ctx->tw_in_sh[d] + (r - 5) * 512;
-    B.otw_tab = ctx->otw_sh[d], B.otw_shift = 15 - (log_n - logS);
+    B.otw_tab = ctx->otw_sh[d], B.otw_shift = 16 - (log_n - logS);
     B.row_tab = ctx->row_sh[d] + (log_n - 13) * 256;
     if (kind == ntt2::FIRST) ntt2::fill_first_pass_constants(B, r);
     B.pre_mode = kind == ntt2::FIRST ? pre_mode : (int)SCALE_NONE, B.pre_geo = pre_geo;

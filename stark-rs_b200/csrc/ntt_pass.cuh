@@ -60,15 +60,18 @@ struct PassParams {
   u32 zero;                  // 0, known only at run time (ff::add_alu)
   wpair pre_g1, pre_gj;      // FIRST, geometric pre-scale c g^i: g and g^(N / first-round radix) in Shoup form
   wpair post_g1, post_gk;    // LAST, geometric post-scale c g^i: g and g^(N/8) in Shoup form (the walks along a row / down a column block)
-  const wpair *otw_tab;      // MIDDLE: w_{2^15}^(+-e), e < 2^15, Shoup form; w_N^(s e) = otw_tab[e << otw_shift]
-  int otw_shift;             //         15 - (logN - logS)
+  const wpair *otw_tab;      // MIDDLE: w_{2^16}^(+-e), e < 2^16, Shoup form; w_N^(s e) = otw_tab[e << otw_shift]
+  int otw_shift;             //         16 - (logN - logS)
   const wpair *row_tab;      // FIRST: w_N^(+-row), row < 256, Shoup form
   u32 dpow[8];               // FIRST: w_N^(+-(R/8) k), k < 8, Montgomery form (see round_compute)
 };
 
-// pass radices (log2) for a transform of length 2^log_n, 13 <= log_n <= 23, largest first (the FIRST pass stores one
-// contiguous block per tile, so its narrower row segments only affect loads).  Radix 2^9 would leave 32-byte rows in
-// a 4096-element tile and is not used.  Returns the pass count.
+// pass radices (log2) for a transform of length 2^log_n, 13 <= log_n <= 23, largest first.  The FIRST pass stores one
+// contiguous R x C block per tile through transposed scalar stores whose contiguous run is 4 * R/8 bytes per 8 lanes: with
+// R = 2^8 a warp writes 128 contiguous bytes, with R = 2^6 only 32.  Giving the FIRST pass the SMALLEST radix instead
+// (it is the FMA-bound pass: 757 / 685 / 599 slots per 32 elements for radix 2^8 / 2^7 / 2^6) was
+// measured slower for that reason: 16 x 2^22 305 vs 292 us with {6, 8, 8}, 2^20 alone 19.8 vs 17.5 us with {6, 7, 7}.
+// Radix 2^9 would leave 32-byte rows in a 4096-element tile and is not used.  Returns the pass count.
 inline int pass_plan(int log_n, int *r) {
   static const int PLAN[11][3] = {{7, 6, 0}, {7, 7, 0}, {8, 7, 0}, {8, 8, 0}, {6, 6, 5}, {6, 6, 6},
                                   {7, 6, 6}, {7, 7, 6}, {7, 7, 7}, {8, 7, 7}, {8, 8, 7}};
@@ -203,7 +206,7 @@ FF_HD u32 root_n(const PassParams &A, u32 e) {
 }
 
 // MIDDLE: otw[k] = w_N^(+-(s p k)) = w_{N/s}^(+-(p k)), k < R, in Shoup form (per-tile table in shared memory).
-// N/s <= 2^15 for every plan (the first radix is >= 2^(logN - 15)), so the pairs come straight from one table.
+// N/s <= 2^16 for every plan (the first radix is >= 2^(logN - 16)), so the pairs come straight from one table.
 template <int LOGR>
 FF_HD void fill_outer_table(u32 tid, const PassParams &A, const TileCtx &T, wpair *otw) {
   for (u32 k = tid; k < (1u << LOGR); k += NT) otw[k] = A.otw_tab[(T.p * k) << A.otw_shift];

@@ -31,10 +31,10 @@ static void init() {
     g_twin[d].resize(4 * 512);
     fill_inner_twiddles(g_twin[d].data(), d);
     // mirrors k_shoup_roots in ntt.cu
-    g_otw[d].resize(1u << 15), g_row[d].resize(11 * 256);
+    g_otw[d].resize(1u << 16), g_row[d].resize(11 * 256);
     for (int tab = 0; tab < 2; tab++)
-      for (u32 i = 0; i < (tab ? 11u * 256 : 1u << 15); i++) {
-        u32 idx = tab ? (i & 255u) << (10 - (i >> 8)) : i << 8;
+      for (u32 i = 0; i < (tab ? 11u * 256 : 1u << 16); i++) {
+        u32 idx = tab ? (i & 255u) << (10 - (i >> 8)) : i << 7;
         if (d) idx = ((1u << 23) - idx) & ((1u << 23) - 1u);
         const u32 w = ff::from_mont(ntt::root_pow(T, idx));
         (tab ? g_row[d] : g_otw[d])[i] = wpair{w, ff::shoup_of(w)};
@@ -92,7 +92,7 @@ static void transform(const u32 *in, u32 *out, int log_n, int d, u32 batch, u64 
     B.n_valid = kind == FIRST ? n_valid : N;
     B.logS = logS;
     B.tw_in = g_twin[d].data() + (r - 5) * 512;
-    B.otw_tab = g_otw[d].data(), B.otw_shift = 15 - (log_n - logS);
+    B.otw_tab = g_otw[d].data(), B.otw_shift = 16 - (log_n - logS);
     B.row_tab = g_row[d].data() + (log_n - 13) * 256;
     if (kind == FIRST) fill_first_pass_constants(B, r);
     B.pre_mode = kind == FIRST ? pre_mode : 0, B.pre_geo = pre_geo;
