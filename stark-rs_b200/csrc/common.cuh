@@ -30,8 +30,8 @@ struct stark_ctx {
   u32 *root_lo, *root_hi;
   // per-length sub-transform twiddles: tw_sub[dir][(1 << logL) + e] = w_L^(+-e), logL <= 12
   u32 *tw_sub[2];
-  u32 w8[2][4];
-  // the same sub-transform twiddles and w_8 powers in Shoup form (plain value + floor(w 2^32 / p)) for ntt_pass.cuh
+  // the same sub-transform twiddles, and the w_8 powers, in Shoup form (plain value + floor(w 2^32 / p)): what the
+  // transforms multiply by (tw_sub is only their source)
   ntt::wpair *tw_sh[2];
   ntt::wpair w8_sh[2][4];
   ntt::wpair *tw_in_sh[2]; // inner twiddles per radix and round (ntt_pass.cuh fill_inner_twiddles), 4 x 512 pairs

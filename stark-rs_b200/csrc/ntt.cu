@@ -91,8 +91,6 @@ int ntt_init(stark_ctx *ctx) {
     KERNEL_CHECK(ctx);
     u32 w8 = ff::pow(ff::GEN, (ff::P - 1) >> 3);
     if (d) w8 = ff::inv(w8);
-    ctx->w8[d][0] = ff::R1;
-    for (int k = 1; k < 4; k++) ctx->w8[d][k] = ff::to_mont(ff::pow(w8, k));
     for (int k = 0; k < 4; k++) ctx->w8_sh[d][k] = wpair{ff::pow(w8, k), ff::shoup_of(ff::pow(w8, k))};
   }
   for (int i = 0; i < 8; i++) ctx->geo[i] = GeoCacheEntry{0, 0, nullptr, nullptr, 0, 0};
@@ -312,12 +310,12 @@ int ntt_transform(stark_ctx *ctx, const u32 *in, u32 *out, int log_n, bool inver
     // one pass, one transform per CTA
     PassArgs A;
     memset(&A, 0, sizeof A);
-    for (int k = 0; k < 4; k++) A.w8[k] = ctx->w8[d][k];
+    for (int k = 0; k < 4; k++) A.w8[k] = ctx->w8_sh[d][k];
     A.pre_mode = pre_mode, A.pre_geo = pre_geo;
     A.post_mode = post_mode, A.post_const = post_c, A.post_geo = post_geo;
     A.in = in, A.out = out, A.logL = log_n;
     A.in_batch = in_batch, A.out_batch = out_batch, A.n_valid = n_valid;
-    A.tw = ctx->tw_sub[d] + (1u << log_n);
+    A.tw = ctx->tw_sh[d] + (1u << log_n);
     LAUNCH(ctx, "ntt_single", 4ull * batch * (n_valid + N), k_ntt_single<<<batch, (u32)(N >> 3), 0, ctx->stream>>>(A));
     return STARK_OK;
   }

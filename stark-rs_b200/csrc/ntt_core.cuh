@@ -53,8 +53,8 @@ struct PassArgs {
   int logL;                  // transform length L = 2^logL, 3 <= logL <= 12
   u64 in_batch, out_batch;   // element stride between the transforms of a batch (one CTA each)
   u64 n_valid;               // inputs at index >= n_valid are zero and are not read
-  const u32 *tw;             // tw[e] = w_L^(+-e) for e < L, Montgomery form
-  u32 w8[4];                 // 1, w_8, w_8^2, w_8^3 in the transform direction, Montgomery form
+  const wpair *tw;           // tw[e] = w_L^(+-e) for e < L, Shoup form (field.cuh shoup_mul)
+  wpair w8[4];               // 1, w_8, w_8^2, w_8^3 in the transform direction, Shoup form
   int pre_mode;              // ScaleMode applied to loaded elements (index = coefficient index); GEO only
   GeoTables pre_geo;
   int post_mode;             // ScaleMode applied to stored elements (index = output index)
@@ -64,7 +64,7 @@ struct PassArgs {
 
 // in-register radix-2^LOGR DIF; a[i] ends up holding output bitrev(i).  Inputs/outputs in [0, 2p).
 template <int LOGR>
-FF_HD void dif_regs(u32 *a, const u32 *w8) {
+FF_HD void dif_regs(u32 *a, const wpair *w8) {
   constexpr int R = 1 << LOGR;
 #pragma unroll
   for (int len = R; len >= 2; len >>= 1) {
@@ -76,7 +76,7 @@ FF_HD void dif_regs(u32 *a, const u32 *w8) {
         u32 u = a[blk + j], v = a[blk + j + h];
         a[blk + j] = ff::red2p(u + v);
         u32 d = u + ff::P2 - v;
-        a[blk + j + h] = (j == 0) ? ff::red2p(d) : ff::mont_mul(d, w8[j * (8 / len)]);
+        a[blk + j + h] = (j == 0) ? ff::red2p(d) : ff::shoup_mul(d, w8[j * (8 / len)].w, w8[j * (8 / len)].s);
       }
     }
   }
@@ -116,7 +116,10 @@ FF_HD void round_load_compute(u32 tid, u32 nthreads, u32 b, const PassArgs &A, i
     for (int pos = 0; pos < R; pos++) {
       const int kk = bitrev<LOGR>(pos);
       u32 val = a[pos];
-      if (kk != 0) val = ff::mont_mul(val, A.tw[(p * (u32)kk) << logS]);
+      if (kk != 0) {
+        const wpair t = A.tw[(p * (u32)kk) << logS];
+        val = ff::shoup_mul(val, t.w, t.s);
+      }
       regs[i * R + kk] = val;
     }
   }

@@ -9,25 +9,26 @@
 using namespace ntt;
 using ff::u32; using ff::u64;
 
-static std::vector<u32> g_lo(4096), g_hi(2048), g_tw[2];
-static u32 g_w8[2][4];
+static std::vector<u32> g_lo(4096), g_hi(2048);
+static std::vector<wpair> g_tw[2];
+static wpair g_w8[2][4];
 static void init() {
   u32 w23 = ff::to_mont(ff::pow(3, (ff::P - 1) >> 23));
   for (u32 i = 0; i < 4096; i++) g_lo[i] = ff::mont_pow(w23, i);
   for (u32 i = 0; i < 2048; i++) g_hi[i] = ff::mont_pow(w23, (u64)i << 12);
   RootTables T = {g_lo.data(), g_hi.data()};
   for (int d = 0; d < 2; d++) {
-    g_tw[d].assign(8192, ff::R1);
+    g_tw[d].assign(8192, wpair{1, ff::shoup_of(1)});
     for (u32 i = 1; i < 8192; i++) {
       int logL = 31 - __builtin_clz(i);
       u32 e = i - (1u << logL), idx = e << (23 - logL);
       if (d) idx = ((1u << 23) - idx) & ((1u << 23) - 1u);
-      g_tw[d][i] = root_pow(T, idx);
+      const u32 w = ff::from_mont(root_pow(T, idx));
+      g_tw[d][i] = wpair{w, ff::shoup_of(w)};
     }
     u32 w8 = ff::pow(3, (ff::P - 1) >> 3);
     if (d) w8 = ff::inv(w8);
-    g_w8[d][0] = ff::R1;
-    for (int k = 1; k < 4; k++) g_w8[d][k] = ff::to_mont(ff::pow(w8, k));
+    for (int k = 0; k < 4; k++) g_w8[d][k] = wpair{ff::pow(w8, k), ff::shoup_of(ff::pow(w8, k))};
   }
 }
 
