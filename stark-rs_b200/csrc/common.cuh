@@ -49,6 +49,8 @@ struct stark_ctx {
   int n_side;            // streams created so far
   int ntt_streams;       // groups in flight (STARK_NTT_STREAMS, default 2; 1 = whole batch per pass)
   int ntt_group_mb;      // bytes of one group's column slice (STARK_NTT_GROUP_MB, default 16)
+  int ntt_l2_persist;    // STARK_NTT_L2_PERSIST=1: mark each pass's destination as L2-persisting (experiment, default off)
+  int l2_persist_ready;
   char err[512];
   // optional per-kernel timing (stark_ctx_profile_begin/end): CUDA events around every launch, on ctx->stream
   bool prof_on;

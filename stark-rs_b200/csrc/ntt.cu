@@ -102,7 +102,32 @@ int ntt_init(stark_ctx *ctx) {
   ctx->ntt_group_mb = e ? atoi(e) : 16;
   if (ctx->ntt_group_mb < 1) ctx->ntt_group_mb = 16;
   ctx->n_side = 0;
+  e = getenv("STARK_NTT_L2_PERSIST");
+  ctx->ntt_l2_persist = e ? atoi(e) : 0;
+  ctx->l2_persist_ready = 0;
   return STARK_OK;
+}
+// L2 persistence for the grouped path: the destination of a pass is read by the next pass of the same group
+static void l2_window(stark_ctx *ctx, cudaStream_t st, const void *base, size_t bytes) {
+  if (!ctx->l2_persist_ready) {
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+    size_t want = (size_t)ctx->ntt_l2_persist << 20;   // MB of set-aside requested through the knob
+    if (want > (size_t)max_persist) want = (size_t)max_persist;
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+    ctx->l2_persist_ready = max_window > 0 ? max_window : -1;
+    fprintf(stderr, "[stark] L2 persistence: set-aside %zu MB (max %d MB), window max %d MB\n", want >> 20, max_persist >> 20, max_window >> 20);
+  }
+  if (ctx->l2_persist_ready <= 0) return;
+  cudaStreamAttrValue v;
+  memset(&v, 0, sizeof v);
+  v.accessPolicyWindow.base_ptr = const_cast<void *>(base);
+  v.accessPolicyWindow.num_bytes = bytes < (size_t)ctx->l2_persist_ready ? bytes : (size_t)ctx->l2_persist_ready;
+  v.accessPolicyWindow.hitRatio = 1.0f;
+  v.accessPolicyWindow.hitProp = bytes ? cudaAccessPropertyPersisting : cudaAccessPropertyNormal;
+  v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v);
 }
 // lazily created side streams + events
 static int side_streams(stark_ctx *ctx, int n) {
@@ -416,6 +441,7 @@ int ntt_transform(stark_ctx *ctx, const u32 *in, u32 *out, int log_n, bool inver
     B.pre_mode = kind == ntt2::FIRST ? pre_mode : (int)SCALE_NONE, B.pre_geo = pre_geo;
     B.post_mode = kind == ntt2::LAST ? post_mode : (int)SCALE_NONE, B.post_const = post_sh, B.post_geo = post_geo, B.post_g1 = post_g1, B.post_gk = post_gk;
     B.pre_g1 = pre_g1, B.pre_gj = pre_gj;
+    if (n_streams > 1 && ctx->ntt_l2_persist) l2_window(ctx, ctx->stream, dst, (size_t)batch * N * 4);
     const u64 bytes = kind == ntt2::FIRST ? 4ull * batch * (n_valid + N) : 8ull * batch * N;
     const char *tag = kind == ntt2::FIRST ? "ntt_pass1" : (kind == ntt2::LAST ? "ntt_pass_last" : "ntt_pass_mid");
     // compile-time specialisation of the per-element options (see round_compute)
@@ -446,6 +472,8 @@ int ntt_transform(stark_ctx *ctx, const u32 *in, u32 *out, int log_n, bool inver
   }
   if (n_streams > 1) {
     ctx->stream = main_stream;
+    if (ctx->ntt_l2_persist)
+      for (int i = 0; i < n_streams; i++) l2_window(ctx, ctx->side[i], nullptr, 0);
     for (int i = 0; i < n_streams; i++) {
       cudaEventRecord(ctx->side_done[i], ctx->side[i]);
       cudaStreamWaitEvent(main_stream, ctx->side_done[i], 0);
