@@ -319,8 +319,13 @@ def run_ours(a):
         threads = os.cpu_count() or 1
         v0, s0 = cpu_pipeline(a, 0, a.cpu_sample_log_n, 2, 0, threads)
         v1, s1 = cpu_pipeline(a, 1, 14, 2, 0, threads)
+        cpu_model = ""
+        try:
+            cpu_model = next(l.split(":", 1)[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name"))
+        except Exception:  # noqa: BLE001
+            pass
         line["cpu_baseline"] = {
-            "value": v0, "unit": UNIT, "cores": threads, "kind": "port",
+            "value": v0, "unit": UNIT, "cores": threads, "cpu_model": cpu_model, "kind": "port",
             "sample": "%d parallel pipelines on 2^%d-row traces, reference algorithms end to end (O(n^3) interpolate + "
                       "Horner eval LDE, Merkle, Fri::prove), %.2f s per sample" % (threads, a.cpu_sample_log_n, s0)}
         line["cpu_baseline_matched"] = {

@@ -241,3 +241,24 @@ def test_poly_div_large(ctx, oracle):
     back = oracle.fast_poly_mul(q, b)
     back = (back[: 1 << 18] + r) % P
     assert np.array_equal(back, a)
+
+
+def test_batched_transforms_larger_than_l2(ctx, oracle):
+    """batches of >= 48 MB take the grouped path of ntt_transform (column groups on side streams, ntt.cu): every column
+    must still be the transform of that column -- three-pass and two-pass sizes, out of place and in place, and the LDE"""
+    for log_n, batch in ((20, 16), (14, 1024)):
+        n = 1 << log_n
+        cols = rf(log_n + batch, n * batch)
+        src, dst = ctx.upload(cols), ctx.alloc(n * batch)
+        ctx.ntt_dev(src, dst, log_n, batch=batch)
+        got = dst.download().reshape(batch, n)
+        for c in (0, 1, batch // 2, batch - 1):
+            assert np.array_equal(got[c], oracle.fast_eval_coset(cols.reshape(batch, n)[c], 1, log_n)), (log_n, c)
+        ctx.ntt_dev(dst, dst, log_n, batch=batch, inverse=True)        # in place, back to the input
+        assert np.array_equal(dst.download(), cols)
+    log_n, n_cols = 20, 16
+    cols = rf(99, n_cols << log_n)
+    out = ctx.lde_dev(ctx.upload(cols), n_cols, log_n, 2, 3).download().reshape(n_cols, -1)
+    for c in (0, 7, n_cols - 1):
+        assert np.array_equal(out[c], oracle.fast_lde(cols.reshape(n_cols, -1)[c], log_n, 2, 3))
+
