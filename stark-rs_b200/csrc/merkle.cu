@@ -203,8 +203,10 @@ int merkle_climb_dev(stark_ctx *ctx, u8 *nodes, size_t n, const TranscriptArgs *
   const TranscriptArgs none = {nullptr, nullptr, 0, nullptr, nullptr};
   u32 level = 0;
   size_t m = n;
-  // throughput-bound levels: one launch each
-  while ((m >> 1) >= ((size_t)1 << 17)) {
+  // throughput-bound levels: one launch each.  A level of 2^17 parents is already half latency (12 us against 6 us for the
+  // same step inside the climb kernel, whose launch is paid anyway), so the climb starts from 2^18 nodes.
+  const size_t climb_from = getenv("STARK_CLIMB_LOG") ? ((size_t)1 << atoi(getenv("STARK_CLIMB_LOG"))) : ((size_t)1 << 18);
+  while (m > climb_from) {
     const size_t half = m >> 1;
     LAUNCH_PDL(ctx, "merkle_level", 96ull * half, k_merkle_level, (u32)((half + 2 * HASH_NT - 1) / (2 * HASH_NT)), HASH_NT,
                (const u8 *)(nodes + 32 * (2 * n - 2 * m)), nodes + 32 * (2 * n - 2 * half), half);
@@ -214,8 +216,10 @@ int merkle_climb_dev(stark_ctx *ctx, u8 *nodes, size_t n, const TranscriptArgs *
   // latency-bound levels (m <= 2^17 nodes left): chunks of 512 nodes climb 9 levels each and the last CTA to finish
   // climbs the <= 256 chunk roots to the root; small trees are a single CTA
   if (m > 1024) {
-    const size_t ctas = m / 512;
-    LAUNCH_PDL(ctx, "merkle_climb", 96ull * (m - 1), k_merkle_climb<256>, (u32)ctas, 256, nodes, n, level, 512u, 9u,
+    // at most 256 chunks (their roots are climbed by the last CTA): 1024-node chunks (10 levels) above 2^17 nodes
+    const u32 chunk = m > ((size_t)1 << 17) ? 1024u : 512u, chunk_levels = chunk == 1024u ? 10u : 9u;
+    const size_t ctas = m / chunk;
+    LAUNCH_PDL(ctx, "merkle_climb", 96ull * (m - 1), k_merkle_climb<256>, (u32)ctas, 256, nodes, n, level, chunk, chunk_levels,
                tr ? *tr : none, ctx->flag + 1);
   } else if (m > 1) {
     u32 levels = 0;
