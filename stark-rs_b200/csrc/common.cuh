@@ -118,8 +118,7 @@ __device__ __forceinline__ void pdl_entry() {
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                                      Args... args) {
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof cfg);
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
