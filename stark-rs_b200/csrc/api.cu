@@ -337,7 +337,7 @@ void stark_buf_free(stark_buf *buf) {
 
 // ---- trace ingestion
 int stark_trace_to_columns(stark_ctx *ctx, const void *rows_i128, size_t n_rows, uint32_t n_cols, stark_buf **out) {
-  if (!ctx || !out || (!rows_i128 && n_rows * (size_t)n_cols)) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+  if (!ctx || !out || (!rows_i128 && n_rows && n_cols)) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
   stark_buf *b = nullptr;
   ST_TRY(stark_buf_alloc(ctx, n_rows * (size_t)n_cols, &b));
   int rc = trace_to_columns_dev(ctx, rows_i128, n_rows, n_cols, b->ptr);

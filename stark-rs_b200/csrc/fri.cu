@@ -826,7 +826,7 @@ int stark_fri_sample_indices(const uint8_t *seed, size_t seed_len, size_t size, 
 
 int stark_fri_proof_size(size_t domain_length, uint32_t ef, uint32_t nq, size_t *bytes) {
   if (!bytes) return stark_fail(nullptr, STARK_ERR_ARG, "null argument");
-  u32 R;
+  u32 R = 0;
   ST_TRY(fri_check(nullptr, domain_length, ef, &R, nq));
   ProofLayout L;
   proof_layout(domain_length, R, nq, &L);

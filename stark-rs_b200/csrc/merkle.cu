@@ -260,7 +260,7 @@ int merkle_open_dev(stark_ctx *ctx, const u8 *nodes, size_t n, const u64 *idx_de
 extern "C" {
 
 int stark_hash_bytes(stark_ctx *ctx, const uint8_t *msgs, size_t n_msgs, size_t msg_len, uint8_t *out) {
-  if (!ctx || (!msgs && n_msgs * msg_len) || !out) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+  if (!ctx || (!msgs && n_msgs && msg_len) || !out) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
   if (n_msgs == 0) return STARK_OK;
   u8 *d_in = nullptr, *d_out = nullptr;
   ST_TRY(dev_alloc(ctx, (void **)&d_in, n_msgs * msg_len));

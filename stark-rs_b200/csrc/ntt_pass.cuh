@@ -141,11 +141,11 @@ FF_HD u32 slot(u32 l, u32 c4) {
 // radix-2^LR DIF on a[0 .. 2^LR) in [0, 2p); a[pos] ends up holding output bitrev(pos).  The outputs are LAZY, in
 // [0, 4p): the caller either multiplies them by a canonical twiddle (-> [0, 2p)) or reduces them.
 // PIN: bit i set = the sums of stage i (0 = the first, widest stage) are pinned to the ALU pipe (ff::add_alu); bit 4 + i
-// = so are the two-input differences of stage i (the other differences are three-input IADD3 anyway).  Chosen per pass kind from the SASS pipe counts (tools/sass_hist.py).
+// = so are the two-input differences of stage i (the other differences are three-input IADD3 anyway).  Chosen per pass
+// kind from the SASS pipe counts (tools/sass_hist.py).
 template <int LR, int PIN>
 FF_HD void dif_lazy(u32 *a, const wpair *w8, u32 zero) {
   constexpr int R = 1 << LR;
-#pragma unroll
   int stage = 0;
 #pragma unroll
   for (int len = R; len >= 2; len >>= 1, stage++) {
