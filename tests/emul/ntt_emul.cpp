@@ -73,11 +73,39 @@ static void ref_ntt(std::vector<u64> &a, u64 root) {
   }
 }
 
+// field.cuh products (host paths; the device paths are the same arithmetic as PTX): ranges and residues of the Montgomery
+// and Shoup forms on edge values and 2 * 10^6 pseudo-random pairs
+static int check_products() {
+  int bad = 0;
+  u64 s = 99;
+  const u32 edge[] = {0u, 1u, 2u, ff::P - 1, ff::P, ff::P + 1, ff::P2 - 1, ff::P2, 2 * ff::P2 - 1, 0x7fffffffu, 0x80000000u, 0xffffffffu};
+  for (int it = 0; it < 2000000 + 144; it++) {
+    u32 x, w;
+    if (it < 144) {
+      x = edge[it / 12], w = edge[it % 12] % ff::P;
+    } else {
+      s = s * 6364136223846793005ull + 1442695040888963407ull;
+      x = (u32)(s >> 32);
+      s = s * 6364136223846793005ull + 1442695040888963407ull;
+      w = (u32)((s >> 33) % ff::P);
+    }
+    const u64 want = (u64)(x % ff::P) * w % ff::P;
+    const u32 sh = ff::shoup_mul(x, w, ff::shoup_of(w));
+    const u32 mm = ff::mont_mul(x, ff::to_mont(w));
+    if (sh >= ff::P2 || sh % ff::P != want) bad++;
+    if (mm >= ff::P2 || mm % ff::P != want) bad++;
+    if (ff::red2p(x % (2 * ff::P2)) >= ff::P2 || ff::canon(x % ff::P2) >= ff::P) bad++;
+    if (ff::add_alu(x, w, 0u) != x + w) bad++;
+  }
+  if (bad) printf("field product check: %d violations\n", bad);
+  return bad;
+}
+
 int main(int argc, char **argv) {
   init();
   int max_log = argc > 1 ? atoi(argv[1]) : 12;
   if (max_log > 12) max_log = 12;
-  int fails = 0;
+  int fails = check_products();
   for (int log_n = 3; log_n <= max_log; log_n++) for (int d = 0; d < 2; d++) for (int mode = 0; mode < 2; mode++) {
     const u64 N = 1ull << log_n; const u32 batch = 3;
     std::vector<u32> in(batch * N), out(batch * N);

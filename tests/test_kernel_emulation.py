@@ -24,7 +24,7 @@ def test_single_pass_ntt_emulation(tmp_path):
 
 
 def test_multi_pass_ntt_emulation(tmp_path):
-    out = _run("ntt2_emul.cpp", 19, tmp_path)                  # 2^13..2^19: 2 and 3 passes, all scale modes
+    out = _run("ntt2_emul.cpp", 22, tmp_path)                  # 2^13..2^22: every pass plan but 2^23's, all scale modes
     assert "bank-conflicted quarter-warp accesses: 0" in out
     assert "smem range violations (>= 2p): 0" in out
     assert "OK" in out
