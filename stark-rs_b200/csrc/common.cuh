@@ -34,9 +34,9 @@ struct stark_ctx {
   // transforms multiply by (tw_sub is only their source)
   ntt::wpair *tw_sh[2];
   ntt::wpair w8_sh[2][4];
-  ntt::wpair *tw_in_sh[2]; // inner twiddles per radix and round (ntt_pass.cuh fill_inner_twiddles), 4 x 512 pairs
+  ntt::wpair *tw_in_sh[2]; // inner twiddles per radix and round (ntt_pass.cuh fill_inner_twiddles)
   ntt::wpair *otw_sh[2];   // w_{2^16}^(+-e), e < 2^16 (outer twiddles of the MIDDLE pass)
-  ntt::wpair *row_sh[2];   // w_{2^logN}^(+-row), row < 256, at [(logN - 13) * 256 + row], logN = 13..23 (FIRST pass)
+  ntt::wpair *row_sh[2];   // w_{2^logN}^(+-row), row < 2048, at [(logN - 13) * 2048 + row], logN = 13..23 (FIRST pass)
   GeoCacheEntry geo[8];
   u64 geo_stamp;
   u32 *flag;       // device int used by validation kernels
@@ -49,6 +49,7 @@ struct stark_ctx {
   int n_side;            // streams created so far
   int ntt_streams;       // groups in flight (STARK_NTT_STREAMS, default 2; 1 = whole batch per pass)
   int ntt_group_mb;      // bytes of one group's column slice (STARK_NTT_GROUP_MB, default 16)
+  int ntt_big;           // STARK_NTT_BIG=1: two-pass plans on 16384-element tiles for 2^20..2^22 (experiment)
   int ntt_l2_persist;    // STARK_NTT_L2_PERSIST=1: mark each pass's destination as L2-persisting (experiment, default off)
   int l2_persist_ready;
   char err[512];

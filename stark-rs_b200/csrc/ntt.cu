@@ -45,11 +45,11 @@ __global__ void k_shoup_table(const u32 *in, wpair *out, u32 n) {
   const u32 w = ff::from_mont(in[i]);
   out[i] = wpair{w, ff::shoup_of(w)};
 }
-// out[i] = w23^(+-(e(i))) in Shoup form: otw table e = i << 7 (i < 2^16); row table i = (logN - 13) * 256 + row, e = row << (23 - logN)
+// out[i] = w23^(+-(e(i))) in Shoup form: otw table e = i << 7 (i < 2^16); row table i = (logN - 13) * 2048 + row, e = row << (23 - logN)
 __global__ void k_shoup_roots(wpair *out, RootTables T, int inverse, int row_table, u32 n) {
   u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  u32 idx = row_table ? (i & 255u) << (10 - (i >> 8)) : i << 7;
+  u32 idx = row_table ? (i & 2047u) << (10 - (i >> 11)) : i << 7;
   if (inverse) idx = ((1u << 23) - idx) & ((1u << 23) - 1u);
   const u32 w = ff::from_mont(root_pow(T, idx));
   out[i] = wpair{w, ff::shoup_of(w)};
@@ -78,16 +78,16 @@ int ntt_init(stark_ctx *ctx) {
     k_shoup_table<<<32, 256, 0, ctx->stream>>>(ctx->tw_sub[d], ctx->tw_sh[d], 8192);
     KERNEL_CHECK(ctx);
     {
-      std::vector<wpair> h(4 * 512);
+      std::vector<wpair> h(ntt2::INNER_TWIDDLE_PAIRS);
       ntt2::fill_inner_twiddles(h.data(), d);
       CU_TRY(ctx, cudaMalloc(&ctx->tw_in_sh[d], h.size() * sizeof(wpair)));
       CU_TRY(ctx, cudaMemcpy(ctx->tw_in_sh[d], h.data(), h.size() * sizeof(wpair), cudaMemcpyHostToDevice));
     }
     CU_TRY(ctx, cudaMalloc(&ctx->otw_sh[d], (1u << 16) * sizeof(wpair)));
-    CU_TRY(ctx, cudaMalloc(&ctx->row_sh[d], 11 * 256 * sizeof(wpair)));
+    CU_TRY(ctx, cudaMalloc(&ctx->row_sh[d], 11 * 2048 * sizeof(wpair)));
     k_shoup_roots<<<(1u << 16) / 256, 256, 0, ctx->stream>>>(ctx->otw_sh[d], T, d, 0, 1u << 16);
     KERNEL_CHECK(ctx);
-    k_shoup_roots<<<11, 256, 0, ctx->stream>>>(ctx->row_sh[d], T, d, 1, 11 * 256);
+    k_shoup_roots<<<11 * 8, 256, 0, ctx->stream>>>(ctx->row_sh[d], T, d, 1, 11 * 2048);
     KERNEL_CHECK(ctx);
     u32 w8 = ff::pow(ff::GEN, (ff::P - 1) >> 3);
     if (d) w8 = ff::inv(w8);
@@ -102,6 +102,8 @@ int ntt_init(stark_ctx *ctx) {
   ctx->ntt_group_mb = e ? atoi(e) : 16;
   if (ctx->ntt_group_mb < 1) ctx->ntt_group_mb = 16;
   ctx->n_side = 0;
+  e = getenv("STARK_NTT_BIG");
+  ctx->ntt_big = e ? atoi(e) : 0;
   e = getenv("STARK_NTT_L2_PERSIST");
   ctx->ntt_l2_persist = e ? atoi(e) : 0;
   ctx->l2_persist_ready = 0;
@@ -251,29 +253,51 @@ __global__ void __launch_bounds__(512) k_ntt_single(const __grid_constant__ Pass
   }
 }
 
-// N >= 2^13: one multi-pass Stockham pass (ntt_pass.cuh).  4096-element tile, 128 threads, 16 KB of shared memory.
-template <int LOGR, int KIND, int MODE>
-__global__ void __launch_bounds__(ntt2::NT, 8) k_ntt2_pass(const __grid_constant__ ntt2::PassParams A) {
+// N >= 2^13: one multi-pass Stockham pass (ntt_pass.cuh).  TL = 12: 4096-element tile, 128 threads, 16 KB of static shared
+// memory, 8 CTAs per SM.  TL = 14 (the two-pass plans, STARK_NTT_BIG): 16384-element tile, 512 threads, 64 KB of dynamic
+// shared memory, 2 CTAs per SM, radix 2^10 / 2^11 in four rounds.
+template <int LOGR, int KIND, int MODE, int TL = ntt2::TILE_LOG>
+__global__ void __launch_bounds__(1 << (TL - 5), TL == ntt2::TILE_LOG ? 8 : 2) k_ntt2_pass(const __grid_constant__ ntt2::PassParams A) {
   using namespace ntt2;
   typedef Plan<LOGR> PL;
-  __shared__ __align__(16) q4 tile[1 << (TILE_LOG - 2)];
+  extern __shared__ __align__(16) unsigned char dyn_tile[];
+  __shared__ __align__(16) q4 static_tile[TL == TILE_LOG ? (1 << (TILE_LOG - 2)) : 1];
   __shared__ wpair otw[KIND == MIDDLE ? (1 << LOGR) : 1];
+  q4 *tile = TL == TILE_LOG ? static_tile : reinterpret_cast<q4 *>(dyn_tile);
   pdl_entry();
   const u32 tid = threadIdx.x;
-  const TileCtx T = tile_ctx<LOGR>(A, blockIdx.x);
-  if (KIND == MIDDLE) fill_outer_table<LOGR>(tid, A, T, otw);
+  const TileCtx T = tile_ctx<LOGR, TL>(A, blockIdx.x);
+  if (KIND == MIDDLE) fill_outer_table<LOGR, TL>(tid, A, T, otw);
   u32 regs[32];
-  round_compute<LOGR, KIND, 0, MODE>(tid, A, T, tile, otw, regs);
-  round_store<LOGR, KIND, 0>(tid, A, T, tile, regs);
+  round_compute<LOGR, KIND, 0, MODE, TL>(tid, A, T, tile, otw, regs);
+  round_store<LOGR, KIND, 0, TL>(tid, A, T, tile, regs);
   __syncthreads();
-  if constexpr (PL::NR == 3) {
-    round_compute<LOGR, KIND, 1, MODE>(tid, A, T, tile, otw, regs);
+  if constexpr (PL::NR >= 3) {
+    round_compute<LOGR, KIND, 1, MODE, TL>(tid, A, T, tile, otw, regs);
     __syncthreads();
-    round_store<LOGR, KIND, 1>(tid, A, T, tile, regs);
+    round_store<LOGR, KIND, 1, TL>(tid, A, T, tile, regs);
     __syncthreads();
   }
-  round_compute<LOGR, KIND, PL::NR - 1, MODE>(tid, A, T, tile, otw, regs);
-  round_store<LOGR, KIND, PL::NR - 1>(tid, A, T, tile, regs);
+  if constexpr (PL::NR == 4) {
+    round_compute<LOGR, KIND, 2, MODE, TL>(tid, A, T, tile, otw, regs);
+    __syncthreads();
+    round_store<LOGR, KIND, 2, TL>(tid, A, T, tile, regs);
+    __syncthreads();
+  }
+  round_compute<LOGR, KIND, PL::NR - 1, MODE, TL>(tid, A, T, tile, otw, regs);
+  round_store<LOGR, KIND, PL::NR - 1, TL>(tid, A, T, tile, regs);
+}
+// launch of a 16384-element-tile pass: 64 KB of dynamic shared memory (opt-in above 48 KB, once per instance)
+template <int LOGR, int KIND, int MODE>
+static cudaError_t launch_big_pass(cudaStream_t st, u32 grid, const ntt2::PassParams &B) {
+  static bool ready = false;
+  auto kernel = k_ntt2_pass<LOGR, KIND, MODE, 14>;
+  if (!ready) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+    if (e != cudaSuccess) return e;
+    ready = true;
+  }
+  return launch_pdl(kernel, dim3(grid), dim3(512), 65536, st, B);
 }
 
 // ----------------------------------------------------------------------------------------- launcher
@@ -347,7 +371,11 @@ int ntt_transform(stark_ctx *ctx, const u32 *in, u32 *out, int log_n, bool inver
 
   // N >= 2^13: 2 or 3 Stockham passes with radices 2^5 .. 2^8 (ntt_pass.cuh)
   int plan[3];
-  const int n_pass = ntt2::pass_plan(log_n, plan);
+  int n_pass = ntt2::pass_plan(log_n, plan);
+  // experiment (STARK_NTT_BIG=1): TWO passes of radix 2^10 / 2^11 on 16384-element tiles for 2^20 .. 2^22
+  const bool big = ctx->ntt_big && log_n >= 20 && log_n <= 22;
+  if (big) plan[0] = (log_n + 1) / 2, plan[1] = log_n / 2, plan[2] = 0, n_pass = 2;
+  const int tile_log = big ? 14 : ntt2::TILE_LOG;
   // FIRST and MIDDLE passes are out of place, the LAST pass may run in place:
   //   2 passes: in -> out -> out           (in == out: in -> tmp -> out)
   //   3 passes: in -> tmp -> out -> out
@@ -388,7 +416,7 @@ int ntt_transform(stark_ctx *ctx, const u32 *in, u32 *out, int log_n, bool inver
   }
   ntt2::PassParams B;
   memset(&B, 0, sizeof B);
-  B.logN = log_n, B.log_tiles = log_n - ntt2::TILE_LOG;
+  B.logN = log_n, B.log_tiles = log_n - tile_log;
   B.roots = roots, B.inverse = d, B.zero = 0;
   for (int k = 0; k < 4; k++) B.w8[k] = ctx->w8_sh[d][k];
   const u32 post_plain = ff::from_mont(post_c);
@@ -396,9 +424,7 @@ int ntt_transform(stark_ctx *ctx, const u32 *in, u32 *out, int log_n, bool inver
   // geometric pre-scale walks: g and g^(N / radix of the FIRST pass's first round)
   wpair pre_g1 = {1, ff::shoup_of(1)}, pre_gj = pre_g1;
   if (pre_mode == SCALE_GEO && log_n >= 13) {
-    int pl[3];
-    ntt2::pass_plan(log_n, pl);
-    const int lr0 = pl[0] % 3 ? pl[0] % 3 : 3;
+    const int lr0 = plan[0] % 3 ? plan[0] % 3 : 3;
     const u32 gj = ff::pow(pre.g, N >> lr0);
     pre_g1 = wpair{pre.g, ff::shoup_of(pre.g)}, pre_gj = wpair{gj, ff::shoup_of(gj)};
   }
@@ -434,9 +460,9 @@ int ntt_transform(stark_ctx *ctx, const u32 *in, u32 *out, int log_n, bool inver
     B.in = src, B.out = dst, B.in_batch = src_batch, B.out_batch = dst_batch;
     B.n_valid = kind == ntt2::FIRST ? n_valid : N;
     B.logS = logS;
-    B.tw_in = ctx->tw_in_sh[d] + (r - 5) * 512;
+    B.tw_in = ctx->tw_in_sh[d] + ntt2::inner_twiddle_offset(r);
     B.otw_tab = ctx->otw_sh[d], B.otw_shift = 16 - (log_n - logS);
-    B.row_tab = ctx->row_sh[d] + (log_n - 13) * 256;
+    B.row_tab = ctx->row_sh[d] + (log_n - 13) * 2048;
     if (kind == ntt2::FIRST) ntt2::fill_first_pass_constants(B, r);
     B.pre_mode = kind == ntt2::FIRST ? pre_mode : (int)SCALE_NONE, B.pre_geo = pre_geo;
     B.post_mode = kind == ntt2::LAST ? post_mode : (int)SCALE_NONE, B.post_const = post_sh, B.post_geo = post_geo, B.post_g1 = post_g1, B.post_gk = post_gk;
@@ -447,6 +473,23 @@ int ntt_transform(stark_ctx *ctx, const u32 *in, u32 *out, int log_n, bool inver
     // compile-time specialisation of the per-element options (see round_compute)
     const int mode = kind == ntt2::FIRST ? ((B.n_valid < N ? 1 : 0) | (B.pre_mode == SCALE_GEO ? 2 : 0))
                                          : (kind == ntt2::LAST ? B.post_mode : 0);
+    if (big) {
+      cudaError_t le = cudaErrorInvalidValue;
+      if (ctx->prof_on) prof_begin(ctx, tag, bytes);
+      const int kmode = (kind == ntt2::FIRST && mode == 2) ? 3 : mode;   // FIRST: pre-scale with or without padding
+#define BIG_CASE(R_, K_, M_) if (r == R_ && kind == K_ && kmode == M_) le = launch_big_pass<R_, K_, M_>(ctx->stream, grid, B); else
+      BIG_CASE(10, ntt2::FIRST, 0) BIG_CASE(10, ntt2::FIRST, 1) BIG_CASE(10, ntt2::FIRST, 3) BIG_CASE(11, ntt2::FIRST, 0)
+      BIG_CASE(11, ntt2::FIRST, 1) BIG_CASE(11, ntt2::FIRST, 3) BIG_CASE(10, ntt2::LAST, 0) BIG_CASE(10, ntt2::LAST, 1)
+      BIG_CASE(10, ntt2::LAST, 2) BIG_CASE(11, ntt2::LAST, 0) BIG_CASE(11, ntt2::LAST, 1) BIG_CASE(11, ntt2::LAST, 2)
+      le = cudaErrorInvalidValue;
+#undef BIG_CASE
+      if (ctx->prof_on) prof_end(ctx);
+      ctx->launches++;
+      if (le != cudaSuccess) rc = stark_fail(ctx, STARK_ERR_CUDA, "NTT pass launch failed: %s", cudaGetErrorString(le));
+      src = dst, src_batch = dst_batch;
+      logS += r;
+      continue;
+    }
 #define NTT2_LAUNCH(R_, K_, M_) LAUNCH_PDL(ctx, tag, bytes, (k_ntt2_pass<R_, K_, M_>), grid, ntt2::NT, B)
 #define NTT2_CASE(R_, K_)                                                                                        \
   if (r == R_ && kind == K_) {                                                                                   \

@@ -38,7 +38,10 @@ constexpr int NT = 128;        // threads per CTA
 #define NTT2_PIN_LAST 0x05
 #define NTT2_PIN_OTHER 0x77
 #endif
-constexpr int PIN_LAST = NTT2_PIN_LAST, PIN_OTHER = NTT2_PIN_OTHER;   // dif_lazy: stages whose sums go to the ALU pipe
+#ifndef NTT2_PIN_LAST_BIG
+#define NTT2_PIN_LAST_BIG 0x07
+#endif
+constexpr int PIN_LAST = NTT2_PIN_LAST, PIN_OTHER = NTT2_PIN_OTHER, PIN_LAST_BIG = NTT2_PIN_LAST_BIG;   // dif_lazy: stages whose sums go to the ALU pipe
 
 struct PassParams {
   const u32 *in;
@@ -62,7 +65,7 @@ struct PassParams {
   wpair post_g1, post_gk;    // LAST, geometric post-scale c g^i: g and g^(N/8) in Shoup form (the walks along a row / down a column block)
   const wpair *otw_tab;      // MIDDLE: w_{2^16}^(+-e), e < 2^16, Shoup form; w_N^(s e) = otw_tab[e << otw_shift]
   int otw_shift;             //         16 - (logN - logS)
-  const wpair *row_tab;      // FIRST: w_N^(+-row), row < 256, Shoup form
+  const wpair *row_tab;      // FIRST: w_N^(+-row), row < 2048, Shoup form
   u32 dpow[8];               // FIRST: w_N^(+-(R/8) k), k < 8, Montgomery form (see round_compute)
 };
 
@@ -104,22 +107,33 @@ struct Plan {
 // round 0 at +0, round 1 at +256, each as [p'][k], k < RAD = the round's radix: entry = w_R^(+-(s' p' k)).  A task needs
 // the RAD - 1 twiddles of ONE p', which are adjacent here: one address computation and RAD/2 128-bit loads instead of
 // RAD - 1 indexed 64-bit loads (each of which cost an IMAD + a 64-bit IMAD.WIDE on the saturated FMA pipe).
+// Radices 2^9 .. 2^11 (the 16384-element tiles of the two-pass plans) follow at inner_twiddle_offset(): three rounds of R pairs.
+constexpr int INNER_TWIDDLE_PAIRS = 2048 + 3 * (512 + 1024 + 2048);
+FF_HD constexpr int inner_twiddle_offset(int logr) {
+  return logr <= 8 ? (logr - 5) * 512 : (logr == 9 ? 2048 : (logr == 10 ? 2048 + 1536 : 2048 + 1536 + 3072));
+}
 inline void fill_inner_twiddles(wpair *out, int inverse) {
-  for (int logr = 5; logr <= 8; logr++) {
+  for (int i = 0; i < INNER_TWIDDLE_PAIRS; i++) out[i] = wpair{1, ff::shoup_of(1)};
+  for (int logr = 5; logr <= 11; logr++) {
     u32 w = ff::pow(ff::GEN, (ff::P - 1) >> logr);   // ff.rs:215-223
     if (inverse) w = ff::inv(w);
     const int b0 = logr % 3, nr = logr / 3 + (b0 ? 1 : 0);
-    wpair *blk = out + (logr - 5) * 512;
-    for (int i = 0; i < 512; i++) blk[i] = wpair{1, ff::shoup_of(1)};
+    wpair *blk = out + inner_twiddle_offset(logr);
+    const int stride = logr <= 8 ? 256 : (1 << logr);
     int logs = 0;
     for (int round = 0; round + 1 < nr; round++) {
       const int lr = (round == 0 && b0) ? b0 : 3;
       const u32 n_pp = 1u << (logr - lr - logs);
-      for (u32 pp = 0; pp < n_pp; pp++)
+      u32 wp = 1;                                     // w^(pp << logs)
+      const u32 wstep = ff::pow(w, 1ull << logs);
+      for (u32 pp = 0; pp < n_pp; pp++) {
+        u32 v = 1;
         for (u32 k = 0; k < (1u << lr); k++) {
-          const u32 v = ff::pow(w, (u64)(pp * k) << logs);
-          blk[256 * round + (pp << lr) + k] = wpair{v, ff::shoup_of(v)};
+          blk[stride * round + (pp << lr) + k] = wpair{v, ff::shoup_of(v)};
+          v = ff::mul(v, wp);
         }
+        wp = ff::mul(wp, wstep);
+      }
       logs += lr;
     }
   }
@@ -128,14 +142,23 @@ inline void fill_inner_twiddles(wpair *out, int inverse) {
 // shared-memory slot (16 bytes = 4 adjacent columns of one row) of (row l, column quad c4).  A 128-bit access is
 // served per quarter-warp, conflict-free when its 8 lanes hit 8 distinct slots mod 8; the XOR keeps that true for the
 // column-fastest (same row) and the row-fastest (8 adjacent rows, same quad) lane mappings used below.
-template <int LOGC4>
+template <int LOGC4, int TL = TILE_LOG>
 FF_HD u32 slot(u32 l, u32 c4) {
   if (LOGC4 >= 3) return (l << LOGC4) + (c4 ^ (l & 7u));
+  if (LOGC4 == 1) {
+    // two quads per row: four rows form one 8-slot group g = l >> 2.  Quarter-warps touch four consecutive rows of one
+    // group (column-fastest), rows 2^LR apart in four or two groups (the strided stores of round 0) or eight consecutive
+    // rows of one quad (row-fastest): bits 1-2 rotate with the group, bit 0 (the quad) flips with its parity.
+    const u32 g = l >> 2, pos = ((l & 3u) << 1) | c4;
+    return (g << 3) + (pos ^ (((g & 3u) << 1) | (g & 1u)));
+  }
   // LOGC4 == 2: two rows form one 8-slot group.  Quarter-warps touch two rows that differ in exactly one of the row
-  // bits 0, 2 or 3 (column-fastest) or eight consecutive rows (row-fastest): the low two slot bits rotate with the
-  // row pair, the half (bit 2) flips with row bits 2 and 3.
+  // bits 0, 2, 3 (column-fastest; also bit 1 in the radix-2 first round of the 16384-element radix-2^10 tiles) or eight
+  // consecutive rows (row-fastest): the low two slot bits rotate with the row pair, the half (bit 2) flips with row
+  // bits 2 and 3 (and 1 for those tiles).
   const u32 sr = l >> 1, pos = ((l & 1u) << 2) | c4;
-  return (sr << 3) + (pos ^ ((sr & 3u) | ((((sr >> 1) ^ (sr >> 2)) & 1u) << 2)));
+  if (TL == TILE_LOG) return (sr << 3) + (pos ^ ((sr & 3u) | ((((sr >> 1) ^ (sr >> 2)) & 1u) << 2)));   // radix 2^8: no bit-1 pattern
+  return (sr << 3) + (pos ^ ((sr & 3u) | (((sr ^ (sr >> 1) ^ (sr >> 2)) & 1u) << 2)));
 }
 
 // radix-2^LR DIF on a[0 .. 2^LR) in [0, 2p); a[pos] ends up holding output bitrev(pos).  The outputs are LAZY, in
@@ -185,9 +208,9 @@ struct TileCtx {
   u32 q0, p;       // col0 = q0 + s p
 };
 
-template <int LOGR>
+template <int LOGR, int TL = TILE_LOG>
 FF_HD TileCtx tile_ctx(const PassParams &A, u32 tile) {
-  constexpr int LOGC = TILE_LOG - LOGR;
+  constexpr int LOGC = TL - LOGR;
   TileCtx T;
   const u32 b = tile >> A.log_tiles, ct = tile & ((1u << A.log_tiles) - 1u);
   T.in = A.in + (u64)b * A.in_batch;
@@ -207,17 +230,17 @@ FF_HD u32 root_n(const PassParams &A, u32 e) {
 
 // MIDDLE: otw[k] = w_N^(+-(s p k)) = w_{N/s}^(+-(p k)), k < R, in Shoup form (per-tile table in shared memory).
 // N/s <= 2^16 for every plan (the first radix is >= 2^(logN - 16)), so the pairs come straight from one table.
-template <int LOGR>
+template <int LOGR, int TL = TILE_LOG>
 FF_HD void fill_outer_table(u32 tid, const PassParams &A, const TileCtx &T, wpair *otw) {
-  for (u32 k = tid; k < (1u << LOGR); k += NT) otw[k] = A.otw_tab[(T.p * k) << A.otw_shift];
+  for (u32 k = tid; k < (1u << LOGR); k += (1u << (TL - 5))) otw[k] = A.otw_tab[(T.p * k) << A.otw_shift];
 }
 
 // task -> (row group u', column quad c4).  Column-fastest: adjacent lanes touch adjacent 16-byte slots of one row.
 // Row-fastest (only the last round of a FIRST pass): adjacent lanes own adjacent output rows, which are adjacent
 // addresses of the transposed store.
-template <int LOGR, int LR, bool ROWFAST>
+template <int LOGR, int LR, bool ROWFAST, int TL = TILE_LOG>
 FF_HD void decode(u32 t, u32 &up, u32 &c4) {
-  constexpr int LOGC4 = TILE_LOG - LOGR - 2;
+  constexpr int LOGC4 = TL - LOGR - 2;
   if (ROWFAST) {
     up = t & ((1u << (LOGR - LR)) - 1u);
     c4 = t >> (LOGR - LR);
@@ -233,18 +256,20 @@ FF_HD void decode(u32 t, u32 &up, u32 &c4) {
 // LAST pass spent 64 of its ~1000 instructions per thread on the post-scale switch):
 //   FIRST:  bit 0 = some inputs are zero padding (n_valid < N), bit 1 = geometric pre-scale
 //   LAST:   the ntt::ScaleMode of the post-scale
-template <int LOGR, int KIND, int ROUND, int MODE>
+template <int LOGR, int KIND, int ROUND, int MODE, int TL = TILE_LOG>
 FF_HD void round_compute(u32 tid, const PassParams &A, const TileCtx &T, const q4 *smem, const wpair *otw, u32 *regs) {
   typedef Plan<LOGR> PL;
   constexpr int LR = PL::lr(ROUND), LOGS = PL::logs(ROUND), RAD = 1 << LR, NTASK = 8 >> LR;
-  constexpr int LOGC4 = TILE_LOG - LOGR - 2;
+  constexpr int LOGC4 = TL - LOGR - 2;
+  constexpr u32 NT = 1u << (TL - 5);               // 32 elements per thread
+  constexpr int TWS = LOGR <= 8 ? 256 : (1 << LOGR);   // pairs per round in the inner-twiddle block (fill_inner_twiddles)
   constexpr bool LASTR = ROUND == PL::NR - 1;
   constexpr bool ROWFAST = LASTR && KIND == FIRST;
   const int logM = A.logN - LOGR;
 #pragma unroll
   for (int i = 0; i < NTASK; i++) {
     u32 up, c4;
-    decode<LOGR, LR, ROWFAST>(tid + (u32)i * NT, up, c4);
+    decode<LOGR, LR, ROWFAST, TL>(tid + (u32)i * NT, up, c4);
     u32 a[4][RAD];
     // FIRST, geometric pre-scale c g^cidx: one table look-up per task, then Shoup walks by g^(N/RAD) from row to row
     // (the RAD inputs of a butterfly are N/RAD apart) and by g along the quad
@@ -277,7 +302,7 @@ FF_HD void round_compute(u32 tid, const PassParams &A, const TileCtx &T, const q
           if (j + 1 < RAD) Gj = ff::canon(ff::shoup_mul(Gj, A.pre_gj.w, A.pre_gj.s));
         }
       } else {
-        v = smem[slot<LOGC4>(l, c4)];
+        v = smem[slot<LOGC4, TL>(l, c4)];
       }
       a[0][j] = v.x, a[1][j] = v.y, a[2][j] = v.z, a[3][j] = v.w;
     }
@@ -285,7 +310,7 @@ FF_HD void round_compute(u32 tid, const PassParams &A, const TileCtx &T, const q
     u32 tw[RAD], step[RAD];   // !LASTR: tw = plain twiddle, step = its Shoup companion
     if (!LASTR) {
       const u32 pp = up >> LOGS;
-      const q4 *tp = reinterpret_cast<const q4 *>(A.tw_in + 256 * ROUND + (pp << LR));   // pairs (2h, 2h + 1)
+      const q4 *tp = reinterpret_cast<const q4 *>(A.tw_in + TWS * ROUND + (pp << LR));   // pairs (2h, 2h + 1)
 #pragma unroll
       for (int h = 0; h < RAD / 2; h++) {
         const q4 t = tp[h];
@@ -337,7 +362,7 @@ FF_HD void round_compute(u32 tid, const PassParams &A, const TileCtx &T, const q
     }
 #pragma unroll
     for (int x = 0; x < 4; x++) {
-      dif_lazy<LR, ((KIND == LAST && MODE == ntt::SCALE_NONE) ? PIN_LAST : PIN_OTHER)>(a[x], A.w8, A.zero);
+      dif_lazy<LR, ((KIND == LAST && MODE == ntt::SCALE_NONE) ? (TL == TILE_LOG ? PIN_LAST : PIN_LAST_BIG) : PIN_OTHER)>(a[x], A.w8, A.zero);
 #pragma unroll
       for (int pos = 0; pos < RAD; pos++) {
         const int k = bitrev<LR>(pos);
@@ -367,17 +392,18 @@ FF_HD void round_compute(u32 tid, const PassParams &A, const TileCtx &T, const q
 }
 
 // Phase B of round ROUND: scatter the register block (shared memory, or HBM in the last round)
-template <int LOGR, int KIND, int ROUND>
+template <int LOGR, int KIND, int ROUND, int TL = TILE_LOG>
 FF_HD void round_store(u32 tid, const PassParams &A, const TileCtx &T, q4 *smem, const u32 *regs) {
   typedef Plan<LOGR> PL;
   constexpr int LR = PL::lr(ROUND), LOGS = PL::logs(ROUND), RAD = 1 << LR, NTASK = 8 >> LR;
-  constexpr int LOGC4 = TILE_LOG - LOGR - 2;
+  constexpr int LOGC4 = TL - LOGR - 2;
+  constexpr u32 NT = 1u << (TL - 5);
   constexpr bool LASTR = ROUND == PL::NR - 1;
   constexpr bool ROWFAST = LASTR && KIND == FIRST;
 #pragma unroll
   for (int i = 0; i < NTASK; i++) {
     u32 up, c4;
-    decode<LOGR, LR, ROWFAST>(tid + (u32)i * NT, up, c4);
+    decode<LOGR, LR, ROWFAST, TL>(tid + (u32)i * NT, up, c4);
     const u32 qp = up & ((1u << LOGS) - 1u), pp = up >> LOGS;
     // MIDDLE / LAST output rows of one task are 2^(LOGS + logS) elements apart: a running 64-bit pointer (two ALU adds per
     // store) instead of an address product per store on the FMA pipe
@@ -390,7 +416,7 @@ FF_HD void round_store(u32 tid, const PassParams &A, const TileCtx &T, q4 *smem,
       const u32 *r = regs + i * 4 * RAD + k;
       if (!LASTR) {
         q4 v = {r[0], r[RAD], r[2 * RAD], r[3 * RAD]};
-        smem[slot<LOGC4>(l, c4)] = v;
+        smem[slot<LOGC4, TL>(l, c4)] = v;
       } else if (KIND == FIRST) {
         // Y[R u + k]: the tile's output is one contiguous block; scalar stores, coalesced along the rows
         u32 *dst = T.out + (((u64)T.col0 + 4u * c4) << LOGR) + l;

@@ -28,13 +28,13 @@ static void init() {
       const u32 w = ff::from_mont(ntt::root_pow(T, idx));
       g_tw[d][i] = wpair{w, ff::shoup_of(w)};
     }
-    g_twin[d].resize(4 * 512);
+    g_twin[d].resize(INNER_TWIDDLE_PAIRS);
     fill_inner_twiddles(g_twin[d].data(), d);
     // mirrors k_shoup_roots in ntt.cu
-    g_otw[d].resize(1u << 16), g_row[d].resize(11 * 256);
+    g_otw[d].resize(1u << 16), g_row[d].resize(11 * 2048);
     for (int tab = 0; tab < 2; tab++)
-      for (u32 i = 0; i < (tab ? 11u * 256 : 1u << 16); i++) {
-        u32 idx = tab ? (i & 255u) << (10 - (i >> 8)) : i << 7;
+      for (u32 i = 0; i < (tab ? 11u * 2048 : 1u << 16); i++) {
+        u32 idx = tab ? (i & 2047u) << (10 - (i >> 11)) : i << 7;
         if (d) idx = ((1u << 23) - idx) & ((1u << 23) - 1u);
         const u32 w = ff::from_mont(ntt::root_pow(T, idx));
         (tab ? g_row[d] : g_otw[d])[i] = wpair{w, ff::shoup_of(w)};
@@ -47,38 +47,47 @@ static void init() {
 
 static long g_range_viol = 0;
 
-template <int LOGR, int KIND, int MODE>
+template <int LOGR, int KIND, int MODE, int TL = TILE_LOG>
 static void run_pass(const PassParams &A, u32 grid) {
   typedef Plan<LOGR> PL;
-  std::vector<q4> tile(1 << (TILE_LOG - 2));
+  constexpr u32 NTH = 1u << (TL - 5);
+  std::vector<q4> tile(1 << (TL - 2));
   std::vector<wpair> otw(1 << LOGR);
-  std::vector<u32> regs((size_t)NT * 32);
+  std::vector<u32> regs((size_t)NTH * 32);
   for (u32 blk = 0; blk < grid; blk++) {
-    const TileCtx T = tile_ctx<LOGR>(A, blk);
-    if (KIND == MIDDLE) for (u32 tid = 0; tid < NT; tid++) fill_outer_table<LOGR>(tid, A, T, otw.data());
-    for (u32 tid = 0; tid < NT; tid++) round_compute<LOGR, KIND, 0, MODE>(tid, A, T, tile.data(), otw.data(), &regs[tid * 32]);
-    for (u32 tid = 0; tid < NT; tid++) round_store<LOGR, KIND, 0>(tid, A, T, tile.data(), &regs[tid * 32]);
-    if (PL::NR == 3) {
-      for (u32 tid = 0; tid < NT; tid++) round_compute<LOGR, KIND, 1, MODE>(tid, A, T, tile.data(), otw.data(), &regs[tid * 32]);
-      for (u32 tid = 0; tid < NT; tid++) round_store<LOGR, KIND, 1>(tid, A, T, tile.data(), &regs[tid * 32]);
+    const TileCtx T = tile_ctx<LOGR, TL>(A, blk);
+    if (KIND == MIDDLE) for (u32 tid = 0; tid < NTH; tid++) fill_outer_table<LOGR, TL>(tid, A, T, otw.data());
+    for (u32 tid = 0; tid < NTH; tid++) round_compute<LOGR, KIND, 0, MODE, TL>(tid, A, T, tile.data(), otw.data(), &regs[tid * 32]);
+    for (u32 tid = 0; tid < NTH; tid++) round_store<LOGR, KIND, 0, TL>(tid, A, T, tile.data(), &regs[tid * 32]);
+    if constexpr (PL::NR >= 3) {
+      for (u32 tid = 0; tid < NTH; tid++) round_compute<LOGR, KIND, 1, MODE, TL>(tid, A, T, tile.data(), otw.data(), &regs[tid * 32]);
+      for (u32 tid = 0; tid < NTH; tid++) round_store<LOGR, KIND, 1, TL>(tid, A, T, tile.data(), &regs[tid * 32]);
+    }
+    if constexpr (PL::NR == 4) {
+      for (u32 tid = 0; tid < NTH; tid++) round_compute<LOGR, KIND, 2, MODE, TL>(tid, A, T, tile.data(), otw.data(), &regs[tid * 32]);
+      for (u32 tid = 0; tid < NTH; tid++) round_store<LOGR, KIND, 2, TL>(tid, A, T, tile.data(), &regs[tid * 32]);
     }
     for (auto &v : tile) if (v.x >= ff::P2 || v.y >= ff::P2 || v.z >= ff::P2 || v.w >= ff::P2) g_range_viol++;
-    for (u32 tid = 0; tid < NT; tid++) round_compute<LOGR, KIND, PL::NR - 1, MODE>(tid, A, T, tile.data(), otw.data(), &regs[tid * 32]);
-    for (u32 tid = 0; tid < NT; tid++) round_store<LOGR, KIND, PL::NR - 1>(tid, A, T, tile.data(), &regs[tid * 32]);
+    for (u32 tid = 0; tid < NTH; tid++) round_compute<LOGR, KIND, PL::NR - 1, MODE, TL>(tid, A, T, tile.data(), otw.data(), &regs[tid * 32]);
+    for (u32 tid = 0; tid < NTH; tid++) round_store<LOGR, KIND, PL::NR - 1, TL>(tid, A, T, tile.data(), &regs[tid * 32]);
   }
 }
+static bool g_big = false;   // the two-pass plans on 16384-element tiles (STARK_NTT_BIG in ntt.cu)
 
 // mirrors the N >= 2^13 branch of ntt_transform() in ntt.cu
 static void transform(const u32 *in, u32 *out, int log_n, int d, u32 batch, u64 n_valid, int post_mode, u32 post_c,
                       GeoTables post_geo, int pre_mode, GeoTables pre_geo) {
   const u64 N = 1ull << log_n;
   int plan[3];
-  const int n_pass = pass_plan(log_n, plan);
+  int n_pass = pass_plan(log_n, plan);
+  const bool big = g_big && log_n >= 20 && log_n <= 22;
+  if (big) plan[0] = (log_n + 1) / 2, plan[1] = log_n / 2, plan[2] = 0, n_pass = 2;
+  const int tile_log = big ? 14 : TILE_LOG;
   std::vector<u32> tmp((size_t)batch * N);
   const bool need_tmp = n_pass == 3 || in == out;
   PassParams B;
   memset(&B, 0, sizeof B);
-  B.logN = log_n, B.log_tiles = log_n - TILE_LOG;
+  B.logN = log_n, B.log_tiles = log_n - tile_log;
   B.roots = {g_lo.data(), g_hi.data()}, B.inverse = d;
   for (int k = 0; k < 4; k++) B.w8[k] = g_w8[d][k];
   const u32 grid = batch << B.log_tiles;
@@ -91,9 +100,9 @@ static void transform(const u32 *in, u32 *out, int log_n, int d, u32 batch, u64 
     B.in = src, B.out = dst, B.in_batch = N, B.out_batch = N;
     B.n_valid = kind == FIRST ? n_valid : N;
     B.logS = logS;
-    B.tw_in = g_twin[d].data() + (r - 5) * 512;
+    B.tw_in = g_twin[d].data() + inner_twiddle_offset(r);
     B.otw_tab = g_otw[d].data(), B.otw_shift = 16 - (log_n - logS);
-    B.row_tab = g_row[d].data() + (log_n - 13) * 256;
+    B.row_tab = g_row[d].data() + (log_n - 13) * 2048;
     if (kind == FIRST) fill_first_pass_constants(B, r);
     B.pre_mode = kind == FIRST ? pre_mode : 0, B.pre_geo = pre_geo;
     B.post_mode = kind == LAST ? post_mode : 0, B.post_const = wpair{ff::from_mont(post_c), ff::shoup_of(ff::from_mont(post_c))}, B.post_geo = post_geo;
@@ -103,6 +112,8 @@ static void transform(const u32 *in, u32 *out, int log_n, int d, u32 batch, u64 
       const u32 gj = ff::pow(g, N >> lr0);
       B.pre_g1 = B.post_g1, B.pre_gj = wpair{gj, ff::shoup_of(gj)}; }
     const int mode = kind == FIRST ? ((B.n_valid < N ? 1 : 0) | (B.pre_mode == ntt::SCALE_GEO ? 2 : 0)) : (kind == LAST ? B.post_mode : 0);
+#define BIGCASE(R_, K_) if (big && r == R_ && kind == K_) { if (mode == 0) run_pass<R_, K_, 0, 14>(B, grid); else if (mode == 1) run_pass<R_, K_, 1, 14>(B, grid); else if (K_ == FIRST) run_pass<R_, K_, 3, 14>(B, grid); else run_pass<R_, K_, 2, 14>(B, grid); } else
+    BIGCASE(10, FIRST) BIGCASE(11, FIRST) BIGCASE(10, LAST) BIGCASE(11, LAST)
 #define CASE(R_, K_) if (r == R_ && kind == K_) { if (K_ == MIDDLE || mode == 0) run_pass<R_, K_, 0>(B, grid); else if (mode == 1) run_pass<R_, K_, 1>(B, grid); else if (K_ == FIRST) run_pass<R_, K_, 3>(B, grid); else run_pass<R_, K_, 2>(B, grid); } else
     CASE(6, FIRST) CASE(7, FIRST) CASE(8, FIRST) CASE(6, MIDDLE) CASE(7, MIDDLE) CASE(8, MIDDLE)
     CASE(5, LAST) CASE(6, LAST) CASE(7, LAST) CASE(8, LAST) abort();
@@ -123,27 +134,29 @@ static void ref_ntt(std::vector<u64> &a, u64 root) {
 }
 
 // bank conflicts: for every round's load / store pattern, per quarter-warp the 8 slots must be distinct mod 8
-template <int LOGR, int KIND, int ROUND>
+template <int LOGR, int KIND, int ROUND, int TL = TILE_LOG>
 static long conflicts() {
   typedef Plan<LOGR> PL;
-  constexpr int LR = PL::lr(ROUND), LOGS = PL::logs(ROUND), RAD = 1 << LR, NTASK = 8 >> LR, LOGC4 = TILE_LOG - LOGR - 2;
+  constexpr int LR = PL::lr(ROUND), LOGS = PL::logs(ROUND), RAD = 1 << LR, NTASK = 8 >> LR, LOGC4 = TL - LOGR - 2;
+  constexpr u32 NT = 1u << (TL - 5);
   constexpr bool LASTR = ROUND == PL::NR - 1, ROWFAST = LASTR && KIND == FIRST;
   long bad = 0;
   for (int i = 0; i < NTASK; i++) for (u32 qw = 0; qw < NT / 8; qw++) for (int j = 0; j < RAD; j++) {
     u32 seenL = 0, seenS = 0;
     for (u32 lane = 0; lane < 8; lane++) {
-      u32 up, c4; decode<LOGR, LR, ROWFAST>(qw * 8 + lane + i * NT, up, c4);
-      if (ROUND > 0) seenL |= 1u << (slot<LOGC4>(up + ((u32)j << (LOGR - LR)), c4) & 7);
-      if (!LASTR) { u32 qp = up & ((1u << LOGS) - 1), pp = up >> LOGS; seenS |= 1u << (slot<LOGC4>(qp + (((pp << LR) + j) << LOGS), c4) & 7); }
+      u32 up, c4; decode<LOGR, LR, ROWFAST, TL>(qw * 8 + lane + i * NT, up, c4);
+      if (ROUND > 0) seenL |= 1u << (slot<LOGC4, TL>(up + ((u32)j << (LOGR - LR)), c4) & 7);
+      if (!LASTR) { u32 qp = up & ((1u << LOGS) - 1), pp = up >> LOGS; seenS |= 1u << (slot<LOGC4, TL>(qp + (((pp << LR) + j) << LOGS), c4) & 7); }
     }
     if (ROUND > 0 && seenL != 0xff) bad++;
     if (!LASTR && seenS != 0xff) bad++;
   }
   return bad;
 }
-template <int LOGR, int KIND> static long conflicts_all() {
-  long b = conflicts<LOGR, KIND, 0>() + conflicts<LOGR, KIND, Plan<LOGR>::NR - 1>();
-  if (Plan<LOGR>::NR == 3) b += conflicts<LOGR, KIND, 1>();
+template <int LOGR, int KIND, int TL = TILE_LOG> static long conflicts_all() {
+  long b = conflicts<LOGR, KIND, 0, TL>() + conflicts<LOGR, KIND, Plan<LOGR>::NR - 1, TL>();
+  if constexpr (Plan<LOGR>::NR >= 3) b += conflicts<LOGR, KIND, 1, TL>();
+  if constexpr (Plan<LOGR>::NR == 4) b += conflicts<LOGR, KIND, 2, TL>();
   return b;
 }
 
@@ -155,14 +168,20 @@ int main(int argc, char **argv) {
             conflicts_all<6, LAST>() + conflicts_all<7, LAST>() + conflicts_all<8, LAST>();
   printf("bank-conflicted quarter-warp accesses: %ld\n", bc);
   if (bc) fails++;
+  const long bc_big = conflicts_all<10, FIRST, 14>() + conflicts_all<11, FIRST, 14>() + conflicts_all<10, LAST, 14>() +
+                      conflicts_all<11, LAST, 14>();
+  printf("bank-conflicted quarter-warp accesses (16384-element tiles): %ld\n", bc_big);
+  if (bc_big) fails++;
+  g_big = argc > 2 && atoi(argv[2]) != 0;
+  int min_log = g_big ? 20 : 13;
   // geometric table for scale tests: c * g^i
   const u32 g = 3, c = ff::inv(1u << 10);
   std::vector<u32> glo(4096), ghi(4096);
   for (u32 i = 0; i < 4096; i++) glo[i] = ff::canon(ff::mont_mul(ff::mont_pow(ff::to_mont(g), i), ff::to_mont(c)));
   for (u32 i = 0; i < 4096; i++) ghi[i] = ff::mont_pow(ff::to_mont(g), (u64)i << 12);
   GeoTables G = {glo.data(), ghi.data()};
-  for (int log_n = 13; log_n <= max_log; log_n++) for (int d = 0; d < 2; d++) for (int mode = 0; mode < 4; mode++) {
-    if (mode >= 2 && log_n > 16 && log_n != max_log) continue;
+  for (int log_n = min_log; log_n <= max_log; log_n++) for (int d = 0; d < 2; d++) for (int mode = 0; mode < 4; mode++) {
+    if (mode >= 2 && log_n > 16 && log_n != max_log && !g_big) continue;
     const u64 N = 1ull << log_n; const u32 batch = log_n <= 15 ? 2 : 1;
     std::vector<u32> in(batch * N), out(batch * N);
     u64 s = 12345 + log_n;

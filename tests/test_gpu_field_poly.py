@@ -262,3 +262,20 @@ def test_batched_transforms_larger_than_l2(ctx, oracle):
     for c in (0, 7, n_cols - 1):
         assert np.array_equal(out[c], oracle.fast_lde(cols.reshape(n_cols, -1)[c], log_n, 2, 3))
 
+
+def test_two_pass_big_tile_plans(oracle, S, monkeypatch):
+    """STARK_NTT_BIG=1 (read when a context is created): 2^20 .. 2^22 run as two passes on 16384-element tiles -- an
+    experiment that is off by default (slower) but must stay bit-exact"""
+    monkeypatch.setenv("STARK_NTT_BIG", "1")
+    c = S.Context(0)
+    try:
+        for log_n in (20, 21, 22):
+            col = rf(log_n, 1 << log_n)
+            ev = c.poly_eval_coset(col, 3, log_n)
+            assert np.array_equal(ev, oracle.fast_eval_coset(col, 3, log_n))
+            assert np.array_equal(c.poly_interpolate_coset(ev, 3, log_n), col)
+        col = rf(5, 1 << 20)
+        assert np.array_equal(c.lde(col, 2, 3)[0], oracle.fast_lde(col, 20, 2, 3))
+    finally:
+        c.close()
+

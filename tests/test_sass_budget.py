@@ -15,11 +15,11 @@ OBJ = os.path.join(ROOT, "stark-rs_b200", "build", "ntt.o")
 
 # kernel -> (max instructions, max FMA slots, max ALU-pipe instructions) per thread = per 32 elements
 BUDGET = {
-    "k_ntt2_pass<8, 0, 0>": (1330, 780, 620),    # FIRST, radix 2^8 (four-step twiddles)
-    "k_ntt2_pass<7, 1, 0>": (1000, 542, 465),    # MIDDLE, radix 2^7
-    "k_ntt2_pass<7, 2, 0>": (950, 480, 465),     # LAST, radix 2^7, no post-scale
-    "k_ntt2_pass<7, 2, 1>": (1010, 540, 495),    # LAST with the constant post-scale (iNTT)
-    "k_ntt2_pass<7, 2, 2>": (1190, 705, 570),    # LAST with the geometric post-scale (coset interpolation, LDE)
+    "k_ntt2_pass<8, 0, 0, 12>": (1330, 780, 620),    # FIRST, radix 2^8 (four-step twiddles)
+    "k_ntt2_pass<7, 1, 0, 12>": (1000, 542, 465),    # MIDDLE, radix 2^7
+    "k_ntt2_pass<7, 2, 0, 12>": (950, 480, 465),     # LAST, radix 2^7, no post-scale
+    "k_ntt2_pass<7, 2, 1, 12>": (1010, 540, 495),    # LAST with the constant post-scale (iNTT)
+    "k_ntt2_pass<7, 2, 2, 12>": (1190, 705, 570),    # LAST with the geometric post-scale (coset interpolation, LDE)
 }
 
 
@@ -30,7 +30,7 @@ def test_ntt_pass_instruction_budgets():
     seen = {}
     name = None
     for line in out.splitlines():
-        m = re.match(r"void (k_ntt2_pass<\d+, \d+, \d+>)", line)
+        m = re.match(r"void (k_ntt2_pass<\d+, \d+, \d+, \d+>)", line)
         if m:
             name = m.group(1)
             continue
