@@ -19,7 +19,7 @@ use crate::trace::Trace;
 
 const P: u64 = 998244353; // 119 * 2^23 + 1
 
-/// BASELINE config 1: Fibonacci trace column -> LDE (blowup 4, offset 3) -> Fri::prove -> proof bytes.
+/// BASELINE config 1: Fibonacci trace column -> LDE (blowup 4, offset 3) -> Fri::prove -> proof bytes -> Fri::verify.
 fn main() {
     let field = FiniteField::new(P);
     let rows = 64usize;
@@ -32,4 +32,11 @@ fn main() {
     let code: Vec<_> = codeword.iter().map(|&v| field.new_element(v)).collect();
     let top = fri.prove(code, &mut transcript, &mut stream);
     println!("proof: {} bytes, top-level indices {:?}", stream.serialize().len(), top);
+    // the reference's own test flow (fri.rs:563-570): a fresh transcript, verify, and the opened points lie on the codeword
+    let mut points = Vec::new();
+    let ok = fri.verify(&mut stream, &mut FiatShamir::new(), &mut points);
+    assert!(ok && points.iter().all(|(i, v)| codeword[*i] == v.value));
+    // the same statement straight from the trace container (row-major i128 rows): identical proof bytes
+    let (roots, proof) = Trace::fibonacci(rows).prove(2, offset.value, 8);
+    println!("verified: {}, {} column root(s), {} proof bytes from Trace::prove", ok, roots.len(), proof.len());
 }
