@@ -36,7 +36,7 @@ def test_header_cites_reference():
     text = open(os.path.join(ROOT, "include", "stark_b200.h")).read()
     for cite in ["ff.rs:138", "mul.rs:6-29", "eval.rs:16-21", "interpolate.rs:6-44", "hash.rs:7-30",
                  "merkle.rs:11-38", "merkle.rs:67-80", "fri.rs:57-91", "fri.rs:105-156", "fri.rs:250-311",
-                 "stream.rs:35-64"]:
+                 "stream.rs:35-64", "fri.rs:313-505", "merkle.rs:82-97", "trace.rs:4-34"]:
         assert cite in text, cite
 
 
@@ -72,6 +72,21 @@ def test_sample_indices_host(S, oracle):
         S.fri_sample_indices(seed, 64, 4, 9)
     with pytest.raises(S.StarkPanic, match="cannot sample more indices"):
         S.fri_sample_indices(seed, 64, 4, 5)
+
+
+def test_verify_reason_texts_are_the_references(S):
+    """stark_fri_verify_reason returns the `println!` lines of fri.rs:313-505 -- the strings the oracle's verifier
+    reports too (oracle/stark_oracle.c fri_verify), so GPU and oracle verdicts can be compared textually"""
+    lib = ctypes.CDLL(S.lib_path)
+    lib.stark_fri_verify_reason.restype = ctypes.c_char_p
+    texts = [lib.stark_fri_verify_reason(ctypes.c_uint32(i)).decode() for i in range(18)]
+    assert texts[0] == "" and texts[17] == "unknown"
+    ref = open("/root/reference/src/fri.rs").read() if os.path.exists("/root/reference/src/fri.rs") else None
+    port = open(os.path.join(ROOT, "oracle", "stark_oracle.c")).read()
+    for t in texts[1:17]:
+        assert '"%s"' % t in port, t
+        if ref is not None:
+            assert '"%s"' % t in ref, t
 
 
 def test_no_cpu_fallback(S):
