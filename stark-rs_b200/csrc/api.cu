@@ -223,6 +223,7 @@ static int ctx_create(int device, cudaStream_t borrowed, bool borrow, stark_ctx 
   if (cudaMalloc(&ctx->flag, 16) != cudaSuccess || cudaMallocHost(&ctx->h_flag, 16) != cudaSuccess)
     rc = stark_fail(nullptr, STARK_ERR_OOM, "context allocation failed");
   if (rc == STARK_OK && cudaMemset(ctx->flag, 0, 16) != cudaSuccess) rc = stark_fail(nullptr, STARK_ERR_CUDA, "context initialisation failed");
+  ctx->climb_counter = ctx->flag + 1;
   if (rc == STARK_OK) rc = ntt_init(ctx);
   if (rc == STARK_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess)
     rc = stark_fail(nullptr, STARK_ERR_CUDA, "context initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));

@@ -39,7 +39,8 @@ struct stark_ctx {
   ntt::wpair *row_sh[2];   // w_{2^logN}^(+-row), row < 2048, at [(logN - 13) * 2048 + row], logN = 13..23 (FIRST pass)
   GeoCacheEntry geo[8];
   u64 geo_stamp;
-  u32 *flag;       // device int used by validation kernels
+  u32 *flag;       // four device ints: [0], [2] validation flags, [1], [3] last-CTA tickets of the Merkle climb kernel
+  u32 *climb_counter;   // the ticket the next climb launch uses: flag + 1, or flag + 3 for work queued on a side stream
   u32 *h_flag;     // pinned host mirror
   u64 launches;    // kernels launched through this context (bench.py "gpu_launches")
   // side streams for batched transforms larger than L2 (ntt.cu: column groups run all passes back to back, a few groups
@@ -154,6 +155,7 @@ struct ScaleSpec {
   u32 g;      // canonical base (SCALE_GEO)
 };
 int ntt_init(stark_ctx *ctx);
+int side_streams(stark_ctx *ctx, int n);   // ntt.cu: make sure ctx->side[0 .. n) and their events exist
 void ntt_destroy(stark_ctx *ctx);
 int geo_tables(stark_ctx *ctx, u32 g, u32 c, u64 max_index, ntt::GeoTables *out);
 // batched transform of length 2^log_n: in/out device u32 (canonical), n_valid = leading input elements that are

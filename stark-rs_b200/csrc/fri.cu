@@ -874,8 +874,17 @@ int stark_prove_trace_dev(stark_ctx *ctx, const stark_buf *cols, uint32_t n_cols
   int rc = lde_dev(ctx, cols->ptr, n_cols, log_n, log_blowup, (u32)offset, lde);
   // commitments of columns 1.. (column 0's tree is built inside Fri::commit, fri.rs:118-127, and its root is
   // the first proof object)
+  // They are throughput work that does not depend on the FRI, whose rounds are a latency-bound chain: queue
+  // them on a side stream so that they fill the SMs the FRI leaves idle.  The climb kernel's last-CTA ticket is per stream.
   std::vector<stark_tree *> trees;
   if (rc == STARK_OK && n_cols > 1) rc = dev_alloc(ctx, (void **)&d_roots, 32 * (size_t)n_cols);
+  cudaStream_t main_stream = ctx->stream;
+  bool forked = false;
+  if (rc == STARK_OK && n_cols > 1 && !ctx->prof_on && side_streams(ctx, 1) == STARK_OK) {
+    cudaEventRecord(ctx->fork_ev, main_stream);
+    cudaStreamWaitEvent(ctx->side[0], ctx->fork_ev, 0);
+    ctx->stream = ctx->side[0], ctx->climb_counter = ctx->flag + 3, forked = true;
+  }
   for (u32 c = 1; c < n_cols && rc == STARK_OK; c++) {
     stark_tree *t = nullptr;
     rc = merkle_build_from_dev_values(ctx, lde + (size_t)c * N, N, 1, 1, 0, &t);
@@ -886,14 +895,21 @@ int stark_prove_trace_dev(stark_ctx *ctx, const stark_buf *cols, uint32_t n_cols
         rc = stark_fail(ctx, STARK_ERR_CUDA, "D2D copy failed");
     }
   }
-  if (rc == STARK_OK && n_cols > 1 && column_roots &&
-      cudaMemcpyAsync(column_roots + 32, d_roots + 32, 32 * (size_t)(n_cols - 1), cudaMemcpyDeviceToHost, ctx->stream) !=
-          cudaSuccess)
-    rc = stark_fail(ctx, STARK_ERR_CUDA, "D2H copy failed");
+  if (forked) {
+    cudaEventRecord(ctx->side_done[0], ctx->side[0]);
+    ctx->stream = main_stream, ctx->climb_counter = ctx->flag + 1;
+  }
   const u32 omega = ff::pow(ff::GEN, (ff::P - 1) >> (log_n + log_blowup));  // prim_nth_root(N), ff.rs:215-223
   if (rc == STARK_OK)
     rc = fri_prove_dev(ctx, lde, N, N, (u32)offset, omega, 1u << log_blowup, nq, nullptr, 0, proof, proof_cap, proof_len,
                        nullptr);
+  if (forked) cudaStreamWaitEvent(main_stream, ctx->side_done[0], 0);   // join (also on an error path: the trees are freed below)
+  if (rc == STARK_OK && n_cols > 1 && column_roots &&
+      cudaMemcpyAsync(column_roots + 32, d_roots + 32, 32 * (size_t)(n_cols - 1), cudaMemcpyDeviceToHost, ctx->stream) !=
+          cudaSuccess)
+    rc = stark_fail(ctx, STARK_ERR_CUDA, "D2H copy failed");
+  if (n_cols > 1 && cudaStreamSynchronize(ctx->stream) != cudaSuccess && rc == STARK_OK)
+    rc = stark_fail(ctx, STARK_ERR_CUDA, "column commitments failed");
   if (rc == STARK_OK && column_roots) memcpy(column_roots, proof + 1, 32);  // first object = root of column 0
   for (stark_tree *t : trees) stark_merkle_free(t);
   dev_free(ctx, lde), dev_free(ctx, d_roots);

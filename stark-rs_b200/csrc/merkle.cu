@@ -220,7 +220,7 @@ int merkle_climb_dev(stark_ctx *ctx, u8 *nodes, size_t n, const TranscriptArgs *
     const u32 chunk = m > ((size_t)1 << 17) ? 1024u : 512u, chunk_levels = chunk == 1024u ? 10u : 9u;
     const size_t ctas = m / chunk;
     LAUNCH_PDL(ctx, "merkle_climb", 96ull * (m - 1), k_merkle_climb<256>, (u32)ctas, 256, nodes, n, level, chunk, chunk_levels,
-               tr ? *tr : none, ctx->flag + 1);
+               tr ? *tr : none, ctx->climb_counter);
   } else if (m > 1) {
     u32 levels = 0;
     for (size_t c = m; c > 1; c >>= 1) levels++;

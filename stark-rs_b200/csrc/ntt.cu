@@ -132,7 +132,7 @@ static void l2_window(stark_ctx *ctx, cudaStream_t st, const void *base, size_t 
   cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v);
 }
 // lazily created side streams + events
-static int side_streams(stark_ctx *ctx, int n) {
+int side_streams(stark_ctx *ctx, int n) {
   if (!ctx->fork_ev) CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
   while (ctx->n_side < n) {
     CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->side[ctx->n_side], cudaStreamNonBlocking));
