@@ -45,7 +45,12 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 stream = torch.cuda.Stream()
 ctx = S.Context(local, stream=stream.cuda_stream)
-b = D.CudaBackend(ctx, "cuda:%d" % local)
+# second context on a second stream: config 4 builds a group's tree there while the next group's LDE runs (distributed.py)
+aux_stream = torch.cuda.Stream()
+aux_ctx = S.Context(local, stream=aux_stream.cuda_stream)
+aux_b = D.CudaBackend(aux_ctx, "cuda:%d" % local)
+aux_b.stream = aux_stream
+b = D.CudaBackend(ctx, "cuda:%d" % local, aux=None if os.environ.get("STARK_NO_OVERLAP") else aux_b)
 comm = D.Comm()
 P = S.P
 
@@ -164,6 +169,7 @@ with torch.cuda.stream(stream):
             print(json.dumps({"config": "cfg4 LDE + Merkle, 64 columns in 8 groups of 8, blowup 2", "log_n": log_n,
                               "n_gpus": world, "ms": ms, "lde_out_elements_per_s": ng * gw * (n << lb) / (ms * 1e-3),
                               "commitment": commitment.hex()}), flush=True)
+aux_ctx.close()
 ctx.close()
 if world > 1:
     dist.destroy_process_group()

@@ -59,9 +59,13 @@ class CudaBackend:
     """The B200 path: tensors are torch.int32 CUDA tensors holding canonical u32 field elements; all work is queued on
     the context's stream (create the Context on a torch stream and run under `torch.cuda.stream(...)`)."""
 
-    def __init__(self, ctx, device):
+    def __init__(self, ctx, device, aux=None):
+        """aux: optional second CudaBackend whose Context lives on ANOTHER torch stream (`aux.stream`); lde_commit_sharded
+        then builds a group's Merkle tree there while the next group's LDE runs on this one (the NTT is bound by the
+        FMA-heavy pipe, the hashing by the ALU pipe: together they fill both)."""
         from . import api
         self.api, self.ctx, self.device = api, ctx, torch.device(device)
+        self.aux, self.stream = aux, None
 
     def _buf(self, t, off=0, n=None):
         n = t.numel() - off if n is None else n
@@ -385,12 +389,27 @@ def lde_commit_sharded(backend, comm, cols_of_group, n_groups, group_width, log_
     owned = list(range(g, n_groups, G))
     mine = backend.new_hashes(len(owned))
     ldes = {}
+    aux = getattr(backend, "aux", None)
+    main_stream = torch.cuda.current_stream() if aux is not None else None
+    if aux is not None:
+        mine.record_stream(aux.stream)
     for j, k in enumerate(owned):
         lde = backend.lde(cols_of_group(k), group_width, log_n, log_blowup, offset)
-        t = backend.subtree(lde, 0, N, group_width)
-        mine[j].copy_(t.root)
-        t.free()
+        if aux is None:
+            t = backend.subtree(lde, 0, N, group_width)
+            mine[j].copy_(t.root)
+            t.free()
+        else:
+            # the tree of group k on the auxiliary stream, overlapping the LDE of the next group on this one
+            aux.stream.wait_stream(main_stream)
+            lde.record_stream(aux.stream)
+            with torch.cuda.stream(aux.stream):
+                t = aux.subtree(lde, 0, N, group_width)
+                mine[j].copy_(t.root)
+                t.free()
         ldes[k] = lde
+    if aux is not None:
+        main_stream.wait_stream(aux.stream)
     allr = backend.new_hashes(n_groups).view(G, len(owned), 32)
     comm.all_gather_rows(allr, mine)
     # rank-major (g, j) -> group k = g + j G

@@ -84,6 +84,25 @@ def test_lde_commit_world1(backend, oracle):
     assert commitment == oracle.merkle_commit(np.frombuffer(b"".join(want), dtype=np.uint8).reshape(ng, 32))
 
 
+def test_lde_commit_overlapped_trees(backend, oracle, S):
+    """the same commitment when every group's tree is built on an auxiliary context / stream while the next LDE runs"""
+    from stark_rs_b200 import distributed as D
+    log_n, lb, ng, gw = 12, 1, 4, 8
+    cols = lambda k: backend.upload(np.concatenate([oracle.splitmix64(77 * k + c, 1 << log_n) for c in range(gw)]))
+    plain = D.lde_commit_sharded(backend, D.Comm(), cols, ng, gw, log_n, lb, 3)
+    aux_stream = torch.cuda.Stream()
+    aux_ctx = S.Context(0, stream=aux_stream.cuda_stream)
+    try:
+        aux = D.CudaBackend(aux_ctx, "cuda:0")
+        aux.stream = aux_stream
+        both = D.CudaBackend(backend.ctx, "cuda:0", aux=aux)
+        got = D.lde_commit_sharded(both, D.Comm(), cols, ng, gw, log_n, lb, 3)
+        torch.cuda.synchronize()
+        assert got[0] == plain[0] and got[1].tobytes() == plain[1].tobytes()
+    finally:
+        aux_ctx.close()
+
+
 def test_fold_bcast_writes_every_replica(backend, oracle):
     """k_fri_fold_bcast with the P2P store path on one GPU: three 'replicas' (plain device buffers standing in for the
     peers' mapped memory) must all receive the folded range, equal to the oracle's fold."""
