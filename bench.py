@@ -306,6 +306,15 @@ def run_ours(a):
         "ms_per_step_profiled": ms_prof / a.steps, "hash_latency_cycles": ctx.hash_latency(), "int_peak": ipk,
     }
 
+    # the NTT / LDE half of the metric on its own: the six pass launches of the step (iNTT of the trace + zero-padded NTT on
+    # the 4x domain), from the per-kernel CUDA events of the profiled pass
+    lde_ms = sum(v["ms_per_step"] for k, v in kernels.items() if k.startswith("ntt_"))
+    if lde_ms > 0:
+        line["lde"] = {"ms_per_step": lde_ms, "out_elems_per_s": a.cols * N / (lde_ms * 1e-3),
+                       "algorithmic_bytes_per_step": a.cols * (20 + 12 * ef) * n,
+                       "hbm_frac": a.cols * (20 + 12 * ef) * n / (lde_ms * 1e-3) / 1e9 / hbm_peak,
+                       "note": "one column is L2-resident and latency-bound at this size (256 / 1024 CTAs per launch); the "
+                               "batched figures are in profiles/r1z3_ntt_micro_batch16.jsonl"}
     # Fri::verify of the timed proof on the device (stark_fri_verify; outside the timed region)
     try:
         t0 = time.perf_counter()
