@@ -463,7 +463,6 @@ int ntt_transform(stark_ctx *ctx, const u32 *in, u32 *out, int log_n, bool inver
     B.tw_in = ctx->tw_in_sh[d] + ntt2::inner_twiddle_offset(r);
     B.otw_tab = ctx->otw_sh[d], B.otw_shift = 16 - (log_n - logS);
     B.row_tab = ctx->row_sh[d] + (log_n - 13) * 2048;
-    if (kind == ntt2::FIRST) ntt2::fill_first_pass_constants(B, r);
     B.pre_mode = kind == ntt2::FIRST ? pre_mode : (int)SCALE_NONE, B.pre_geo = pre_geo;
     B.post_mode = kind == ntt2::LAST ? post_mode : (int)SCALE_NONE, B.post_const = post_sh, B.post_geo = post_geo, B.post_g1 = post_g1, B.post_gk = post_gk;
     B.pre_g1 = pre_g1, B.pre_gj = pre_gj;

@@ -66,7 +66,6 @@ struct PassParams {
   const wpair *otw_tab;      // MIDDLE: w_{2^16}^(+-e), e < 2^16, Shoup form; w_N^(s e) = otw_tab[e << otw_shift]
   int otw_shift;             //         16 - (logN - logS)
   const wpair *row_tab;      // FIRST: w_N^(+-row), row < 2048, Shoup form
-  u32 dpow[8];               // FIRST: w_N^(+-(R/8) k), k < 8, Montgomery form (see round_compute)
 };
 
 // pass radices (log2) for a transform of length 2^log_n, 13 <= log_n <= 23, largest first.  The FIRST pass stores one
@@ -80,15 +79,6 @@ inline int pass_plan(int log_n, int *r) {
                                   {7, 6, 6}, {7, 7, 6}, {7, 7, 7}, {8, 7, 7}, {8, 8, 7}};
   for (int i = 0; i < 3; i++) r[i] = PLAN[log_n - 13][i];
   return r[2] ? 3 : 2;
-}
-
-// host side: the pass constants that depend on (log N, radix, direction)
-inline void fill_first_pass_constants(PassParams &A, int log_r) {
-  u32 w = ff::pow(ff::GEN, (ff::P - 1) >> (A.logN - log_r + 3));   // w_N^(R/8), ff.rs:215-223
-  if (A.inverse) w = ff::inv(w);
-  const u32 wm = ff::to_mont(w);
-  A.dpow[0] = ff::R1;
-  for (int k = 1; k < 8; k++) A.dpow[k] = ff::canon(ff::mont_mul(A.dpow[k - 1], wm));
 }
 
 template <int LOGR>

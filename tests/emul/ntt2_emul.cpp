@@ -103,7 +103,6 @@ static void transform(const u32 *in, u32 *out, int log_n, int d, u32 batch, u64 
     B.tw_in = g_twin[d].data() + inner_twiddle_offset(r);
     B.otw_tab = g_otw[d].data(), B.otw_shift = 16 - (log_n - logS);
     B.row_tab = g_row[d].data() + (log_n - 13) * 2048;
-    if (kind == FIRST) fill_first_pass_constants(B, r);
     B.pre_mode = kind == FIRST ? pre_mode : 0, B.pre_geo = pre_geo;
     B.post_mode = kind == LAST ? post_mode : 0, B.post_const = wpair{ff::from_mont(post_c), ff::shoup_of(ff::from_mont(post_c))}, B.post_geo = post_geo;
     { const u32 g = 3, gk = ff::pow(g, N >> 3);   // the geometric scale of main(): c * 3^i
