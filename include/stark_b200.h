@@ -17,6 +17,9 @@
  *     valid only on the context that made them.  A context owns one CUDA device + one stream and is not
  *     thread-safe; use one per thread / per process (one process per GPU).
  *   - On the device an element is ONE uint32_t (canonical).  stark_buf wraps such an array.
+ *   - ALIGNMENT: device arrays handed to the library (stark_buf_wrap, peer / multicast addresses) must be 16-byte aligned -- the kernels use 128-bit accesses -- and are rejected with STARK_ERR_ARG
+ *     otherwise.  Element offsets into a stark_buf (out_off, i0 of the range entry points) may be arbitrary: a range
+ *     whose addresses are not 16-byte aligned takes the scalar kernel.
  *   - There is no CPU fallback: every compute entry point fails with STARK_ERR_CUDA when no device is usable.
  */
 #ifndef STARK_B200_H
@@ -228,7 +231,8 @@ int stark_prove_trace_dev(stark_ctx *ctx, const stark_buf *cols, uint32_t n_cols
  * Optional outputs: roots_out = the num_rounds() Merkle roots popped from the stream (the shim absorbs them into its
  * FiatShamir like fri.rs:327), top_indices = the num_colinearity_tests sampled indices (fri.rs:401-407), poly_indices /
  * poly_values = the 2 * num_colinearity_tests (index, value) pairs of `polynomial_values` (fri.rs:437-441); the last
- * three are written only when *ok.  Status 1 mirrors the reference's panics: Fri::new asserts (fri.rs:37-45),
+ * three are written only when *ok (polynomial_values only when num_rounds() > 1: the reference fills it in query
+ * round 0 and there are num_rounds() - 1 query rounds; otherwise the two arrays are left untouched).  Status 1 mirrors the reference's panics: Fri::new asserts (fri.rs:37-45),
  * MerkleTree::new on an empty / non-power-of-two last codeword (merkle.rs:12-16), the sample_indices asserts
  * (fri.rs:183-192), u128 underflow in FiniteField::sub on non-canonical stream values (ff.rs:154-160).  omega must be
  * FiniteField::prim_nth_root(domain_length) (what every Fri in the reference is built with). */

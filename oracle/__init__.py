@@ -424,6 +424,11 @@ def fast_fri_fold(cw, alpha, offset, omega):
     return out
 
 
+def set_threads(n):
+    """threads used inside leaf hashing, Merkle levels and the fold (oracle_set_threads); returns the previous value"""
+    return lib().oracle_set_threads(C.c_int(int(n)))
+
+
 def splitmix64(seed, n, p=P):
     """SURVEY 8(d) deterministic input generator: element = next() mod p."""
     out = np.empty(n, dtype=np.uint64)

@@ -26,6 +26,7 @@
  * Error convention: a reference panic/assert becomes a longjmp to the API entry, which
  * returns 1 and leaves the panic message in oracle_last_error().
  */
+#include <pthread.h>
 #include <setjmp.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -64,6 +65,66 @@ static void *xmalloc(size_t n) {
   void *p = malloc(n ? n : 1);
   if (!p) panic_("oracle: out of memory");
   return p;
+}
+
+
+/* ---- optional host threading (NOT in the reference, which is single-threaded).  bench.py's CPU legs and
+ * the full-size parity tests call oracle_set_threads(k) so that "the reference's algorithm on all host cores" finishes in
+ * seconds at 2^22 leaves.  Only the ITERATION RANGE of three embarrassingly parallel loops is split (leaf hashing
+ * fri.rs:118-121, one Merkle level merkle.rs:21-27, fold_codeword fri.rs:70-88); every loop body is the unchanged
+ * restatement, so results are identical for any thread count (tests/test_oracle_fast.py checks that).  A panic raised in
+ * a worker is re-raised on the calling thread after the join. */
+static int g_threads = 1;
+int oracle_set_threads(int n) {
+  int old = g_threads;
+  g_threads = n < 1 ? 1 : (n > 256 ? 256 : n);
+  return old;
+}
+typedef void (*par_body)(size_t lo, size_t hi, void *arg);
+typedef struct {
+  par_body body;
+  size_t lo, hi;
+  void *arg;
+  int panicked;
+  char err[256];
+} ParJob;
+static void *par_run(void *v) {
+  ParJob *j = (ParJob *)v;
+  g_err[0] = 0;
+  g_env_set = 1;
+  if (setjmp(g_env)) {
+    g_env_set = 0;
+    j->panicked = 1;
+    snprintf(j->err, sizeof j->err, "%s", g_err);
+    return NULL;
+  }
+  j->body(j->lo, j->hi, j->arg);
+  g_env_set = 0;
+  return NULL;
+}
+static void par_for(size_t n, par_body body, void *arg) {
+  int T = g_threads;
+  if (T <= 1 || n < 4096) {
+    body(0, n, arg);
+    return;
+  }
+  pthread_t th[256];
+  ParJob jobs[256];
+  int started[256];
+  for (int t = 0; t < T; t++) {
+    jobs[t].body = body, jobs[t].arg = arg, jobs[t].panicked = 0, jobs[t].err[0] = 0;
+    jobs[t].lo = n * (size_t)t / (size_t)T, jobs[t].hi = n * (size_t)(t + 1) / (size_t)T;
+    started[t] = pthread_create(&th[t], NULL, par_run, &jobs[t]) == 0;
+  }
+  const char *msg = NULL;
+  for (int t = 0; t < T; t++) {
+    if (started[t]) pthread_join(th[t], NULL);
+    if (jobs[t].panicked && !msg) msg = jobs[t].err;
+  }
+  /* a slice whose thread could not be started runs here (after the joins, so a panic in it cannot leak threads) */
+  for (int t = 0; t < T && !msg; t++)
+    if (!started[t]) body(jobs[t].lo, jobs[t].hi, arg);
+  if (msg) panic_(msg);
 }
 
 /* ------------------------------------------------------------------ ff.rs */
@@ -428,6 +489,16 @@ typedef struct {
   u8 root[32];
 } Merkle;
 
+typedef struct {
+  const u8 *in;
+  u8 *out;
+} MerkleLevelJob;
+/* merkle.rs:21-27, parents [lo, hi) of one level */
+static void merkle_level_body(size_t lo, size_t hi, void *arg) {
+  MerkleLevelJob *j = (MerkleLevelJob *)arg;
+  for (size_t i = 2 * lo; i < 2 * hi; i += 2)
+    hash_combine(j->in + 32 * i, j->in + 32 * (i + 1), j->out + 32 * (i / 2));
+}
 /* merkle.rs:11-38 */
 static Merkle merkle_new(const u8 *leaves, size_t n) {
   if (n == 0) panic_("Cannot create tree from empty leaves");
@@ -444,8 +515,8 @@ static Merkle merkle_new(const u8 *leaves, size_t n) {
   for (size_t l = 1; l < lv; l++) {
     size_t nxt = cur / 2;
     t.nodes[l] = (u8 *)xmalloc(nxt * 32);
-    for (size_t i = 0; i < cur; i += 2)
-      hash_combine(t.nodes[l - 1] + 32 * i, t.nodes[l - 1] + 32 * (i + 1), t.nodes[l] + 32 * (i / 2));
+    MerkleLevelJob job = {t.nodes[l - 1], t.nodes[l]};
+    par_for(nxt, merkle_level_body, &job);
     cur = nxt;
   }
   memcpy(t.root, t.nodes[lv - 1], 32);
@@ -640,6 +711,28 @@ static Fri fri_new(u64 p, u64 omega, u64 offset, size_t n, size_t ef, size_t nq)
   Fri f = {p, offset, omega, n, ef, nq};
   return f;
 }
+typedef struct {
+  u64 p, one, two_inv;
+  size_t half;
+  u64 alpha, offset, omega;
+  const u64 *cw;
+  u64 *out;
+} FoldJob;
+/* fri.rs:70-88, outputs [lo, hi) */
+static void fold_body(size_t lo, size_t hi, void *arg) {
+  FoldJob *j = (FoldJob *)arg;
+  u64 p = j->p, one = j->one, two_inv = j->two_inv, alpha = j->alpha, offset = j->offset, omega = j->omega;
+  size_t half = j->half;
+  const u64 *cw = j->cw;
+  u64 *out = j->out;
+  for (size_t i = lo; i < hi; i++) {
+    u64 x = ff_mul(p, offset, ff_exp(p, omega, (u64)i));
+    u64 a = ff_add(p, one, ff_div(p, alpha, x));
+    u64 b = ff_sub(p, one, ff_div(p, alpha, x));
+    u64 term = ff_add(p, ff_mul(p, a, cw[i]), ff_mul(p, b, cw[half + i]));
+    out[i] = ff_mul(p, two_inv, term);
+  }
+}
 /* fri.rs:57-91 */
 static u64 *fri_fold_codeword(const Fri *f, const u64 *cw, size_t n, u64 alpha, u64 offset, u64 omega) {
   u64 p = f->p;
@@ -647,13 +740,8 @@ static u64 *fri_fold_codeword(const Fri *f, const u64 *cw, size_t n, u64 alpha, 
   u64 two_inv = ff_inv(p, 2);
   size_t half = n / 2;
   u64 *out = (u64 *)xmalloc(half * sizeof(u64));
-  for (size_t i = 0; i < half; i++) {
-    u64 x = ff_mul(p, offset, ff_exp(p, omega, (u64)i));
-    u64 a = ff_add(p, one, ff_div(p, alpha, x));
-    u64 b = ff_sub(p, one, ff_div(p, alpha, x));
-    u64 term = ff_add(p, ff_mul(p, a, cw[i]), ff_mul(p, b, cw[half + i]));
-    out[i] = ff_mul(p, two_inv, term);
-  }
+  FoldJob job = {p, one, two_inv, half, alpha, offset, omega, cw, out};
+  par_for(half, fold_body, &job);
   return out;
 }
 /* fri.rs:93-103 */
@@ -666,8 +754,18 @@ static u64 fri_num_rounds(const Fri *f) {
   }
   return r;
 }
+typedef struct {
+  const u64 *vals;
+  size_t width;
+  u8 *out;
+} LeafJob;
+static void leaf_body(size_t lo, size_t hi, void *arg) {
+  LeafJob *j = (LeafJob *)arg;
+  for (size_t i = lo; i < hi; i++) hash_from_field_elements(j->vals + i * j->width, j->width, j->out + 32 * i);
+}
 static void leaf_hashes(const u64 *cw, size_t n, u8 *out) { /* fri.rs:118-121 */
-  for (size_t i = 0; i < n; i++) hash_from_field_elements(&cw[i], 1, out + 32 * i);
+  LeafJob job = {cw, 1, out};
+  par_for(n, leaf_body, &job);
 }
 typedef struct {
   u64 **cw;
@@ -994,7 +1092,7 @@ int oracle_hash_combine(const u8 *l, const u8 *r, u8 *out) { API_ENTER(); hash_c
 int oracle_sbox(u8 b, u8 *out) { API_ENTER(); *out = sbox(b); API_LEAVE(); }
 /* leaf i = from_field_elements(vals[i*width .. (i+1)*width]) */
 int oracle_hash_leaves(const u64 *vals, size_t n_leaves, size_t width, u8 *out) {
-  API_ENTER(); for (size_t i = 0; i < n_leaves; i++) hash_from_field_elements(vals + i * width, width, out + 32 * i); API_LEAVE(); }
+  API_ENTER(); LeafJob job = {vals, width, out}; par_for(n_leaves, leaf_body, &job); API_LEAVE(); }
 
 /* all levels, concatenated: level 0 (n hashes), level 1 (n/2) ... root ; (2n-1)*32 bytes */
 int oracle_merkle_build(const u8 *leaves, size_t n, u8 *out_nodes) {

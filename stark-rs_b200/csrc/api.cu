@@ -224,6 +224,13 @@ static int ctx_create(int device, cudaStream_t borrowed, bool borrow, stark_ctx 
     rc = stark_fail(nullptr, STARK_ERR_OOM, "context allocation failed");
   if (rc == STARK_OK && cudaMemset(ctx->flag, 0, 16) != cudaSuccess) rc = stark_fail(nullptr, STARK_ERR_CUDA, "context initialisation failed");
   ctx->climb_counter = ctx->flag + 1;
+  // k_merkle_climb<256> takes at most 256 chunks of 512 / 1024 nodes (its fused top holds the chunk roots in 16 KB of
+  // shared memory): the tuning knob is clamped to the range the kernel supports
+  ctx->climb_log = 18;
+  if (const char *e = getenv("STARK_CLIMB_LOG")) {
+    const int v = atoi(e);
+    ctx->climb_log = v < 11 ? 11 : (v > 18 ? 18 : v);
+  }
   if (rc == STARK_OK) rc = ntt_init(ctx);
   if (rc == STARK_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess)
     rc = stark_fail(nullptr, STARK_ERR_CUDA, "context initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -325,6 +332,8 @@ int stark_buf_download(stark_ctx *ctx, const stark_buf *buf, size_t off, size_t 
 }
 int stark_buf_wrap(stark_ctx *ctx, void *device_u32, size_t n, stark_buf **out) {
   if (!ctx || !out || (!device_u32 && n)) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+  // the kernels read and write field elements with 128-bit accesses (stark_b200.h, ALIGNMENT)
+  if ((uintptr_t)device_u32 & 15u) return stark_fail(ctx, STARK_ERR_ARG, "device pointer must be 16-byte aligned");
   *out = new stark_buf{ctx, (u32 *)device_u32, n, false};
   return STARK_OK;
 }

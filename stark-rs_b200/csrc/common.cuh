@@ -53,6 +53,7 @@ struct stark_ctx {
   int ntt_big;           // STARK_NTT_BIG=1: two-pass plans on 16384-element tiles for 2^20..2^22 (experiment)
   int ntt_l2_persist;    // STARK_NTT_L2_PERSIST=1: mark each pass's destination as L2-persisting (experiment, default off)
   int l2_persist_ready;
+  int climb_log;         // Merkle levels above 2^climb_log nodes get one launch each, the rest one climb launch (merkle.cu)
   char err[512];
   // optional per-kernel timing (stark_ctx_profile_begin/end): CUDA events around every launch, on ctx->stream
   bool prof_on;

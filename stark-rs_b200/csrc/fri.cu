@@ -408,7 +408,9 @@ static int fold_launch_range(stark_ctx *ctx, const u32 *cw, u32 *out, size_t h, 
                              u32 g_r_m, const u32 *alpha_m, u32 inv2off_m, u32 alpha_val = 0) {
   if (i1 <= i0) return STARK_OK;
   const size_t cnt = i1 - i0;
-  if (h % 4 == 0 && i0 % 4 == 0 && cnt % 4 == 0) {
+  // 128-bit path only when every address the kernel touches is 16-byte aligned (out may be an offset view)
+  const bool aligned = (((uintptr_t)(cw + i0) | (uintptr_t)(cw + h + i0) | (uintptr_t)(out + i0)) & 15u) == 0;
+  if (h % 4 == 0 && i0 % 4 == 0 && cnt % 4 == 0 && aligned) {
     size_t blocks = (cnt / 4 + 255) / 256, cap = (size_t)ctx->sm_count * 8;
     LAUNCH_PDL(ctx, "fri_fold", 12ull * cnt, k_fri_fold<4>, (u32)(blocks < cap ? blocks : cap), 256, cw, out, h, i0, i1, r, G,
                g_r_m, alpha_m, alpha_val, inv2off_m);
@@ -698,6 +700,9 @@ int stark_fri_fold_bcast_dev(stark_ctx *ctx, const stark_buf *codeword, size_t n
   if (codeword->n < n || i0 + count > h) return stark_fail(ctx, STARK_ERR_ARG, "range out of bounds");
   if (n_peers < 0 || n_peers > 8) return stark_fail(ctx, STARK_ERR_ARG, "at most 8 peers");
   if ((h % 4) || (i0 % 4) || (count % 4)) return stark_fail(ctx, STARK_ERR_ARG, "fold range must be a multiple of 4");
+  if (((uintptr_t)codeword->ptr | (uintptr_t)multicast) & 15u) return stark_fail(ctx, STARK_ERR_ARG, "device pointer must be 16-byte aligned");
+  for (int g = 0; g < n_peers; g++)
+    if ((uintptr_t)peers[g] & 15u) return stark_fail(ctx, STARK_ERR_ARG, "device pointer must be 16-byte aligned");
   if (count == 0) return STARK_OK;
   u32 off, om;
   reduce_params(ctx, offset, omega, &off, &om);
@@ -885,7 +890,13 @@ int stark_prove_trace_dev(stark_ctx *ctx, const stark_buf *cols, uint32_t n_cols
     cudaStreamWaitEvent(ctx->side[0], ctx->fork_ev, 0);
     ctx->stream = ctx->side[0], ctx->climb_counter = ctx->flag + 3, forked = true;
   }
-  for (u32 c = 1; c < n_cols && rc == STARK_OK; c++) {
+  // With num_rounds() == 0 (N <= expansion factor or N <= 4 nq, fri.rs:93-103) Fri::commit builds no tree and the proof
+  // starts with the last codeword, so column 0 is committed here like the others.
+  u32 fri_rounds = 0;
+  if (rc == STARK_OK) rc = fri_check(ctx, N, 1u << log_blowup, &fri_rounds, nq);
+  const u32 first_col = fri_rounds == 0 ? 0u : 1u;
+  if (rc == STARK_OK && n_cols == 1 && first_col == 0) rc = dev_alloc(ctx, (void **)&d_roots, 32);
+  for (u32 c = first_col; c < n_cols && rc == STARK_OK; c++) {
     stark_tree *t = nullptr;
     rc = merkle_build_from_dev_values(ctx, lde + (size_t)c * N, N, 1, 1, 0, &t);
     if (rc == STARK_OK) {
@@ -904,13 +915,13 @@ int stark_prove_trace_dev(stark_ctx *ctx, const stark_buf *cols, uint32_t n_cols
     rc = fri_prove_dev(ctx, lde, N, N, (u32)offset, omega, 1u << log_blowup, nq, nullptr, 0, proof, proof_cap, proof_len,
                        nullptr);
   if (forked) cudaStreamWaitEvent(main_stream, ctx->side_done[0], 0);   // join (also on an error path: the trees are freed below)
-  if (rc == STARK_OK && n_cols > 1 && column_roots &&
-      cudaMemcpyAsync(column_roots + 32, d_roots + 32, 32 * (size_t)(n_cols - 1), cudaMemcpyDeviceToHost, ctx->stream) !=
-          cudaSuccess)
+  if (rc == STARK_OK && d_roots && column_roots && n_cols > first_col &&
+      cudaMemcpyAsync(column_roots + 32 * first_col, d_roots + 32 * first_col, 32 * (size_t)(n_cols - first_col),
+                      cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
     rc = stark_fail(ctx, STARK_ERR_CUDA, "D2H copy failed");
-  if (n_cols > 1 && cudaStreamSynchronize(ctx->stream) != cudaSuccess && rc == STARK_OK)
+  if (d_roots && cudaStreamSynchronize(ctx->stream) != cudaSuccess && rc == STARK_OK)
     rc = stark_fail(ctx, STARK_ERR_CUDA, "column commitments failed");
-  if (rc == STARK_OK && column_roots) memcpy(column_roots, proof + 1, 32);  // first object = root of column 0
+  if (rc == STARK_OK && column_roots && first_col == 1) memcpy(column_roots, proof + 1, 32);  // first object = root of column 0
   for (stark_tree *t : trees) stark_merkle_free(t);
   dev_free(ctx, lde), dev_free(ctx, d_roots);
   return rc;

@@ -205,7 +205,7 @@ int merkle_climb_dev(stark_ctx *ctx, u8 *nodes, size_t n, const TranscriptArgs *
   size_t m = n;
   // throughput-bound levels: one launch each.  A level of 2^17 parents is already half latency (12 us against 6 us for the
   // same step inside the climb kernel, whose launch is paid anyway), so the climb starts from 2^18 nodes.
-  const size_t climb_from = getenv("STARK_CLIMB_LOG") ? ((size_t)1 << atoi(getenv("STARK_CLIMB_LOG"))) : ((size_t)1 << 18);
+  const size_t climb_from = (size_t)1 << ctx->climb_log;   // STARK_CLIMB_LOG, read once at context creation, clamped to 11..18
   while (m > climb_from) {
     const size_t half = m >> 1;
     LAUNCH_PDL(ctx, "merkle_level", 96ull * half, k_merkle_level, (u32)((half + 2 * HASH_NT - 1) / (2 * HASH_NT)), HASH_NT,

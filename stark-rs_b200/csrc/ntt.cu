@@ -400,17 +400,30 @@ int ntt_transform(stark_ctx *ctx, const u32 *in, u32 *out, int log_n, bool inver
   u32 *tmp_all = nullptr;
   if (need_tmp) ST_TRY(dev_alloc(ctx, (void **)&tmp_all, (size_t)std::min(batch_total, group) * N * 4 * n_streams));
   cudaStream_t main_stream = ctx->stream;
-  struct RestoreStream {   // the launch macros return on a failed launch: never leave a side stream in the context
+  // Every exit of this function -- the launch macros return on a failed launch -- must leave the context on its own
+  // stream, join the side streams (a later call on this context must not race with work still queued there), drop
+  // the L2 window and release the scratch: a scope guard does all of it.
+  struct PassGuard {
     stark_ctx *c;
-    cudaStream_t s;
-    ~RestoreStream() { c->stream = s; }
-  } restore_stream{ctx, main_stream};
-  if (n_streams > 1) {
-    int src_ = side_streams(ctx, n_streams);
-    if (src_ != STARK_OK) {
-      dev_free(ctx, tmp_all);
-      return src_;
+    cudaStream_t main;
+    int n_streams;
+    u32 *tmp;
+    ~PassGuard() {
+      c->stream = main;
+      if (n_streams > 1) {
+        if (c->ntt_l2_persist)
+          for (int i = 0; i < n_streams; i++) l2_window(c, c->side[i], nullptr, 0);
+        for (int i = 0; i < n_streams; i++) {
+          cudaEventRecord(c->side_done[i], c->side[i]);
+          cudaStreamWaitEvent(main, c->side_done[i], 0);
+        }
+      }
+      dev_free(c, tmp);
     }
+  } guard{ctx, main_stream, 1, tmp_all};
+  if (n_streams > 1) {
+    ST_TRY(side_streams(ctx, n_streams));
+    guard.n_streams = n_streams;
     cudaEventRecord(ctx->fork_ev, main_stream);
     for (int i = 0; i < n_streams; i++) cudaStreamWaitEvent(ctx->side[i], ctx->fork_ev, 0);
   }
@@ -512,15 +525,5 @@ int ntt_transform(stark_ctx *ctx, const u32 *in, u32 *out, int log_n, bool inver
     logS += r;
   }
   }
-  if (n_streams > 1) {
-    ctx->stream = main_stream;
-    if (ctx->ntt_l2_persist)
-      for (int i = 0; i < n_streams; i++) l2_window(ctx, ctx->side[i], nullptr, 0);
-    for (int i = 0; i < n_streams; i++) {
-      cudaEventRecord(ctx->side_done[i], ctx->side[i]);
-      cudaStreamWaitEvent(main_stream, ctx->side_done[i], 0);
-    }
-  }
-  dev_free(ctx, tmp_all);
   return rc;
 }

@@ -396,7 +396,8 @@ int stark_fri_verify(stark_ctx *ctx, const uint8_t *proof, size_t proof_len, siz
       return stark_fail(ctx, STARK_ERR_ARG, "cannot sample more indices than available in last codeword; requested: %u, available: %llu", nq, (unsigned long long)reduced);
     if (why == V_PANIC_SUB) return stark_fail(ctx, STARK_ERR_ARG, "attempt to subtract with overflow");
   }
-  if (fail == NO_FAIL && poly_indices && poly_values)
+  // polynomial_values is filled in query round 0 only (fri.rs:437-441): with num_rounds() <= 1 the reference pushes nothing
+  if (fail == NO_FAIL && R > 1 && poly_indices && poly_values)
     for (size_t i = 0; i < 2 * (size_t)nq; i++) poly_indices[i] = poly[i], poly_values[i] = poly[2 * (size_t)nq + i];
   return finish();
 }

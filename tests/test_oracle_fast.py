@@ -48,3 +48,42 @@ def test_splitmix(oracle):
             out.append((z ^ (z >> 31)) % P)
         return out
     assert list(oracle.splitmix64(0x5354524B, 16)) == ref(0x5354524B, 16)
+
+
+def test_oracle_threads_do_not_change_results(oracle):
+    """oracle_set_threads only splits the iteration range of the leaf-hash / Merkle-level / fold loops: same bytes for
+    any thread count, and a panic raised inside a worker still surfaces with the reference's text (ff.rs:182)."""
+    O = oracle
+    n = 1 << 14
+    cw = O.splitmix64(7, n)
+    w = O.ff_prim_nth_root(n)
+    base = (O.fri_prove(cw, w, 3, 4, 16)["proof"], O.merkle_build(O.hash_leaves(cw)).tobytes(), O.fri_fold(cw, 99, 3, w).tobytes(),
+            O.hash_leaves(cw, 8).tobytes())
+    for t in (2, 3, 8):
+        old = O.set_threads(t)
+        try:
+            got = (O.fri_prove(cw, w, 3, 4, 16)["proof"], O.merkle_build(O.hash_leaves(cw)).tobytes(),
+                   O.fri_fold(cw, 99, 3, w).tobytes(), O.hash_leaves(cw, 8).tobytes())
+            assert got == base, t
+            with pytest.raises(O.OraclePanic, match="no division by zero"):
+                O.fri_fold(cw, 5, 0, w)
+        finally:
+            O.set_threads(old)
+
+
+def test_baseline_digests_small_crosscheck(oracle):
+    """the golden generator's code path (tests/golden/make_baseline_digests.py) on a small instance of config 5, so the
+    committed full-size digests cannot silently drift from what the oracle computes"""
+    import hashlib
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "mk", os.path.join(os.path.dirname(__file__), "golden", "make_baseline_digests.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    r = mk.cfg5(12)
+    cw = oracle.splitmix64(mk.SEED + 12, 1 << 12)
+    root = oracle.merkle_commit(oracle.hash_leaves(cw))
+    assert r["root"] == root.hex() and r["alpha"] == oracle.fs_challenge(root)
+    out = oracle.fast_fri_fold(cw, r["alpha"], 3, oracle.ff_prim_nth_root(1 << 23))
+    assert r["folded_sha256"] == hashlib.sha256(out.astype("<u8").tobytes()).hexdigest()
