@@ -1,27 +1,32 @@
 #!/usr/bin/env python
 """bench.py -- BASELINE.json metric: "prove time and NTT/LDE field elems/s at 2^20-row trace, 1/2/4/8 B200".
 
-One STEP = one pass of the hot path over one synthetic trace (BASELINE config 3):
-    n_cols x 2^20-row column(s)  ->  coset LDE (blowup 4, offset 3, N = 2^22)  ->  one Merkle tree per column
-    (leaf rule fri.rs:118-121)  ->  Fri::prove on column 0 (omega = prim_nth_root(2^22), ef 4, 32 queries, 15 rounds)
-    ->  ProofStream::serialize bytes on the host.
-`value`  = LDE-output field elements proved per second, whole job (all ranks), trace already resident in HBM.
+One STEP = one pass of the hot path over one synthetic trace (BASELINE config 3, SURVEY 8(d), W = 16 columns):
+    16 x 2^20-row columns  ->  coset LDE (blowup 4, offset 3, N = 2^22)  ->  one Merkle tree per column (leaf rule
+    fri.rs:118-121)  ->  Fri::prove on column 0 (omega = prim_nth_root(2^22), ef 4, 32 queries, 15 rounds)  ->
+    ProofStream::serialize bytes + the 16 column roots on the host.
+`value`  = LDE-output field elements proved per second, whole job, trace already resident in HBM.
 `e2e`    = the same through the reference-facing C-ABI call with HOST buffers: the uint64 trace is copied from pinned
-           host memory inside the timed region and the proof bytes come back to the host.
-Multi-GPU (torchrun, one process per GPU): every rank proves its own trace (independent objects, no data-path
-collective) -> "weak" scaling; NCCL is used for the barrier and the max-over-ranks reduction only.
+           host memory inside the timed region and the proof bytes + column roots come back to the host.
+
+Multi-GPU (torchrun, one process per GPU): the SAME trace is proved by the group -- STRONG scaling, fixed total work --
+through the library's own multi-GPU entry points (stark_mgpu_*, include/stark_b200.h): columns 1.. are LDE'd and
+committed round robin, column 0 is LDE'd by every rank and Fri::prove runs sharded (subtree roots and folded-codeword
+slices exchanged through peer memory over NVLink inside the kernels); every rank ends with the identical
+proof bytes and column roots.  torch.distributed only carries the 128-byte NCCL id, the barrier and the max-over-ranks.
 
 `--impl reference` times the CPU restatement of the reference (oracle/, "port": no rustc in the image, so the Rust
-crate itself cannot be built) on the host cores, one independent pipeline per core, on a bounded sample of the same
-workload.
+crate itself cannot be built) on all host cores, on a bounded sample of the same workload.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
 import sys
 import tempfile
 import time
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -40,52 +45,101 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-n", type=int, default=20)
     ap.add_argument("--log-blowup", type=int, default=2)
-    ap.add_argument("--cols", type=int, default=1)
+    ap.add_argument("--cols", type=int, default=16)
     ap.add_argument("--nq", type=int, default=32)
     ap.add_argument("--seed", type=lambda s: int(s, 0), default=0x5354524B)
-    ap.add_argument("--cpu-sample-log-n", type=int, default=9, help="trace rows (log2) of the bounded CPU sample")
+    ap.add_argument("--ref-log-n", type=int, default=0, help="rows (log2) of the reference arm's sample; 0 = the largest "
+                    "size whose steps + warmup fit --ref-budget-s")
+    ap.add_argument("--ref-budget-s", type=float, default=240.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
     return ap.parse_args()
 
 
-def workload_name(a):
-    return ("cfg3: %d col x 2^%d rows, coset LDE blowup %d offset 3 -> N=2^%d, Merkle per column, Fri::prove(ef %d, "
-            "%d queries) -> proof bytes" % (a.cols, a.log_n, 1 << a.log_blowup, a.log_n + a.log_blowup,
-                                          1 << a.log_blowup, a.nq))
+def config_of(a):
+    """identical in both arms (the driver compares it)"""
+    return {"workload": "cfg3: %d cols x 2^%d rows, coset LDE blowup %d offset 3 -> N=2^%d, Merkle per column, "
+                        "Fri::prove(ef %d, %d queries) on column 0 -> proof bytes + column roots"
+                        % (a.cols, a.log_n, 1 << a.log_blowup, a.log_n + a.log_blowup, 1 << a.log_blowup, a.nq),
+            "cols": a.cols, "log_n": a.log_n, "log_blowup": a.log_blowup, "num_colinearity_tests": a.nq,
+            "seed": "0x%X + column index" % a.seed}
 
 
 # ----------------------------------------------------------------------------------------------------- CPU arm
 
-def cpu_pipeline(a, mode, log_n, steps, warmup, threads):
-    import oracle as O
-    O.build()
-    for _ in range(warmup):
-        O.bench_pipeline(mode, log_n, a.log_blowup, min(a.nq, 1 << max(log_n - 2, 0)), a.seed, threads)
-    t = 0.0
-    for s in range(steps):
-        sec, _ = O.bench_pipeline(mode, log_n, a.log_blowup, min(a.nq, 1 << max(log_n - 2, 0)), a.seed + 1000 * s, threads)
-        t += sec
-    elems = threads * a.cols * (1 << (log_n + a.log_blowup)) * steps
-    return elems / t, t / steps
+def cpu_config3(O, cols, log_n, log_blowup, nq, threads):
+    """The config-3 pipeline on the host with the oracle: per column LDE (O(n log n) CPU NTT, oracle/fast_cpu.c -- the
+    reference's own interpolate_domain is O(n^3) and cannot reach these sizes) + leaf hashes + MerkleTree::new; column 0
+    through Fri::prove (the restatement of fri.rs:250-311, which rebuilds every tree in the query phase like the
+    reference).  The hashing / Merkle / fold loops run on `threads` host threads.  -> (seconds, roots, proof)"""
+    n_cols = len(cols)
+    # a few columns at a time, each with its share of the threads inside the oracle's loops (one column alone does not keep
+    # all cores busy: the reference's Vec clones and level allocations are serial)
+    conc = max(1, min(n_cols, 4, threads))
+    O.set_threads(max(1, -(-threads // conc)))
+    N = 1 << (log_n + log_blowup)
+    w = O.ff_prim_nth_root(N)
+    t0 = time.perf_counter()
+
+    def job(c):
+        lde = O.fast_lde(cols[c], log_n, log_blowup, 3)
+        if c == 0:
+            return O.fri_prove(lde, w, 3, 1 << log_blowup, nq)["proof"]
+        return O.merkle_commit(O.hash_leaves(lde))
+
+    with ThreadPoolExecutor(max_workers=conc) as ex:
+        res = list(ex.map(job, range(n_cols)))      # column 0 (the long one) starts first
+    sec = time.perf_counter() - t0
+    return sec, [res[0][1:33]] + res[1:], res[0]
+
+
+def synth_cols(a, log_n, O=None):
+    from stark_rs_b200 import synthetic as G          # numpy only
+    return [G.splitmix64(a.seed + c, 1 << log_n) for c in range(a.cols)]
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import oracle as O
+    O.build()
     threads = os.cpu_count() or 1
-    val, sec = cpu_pipeline(a, 0, a.cpu_sample_log_n, a.steps, min(a.warmup, 1), threads)
-    sample = ("%d independent pipelines (one per host thread) on a 2^%d-row trace each: LDE by the reference's own "
-              "interpolate_domain O(n^3) + eval_domain O(n*m), Merkle commit, Fri::prove, serialize"
-              % (threads, a.cpu_sample_log_n))
+    nq_of = lambda ln: min(a.nq, 1 << max(ln + a.log_blowup - 3, 0))
+    # size of the bounded sample: calibrate on a 2^14-row trace (per-element cost is flat in n: hashing dominates)
+    cal_ln = min(14, a.log_n)
+    t_cal, _, _ = cpu_config3(O, synth_cols(a, cal_ln), cal_ln, a.log_blowup, nq_of(cal_ln), threads)
+    ln = a.ref_log_n or a.log_n
+    if not a.ref_log_n:
+        while ln > cal_ln and t_cal * (1 << (ln - cal_ln)) * (a.steps + a.warmup) > a.ref_budget_s:
+            ln -= 1
+    cols = synth_cols(a, ln)
+    for _ in range(a.warmup):
+        cpu_config3(O, cols, ln, a.log_blowup, nq_of(ln), threads)
+    t = 0.0
+    for _ in range(a.steps):
+        t += cpu_config3(O, cols, ln, a.log_blowup, nq_of(ln), threads)[0]
+    elems = a.cols * (1 << (ln + a.log_blowup)) * a.steps
+    val = elems / t
+    sample = ("%d cols x 2^%d rows per step (the GPU arm: 2^%d rows), all %d host threads inside the leaf-hash / Merkle / "
+              "fold loops; LDE by an O(n log n) CPU NTT (NOT in the reference, whose O(n^3) interpolate_domain cannot reach "
+              "this size), hash / Merkle / Fiat-Shamir / Fri::prove by the restatement of the reference"
+              % (a.cols, ln, a.log_n, threads))
+    cfg = config_of(a)
+    if ln != a.log_n:
+        cfg["sample_log_n"] = ln
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-        "warmup": min(a.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u64 (u128 % p)", "data": "synthetic (splitmix64, seed 0x%X)" % a.seed,
-        "config": {"workload": workload_name(a), "sample": sample},
+        "warmup": a.warmup, "ms_per_step": 1e3 * t / a.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u64 (u128 % p)", "data": "synthetic (splitmix64, seed 0x%X + column)" % a.seed,
+        "config": cfg, "same_config": ln == a.log_n,
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "extrapolated": None if ln == a.log_n else {
+            "to": "2^%d rows" % a.log_n, "value": val, "unit": UNIT,
+            "method": "elements/s measured at 2^%d rows taken as the 2^%d-row rate: every stage but the NTT is linear in the "
+                      "codeword length (leaf + node hashes, fold), the NTT is < 3 %% of the CPU time; the GPU arm's own "
+                      "cpu_baseline runs the full 2^%d-row config once and reports the measured figure" % (ln, a.log_n, a.log_n)},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
@@ -137,6 +191,25 @@ class ClockSampler:
         return out
 
 
+# which roof bounds each kernel of the step: the hash kernels run on the integer pipes, the climb kernel
+# is a chain of dependent hashes, the transforms and the fold stream HBM
+KERNEL_BOUND = {"merkle_level": "int_pipe", "leaf_hash": "int_pipe", "fold_leaf": "int_pipe", "mg_fold_leaf": "int_pipe",
+                "leaf_hash_w": "int_pipe", "merkle_climb": "latency", "merkle_top": "latency", "fri_tail": "latency",
+                "mg_top": "latency", "query_phase": "latency", "ntt_pass1": "hbm", "ntt_pass_mid": "hbm",
+                "ntt_pass_last": "hbm", "ntt_single": "hbm", "fri_fold": "hbm", "narrow_u64": "hbm"}
+
+
+def hash_instr_table():
+    """Per-hash dynamic instruction counts of the shipped hash kernels, from the current round's ncu capture of THIS
+    command (profiles/r2_hash_instr.json, written by tools/hash_instr_from_ncu.py; tests/test_sass_budget.py fails when
+    the built kernels no longer match the SASS the capture was taken from)."""
+    path = os.path.join(ROOT, "profiles", "r2_hash_instr.json")
+    try:
+        return json.load(open(path)), os.path.relpath(path, ROOT)
+    except Exception:
+        return None, None
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -156,17 +229,40 @@ def run_ours(a):
     n, N = 1 << a.log_n, 1 << (a.log_n + a.log_blowup)
     ef = 1 << a.log_blowup
 
-    # synthetic trace (SURVEY 8(d) generator), column-major, in PINNED host memory as uint64 (the ABI's layout)
+    # the synthetic trace (SURVEY 8(d) generator), column-major, in PINNED host memory as uint64 (the ABI's layout); the
+    # same trace on every rank
     from stark_rs_b200 import synthetic as G
     host = torch.empty(a.cols * n, dtype=torch.int64).pin_memory()
     hv = host.numpy().view(np.uint64)
     for c in range(a.cols):
-        hv[c * n:(c + 1) * n] = G.splitmix64(a.seed + c + 1000003 * rank, n)
+        hv[c * n:(c + 1) * n] = G.splitmix64(a.seed + c, n)
     proof_cap = S.fri_proof_size(N, ef, a.nq)
     proof = torch.empty(proof_cap, dtype=torch.uint8).pin_memory().numpy()
     roots = torch.empty(a.cols * 32, dtype=torch.uint8).pin_memory().numpy().reshape(a.cols, 32)
-    dev_cols = ctx.upload_ptr(host.data_ptr(), a.cols * n)      # resident copy for the `value` measurement
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    group = None
+    if world > 1:
+        ids = [S.mgpu_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        group = S.Group.init(ctx, ids[0], rank, world, N)
+        owned = group.owned_columns(a.cols)[0]
+        mine = [0] + owned
+        # resident copy for the `value` measurement: column 0 followed by this rank's owned columns
+        stage = torch.empty(len(mine) * n, dtype=torch.int64).pin_memory()
+        sv = stage.numpy().view(np.uint64)
+        for i, c in enumerate(mine):
+            sv[i * n:(i + 1) * n] = hv[c * n:(c + 1) * n]
+        dev_cols = ctx.upload_ptr(stage.data_ptr(), len(mine) * n)
+        step_dev = lambda cols=a.cols: group.prove_trace_dev([dev_cols], cols, a.log_n, a.log_blowup, 3, a.nq, [roots], [proof])
+        step_e2e = lambda: group.prove_trace_ptr(host.data_ptr(), a.cols, a.log_n, a.log_blowup, 3, a.nq, [roots], [proof])
+        h2d_mine = len(mine) * n * 8
+    else:
+        mine = list(range(a.cols))
+        dev_cols = ctx.upload_ptr(host.data_ptr(), a.cols * n)
+        step_dev = lambda cols=a.cols: ctx.prove_trace_dev(dev_cols, cols, a.log_n, a.log_blowup, 3, a.nq, roots, proof)
+        step_e2e = lambda: ctx.prove_trace_ptr(host.data_ptr(), a.cols, a.log_n, a.log_blowup, 3, a.nq, roots, proof)
+        h2d_mine = a.cols * n * 8
 
     per_rank = []      # total ms of each timed pass on every rank (diagnostic; the reported time is the max)
 
@@ -194,35 +290,54 @@ def run_ours(a):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    step_dev = lambda: ctx.prove_trace_dev(dev_cols, a.cols, a.log_n, a.log_blowup, 3, a.nq, roots, proof)
-    step_e2e = lambda: ctx.prove_trace_ptr(host.data_ptr(), a.cols, a.log_n, a.log_blowup, 3, a.nq, roots, proof)
+    def total(x):
+        if world == 1:
+            return x
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
 
     # clocks are sampled (nvidia-smi, 20 ms period) from before the warm-up to the end of the last timed pass: the timed
     # region itself is a few tens of milliseconds, too short for more than a sample or two on its own
     sampler = ClockSampler(local) if rank == 0 else None
     time.sleep(0.3 if rank == 0 else 0.0)       # let nvidia-smi start before the GPU gets busy
-    for _ in range(max(a.warmup, 3)):
+    W = max(a.warmup, 3)
+    for _ in range(W):
         step_dev()
     l0 = ctx.launches
+    b0 = group.bytes_sent[0] if group else 0
     ms_dev = timed(step_dev, a.steps)
     launches = ctx.launches - l0
+    comm_bytes = total((group.bytes_sent[0] - b0) if group else 0) / a.steps
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, a.steps)
     proof_len = step_dev()
     proof_bytes = bytes(proof[:proof_len])
+    roots_bytes = roots.tobytes()
+    # the one-column variant (Fri::prove latency: LDE + commit + sharded FRI on a single column), same path
+    for _ in range(2):
+        step_dev(1)
+    ms_1col = timed(lambda: step_dev(1), a.steps)
+    proof_1col = bytes(proof[:proof_len])
 
     # per-kernel device times (CUDA events on the launching stream) over a further timed pass with profiling on
+    step_dev()
     ctx.profile_begin()
     ms_prof = timed(step_dev, a.steps)
     prof = ctx.profile_end()
     clocks = sampler.stop() if sampler else None
+    h2d_total = total(h2d_mine)
+    same_everywhere = total(1.0 if hashlib.sha256(proof_bytes + roots_bytes).digest() ==
+                            _bcast_digest(dist, world, hashlib.sha256(proof_bytes + roots_bytes).digest()) else 0.0) == world
 
-    elems = world * a.cols * N * a.steps
+    elems = a.cols * N * a.steps
     value = elems / (ms_dev * 1e-3)
     e2e_value = elems / (ms_e2e * 1e-3)
 
     if rank != 0:
+        if group:
+            group.close()
         if world > 1:
             dist.destroy_process_group()
         return
@@ -234,122 +349,173 @@ def run_ours(a):
         pass
     hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
 
+    # measured live: register-only LOP3 / IMAD / mixed issue rates (stark_bench_int_peak), i.e. the integer-pipe roof
+    ipk = ctx.int_peak()
+    instr, instr_src = hash_instr_table()
     kernels = {}
     for k in prof:
-        per_step_ms = k["ms"] / a.steps
-        kernels[k["kernel"]] = {
-            "launches_per_step": k["launches"] / a.steps, "ms_per_step": per_step_ms,
-            "share": k["ms"] / ms_prof if ms_prof else None,
-            "algorithmic_bytes_per_step": k["bytes"] / a.steps,
-            "achieved_gbs": (k["bytes"] / (k["ms"] * 1e-3) / 1e9) if k["ms"] > 0 and k["bytes"] else None,
-        }
-        if kernels[k["kernel"]]["achieved_gbs"]:
-            kernels[k["kernel"]]["hbm_frac"] = kernels[k["kernel"]]["achieved_gbs"] / hbm_peak
+        name = k["kernel"]
+        e = {"launches_per_step": k["launches"] / a.steps, "ms_per_step": k["ms"] / a.steps,
+             "share": k["ms"] / ms_prof if ms_prof else None, "bound": KERNEL_BOUND.get(name, "latency"),
+             "algorithmic_bytes_per_step": k["bytes"] / a.steps}
+        if k["ms"] > 0 and k["bytes"]:
+            e["achieved_gbs"] = k["bytes"] / (k["ms"] * 1e-3) / 1e9
+            e["hbm_frac"] = e["achieved_gbs"] / hbm_peak
+        h = (instr or {}).get("kernels", {}).get(name)
+        if h and k["ms"] > 0 and k["bytes"]:
+            hashes = k["bytes"] / h["algorithmic_bytes_per_hash"]
+            rate = hashes / (k["ms"] * 1e-3)
+            e.update({"hashes_per_s": rate, "thread_instr_per_hash": h["thread_instr_per_hash"],
+                      "alu_instr_per_hash": h["alu_instr_per_hash"],
+                      "alu_pipe_frac": rate * h["alu_instr_per_hash"] / ipk["alu_per_s"],
+                      "issue_frac": rate * h["thread_instr_per_hash"] / ipk["mixed_per_s"]})
+        kernels[name] = e
     dom = max(prof, key=lambda k: k["ms"])
     dk = kernels[dom["kernel"]]
-    # Integer-pipe view of the hash kernels ("integer-pipe utilisation for ... hashing").  B200 issues 64
-    # lanes/clk/SM on each of the ALU and FMA pipes (B300_MICROARCH.md: both rt_SMSP = 2), so a pipe's peak is
-    # sm_count * 64 * clock thread-instructions/s.  Per-hash instruction counts come from the ncu captures under
-    # profiles/ (smsp__inst_executed / hashes; ALU share from sm__inst_executed_pipe_alu): see DESIGN.md 3.4.
-    # (round 1, final hs2 form: SASS of k_merkle_level / k_leaf_hash1 / k_fold_leaf1 -- two 528-instruction chunk
-    # iterations + eight 238-instruction mixes + ~180 per thread of two hashes; ALU = PRMT/LOP3/IADD3/..., FMA = IMAD)
-    HASH = {"merkle_level": {"bytes": 96.0, "instr": 1569.0, "alu_instr": 832.0},
-            "leaf_hash": {"bytes": 36.0, "instr": 1151.0, "alu_instr": 578.0},
-            "fold_leaf": {"bytes": 44.0, "instr": 1187.0, "alu_instr": 600.0}}
-    # measured live: register-only LOP3 / IMAD / mixed issue rates (stark_bench_int_peak: 18.55 T, 18.56 T and 35.5 T
-    # thread-instructions/s on this B200, i.e. 64 lanes/clk/SM per pipe and both pipes at once)
-    ipk = ctx.int_peak()
-    pipe_peak = ipk["alu_per_s"]
-    int_pipe = {}
-    for name, h in HASH.items():
-        k = next((x for x in prof if x["kernel"] == name), None)
-        if not k or not k["ms"]:
-            continue
-        hashes = k["bytes"] / h["bytes"]
-        rate = hashes / (k["ms"] * 1e-3)
-        int_pipe[name] = {"hashes_per_s": rate, "thread_instr_per_hash": h["instr"], "alu_instr_per_hash": h["alu_instr"],
-                          "alu_pipe_peak_thread_instr_per_s": pipe_peak,
-                          "frac_of_alu_pipe_peak": rate * h["alu_instr"] / pipe_peak,
-                          "frac_of_issue_peak": rate * h["instr"] / ipk["mixed_per_s"]}
-    # DRAM traffic per launch from ncu --set full captures of this same command (profiles/r1k_bench_kernels_ncu_full.csv,
-    # profiles/r1u_bench_kernels_ncu_full.csv), quoted with the algorithmic bytes of the SAME launch: the written level /
-    # tree is still in L2 when a kernel ends, so the measured write traffic is below the algorithmic figure
-    NCU_TRAFFIC = {"merkle_level": {"launch": "2^19 parents", "traffic": 33573120 + 5376000, "algorithmic": 96 * (1 << 19)},
-                   "merkle_climb": {"launch": "128 CTAs: 2^16 nodes -> root", "traffic": 2162944,
-                                    "algorithmic": 96 * ((1 << 16) - 1)}}
-    roofline = {
-        "kernel": dom["kernel"], "bound": "hbm", "achieved": dk["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
-        "frac": (dk["achieved_gbs"] / hbm_peak) if dk["achieved_gbs"] else None,
-        "traffic": NCU_TRAFFIC.get(dom["kernel"], {}).get("traffic"),
-        "traffic_note": NCU_TRAFFIC.get(dom["kernel"]),
-        "peak_source": peak_src, "launches_per_step": dk["launches_per_step"], "avg_launch_ms":
-            dom["ms"] / dom["launches"], "share_of_step": dk["share"],
-        "note": "the dominant kernels hash: merkle_level / leaf_hash / fold_leaf are integer-pipe bound (see int_pipe: "
-                "fraction of the 64 lanes/clk/SM ALU pipe), merkle_climb is latency bound (per tree a chain of ~17 dependent "
-                "node hashes of 1.5-3 us each on a handful of SMs, DESIGN.md section 4), so their HBM fraction is low by "
-                "construction; the HBM-bound kernels (ntt_pass*, fri_fold) are listed under kernels with their own fractions",
-        "int_pipe": int_pipe,
-    }
+    if dk["bound"] == "int_pipe" and "alu_pipe_frac" in dk:
+        roof = {"bound": "int_pipe", "achieved": dk["hashes_per_s"] * dk["alu_instr_per_hash"] / 1e12, "peak": ipk["alu_per_s"] / 1e12,
+                "unit": "T thread-instr/s (ALU pipe)", "frac": dk["alu_pipe_frac"],
+                "peak_source": "measured live: register-only LOP3 loop (stark_bench_int_peak), 64 lanes/clk/SM",
+                "instr_source": instr_src}
+    elif dk["bound"] == "hbm":
+        roof = {"bound": "hbm", "achieved": dk.get("achieved_gbs"), "peak": hbm_peak, "unit": "GB/s", "frac": dk.get("hbm_frac"),
+                "peak_source": peak_src}
+    else:
+        roof = {"bound": dk["bound"], "achieved": dk.get("achieved_gbs"), "peak": hbm_peak, "unit": "GB/s",
+                "frac": dk.get("hbm_frac"), "peak_source": peak_src,
+                "note": "a chain of dependent hashes: neither roof applies; see hash_latency_cycles"}
+    roof.update({"kernel": dom["kernel"], "launches_per_step": dk["launches_per_step"],
+                 "avg_launch_ms": dom["ms"] / dom["launches"], "share_of_step": dk["share"],
+                 "traffic": (instr or {}).get("kernels", {}).get(dom["kernel"], {}).get("dram_bytes_per_launch"),
+                 "traffic_source": instr_src if instr else None,
+                 "algorithmic_bytes_per_launch": dom["bytes"] / dom["launches"] if dom["launches"] else None})
+    # the dominant HBM-bound kernel beside it
+    hb = [k for k in prof if KERNEL_BOUND.get(k["kernel"]) == "hbm" and k["bytes"] and k["ms"] > 0]
+    if hb:
+        hk = max(hb, key=lambda k: k["ms"])
+        roof["hbm_kernel"] = {"kernel": hk["kernel"], "achieved": kernels[hk["kernel"]]["achieved_gbs"], "peak": hbm_peak,
+                              "unit": "GB/s", "frac": kernels[hk["kernel"]]["hbm_frac"], "share_of_step": kernels[hk["kernel"]]["share"]}
 
+    golden = None
+    try:
+        golden = json.load(open(os.path.join(ROOT, "tests", "golden", "baseline_digests.json")))["cfg3"]
+    except Exception:
+        pass
+    default_cfg = (a.seed, a.log_n, a.log_blowup, a.nq) == (0x5354524B, 20, 2, 32)
+    psha = hashlib.sha256(proof_bytes).hexdigest()
+    cfg = config_of(a)
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
-        "ms_per_step": ms_dev / a.steps, "prove_ms": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u32 (Montgomery, p = 998244353)", "data": "synthetic (splitmix64, seed 0x%X)" % a.seed,
-        "config": {"workload": workload_name(a), "l2": "256 MiB buffer written between timed iterations",
-                   "timing": "CUDA events per step on the launching stream, summed, max over ranks",
-                   "proof_bytes": proof_len, "parallelism": "1 trace per GPU (no data-path collective)"},
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": W,
+        "ms_per_step": ms_dev / a.steps, "prove_ms": ms_dev / a.steps, "prove_ms_1col": ms_1col / a.steps,
+        "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u32 (Montgomery, p = 998244353)", "data": "synthetic (splitmix64, seed 0x%X + column)" % a.seed,
+        "config": cfg,
+        "notes": {"l2": "256 MiB buffer written between timed iterations",
+                  "timing": "CUDA events per step on the launching stream, summed, max over ranks",
+                  "parallelism": ("1 GPU" if world == 1 else
+                                  "%d ranks: columns 1.. round robin (LDE + tree, no exchange), column 0 LDE'd by every rank, "
+                                  "Fri::prove sharded by leaf / output range with peer-memory exchanges inside the kernels "
+                                  "(stark_mgpu_prove_trace)" % world)},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
-                "h2d_bytes_per_step": a.cols * n * 8, "d2h_bytes_per_step": proof_len + 32 * max(a.cols - 1, 0)},
+                "h2d_bytes_per_step": int(h2d_total), "d2h_bytes_per_step": world * (proof_len + 32 * a.cols)},
+        "comm": {"bytes_per_step": comm_bytes, "what": "subtree roots (36 B per rank pair and sharded round), folded-codeword "
+                 "slices and sharded authentication-path nodes stored into peers over NVLink, column roots",
+                 "limiter": "the serial Fiat-Shamir chain: per sharded round one subtree climb (~17 dependent hashes) + "
+                            "one root exchange; the column trees scale, the chain does not"} if world > 1 else None,
+        "proof": {"bytes": proof_len, "sha256": psha, "roots_sha256": hashlib.sha256(roots_bytes).hexdigest(),
+                  "identical_on_every_rank": bool(same_everywhere), "same_proof_with_1_column": proof_1col == proof_bytes,
+                  "matches_oracle_digest": (psha == golden["proof_sha256"]) if (golden and default_cfg) else None},
         "gpu_launches": launches, "gpu_launches_per_step": launches / a.steps,
-        "clocks": clocks, "roofline": roofline, "kernels": kernels,
+        "clocks": clocks, "roofline": roof, "kernels": kernels,
         "ms_per_rank_device_pass": (per_rank[0] if per_rank else None),
         "ms_per_step_profiled": ms_prof / a.steps, "hash_latency_cycles": ctx.hash_latency(), "int_peak": ipk,
     }
 
-    # the NTT / LDE half of the metric on its own: the six pass launches of the step (iNTT of the trace + zero-padded NTT on
-    # the 4x domain), from the per-kernel CUDA events of the profiled pass
+    # the NTT / LDE half of the metric on its own: the pass launches of the step, from the per-kernel CUDA events of the
+    # profiled pass (rank 0's share of the columns)
     lde_ms = sum(v["ms_per_step"] for k, v in kernels.items() if k.startswith("ntt_"))
     if lde_ms > 0:
-        line["lde"] = {"ms_per_step": lde_ms, "out_elems_per_s": a.cols * N / (lde_ms * 1e-3),
-                       "algorithmic_bytes_per_step": a.cols * (20 + 12 * ef) * n,
-                       "hbm_frac": a.cols * (20 + 12 * ef) * n / (lde_ms * 1e-3) / 1e9 / hbm_peak,
-                       "note": "one column is L2-resident and latency-bound at this size (256 / 1024 CTAs per launch); the "
-                               "batched figures are in profiles/r1z3_ntt_micro_batch16.jsonl"}
+        nc = len(mine)
+        line["lde"] = {"ms_per_step": lde_ms, "columns_on_rank0": nc, "out_elems_per_s": nc * N / (lde_ms * 1e-3),
+                       "algorithmic_bytes_per_step": nc * (20 + 12 * ef) * n,
+                       "hbm_frac": nc * (20 + 12 * ef) * n / (lde_ms * 1e-3) / 1e9 / hbm_peak}
     # Fri::verify of the timed proof on the device (stark_fri_verify; outside the timed region)
     try:
         t0 = time.perf_counter()
-        okd, whyd = ctx.fri_verify(proof_bytes, pow(3, (998244353 - 1) // N, 998244353), 3, N, ef, a.nq)
+        okd, whyd = ctx.fri_verify(proof_bytes, pow(3, (P - 1) // N, P), 3, N, ef, a.nq)
         line["proof_verified_on_device"] = {"ok": bool(okd), "reason": whyd, "ms_host_to_verdict": 1e3 * (time.perf_counter() - t0)}
     except Exception as e:  # noqa: BLE001
         line["proof_verified_on_device"] = {"ok": False, "reason": "error: %s" % e}
 
     if world == 1 and not a.no_cpu_baseline:
-        import oracle as O
-        threads = os.cpu_count() or 1
-        v0, s0 = cpu_pipeline(a, 0, a.cpu_sample_log_n, 2, 0, threads)
-        v1, s1 = cpu_pipeline(a, 1, 14, 2, 0, threads)
-        cpu_model = ""
-        try:
-            cpu_model = next(l.split(":", 1)[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name"))
-        except Exception:  # noqa: BLE001
-            pass
-        line["cpu_baseline"] = {
-            "value": v0, "unit": UNIT, "cores": threads, "cpu_model": cpu_model, "kind": "port",
-            "sample": "%d parallel pipelines on 2^%d-row traces, reference algorithms end to end (O(n^3) interpolate + "
-                      "Horner eval LDE, Merkle, Fri::prove), %.2f s per sample" % (threads, a.cpu_sample_log_n, s0)}
-        line["cpu_baseline_matched"] = {
-            "value": v1, "unit": UNIT, "cores": threads, "kind": "port+fast-ntt",
-            "sample": "%d parallel pipelines on 2^14-row traces, O(n log n) CPU NTT for the LDE (not in the reference), "
-                      "reference hash/Merkle/Fri::prove, %.2f s per sample" % (threads, s1)}
-        if not a.no_verify:
-            w = O.ff_prim_nth_root(N)
-            ok, why = O.fri_verify(proof_bytes, w, 3, N, ef, a.nq)
-            line["proof_verified_by_oracle"] = bool(ok)
-            if not ok:
-                line["verify_error"] = why
+        line.update(cpu_legs(a, proof_bytes, roots))
     print(json.dumps(line))
+    if group:
+        group.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def _bcast_digest(dist, world, digest):
+    """rank 0's digest on every rank"""
+    if world == 1:
+        return digest
+    box = [digest]
+    dist.broadcast_object_list(box, src=0)
+    return box[0]
+
+
+def cpu_legs(a, proof_bytes, roots):
+    """cpu_baseline: the SAME config once at full size on all host cores with the outputs compared
+    byte for byte with the GPU's; a 1-thread figure; the reference's own O(n^3) LDE timed at 2^7..2^10 rows with the
+    fitted exponent and the figure it extrapolates to at 2^20 rows (labelled as such)."""
+    import oracle as O
+    O.build()
+    threads = os.cpu_count() or 1
+    cpu_model = ""
+    try:
+        cpu_model = next(l.split(":", 1)[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name"))
+    except Exception:  # noqa: BLE001
+        pass
+    out = {}
+    cols = synth_cols(a, a.log_n)
+    sec, c_roots, c_proof = cpu_config3(O, cols, a.log_n, a.log_blowup, a.nq, threads)
+    N = 1 << (a.log_n + a.log_blowup)
+    out["cpu_baseline"] = {
+        "value": a.cols * N / sec, "unit": UNIT, "cores": threads, "cpu_model": cpu_model, "kind": "port", "same_config": True,
+        "seconds_per_step": sec,
+        "sample": "ONE execution of the full config (%d cols x 2^%d rows) on %d host threads: O(n log n) CPU NTT for the LDE "
+                  "(the reference's O(n^3) interpolate_domain cannot reach this size; see reference_algorithm), hash / Merkle "
+                  "/ Fiat-Shamir / Fri::prove by the restatement of the reference" % (a.cols, a.log_n, threads),
+        "outputs_identical_to_gpu": bool(c_proof == proof_bytes and b"".join(c_roots) == roots.tobytes())}
+    if not a.no_verify:
+        ok, why = O.fri_verify(proof_bytes, O.ff_prim_nth_root(N), 3, N, 1 << a.log_blowup, a.nq)
+        out["proof_verified_by_oracle"] = bool(ok)
+        if not ok:
+            out["verify_error"] = why
+    # one thread, one column, 2^16 rows (per-element cost is flat in n)
+    ln1 = min(16, a.log_n)
+    a1 = argparse.Namespace(**vars(a))
+    a1.cols = 1
+    s1, _, _ = cpu_config3(O, synth_cols(a1, ln1), ln1, a.log_blowup, min(a.nq, 1 << (ln1 - 1)), 1)
+    out["cpu_baseline_1thread"] = {"value": (1 << (ln1 + a.log_blowup)) / s1, "unit": UNIT, "cores": 1, "kind": "port",
+                                   "sample": "1 col x 2^%d rows, LDE + Merkle + Fri::prove, one thread, %.2f s" % (ln1, s1)}
+    # the reference's own LDE (interpolate_domain O(n^3) + eval_domain O(n m)) end to end, one pipeline, one thread
+    O.set_threads(1)
+    pts = []
+    for ln in (7, 8, 9, 10):
+        s, _ = O.bench_pipeline(0, ln, a.log_blowup, min(a.nq, 1 << max(ln - 2, 0)), a.seed, 1)
+        pts.append((ln, s))
+    (l0, s0), (l1, sl) = pts[-2], pts[-1]
+    expo = float(np.log2(sl / s0) / (l1 - l0))
+    out["reference_algorithm"] = {
+        "what": "the reference's own algorithms end to end (interpolate_domain + eval_domain LDE, Merkle, Fri::prove), one "
+                "pipeline on one thread (the reference is single-threaded), one column",
+        "seconds": {"2^%d" % ln: s for ln, s in pts}, "fitted_exponent": expo,
+        "extrapolated": {"rows": "2^%d" % a.log_n, "seconds_per_column": sl * 2.0 ** (expo * (a.log_n - l1)),
+                         "label": "EXTRAPOLATED from 2^%d rows with the fitted exponent; never run" % l1}}
+    O.set_threads(threads)
+    return out
 
 
 def _protect_stdout():

@@ -252,6 +252,79 @@ int stark_prove_trace_rows(stark_ctx *ctx, const void *rows_i128, uint32_t n_col
                            uint64_t offset, uint32_t num_colinearity_tests, uint8_t *column_roots, uint8_t *proof,
                            size_t proof_cap, size_t *proof_len);
 
+/* ---- groups of GPUs ---------------------------------------------------------------------------------
+ * The reference is single-threaded and has no parallel path; these entry points shard ITS functions over
+ * the GPUs of one node with byte-identical results for every group size: independent trace-column LDEs and column trees
+ * (no exchange), Merkle trees split by leaf range (MerkleTree::new, merkle.rs:11-38: the ranks' subtree roots are
+ * exchanged and the top levels replicated), fold_codeword split by output range (fri.rs:57-91: every rank stores its
+ * slice into all replicas of the next codeword).  The library owns the NCCL communicator (loaded with dlopen) and the
+ * peer-memory windows; a host in any language drives it through these calls.
+ *
+ * A stark_mgpu is ONE RANK's membership in a group of `world` (1, 2, 4 or 8) GPUs.  Two ways to make a group:
+ *   stark_mgpu_init          one process or thread per GPU.  Rank 0 calls stark_mgpu_unique_id and hands the 128 bytes
+ *                            to the others (any channel); every rank then calls stark_mgpu_init on its own context.
+ *                            Collective: all ranks must call it, and every later operation, in the same order.
+ *   stark_mgpu_create_local  one host thread driving `world` contexts (distinct devices with peer access -- or the same
+ *                            device, which is how single-GPU tests exercise the sharded path; such a group runs in
+ *                            lock step).  Fills out[0 .. world).
+ * Operations take the ranks THIS CALL DRIVES: one handle (n_here = 1) in a multi-process group, all `world` handles in
+ * rank order in a local group; per-rank arguments are arrays of n_here entries.  Errors: STARK_ERR_NCCL when NCCL fails
+ * or a peer does not arrive within 4 s (the kernels never spin forever); STARK_ERR_ARG mirrors the reference's panics as
+ * everywhere else.  max_codeword = the longest codeword / LDE column the group will fold (sizes the window).          */
+typedef struct stark_mgpu stark_mgpu;
+#define STARK_MGPU_ID_BYTES 128
+int stark_mgpu_unique_id(uint8_t id[STARK_MGPU_ID_BYTES]);
+int stark_mgpu_init(stark_ctx *ctx, const uint8_t id[STARK_MGPU_ID_BYTES], int rank, int world, size_t max_codeword,
+                    stark_mgpu **out);
+int stark_mgpu_create_local(stark_ctx *const *ctxs, int world, size_t max_codeword, stark_mgpu **out);
+void stark_mgpu_destroy(stark_mgpu *m); /* a local group is destroyed as a whole, through any one of its handles */
+int stark_mgpu_rank(const stark_mgpu *m);
+int stark_mgpu_world(const stark_mgpu *m);
+/* bytes this rank has stored into its peers or handed to NCCL so far (data path only) */
+uint64_t stark_mgpu_bytes_sent(const stark_mgpu *m);
+/* FRI rounds of at least 2^log_n elements are sharded, shorter ones run replicated (default 17, STARK_MGPU_SHARD_LOG) */
+int stark_mgpu_set_shard_log(stark_mgpu *m, uint32_t log_n);
+int stark_mgpu_barrier(stark_mgpu *m); /* device-side barrier over the group + synchronisation of this rank's stream */
+/* the trace columns (indices > 0) this rank commits in stark_mgpu_prove_trace; returns their number */
+uint32_t stark_mgpu_owned_columns(const stark_mgpu *m, uint32_t n_cols, uint32_t *out);
+
+/* BASELINE config 3 on a group = stark_prove_trace with the work sharded: column 0 is LDE'd by every rank (its codeword
+ * is the FRI input), columns 1.. are LDE'd and committed round robin (column c by rank (c - 1) % world), Fri::prove runs
+ * sharded (fri.rs:250-311).  `cols` is the WHOLE column-major trace on every rank (each rank uploads only what it needs);
+ * the _dev form takes per rank a buffer holding column 0 followed by the rank's owned columns.  EVERY rank receives all
+ * n_cols column roots and the complete proof bytes, identical to stark_prove_trace's.                               */
+int stark_mgpu_prove_trace(stark_mgpu *const *ranks, int n_here, const uint64_t *cols, uint32_t n_cols, uint32_t log_n,
+                           uint32_t log_blowup, uint64_t offset, uint32_t num_colinearity_tests,
+                           uint8_t *const *column_roots, uint8_t *const *proofs, size_t proof_cap, size_t *proof_len);
+int stark_mgpu_prove_trace_dev(stark_mgpu *const *ranks, int n_here, const stark_buf *const *my_cols, uint32_t n_cols,
+                               uint32_t log_n, uint32_t log_blowup, uint64_t offset, uint32_t num_colinearity_tests,
+                               uint8_t *const *column_roots, uint8_t *const *proofs, size_t proof_cap, size_t *proof_len);
+/* Fri::prove (fri.rs:250-311) + ProofStream::serialize on a group; codewords[k] = rank k's replica of the codeword */
+int stark_mgpu_fri_prove_dev(stark_mgpu *const *ranks, int n_here, const stark_buf *const *codewords, size_t n,
+                             size_t domain_length, uint64_t offset, uint64_t omega, uint32_t expansion_factor,
+                             uint32_t num_colinearity_tests, const uint8_t *transcript, size_t transcript_len,
+                             uint8_t *const *proofs, size_t proof_cap, size_t *proof_len, uint64_t *const *top_indices);
+/* BASELINE config 5: ONE round of Fri::commit (fri.rs:116-147) on a replicated codeword -- leaf hashes + tree (sharded by
+ * leaf range), alpha from a fresh transcript, fold (sharded by output range, stored into every replica).  roots[k] (32
+ * bytes), alpha_raw[k], folded[k] (a view of rank k's replica of the folded codeword inside the window: valid until the
+ * group's next operation; free the view with stark_buf_free) are per driven rank; omega need not have order n
+ * (Fri::new never checks it, fri.rs:30-55).                                                                        */
+int stark_mgpu_fold_commit_round(stark_mgpu *const *ranks, int n_here, const stark_buf *const *codewords, size_t n,
+                                 uint64_t offset, uint64_t omega, uint8_t *const *roots, uint64_t *alpha_raw,
+                                 stark_buf **folded);
+/* BASELINE config 4: n_groups fixed groups of group_width trace columns (column-major, group k at cols + k *
+ * group_width * 2^log_n); rank g owns groups {g, g + world, ...}: coset LDE (eval.rs / interpolate.rs composed, SURVEY
+ * 3.4) and one Merkle tree per group with leaf i = Hash::from_field_elements(row i of the group's LDE) (hash.rs:32-35);
+ * the group roots are gathered (ncclAllGather in a multi-process group) and the commitment is MerkleTree::new over them
+ * (merkle.rs:11-38).  The _dev form takes, per driven rank, n_groups / world device buffers (rank-major array).
+ * group_roots[k]: n_groups x 32 bytes; commitments[k]: 32 bytes.                                                    */
+int stark_mgpu_lde_commit(stark_mgpu *const *ranks, int n_here, const uint64_t *cols, uint32_t n_groups, uint32_t group_width,
+                          uint32_t log_n, uint32_t log_blowup, uint64_t offset, uint8_t *const *group_roots,
+                          uint8_t *const *commitments);
+int stark_mgpu_lde_commit_dev(stark_mgpu *const *ranks, int n_here, const stark_buf *const *owned_groups, uint32_t n_groups,
+                              uint32_t group_width, uint32_t log_n, uint32_t log_blowup, uint64_t offset,
+                              uint8_t *const *group_roots, uint8_t *const *commitments);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,7 +13,7 @@ import numpy as np
 
 __all__ = ["P", "StarkError", "StarkPanic", "Context", "Buffer", "MerkleTree", "FriState", "lib", "lib_path",
            "build_library", "prim_nth_root", "fri_num_rounds", "fri_proof_size", "fri_sample_indices",
-           "fiat_shamir_challenge", "hash_from_u64"]
+           "fiat_shamir_challenge", "hash_from_u64", "Group", "mgpu_unique_id"]
 
 P = 998244353
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -668,3 +668,163 @@ class Context:
         _chk(lib().stark_prove_trace_dev(self.h, cols_buf.h, U32(n_cols), U32(log_n), U32(log_blowup), U64(offset),
                                          U32(nq), _p8(roots), _p8(proof), SZ(len(proof)), C.byref(ln)))
         return ln.value
+
+
+# ---------------------------------------------------------------------------------------------- groups of GPUs
+
+def mgpu_unique_id():
+    """stark_mgpu_unique_id: 128 bytes rank 0 hands to the other ranks (any channel) before Group.init"""
+    out = np.zeros(128, dtype=np.uint8)
+    _chk(lib().stark_mgpu_unique_id(_p8(out)))
+    return out.tobytes()
+
+
+class Group:
+    """The ranks of a GPU group THIS PROCESS drives (include/stark_b200.h, "groups of GPUs"): one handle after
+    Group.init (one process per GPU, NCCL + CUDA IPC inside the library), all of them after Group.local (one host thread,
+    several contexts).  Every operation is collective: all ranks of the group call it in the same order.  Per-rank
+    results come back as lists with one entry per driven rank."""
+
+    def __init__(self, handles, ctxs, local):
+        self.h, self.ctxs, self.is_local = handles, ctxs, local
+        self.n_here = len(handles)
+        self._arr = (C.c_void_p * self.n_here)(*[x.value for x in handles])
+        lib().stark_mgpu_bytes_sent.restype = C.c_uint64
+
+    @classmethod
+    def init(cls, ctx, unique_id, rank, world, max_codeword):
+        h = C.c_void_p()
+        uid = _b(unique_id)
+        assert len(uid) == 128
+        _chk(lib().stark_mgpu_init(ctx.h, _p8(uid), C.c_int(rank), C.c_int(world), SZ(max_codeword), C.byref(h)))
+        return cls([h], [ctx], False)
+
+    @classmethod
+    def local(cls, ctxs, max_codeword):
+        n = len(ctxs)
+        arr = (C.c_void_p * n)(*[c.h.value for c in ctxs])
+        out = (C.c_void_p * n)()
+        _chk(lib().stark_mgpu_create_local(arr, C.c_int(n), SZ(max_codeword), out))
+        return cls([C.c_void_p(out[i]) for i in range(n)], list(ctxs), True)
+
+    def close(self):
+        if self.h:
+            if self.is_local:
+                lib().stark_mgpu_destroy(self.h[0])
+            else:
+                for x in self.h:
+                    lib().stark_mgpu_destroy(x)
+            self.h = []
+
+    @property
+    def world(self):
+        return lib().stark_mgpu_world(self.h[0])
+
+    @property
+    def ranks(self):
+        return [lib().stark_mgpu_rank(x) for x in self.h]
+
+    @property
+    def bytes_sent(self):
+        return [int(lib().stark_mgpu_bytes_sent(x)) for x in self.h]
+
+    def set_shard_log(self, log_n):
+        _chk(lib().stark_mgpu_set_shard_log(self.h[0], U32(log_n)))
+
+    def barrier(self):
+        if self.is_local:
+            _chk(lib().stark_mgpu_barrier(self.h[0]))
+        else:
+            for x in self.h:
+                _chk(lib().stark_mgpu_barrier(x))
+
+    def owned_columns(self, n_cols):
+        """per driven rank: the trace columns (> 0) it commits in prove_trace"""
+        res = []
+        for x in self.h:
+            out = (C.c_uint32 * max(n_cols, 1))()
+            k = lib().stark_mgpu_owned_columns(x, U32(n_cols), out)
+            res.append([int(out[i]) for i in range(k)])
+        return res
+
+    # per-rank output arrays -> C arrays of pointers
+    def _outs(self, arrays):
+        return (C.c_void_p * self.n_here)(*[a.ctypes.data for a in arrays])
+
+    def _bufs(self, bufs):
+        return (C.c_void_p * len(bufs))(*[b.h.value for b in bufs])
+
+    def prove_trace(self, cols, log_blowup, offset=3, num_colinearity_tests=32):
+        """stark_mgpu_prove_trace: cols = the WHOLE trace (n_cols, n).  -> [(column_roots, proof bytes)] per driven rank"""
+        cols = np.ascontiguousarray(np.asarray(cols, dtype=np.uint64))
+        if cols.ndim == 1:
+            cols = cols[None, :]
+        n_cols, n = cols.shape
+        log_n = n.bit_length() - 1
+        cap = fri_proof_size(n << log_blowup, 1 << log_blowup, num_colinearity_tests)
+        proofs = [np.zeros(cap, dtype=np.uint8) for _ in self.h]
+        roots = [np.zeros((n_cols, 32), dtype=np.uint8) for _ in self.h]
+        ln = SZ()
+        _chk(lib().stark_mgpu_prove_trace(self._arr, C.c_int(self.n_here), _p64(cols), U32(n_cols), U32(log_n), U32(log_blowup),
+                                          U64(offset), U32(num_colinearity_tests), self._outs(roots), self._outs(proofs),
+                                          SZ(cap), C.byref(ln)))
+        return [(r, p[: ln.value].tobytes()) for r, p in zip(roots, proofs)]
+
+    def prove_trace_ptr(self, host_ptr, n_cols, log_n, log_blowup, offset, nq, roots, proofs):
+        """same from a raw (pinned) host pointer to the whole trace into preallocated per-rank numpy outputs"""
+        ln = SZ()
+        _chk(lib().stark_mgpu_prove_trace(self._arr, C.c_int(self.n_here), C.cast(host_ptr, U64P), U32(n_cols), U32(log_n),
+                                          U32(log_blowup), U64(offset), U32(nq), self._outs(roots), self._outs(proofs),
+                                          SZ(len(proofs[0])), C.byref(ln)))
+        return ln.value
+
+    def prove_trace_dev(self, my_cols, n_cols, log_n, log_blowup, offset, nq, roots, proofs):
+        """my_cols[k]: Buffer with column 0 followed by rank k's owned columns"""
+        ln = SZ()
+        _chk(lib().stark_mgpu_prove_trace_dev(self._arr, C.c_int(self.n_here), self._bufs(my_cols), U32(n_cols), U32(log_n),
+                                              U32(log_blowup), U64(offset), U32(nq), self._outs(roots), self._outs(proofs),
+                                              SZ(len(proofs[0])), C.byref(ln)))
+        return ln.value
+
+    def fri_prove_dev(self, codewords, n, offset, omega, expansion_factor, num_colinearity_tests, transcript=b"",
+                      domain_length=None):
+        """-> [(proof bytes, top indices)] per driven rank"""
+        t = _b(transcript)
+        cap = fri_proof_size(n, expansion_factor, num_colinearity_tests)
+        proofs = [np.zeros(cap, dtype=np.uint8) for _ in self.h]
+        tops = [np.zeros(max(num_colinearity_tests, 1), dtype=np.uint64) for _ in self.h]
+        ln = SZ()
+        _chk(lib().stark_mgpu_fri_prove_dev(self._arr, C.c_int(self.n_here), self._bufs(codewords), SZ(n),
+                                            SZ(n if domain_length is None else domain_length), U64(offset), U64(omega),
+                                            U32(expansion_factor), U32(num_colinearity_tests), _p8(t), SZ(len(t)),
+                                            self._outs(proofs), SZ(cap), C.byref(ln), self._outs(tops)))
+        return [(p[: ln.value].tobytes(), [int(x) for x in tp[:num_colinearity_tests]]) for p, tp in zip(proofs, tops)]
+
+    def fold_commit_round(self, codewords, n, offset, omega):
+        """BASELINE config 5 round -> [(root bytes, alpha_raw, folded Buffer view)] per driven rank"""
+        roots = [np.zeros(32, dtype=np.uint8) for _ in self.h]
+        alphas = (C.c_uint64 * self.n_here)()
+        folded = (C.c_void_p * self.n_here)()
+        _chk(lib().stark_mgpu_fold_commit_round(self._arr, C.c_int(self.n_here), self._bufs(codewords), SZ(n), U64(offset),
+                                                U64(omega), self._outs(roots), alphas, folded))
+        return [(roots[k].tobytes(), int(alphas[k]), Buffer(self.ctxs[k], C.c_void_p(folded[k]))) for k in range(self.n_here)]
+
+    def lde_commit(self, cols, n_groups, group_width, log_n, log_blowup, offset=3):
+        """BASELINE config 4 from the whole host trace (n_groups * group_width columns of 2^log_n rows, column-major)
+        -> [(group roots (n_groups, 32), commitment bytes)] per driven rank"""
+        cols = _u64(cols)
+        assert len(cols) == (n_groups * group_width) << log_n
+        roots = [np.zeros((n_groups, 32), dtype=np.uint8) for _ in self.h]
+        com = [np.zeros(32, dtype=np.uint8) for _ in self.h]
+        _chk(lib().stark_mgpu_lde_commit(self._arr, C.c_int(self.n_here), _p64(cols), U32(n_groups), U32(group_width),
+                                         U32(log_n), U32(log_blowup), U64(offset), self._outs(roots), self._outs(com)))
+        return [(r, c.tobytes()) for r, c in zip(roots, com)]
+
+    def lde_commit_dev(self, owned_groups, n_groups, group_width, log_n, log_blowup, offset=3):
+        """owned_groups: rank-major flat list of Buffers (n_groups / world per driven rank)"""
+        roots = [np.zeros((n_groups, 32), dtype=np.uint8) for _ in self.h]
+        com = [np.zeros(32, dtype=np.uint8) for _ in self.h]
+        _chk(lib().stark_mgpu_lde_commit_dev(self._arr, C.c_int(self.n_here), self._bufs(owned_groups), U32(n_groups),
+                                             U32(group_width), U32(log_n), U32(log_blowup), U64(offset), self._outs(roots),
+                                             self._outs(com)))
+        return [(r, c.tobytes()) for r, c in zip(roots, com)]

@@ -19,6 +19,7 @@
 #include "hash.cuh"
 #include "merkle.h"
 #include "merkle_dev.cuh"
+#include "mgpu.h"
 
 using hs::State;
 using ntt::GeoTables;
@@ -373,7 +374,11 @@ struct stark_fri_state {
   u32 rounds;                 // Fri::num_rounds()
   std::vector<u32 *> cw;      // codewords[i] (fri.rs:110,140,153); cw[0] borrowed if !own0
   std::vector<size_t> len;
-  std::vector<stark_tree *> trees;  // tree of codewords[i] for i < rounds
+  std::vector<stark_tree *> trees;  // tree of codewords[i] for i < rounds (sharded rounds: this rank's SUBTREE)
+  std::vector<bool> borrowed;       // cw[i] lives in the multi-GPU window (not freed here)
+  // sharded prover (mgpu.h): rounds [0, sharded) have their tree split by leaf range over the ranks
+  u32 sharded = 0, log_per[MG_MAX_ROUNDS] = {};   // log2 of the leaves per rank of a sharded round
+  std::vector<u8 *> top_nodes;      // per sharded round: the replicated top tree over the ranks' subtree roots
   bool own0;
   u8 *d_roots;        // rounds * 32
   u64 *d_alpha_raw;   // rounds entries (last unused)
@@ -397,8 +402,9 @@ static void fri_state_free(stark_fri_state *s) {
   if (!s) return;
   stark_ctx *ctx = s->ctx;
   for (size_t i = 0; i < s->cw.size(); i++)
-    if (i > 0 || s->own0) dev_free(ctx, s->cw[i]);
+    if ((i > 0 || s->own0) && !(i < s->borrowed.size() && s->borrowed[i])) dev_free(ctx, s->cw[i]);
   for (stark_tree *t : s->trees) stark_merkle_free(t);
+  for (u8 *t : s->top_nodes) dev_free(ctx, t);
   dev_free(ctx, s->d_roots), dev_free(ctx, s->d_alpha_raw), dev_free(ctx, s->d_alpha_m), dev_free(ctx, s->d_tr);
   delete s;
 }
@@ -425,9 +431,22 @@ static int fold_launch(stark_ctx *ctx, const u32 *cw, u32 *out, size_t h, int r,
   return fold_launch_range(ctx, cw, out, h, 0, h, r, G, g_r_m, alpha_m, inv2off_m);
 }
 
-// Fri::commit (fri.rs:105-156) on device.  cw0 is borrowed unless copy0.
-static int fri_commit_dev(stark_ctx *ctx, const u32 *cw0, size_t n, u32 offset, u32 omega, u32 ef, u32 nq,
-                          const u8 *transcript, size_t transcript_len, bool copy0, stark_fri_state **out) {
+// The domain constants a round of Fri::commit carries (fri.rs:146-147): off_r / g_r belong to round r, the fold INTO
+// round r uses those of round r-1.
+struct RoundConsts {
+  u32 off_r, g_r, off_prev, g_prev;
+  size_t len;     // length of codewords[r]
+};
+static void round_consts_next(RoundConsts &c) {
+  c.off_prev = c.off_r, c.g_prev = c.g_r;
+  c.off_r = ff::mul(c.off_r, c.off_r), c.g_r = ff::mul(c.g_r, c.g_r);  // fri.rs:146-147
+  c.len /= 2;
+}
+
+// Allocations and transcript of Fri::commit (fri.rs:105-115).  cw0 is borrowed unless copy0.
+static int fri_commit_setup(stark_ctx *ctx, const u32 *cw0, size_t n, u32 offset, u32 omega, u32 ef, u32 nq,
+                            const u8 *transcript, size_t transcript_len, bool copy0, stark_fri_state **out, GeoTables *G_out,
+                            RoundConsts *C_out) {
   u32 R = 0;
   ST_TRY(fri_check(ctx, n, ef, &R, nq));
   // fold_codeword divides by x = offset * w^i (fri.rs:72-78 -> ff.rs:182)
@@ -442,6 +461,7 @@ static int fri_commit_dev(stark_ctx *ctx, const u32 *cw0, size_t n, u32 offset, 
   TRY_(dev_alloc(ctx, (void **)&s->d_alpha_raw, (size_t)(R ? R : 1) * 8));
   TRY_(dev_alloc(ctx, (void **)&s->d_alpha_m, (size_t)(R ? R : 1) * 4));
   TRY_(dev_alloc(ctx, (void **)&s->d_tr, sizeof(TranscriptDev)));
+#undef TRY_
   if (rc == STARK_OK) {
     TranscriptDev t;
     tr_init(t);
@@ -457,24 +477,36 @@ static int fri_commit_dev(stark_ctx *ctx, const u32 *cw0, size_t n, u32 offset, 
       rc = stark_fail(ctx, STARK_ERR_CUDA, "D2D copy failed");
     cur = c;
   }
-  if (rc == STARK_OK) s->cw.push_back(cur), s->len.push_back(n);
+  if (rc == STARK_OK) s->cw.push_back(cur), s->len.push_back(n), s->borrowed.push_back(false);
   GeoTables G = {nullptr, nullptr};
   u32 g0 = 1;
   if (rc == STARK_OK && R > 1) {
     g0 = ff::inv(omega);
     rc = geo_tables(ctx, g0, 1, n / 2, &G);
   }
-  // Round r:  [r > 0: fold of round r-1 fused with this round's leaf hashes]  ->  tree  ->  root + transcript (alpha_r).
-  // off_r / g_r are the domain constants of round r (fri.rs:146-147); the fold INTO round r uses those of round r-1.
-  u32 off_r = offset, g_r = g0, off_prev = offset, g_prev = g0;
-  size_t len = n;
-  for (u32 r = 0; r < R && rc == STARK_OK; r++) {
+  if (rc != STARK_OK) {
+    fri_state_free(s);
+    return rc;
+  }
+  *out = s, *G_out = G;
+  *C_out = RoundConsts{offset, g0, offset, g0, n};
+  return STARK_OK;
+}
+
+// Rounds [r0, R) of Fri::commit (fri.rs:116-147) on this device alone; codewords[r0 - 1] (if r0 > 0) and its alpha are in
+// the state.  Round r:  [r > 0: fold of round r-1 fused with this round's leaf hashes]  ->  tree  ->  root + transcript.
+static int fri_commit_rounds(stark_ctx *ctx, stark_fri_state *s, u32 r0, GeoTables G, RoundConsts C) {
+  const u32 R = s->rounds;
+  int rc = STARK_OK;
+  u32 &off_r = C.off_r, &off_prev = C.off_prev, &g_prev = C.g_prev;
+  size_t &len = C.len;
+  for (u32 r = r0; r < R && rc == STARK_OK; r++) {
     const bool tail = len >= 2 && len <= ((size_t)1 << TAIL_LOG) && R - r <= (u32)TAIL_MAX_ROUNDS;
     if (r > 0) {
       u32 *nxt = nullptr;
       rc = dev_alloc(ctx, (void **)&nxt, len * 4);
       if (rc != STARK_OK) break;
-      s->cw.push_back(nxt), s->len.push_back(len);
+      s->cw.push_back(nxt), s->len.push_back(len), s->borrowed.push_back(false);
     }
     if (tail) {
       // the remaining rounds in one single-CTA launch (its input codeword still has to be folded)
@@ -503,7 +535,7 @@ static int fri_commit_dev(stark_ctx *ctx, const u32 *cw0, size_t n, u32 offset, 
           rc = dev_alloc(ctx, (void **)&nxt, (l / 2) * 4);
           if (rc != STARK_OK) break;
           A.cw[i + 1] = nxt;
-          s->cw.push_back(nxt), s->len.push_back(l / 2);
+          s->cw.push_back(nxt), s->len.push_back(l / 2), s->borrowed.push_back(false);
           l /= 2;
           off_r = ff::mul(off_r, off_r);
         }
@@ -534,12 +566,20 @@ static int fri_commit_dev(stark_ctx *ctx, const u32 *cw0, size_t n, u32 offset, 
     const TranscriptArgs tr = {s->d_tr, s->d_roots + 32 * r, last ? 0 : 1, s->d_alpha_raw + r, s->d_alpha_m + r};
     rc = merkle_climb_dev(ctx, tree->nodes, len, &tr);
     if (rc != STARK_OK) break;
-    off_prev = off_r, g_prev = g_r;
-    off_r = ff::mul(off_r, off_r), g_r = ff::mul(g_r, g_r);  // fri.rs:146-147
-    len /= 2;
+    round_consts_next(C);
   }
-#undef TRY_
   if (rc == STARK_OK && cudaGetLastError() != cudaSuccess) rc = stark_fail(ctx, STARK_ERR_CUDA, "kernel launch failed");
+  return rc;
+}
+
+// Fri::commit (fri.rs:105-156) on device.  cw0 is borrowed unless copy0.
+static int fri_commit_dev(stark_ctx *ctx, const u32 *cw0, size_t n, u32 offset, u32 omega, u32 ef, u32 nq,
+                          const u8 *transcript, size_t transcript_len, bool copy0, stark_fri_state **out) {
+  stark_fri_state *s = nullptr;
+  GeoTables G;
+  RoundConsts C;
+  ST_TRY(fri_commit_setup(ctx, cw0, n, offset, omega, ef, nq, transcript, transcript_len, copy0, &s, &G, &C));
+  const int rc = fri_commit_rounds(ctx, s, 0, G, C);
   if (rc != STARK_OK) {
     fri_state_free(s);
     return rc;
@@ -642,6 +682,761 @@ static int reduce_params(stark_ctx *ctx, uint64_t offset, uint64_t omega, u32 *o
   *off = ff::reduce64(offset), *om = ff::reduce64(omega);
   (void)ctx;
   return STARK_OK;
+}
+
+// ============================================================================ sharded prover (mgpu.h)
+//
+// Fri::prove on G ranks.  Every rank holds a replica of the round-0 codeword.  Rounds with at least 2^shard_log elements
+// are SHARDED: rank g hashes the leaves [g n/G, (g+1) n/G) into a subtree, the subtree roots are exchanged through the
+// peer windows inside the kernel that produces them (merkle_dev.cuh: mg_exchange_top), every rank climbs the G roots to
+// the root and draws alpha; the fold into the next sharded round computes the rank's own output range and stores it
+// into EVERY rank's replica (fused fold + all-gather over NVLink), hashing its leaves on the way.  The remaining rounds
+// are latency-bound and run replicated on every rank (no exchange).  In the query phase the rank that owns a subtree
+// node stores it into every rank's proof buffer, so that every rank ends up with the complete ProofStream::serialize
+// bytes -- identical to the single-GPU path and to the reference for every G.
+
+struct FoldPeersN {
+  u32 *out[MG_MAX_RANKS];   // every rank's replica of the next codeword (own included), indexed by the global output index
+  int n;
+};
+// outputs [i0, i1) of fold_codeword (fri.rs:57-91): two per thread, stored into all replicas, leaf-hashed (fri.rs:118-121)
+// into this rank's subtree (leaf index i - i0).  i0, i1, h even.
+__global__ void __launch_bounds__(64) k_mg_fold_leaf(const u32 *__restrict__ cw, const __grid_constant__ FoldPeersN P, size_t h,
+                                                      size_t i0, size_t i1, int r, GeoTables G, u32 g_r_m,
+                                                      const u32 *__restrict__ alpha_m, u32 inv2off_m, u8 *__restrict__ leaves) {
+  pdl_entry();
+  const size_t i = i0 + 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
+  if (i >= i1) return;
+  const u32 K = ff::canon(ff::mont_mul(*alpha_m, inv2off_m));
+  // the codeword was written by the peers: read it past L1
+  const uint2 x = __ldcg(reinterpret_cast<const uint2 *>(cw + i)), y = __ldcg(reinterpret_cast<const uint2 *>(cw + h + i));
+  const u32 tw0 = ff::canon(ff::mont_mul(ntt::geo_pow(G, (u64)i << r), K));
+  const u32 tw1 = ff::canon(ff::mont_mul(tw0, g_r_m));
+  const u32 o0 = ff::canon4(ff::half(x.x + y.x) + ff::mont_mul(x.x + ff::P - y.x, tw0));
+  const u32 o1 = ff::canon4(ff::half(x.y + y.y) + ff::mont_mul(x.y + ff::P - y.y, tw1));
+  const uint2 o = make_uint2(o0, o1);
+#pragma unroll 1
+  for (int g = 0; g < P.n; g++) *reinterpret_cast<uint2 *>(P.out[g] + i) = o;
+  u32 wa[8], wb[8];
+  hs2::leaf2(o0, o1, wa, wb, blockDim.y);
+  store_hash(leaves + 32 * (i - i0), wa);
+  store_hash(leaves + 32 * (i - i0) + 32, wb);
+  __threadfence_system();   // the slice is visible to the peers before this rank raises the round's root flag
+}
+
+// the query rounds (k_proof_rounds) when some trees are sharded.  Replicated data (triples, path headers, top-tree and
+// unsharded-tree nodes) goes to this rank's own proof buffer; a node of a sharded level is written by the rank that
+// owns it, into EVERY rank's buffer.
+struct MgProofArgs {
+  ProofRoundsArgs A;
+  u32 log_per[MG_MAX_ROUNDS + 1];        // sharded tree: log2(leaves per rank); 0xff: whole tree in A.nodes
+  const u8 *top[MG_MAX_ROUNDS + 1];      // sharded tree: replicated top tree (2G - 1 hashes)
+  u8 *out[MG_MAX_RANKS];                 // every rank's proof buffer
+  int world, rank;
+};
+__global__ void k_mg_proof_rounds(const __grid_constant__ MgProofArgs M, const u64 *top) {
+  pdl_entry();
+  const ProofRoundsArgs &A = M.A;
+  const u32 i = blockIdx.y, nq = A.nq;
+  u8 *out = M.out[M.rank] + A.out_off[i];
+  const u64 cur_len = A.len0 >> i;
+  const u32 depth_cur = A.depth0 - i;
+  const u64 half = cur_len >> 1;
+  const u32 depth_nxt = depth_cur - 1;
+  const u64 triples = 33ull * nq;
+  const u64 path_cur = 9 + 32ull * depth_cur, path_nxt = 9 + 32ull * depth_nxt;
+  const u64 per_q = 2 * path_cur + path_nxt;
+  const u32 hashes_per_q = 2 * depth_cur + depth_nxt;
+  const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nq) {
+    const u32 *cur = A.cw[i], *nxt = A.cw[i + 1];
+    const u64 c = top[t] % half;
+    u8 *d = out + 33 * t;
+    d[0] = 2;
+    put_u64(d + 1, 3);
+    put_u64(d + 9, __ldcg(cur + c));
+    put_u64(d + 17, __ldcg(cur + c + half));
+    put_u64(d + 25, __ldcg(nxt + c));
+    u8 *p = out + triples + per_q * t;
+    p[0] = 3, put_u64(p + 1, depth_cur);
+    p += path_cur;
+    p[0] = 3, put_u64(p + 1, depth_cur);
+    p += path_cur;
+    p[0] = 3, put_u64(p + 1, depth_nxt);
+  }
+  if (t >= (u64)nq * hashes_per_q) return;
+  const u32 q = (u32)(t / hashes_per_q), k = (u32)(t % hashes_per_q);
+  const u64 c = top[q] % half;
+  u64 leaf, n_tree;
+  u32 level, tree;
+  u64 dst_off = A.out_off[i] + triples + per_q * q;
+  if (k < depth_cur) {
+    leaf = c, tree = i, n_tree = cur_len, level = k, dst_off += 9 + 32ull * level;
+  } else if (k < 2 * depth_cur) {
+    leaf = c + half, tree = i, n_tree = cur_len, level = k - depth_cur, dst_off += path_cur + 9 + 32ull * level;
+  } else {
+    leaf = c, tree = i + 1, n_tree = half, level = k - 2 * depth_cur, dst_off += 2 * path_cur + 9 + 32ull * level;
+  }
+  const u64 sib = (leaf >> level) ^ 1;  // merkle.rs:73-77
+  const u32 lp = M.log_per[tree];
+  const uint4 *src;
+  bool everywhere = false;
+  if (lp == 0xffu) {
+    src = reinterpret_cast<const uint4 *>(A.nodes[tree] + 32 * ((2 * n_tree - 2 * (n_tree >> level)) + sib));
+  } else if (level >= lp) {
+    const u64 G = (u64)M.world;
+    const u32 tl = level - lp;
+    src = reinterpret_cast<const uint4 *>(M.top[tree] + 32 * ((2 * G - 2 * (G >> tl)) + sib));
+  } else {
+    // level `level` of the sharded tree: rank g owns nodes [g per >> level, (g + 1) per >> level)
+    const u64 per = 1ull << lp, owner = sib >> (lp - level);
+    if (owner != (u64)M.rank) return;
+    const u64 local = sib & ((per >> level) - 1);
+    src = reinterpret_cast<const uint4 *>(A.nodes[tree] + 32 * ((2 * per - 2 * (per >> level)) + local));
+    everywhere = true;
+  }
+  const uint4 x = src[0], y = src[1];
+  const u32 w[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+  if (everywhere) {
+#pragma unroll 1
+    for (int g = 0; g < M.world; g++) {
+      u8 *dst = M.out[g] + dst_off;
+#pragma unroll
+      for (int b = 0; b < 32; b++) dst[b] = (u8)(w[b >> 2] >> (8 * (b & 3)));
+    }
+    __threadfence_system();
+  } else {
+    u8 *dst = M.out[M.rank] + dst_off;
+#pragma unroll
+    for (int b = 0; b < 32; b++) dst[b] = (u8)(w[b >> 2] >> (8 * (b & 3)));
+  }
+}
+
+// one rank's share of a sharded Fri::prove, cut into the phases a lock-step driver interleaves over the ranks
+struct MgProve {
+  stark_mgpu *m = nullptr;
+  stark_ctx *ctx = nullptr;
+  stark_fri_state *s = nullptr;
+  GeoTables G = {nullptr, nullptr};
+  RoundConsts C = {};
+  ProofLayout L;
+  size_t n = 0;
+  u32 R = 0, Rs = 0, nq = 0;
+  size_t arena_off[MG_MAX_ROUNDS + 1] = {};
+  u64 *d_top = nullptr, *d_seed = nullptr;
+  int rc = STARK_OK;
+
+  u32 *arena(int g, size_t off) const { return reinterpret_cast<u32 *>(m->peer[g] + m->L.arena) + off; }
+  u8 *proof_buf(int g) const { return m->peer[g] + m->L.proof; }
+
+  MgExchange exchange(u32 r, int mode) const {
+    MgExchange X;
+    memset(&X, 0, sizeof X);
+    X.world = m->world, X.rank = m->rank, X.mode = mode, X.epoch = mg_epoch(m, r);
+    const size_t slot = m->L.slots + 32 * (size_t)MG_MAX_RANKS * r;
+    for (int g = 0; g < m->world; g++) X.slot_peer[g] = m->peer[g] + slot, X.flag_peer[g] = mg_flags(m, g, 0);
+    X.slot_local = m->win + slot, X.flag_local = mg_flags(m, m->rank, 0);
+    X.err_local = reinterpret_cast<u32 *>(m->win + m->L.err);
+    X.top_nodes = s->top_nodes[r];
+    return X;
+  }
+  TranscriptArgs transcript(u32 r) const {
+    return TranscriptArgs{s->d_tr, s->d_roots + 32 * r, r == R - 1 ? 0 : 1, s->d_alpha_raw + r, s->d_alpha_m + r};
+  }
+
+  // Fri::prove's checks (fri.rs:256-260, 183-192), allocations, and which rounds are sharded
+  int begin(stark_mgpu *m_, const u32 *cw0, size_t n_, size_t domain_length, u32 offset, u32 omega, u32 ef, u32 nq_,
+            const u8 *transcript_, size_t transcript_len, size_t proof_cap, size_t *proof_len) {
+    m = m_, ctx = m_->ctx, n = n_, nq = nq_;
+    mg_begin_op(m);
+    if (n != domain_length)
+      return rc = stark_fail(ctx, STARK_ERR_ARG, "initial codeword length does not match domain length");  // fri.rs:256-260
+    if ((rc = fri_check(ctx, n, ef, &R, nq)) != STARK_OK) return rc;
+    proof_layout(n, R, nq, &L);
+    if (proof_len) *proof_len = L.total;
+    if ((size_t)nq > 2 * L.last_len) return rc = stark_fail(ctx, STARK_ERR_ARG, "not enough entropy in indices wrt last codeword");
+    if ((size_t)nq > L.last_len)
+      return rc = stark_fail(ctx, STARK_ERR_ARG, "cannot sample more indices than available in last codeword; requested: %u, available: %zu", nq, L.last_len);
+    if (proof_cap < L.total) return rc = stark_fail(ctx, STARK_ERR_ARG, "proof buffer too small: need %zu bytes", L.total);
+    if (L.total + 8 * (size_t)nq + 16 > m->L.proof_cap) return rc = stark_fail(ctx, STARK_ERR_ARG, "proof larger than the group's window");
+    if (L.n_cw > (u32)MAX_FRI_ROUNDS) return rc = stark_fail(ctx, STARK_ERR_ARG, "more than %d FRI rounds are not supported", MAX_FRI_ROUNDS);
+    if ((rc = fri_commit_setup(ctx, cw0, n, offset, omega, ef, nq, transcript_, transcript_len, false, &s, &G, &C)) != STARK_OK) return rc;
+    // sharded rounds: long enough to be throughput-bound, at least 4 leaves per rank, folded codewords fit the arena
+    const size_t W = (size_t)m->world;
+    size_t len = n, used = 0;
+    Rs = 0;
+    while (W > 1 && Rs < R && len >= ((size_t)1 << m->shard_log) && len / W >= 4) {
+      if (Rs > 0) {
+        if (used + len > m->L.arena_elems) break;
+        arena_off[Rs] = used, used += len;
+      }
+      Rs++, len >>= 1;
+    }
+    s->sharded = Rs;
+    for (u32 r = 0; r < Rs && rc == STARK_OK; r++) {
+      u8 *t = nullptr;
+      rc = dev_alloc(ctx, (void **)&t, 32 * (2 * W - 1));
+      if (rc == STARK_OK) s->top_nodes.push_back(t);
+    }
+    if (rc == STARK_OK) rc = dev_alloc(ctx, (void **)&d_seed, 8);
+    return rc;
+  }
+
+  // sharded round r, first half: [fold into this round, own range, stored into every replica + leaf hashes] -> subtree ->
+  // subtree root into every window (+ in a fused group: wait, top levels, transcript)
+  int round_signal(u32 r) {
+    if (rc != STARK_OK) return rc;
+    const size_t W = (size_t)m->world, len = C.len, per = len / W, lo = per * (size_t)m->rank;
+    stark_tree *sub = nullptr;
+    if ((rc = merkle_tree_alloc(ctx, per, &sub)) != STARK_OK) return rc;
+    s->trees.push_back(sub);
+    u32 lp = 0;
+    for (size_t c = per; c > 1; c >>= 1) lp++;
+    s->log_per[r] = lp;
+    if (r == 0) {
+      rc = merkle_leaves_dev(ctx, s->cw[0] + lo, per, 1, 1, 0, sub->nodes);   // fri.rs:118-121
+    } else {
+      s->cw.push_back(arena(m->rank, arena_off[r])), s->len.push_back(len), s->borrowed.push_back(true);
+      FoldPeersN P;
+      memset(&P, 0, sizeof P);
+      P.n = m->world;
+      for (int g = 0; g < m->world; g++) P.out[g] = arena(g, arena_off[r]);
+      const u32 inv2off_m = ff::to_mont(ff::inv(ff::mul(2, C.off_prev)));
+      if (ctx->prof_on) prof_begin(ctx, "mg_fold_leaf", 12ull * per + 32ull * per);
+      cudaError_t e = launch_pdl(k_mg_fold_leaf, dim3((u32)((per / 2 + 63) / 64)), dim3(64), 0, ctx->stream, (const u32 *)s->cw[r - 1], P, len,
+                                 lo, lo + per, (int)(r - 1), G, ff::to_mont(C.g_prev), (const u32 *)(s->d_alpha_m + (r - 1)), inv2off_m,
+                                 sub->nodes);
+      if (ctx->prof_on) prof_end(ctx);
+      ctx->launches++;
+      if (e != cudaSuccess) rc = stark_fail(ctx, STARK_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+      m->bytes_sent += 4ull * per * (W - 1);
+    }
+    if (rc != STARK_OK) return rc;
+    const TranscriptArgs tr = transcript(r);
+    const MgExchange X = exchange(r, m->lockstep ? MG_X_SIGNAL : MG_X_FUSED);
+    rc = merkle_climb_dev(ctx, sub->nodes, per, &tr, &X);
+    m->bytes_sent += 36ull * (W - 1);
+    if (!m->lockstep) round_consts_next(C);
+    return rc;
+  }
+  // second half for lock-step groups: wait for the peers' roots, top levels, transcript
+  int round_wait(u32 r) {
+    if (rc != STARK_OK || !m->lockstep) return rc;
+    const TranscriptArgs tr = transcript(r);
+    const MgExchange X = exchange(r, MG_X_WAIT);
+    rc = merkle_mg_top_dev(ctx, &tr, &X);
+    round_consts_next(C);
+    return rc;
+  }
+
+  // the replicated rounds, index sampling and proof assembly; column roots (optional) ride the same final barrier
+  int rest() {
+    if (rc != STARK_OK) return rc;
+    if ((rc = fri_commit_rounds(ctx, s, Rs, G, C)) != STARK_OK) return rc;
+    u8 *d_proof = proof_buf(m->rank);
+    d_top = reinterpret_cast<u64 *>(d_proof + ((L.total + 7) & ~(size_t)7));
+    if (ctx->prof_on) prof_begin(ctx, "query_phase", 0);
+    const size_t sample_size = L.n_cw > 1 ? s->len[1] : s->len[0];       // fri.rs:266-270
+    cudaError_t qe = launch_pdl(k_sample_indices, dim3(1), dim3(256), 0, ctx->stream, (const TranscriptDev *)s->d_tr, d_seed,
+                                (u64)sample_size, (u64)L.last_len, nq, d_top);  // fri.rs:272-276
+    const size_t hdr_threads = L.last_len > R ? L.last_len : R;
+    if (qe == cudaSuccess)
+      qe = launch_pdl(k_proof_header, dim3((u32)((hdr_threads + 255) / 256)), dim3(256), 0, ctx->stream, d_proof,
+                      (const u8 *)s->d_roots, R, (const u32 *)s->cw[L.n_cw - 1], (u64)L.last_len);
+    ctx->launches += 2;
+    if (L.n_cw > 1 && nq) {
+      MgProofArgs M;
+      memset(&M, 0, sizeof M);
+      u32 d0 = 0;
+      for (size_t c = s->len[0]; c > 1; c >>= 1) d0++;
+      M.A.len0 = s->len[0], M.A.nq = nq, M.A.depth0 = d0;
+      for (u32 i = 0; i < L.n_cw; i++) {
+        M.A.cw[i] = s->cw[i], M.A.nodes[i] = s->trees[i]->nodes;
+        M.log_per[i] = i < Rs ? s->log_per[i] : 0xffu;
+        M.top[i] = i < Rs ? s->top_nodes[i] : nullptr;
+      }
+      for (u32 i = 0; i + 1 < L.n_cw; i++) M.A.out_off[i] = L.round_off[i];
+      M.world = m->world, M.rank = m->rank;
+      for (int g = 0; g < m->world; g++) M.out[g] = proof_buf(g);
+      const size_t threads = (size_t)nq * (3 * d0 - 1);
+      if (qe == cudaSuccess)
+        qe = launch_pdl(k_mg_proof_rounds, dim3((u32)((threads + 127) / 128), L.n_cw - 1), dim3(128), 0, ctx->stream, M,
+                        (const u64 *)d_top);
+      ctx->launches++;
+      // path nodes of the sharded levels: about a 1/G share of them goes to each of the G - 1 peers
+      u64 sharded_hashes = 0;
+      for (u32 i = 0; i < Rs; i++) sharded_hashes += (u64)nq * s->log_per[i] * (i == 0 ? 2 : 3);
+      m->bytes_sent += 32ull * sharded_hashes * (u64)(m->world - 1) / (u64)m->world;
+    }
+    if (ctx->prof_on) prof_end(ctx);
+    if (qe != cudaSuccess) rc = stark_fail(ctx, STARK_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(qe));
+    return rc;
+  }
+  u32 final_epoch() const { return mg_epoch(m, MG_MAX_ROUNDS + 1); }
+  int finish_signal() {
+    if (rc != STARK_OK) return rc;
+    return rc = m->lockstep ? mg_barrier_signal(m, 1, final_epoch()) : mg_barrier(m, 1, final_epoch());
+  }
+  int finish_wait() {
+    if (rc != STARK_OK || !m->lockstep) return rc;
+    return rc = mg_barrier_wait(m, 1, final_epoch());
+  }
+  // proof bytes (and optionally the top-level indices) to the host; frees the state
+  int download(u8 *proof, u64 *top_indices) {
+    if (rc == STARK_OK && proof &&
+        cudaMemcpyAsync(proof, proof_buf(m->rank), L.total, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+      rc = stark_fail(ctx, STARK_ERR_CUDA, "D2H copy failed");
+    if (rc == STARK_OK && top_indices && nq &&
+        cudaMemcpyAsync(top_indices, d_top, 8 * (size_t)nq, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+      rc = stark_fail(ctx, STARK_ERR_CUDA, "D2H copy failed");
+    return rc;
+  }
+  void release() {
+    if (ctx) dev_free(ctx, d_seed);
+    d_seed = nullptr;
+    fri_state_free(s);
+    s = nullptr;
+  }
+};
+
+// Runs `world` MgProve objects through their phases.  A multi-process rank passes its own single object; a local group
+// passes all of them and the phases are interleaved over the ranks (lock step when they share a device).
+template <typename PerRank>
+static void mg_each(MgProve *P, int count, PerRank fn) {
+  for (int k = 0; k < count; k++) {
+    mg_use(P[k].m);
+    fn(P[k]);
+  }
+}
+static int mg_prove_run(MgProve *P, int count) {
+  u32 Rs = 0;
+  for (int k = 0; k < count; k++) Rs = P[k].Rs > Rs ? P[k].Rs : Rs;
+  auto failed = [&]() {
+    for (int k = 0; k < count; k++)
+      if (P[k].rc != STARK_OK) return P[k].rc;
+    return (int)STARK_OK;
+  };
+  // a rank of this call that failed stops all of them (the others' queued waits give up after MG_TIMEOUT_NS)
+  for (u32 r = 0; r < Rs && failed() == STARK_OK; r++) {
+    mg_each(P, count, [&](MgProve &p) { p.round_signal(r); });
+    if (failed() != STARK_OK) break;
+    mg_each(P, count, [&](MgProve &p) { p.round_wait(r); });
+  }
+  if (failed() == STARK_OK) mg_each(P, count, [&](MgProve &p) { p.rest(); });
+  return failed();
+}
+static int mg_prove_finish(MgProve *P, int count) {
+  mg_each(P, count, [&](MgProve &p) { p.finish_signal(); });
+  mg_each(P, count, [&](MgProve &p) { p.finish_wait(); });
+  int rc = STARK_OK;
+  for (int k = 0; k < count; k++)
+    if (P[k].rc != STARK_OK) rc = P[k].rc;
+  return rc;
+}
+
+// ---- per-column commitments on a side stream (shared by the single-GPU and the sharded config-3 pipelines)
+// The trees of the columns that are not FRI-proved are throughput work that does not depend on the FRI, whose rounds are
+// a latency-bound chain: they are queued on a side stream so that they fill the SMs the FRI leaves idle.
+// The climb kernel's last-CTA ticket is per stream.
+struct ColumnCommit {
+  std::vector<stark_tree *> trees;
+  u8 *d_roots = nullptr;      // one root per committed column, in the order given
+  bool forked = false;
+  cudaStream_t main_stream = nullptr;
+};
+static int column_commit_begin(stark_ctx *ctx, const u32 *lde, size_t N, const u32 *local_cols, u32 count, ColumnCommit *cc) {
+  cc->main_stream = ctx->stream;
+  if (count == 0) return STARK_OK;
+  ST_TRY(dev_alloc(ctx, (void **)&cc->d_roots, 32 * (size_t)count));
+  if (!ctx->prof_on && side_streams(ctx, 1) == STARK_OK) {
+    cudaEventRecord(ctx->fork_ev, cc->main_stream);
+    cudaStreamWaitEvent(ctx->side[0], ctx->fork_ev, 0);
+    ctx->stream = ctx->side[0], ctx->climb_counter = ctx->flag + 3, cc->forked = true;
+  }
+  int rc = STARK_OK;
+  for (u32 i = 0; i < count && rc == STARK_OK; i++) {
+    stark_tree *t = nullptr;
+    rc = merkle_build_from_dev_values(ctx, lde + (size_t)local_cols[i] * N, N, 1, 1, 0, &t);
+    if (rc == STARK_OK) {
+      cc->trees.push_back(t);
+      if (cudaMemcpyAsync(cc->d_roots + 32 * (size_t)i, t->nodes + 32 * (2 * N - 2), 32, cudaMemcpyDeviceToDevice, ctx->stream) !=
+          cudaSuccess)
+        rc = stark_fail(ctx, STARK_ERR_CUDA, "D2D copy failed");
+    }
+  }
+  if (cc->forked) {
+    cudaEventRecord(ctx->side_done[0], ctx->side[0]);
+    ctx->stream = cc->main_stream, ctx->climb_counter = ctx->flag + 1;
+  }
+  return rc;
+}
+// the context's stream waits for the column trees (also on an error path: the trees are freed afterwards)
+static void column_commit_join(stark_ctx *ctx, ColumnCommit *cc) {
+  if (cc->forked) cudaStreamWaitEvent(cc->main_stream, ctx->side_done[0], 0);
+  cc->forked = false;
+}
+static void column_commit_free(stark_ctx *ctx, ColumnCommit *cc) {
+  column_commit_join(ctx, cc);
+  for (stark_tree *t : cc->trees) stark_merkle_free(t);
+  cc->trees.clear();
+  dev_free(ctx, cc->d_roots);
+  cc->d_roots = nullptr;
+}
+
+// which trace columns a rank commits in the sharded config 3: column 0 is LDE'd by every rank (its codeword is the FRI
+// input, replicated without a broadcast) and committed by the sharded FRI itself; columns 1.. go round robin
+static u32 mg_owned_columns(int rank, int world, u32 n_cols, u32 *out) {
+  u32 k = 0;
+  for (u32 c = 1; c < n_cols; c++)
+    if ((int)((c - 1) % (u32)world) == rank) {
+      if (out) out[k] = c;
+      k++;
+    }
+  return k;
+}
+
+struct MgTraceRank {
+  MgProve P;
+  ColumnCommit cc;
+  u32 *lde = nullptr;
+  stark_buf *in = nullptr;       // host-input variant: this rank's columns on the device
+  std::vector<u32> owned;        // global indices of the committed columns
+  u32 n_my = 0;
+  int rc = STARK_OK;
+};
+
+static int mg_prove_trace_impl(stark_mgpu *const *ranks, int n_here, const uint64_t *host_cols, const stark_buf *const *my_cols,
+                               uint32_t n_cols, uint32_t log_n, uint32_t log_blowup, uint64_t offset, uint32_t nq,
+                               uint8_t *const *column_roots, uint8_t *const *proofs, size_t proof_cap, size_t *proof_len) {
+  if (!ranks || n_here < 1 || n_cols == 0 || (!host_cols && !my_cols)) return stark_fail(nullptr, STARK_ERR_ARG, "null argument");
+  for (int k = 0; k < n_here; k++)
+    if (!ranks[k] || (my_cols && !my_cols[k]) || !proofs || !proofs[k]) return stark_fail(nullptr, STARK_ERR_ARG, "null argument");
+  stark_ctx *ctx0 = ranks[0]->ctx;
+  if (ranks[0]->mode == MG_LOCAL && n_here != ranks[0]->world)
+    return stark_fail(ctx0, STARK_ERR_ARG, "a local group is driven with all of its ranks in one call");
+  if (log_n + log_blowup > (u32)ff::TWO_ADICITY) return stark_fail(ctx0, STARK_ERR_ARG, "n > 2^23 not supported by this modulus");
+  if (offset == 0 || offset >= ff::P) return stark_fail(ctx0, STARK_ERR_ARG, "offset must be a non-zero canonical element");
+  if (n_cols > ranks[0]->L.max_cols / 2) return stark_fail(ctx0, STARK_ERR_ARG, "more columns than the group's window holds");
+  const size_t n = (size_t)1 << log_n, N = n << log_blowup;
+  const u32 omega = ff::pow(ff::GEN, (ff::P - 1) >> (log_n + log_blowup));  // prim_nth_root(N), ff.rs:215-223
+  u32 fri_rounds = 0;
+  ST_TRY(fri_check(ctx0, N, 1u << log_blowup, &fri_rounds, nq));
+  std::vector<MgTraceRank> T(n_here);
+  std::vector<MgProve> P(n_here);
+  int rc = STARK_OK;
+  // phase 1 (no exchange): upload / LDE of column 0 and the owned columns, column trees on the side stream
+  for (int k = 0; k < n_here && rc == STARK_OK; k++) {
+    stark_mgpu *m = ranks[k];
+    stark_ctx *ctx = m->ctx;
+    mg_use(m);
+    MgTraceRank &t = T[k];
+    t.owned.resize(n_cols);
+    t.owned.resize(mg_owned_columns(m->rank, m->world, n_cols, t.owned.data()));
+    t.n_my = 1 + (u32)t.owned.size();
+    const u32 *cols_dev = nullptr;
+    if (host_cols) {
+      rc = stark_buf_alloc(ctx, n * t.n_my, &t.in);
+      if (rc == STARK_OK) rc = upload_flag_reset(ctx);
+      if (rc == STARK_OK) rc = upload_u64_nosync(ctx, host_cols, n, t.in->ptr);
+      for (u32 i = 0; i < t.owned.size() && rc == STARK_OK; i++)
+        rc = upload_u64_nosync(ctx, host_cols + (size_t)t.owned[i] * n, n, t.in->ptr + (size_t)(i + 1) * n);
+      if (rc == STARK_OK) cols_dev = t.in->ptr;
+    } else {
+      if (my_cols[k]->n < n * t.n_my) rc = stark_fail(ctx, STARK_ERR_ARG, "buffer too small");
+      cols_dev = my_cols[k]->ptr;
+    }
+    if (rc == STARK_OK) rc = dev_alloc(ctx, (void **)&t.lde, N * t.n_my * 4);
+    if (rc == STARK_OK) rc = lde_dev(ctx, cols_dev, t.n_my, log_n, log_blowup, (u32)offset, t.lde);
+    if (rc == STARK_OK) {
+      // local column indices to commit here: 1.. (the owned ones); with num_rounds() == 0 Fri::commit builds no tree, so
+      // rank 0 commits column 0 as well
+      std::vector<u32> local;
+      if (fri_rounds == 0 && m->rank == 0) local.push_back(0);
+      for (u32 i = 0; i < t.owned.size(); i++) local.push_back(i + 1);
+      rc = column_commit_begin(ctx, t.lde, N, local.data(), (u32)local.size(), &t.cc);
+    }
+    if (rc == STARK_OK)
+      rc = P[k].begin(m, t.lde, N, N, (u32)offset, omega, 1u << log_blowup, nq, nullptr, 0, proof_cap, proof_len);
+    else
+      mg_begin_op(m);   // keep the operation count in step with the ranks that did begin
+  }
+  // phase 2: the sharded Fri::prove on column 0
+  if (rc == STARK_OK) rc = mg_prove_run(P.data(), n_here);
+  // phase 3: the column roots into every rank's table, then the barrier that ends the operation
+  for (int k = 0; k < n_here && rc == STARK_OK; k++) {
+    stark_mgpu *m = ranks[k];
+    mg_use(m);
+    MgTraceRank &t = T[k];
+    column_commit_join(m->ctx, &t.cc);
+    std::vector<u32> idx;
+    if (fri_rounds == 0 && m->rank == 0) idx.push_back(0);
+    for (u32 c : t.owned) idx.push_back(c);
+    if (!idx.empty()) rc = mg_put_roots(m, t.cc.d_roots, idx.data(), (u32)idx.size());
+  }
+  if (rc == STARK_OK) rc = mg_prove_finish(P.data(), n_here);
+  for (int k = 0; k < n_here; k++) {
+    stark_mgpu *m = ranks[k];
+    stark_ctx *ctx = m->ctx;
+    mg_use(m);
+    if (rc == STARK_OK) rc = P[k].download(proofs[k], nullptr);
+    if (rc == STARK_OK && column_roots && column_roots[k] &&
+        cudaMemcpyAsync(column_roots[k], mg_colroots(m, m->rank), 32 * (size_t)n_cols, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+      rc = stark_fail(ctx, STARK_ERR_CUDA, "D2H copy failed");
+  }
+  for (int k = 0; k < n_here; k++) {
+    stark_mgpu *m = ranks[k];
+    stark_ctx *ctx = m->ctx;
+    mg_use(m);
+    const int e = mg_check_err(m);   // synchronises the rank's stream
+    if (rc == STARK_OK) rc = e;
+    if (rc == STARK_OK && fri_rounds > 0 && column_roots && column_roots[k]) memcpy(column_roots[k], proofs[k] + 1, 32);  // root of column 0
+    if (rc == STARK_OK && host_cols) rc = upload_u64_check(ctx);
+    P[k].release();
+    column_commit_free(ctx, &T[k].cc);
+    dev_free(ctx, T[k].lde);
+    stark_buf_free(T[k].in);
+  }
+  return rc;
+}
+
+// ---- BASELINE config 5 on a group: ONE Fri::commit round (fri.rs:116-147) of a replicated codeword -- sharded leaf hashes
+// and subtree, root exchange, alpha, sharded fold stored into every replica.  Returns views of the folded replicas.
+static int mg_fold_commit_round_impl(stark_mgpu *const *ranks, int n_here, const stark_buf *const *codewords, size_t n,
+                                     u32 offset, u32 omega, uint8_t *const *roots, uint64_t *alpha_raw, stark_buf **folded) {
+  stark_ctx *ctx0 = ranks[0]->ctx;
+  const size_t W = (size_t)ranks[0]->world;
+  if (n < 8 * W || (n & (n - 1))) return stark_fail(ctx0, STARK_ERR_ARG, "codeword length must be a power of two, at least 8 per rank");
+  if (n / 2 > ranks[0]->L.arena_elems) return stark_fail(ctx0, STARK_ERR_ARG, "codeword larger than the group's window (max_codeword)");
+  if (offset == 0 || omega == 0) return stark_fail(ctx0, STARK_ERR_ARG, "no division by zero");   // ff.rs:182
+  struct Rk {
+    stark_tree *sub = nullptr;
+    u8 *top = nullptr, *d_root = nullptr;
+    u64 *d_alpha_raw = nullptr;
+    u32 *d_alpha_m = nullptr;
+    TranscriptDev *d_tr = nullptr;
+    GeoTables G = {nullptr, nullptr};
+  };
+  std::vector<Rk> K(n_here);
+  const size_t per = n / W, h = n / 2, hper = h / W;
+  const u32 g0 = ff::inv(omega);
+  int rc = STARK_OK;
+  auto exchange = [&](stark_mgpu *m, Rk &k, int mode) {
+    MgExchange X;
+    memset(&X, 0, sizeof X);
+    X.world = m->world, X.rank = m->rank, X.mode = mode, X.epoch = mg_epoch(m, 0);
+    for (int g = 0; g < m->world; g++) X.slot_peer[g] = m->peer[g] + m->L.slots, X.flag_peer[g] = mg_flags(m, g, 0);
+    X.slot_local = m->win + m->L.slots, X.flag_local = mg_flags(m, m->rank, 0);
+    X.err_local = reinterpret_cast<u32 *>(m->win + m->L.err);
+    X.top_nodes = k.top;
+    return X;
+  };
+  // leaf hashes + subtree + root into every window (+ wait, top, alpha when fused)
+  for (int i = 0; i < n_here && rc == STARK_OK; i++) {
+    stark_mgpu *m = ranks[i];
+    stark_ctx *ctx = m->ctx;
+    mg_use(m);
+    mg_begin_op(m);
+    Rk &k = K[i];
+    if (!codewords[i] || codewords[i]->n < n) rc = stark_fail(ctx, STARK_ERR_ARG, "buffer too small");
+    if (rc == STARK_OK) rc = merkle_tree_alloc(ctx, per, &k.sub);
+    if (rc == STARK_OK) rc = dev_alloc(ctx, (void **)&k.top, 32 * (2 * W - 1));
+    if (rc == STARK_OK) rc = dev_alloc(ctx, (void **)&k.d_root, 32);
+    if (rc == STARK_OK) rc = dev_alloc(ctx, (void **)&k.d_alpha_raw, 8);
+    if (rc == STARK_OK) rc = dev_alloc(ctx, (void **)&k.d_alpha_m, 4);
+    if (rc == STARK_OK) rc = dev_alloc(ctx, (void **)&k.d_tr, sizeof(TranscriptDev));
+    if (rc == STARK_OK) rc = geo_tables(ctx, g0, 1, h, &k.G);
+    if (rc != STARK_OK) break;
+    TranscriptDev t;
+    tr_init(t);
+    if (cudaMemcpyAsync(k.d_tr, &t, sizeof t, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = stark_fail(ctx, STARK_ERR_CUDA, "H2D copy failed");
+    if (rc == STARK_OK) rc = merkle_leaves_dev(ctx, codewords[i]->ptr + per * (size_t)m->rank, per, 1, 1, 0, k.sub->nodes);
+    const TranscriptArgs tr = {k.d_tr, k.d_root, 1, k.d_alpha_raw, k.d_alpha_m};
+    const MgExchange X = exchange(m, k, W == 1 ? MG_X_FUSED : (m->lockstep ? MG_X_SIGNAL : MG_X_FUSED));
+    if (rc == STARK_OK) rc = merkle_climb_dev(ctx, k.sub->nodes, per, &tr, W > 1 ? &X : nullptr);
+    m->bytes_sent += 36ull * (W - 1);
+  }
+  for (int i = 0; i < n_here && rc == STARK_OK; i++) {
+    stark_mgpu *m = ranks[i];
+    if (!m->lockstep || W == 1) continue;
+    mg_use(m);
+    const TranscriptArgs tr = {K[i].d_tr, K[i].d_root, 1, K[i].d_alpha_raw, K[i].d_alpha_m};
+    const MgExchange X = exchange(m, K[i], MG_X_WAIT);
+    rc = merkle_mg_top_dev(m->ctx, &tr, &X);
+  }
+  // fold of the rank's output range into every replica (k_fri_fold_bcast), then the barrier that completes the replicas
+  for (int i = 0; i < n_here && rc == STARK_OK; i++) {
+    stark_mgpu *m = ranks[i];
+    stark_ctx *ctx = m->ctx;
+    mg_use(m);
+    FoldPeers P;
+    memset(&P, 0, sizeof P);
+    P.n = m->world, P.mc = nullptr;
+    for (int g = 0; g < m->world; g++) P.out[g] = reinterpret_cast<u32 *>(m->peer[g] + m->L.arena);
+    const size_t i0 = hper * (size_t)m->rank;
+    size_t blocks = (hper / 4 + 255) / 256, cap = (size_t)ctx->sm_count * 8;
+    LAUNCH(ctx, "fri_fold_bcast", 12ull * hper,
+           k_fri_fold_bcast<<<(u32)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(
+               codewords[i]->ptr, P, h, i0, i0 + hper, 0, K[i].G, ff::to_mont(g0), (const u32 *)K[i].d_alpha_m, 0u,
+               ff::to_mont(ff::inv(ff::mul(2, offset)))));
+    m->bytes_sent += 4ull * hper * (W - 1);
+  }
+  const u32 fin = MG_MAX_ROUNDS + 1;
+  for (int i = 0; i < n_here && rc == STARK_OK; i++) {
+    mg_use(ranks[i]);
+    rc = ranks[i]->lockstep ? mg_barrier_signal(ranks[i], 1, mg_epoch(ranks[i], fin)) : mg_barrier(ranks[i], 1, mg_epoch(ranks[i], fin));
+  }
+  for (int i = 0; i < n_here && rc == STARK_OK; i++) {
+    mg_use(ranks[i]);
+    if (ranks[i]->lockstep) rc = mg_barrier_wait(ranks[i], 1, mg_epoch(ranks[i], fin));
+  }
+  for (int i = 0; i < n_here; i++) {
+    stark_mgpu *m = ranks[i];
+    stark_ctx *ctx = m->ctx;
+    mg_use(m);
+    Rk &k = K[i];
+    if (rc == STARK_OK && roots && roots[i] && cudaMemcpyAsync(roots[i], k.d_root, 32, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+      rc = stark_fail(ctx, STARK_ERR_CUDA, "D2H copy failed");
+    if (rc == STARK_OK && alpha_raw && cudaMemcpyAsync(alpha_raw + i, k.d_alpha_raw, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+      rc = stark_fail(ctx, STARK_ERR_CUDA, "D2H copy failed");
+    const int e = mg_check_err(m);
+    if (rc == STARK_OK) rc = e;
+    if (k.sub) stark_merkle_free(k.sub);
+    dev_free(ctx, k.top), dev_free(ctx, k.d_root), dev_free(ctx, k.d_alpha_raw), dev_free(ctx, k.d_alpha_m), dev_free(ctx, k.d_tr);
+    if (rc == STARK_OK && folded) rc = stark_buf_wrap(ctx, m->win + m->L.arena, h, &folded[i]);
+  }
+  return rc;
+}
+
+// ---- BASELINE config 4 on a group: n_groups fixed groups of group_width trace columns; rank g owns
+// groups {g, g + G, ...}.  Per owned group: coset LDE of its columns (no communication) and one Merkle tree whose leaf i
+// is Hash::from_field_elements(row i of the group's LDE) (hash.rs:32-35), built on a side stream while the next group's
+// LDE runs (the NTT loads the FMA-heavy pipe, the hashing the ALU pipe); the group roots are gathered -- ncclAllGather
+// in a multi-process group, peer stores in a local one -- and every rank builds MerkleTree::new over them.
+static int mg_lde_commit_impl(stark_mgpu *const *ranks, int n_here, const uint64_t *host_cols,
+                              const stark_buf *const *owned_groups, uint32_t n_groups, uint32_t gw, uint32_t log_n,
+                              uint32_t log_blowup, uint64_t offset, uint8_t *const *group_roots, uint8_t *const *commitments) {
+  stark_ctx *ctx0 = ranks[0]->ctx;
+  const u32 W = (u32)ranks[0]->world;
+  if (n_groups == 0 || gw == 0 || n_groups % W) return stark_fail(ctx0, STARK_ERR_ARG, "the group count must be a multiple of the world size");
+  if (n_groups & (n_groups - 1)) return stark_fail(ctx0, STARK_ERR_ARG, "Number of leaves must be power of 2");   // merkle.rs:13-16
+  if (log_n + log_blowup > (u32)ff::TWO_ADICITY) return stark_fail(ctx0, STARK_ERR_ARG, "n > 2^23 not supported by this modulus");
+  if (offset == 0 || offset >= ff::P) return stark_fail(ctx0, STARK_ERR_ARG, "offset must be a non-zero canonical element");
+  if (n_groups > ranks[0]->L.max_cols / 2) return stark_fail(ctx0, STARK_ERR_ARG, "more groups than the group's window holds");
+  const size_t n = (size_t)1 << log_n, N = n << log_blowup;
+  const u32 own = n_groups / W;
+  struct Rk {
+    std::vector<u32 *> lde;
+    std::vector<stark_tree *> trees;
+    std::vector<stark_buf *> in;
+    u8 *d_mine = nullptr, *d_all = nullptr, *d_ordered = nullptr;
+    stark_tree *top = nullptr;
+  };
+  std::vector<Rk> K(n_here);
+  int rc = STARK_OK;
+  for (int i = 0; i < n_here && rc == STARK_OK; i++) {
+    stark_mgpu *m = ranks[i];
+    stark_ctx *ctx = m->ctx;
+    mg_use(m);
+    mg_begin_op(m);
+    Rk &k = K[i];
+    rc = dev_alloc(ctx, (void **)&k.d_mine, 32 * (size_t)own);
+    if (rc == STARK_OK) rc = dev_alloc(ctx, (void **)&k.d_all, 32 * (size_t)n_groups);
+    if (rc == STARK_OK) rc = dev_alloc(ctx, (void **)&k.d_ordered, 32 * (size_t)n_groups);
+    if (rc == STARK_OK) rc = side_streams(ctx, 4);
+    if (rc == STARK_OK && host_cols) rc = upload_flag_reset(ctx);
+    cudaStream_t main_stream = ctx->stream, tree_stream = ctx->side[3];
+    for (u32 j = 0; j < own && rc == STARK_OK; j++) {
+      const u32 grp = (u32)m->rank + j * W;
+      const u32 *cols_dev = nullptr;
+      if (host_cols) {
+        stark_buf *b = nullptr;
+        rc = stark_buf_alloc(ctx, n * gw, &b);
+        if (rc == STARK_OK) k.in.push_back(b), rc = upload_u64_nosync(ctx, host_cols + (size_t)grp * gw * n, n * gw, b->ptr);
+        if (rc == STARK_OK) cols_dev = b->ptr;
+      } else {
+        const stark_buf *b = owned_groups[(size_t)i * own + j];
+        if (!b || b->n < n * gw) rc = stark_fail(ctx, STARK_ERR_ARG, "buffer too small");
+        else cols_dev = b->ptr;
+      }
+      u32 *lde = nullptr;
+      if (rc == STARK_OK) rc = dev_alloc(ctx, (void **)&lde, N * gw * 4);
+      if (rc == STARK_OK) k.lde.push_back(lde), rc = lde_dev(ctx, cols_dev, gw, log_n, log_blowup, (u32)offset, lde);
+      if (rc != STARK_OK) break;
+      // the group's tree on the tree stream, after its LDE
+      cudaEventRecord(ctx->fork_ev, main_stream);
+      cudaStreamWaitEvent(tree_stream, ctx->fork_ev, 0);
+      ctx->stream = tree_stream, ctx->climb_counter = ctx->flag + 3;
+      stark_tree *t = nullptr;
+      rc = merkle_build_from_dev_values(ctx, lde, N, gw, 1, N, &t);   // column-major [gw][N]: row stride 1, column stride N
+      if (rc == STARK_OK) {
+        k.trees.push_back(t);
+        if (cudaMemcpyAsync(k.d_mine + 32 * (size_t)j, t->nodes + 32 * (2 * N - 2), 32, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess)
+          rc = stark_fail(ctx, STARK_ERR_CUDA, "D2D copy failed");
+      }
+      ctx->stream = main_stream, ctx->climb_counter = ctx->flag + 1;
+    }
+    cudaEventRecord(ctx->side_done[3], tree_stream);
+    cudaStreamWaitEvent(main_stream, ctx->side_done[3], 0);
+    if (rc != STARK_OK) break;
+    // gather the group roots
+    if (m->mode == MG_PROC && W > 1) {
+      rc = mg_all_gather(m, k.d_mine, k.d_all, 32 * (size_t)own);   // rank-major: entry (g, j) = group g + j W
+    } else {
+      std::vector<u32> idx(own);
+      for (u32 j = 0; j < own; j++) idx[j] = (u32)m->rank + j * W;
+      rc = mg_put_roots(m, k.d_mine, idx.data(), own);
+    }
+  }
+  const u32 fin = MG_MAX_ROUNDS + 1;
+  const bool peer_path = ranks[0]->mode != MG_PROC || W == 1;
+  if (peer_path) {
+    for (int i = 0; i < n_here && rc == STARK_OK; i++) {
+      mg_use(ranks[i]);
+      rc = ranks[i]->lockstep ? mg_barrier_signal(ranks[i], 1, mg_epoch(ranks[i], fin)) : mg_barrier(ranks[i], 1, mg_epoch(ranks[i], fin));
+    }
+    for (int i = 0; i < n_here && rc == STARK_OK; i++) {
+      mg_use(ranks[i]);
+      if (ranks[i]->lockstep) rc = mg_barrier_wait(ranks[i], 1, mg_epoch(ranks[i], fin));
+    }
+  }
+  for (int i = 0; i < n_here && rc == STARK_OK; i++) {
+    stark_mgpu *m = ranks[i];
+    stark_ctx *ctx = m->ctx;
+    mg_use(m);
+    Rk &k = K[i];
+    if (peer_path) {
+      if (cudaMemcpyAsync(k.d_ordered, mg_colroots(m, m->rank), 32 * (size_t)n_groups, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess)
+        rc = stark_fail(ctx, STARK_ERR_CUDA, "D2D copy failed");
+    } else {
+      // rank-major (g, j) -> group order g + j W
+      for (u32 g = 0; g < W && rc == STARK_OK; g++)
+        if (cudaMemcpy2DAsync(k.d_ordered + 32 * (size_t)g, 32 * (size_t)W, k.d_all + 32 * (size_t)g * own, 32, 32, own,
+                              cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess)
+          rc = stark_fail(ctx, STARK_ERR_CUDA, "D2D copy failed");
+    }
+    if (rc == STARK_OK) rc = stark_merkle_build_dev(ctx, k.d_ordered, n_groups, &k.top);   // MerkleTree::new over the group roots
+    if (rc == STARK_OK && group_roots && group_roots[i] &&
+        cudaMemcpyAsync(group_roots[i], k.d_ordered, 32 * (size_t)n_groups, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+      rc = stark_fail(ctx, STARK_ERR_CUDA, "D2H copy failed");
+    if (rc == STARK_OK && commitments && commitments[i] &&
+        cudaMemcpyAsync(commitments[i], k.top->nodes + 32 * (2 * (size_t)n_groups - 2), 32, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+      rc = stark_fail(ctx, STARK_ERR_CUDA, "D2H copy failed");
+  }
+  for (int i = 0; i < n_here; i++) {
+    stark_mgpu *m = ranks[i];
+    stark_ctx *ctx = m->ctx;
+    mg_use(m);
+    Rk &k = K[i];
+    const int e = mg_check_err(m);
+    if (rc == STARK_OK) rc = e;
+    if (rc == STARK_OK && host_cols) rc = upload_u64_check(ctx);
+    for (stark_tree *t : k.trees) stark_merkle_free(t);
+    if (k.top) stark_merkle_free(k.top);
+    for (u32 *p : k.lde) dev_free(ctx, p);
+    for (stark_buf *b : k.in) stark_buf_free(b);
+    dev_free(ctx, k.d_mine), dev_free(ctx, k.d_all), dev_free(ctx, k.d_ordered);
+  }
+  return rc;
 }
 
 // ----------------------------------------------------------------------------------------------- C ABI
@@ -874,56 +1669,34 @@ int stark_prove_trace_dev(stark_ctx *ctx, const stark_buf *cols, uint32_t n_cols
   const size_t n = (size_t)1 << log_n, N = n << log_blowup;
   if (cols->n < n * n_cols) return stark_fail(ctx, STARK_ERR_ARG, "buffer too small");
   u32 *lde = nullptr;
-  u8 *d_roots = nullptr;
   ST_TRY(dev_alloc(ctx, (void **)&lde, N * n_cols * 4));
   int rc = lde_dev(ctx, cols->ptr, n_cols, log_n, log_blowup, (u32)offset, lde);
-  // commitments of columns 1.. (column 0's tree is built inside Fri::commit, fri.rs:118-127, and its root is
-  // the first proof object)
-  // They are throughput work that does not depend on the FRI, whose rounds are a latency-bound chain: queue
-  // them on a side stream so that they fill the SMs the FRI leaves idle.  The climb kernel's last-CTA ticket is per stream.
-  std::vector<stark_tree *> trees;
-  if (rc == STARK_OK && n_cols > 1) rc = dev_alloc(ctx, (void **)&d_roots, 32 * (size_t)n_cols);
-  cudaStream_t main_stream = ctx->stream;
-  bool forked = false;
-  if (rc == STARK_OK && n_cols > 1 && !ctx->prof_on && side_streams(ctx, 1) == STARK_OK) {
-    cudaEventRecord(ctx->fork_ev, main_stream);
-    cudaStreamWaitEvent(ctx->side[0], ctx->fork_ev, 0);
-    ctx->stream = ctx->side[0], ctx->climb_counter = ctx->flag + 3, forked = true;
-  }
-  // With num_rounds() == 0 (N <= expansion factor or N <= 4 nq, fri.rs:93-103) Fri::commit builds no tree and the proof
-  // starts with the last codeword, so column 0 is committed here like the others.
+  // commitments of columns 1.. on the side stream (column 0's tree is built inside Fri::commit, fri.rs:118-127, and its
+  // root is the first proof object).  With num_rounds() == 0 (N <= expansion factor or N <= 4 nq, fri.rs:93-103)
+  // Fri::commit builds no tree and the proof starts with the last codeword, so column 0 is committed here like the others.
   u32 fri_rounds = 0;
   if (rc == STARK_OK) rc = fri_check(ctx, N, 1u << log_blowup, &fri_rounds, nq);
   const u32 first_col = fri_rounds == 0 ? 0u : 1u;
-  if (rc == STARK_OK && n_cols == 1 && first_col == 0) rc = dev_alloc(ctx, (void **)&d_roots, 32);
-  for (u32 c = first_col; c < n_cols && rc == STARK_OK; c++) {
-    stark_tree *t = nullptr;
-    rc = merkle_build_from_dev_values(ctx, lde + (size_t)c * N, N, 1, 1, 0, &t);
-    if (rc == STARK_OK) {
-      trees.push_back(t);
-      if (cudaMemcpyAsync(d_roots + 32 * (size_t)c, t->nodes + 32 * (2 * N - 2), 32, cudaMemcpyDeviceToDevice,
-                          ctx->stream) != cudaSuccess)
-        rc = stark_fail(ctx, STARK_ERR_CUDA, "D2D copy failed");
-    }
-  }
-  if (forked) {
-    cudaEventRecord(ctx->side_done[0], ctx->side[0]);
-    ctx->stream = main_stream, ctx->climb_counter = ctx->flag + 1;
+  ColumnCommit cc;
+  if (rc == STARK_OK) {
+    std::vector<u32> local;
+    for (u32 c = first_col; c < n_cols; c++) local.push_back(c);
+    rc = column_commit_begin(ctx, lde, N, local.data(), (u32)local.size(), &cc);
   }
   const u32 omega = ff::pow(ff::GEN, (ff::P - 1) >> (log_n + log_blowup));  // prim_nth_root(N), ff.rs:215-223
   if (rc == STARK_OK)
     rc = fri_prove_dev(ctx, lde, N, N, (u32)offset, omega, 1u << log_blowup, nq, nullptr, 0, proof, proof_cap, proof_len,
                        nullptr);
-  if (forked) cudaStreamWaitEvent(main_stream, ctx->side_done[0], 0);   // join (also on an error path: the trees are freed below)
-  if (rc == STARK_OK && d_roots && column_roots && n_cols > first_col &&
-      cudaMemcpyAsync(column_roots + 32 * first_col, d_roots + 32 * first_col, 32 * (size_t)(n_cols - first_col),
-                      cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+  column_commit_join(ctx, &cc);
+  if (rc == STARK_OK && cc.d_roots && column_roots && n_cols > first_col &&
+      cudaMemcpyAsync(column_roots + 32 * first_col, cc.d_roots, 32 * (size_t)(n_cols - first_col), cudaMemcpyDeviceToHost,
+                      ctx->stream) != cudaSuccess)
     rc = stark_fail(ctx, STARK_ERR_CUDA, "D2H copy failed");
-  if (d_roots && cudaStreamSynchronize(ctx->stream) != cudaSuccess && rc == STARK_OK)
+  if (cc.d_roots && cudaStreamSynchronize(ctx->stream) != cudaSuccess && rc == STARK_OK)
     rc = stark_fail(ctx, STARK_ERR_CUDA, "column commitments failed");
   if (rc == STARK_OK && column_roots && first_col == 1) memcpy(column_roots, proof + 1, 32);  // first object = root of column 0
-  for (stark_tree *t : trees) stark_merkle_free(t);
-  dev_free(ctx, lde), dev_free(ctx, d_roots);
+  column_commit_free(ctx, &cc);
+  dev_free(ctx, lde);
   return rc;
 }
 
@@ -959,6 +1732,103 @@ int stark_prove_trace_rows(stark_ctx *ctx, const void *rows_i128, uint32_t n_col
     rc = stark_prove_trace_dev(ctx, in, n_cols, log_n, log_blowup, offset, nq, column_roots, proof, proof_cap, proof_len);
   stark_buf_free(in);
   return rc;
+}
+
+}  // extern "C"
+
+extern "C" {
+
+uint32_t stark_mgpu_owned_columns(const stark_mgpu *m, uint32_t n_cols, uint32_t *out) {
+  return m ? mg_owned_columns(m->rank, m->world, n_cols, out) : 0;
+}
+
+static int mg_check_ranks(stark_mgpu *const *ranks, int n_here) {
+  if (!ranks || n_here < 1 || n_here > MG_MAX_RANKS) return stark_fail(nullptr, STARK_ERR_ARG, "null argument");
+  for (int k = 0; k < n_here; k++)
+    if (!ranks[k]) return stark_fail(nullptr, STARK_ERR_ARG, "null argument");
+  if (ranks[0]->mode == MG_LOCAL) {
+    if (n_here != ranks[0]->world) return stark_fail(ranks[0]->ctx, STARK_ERR_ARG, "a local group is driven with all of its ranks in one call");
+    for (int k = 0; k < n_here; k++)
+      if (ranks[k]->rank != k || ranks[k]->group != ranks[0]->group) return stark_fail(ranks[0]->ctx, STARK_ERR_ARG, "ranks of a local group must be passed in rank order");
+  } else if (n_here != 1) {
+    return stark_fail(ranks[0]->ctx, STARK_ERR_ARG, "a multi-process group is driven one rank per call");
+  }
+  return STARK_OK;
+}
+
+int stark_mgpu_prove_trace(stark_mgpu *const *ranks, int n_here, const uint64_t *cols, uint32_t n_cols, uint32_t log_n,
+                           uint32_t log_blowup, uint64_t offset, uint32_t nq, uint8_t *const *column_roots,
+                           uint8_t *const *proofs, size_t proof_cap, size_t *proof_len) {
+  ST_TRY(mg_check_ranks(ranks, n_here));
+  if (!cols) return stark_fail(ranks[0]->ctx, STARK_ERR_ARG, "null argument");
+  return mg_prove_trace_impl(ranks, n_here, cols, nullptr, n_cols, log_n, log_blowup, offset, nq, column_roots, proofs, proof_cap, proof_len);
+}
+int stark_mgpu_prove_trace_dev(stark_mgpu *const *ranks, int n_here, const stark_buf *const *my_cols, uint32_t n_cols,
+                               uint32_t log_n, uint32_t log_blowup, uint64_t offset, uint32_t nq,
+                               uint8_t *const *column_roots, uint8_t *const *proofs, size_t proof_cap, size_t *proof_len) {
+  ST_TRY(mg_check_ranks(ranks, n_here));
+  if (!my_cols) return stark_fail(ranks[0]->ctx, STARK_ERR_ARG, "null argument");
+  return mg_prove_trace_impl(ranks, n_here, nullptr, my_cols, n_cols, log_n, log_blowup, offset, nq, column_roots, proofs, proof_cap, proof_len);
+}
+
+int stark_mgpu_fri_prove_dev(stark_mgpu *const *ranks, int n_here, const stark_buf *const *codewords, size_t n,
+                             size_t domain_length, uint64_t offset, uint64_t omega, uint32_t ef, uint32_t nq,
+                             const uint8_t *transcript, size_t transcript_len, uint8_t *const *proofs, size_t proof_cap,
+                             size_t *proof_len, uint64_t *const *top_indices) {
+  ST_TRY(mg_check_ranks(ranks, n_here));
+  if (!codewords || !proofs) return stark_fail(ranks[0]->ctx, STARK_ERR_ARG, "null argument");
+  u32 off, om;
+  reduce_params(ranks[0]->ctx, offset, omega, &off, &om);
+  std::vector<MgProve> P(n_here);
+  int rc = STARK_OK;
+  for (int k = 0; k < n_here; k++) {
+    mg_use(ranks[k]);
+    if (!codewords[k] || !proofs[k] || codewords[k]->n < n) {
+      mg_begin_op(ranks[k]);
+      rc = stark_fail(ranks[k]->ctx, STARK_ERR_ARG, "buffer too small");
+      continue;
+    }
+    const int e = P[k].begin(ranks[k], codewords[k]->ptr, n, domain_length, off, om, ef, nq, transcript, transcript_len, proof_cap, proof_len);
+    if (rc == STARK_OK) rc = e;
+  }
+  if (rc == STARK_OK) rc = mg_prove_run(P.data(), n_here);
+  if (rc == STARK_OK) rc = mg_prove_finish(P.data(), n_here);
+  for (int k = 0; k < n_here; k++) {
+    mg_use(ranks[k]);
+    if (rc == STARK_OK) rc = P[k].download(proofs[k], top_indices ? top_indices[k] : nullptr);
+  }
+  for (int k = 0; k < n_here; k++) {
+    mg_use(ranks[k]);
+    const int e = mg_check_err(ranks[k]);
+    if (rc == STARK_OK) rc = e;
+    P[k].release();
+  }
+  return rc;
+}
+
+int stark_mgpu_fold_commit_round(stark_mgpu *const *ranks, int n_here, const stark_buf *const *codewords, size_t n,
+                                 uint64_t offset, uint64_t omega, uint8_t *const *roots, uint64_t *alpha_raw,
+                                 stark_buf **folded) {
+  ST_TRY(mg_check_ranks(ranks, n_here));
+  if (!codewords) return stark_fail(ranks[0]->ctx, STARK_ERR_ARG, "null argument");
+  u32 off, om;
+  reduce_params(ranks[0]->ctx, offset, omega, &off, &om);
+  return mg_fold_commit_round_impl(ranks, n_here, codewords, n, off, om, roots, alpha_raw, folded);
+}
+
+int stark_mgpu_lde_commit(stark_mgpu *const *ranks, int n_here, const uint64_t *cols, uint32_t n_groups, uint32_t group_width,
+                          uint32_t log_n, uint32_t log_blowup, uint64_t offset, uint8_t *const *group_roots,
+                          uint8_t *const *commitments) {
+  ST_TRY(mg_check_ranks(ranks, n_here));
+  if (!cols) return stark_fail(ranks[0]->ctx, STARK_ERR_ARG, "null argument");
+  return mg_lde_commit_impl(ranks, n_here, cols, nullptr, n_groups, group_width, log_n, log_blowup, offset, group_roots, commitments);
+}
+int stark_mgpu_lde_commit_dev(stark_mgpu *const *ranks, int n_here, const stark_buf *const *owned_groups, uint32_t n_groups,
+                              uint32_t group_width, uint32_t log_n, uint32_t log_blowup, uint64_t offset,
+                              uint8_t *const *group_roots, uint8_t *const *commitments) {
+  ST_TRY(mg_check_ranks(ranks, n_here));
+  if (!owned_groups) return stark_fail(ranks[0]->ctx, STARK_ERR_ARG, "null argument");
+  return mg_lde_commit_impl(ranks, n_here, nullptr, owned_groups, n_groups, group_width, log_n, log_blowup, offset, group_roots, commitments);
 }
 
 }  // extern "C"

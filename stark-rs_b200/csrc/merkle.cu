@@ -128,9 +128,11 @@ __global__ void __launch_bounds__(HASH_NT) k_merkle_level(const u8 *__restrict__
 // climb ends at the root and tr.T is set, thread 0 runs the transcript round (fri.rs:129-138) on it.
 //   <256>: many CTAs, chunks of 512 nodes, 9 levels per launch (two hs2 steps, then seven 4-lanes-per-hash steps)
 //   <512>: the single top CTA, up to 1024 nodes
+//   X.world > 1: the tree is one rank's SUBTREE of a sharded tree -- the CTA that ends up with the subtree root exchanges
+//   it with the peers and climbs the replicated top levels before the transcript round (mg_exchange_top)
 template <int NT>
 __global__ void __launch_bounds__(NT) k_merkle_climb(u8 *nodes, size_t n, u32 level_in, u32 cnt, u32 levels,
-                                                     TranscriptArgs tr, u32 *counter) {
+                                                     TranscriptArgs tr, u32 *counter, const __grid_constant__ MgExchange X) {
   __shared__ __align__(16) u8 sm[2 * NT * 32];
   __shared__ u32 ticket;
   pdl_entry();
@@ -157,7 +159,16 @@ __global__ void __launch_bounds__(NT) k_merkle_climb(u8 *nodes, size_t n, u32 le
     cta_climb<NT>(nodes, n, level, 0, m, top_levels, sm, sm, blockDim.y);
     level += top_levels;
   }
-  if (tr.T != nullptr && t < 32 && (n >> level) == 1) transcript_round_warp(tr, sm);
+  if ((n >> level) != 1) return;
+  if (X.world > 1 && !mg_exchange_top<NT>(X, sm, blockDim.y)) return;
+  if (tr.T != nullptr && t < 32) transcript_round_warp(tr, sm);
+}
+// lock-step groups (virtual ranks on one device): the wait / top / transcript half as its own launch
+__global__ void __launch_bounds__(128) k_mg_top(TranscriptArgs tr, const __grid_constant__ MgExchange X) {
+  __shared__ __align__(16) u8 sm[2 * 128 * 32];
+  pdl_entry();
+  mg_exchange_top<128>(X, sm, blockDim.y);
+  if (tr.T != nullptr && threadIdx.x < 32) transcript_round_warp(tr, sm);
 }
 // the root of a one-leaf tree is the leaf itself (merkle.rs:11-38 with n = 1)
 __global__ void k_transcript_only(const u8 *root_hash, TranscriptArgs tr) {
@@ -199,8 +210,12 @@ int merkle_leaves_dev(stark_ctx *ctx, const u32 *vals, size_t n, u32 width, size
 }
 
 // nodes[0 .. n) already holds the leaves; fill the upper levels.  tr (optional): transcript round on the root.
-int merkle_climb_dev(stark_ctx *ctx, u8 *nodes, size_t n, const TranscriptArgs *tr) {
+int merkle_climb_dev(stark_ctx *ctx, u8 *nodes, size_t n, const TranscriptArgs *tr, const MgExchange *mx) {
   const TranscriptArgs none = {nullptr, nullptr, 0, nullptr, nullptr};
+  MgExchange X;
+  memset(&X, 0, sizeof X);
+  if (mx) X = *mx;
+  if (X.world > 1 && n < 2) return stark_fail(ctx, STARK_ERR_ARG, "a sharded tree needs at least two leaves per rank");
   u32 level = 0;
   size_t m = n;
   // throughput-bound levels: one launch each.  A level of 2^17 parents is already half latency (12 us against 6 us for the
@@ -220,14 +235,20 @@ int merkle_climb_dev(stark_ctx *ctx, u8 *nodes, size_t n, const TranscriptArgs *
     const u32 chunk = m > ((size_t)1 << 17) ? 1024u : 512u, chunk_levels = chunk == 1024u ? 10u : 9u;
     const size_t ctas = m / chunk;
     LAUNCH_PDL(ctx, "merkle_climb", 96ull * (m - 1), k_merkle_climb<256>, (u32)ctas, 256, nodes, n, level, chunk, chunk_levels,
-               tr ? *tr : none, ctx->climb_counter);
+               tr ? *tr : none, ctx->climb_counter, X);
   } else if (m > 1) {
     u32 levels = 0;
     for (size_t c = m; c > 1; c >>= 1) levels++;
     LAUNCH_PDL(ctx, "merkle_top", 96ull * (m - 1), k_merkle_climb<512>, 1u, 512, nodes, n, level, (u32)m, levels,
-               tr ? *tr : none, (u32 *)nullptr);
+               tr ? *tr : none, (u32 *)nullptr, X);
   }
   if (n == 1 && tr) LAUNCH(ctx, "transcript", 0, k_transcript_only<<<1, 32, 0, ctx->stream>>>(nodes, *tr));
+  return STARK_OK;
+}
+// the second half of a sharded tree's root step for lock-step groups (MG_X_WAIT)
+int merkle_mg_top_dev(stark_ctx *ctx, const TranscriptArgs *tr, const MgExchange *mx) {
+  const TranscriptArgs none = {nullptr, nullptr, 0, nullptr, nullptr};
+  LAUNCH_PDL(ctx, "mg_top", 0, k_mg_top, 1u, 128, tr ? *tr : none, *mx);
   return STARK_OK;
 }
 

@@ -21,7 +21,9 @@ int merkle_check_n(stark_ctx *ctx, size_t n);
 int merkle_tree_alloc(stark_ctx *ctx, size_t n, stark_tree **out);
 int merkle_leaves_dev(stark_ctx *ctx, const u32 *vals, size_t n, u32 width, size_t row_stride, size_t col_stride,
                       u8 *out);
-int merkle_climb_dev(stark_ctx *ctx, u8 *nodes, size_t n, const TranscriptArgs *tr = nullptr);
+struct MgExchange;
+int merkle_climb_dev(stark_ctx *ctx, u8 *nodes, size_t n, const TranscriptArgs *tr = nullptr, const MgExchange *mx = nullptr);
+int merkle_mg_top_dev(stark_ctx *ctx, const TranscriptArgs *tr, const MgExchange *mx);
 int merkle_build_from_dev_values(stark_ctx *ctx, const u32 *vals, size_t n, u32 width, size_t row_stride,
                                  size_t col_stride, stark_tree **out, const TranscriptArgs *tr = nullptr);
 int merkle_open_dev(stark_ctx *ctx, const u8 *nodes, size_t n, const u64 *idx_dev, u32 n_idx, u8 *out_dev);

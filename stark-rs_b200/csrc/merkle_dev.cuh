@@ -82,3 +82,68 @@ __device__ __forceinline__ void cta_climb(uint8_t *nodes, size_t n, uint32_t lev
     CLIMB_TICK();
   }
 }
+
+// ------------------------------------------------------------------------------------ multi-GPU root exchange
+// (mgpu.h)  Called by ALL threads of the CTA that holds a rank's 32-byte subtree root in sm[0..32): store it into every
+// peer's window, raise this round's epoch flag there, wait until every peer's flag has arrived here, then climb the
+// `world` roots to the tree root (the top log2(world) levels of MerkleTree::new, merkle.rs:21-27, replicated on every
+// rank) and leave it in sm[0..32).  Returns false when this launch only signals (lock-step groups).
+#include "mgpu.h"
+
+__device__ __forceinline__ void mg_st_release_sys(uint32_t *p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t mg_ld_acquire_sys(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long mg_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// spin until *flag has reached `epoch` (epochs only grow; compared modulo 2^32).  A peer that never arrives must not hang
+// the GPU: after MG_TIMEOUT_NS the wait gives up and records the failure (the host returns STARK_ERR_NCCL).
+constexpr unsigned long long MG_TIMEOUT_NS = 4000000000ull;
+__device__ __forceinline__ void mg_wait_flag(const uint32_t *flag, uint32_t epoch, uint32_t *err) {
+  if ((int32_t)(mg_ld_acquire_sys(flag) - epoch) >= 0) return;
+  const unsigned long long t0 = mg_now_ns();
+  while ((int32_t)(mg_ld_acquire_sys(flag) - epoch) < 0) {
+    if (mg_now_ns() - t0 > MG_TIMEOUT_NS) {
+      atomicOr(err, 1u);
+      return;
+    }
+    __nanosleep(64);
+  }
+}
+
+template <int NT>
+__device__ __forceinline__ bool mg_exchange_top(const MgExchange &X, uint8_t *sm, uint32_t one) {
+  const uint32_t t = threadIdx.x;
+  const int G = X.world;
+  if (X.mode != MG_X_WAIT) {
+    // the root as 8 words to each of the G ranks (own window included: the top tree reads all roots from one place)
+    if (t < 8u * G) {
+      const uint32_t g = t >> 3, w = t & 7u;
+      reinterpret_cast<uint32_t *>(X.slot_peer[g] + 32 * X.rank)[w] = reinterpret_cast<const uint32_t *>(sm)[w];
+      __threadfence_system();
+    }
+    __syncthreads();
+    if (t < (uint32_t)G) mg_st_release_sys(X.flag_peer[t] + X.rank, X.epoch);
+    if (X.mode == MG_X_SIGNAL) return false;
+  }
+  if (t < (uint32_t)G) mg_wait_flag(X.flag_local + t, X.epoch, X.err_local);
+  __syncthreads();
+  // leaves of the top tree: the G roots, written by the peers into this rank's window (read past L1)
+  if (t < 2u * G) {
+    const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(X.slot_local) + t);
+    reinterpret_cast<uint4 *>(sm)[t] = v;
+    reinterpret_cast<uint4 *>(X.top_nodes)[t] = v;
+  }
+  __syncthreads();
+  uint32_t levels = 0;
+  for (int c = G; c > 1; c >>= 1) levels++;
+  cta_climb<NT>(X.top_nodes, (size_t)G, 0, 0, (uint32_t)G, levels, sm, sm, one);
+  return true;
+}
