@@ -154,6 +154,17 @@ int upload_u64_nosync(stark_ctx *ctx, const uint64_t *host, size_t n, u32 *dst) 
   CU_TRY(ctx, cudaMemcpyAsync(ctx->h_flag + 2, ctx->flag + 2, 4, cudaMemcpyDeviceToHost, ctx->stream));
   return STARK_OK;
 }
+// pipelines that copy the host values themselves (column groups on a copy stream, fri.cu): narrowing of values already
+// on the device, on the context's current stream, and the flag copy queued once at the end
+int narrow_dev(stark_ctx *ctx, const uint64_t *staging_dev, size_t n, u32 *dst) {
+  if (n == 0) return STARK_OK;
+  LAUNCH(ctx, "narrow_u64", 12ull * n, k_narrow<<<(u32)((n + 255) / 256), 256, 0, ctx->stream>>>(staging_dev, dst, n, ctx->flag + 2));
+  return STARK_OK;
+}
+int upload_flag_fetch(stark_ctx *ctx) {
+  CU_TRY(ctx, cudaMemcpyAsync(ctx->h_flag + 2, ctx->flag + 2, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  return STARK_OK;
+}
 int upload_u64_check(stark_ctx *ctx) {   // call after the stream has been synchronised
   if (ctx->h_flag[2]) return stark_fail(ctx, STARK_ERR_ARG, "non-canonical field element (value >= p) in input");
   return STARK_OK;
@@ -220,10 +231,10 @@ static int ctx_create(int device, cudaStream_t borrowed, bool borrow, stark_ctx 
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
   }
   int rc = STARK_OK;
-  if (cudaMalloc(&ctx->flag, 16) != cudaSuccess || cudaMallocHost(&ctx->h_flag, 16) != cudaSuccess)
+  if (cudaMalloc(&ctx->flag, 4 * FLAG_WORDS) != cudaSuccess || cudaMallocHost(&ctx->h_flag, 16) != cudaSuccess)
     rc = stark_fail(nullptr, STARK_ERR_OOM, "context allocation failed");
-  if (rc == STARK_OK && cudaMemset(ctx->flag, 0, 16) != cudaSuccess) rc = stark_fail(nullptr, STARK_ERR_CUDA, "context initialisation failed");
-  ctx->climb_counter = ctx->flag + 1;
+  if (rc == STARK_OK && cudaMemset(ctx->flag, 0, 4 * FLAG_WORDS) != cudaSuccess) rc = stark_fail(nullptr, STARK_ERR_CUDA, "context initialisation failed");
+  ctx->climb_counter = ctx->flag + TICKET_MAIN;
   // k_merkle_climb<256> takes at most 256 chunks of 512 / 1024 nodes (its fused top holds the chunk roots in 16 KB of
   // shared memory): the tuning knob is clamped to the range the kernel supports
   ctx->climb_log = 18;

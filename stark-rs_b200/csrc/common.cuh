@@ -19,6 +19,7 @@ struct GeoCacheEntry {
   u32 *lo, *hi;    // device tables (4096 + hi_len entries)
   u32 hi_len;
   u64 stamp;
+  cudaEvent_t ready;   // recorded behind the kernel that fills the tables: a hit from another stream waits for it
 };
 
 struct stark_ctx {
@@ -39,8 +40,9 @@ struct stark_ctx {
   ntt::wpair *row_sh[2];   // w_{2^logN}^(+-row), row < 2048, at [(logN - 13) * 2048 + row], logN = 13..23 (FIRST pass)
   GeoCacheEntry geo[8];
   u64 geo_stamp;
-  u32 *flag;       // four device ints: [0], [2] validation flags, [1], [3] last-CTA tickets of the Merkle climb kernel
-  u32 *climb_counter;   // the ticket the next climb launch uses: flag + 1, or flag + 3 for work queued on a side stream
+  u32 *flag;       // device ints: [0], [2] validation flags; [4 .. 4 + 64): last-CTA tickets of the Merkle climb kernel for
+                   // launches on the context's stream, [68 .. 132): the same for work queued on a side stream
+  u32 *climb_counter;   // the tickets the next climb launch uses (one per tree of a batch): flag + 4, or flag + 68
   u32 *h_flag;     // pinned host mirror
   u64 launches;    // kernels launched through this context (bench.py "gpu_launches")
   // side streams for batched transforms larger than L2 (ntt.cu: column groups run all passes back to back, a few groups
@@ -60,6 +62,7 @@ struct stark_ctx {
   struct ProfRec *prof;   // growing array
   size_t prof_n, prof_cap;
 };
+constexpr int FLAG_WORDS = 4 + 2 * 64, TICKET_MAIN = 4, TICKET_SIDE = 68;   // layout of stark_ctx::flag
 struct ProfRec {
   const char *tag;
   u64 bytes;              // algorithmic HBM bytes of this launch, 0 if not meaningful

@@ -1034,53 +1034,162 @@ static int mg_prove_finish(MgProve *P, int count) {
   return rc;
 }
 
-// ---- per-column commitments on a side stream (shared by the single-GPU and the sharded config-3 pipelines)
-// The trees of the columns that are not FRI-proved are throughput work that does not depend on the FRI, whose rounds are
-// a latency-bound chain: they are queued on a side stream so that they fill the SMs the FRI leaves idle.
-// The climb kernel's last-CTA ticket is per stream.
-struct ColumnCommit {
-  std::vector<stark_tree *> trees;
-  u8 *d_roots = nullptr;      // one root per committed column, in the order given
-  bool forked = false;
+// ---- the columns that are not FRI-proved, on their own stream (shared by the single-GPU and the sharded config-3
+// pipelines).  Their LDE and trees are throughput work that does not depend on the FRI, whose rounds are a latency-bound
+// chain: queued on the column stream they fill the SMs the FRI leaves idle.  Columns go through in GROUPS:
+// one batched LDE per group and ONE set of tree launches for all trees of the group (merkle_build_batch_dev), so the
+// latency-bound top levels of the trees overlap instead of queueing behind one another.  With host input every group is
+// copied on a third stream (ctx->side[3]) while the groups before it compute: only the first copy is exposed.
+// The climb kernel's last-CTA tickets are per stream (TICKET_SIDE for the column stream).
+constexpr int COL_STREAM = 2, COPY_STREAM = 3;
+struct ColumnPipe {
   cudaStream_t main_stream = nullptr;
+  bool forked = false;
+  std::vector<u8 *> node_blocks;    // one allocation per group: its trees, tree_stride bytes apart
+  std::vector<cudaEvent_t> events;  // copy-done events (host input)
+  u64 *staging = nullptr;           // host input: the uint64 trace as copied (column-major), narrowed group by group
+  u8 *d_roots = nullptr;            // one root per committed column, in the order committed
+  u32 n_roots = 0;
 };
-static int column_commit_begin(stark_ctx *ctx, const u32 *lde, size_t N, const u32 *local_cols, u32 count, ColumnCommit *cc) {
-  cc->main_stream = ctx->stream;
-  if (count == 0) return STARK_OK;
-  ST_TRY(dev_alloc(ctx, (void **)&cc->d_roots, 32 * (size_t)count));
-  if (!ctx->prof_on && side_streams(ctx, 1) == STARK_OK) {
-    cudaEventRecord(ctx->fork_ev, cc->main_stream);
-    cudaStreamWaitEvent(ctx->side[0], ctx->fork_ev, 0);
-    ctx->stream = ctx->side[0], ctx->climb_counter = ctx->flag + 3, cc->forked = true;
+static size_t tree_stride_of(size_t N) { return ((2 * N - 1) * 32 + 255) & ~(size_t)255; }
+
+// route the context's launches to the column stream / back (the launch macros use ctx->stream)
+static void column_pipe_enter(stark_ctx *ctx, ColumnPipe *cp) {
+  if (cp->forked) ctx->stream = ctx->side[COL_STREAM], ctx->climb_counter = ctx->flag + TICKET_SIDE;
+}
+static void column_pipe_leave(stark_ctx *ctx, ColumnPipe *cp) {
+  if (cp->forked) ctx->stream = cp->main_stream, ctx->climb_counter = ctx->flag + TICKET_MAIN;
+}
+// fork the column (and copy) stream from the context's stream: everything allocated or written so far is visible there
+static int column_pipe_begin(stark_ctx *ctx, ColumnPipe *cp, u32 max_roots) {
+  cp->main_stream = ctx->stream;
+  if (max_roots) ST_TRY(dev_alloc(ctx, (void **)&cp->d_roots, 32 * (size_t)max_roots));
+  if (!ctx->prof_on && side_streams(ctx, 4) == STARK_OK) {
+    cudaEventRecord(ctx->fork_ev, cp->main_stream);
+    cudaStreamWaitEvent(ctx->side[COL_STREAM], ctx->fork_ev, 0);
+    cudaStreamWaitEvent(ctx->side[COPY_STREAM], ctx->fork_ev, 0);
+    cp->forked = true;
   }
+  return STARK_OK;
+}
+// queue the H2D copy of n_elems host values into the staging buffer at element offset dst_off (copy stream); when
+// `record` the event to wait for is returned (one per group, after the group's last copy)
+static int column_pipe_copy(stark_ctx *ctx, ColumnPipe *cp, const uint64_t *src, size_t dst_off, size_t n_elems, bool record,
+                            cudaEvent_t *ev) {
+  cudaStream_t st = cp->forked ? ctx->side[COPY_STREAM] : ctx->stream;
+  CU_TRY(ctx, cudaMemcpyAsync(cp->staging + dst_off, src, 8 * n_elems, cudaMemcpyHostToDevice, st));
+  if (ev) *ev = nullptr;
+  if (cp->forked && record && ev) {
+    CU_TRY(ctx, cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+    cp->events.push_back(*ev);
+    CU_TRY(ctx, cudaEventRecord(*ev, st));
+  }
+  return STARK_OK;
+}
+// On the CURRENT stream of the context: [wait for the group's copy, narrow it] -> [LDE of the group] -> batched trees ->
+// roots appended to d_roots.  cols_dev: the u32 columns (source of the LDE; written here when the input is on the host).
+static int column_pipe_group(stark_ctx *ctx, ColumnPipe *cp, cudaEvent_t copied, u32 *cols_dev, u32 *lde, u32 c0, u32 cnt,
+                             u32 log_n, u32 log_blowup, u32 offset, bool do_lde, bool do_trees) {
+  const size_t n = (size_t)1 << log_n, N = n << log_blowup;
+  if (cnt == 0) return STARK_OK;
+  if (copied) CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, copied, 0));
+  if (cp->staging) ST_TRY(narrow_dev(ctx, cp->staging + (size_t)c0 * n, n * cnt, cols_dev + (size_t)c0 * n));
+  if (do_lde) ST_TRY(lde_dev(ctx, cols_dev + (size_t)c0 * n, cnt, log_n, log_blowup, offset, lde + (size_t)c0 * N));
+  for (u32 b0 = 0; do_trees && b0 < cnt; b0 += CLIMB_TICKETS) {
+    const u32 nb = cnt - b0 < (u32)CLIMB_TICKETS ? cnt - b0 : (u32)CLIMB_TICKETS;
+    const size_t stride = tree_stride_of(N);
+    u8 *nodes = nullptr;
+    ST_TRY(dev_alloc(ctx, (void **)&nodes, stride * nb));
+    cp->node_blocks.push_back(nodes);
+    ST_TRY(merkle_build_batch_dev(ctx, lde + (size_t)(c0 + b0) * N, N, nb, N, nodes, stride));
+    CU_TRY(ctx, cudaMemcpy2DAsync(cp->d_roots + 32 * (size_t)cp->n_roots, 32, nodes + 32 * (2 * N - 2), stride, 32, nb,
+                                  cudaMemcpyDeviceToDevice, ctx->stream));
+    cp->n_roots += nb;
+  }
+  return STARK_OK;
+}
+// the context's stream waits for the column stream (also on an error path: the buffers are freed afterwards)
+static void column_pipe_join(stark_ctx *ctx, ColumnPipe *cp) {
+  if (cp->forked) {
+    cudaEventRecord(ctx->side_done[COL_STREAM], ctx->side[COL_STREAM]);
+    cudaStreamWaitEvent(cp->main_stream, ctx->side_done[COL_STREAM], 0);
+    cudaEventRecord(ctx->side_done[COPY_STREAM], ctx->side[COPY_STREAM]);
+    cudaStreamWaitEvent(cp->main_stream, ctx->side_done[COPY_STREAM], 0);
+  }
+  ctx->stream = cp->main_stream, ctx->climb_counter = ctx->flag + TICKET_MAIN;
+  cp->forked = false;
+}
+static void column_pipe_free(stark_ctx *ctx, ColumnPipe *cp) {
+  column_pipe_join(ctx, cp);
+  for (u8 *b : cp->node_blocks) dev_free(ctx, b);
+  cp->node_blocks.clear();
+  for (cudaEvent_t e : cp->events) cudaEventDestroy(e);
+  cp->events.clear();
+  dev_free(ctx, cp->d_roots), dev_free(ctx, cp->staging);
+  cp->d_roots = nullptr, cp->staging = nullptr;
+}
+
+// BASELINE config 3 on one device, from device columns (cols_dev) or from the host trace (host_cols; cols_dev then is the
+// buffer the narrowed columns go to): column 0 -> LDE -> Fri::prove on the context's stream, the other columns ->
+// LDE + trees on the column stream.
+static int prove_trace_pipeline(stark_ctx *ctx, const uint64_t *host_cols, u32 *cols_dev, uint32_t n_cols, uint32_t log_n,
+                                uint32_t log_blowup, uint32_t offset, uint32_t nq, uint8_t *column_roots, uint8_t *proof,
+                                size_t proof_cap, size_t *proof_len) {
+  const size_t n = (size_t)1 << log_n, N = n << log_blowup;
+  u32 fri_rounds = 0;
+  ST_TRY(fri_check(ctx, N, 1u << log_blowup, &fri_rounds, nq));
+  // With num_rounds() == 0 (N <= expansion factor or N <= 4 nq, fri.rs:93-103) Fri::commit builds no tree and the proof
+  // starts with the last codeword, so column 0 is committed like the others.
+  const bool tree0 = fri_rounds == 0;
+  u32 *lde = nullptr;
+  ColumnPipe cp;
+  ST_TRY(dev_alloc(ctx, (void **)&lde, N * n_cols * 4));
   int rc = STARK_OK;
-  for (u32 i = 0; i < count && rc == STARK_OK; i++) {
-    stark_tree *t = nullptr;
-    rc = merkle_build_from_dev_values(ctx, lde + (size_t)local_cols[i] * N, N, 1, 1, 0, &t);
-    if (rc == STARK_OK) {
-      cc->trees.push_back(t);
-      if (cudaMemcpyAsync(cc->d_roots + 32 * (size_t)i, t->nodes + 32 * (2 * N - 2), 32, cudaMemcpyDeviceToDevice, ctx->stream) !=
-          cudaSuccess)
-        rc = stark_fail(ctx, STARK_ERR_CUDA, "D2D copy failed");
+  if (host_cols) {
+    rc = dev_alloc(ctx, (void **)&cp.staging, 8 * n * n_cols);
+    if (rc == STARK_OK) rc = upload_flag_reset(ctx);
+  }
+  if (rc == STARK_OK) rc = column_pipe_begin(ctx, &cp, n_cols);
+  // groups: column 0 alone (the FRI waits for nothing else), then the rest -- in groups of 4 when they arrive from the
+  // host (compute of a group hides the copy of the next), in one group when they are already on the device
+  const u32 gs = host_cols ? 4u : (n_cols > 1 ? n_cols - 1 : 1u);
+  std::vector<cudaEvent_t> ev;
+  if (host_cols)
+    for (u32 c0 = 0; c0 < n_cols && rc == STARK_OK; c0 += (c0 == 0 ? 1 : gs)) {
+      cudaEvent_t e = nullptr;
+      const u32 cnt = c0 == 0 ? 1 : (n_cols - c0 < gs ? n_cols - c0 : gs);
+      rc = column_pipe_copy(ctx, &cp, host_cols + (size_t)c0 * n, (size_t)c0 * n, n * cnt, true, &e);
+      ev.push_back(e);
     }
+  // column 0 on the context's stream
+  if (rc == STARK_OK) rc = column_pipe_group(ctx, &cp, host_cols ? ev[0] : nullptr, cols_dev, lde, 0, 1, log_n, log_blowup, offset, true, tree0);
+  // the other columns on the column stream
+  if (rc == STARK_OK) {
+    column_pipe_enter(ctx, &cp);
+    u32 gi = 1;
+    for (u32 c0 = 1; c0 < n_cols && rc == STARK_OK; c0 += gs, gi++) {
+      const u32 cnt = n_cols - c0 < gs ? n_cols - c0 : gs;
+      rc = column_pipe_group(ctx, &cp, host_cols ? ev[gi] : nullptr, cols_dev, lde, c0, cnt, log_n, log_blowup, offset, true, true);
+    }
+    column_pipe_leave(ctx, &cp);
   }
-  if (cc->forked) {
-    cudaEventRecord(ctx->side_done[0], ctx->side[0]);
-    ctx->stream = cc->main_stream, ctx->climb_counter = ctx->flag + 1;
-  }
+  const u32 omega = ff::pow(ff::GEN, (ff::P - 1) >> (log_n + log_blowup));  // prim_nth_root(N), ff.rs:215-223
+  if (rc == STARK_OK)
+    rc = fri_prove_dev(ctx, lde, N, N, offset, omega, 1u << log_blowup, nq, nullptr, 0, proof, proof_cap, proof_len, nullptr);
+  column_pipe_join(ctx, &cp);
+  // roots: d_roots holds [column 0 if tree0] followed by columns 1..
+  const u32 first_col = tree0 ? 0u : 1u;
+  if (rc == STARK_OK && column_roots && cp.n_roots &&
+      cudaMemcpyAsync(column_roots + 32 * first_col, cp.d_roots, 32 * (size_t)cp.n_roots, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+    rc = stark_fail(ctx, STARK_ERR_CUDA, "D2H copy failed");
+  if (rc == STARK_OK && host_cols) rc = upload_flag_fetch(ctx);
+  if ((cp.n_roots || host_cols) && cudaStreamSynchronize(ctx->stream) != cudaSuccess && rc == STARK_OK)
+    rc = stark_fail(ctx, STARK_ERR_CUDA, "column commitments failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (rc == STARK_OK && column_roots && !tree0) memcpy(column_roots, proof + 1, 32);  // first object = root of column 0
+  if (rc == STARK_OK && host_cols) rc = upload_u64_check(ctx);
+  column_pipe_free(ctx, &cp);
+  dev_free(ctx, lde);
   return rc;
-}
-// the context's stream waits for the column trees (also on an error path: the trees are freed afterwards)
-static void column_commit_join(stark_ctx *ctx, ColumnCommit *cc) {
-  if (cc->forked) cudaStreamWaitEvent(cc->main_stream, ctx->side_done[0], 0);
-  cc->forked = false;
-}
-static void column_commit_free(stark_ctx *ctx, ColumnCommit *cc) {
-  column_commit_join(ctx, cc);
-  for (stark_tree *t : cc->trees) stark_merkle_free(t);
-  cc->trees.clear();
-  dev_free(ctx, cc->d_roots);
-  cc->d_roots = nullptr;
 }
 
 // which trace columns a rank commits in the sharded config 3: column 0 is LDE'd by every rank (its codeword is the FRI
@@ -1096,13 +1205,11 @@ static u32 mg_owned_columns(int rank, int world, u32 n_cols, u32 *out) {
 }
 
 struct MgTraceRank {
-  MgProve P;
-  ColumnCommit cc;
+  ColumnPipe cp;
   u32 *lde = nullptr;
   stark_buf *in = nullptr;       // host-input variant: this rank's columns on the device
   std::vector<u32> owned;        // global indices of the committed columns
   u32 n_my = 0;
-  int rc = STARK_OK;
 };
 
 static int mg_prove_trace_impl(stark_mgpu *const *ranks, int n_here, const uint64_t *host_cols, const stark_buf *const *my_cols,
@@ -1133,27 +1240,45 @@ static int mg_prove_trace_impl(stark_mgpu *const *ranks, int n_here, const uint6
     t.owned.resize(n_cols);
     t.owned.resize(mg_owned_columns(m->rank, m->world, n_cols, t.owned.data()));
     t.n_my = 1 + (u32)t.owned.size();
-    const u32 *cols_dev = nullptr;
+    u32 *cols_dev = nullptr;
     if (host_cols) {
       rc = stark_buf_alloc(ctx, n * t.n_my, &t.in);
-      if (rc == STARK_OK) rc = upload_flag_reset(ctx);
-      if (rc == STARK_OK) rc = upload_u64_nosync(ctx, host_cols, n, t.in->ptr);
-      for (u32 i = 0; i < t.owned.size() && rc == STARK_OK; i++)
-        rc = upload_u64_nosync(ctx, host_cols + (size_t)t.owned[i] * n, n, t.in->ptr + (size_t)(i + 1) * n);
       if (rc == STARK_OK) cols_dev = t.in->ptr;
+      if (rc == STARK_OK) rc = dev_alloc(ctx, (void **)&t.cp.staging, 8 * n * t.n_my);
+      if (rc == STARK_OK) rc = upload_flag_reset(ctx);
     } else {
       if (my_cols[k]->n < n * t.n_my) rc = stark_fail(ctx, STARK_ERR_ARG, "buffer too small");
       cols_dev = my_cols[k]->ptr;
     }
     if (rc == STARK_OK) rc = dev_alloc(ctx, (void **)&t.lde, N * t.n_my * 4);
-    if (rc == STARK_OK) rc = lde_dev(ctx, cols_dev, t.n_my, log_n, log_blowup, (u32)offset, t.lde);
+    // local column 0 = trace column 0 (LDE on the context's stream: the FRI input); local columns 1.. = the owned ones,
+    // LDE + batched trees on the column stream, in groups of 4 when they are copied from the host.  With
+    // num_rounds() == 0 Fri::commit builds no tree, so rank 0 commits column 0 as well.
+    const bool tree0 = fri_rounds == 0 && m->rank == 0;
+    if (rc == STARK_OK) rc = column_pipe_begin(ctx, &t.cp, t.n_my);
+    const u32 gs = host_cols ? 4u : (t.n_my > 1 ? t.n_my - 1 : 1u);
+    std::vector<cudaEvent_t> ev;
+    if (host_cols && rc == STARK_OK) {
+      cudaEvent_t e = nullptr;
+      rc = column_pipe_copy(ctx, &t.cp, host_cols, 0, n, true, &e);
+      ev.push_back(e);
+      for (u32 i0 = 1; i0 < t.n_my && rc == STARK_OK; i0 += gs) {
+        const u32 cnt = t.n_my - i0 < gs ? t.n_my - i0 : gs;
+        for (u32 i = i0; i < i0 + cnt && rc == STARK_OK; i++)
+          rc = column_pipe_copy(ctx, &t.cp, host_cols + (size_t)t.owned[i - 1] * n, (size_t)i * n, n, i + 1 == i0 + cnt, &e);
+        ev.push_back(e);
+      }
+    }
+    if (rc == STARK_OK)
+      rc = column_pipe_group(ctx, &t.cp, host_cols ? ev[0] : nullptr, cols_dev, t.lde, 0, 1, log_n, log_blowup, (u32)offset, true, tree0);
     if (rc == STARK_OK) {
-      // local column indices to commit here: 1.. (the owned ones); with num_rounds() == 0 Fri::commit builds no tree, so
-      // rank 0 commits column 0 as well
-      std::vector<u32> local;
-      if (fri_rounds == 0 && m->rank == 0) local.push_back(0);
-      for (u32 i = 0; i < t.owned.size(); i++) local.push_back(i + 1);
-      rc = column_commit_begin(ctx, t.lde, N, local.data(), (u32)local.size(), &t.cc);
+      column_pipe_enter(ctx, &t.cp);
+      u32 gi = 1;
+      for (u32 i0 = 1; i0 < t.n_my && rc == STARK_OK; i0 += gs, gi++) {
+        const u32 cnt = t.n_my - i0 < gs ? t.n_my - i0 : gs;
+        rc = column_pipe_group(ctx, &t.cp, host_cols ? ev[gi] : nullptr, cols_dev, t.lde, i0, cnt, log_n, log_blowup, (u32)offset, true, true);
+      }
+      column_pipe_leave(ctx, &t.cp);
     }
     if (rc == STARK_OK)
       rc = P[k].begin(m, t.lde, N, N, (u32)offset, omega, 1u << log_blowup, nq, nullptr, 0, proof_cap, proof_len);
@@ -1167,11 +1292,12 @@ static int mg_prove_trace_impl(stark_mgpu *const *ranks, int n_here, const uint6
     stark_mgpu *m = ranks[k];
     mg_use(m);
     MgTraceRank &t = T[k];
-    column_commit_join(m->ctx, &t.cc);
+    column_pipe_join(m->ctx, &t.cp);
     std::vector<u32> idx;
     if (fri_rounds == 0 && m->rank == 0) idx.push_back(0);
     for (u32 c : t.owned) idx.push_back(c);
-    if (!idx.empty()) rc = mg_put_roots(m, t.cc.d_roots, idx.data(), (u32)idx.size());
+    if (!idx.empty()) rc = mg_put_roots(m, t.cp.d_roots, idx.data(), (u32)idx.size());
+    if (rc == STARK_OK && host_cols) rc = upload_flag_fetch(m->ctx);
   }
   if (rc == STARK_OK) rc = mg_prove_finish(P.data(), n_here);
   for (int k = 0; k < n_here; k++) {
@@ -1192,7 +1318,7 @@ static int mg_prove_trace_impl(stark_mgpu *const *ranks, int n_here, const uint6
     if (rc == STARK_OK && fri_rounds > 0 && column_roots && column_roots[k]) memcpy(column_roots[k], proofs[k] + 1, 32);  // root of column 0
     if (rc == STARK_OK && host_cols) rc = upload_u64_check(ctx);
     P[k].release();
-    column_commit_free(ctx, &T[k].cc);
+    column_pipe_free(ctx, &T[k].cp);
     dev_free(ctx, T[k].lde);
     stark_buf_free(T[k].in);
   }
@@ -1365,7 +1491,7 @@ static int mg_lde_commit_impl(stark_mgpu *const *ranks, int n_here, const uint64
       // the group's tree on the tree stream, after its LDE
       cudaEventRecord(ctx->fork_ev, main_stream);
       cudaStreamWaitEvent(tree_stream, ctx->fork_ev, 0);
-      ctx->stream = tree_stream, ctx->climb_counter = ctx->flag + 3;
+      ctx->stream = tree_stream, ctx->climb_counter = ctx->flag + TICKET_SIDE;
       stark_tree *t = nullptr;
       rc = merkle_build_from_dev_values(ctx, lde, N, gw, 1, N, &t);   // column-major [gw][N]: row stride 1, column stride N
       if (rc == STARK_OK) {
@@ -1373,7 +1499,7 @@ static int mg_lde_commit_impl(stark_mgpu *const *ranks, int n_here, const uint64
         if (cudaMemcpyAsync(k.d_mine + 32 * (size_t)j, t->nodes + 32 * (2 * N - 2), 32, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess)
           rc = stark_fail(ctx, STARK_ERR_CUDA, "D2D copy failed");
       }
-      ctx->stream = main_stream, ctx->climb_counter = ctx->flag + 1;
+      ctx->stream = main_stream, ctx->climb_counter = ctx->flag + TICKET_MAIN;
     }
     cudaEventRecord(ctx->side_done[3], tree_stream);
     cudaStreamWaitEvent(main_stream, ctx->side_done[3], 0);
@@ -1668,53 +1794,23 @@ int stark_prove_trace_dev(stark_ctx *ctx, const stark_buf *cols, uint32_t n_cols
   if (offset == 0 || offset >= ff::P) return stark_fail(ctx, STARK_ERR_ARG, "offset must be a non-zero canonical element");
   const size_t n = (size_t)1 << log_n, N = n << log_blowup;
   if (cols->n < n * n_cols) return stark_fail(ctx, STARK_ERR_ARG, "buffer too small");
-  u32 *lde = nullptr;
-  ST_TRY(dev_alloc(ctx, (void **)&lde, N * n_cols * 4));
-  int rc = lde_dev(ctx, cols->ptr, n_cols, log_n, log_blowup, (u32)offset, lde);
-  // commitments of columns 1.. on the side stream (column 0's tree is built inside Fri::commit, fri.rs:118-127, and its
-  // root is the first proof object).  With num_rounds() == 0 (N <= expansion factor or N <= 4 nq, fri.rs:93-103)
-  // Fri::commit builds no tree and the proof starts with the last codeword, so column 0 is committed here like the others.
-  u32 fri_rounds = 0;
-  if (rc == STARK_OK) rc = fri_check(ctx, N, 1u << log_blowup, &fri_rounds, nq);
-  const u32 first_col = fri_rounds == 0 ? 0u : 1u;
-  ColumnCommit cc;
-  if (rc == STARK_OK) {
-    std::vector<u32> local;
-    for (u32 c = first_col; c < n_cols; c++) local.push_back(c);
-    rc = column_commit_begin(ctx, lde, N, local.data(), (u32)local.size(), &cc);
-  }
-  const u32 omega = ff::pow(ff::GEN, (ff::P - 1) >> (log_n + log_blowup));  // prim_nth_root(N), ff.rs:215-223
-  if (rc == STARK_OK)
-    rc = fri_prove_dev(ctx, lde, N, N, (u32)offset, omega, 1u << log_blowup, nq, nullptr, 0, proof, proof_cap, proof_len,
-                       nullptr);
-  column_commit_join(ctx, &cc);
-  if (rc == STARK_OK && cc.d_roots && column_roots && n_cols > first_col &&
-      cudaMemcpyAsync(column_roots + 32 * first_col, cc.d_roots, 32 * (size_t)(n_cols - first_col), cudaMemcpyDeviceToHost,
-                      ctx->stream) != cudaSuccess)
-    rc = stark_fail(ctx, STARK_ERR_CUDA, "D2H copy failed");
-  if (cc.d_roots && cudaStreamSynchronize(ctx->stream) != cudaSuccess && rc == STARK_OK)
-    rc = stark_fail(ctx, STARK_ERR_CUDA, "column commitments failed");
-  if (rc == STARK_OK && column_roots && first_col == 1) memcpy(column_roots, proof + 1, 32);  // first object = root of column 0
-  column_commit_free(ctx, &cc);
-  dev_free(ctx, lde);
-  return rc;
+  return prove_trace_pipeline(ctx, nullptr, cols->ptr, n_cols, log_n, log_blowup, (u32)offset, nq, column_roots, proof, proof_cap,
+                              proof_len);
 }
 
 int stark_prove_trace(stark_ctx *ctx, const uint64_t *cols, uint32_t n_cols, uint32_t log_n, uint32_t log_blowup,
                       uint64_t offset, uint32_t nq, uint8_t *column_roots, uint8_t *proof, size_t proof_cap,
                       size_t *proof_len) {
-  if (!ctx || !cols) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
-  if (log_n > (u32)ff::TWO_ADICITY) return stark_fail(ctx, STARK_ERR_ARG, "n > 2^23 not supported by this modulus");
+  if (!ctx || !cols || n_cols == 0) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+  if (log_n + log_blowup > (u32)ff::TWO_ADICITY) return stark_fail(ctx, STARK_ERR_ARG, "n > 2^23 not supported by this modulus");
+  if (offset == 0 || offset >= ff::P) return stark_fail(ctx, STARK_ERR_ARG, "offset must be a non-zero canonical element");
   stark_buf *in = nullptr;
-  const size_t total = ((size_t)1 << log_n) * n_cols;
-  ST_TRY(stark_buf_alloc(ctx, total, &in));
-  // H2D + narrowing without a host round trip: the canonical check is read after the pipeline's final sync
-  int rc = upload_flag_reset(ctx);
-  if (rc == STARK_OK) rc = upload_u64_nosync(ctx, cols, total, in->ptr);
-  if (rc == STARK_OK)
-    rc = stark_prove_trace_dev(ctx, in, n_cols, log_n, log_blowup, offset, nq, column_roots, proof, proof_cap, proof_len);
+  ST_TRY(stark_buf_alloc(ctx, ((size_t)1 << log_n) * n_cols, &in));
+  // H2D (group by group on the copy stream) + narrowing without a host round trip: the canonical check is read after
+  // the pipeline's final synchronisation
+  const int rc = prove_trace_pipeline(ctx, cols, in->ptr, n_cols, log_n, log_blowup, (u32)offset, nq, column_roots, proof, proof_cap,
+                                      proof_len);
   stark_buf_free(in);
-  if (rc == STARK_OK) rc = upload_u64_check(ctx);
   return rc;
 }
 

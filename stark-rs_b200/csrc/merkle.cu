@@ -23,10 +23,13 @@ using hs::State;
 constexpr int HASH_NT = 64;
 
 // leaf i = Hash::from_field_elements(&[vals[i]])  (fri.rs:118-121, hash.rs:32-35); two leaves per thread (hs2)
-__global__ void __launch_bounds__(HASH_NT) k_leaf_hash1(const u32 *__restrict__ vals, size_t n, u8 *__restrict__ out) {
+// blockIdx.y = tree of a batch of equally sized trees (column c of an LDE matrix -> tree c): strides in elements / bytes
+__global__ void __launch_bounds__(HASH_NT) k_leaf_hash1(const u32 *__restrict__ vals, size_t n, u8 *__restrict__ out,
+                                                        size_t val_stride, size_t out_stride) {
   pdl_entry();
   const size_t i = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
   if (i >= n) return;
+  vals += (size_t)blockIdx.y * val_stride, out += (size_t)blockIdx.y * out_stride;
   const bool two = i + 1 < n;
   u32 va, vb = 0;
   if (two) {
@@ -109,10 +112,12 @@ __global__ void __launch_bounds__(128) k_hash_bytes(const u8 *__restrict__ msgs,
 }
 
 // one tree level: parent i = Hash::combine(child 2i, child 2i+1)  (merkle.rs:21-27); two parents per thread
-__global__ void __launch_bounds__(HASH_NT) k_merkle_level(const u8 *__restrict__ in, u8 *__restrict__ out, size_t n_out) {
+__global__ void __launch_bounds__(HASH_NT) k_merkle_level(const u8 *__restrict__ in, u8 *__restrict__ out, size_t n_out,
+                                                          size_t tree_stride) {
   pdl_entry();
   const size_t i = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
   if (i >= n_out) return;
+  in += (size_t)blockIdx.y * tree_stride, out += (size_t)blockIdx.y * tree_stride;
   const bool two = i + 1 < n_out;
   u32 la[8], ra[8], lb[8], rb[8], wa[8], wb[8];
   load_hash(in + 64 * i, la);
@@ -132,10 +137,13 @@ __global__ void __launch_bounds__(HASH_NT) k_merkle_level(const u8 *__restrict__
 //   it with the peers and climbs the replicated top levels before the transcript round (mg_exchange_top)
 template <int NT>
 __global__ void __launch_bounds__(NT) k_merkle_climb(u8 *nodes, size_t n, u32 level_in, u32 cnt, u32 levels,
-                                                     TranscriptArgs tr, u32 *counter, const __grid_constant__ MgExchange X) {
+                                                     TranscriptArgs tr, u32 *counter, const __grid_constant__ MgExchange X,
+                                                     size_t tree_stride) {
   __shared__ __align__(16) u8 sm[2 * NT * 32];
   __shared__ u32 ticket;
   pdl_entry();
+  nodes += (size_t)blockIdx.y * tree_stride;   // batch of equally sized trees: one ticket per tree
+  if (counter != nullptr) counter += blockIdx.y;
   const u32 t = threadIdx.x;
   const size_t first = (size_t)blockIdx.x * cnt;
   cta_climb<NT>(nodes, n, level_in, first, cnt, levels, nodes + 32 * (level_off(n, level_in) + first), sm, blockDim.y);
@@ -202,7 +210,8 @@ int merkle_leaves_dev(stark_ctx *ctx, const u32 *vals, size_t n, u32 width, size
                       u8 *out) {
   if (n == 0) return STARK_OK;
   if (width == 1)
-    LAUNCH_PDL(ctx, "leaf_hash", 36ull * n, k_leaf_hash1, (u32)((n + 2 * HASH_NT - 1) / (2 * HASH_NT)), HASH_NT, vals, n, out);
+    LAUNCH_PDL(ctx, "leaf_hash", 36ull * n, k_leaf_hash1, (u32)((n + 2 * HASH_NT - 1) / (2 * HASH_NT)), HASH_NT, vals, n, out,
+               (size_t)0, (size_t)0);
   else
     LAUNCH_PDL(ctx, "leaf_hash_w", (4ull * width + 32) * n, k_leaf_hashw2, (u32)((n + 2 * HASH_NT - 1) / (2 * HASH_NT)), HASH_NT,
                vals, n, width, row_stride, col_stride, out);
@@ -211,11 +220,20 @@ int merkle_leaves_dev(stark_ctx *ctx, const u32 *vals, size_t n, u32 width, size
 
 // nodes[0 .. n) already holds the leaves; fill the upper levels.  tr (optional): transcript round on the root.
 int merkle_climb_dev(stark_ctx *ctx, u8 *nodes, size_t n, const TranscriptArgs *tr, const MgExchange *mx) {
+  return merkle_climb_batch_dev(ctx, nodes, n, 1, 0, tr, mx);
+}
+// `batch` equally sized trees, tree b at nodes + b * tree_stride bytes: every level of all of them in one launch, and ONE
+// climb launch whose grid covers all trees -- the latency-bound top levels of the trees overlap instead of queueing
+int merkle_climb_batch_dev(stark_ctx *ctx, u8 *nodes, size_t n, u32 batch, size_t tree_stride, const TranscriptArgs *tr,
+                           const MgExchange *mx) {
   const TranscriptArgs none = {nullptr, nullptr, 0, nullptr, nullptr};
   MgExchange X;
   memset(&X, 0, sizeof X);
   if (mx) X = *mx;
   if (X.world > 1 && n < 2) return stark_fail(ctx, STARK_ERR_ARG, "a sharded tree needs at least two leaves per rank");
+  if (batch == 0) return STARK_OK;
+  if (batch > (u32)CLIMB_TICKETS || (batch > 1 && (tr || mx)))
+    return stark_fail(ctx, STARK_ERR_ARG, "unsupported tree batch");
   u32 level = 0;
   size_t m = n;
   // throughput-bound levels: one launch each.  A level of 2^17 parents is already half latency (12 us against 6 us for the
@@ -223,8 +241,8 @@ int merkle_climb_dev(stark_ctx *ctx, u8 *nodes, size_t n, const TranscriptArgs *
   const size_t climb_from = (size_t)1 << ctx->climb_log;   // STARK_CLIMB_LOG, read once at context creation, clamped to 11..18
   while (m > climb_from) {
     const size_t half = m >> 1;
-    LAUNCH_PDL(ctx, "merkle_level", 96ull * half, k_merkle_level, (u32)((half + 2 * HASH_NT - 1) / (2 * HASH_NT)), HASH_NT,
-               (const u8 *)(nodes + 32 * (2 * n - 2 * m)), nodes + 32 * (2 * n - 2 * half), half);
+    LAUNCH_PDL(ctx, "merkle_level", 96ull * half * batch, k_merkle_level, dim3((u32)((half + 2 * HASH_NT - 1) / (2 * HASH_NT)), batch),
+               HASH_NT, (const u8 *)(nodes + 32 * (2 * n - 2 * m)), nodes + 32 * (2 * n - 2 * half), half, tree_stride);
     m = half;
     level++;
   }
@@ -234,13 +252,13 @@ int merkle_climb_dev(stark_ctx *ctx, u8 *nodes, size_t n, const TranscriptArgs *
     // at most 256 chunks (their roots are climbed by the last CTA): 1024-node chunks (10 levels) above 2^17 nodes
     const u32 chunk = m > ((size_t)1 << 17) ? 1024u : 512u, chunk_levels = chunk == 1024u ? 10u : 9u;
     const size_t ctas = m / chunk;
-    LAUNCH_PDL(ctx, "merkle_climb", 96ull * (m - 1), k_merkle_climb<256>, (u32)ctas, 256, nodes, n, level, chunk, chunk_levels,
-               tr ? *tr : none, ctx->climb_counter, X);
+    LAUNCH_PDL(ctx, "merkle_climb", 96ull * (m - 1) * batch, k_merkle_climb<256>, dim3((u32)ctas, batch), 256, nodes, n, level, chunk,
+               chunk_levels, tr ? *tr : none, ctx->climb_counter, X, tree_stride);
   } else if (m > 1) {
     u32 levels = 0;
     for (size_t c = m; c > 1; c >>= 1) levels++;
-    LAUNCH_PDL(ctx, "merkle_top", 96ull * (m - 1), k_merkle_climb<512>, 1u, 512, nodes, n, level, (u32)m, levels,
-               tr ? *tr : none, (u32 *)nullptr, X);
+    LAUNCH_PDL(ctx, "merkle_top", 96ull * (m - 1) * batch, k_merkle_climb<512>, dim3(1u, batch), 512, nodes, n, level, (u32)m, levels,
+               tr ? *tr : none, (u32 *)nullptr, X, tree_stride);
   }
   if (n == 1 && tr) LAUNCH(ctx, "transcript", 0, k_transcript_only<<<1, 32, 0, ctx->stream>>>(nodes, *tr));
   return STARK_OK;
@@ -340,6 +358,17 @@ int merkle_build_from_dev_values(stark_ctx *ctx, const u32 *vals, size_t n, u32 
   }
   *out = t;
   return STARK_OK;
+}
+
+// `batch` trees over the columns of a column-major matrix (tree b over vals[b * val_stride ..], one value per leaf, the
+// rule of fri.rs:118-121), tree b at nodes + b * tree_stride bytes ((2n - 1) * 32 bytes each, rounded up by the caller)
+int merkle_build_batch_dev(stark_ctx *ctx, const u32 *vals, size_t n, u32 batch, size_t val_stride, u8 *nodes,
+                           size_t tree_stride) {
+  if (batch == 0) return STARK_OK;
+  ST_TRY(merkle_check_n(ctx, n));
+  LAUNCH_PDL(ctx, "leaf_hash", 36ull * n * batch, k_leaf_hash1, dim3((u32)((n + 2 * HASH_NT - 1) / (2 * HASH_NT)), batch), HASH_NT,
+             vals, n, nodes, val_stride, tree_stride);
+  return merkle_climb_batch_dev(ctx, nodes, n, batch, tree_stride, nullptr, nullptr);
 }
 
 extern "C" {

@@ -24,6 +24,11 @@ int merkle_leaves_dev(stark_ctx *ctx, const u32 *vals, size_t n, u32 width, size
 struct MgExchange;
 int merkle_climb_dev(stark_ctx *ctx, u8 *nodes, size_t n, const TranscriptArgs *tr = nullptr, const MgExchange *mx = nullptr);
 int merkle_mg_top_dev(stark_ctx *ctx, const TranscriptArgs *tr, const MgExchange *mx);
+constexpr int CLIMB_TICKETS = 64;   // trees per batched climb launch (one last-CTA ticket each)
+int merkle_climb_batch_dev(stark_ctx *ctx, u8 *nodes, size_t n, u32 batch, size_t tree_stride, const TranscriptArgs *tr,
+                           const MgExchange *mx);
+int merkle_build_batch_dev(stark_ctx *ctx, const u32 *vals, size_t n, u32 batch, size_t val_stride, u8 *nodes,
+                           size_t tree_stride);
 int merkle_build_from_dev_values(stark_ctx *ctx, const u32 *vals, size_t n, u32 width, size_t row_stride,
                                  size_t col_stride, stark_tree **out, const TranscriptArgs *tr = nullptr);
 int merkle_open_dev(stark_ctx *ctx, const u8 *nodes, size_t n, const u64 *idx_dev, u32 n_idx, u8 *out_dev);
@@ -33,6 +38,8 @@ int upload_u64(stark_ctx *ctx, const uint64_t *host, size_t n, u32 *dst);     //
 int upload_flag_reset(stark_ctx *ctx);                                         // before a group of nosync uploads
 int upload_u64_nosync(stark_ctx *ctx, const uint64_t *host, size_t n, u32 *dst);  // no host round trip ...
 int upload_u64_check(stark_ctx *ctx);                                          // ... flag read after the final sync
+int narrow_dev(stark_ctx *ctx, const uint64_t *staging_dev, size_t n, u32 *dst);   // values already on the device
+int upload_flag_fetch(stark_ctx *ctx);                                             // queue the flag's D2H copy
 int download_u64(stark_ctx *ctx, const u32 *src, size_t n, uint64_t *host);   // widen + D2H (synchronises)
 int trace_to_columns_dev(stark_ctx *ctx, const void *rows_i128, size_t n_rows, u32 n_cols, u32 *cols);
 int lde_dev(stark_ctx *ctx, const u32 *cols, u32 n_cols, u32 log_n, u32 log_blowup, u32 offset, u32 *out);

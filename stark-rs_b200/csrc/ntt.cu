@@ -148,7 +148,10 @@ void ntt_destroy(stark_ctx *ctx) {
   cudaFree(ctx->tw_sh[0]), cudaFree(ctx->tw_sh[1]);
   cudaFree(ctx->tw_in_sh[0]), cudaFree(ctx->tw_in_sh[1]);
   cudaFree(ctx->otw_sh[0]), cudaFree(ctx->otw_sh[1]), cudaFree(ctx->row_sh[0]), cudaFree(ctx->row_sh[1]);
-  for (int i = 0; i < 8; i++) cudaFree(ctx->geo[i].lo);
+  for (int i = 0; i < 8; i++) {
+    cudaFree(ctx->geo[i].lo);
+    if (ctx->geo[i].ready) cudaEventDestroy(ctx->geo[i].ready);
+  }
 }
 
 // small LRU of geometric tables keyed by (g, c); max_index = largest exponent that will be looked up
@@ -160,14 +163,16 @@ int geo_tables(stark_ctx *ctx, u32 g, u32 c, u64 max_index, GeoTables *out) {
     if (e.lo && e.g == g && e.c == c && e.hi_len >= hi_len) {
       e.stamp = ++ctx->geo_stamp;
       out->lo = e.lo, out->hi = e.hi;
+      // the tables may have been filled on another stream of this context (column pipeline, fri.cu)
+      if (e.ready) CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, e.ready, 0));
       return STARK_OK;
     }
     if (ctx->geo[i].stamp < ctx->geo[victim].stamp) victim = i;
   }
   GeoCacheEntry &e = ctx->geo[victim];
   if (e.lo) {
-    // the old tables may still be in use by queued kernels: order the free after them
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    // the old tables may still be in use by queued kernels (on any stream of the context): order the free after them
+    CU_TRY(ctx, cudaDeviceSynchronize());
     cudaFree(e.lo);
     e.lo = nullptr;
   }
@@ -177,6 +182,8 @@ int geo_tables(stark_ctx *ctx, u32 g, u32 c, u64 max_index, GeoTables *out) {
   e.g = g, e.c = c, e.hi_len = alloc_hi, e.stamp = ++ctx->geo_stamp;
   LAUNCH(ctx, "geo_tables", 0, k_geo_tables<<<(alloc_hi + 4095 + 255) / 256, 256, 0, ctx->stream>>>(
                                    e.lo, e.hi, ff::to_mont(g), ff::to_mont(c), alloc_hi));
+  if (!e.ready) CU_TRY(ctx, cudaEventCreateWithFlags(&e.ready, cudaEventDisableTiming));
+  CU_TRY(ctx, cudaEventRecord(e.ready, ctx->stream));
   out->lo = e.lo, out->hi = e.hi;
   return STARK_OK;
 }

@@ -158,6 +158,17 @@ struct Polynomial {
     out.resize(n);
     return Polynomial(wrap(out, l.field), l.field);
   }
+  // exp.rs:6-33: square and multiply over mul (each product one stark_poly_mul); exp 0 -> [1], zero base -> []
+  static Polynomial exp(const Polynomial &base, uint64_t e) {
+    if (e == 0) return Polynomial({base.field.one()}, base.field);
+    if (base.is_zero()) return Polynomial({}, base.field);
+    Polynomial result({base.field.one()}, base.field), bpower = base;
+    for (; e; e >>= 1) {
+      if (e & 1) result = mul(result, bpower);
+      bpower = mul(bpower, bpower);
+    }
+    return result;
+  }
   FieldElement eval(const FieldElement &x) const {  // eval.rs:6-14
     FieldElement xi = x.field.one(), val = x.field.zero();
     for (const auto &c : coeffs) val = val + c * xi, xi = xi * x;
@@ -303,6 +314,16 @@ struct MerkleTree {  // merkle.rs:4-97; all levels live on the device
     out.resize(n);
     return out;
   }
+  // MerkleTree::open for many leaves in one device gather (stark_merkle_open_batch)
+  std::vector<std::vector<Hash>> open_batch(const std::vector<size_t> &indices) const {
+    const size_t depth = stark_merkle_num_levels(h) - 1;
+    std::vector<uint64_t> idx(indices.begin(), indices.end());
+    std::vector<Hash> flat(depth * idx.size() + 1);
+    check(stark_merkle_open_batch(h, idx.data(), idx.size(), flat[0].b));
+    std::vector<std::vector<Hash>> out;
+    for (size_t q = 0; q < idx.size(); q++) out.emplace_back(flat.begin() + q * depth, flat.begin() + (q + 1) * depth);
+    return out;
+  }
   static bool verify(const Hash &leaf, size_t index, const std::vector<Hash> &proof, const Hash &root) {
     Hash cur = leaf;
     for (const Hash &s : proof) {
@@ -398,6 +419,61 @@ struct Fri {
     std::vector<uint64_t> out(v.size() / 2);
     check(stark_fri_fold(ctx(), v.data(), v.size(), alpha.value, off.value, om.value, out.data()));
     return wrap(out, field);
+  }
+  // fri.rs:105-156: the round loop runs on the device (stark_fri_commit); roots and the last codeword are pushed /
+  // absorbed in the reference's order and every intermediate codeword is returned
+  std::vector<std::vector<FieldElement>> commit(const std::vector<FieldElement> &initial_codeword, ProofStream &proof_stream,
+                                                FiatShamir &fiat_shamir) const {
+    const auto v = raw(initial_codeword);
+    stark_fri_state *st = nullptr;
+    check(stark_fri_commit(ctx(), v.data(), v.size(), offset.value, omega.value, (uint32_t)expansion_factor,
+                           (uint32_t)num_colinearity_tests, fiat_shamir.transcript.data(), fiat_shamir.transcript.size(), &st));
+    const size_t R = stark_fri_rounds(st);
+    std::vector<uint8_t> roots(32 * (R ? R : 1));
+    check(stark_fri_roots(st, roots.data()));
+    for (size_t r = 0; r < R; r++) {
+      ProofObject o{ProofObject::MerkleRoot, {}, {Hash()}};
+      memcpy(o.hashes[0].b, &roots[32 * r], 32);
+      proof_stream.push(o);                     // fri.rs:129-131
+      fiat_shamir.absorb(&roots[32 * r], 32);
+    }
+    std::vector<std::vector<FieldElement>> codewords;
+    for (size_t r = 0; r < (R ? R : 1); r++) {
+      size_t len = 0;
+      check(stark_fri_codeword_len(st, (uint32_t)r, &len));
+      std::vector<uint64_t> cw(len);
+      check(stark_fri_codeword(st, (uint32_t)r, cw.data()));
+      codewords.push_back(wrap(cw, field));
+    }
+    proof_stream.push(ProofObject{ProofObject::Elements, raw(codewords.back()), {}});   // fri.rs:151
+    stark_fri_free(st);
+    return codewords;
+  }
+  // fri.rs:176-213 (same asserts, same text)
+  std::vector<size_t> sample_indices(const std::vector<uint8_t> &seed, size_t size, size_t reduced_size, size_t number) const {
+    std::vector<uint64_t> out(number ? number : 1);
+    check(stark_fri_sample_indices(seed.data(), seed.size(), size, reduced_size, number, out.data()));
+    return std::vector<size_t>(out.begin(), out.begin() + number);
+  }
+  // fri.rs:215-248: triples, then the authentication paths (one batched device gather per tree)
+  std::vector<size_t> query(const std::vector<FieldElement> &current_codeword, const std::vector<FieldElement> &next_codeword,
+                            const std::vector<size_t> &c_indices, ProofStream &proof_stream, const MerkleTree &current_tree,
+                            const MerkleTree &next_tree) const {
+    const size_t half = current_codeword.size() / 2;
+    std::vector<size_t> a_indices = c_indices, b_indices;
+    for (size_t i : a_indices) b_indices.push_back(i + half);
+    for (size_t s = 0; s < num_colinearity_tests; s++)
+      proof_stream.push(ProofObject{ProofObject::Elements,
+                                    {current_codeword[a_indices[s]].value, current_codeword[b_indices[s]].value, next_codeword[c_indices[s]].value},
+                                    {}});
+    const auto pa = current_tree.open_batch(a_indices), pb = current_tree.open_batch(b_indices), pc = next_tree.open_batch(c_indices);
+    for (size_t s = 0; s < num_colinearity_tests; s++) {
+      proof_stream.push(ProofObject{ProofObject::MerklePath, {}, pa[s]});
+      proof_stream.push(ProofObject{ProofObject::MerklePath, {}, pb[s]});
+      proof_stream.push(ProofObject{ProofObject::MerklePath, {}, pc[s]});
+    }
+    a_indices.insert(a_indices.end(), b_indices.begin(), b_indices.end());
+    return a_indices;
   }
   // fri.rs:250-311: returns top_level_indices; proof_stream receives the objects, fiat_shamir the roots
   std::vector<size_t> prove(const std::vector<FieldElement> &initial_codeword, FiatShamir &fiat_shamir,

@@ -6,6 +6,7 @@
 #[repr(C)] pub struct StarkBuf { _private: [u8; 0] }
 #[repr(C)] pub struct StarkTree { _private: [u8; 0] }
 #[repr(C)] pub struct StarkFriState { _private: [u8; 0] }
+#[repr(C)] pub struct StarkMgpu { _private: [u8; 0] }
 
 extern "C" {
     pub fn stark_ctx_create(device: i32, out: *mut *mut StarkCtx) -> i32;
@@ -88,6 +89,23 @@ extern "C" {
     pub fn stark_fri_prove(ctx: *mut StarkCtx, codeword: *const u64, n: usize, domain_length: usize, offset: u64, omega: u64, expansion_factor: u32, num_colinearity_tests: u32, transcript: *const u8, transcript_len: usize, proof: *mut u8, proof_cap: usize, proof_len: *mut usize, top_indices: *mut u64) -> i32;
     pub fn stark_fri_prove_dev(ctx: *mut StarkCtx, codeword: *const StarkBuf, n: usize, domain_length: usize, offset: u64, omega: u64, expansion_factor: u32, num_colinearity_tests: u32, transcript: *const u8, transcript_len: usize, proof: *mut u8, proof_cap: usize, proof_len: *mut usize, top_indices: *mut u64) -> i32;
     pub fn stark_prove_trace(ctx: *mut StarkCtx, cols: *const u64, n_cols: u32, log_n: u32, log_blowup: u32, offset: u64, num_colinearity_tests: u32, column_roots: *mut u8, proof: *mut u8, proof_cap: usize, proof_len: *mut usize) -> i32;
+    // groups of GPUs (include/stark_b200.h): one StarkMgpu per rank; `ranks` = the handles this call drives
+    pub fn stark_mgpu_unique_id(id: *mut u8) -> i32;
+    pub fn stark_mgpu_init(ctx: *mut StarkCtx, id: *const u8, rank: i32, world: i32, max_codeword: usize, out: *mut *mut StarkMgpu) -> i32;
+    pub fn stark_mgpu_create_local(ctxs: *const *mut StarkCtx, world: i32, max_codeword: usize, out: *mut *mut StarkMgpu) -> i32;
+    pub fn stark_mgpu_destroy(m: *mut StarkMgpu);
+    pub fn stark_mgpu_rank(m: *const StarkMgpu) -> i32;
+    pub fn stark_mgpu_world(m: *const StarkMgpu) -> i32;
+    pub fn stark_mgpu_bytes_sent(m: *const StarkMgpu) -> u64;
+    pub fn stark_mgpu_set_shard_log(m: *mut StarkMgpu, log_n: u32) -> i32;
+    pub fn stark_mgpu_barrier(m: *mut StarkMgpu) -> i32;
+    pub fn stark_mgpu_owned_columns(m: *const StarkMgpu, n_cols: u32, out: *mut u32) -> u32;
+    pub fn stark_mgpu_prove_trace(ranks: *const *mut StarkMgpu, n_here: i32, cols: *const u64, n_cols: u32, log_n: u32, log_blowup: u32, offset: u64, num_colinearity_tests: u32, column_roots: *const *mut u8, proofs: *const *mut u8, proof_cap: usize, proof_len: *mut usize) -> i32;
+    pub fn stark_mgpu_prove_trace_dev(ranks: *const *mut StarkMgpu, n_here: i32, my_cols: *const *const StarkBuf, n_cols: u32, log_n: u32, log_blowup: u32, offset: u64, num_colinearity_tests: u32, column_roots: *const *mut u8, proofs: *const *mut u8, proof_cap: usize, proof_len: *mut usize) -> i32;
+    pub fn stark_mgpu_fri_prove_dev(ranks: *const *mut StarkMgpu, n_here: i32, codewords: *const *const StarkBuf, n: usize, domain_length: usize, offset: u64, omega: u64, expansion_factor: u32, num_colinearity_tests: u32, transcript: *const u8, transcript_len: usize, proofs: *const *mut u8, proof_cap: usize, proof_len: *mut usize, top_indices: *const *mut u64) -> i32;
+    pub fn stark_mgpu_fold_commit_round(ranks: *const *mut StarkMgpu, n_here: i32, codewords: *const *const StarkBuf, n: usize, offset: u64, omega: u64, roots: *const *mut u8, alpha_raw: *mut u64, folded: *mut *mut StarkBuf) -> i32;
+    pub fn stark_mgpu_lde_commit(ranks: *const *mut StarkMgpu, n_here: i32, cols: *const u64, n_groups: u32, group_width: u32, log_n: u32, log_blowup: u32, offset: u64, group_roots: *const *mut u8, commitments: *const *mut u8) -> i32;
+    pub fn stark_mgpu_lde_commit_dev(ranks: *const *mut StarkMgpu, n_here: i32, owned_groups: *const *const StarkBuf, n_groups: u32, group_width: u32, log_n: u32, log_blowup: u32, offset: u64, group_roots: *const *mut u8, commitments: *const *mut u8) -> i32;
     pub fn stark_prove_trace_dev(ctx: *mut StarkCtx, cols: *const StarkBuf, n_cols: u32, log_n: u32, log_blowup: u32, offset: u64, num_colinearity_tests: u32, column_roots: *mut u8, proof: *mut u8, proof_cap: usize, proof_len: *mut usize) -> i32;
 }
 

@@ -29,6 +29,63 @@ impl Fri {
         ffi::check(unsafe { ffi::stark_fri_fold(ffi::ctx(), vals.as_ptr(), vals.len(), alpha.value, offset.value, omega.value, out.as_mut_ptr()) });
         out.into_iter().map(|v| self.field.new_element(v)).collect()
     }
+    /// fri.rs:105-156: the whole round loop runs on the device (stark_fri_commit: leaf hashes, trees, transcript, folds);
+    /// the roots and the last codeword are pushed / absorbed here in the reference's order and every intermediate codeword
+    /// is returned, like the reference does.
+    pub fn commit(&self, initial_codeword: Vec<FieldElement>, proof_stream: &mut ProofStream, fiat_shamir: &mut FiatShamir) -> Vec<Vec<FieldElement>> {
+        let vals: Vec<u64> = initial_codeword.iter().map(|e| e.value).collect();
+        let mut st = std::ptr::null_mut();
+        ffi::check(unsafe {
+            ffi::stark_fri_commit(ffi::ctx(), vals.as_ptr(), vals.len(), self.offset.value, self.omega.value, self.expansion_factor as u32,
+                                  self.num_colinearity_tests as u32, fiat_shamir.transcript.as_ptr(), fiat_shamir.transcript.len(), &mut st)
+        });
+        let rounds = unsafe { ffi::stark_fri_rounds(st) } as usize;
+        let mut roots = vec![0u8; 32 * rounds.max(1)];
+        ffi::check(unsafe { ffi::stark_fri_roots(st, roots.as_mut_ptr()) });
+        for r in 0..rounds {
+            let root = crate::hash::Hash(roots[32 * r..32 * r + 32].try_into().unwrap());
+            proof_stream.push(ProofObject::MerkleRoot(root));     // fri.rs:129-131
+            fiat_shamir.absorb(&root.0);
+        }
+        let mut codewords = Vec::new();
+        for r in 0..rounds.max(1) {
+            let mut len = 0usize;
+            ffi::check(unsafe { ffi::stark_fri_codeword_len(st, r as u32, &mut len) });
+            let mut cw = vec![0u64; len];
+            ffi::check(unsafe { ffi::stark_fri_codeword(st, r as u32, cw.as_mut_ptr()) });
+            codewords.push(cw.into_iter().map(|v| self.field.new_element(v)).collect::<Vec<_>>());
+        }
+        proof_stream.push(ProofObject::FieldElements(codewords.last().unwrap().clone()));   // fri.rs:151
+        unsafe { ffi::stark_fri_free(st) };
+        codewords
+    }
+    /// fri.rs:176-213 (same asserts, same text)
+    pub fn sample_indices(&self, seed: &[u8], size: usize, reduced_size: usize, number: usize) -> Vec<usize> {
+        let mut out = vec![0u64; number.max(1)];
+        ffi::check(unsafe { ffi::stark_fri_sample_indices(seed.as_ptr(), seed.len(), size, reduced_size, number, out.as_mut_ptr()) });
+        out.truncate(number);
+        out.into_iter().map(|i| i as usize).collect()
+    }
+    /// fri.rs:215-248: reveal the triples and their authentication paths (the trees live on the device: one batched
+    /// gather per tree through MerkleTree::open_batch)
+    pub fn query(&self, current_codeword: &[FieldElement], next_codeword: &[FieldElement], c_indices: &[usize], proof_stream: &mut ProofStream,
+                 current_tree: &crate::merkle::MerkleTree, next_tree: &crate::merkle::MerkleTree) -> Vec<usize> {
+        let half = current_codeword.len() / 2;
+        let a_indices: Vec<usize> = c_indices.to_vec();
+        let b_indices: Vec<usize> = a_indices.iter().map(|&i| i + half).collect();
+        for s in 0..self.num_colinearity_tests {
+            proof_stream.push(ProofObject::FieldElements(vec![current_codeword[a_indices[s]], current_codeword[b_indices[s]], next_codeword[c_indices[s]]]));
+        }
+        let (pa, pb, pc) = (current_tree.open_batch(&a_indices), current_tree.open_batch(&b_indices), next_tree.open_batch(c_indices));
+        for s in 0..self.num_colinearity_tests {
+            proof_stream.push(ProofObject::MerklePath(pa[s].clone()));
+            proof_stream.push(ProofObject::MerklePath(pb[s].clone()));
+            proof_stream.push(ProofObject::MerklePath(pc[s].clone()));
+        }
+        let mut all = a_indices;
+        all.extend(b_indices);
+        all
+    }
     /// fri.rs:250-311.  The GPU returns ProofStream::serialize's bytes; they are parsed back into `proof_stream`
     /// and the roots are absorbed into `fiat_shamir`, so both end in the state the reference leaves them in.
     pub fn prove(&self, initial_codeword: Vec<FieldElement>, fiat_shamir: &mut FiatShamir, proof_stream: &mut ProofStream) -> Vec<usize> {

@@ -34,6 +34,14 @@ impl MerkleTree {
         out.truncate(n);
         out
     }
+    /// MerkleTree::open for many leaves in one device gather (stark_merkle_open_batch); "Index out of bounds" as open()
+    pub fn open_batch(&self, indices: &[usize]) -> Vec<Vec<Hash>> {
+        let depth = (unsafe { ffi::stark_merkle_num_levels(self.handle) } as usize).saturating_sub(1);
+        let idx: Vec<u64> = indices.iter().map(|&i| i as u64).collect();
+        let mut out = vec![Hash([0; 32]); (depth * idx.len()).max(1)];
+        ffi::check(unsafe { ffi::stark_merkle_open_batch(self.handle, idx.as_ptr(), idx.len(), out.as_mut_ptr() as *mut u8) });
+        (0..idx.len()).map(|q| out[q * depth..(q + 1) * depth].to_vec()).collect()
+    }
     pub fn verify(leaf: &Hash, index: usize, proof: &[Hash], root: &Hash) -> bool {
         let (mut cur, mut idx) = (*leaf, index);
         for sib in proof {

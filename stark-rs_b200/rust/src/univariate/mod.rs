@@ -52,6 +52,19 @@ impl Polynomial {
         out.truncate(n);
         Self::from_raw(out, l.field)
     }
+    /// exp.rs:6-33: square and multiply over Polynomial::mul (every product is one stark_poly_mul on the device); the same
+    /// shape rules: exp 0 -> [1], zero base -> []
+    pub fn exp(base: &Polynomial, exp: u64) -> Polynomial {
+        if exp == 0 { return Polynomial::new(vec![base.field.one()], base.field); }
+        if base.is_zero() { return Polynomial::new(vec![], base.field); }
+        let (mut e, mut result, mut bpower) = (exp, Polynomial::new(vec![base.field.one()], base.field), base.clone());
+        while e != 0 {
+            if e & 1 == 1 { result = Self::mul(&result, &bpower); }
+            bpower = Self::mul(&bpower, &bpower);
+            e >>= 1;
+        }
+        result
+    }
     pub fn eval(&self, x: &FieldElement) -> FieldElement { self.coeffs.iter().rev().fold(x.field.zero(), |acc, c| acc * *x + *c) }
     /// (offset, log_n) if `domain` is offset * w_N^i in natural order
     fn as_coset(field: &FiniteField, domain: &[FieldElement]) -> Option<(u64, u32)> {
@@ -120,4 +133,5 @@ impl std::ops::Add<&Polynomial> for &Polynomial { type Output = Polynomial; fn a
 impl std::ops::Sub<&Polynomial> for &Polynomial { type Output = Polynomial; fn sub(self, r: &Polynomial) -> Polynomial { Polynomial::sub(self, r) } }
 impl std::ops::Mul<&Polynomial> for &Polynomial { type Output = Polynomial; fn mul(self, r: &Polynomial) -> Polynomial { Polynomial::mul(self, r) } }
 impl std::ops::Div<&Polynomial> for &Polynomial { type Output = (Polynomial, Polynomial); fn div(self, r: &Polynomial) -> (Polynomial, Polynomial) { Polynomial::div(self, r) } }
+impl std::ops::BitXor<u64> for &Polynomial { type Output = Polynomial; fn bitxor(self, e: u64) -> Polynomial { Polynomial::exp(self, e) } }
 impl std::ops::Rem<&Polynomial> for &Polynomial { type Output = Polynomial; fn rem(self, r: &Polynomial) -> Polynomial { Polynomial::modulo(self, r) } }

@@ -38,6 +38,24 @@ static void fri_case(size_t n, uint64_t off, size_t ef, size_t nq, std::vector<u
   EXPECT(fs2.transcript == fs.transcript && ps.objects.size() < n_obj);
   EXPECT(points.size() == 2 * nq);
   for (auto &pt : points) EXPECT(codeword[pt.first] == pt.second);
+  // Fri::prove re-assembled from its public pieces exactly as fri.rs:250-311 composes them -- commit, the seed challenge,
+  // sample_indices, one query per round on trees rebuilt from the codewords -- must serialize to the same bytes
+  {
+    ProofStream ps2;
+    FiatShamir fsc;
+    auto codewords = fri.commit(codeword, ps2, fsc);
+    EXPECT(codewords.size() == (fri.num_rounds() ? fri.num_rounds() : 1) && fsc.transcript == fs.transcript);
+    const Hash seed = Hash::from_u64(fsc.challenge(field).value);                    // fri.rs:272
+    const size_t sample_size = codewords.size() > 1 ? codewords[1].size() : codewords[0].size();
+    auto idx = fri.sample_indices(std::vector<uint8_t>(seed.b, seed.b + 32), sample_size, codewords.back().size(), nq);
+    EXPECT(idx == top);
+    for (size_t i = 0; i + 1 < codewords.size(); i++) {
+      for (auto &x : idx) x %= codewords[i].size() / 2;                              // fri.rs:282-285
+      MerkleTree t0(Hash::leaves(raw(codewords[i]))), t1(Hash::leaves(raw(codewords[i + 1])));
+      fri.query(codewords[i], codewords[i + 1], idx, ps2, t0, t1);
+    }
+    EXPECT(ps2.serialize() == bytes);
+  }
   // a tampered stream is rejected (fri.rs has no negative test; the oracle's verdict is the reference here)
   ProofStream bad = ProofStream::deserialize(bytes);
   bad.objects[fri.num_rounds()].values[0] ^= 1;
@@ -65,6 +83,10 @@ int main() {
   auto ip = Polynomial::interpolate_domain(wrap({1, 2, 3}, field), wrap({1, 4, 9}, field));
   EXPECT(raw(ip.coeffs) == (std::vector<uint64_t>{0, 0, 1}));
   EXPECT(raw(Polynomial(wrap({2, 3}, field), field).scale(field.new_element(5)).coeffs) == (std::vector<uint64_t>{2, 15}));
+  // exp.rs:35-80: (1 + x)^3, exponent 0, zero base
+  EXPECT(raw(Polynomial::exp(Polynomial(wrap({1, 1}, field), field), 3).coeffs) == (std::vector<uint64_t>{1, 3, 3, 1}));
+  EXPECT(raw(Polynomial::exp(a, 0).coeffs) == (std::vector<uint64_t>{1}));
+  EXPECT(Polynomial::exp(Polynomial(wrap({0, 0}, field), field), 5).coeffs.empty());
   // div.rs:83-123
   auto qr = Polynomial::div(Polynomial(wrap({2, 3, 1}, field), field), Polynomial(wrap({1, 1}, field), field));
   EXPECT(raw(qr.first.coeffs) == (std::vector<uint64_t>{2, 1}));

@@ -185,3 +185,55 @@ def test_trace_columns(oracle):
     fib = [[int(v)] for v in oracle.trace_fibonacci(64)]                    # Trace::fibonacci(64).get_col(0)
     assert np.array_equal(oracle.trace_columns(fib)[0], oracle.trace_fibonacci(64))
 
+
+
+def _emitter_shaped_json(O):
+    """what tools/emit_golden.rs prints, computed with the oracle instead of the reference crate"""
+    def fri_case(n, off, ef, nq, coeffs):
+        w = O.ff_prim_nth_root(n)
+        dom = [O.ff_mul(off, O.ff_exp(w, i)) for i in range(n)]
+        cw = [int(x) for x in O.poly_eval_domain(coeffs, dom)]
+        r = O.fri_prove(cw, w, off, ef, nq)
+        return {"n": n, "offset": off, "ef": ef, "nq": nq, "coeffs": coeffs, "codeword": cw, "bytes": len(r["proof"]),
+                "top": r["top_indices"], "verify": True, "proof_hex": r["proof"].hex()}
+    msgs = [b"hello", b"world", b"", b"\0", bytes([7] * 32), bytes([9] * 33)]
+    ref = {"hash_from_bytes": {m.hex(): O.hash_from_bytes(m).hex() for m in msgs},
+           "hash_from_u64_0": O.hash_from_u64(0).hex(), "hash_from_field_elements_1": O.hash_from_field_elements([1]).hex(),
+           "hash_from_field_elements_8": O.hash_from_field_elements([1, 2, 3, 4, 5, 6, 7, 998244352]).hex(),
+           "combine_zero_zero": O.hash_combine(bytes(32), bytes(32)).hex(),
+           "challenge_empty": O.fs_challenge(b""), "challenge_stark_rs": O.fs_challenge(b"stark-rs"),
+           "roots_of_unity": {str(k): O.ff_prim_nth_root(1 << k) for k in (3, 16, 20, 22, 23)}}
+    for n in (4, 8, 16):
+        leaves = np.stack([np.frombuffer(O.hash_from_bytes(bytes([i])), dtype=np.uint8) for i in range(n)])
+        ref["merkle_root_%d" % n] = O.merkle_commit(leaves).hex()
+        ref["merkle_open_%d_%d" % (n, n - 3)] = [bytes(h).hex() for h in O.merkle_open(leaves, n - 3)]
+    cw = [(i * 1234567 + 89) % 998244353 for i in range(16)]
+    a = 15764728482632548394
+    ref["fold_16"] = {"codeword": cw, "alpha_raw": a, "folded": [int(x) for x in O.fri_fold(cw, a, 3, O.ff_prim_nth_root(16))]}
+    ref["sample_indices_seed_abc"] = [int(x) for x in O.fri_sample_indices(b"abc", 64, 8, 5)]
+    ref["fri_proofs"] = [fri_case(32, 3, 4, 2, [5]), fri_case(64, 7, 4, 3, [5, 3]), fri_case(128, 13, 4, 4, [1, 3, 2]),
+                         fri_case(256, 17, 8, 5, [1, 2, 5, 3, 7, 4, 1, 2])]
+    return ref
+
+
+def test_reference_golden_checker(oracle):
+    """tools/check_golden.py (the checker for the output of tools/emit_golden.rs, which only someone with cargo can run):
+    it accepts an emitter-shaped JSON built from the oracle, catches a flipped byte, agrees with the survey vectors -- and
+    if a reference-emitted file has been committed (tests/golden/reference_emitted.json) the oracle must reproduce it."""
+    import importlib.util
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("check_golden", os.path.join(root, "tools", "check_golden.py"))
+    C = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(C)
+    ref = _emitter_shaped_json(oracle)
+    assert C.check(ref, oracle, verbose=False) == [] and C.check_survey(ref) == []
+    broken = json.loads(json.dumps(ref))
+    broken["fri_proofs"][2]["proof_hex"] = broken["fri_proofs"][2]["proof_hex"][:-2] + "00"
+    broken["combine_zero_zero"] = "00" * 32
+    assert len(C.check(broken, oracle, verbose=False)) == 2
+    emitted = os.path.join(root, "tests", "golden", "reference_emitted.json")
+    if os.path.exists(emitted):
+        real = json.load(open(emitted))
+        assert C.check(real, oracle, verbose=False) == [] and C.check_survey(real) == []

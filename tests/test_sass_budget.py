@@ -41,3 +41,19 @@ def test_ntt_pass_instruction_budgets():
         assert k in seen, "kernel %s not found in the SASS" % k
         t, f, a = seen[k]
         assert t <= mt and f <= mf and a <= ma, "%s: %d instructions, %d FMA slots, %d ALU (budget %d / %d / %d)" % (k, t, f, a, mt, mf, ma)
+
+
+def test_hash_instruction_table_matches_build():
+    """bench.py takes the per-hash instruction counts of the hash kernels from profiles/r2_hash_instr.json (an ncu capture
+    of this round, tools/hash_instr_from_ncu.py).  The file records the static SASS size of each kernel at capture time:
+    if the shipped build has drifted from it (more than 1 %) the dynamic counts are stale and must be re-captured."""
+    import json
+    path = os.path.join(ROOT, "profiles", "r2_hash_instr.json")
+    if not os.path.exists(path) or not os.path.exists(os.path.join(ROOT, "stark-rs_b200", "build", "merkle.o")):
+        pytest.skip("no capture / no objects")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import hash_instr_from_ncu as H
+    now = H.static_counts(os.path.join(ROOT, "stark-rs_b200", "build"))
+    for tag, e in json.load(open(path))["kernels"].items():
+        if e.get("static_sass_instr"):
+            assert abs(now[e["kernel"]] - e["static_sass_instr"]) <= 0.01 * e["static_sass_instr"], (tag, now[e["kernel"]], e["static_sass_instr"])
