@@ -55,6 +55,8 @@ struct stark_ctx {
   int ntt_big;           // STARK_NTT_BIG=1: two-pass plans on 16384-element tiles for 2^20..2^22 (experiment)
   int ntt_l2_persist;    // STARK_NTT_L2_PERSIST=1: mark each pass's destination as L2-persisting (experiment, default off)
   int l2_persist_ready;
+  int colpipe_serial;    // STARK_COLPIPE_SERIAL=1: no column / copy stream (everything on the context's stream; diagnosis)
+  int colpipe_group;     // columns per group when the trace is copied from the host (STARK_COLPIPE_GROUP, default 4)
   int climb_log;         // Merkle levels above 2^climb_log nodes get one launch each, the rest one climb launch (merkle.cu)
   char err[512];
   // optional per-kernel timing (stark_ctx_profile_begin/end): CUDA events around every launch, on ctx->stream

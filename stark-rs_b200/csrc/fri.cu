@@ -1045,7 +1045,8 @@ constexpr int COL_STREAM = 2, COPY_STREAM = 3;
 struct ColumnPipe {
   cudaStream_t main_stream = nullptr;
   bool forked = false;
-  std::vector<u8 *> node_blocks;    // one allocation per group: its trees, tree_stride bytes apart
+  u8 *nodes = nullptr;              // the trees of all committed columns, tree_stride bytes apart
+  size_t trees_reserved = 0;
   std::vector<cudaEvent_t> events;  // copy-done events (host input)
   u64 *staging = nullptr;           // host input: the uint64 trace as copied (column-major), narrowed group by group
   u8 *d_roots = nullptr;            // one root per committed column, in the order committed
@@ -1061,10 +1062,14 @@ static void column_pipe_leave(stark_ctx *ctx, ColumnPipe *cp) {
   if (cp->forked) ctx->stream = cp->main_stream, ctx->climb_counter = ctx->flag + TICKET_MAIN;
 }
 // fork the column (and copy) stream from the context's stream: everything allocated or written so far is visible there
-static int column_pipe_begin(stark_ctx *ctx, ColumnPipe *cp, u32 max_roots) {
+static int column_pipe_begin(stark_ctx *ctx, ColumnPipe *cp, u32 max_roots, size_t N) {
   cp->main_stream = ctx->stream;
-  if (max_roots) ST_TRY(dev_alloc(ctx, (void **)&cp->d_roots, 32 * (size_t)max_roots));
-  if (!ctx->prof_on && side_streams(ctx, 4) == STARK_OK) {
+  if (max_roots) {
+    ST_TRY(dev_alloc(ctx, (void **)&cp->d_roots, 32 * (size_t)max_roots));
+    ST_TRY(dev_alloc(ctx, (void **)&cp->nodes, tree_stride_of(N) * max_roots));
+    cp->trees_reserved = max_roots;
+  }
+  if (!ctx->prof_on && !ctx->colpipe_serial && side_streams(ctx, 4) == STARK_OK) {
     cudaEventRecord(ctx->fork_ev, cp->main_stream);
     cudaStreamWaitEvent(ctx->side[COL_STREAM], ctx->fork_ev, 0);
     cudaStreamWaitEvent(ctx->side[COPY_STREAM], ctx->fork_ev, 0);
@@ -1098,9 +1103,10 @@ static int column_pipe_group(stark_ctx *ctx, ColumnPipe *cp, cudaEvent_t copied,
   for (u32 b0 = 0; do_trees && b0 < cnt; b0 += CLIMB_TICKETS) {
     const u32 nb = cnt - b0 < (u32)CLIMB_TICKETS ? cnt - b0 : (u32)CLIMB_TICKETS;
     const size_t stride = tree_stride_of(N);
-    u8 *nodes = nullptr;
-    ST_TRY(dev_alloc(ctx, (void **)&nodes, stride * nb));
-    cp->node_blocks.push_back(nodes);
+    // the trees of all groups live in ONE block reserved on the context's stream before the fork (column_pipe_begin):
+    // every stream-ordered allocation and free of the pipeline's big buffers happens on the same stream
+    if ((size_t)(cp->n_roots + nb) > cp->trees_reserved) return stark_fail(ctx, STARK_ERR_ARG, "column pipeline: tree block too small");
+    u8 *nodes = cp->nodes + stride * cp->n_roots;
     ST_TRY(merkle_build_batch_dev(ctx, lde + (size_t)(c0 + b0) * N, N, nb, N, nodes, stride));
     CU_TRY(ctx, cudaMemcpy2DAsync(cp->d_roots + 32 * (size_t)cp->n_roots, 32, nodes + 32 * (2 * N - 2), stride, 32, nb,
                                   cudaMemcpyDeviceToDevice, ctx->stream));
@@ -1121,8 +1127,8 @@ static void column_pipe_join(stark_ctx *ctx, ColumnPipe *cp) {
 }
 static void column_pipe_free(stark_ctx *ctx, ColumnPipe *cp) {
   column_pipe_join(ctx, cp);
-  for (u8 *b : cp->node_blocks) dev_free(ctx, b);
-  cp->node_blocks.clear();
+  dev_free(ctx, cp->nodes);
+  cp->nodes = nullptr;
   for (cudaEvent_t e : cp->events) cudaEventDestroy(e);
   cp->events.clear();
   dev_free(ctx, cp->d_roots), dev_free(ctx, cp->staging);
@@ -1149,10 +1155,10 @@ static int prove_trace_pipeline(stark_ctx *ctx, const uint64_t *host_cols, u32 *
     rc = dev_alloc(ctx, (void **)&cp.staging, 8 * n * n_cols);
     if (rc == STARK_OK) rc = upload_flag_reset(ctx);
   }
-  if (rc == STARK_OK) rc = column_pipe_begin(ctx, &cp, n_cols);
+  if (rc == STARK_OK) rc = column_pipe_begin(ctx, &cp, tree0 ? n_cols : n_cols - 1, N);
   // groups: column 0 alone (the FRI waits for nothing else), then the rest -- in groups of 4 when they arrive from the
   // host (compute of a group hides the copy of the next), in one group when they are already on the device
-  const u32 gs = host_cols ? 4u : (n_cols > 1 ? n_cols - 1 : 1u);
+  const u32 gs = host_cols ? (u32)ctx->colpipe_group : (n_cols > 1 ? n_cols - 1 : 1u);
   std::vector<cudaEvent_t> ev;
   if (host_cols)
     for (u32 c0 = 0; c0 < n_cols && rc == STARK_OK; c0 += (c0 == 0 ? 1 : gs)) {
@@ -1255,8 +1261,8 @@ static int mg_prove_trace_impl(stark_mgpu *const *ranks, int n_here, const uint6
     // LDE + batched trees on the column stream, in groups of 4 when they are copied from the host.  With
     // num_rounds() == 0 Fri::commit builds no tree, so rank 0 commits column 0 as well.
     const bool tree0 = fri_rounds == 0 && m->rank == 0;
-    if (rc == STARK_OK) rc = column_pipe_begin(ctx, &t.cp, t.n_my);
-    const u32 gs = host_cols ? 4u : (t.n_my > 1 ? t.n_my - 1 : 1u);
+    if (rc == STARK_OK) rc = column_pipe_begin(ctx, &t.cp, tree0 ? t.n_my : t.n_my - 1, N);
+    const u32 gs = host_cols ? (u32)ctx->colpipe_group : (t.n_my > 1 ? t.n_my - 1 : 1u);
     std::vector<cudaEvent_t> ev;
     if (host_cols && rc == STARK_OK) {
       cudaEvent_t e = nullptr;

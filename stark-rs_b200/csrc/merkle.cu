@@ -238,7 +238,11 @@ int merkle_climb_batch_dev(stark_ctx *ctx, u8 *nodes, size_t n, u32 batch, size_
   size_t m = n;
   // throughput-bound levels: one launch each.  A level of 2^17 parents is already half latency (12 us against 6 us for the
   // same step inside the climb kernel, whose launch is paid anyway), so the climb starts from 2^18 nodes.
-  const size_t climb_from = (size_t)1 << ctx->climb_log;   // STARK_CLIMB_LOG, read once at context creation, clamped to 11..18
+  // STARK_CLIMB_LOG (read once at context creation, clamped to 11..18).  A batch of trees has enough hashes per level to
+  // stay throughput-bound much further up: its levels run as full-width launches down to 2^13 nodes per tree, and the
+  // climb kernel -- whose CTAs are latency-bound and occupancy-limited (2 per SM) -- only takes the top 13 levels
+  const int batch_log = ctx->climb_log < 13 ? ctx->climb_log : 13;
+  const size_t climb_from = (size_t)1 << (batch >= 4 ? batch_log : ctx->climb_log);
   while (m > climb_from) {
     const size_t half = m >> 1;
     LAUNCH_PDL(ctx, "merkle_level", 96ull * half * batch, k_merkle_level, dim3((u32)((half + 2 * HASH_NT - 1) / (2 * HASH_NT)), batch),

@@ -38,10 +38,18 @@ def static_counts(build_dir):
 def main():
     rep, dst = sys.argv[1], sys.argv[2]
     build = sys.argv[3] if len(sys.argv) > 3 else "stark-rs_b200/build"
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if rep.endswith(".csv"):     # `ncu -i x.ncu-rep --page raw --csv` made on the GPU box (the report itself may exceed the copy-back limit)
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(raw.splitlines()))
-    hdr = rows[0]
+    hdr, units = rows[0], rows[1]
     col = {n: i for i, n in enumerate(hdr)}
+    SCALE = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "s": 1e9, "ms": 1e6, "us": 1e3, "ns": 1.0}
+
+    def scaled(r, name):     # bytes, or nanoseconds
+        v = num(r, name)
+        return None if v is None else v * SCALE.get(units[col[name]], 1.0)
 
     def num(r, name):
         return float(r[col[name]].replace(",", "")) if name in col and r[col[name]] not in ("", "n/a") else None
@@ -62,11 +70,17 @@ def main():
         tag, per_thread, bytes_per_hash = KERNELS[k]
         hashes = threads * per_thread
         ti, alu = num(r, "smsp__thread_inst_executed.sum"), num(r, "sm__inst_executed_pipe_alu.sum")
-        rd, wr = num(r, "dram__bytes_read.sum"), num(r, "dram__bytes_write.sum")
+        if ti is None and num(r, "smsp__inst_executed.sum"):
+            ti = 32 * num(r, "smsp__inst_executed.sum")      # warp-level count x 32 lanes (these kernels run full warps)
+        fma = num(r, "sm__inst_executed_pipe_fma.sum")
+        rd, wr = scaled(r, "dram__bytes_read.sum"), scaled(r, "dram__bytes_write.sum")
         out["kernels"][tag] = {
             "kernel": k, "hashes_in_launch": hashes, "thread_instr_per_hash": ti / hashes if ti else None,
-            "alu_instr_per_hash": alu * 32 / hashes if alu else None, "algorithmic_bytes_per_hash": bytes_per_hash,
-            "dram_bytes_per_launch": (rd or 0) + (wr or 0), "duration_ns": num(r, "gpu__time_duration.sum"),
+            "alu_instr_per_hash": alu * 32 / hashes if alu else None, "fma_instr_per_hash": fma * 32 / hashes if fma else None,
+            "algorithmic_bytes_per_hash": bytes_per_hash,
+            "alu_pipe_pct_ncu": num(r, "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+            "issue_active_pct_ncu": num(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+            "dram_bytes_per_launch": (rd or 0) + (wr or 0), "duration_ns": scaled(r, "gpu__time_duration.sum"),
             "static_sass_instr": stat.get(k)}
     json.dump(out, open(dst, "w"), indent=1)
     print(json.dumps(out, indent=1))

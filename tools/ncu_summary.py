@@ -26,7 +26,10 @@ WANT = [
 
 def main():
     rep, out = sys.argv[1], sys.argv[2]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if rep.endswith(".csv"):   # a raw page exported on the GPU box
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     cols = [(w, hdr.index(w)) for w in WANT if w in hdr]
