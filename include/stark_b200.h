@@ -52,6 +52,8 @@ int stark_ctx_create(int device, stark_ctx **out);
 int stark_ctx_create_on_stream(int device, void *cuda_stream, stark_ctx **out);
 void stark_ctx_destroy(stark_ctx *ctx);
 int stark_ctx_sync(stark_ctx *ctx);
+/* cudaSetDevice(the context's device): needed only by a host thread that uses contexts on DIFFERENT devices in turn */
+int stark_ctx_make_current(stark_ctx *ctx);
 void *stark_ctx_stream(stark_ctx *ctx);
 uint64_t stark_ctx_launches(stark_ctx *ctx); /* kernels launched so far through this context */
 /* per-kernel device timing with CUDA events on the context's stream (measurement only; bench.py roofline) */

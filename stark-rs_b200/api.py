@@ -289,6 +289,11 @@ class Context:
     def sync(self):
         _chk(lib().stark_ctx_sync(self.h))
 
+    def make_current(self):
+        """cudaSetDevice(this context's device) -- for a thread that uses contexts on several devices in turn"""
+        _chk(lib().stark_ctx_make_current(self.h))
+        return self
+
     @property
     def launches(self):
         return lib().stark_ctx_launches(self.h)

@@ -273,6 +273,13 @@ void stark_ctx_destroy(stark_ctx *ctx) {
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
+// A host thread that drives contexts on several devices makes a context's device current before using it (the group
+// entry points do this themselves for every rank they drive).
+int stark_ctx_make_current(stark_ctx *ctx) {
+  if (!ctx) return stark_fail(nullptr, STARK_ERR_ARG, "null context");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  return STARK_OK;
+}
 int stark_ctx_sync(stark_ctx *ctx) {
   if (!ctx) return stark_fail(nullptr, STARK_ERR_ARG, "null context");
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));

@@ -13,6 +13,7 @@ extern "C" {
     pub fn stark_ctx_create_on_stream(device: i32, cuda_stream: *mut std::ffi::c_void, out: *mut *mut StarkCtx) -> i32;
     pub fn stark_ctx_destroy(ctx: *mut StarkCtx);
     pub fn stark_ctx_sync(ctx: *mut StarkCtx) -> i32;
+    pub fn stark_ctx_make_current(ctx: *mut StarkCtx) -> i32;
     pub fn stark_ctx_stream(ctx: *mut StarkCtx) -> *mut std::ffi::c_void;
     pub fn stark_ctx_launches(ctx: *mut StarkCtx) -> u64;
     pub fn stark_ctx_profile_begin(ctx: *mut StarkCtx) -> i32;

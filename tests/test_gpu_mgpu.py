@@ -213,7 +213,7 @@ def test_peer_group_one_process(S, par_oracle, world):
         cw = O.fast_lde(O.splitmix64(SEED, n // 4), 16, 2, 3)
         w = O.ff_prim_nth_root(n)
         ref = O.fri_prove(cw, w, 3, 4, 32)
-        bufs = [c.upload(cw) for c in ctxs]
+        bufs = [c.make_current().upload(cw) for c in ctxs]      # one thread, several devices
         for rep in range(3):
             for proof, top in g.fri_prove_dev(bufs, n, 3, w, 4, 32):
                 assert proof == ref["proof"] and top == ref["top_indices"]
@@ -221,11 +221,13 @@ def test_peer_group_one_process(S, par_oracle, world):
         res = g.prove_trace(cols, 2, 3, 32)
         assert all(p == ref["proof"] for _, p in res)
         assert all(np.array_equal(r, res[0][0]) for r, _ in res)
-        for b in bufs:
+        for c, b in zip(ctxs, bufs):
+            c.make_current()
             b.free()
     finally:
         g.close()
         for c in ctxs:
+            c.make_current()
             c.close()
 
 
