@@ -50,11 +50,17 @@ struct stark_ctx {
   cudaStream_t side[4];
   cudaEvent_t side_done[4], fork_ev;
   int n_side;            // streams created so far
+  // the latency chain of a proof (column 0 -> LDE -> Fri::prove: ~50 short dependent kernels) runs on a stream of the
+  // HIGHEST priority, so that its kernels are dispatched ahead of the pending CTAs of the throughput kernels the column
+  // stream has in flight (fri.cu PrioScope); created on first use
+  cudaStream_t prio_stream;
+  cudaEvent_t prio_ev;
   int ntt_streams;       // groups in flight (STARK_NTT_STREAMS, default 2; 1 = whole batch per pass)
   int ntt_group_mb;      // bytes of one group's column slice (STARK_NTT_GROUP_MB, default 16)
   int ntt_big;           // STARK_NTT_BIG=1: two-pass plans on 16384-element tiles for 2^20..2^22 (experiment)
   int ntt_l2_persist;    // STARK_NTT_L2_PERSIST=1: mark each pass's destination as L2-persisting (experiment, default off)
   int l2_persist_ready;
+  int no_prio;           // STARK_NO_PRIO=1: keep the latency chain on the caller's stream (diagnosis)
   int colpipe_serial;    // STARK_COLPIPE_SERIAL=1: no column / copy stream (everything on the context's stream; diagnosis)
   int colpipe_group;     // columns per group when the trace is copied from the host (STARK_COLPIPE_GROUP, default 4)
   int climb_log;         // Merkle levels above 2^climb_log nodes get one launch each, the rest one climb launch (merkle.cu)

@@ -1135,6 +1135,40 @@ static void column_pipe_free(stark_ctx *ctx, ColumnPipe *cp) {
   cp->d_roots = nullptr, cp->staging = nullptr;
 }
 
+// For the duration of an operation the context's launches go to its high-priority stream (forked from the caller's stream,
+// joined back to it at the end).  The FRI rounds are a chain of short latency-bound kernels; while the column stream has
+// thousands of throughput CTAs pending, a default-priority launch of the chain waits for CTA slots behind them: measured
+// on 8 GPUs, 2 column trees per rank added 0.7 ms to a 1.0 ms chain that should have hidden them (profiles/r2e_bench_g8.json).
+struct PrioScope {
+  stark_ctx *ctx = nullptr;
+  cudaStream_t user = nullptr;
+  bool on = false;
+  void enter(stark_ctx *c) {
+    ctx = c, user = c->stream;
+    if (c->prof_on || c->colpipe_serial || c->no_prio) return;
+    if (!c->prio_stream) {
+      int lo = 0, hi = 0;
+      cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi = numerically smallest = greatest priority
+      if (cudaStreamCreateWithPriority(&c->prio_stream, cudaStreamNonBlocking, hi) != cudaSuccess ||
+          cudaEventCreateWithFlags(&c->prio_ev, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        c->prio_stream = nullptr;
+        return;
+      }
+    }
+    cudaEventRecord(c->prio_ev, user);
+    cudaStreamWaitEvent(c->prio_stream, c->prio_ev, 0);
+    c->stream = c->prio_stream, on = true;
+  }
+  void leave() {
+    if (!on) return;
+    cudaEventRecord(ctx->prio_ev, ctx->prio_stream);
+    cudaStreamWaitEvent(user, ctx->prio_ev, 0);
+    ctx->stream = user, on = false;
+  }
+  ~PrioScope() { leave(); }
+};
+
 // BASELINE config 3 on one device, from device columns (cols_dev) or from the host trace (host_cols; cols_dev then is the
 // buffer the narrowed columns go to): column 0 -> LDE -> Fri::prove on the context's stream, the other columns ->
 // LDE + trees on the column stream.
@@ -1149,6 +1183,8 @@ static int prove_trace_pipeline(stark_ctx *ctx, const uint64_t *host_cols, u32 *
   const bool tree0 = fri_rounds == 0;
   u32 *lde = nullptr;
   ColumnPipe cp;
+  PrioScope prio;
+  if (n_cols > 1) prio.enter(ctx);     // with one column nothing competes with the chain
   ST_TRY(dev_alloc(ctx, (void **)&lde, N * n_cols * 4));
   int rc = STARK_OK;
   if (host_cols) {
@@ -1236,6 +1272,7 @@ static int mg_prove_trace_impl(stark_mgpu *const *ranks, int n_here, const uint6
   ST_TRY(fri_check(ctx0, N, 1u << log_blowup, &fri_rounds, nq));
   std::vector<MgTraceRank> T(n_here);
   std::vector<MgProve> P(n_here);
+  std::vector<PrioScope> prio(n_here);
   int rc = STARK_OK;
   // phase 1 (no exchange): upload / LDE of column 0 and the owned columns, column trees on the side stream
   for (int k = 0; k < n_here && rc == STARK_OK; k++) {
@@ -1246,6 +1283,8 @@ static int mg_prove_trace_impl(stark_mgpu *const *ranks, int n_here, const uint6
     t.owned.resize(n_cols);
     t.owned.resize(mg_owned_columns(m->rank, m->world, n_cols, t.owned.data()));
     t.n_my = 1 + (u32)t.owned.size();
+    // ranks that share a stream (virtual ranks in lock step) stay on it: their order IS the stream order
+    if (!m->lockstep && n_cols > 1) prio[k].enter(ctx);
     u32 *cols_dev = nullptr;
     if (host_cols) {
       rc = stark_buf_alloc(ctx, n * t.n_my, &t.in);
@@ -1327,6 +1366,7 @@ static int mg_prove_trace_impl(stark_mgpu *const *ranks, int n_here, const uint6
     column_pipe_free(ctx, &T[k].cp);
     dev_free(ctx, T[k].lde);
     stark_buf_free(T[k].in);
+    prio[k].leave();
   }
   return rc;
 }

@@ -142,6 +142,8 @@ int side_streams(stark_ctx *ctx, int n) {
   return STARK_OK;
 }
 void ntt_destroy(stark_ctx *ctx) {
+  if (ctx->prio_stream) cudaStreamDestroy(ctx->prio_stream);
+  if (ctx->prio_ev) cudaEventDestroy(ctx->prio_ev);
   for (int i = 0; i < ctx->n_side; i++) cudaStreamDestroy(ctx->side[i]), cudaEventDestroy(ctx->side_done[i]);
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
   cudaFree(ctx->root_lo), cudaFree(ctx->root_hi), cudaFree(ctx->tw_sub[0]), cudaFree(ctx->tw_sub[1]);
