@@ -238,6 +238,7 @@ static int ctx_create(int device, cudaStream_t borrowed, bool borrow, stark_ctx 
   // k_merkle_climb<256> takes at most 256 chunks of 512 / 1024 nodes (its fused top holds the chunk roots in 16 KB of
   // shared memory): the tuning knob is clamped to the range the kernel supports
   ctx->colpipe_serial = getenv("STARK_COLPIPE_SERIAL") && atoi(getenv("STARK_COLPIPE_SERIAL")) != 0;
+  ctx->keep_pdl = getenv("STARK_KEEP_PDL") && atoi(getenv("STARK_KEEP_PDL")) != 0;
   ctx->no_prio = getenv("STARK_NO_PRIO") && atoi(getenv("STARK_NO_PRIO")) != 0;
   ctx->colpipe_group = 4;
   if (const char *e = getenv("STARK_COLPIPE_GROUP")) {

@@ -60,6 +60,7 @@ struct stark_ctx {
   int ntt_big;           // STARK_NTT_BIG=1: two-pass plans on 16384-element tiles for 2^20..2^22 (experiment)
   int ntt_l2_persist;    // STARK_NTT_L2_PERSIST=1: mark each pass's destination as L2-persisting (experiment, default off)
   int l2_persist_ready;
+  int keep_pdl;          // STARK_KEEP_PDL=1: programmatic dependent launch stays on inside multi-column pipelines (diagnosis)
   int no_prio;           // STARK_NO_PRIO=1: keep the latency chain on the caller's stream (diagnosis)
   int colpipe_serial;    // STARK_COLPIPE_SERIAL=1: no column / copy stream (everything on the context's stream; diagnosis)
   int colpipe_group;     // columns per group when the trace is copied from the host (STARK_COLPIPE_GROUP, default 4)
@@ -129,6 +130,11 @@ __device__ __forceinline__ void pdl_entry() {
   asm volatile("griddepcontrol.launch_dependents;");
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
+// While a multi-column pipeline is in flight the chain's kernels are launched the classic way: a dependent launched early
+// sits in griddepcontrol.wait and holds CTA slots for as long as its predecessor runs -- behind a latency-bound climb
+// kernel (~40 us, a handful of busy SMs) that idles the slots the column stream's throughput kernels would have used
+// (measured: 16-column prove 6.9 -> 8.2 ms once the chain also had stream priority).  Set by PrioScope (fri.cu).
+inline thread_local bool t_pdl_off = false;
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                                      Args... args) {
@@ -137,7 +143,7 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at, cfg.numAttrs = 1;
+  cfg.attrs = at, cfg.numAttrs = t_pdl_off ? 0 : 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 #endif

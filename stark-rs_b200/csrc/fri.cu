@@ -1142,7 +1142,7 @@ static void column_pipe_free(stark_ctx *ctx, ColumnPipe *cp) {
 struct PrioScope {
   stark_ctx *ctx = nullptr;
   cudaStream_t user = nullptr;
-  bool on = false;
+  bool on = false, pdl_was_off = false;
   void enter(stark_ctx *c) {
     ctx = c, user = c->stream;
     if (c->prof_on || c->colpipe_serial || c->no_prio) return;
@@ -1159,9 +1159,11 @@ struct PrioScope {
     cudaEventRecord(c->prio_ev, user);
     cudaStreamWaitEvent(c->prio_stream, c->prio_ev, 0);
     c->stream = c->prio_stream, on = true;
+    pdl_was_off = t_pdl_off, t_pdl_off = !c->keep_pdl;
   }
   void leave() {
     if (!on) return;
+    t_pdl_off = pdl_was_off;
     cudaEventRecord(ctx->prio_ev, ctx->prio_stream);
     cudaStreamWaitEvent(user, ctx->prio_ev, 0);
     ctx->stream = user, on = false;
