@@ -37,6 +37,8 @@ struct stark_ctx {
   ntt::wpair w8_sh[2][4];
   ntt::wpair *tw_in_sh[2]; // inner twiddles per radix and round (ntt_pass.cuh fill_inner_twiddles)
   ntt::wpair *otw_sh[2];   // w_{2^16}^(+-e), e < 2^16 (outer twiddles of the MIDDLE pass)
+  ntt::wpair *row12_sh[2]; // w_4096^(+-row), row < 128 (FIRST pass of the fused 2^12 kernel, ntt.cu k_ntt_small12)
+  int ntt_small_off;       // STARK_NTT_SMALL_OFF=1: batches of 2^12 keep the one-CTA-per-transform kernel (comparison)
   ntt::wpair *row_sh[2];   // w_{2^logN}^(+-row), row < 2048, at [(logN - 13) * 2048 + row], logN = 13..23 (FIRST pass)
   GeoCacheEntry geo[8];
   u64 geo_stamp;

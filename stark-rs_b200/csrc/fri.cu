@@ -1171,6 +1171,21 @@ struct PrioScope {
   ~PrioScope() { leave(); }
 };
 
+// The groups local columns [1, n_my) go through the column stream in: (first column, count).  On the device already: one
+// group (the widest batches).  From the host: 1, 2, then `gs` columns -- the column stream starts as soon as ONE column has
+// arrived instead of idling until a full group is there, and the compute of a group hides the copy of the next.
+static std::vector<std::pair<u32, u32>> column_groups(u32 n_my, bool from_host, u32 gs) {
+  std::vector<std::pair<u32, u32>> g;
+  u32 c0 = 1, step = from_host ? 1u : (n_my > 1 ? n_my - 1 : 1u);
+  while (c0 < n_my) {
+    const u32 cnt = n_my - c0 < step ? n_my - c0 : step;
+    g.push_back({c0, cnt});
+    c0 += cnt;
+    if (from_host) step = step * 2 < gs ? step * 2 : gs;
+  }
+  return g;
+}
+
 // BASELINE config 3 on one device, from device columns (cols_dev) or from the host trace (host_cols; cols_dev then is the
 // buffer the narrowed columns go to): column 0 -> LDE -> Fri::prove on the context's stream, the other columns ->
 // LDE + trees on the column stream.
@@ -1194,27 +1209,22 @@ static int prove_trace_pipeline(stark_ctx *ctx, const uint64_t *host_cols, u32 *
     if (rc == STARK_OK) rc = upload_flag_reset(ctx);
   }
   if (rc == STARK_OK) rc = column_pipe_begin(ctx, &cp, tree0 ? n_cols : n_cols - 1, N);
-  // groups: column 0 alone (the FRI waits for nothing else), then the rest -- in groups of 4 when they arrive from the
-  // host (compute of a group hides the copy of the next), in one group when they are already on the device
-  const u32 gs = host_cols ? (u32)ctx->colpipe_group : (n_cols > 1 ? n_cols - 1 : 1u);
-  std::vector<cudaEvent_t> ev;
-  if (host_cols)
-    for (u32 c0 = 0; c0 < n_cols && rc == STARK_OK; c0 += (c0 == 0 ? 1 : gs)) {
-      cudaEvent_t e = nullptr;
-      const u32 cnt = c0 == 0 ? 1 : (n_cols - c0 < gs ? n_cols - c0 : gs);
-      rc = column_pipe_copy(ctx, &cp, host_cols + (size_t)c0 * n, (size_t)c0 * n, n * cnt, true, &e);
-      ev.push_back(e);
-    }
+  // groups: column 0 alone (the FRI waits for nothing else), then the rest (column_groups)
+  const auto groups = column_groups(n_cols, host_cols != nullptr, (u32)ctx->colpipe_group);
+  std::vector<cudaEvent_t> ev(1 + groups.size(), nullptr);
+  if (host_cols) {
+    rc = column_pipe_copy(ctx, &cp, host_cols, 0, n, true, &ev[0]);
+    for (size_t gi = 0; gi < groups.size() && rc == STARK_OK; gi++)
+      rc = column_pipe_copy(ctx, &cp, host_cols + (size_t)groups[gi].first * n, (size_t)groups[gi].first * n,
+                            n * groups[gi].second, true, &ev[1 + gi]);
+  }
   // column 0 on the context's stream
-  if (rc == STARK_OK) rc = column_pipe_group(ctx, &cp, host_cols ? ev[0] : nullptr, cols_dev, lde, 0, 1, log_n, log_blowup, offset, true, tree0);
+  if (rc == STARK_OK) rc = column_pipe_group(ctx, &cp, ev[0], cols_dev, lde, 0, 1, log_n, log_blowup, offset, true, tree0);
   // the other columns on the column stream
   if (rc == STARK_OK) {
     column_pipe_enter(ctx, &cp);
-    u32 gi = 1;
-    for (u32 c0 = 1; c0 < n_cols && rc == STARK_OK; c0 += gs, gi++) {
-      const u32 cnt = n_cols - c0 < gs ? n_cols - c0 : gs;
-      rc = column_pipe_group(ctx, &cp, host_cols ? ev[gi] : nullptr, cols_dev, lde, c0, cnt, log_n, log_blowup, offset, true, true);
-    }
+    for (size_t gi = 0; gi < groups.size() && rc == STARK_OK; gi++)
+      rc = column_pipe_group(ctx, &cp, ev[1 + gi], cols_dev, lde, groups[gi].first, groups[gi].second, log_n, log_blowup, offset, true, true);
     column_pipe_leave(ctx, &cp);
   }
   const u32 omega = ff::pow(ff::GEN, (ff::P - 1) >> (log_n + log_blowup));  // prim_nth_root(N), ff.rs:215-223
@@ -1303,28 +1313,22 @@ static int mg_prove_trace_impl(stark_mgpu *const *ranks, int n_here, const uint6
     // num_rounds() == 0 Fri::commit builds no tree, so rank 0 commits column 0 as well.
     const bool tree0 = fri_rounds == 0 && m->rank == 0;
     if (rc == STARK_OK) rc = column_pipe_begin(ctx, &t.cp, tree0 ? t.n_my : t.n_my - 1, N);
-    const u32 gs = host_cols ? (u32)ctx->colpipe_group : (t.n_my > 1 ? t.n_my - 1 : 1u);
-    std::vector<cudaEvent_t> ev;
+    const auto groups = column_groups(t.n_my, host_cols != nullptr, (u32)ctx->colpipe_group);
+    std::vector<cudaEvent_t> ev(1 + groups.size(), nullptr);
     if (host_cols && rc == STARK_OK) {
-      cudaEvent_t e = nullptr;
-      rc = column_pipe_copy(ctx, &t.cp, host_cols, 0, n, true, &e);
-      ev.push_back(e);
-      for (u32 i0 = 1; i0 < t.n_my && rc == STARK_OK; i0 += gs) {
-        const u32 cnt = t.n_my - i0 < gs ? t.n_my - i0 : gs;
-        for (u32 i = i0; i < i0 + cnt && rc == STARK_OK; i++)
-          rc = column_pipe_copy(ctx, &t.cp, host_cols + (size_t)t.owned[i - 1] * n, (size_t)i * n, n, i + 1 == i0 + cnt, &e);
-        ev.push_back(e);
-      }
+      rc = column_pipe_copy(ctx, &t.cp, host_cols, 0, n, true, &ev[0]);
+      for (size_t gi = 0; gi < groups.size() && rc == STARK_OK; gi++)
+        for (u32 i = groups[gi].first; i < groups[gi].first + groups[gi].second && rc == STARK_OK; i++)
+          rc = column_pipe_copy(ctx, &t.cp, host_cols + (size_t)t.owned[i - 1] * n, (size_t)i * n, n,
+                                i + 1 == groups[gi].first + groups[gi].second, &ev[1 + gi]);
     }
     if (rc == STARK_OK)
-      rc = column_pipe_group(ctx, &t.cp, host_cols ? ev[0] : nullptr, cols_dev, t.lde, 0, 1, log_n, log_blowup, (u32)offset, true, tree0);
+      rc = column_pipe_group(ctx, &t.cp, ev[0], cols_dev, t.lde, 0, 1, log_n, log_blowup, (u32)offset, true, tree0);
     if (rc == STARK_OK) {
       column_pipe_enter(ctx, &t.cp);
-      u32 gi = 1;
-      for (u32 i0 = 1; i0 < t.n_my && rc == STARK_OK; i0 += gs, gi++) {
-        const u32 cnt = t.n_my - i0 < gs ? t.n_my - i0 : gs;
-        rc = column_pipe_group(ctx, &t.cp, host_cols ? ev[gi] : nullptr, cols_dev, t.lde, i0, cnt, log_n, log_blowup, (u32)offset, true, true);
-      }
+      for (size_t gi = 0; gi < groups.size() && rc == STARK_OK; gi++)
+        rc = column_pipe_group(ctx, &t.cp, ev[1 + gi], cols_dev, t.lde, groups[gi].first, groups[gi].second, log_n, log_blowup,
+                               (u32)offset, true, true);
       column_pipe_leave(ctx, &t.cp);
     }
     if (rc == STARK_OK)

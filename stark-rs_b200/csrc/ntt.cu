@@ -89,12 +89,23 @@ int ntt_init(stark_ctx *ctx) {
     KERNEL_CHECK(ctx);
     k_shoup_roots<<<11 * 8, 256, 0, ctx->stream>>>(ctx->row_sh[d], T, d, 1, 11 * 2048);
     KERNEL_CHECK(ctx);
+    {
+      // FIRST-pass row table of the fused 2^12 kernel: w_4096^(+-row), row < 128
+      u32 w12 = ff::pow(ff::GEN, (ff::P - 1) >> 12);
+      if (d) w12 = ff::inv(w12);
+      std::vector<wpair> h(128);
+      u32 v = 1;
+      for (int r = 0; r < 128; r++) h[r] = wpair{v, ff::shoup_of(v)}, v = ff::mul(v, w12);
+      CU_TRY(ctx, cudaMalloc(&ctx->row12_sh[d], h.size() * sizeof(wpair)));
+      CU_TRY(ctx, cudaMemcpy(ctx->row12_sh[d], h.data(), h.size() * sizeof(wpair), cudaMemcpyHostToDevice));
+    }
     u32 w8 = ff::pow(ff::GEN, (ff::P - 1) >> 3);
     if (d) w8 = ff::inv(w8);
     for (int k = 0; k < 4; k++) ctx->w8_sh[d][k] = wpair{ff::pow(w8, k), ff::shoup_of(ff::pow(w8, k))};
   }
   for (int i = 0; i < 8; i++) ctx->geo[i] = GeoCacheEntry{0, 0, nullptr, nullptr, 0, 0};
   ctx->geo_stamp = 0;
+  ctx->ntt_small_off = getenv("STARK_NTT_SMALL_OFF") && atoi(getenv("STARK_NTT_SMALL_OFF")) != 0;
   const char *e = getenv("STARK_NTT_STREAMS");
   ctx->ntt_streams = e ? atoi(e) : 2;
   if (ctx->ntt_streams < 1 || ctx->ntt_streams > 4) ctx->ntt_streams = 2;
@@ -150,6 +161,7 @@ void ntt_destroy(stark_ctx *ctx) {
   cudaFree(ctx->tw_sh[0]), cudaFree(ctx->tw_sh[1]);
   cudaFree(ctx->tw_in_sh[0]), cudaFree(ctx->tw_in_sh[1]);
   cudaFree(ctx->otw_sh[0]), cudaFree(ctx->otw_sh[1]), cudaFree(ctx->row_sh[0]), cudaFree(ctx->row_sh[1]);
+  cudaFree(ctx->row12_sh[0]), cudaFree(ctx->row12_sh[1]);
   for (int i = 0; i < 8; i++) {
     cudaFree(ctx->geo[i].lo);
     if (ctx->geo[i].ready) cudaEventDestroy(ctx->geo[i].ready);
@@ -296,6 +308,43 @@ __global__ void __launch_bounds__(1 << (TL - 5), TL == ntt2::TILE_LOG ? 8 : 2) k
   round_compute<LOGR, KIND, PL::NR - 1, MODE, TL>(tid, A, T, tile, otw, regs);
   round_store<LOGR, KIND, PL::NR - 1, TL>(tid, A, T, tile, regs);
 }
+// Batches of 2^12-point transforms: ONE 128-thread CTA per transform on the 4096-element-tile machinery of ntt_pass.cuh
+// instead of the 512-thread, 8-elements-per-thread k_ntt_single (1024 x 2^12 ran at 20 % of the HBM peak: one wave and a
+// half of fat CTAs, little instruction-level parallelism).  The transform is the two-pass plan {2^7, 2^5} with both passes
+// in one launch: the radix-2^7 FIRST pass (four-step twiddles w_4096^(u k)) leaves its transposed result Y[128 u + k] in a
+// second 16 KB shared buffer, the radix-2^5 LAST pass reads it from there and stores to HBM with the fused post-scale.
+// 32 KB of shared memory, 7 CTAs per SM, 32 elements per thread, 128-bit HBM accesses on both ends.
+template <int FM, int LM>
+__global__ void __launch_bounds__(ntt2::NT, 7) k_ntt_small12(const __grid_constant__ ntt2::PassParams A,
+                                                            const __grid_constant__ ntt2::PassParams B) {
+  using namespace ntt2;
+  __shared__ __align__(16) q4 tile[1 << (TILE_LOG - 2)];
+  __shared__ __align__(16) u32 ybuf[1 << TILE_LOG];
+  pdl_entry();
+  const u32 tid = threadIdx.x, b = blockIdx.x;
+  const wpair *otw = nullptr;
+  u32 regs[32];
+  TileCtx T1;
+  T1.in = A.in + (u64)b * A.in_batch, T1.out = ybuf, T1.col0 = 0, T1.q0 = 0, T1.p = 0;
+  round_compute<7, FIRST, 0, FM>(tid, A, T1, tile, otw, regs);
+  round_store<7, FIRST, 0>(tid, A, T1, tile, regs);
+  __syncthreads();
+  round_compute<7, FIRST, 1, FM>(tid, A, T1, tile, otw, regs);
+  __syncthreads();
+  round_store<7, FIRST, 1>(tid, A, T1, tile, regs);
+  __syncthreads();
+  round_compute<7, FIRST, 2, FM>(tid, A, T1, tile, otw, regs);
+  round_store<7, FIRST, 2>(tid, A, T1, tile, regs);   // -> ybuf
+  __syncthreads();
+  TileCtx T2;
+  T2.in = ybuf, T2.out = B.out + (u64)b * B.out_batch, T2.col0 = 0, T2.q0 = 0, T2.p = 0;
+  round_compute<5, LAST, 0, LM>(tid, B, T2, tile, otw, regs);
+  round_store<5, LAST, 0>(tid, B, T2, tile, regs);
+  __syncthreads();
+  round_compute<5, LAST, 1, LM>(tid, B, T2, tile, otw, regs);
+  round_store<5, LAST, 1>(tid, B, T2, tile, regs);
+}
+
 // launch of a 16384-element-tile pass: 64 KB of dynamic shared memory (opt-in above 48 KB, once per instance)
 template <int LOGR, int KIND, int MODE>
 static cudaError_t launch_big_pass(cudaStream_t st, u32 grid, const ntt2::PassParams &B) {
@@ -361,6 +410,53 @@ int ntt_transform(stark_ctx *ctx, const u32 *in, u32 *out, int log_n, bool inver
                   pre_geo, post_geo, post_c};
     // in == out is fine: each thread reads its whole transform before writing
     LAUNCH(ctx, "ntt_tiny", 8ull * N * batch, k_ntt_tiny<<<(batch + 127) / 128, 128, 0, ctx->stream>>>(A));
+    return STARK_OK;
+  }
+
+  if (log_n == 12 && batch >= 8 && !ctx->ntt_small_off) {
+    // batches of 2^12: the fused two-pass kernel (k_ntt_small12)
+    ntt2::PassParams A, B;
+    memset(&A, 0, sizeof A);
+    A.logN = 12, A.log_tiles = 0, A.roots = roots, A.inverse = d, A.zero = 0;
+    for (int k = 0; k < 4; k++) A.w8[k] = ctx->w8_sh[d][k];
+    B = A;
+    A.in = in, A.in_batch = in_batch, A.n_valid = n_valid, A.logS = 0;
+    A.tw_in = ctx->tw_in_sh[d] + ntt2::inner_twiddle_offset(7), A.row_tab = ctx->row12_sh[d];
+    A.pre_mode = pre_mode, A.pre_geo = pre_geo;
+    A.pre_g1 = A.pre_gj = wpair{1, ff::shoup_of(1)};
+    if (pre_mode == SCALE_GEO) {
+      const u32 gj = ff::pow(pre.g, N >> 1);   // the FIRST pass's first round is the radix-2 one (7 = 1 + 3 + 3)
+      A.pre_g1 = wpair{pre.g, ff::shoup_of(pre.g)}, A.pre_gj = wpair{gj, ff::shoup_of(gj)};
+    }
+    B.out = out, B.out_batch = out_batch, B.n_valid = N, B.logS = 7;
+    B.tw_in = ctx->tw_in_sh[d] + ntt2::inner_twiddle_offset(5);
+    const u32 post_plain = ff::from_mont(post_c);
+    B.post_mode = post_mode, B.post_const = wpair{post_plain, ff::shoup_of(post_plain)}, B.post_geo = post_geo;
+    B.post_g1 = B.post_gk = wpair{1, ff::shoup_of(1)};
+    if (post_mode == SCALE_GEO) {
+      const u32 gk = ff::pow(post.g, N >> 3);
+      B.post_g1 = wpair{post.g, ff::shoup_of(post.g)}, B.post_gk = wpair{gk, ff::shoup_of(gk)};
+    }
+    const int fm = (n_valid < N ? 1 : 0) | (pre_mode == SCALE_GEO ? 2 : 0);
+    const u64 bytes = 4ull * batch * (n_valid + N);
+#define SMALL12(F_, L_) LAUNCH_PDL(ctx, "ntt_small12", bytes, (k_ntt_small12<F_, L_>), batch, ntt2::NT, A, B)
+#define SMALL12_L(F_)                       \
+  if (post_mode == SCALE_NONE) {            \
+    SMALL12(F_, 0);                         \
+  } else if (post_mode == SCALE_CONST) {    \
+    SMALL12(F_, 1);                         \
+  } else {                                  \
+    SMALL12(F_, 2);                         \
+  }
+    if (fm == 0) {
+      SMALL12_L(0)
+    } else if (fm == 1) {
+      SMALL12_L(1)
+    } else {
+      SMALL12_L(3)   // pre-scale, with or without zero padding
+    }
+#undef SMALL12
+#undef SMALL12_L
     return STARK_OK;
   }
 

@@ -72,6 +72,61 @@ static void run_pass(const PassParams &A, u32 grid) {
     for (u32 tid = 0; tid < NTH; tid++) round_store<LOGR, KIND, PL::NR - 1, TL>(tid, A, T, tile.data(), &regs[tid * 32]);
   }
 }
+// mirrors k_ntt_small12 in ntt.cu: radix-2^7 FIRST pass into a second shared buffer, radix-2^5 LAST pass out of it
+template <int FM, int LM>
+static void run_small12(const PassParams &A, const PassParams &B, u32 batch) {
+  constexpr u32 NTH = 128;
+  std::vector<q4> tile(1024);
+  std::vector<u32> ybuf(4096), regs((size_t)NTH * 32);
+  const wpair *otw = nullptr;
+  for (u32 b = 0; b < batch; b++) {
+    TileCtx T1;
+    T1.in = A.in + (u64)b * A.in_batch, T1.out = ybuf.data(), T1.col0 = 0, T1.q0 = 0, T1.p = 0;
+    for (u32 t = 0; t < NTH; t++) round_compute<7, FIRST, 0, FM>(t, A, T1, tile.data(), otw, &regs[t * 32]);
+    for (u32 t = 0; t < NTH; t++) round_store<7, FIRST, 0>(t, A, T1, tile.data(), &regs[t * 32]);
+    for (u32 t = 0; t < NTH; t++) round_compute<7, FIRST, 1, FM>(t, A, T1, tile.data(), otw, &regs[t * 32]);
+    for (u32 t = 0; t < NTH; t++) round_store<7, FIRST, 1>(t, A, T1, tile.data(), &regs[t * 32]);
+    for (u32 t = 0; t < NTH; t++) round_compute<7, FIRST, 2, FM>(t, A, T1, tile.data(), otw, &regs[t * 32]);
+    for (u32 t = 0; t < NTH; t++) round_store<7, FIRST, 2>(t, A, T1, tile.data(), &regs[t * 32]);
+    TileCtx T2;
+    T2.in = ybuf.data(), T2.out = B.out + (u64)b * B.out_batch, T2.col0 = 0, T2.q0 = 0, T2.p = 0;
+    for (u32 t = 0; t < NTH; t++) round_compute<5, LAST, 0, LM>(t, B, T2, tile.data(), otw, &regs[t * 32]);
+    for (u32 t = 0; t < NTH; t++) round_store<5, LAST, 0>(t, B, T2, tile.data(), &regs[t * 32]);
+    for (u32 t = 0; t < NTH; t++) round_compute<5, LAST, 1, LM>(t, B, T2, tile.data(), otw, &regs[t * 32]);
+    for (u32 t = 0; t < NTH; t++) round_store<5, LAST, 1>(t, B, T2, tile.data(), &regs[t * 32]);
+  }
+}
+// mirrors the `log_n == 12 && batch >= 8` branch of ntt_transform() in ntt.cu
+static void transform12(const u32 *in, u32 *out, int d, u32 batch, u64 n_valid, int post_mode, u32 post_c, GeoTables post_geo,
+                        int pre_mode, GeoTables pre_geo) {
+  const u64 N = 4096;
+  static std::vector<wpair> row12[2];
+  if (row12[d].empty()) {
+    u32 w12 = ff::pow(3, (ff::P - 1) >> 12);
+    if (d) w12 = ff::inv(w12);
+    u32 v = 1;
+    for (int r = 0; r < 128; r++) row12[d].push_back(wpair{v, ff::shoup_of(v)}), v = ff::mul(v, w12);
+  }
+  PassParams A, B;
+  memset(&A, 0, sizeof A);
+  A.logN = 12, A.log_tiles = 0, A.roots = {g_lo.data(), g_hi.data()}, A.inverse = d;
+  for (int k = 0; k < 4; k++) A.w8[k] = g_w8[d][k];
+  B = A;
+  const u32 g = 3;   // the geometric scale of main(): c * 3^i
+  A.in = in, A.in_batch = N, A.n_valid = n_valid, A.logS = 0;
+  A.tw_in = g_twin[d].data() + inner_twiddle_offset(7), A.row_tab = row12[d].data();
+  A.pre_mode = pre_mode, A.pre_geo = pre_geo;
+  { const u32 gj = ff::pow(g, N >> 1); A.pre_g1 = wpair{g, ff::shoup_of(g)}, A.pre_gj = wpair{gj, ff::shoup_of(gj)}; }
+  B.out = out, B.out_batch = N, B.n_valid = N, B.logS = 7;
+  B.tw_in = g_twin[d].data() + inner_twiddle_offset(5);
+  B.post_mode = post_mode, B.post_const = wpair{ff::from_mont(post_c), ff::shoup_of(ff::from_mont(post_c))}, B.post_geo = post_geo;
+  { const u32 gk = ff::pow(g, N >> 3); B.post_g1 = wpair{g, ff::shoup_of(g)}, B.post_gk = wpair{gk, ff::shoup_of(gk)}; }
+  const int fm = (n_valid < N ? 1 : 0) | (pre_mode == ntt::SCALE_GEO ? 2 : 0);
+#define S12(F_) { if (post_mode == ntt::SCALE_NONE) run_small12<F_, 0>(A, B, batch); else if (post_mode == ntt::SCALE_CONST) run_small12<F_, 1>(A, B, batch); else run_small12<F_, 2>(A, B, batch); }
+  if (fm == 0) S12(0) else if (fm == 1) S12(1) else S12(3)
+#undef S12
+}
+
 static bool g_big = false;   // the two-pass plans on 16384-element tiles (STARK_NTT_BIG in ntt.cu)
 
 // mirrors the N >= 2^13 branch of ntt_transform() in ntt.cu
@@ -172,7 +227,7 @@ int main(int argc, char **argv) {
   printf("bank-conflicted quarter-warp accesses (16384-element tiles): %ld\n", bc_big);
   if (bc_big) fails++;
   g_big = argc > 2 && atoi(argv[2]) != 0;
-  int min_log = g_big ? 20 : 13;
+  int min_log = g_big ? 20 : 12;   // 12 = the fused small-transform kernel (transform12)
   // geometric table for scale tests: c * g^i
   const u32 g = 3, c = ff::inv(1u << 10);
   std::vector<u32> glo(4096), ghi(4096);
@@ -190,8 +245,15 @@ int main(int argc, char **argv) {
     int post_mode = mode == 2 ? ntt::SCALE_GEO : (mode == 3 ? ntt::SCALE_CONST : ntt::SCALE_NONE);
     int pre_mode = mode == 1 ? ntt::SCALE_GEO : ntt::SCALE_NONE;
     std::vector<u32> keep = in;
-    if (inplace) { transform(in.data(), in.data(), log_n, d, batch, n_valid, post_mode, ff::to_mont(c), G, pre_mode, G); out = in; in = keep; }
-    else transform(in.data(), out.data(), log_n, d, batch, n_valid, post_mode, ff::to_mont(c), G, pre_mode, G);
+    // extra mode combinations for the small kernel: pre-scale without padding, padding without pre-scale
+    if (log_n == 12 && mode == 1 && d == 1) n_valid = N;
+    if (log_n == 12 && mode == 3 && d == 1) pre_mode = ntt::SCALE_GEO;
+    auto run = [&](const u32 *i_, u32 *o_) {
+      if (log_n == 12) transform12(i_, o_, d, batch, n_valid, post_mode, ff::to_mont(c), G, pre_mode, G);
+      else transform(i_, o_, log_n, d, batch, n_valid, post_mode, ff::to_mont(c), G, pre_mode, G);
+    };
+    if (inplace) { run(in.data(), in.data()); out = in; in = keep; }
+    else run(in.data(), out.data());
     u64 root = ff::pow(3, (ff::P - 1) >> log_n); if (d) root = ff::inv((u32)root);
     for (u32 b = 0; b < batch; b++) {
       std::vector<u64> r(N);

@@ -279,3 +279,31 @@ def test_two_pass_big_tile_plans(oracle, S, monkeypatch):
     finally:
         c.close()
 
+
+
+def test_batched_small_transforms_2_12(ctx, oracle, S, monkeypatch):
+    """batches of >= 8 transforms of length 2^12 take the fused two-pass kernel (k_ntt_small12, ntt.cu): forward, inverse
+    (constant post-scale), in place, and -- through the LDE 2^10 -> 2^12 -- the zero-padded input with the geometric
+    post-scale before it; every transform checked, and the one-CTA-per-transform kernel must give the same bytes"""
+    log_n, batch = 12, 24
+    n = 1 << log_n
+    cols = rf(4242, n * batch)
+    src, dst = ctx.upload(cols), ctx.alloc(n * batch)
+    ctx.ntt_dev(src, dst, log_n, batch=batch)
+    got = dst.download().reshape(batch, n)
+    for c in range(batch):
+        assert np.array_equal(got[c], oracle.fast_eval_coset(cols.reshape(batch, n)[c], 1, log_n)), c
+    ctx.ntt_dev(dst, dst, log_n, batch=batch, inverse=True)            # in place, back to the input
+    assert np.array_equal(dst.download(), cols)
+    small = rf(77, 16 << 10).reshape(16, -1)
+    lde = ctx.lde(small, 2, 3)                                          # iNTT 16 x 2^10, then NTT 16 x 2^12 with padding
+    for c in range(16):
+        assert np.array_equal(lde[c], oracle.fast_lde(small[c], 10, 2, 3)), c
+    monkeypatch.setenv("STARK_NTT_SMALL_OFF", "1")
+    c2 = S.Context(0)
+    try:
+        d2 = c2.alloc(n * batch)
+        c2.ntt_dev(c2.upload(cols), d2, log_n, batch=batch)
+        assert np.array_equal(d2.download().reshape(batch, n), got)
+    finally:
+        c2.close()
