@@ -387,6 +387,11 @@ def run_ours(a):
     roof.update({"kernel": dom["kernel"], "launches_per_step": dk["launches_per_step"],
                  "avg_launch_ms": dom["ms"] / dom["launches"], "share_of_step": dk["share"],
                  "traffic": (instr or {}).get("kernels", {}).get(dom["kernel"], {}).get("dram_bytes_per_launch"),
+                 "traffic_launch": (lambda h: None if not h else {
+                     "what": "the largest launch of this kernel in the ncu --set full capture of this command",
+                     "hashes": h.get("hashes_in_launch"), "duration_ns": h.get("duration_ns"),
+                     "algorithmic_bytes": (h.get("hashes_in_launch") or 0) * h.get("algorithmic_bytes_per_hash", 0)})(
+                     (instr or {}).get("kernels", {}).get(dom["kernel"])),
                  "traffic_source": instr_src if instr else None,
                  "algorithmic_bytes_per_launch": dom["bytes"] / dom["launches"] if dom["launches"] else None})
     # the dominant HBM-bound kernel beside it
