@@ -65,7 +65,7 @@ struct stark_ctx {
   int keep_pdl;          // STARK_KEEP_PDL=1: programmatic dependent launch stays on inside multi-column pipelines (diagnosis)
   int no_prio;           // STARK_NO_PRIO=1: keep the latency chain on the caller's stream (diagnosis)
   int colpipe_serial;    // STARK_COLPIPE_SERIAL=1: no column / copy stream (everything on the context's stream; diagnosis)
-  int colpipe_group;     // columns per group when the trace is copied from the host (STARK_COLPIPE_GROUP, default 4)
+  int colpipe_group;     // columns per group when the trace is copied from the host (STARK_COLPIPE_GROUP, default 8)
   int climb_log;         // Merkle levels above 2^climb_log nodes get one launch each, the rest one climb launch (merkle.cu)
   char err[512];
   // optional per-kernel timing (stark_ctx_profile_begin/end): CUDA events around every launch, on ctx->stream

@@ -613,7 +613,9 @@ static void proof_layout(size_t n, u32 R, u32 nq, ProofLayout *L) {
 // Fri::prove (fri.rs:250-311) + ProofStream::serialize: proof bytes to host in one D2H copy
 static int fri_prove_dev(stark_ctx *ctx, const u32 *cw0, size_t n, size_t domain_length, u32 offset, u32 omega, u32 ef,
                          u32 nq, const u8 *transcript, size_t transcript_len, u8 *proof, size_t proof_cap,
-                         size_t *proof_len, u64 *top_indices) {
+                         size_t *proof_len, u64 *top_indices, bool sync = true) {
+  // sync == false: everything (incl. the D2H copies of the result) is queued and the CALLER synchronises the stream --
+  // the multi-column pipeline queues the latency chain first and its throughput work behind it
   if (n != domain_length)
     return stark_fail(ctx, STARK_ERR_ARG, "initial codeword length does not match domain length");  // fri.rs:256-260
   u32 R = 0;
@@ -670,7 +672,7 @@ static int fri_prove_dev(stark_ctx *ctx, const u32 *cw0, size_t n, size_t domain
     rc = stark_fail(ctx, STARK_ERR_CUDA, "D2H copy failed");
   dev_free(ctx, d_proof), dev_free(ctx, d_seed);
   fri_state_free(s);
-  if (rc == STARK_OK) {
+  if (rc == STARK_OK && sync) {
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) rc = stark_fail(ctx, STARK_ERR_CUDA, "prove failed: %s", cudaGetErrorString(e));
   }
@@ -1218,8 +1220,14 @@ static int prove_trace_pipeline(stark_ctx *ctx, const uint64_t *host_cols, u32 *
       rc = column_pipe_copy(ctx, &cp, host_cols + (size_t)groups[gi].first * n, (size_t)groups[gi].first * n,
                             n * groups[gi].second, true, &ev[1 + gi]);
   }
-  // column 0 on the context's stream
+  // column 0 and the whole latency chain are QUEUED FIRST (no host synchronisation inside): the ~60 launches of the
+  // chain are on the critical path, the ~25 launches per column group are not -- issued in the other order the chain
+  // started half a millisecond of host launch time late (a constant 0.9 ms between the host-input and the
+  // device-resident call at every group size, profiles/r2h_bench_g*.json)
   if (rc == STARK_OK) rc = column_pipe_group(ctx, &cp, ev[0], cols_dev, lde, 0, 1, log_n, log_blowup, offset, true, tree0);
+  const u32 omega = ff::pow(ff::GEN, (ff::P - 1) >> (log_n + log_blowup));  // prim_nth_root(N), ff.rs:215-223
+  if (rc == STARK_OK)
+    rc = fri_prove_dev(ctx, lde, N, N, offset, omega, 1u << log_blowup, nq, nullptr, 0, proof, proof_cap, proof_len, nullptr, false);
   // the other columns on the column stream
   if (rc == STARK_OK) {
     column_pipe_enter(ctx, &cp);
@@ -1227,9 +1235,6 @@ static int prove_trace_pipeline(stark_ctx *ctx, const uint64_t *host_cols, u32 *
       rc = column_pipe_group(ctx, &cp, ev[1 + gi], cols_dev, lde, groups[gi].first, groups[gi].second, log_n, log_blowup, offset, true, true);
     column_pipe_leave(ctx, &cp);
   }
-  const u32 omega = ff::pow(ff::GEN, (ff::P - 1) >> (log_n + log_blowup));  // prim_nth_root(N), ff.rs:215-223
-  if (rc == STARK_OK)
-    rc = fri_prove_dev(ctx, lde, N, N, offset, omega, 1u << log_blowup, nq, nullptr, 0, proof, proof_cap, proof_len, nullptr);
   column_pipe_join(ctx, &cp);
   // roots: d_roots holds [column 0 if tree0] followed by columns 1..
   const u32 first_col = tree0 ? 0u : 1u;
@@ -1237,8 +1242,8 @@ static int prove_trace_pipeline(stark_ctx *ctx, const uint64_t *host_cols, u32 *
       cudaMemcpyAsync(column_roots + 32 * first_col, cp.d_roots, 32 * (size_t)cp.n_roots, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
     rc = stark_fail(ctx, STARK_ERR_CUDA, "D2H copy failed");
   if (rc == STARK_OK && host_cols) rc = upload_flag_fetch(ctx);
-  if ((cp.n_roots || host_cols) && cudaStreamSynchronize(ctx->stream) != cudaSuccess && rc == STARK_OK)
-    rc = stark_fail(ctx, STARK_ERR_CUDA, "column commitments failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && rc == STARK_OK)
+    rc = stark_fail(ctx, STARK_ERR_CUDA, "prove failed: %s", cudaGetErrorString(cudaGetLastError()));
   if (rc == STARK_OK && column_roots && !tree0) memcpy(column_roots, proof + 1, 32);  // first object = root of column 0
   if (rc == STARK_OK && host_cols) rc = upload_u64_check(ctx);
   column_pipe_free(ctx, &cp);
@@ -1264,6 +1269,9 @@ struct MgTraceRank {
   stark_buf *in = nullptr;       // host-input variant: this rank's columns on the device
   std::vector<u32> owned;        // global indices of the committed columns
   u32 n_my = 0;
+  std::vector<std::pair<u32, u32>> groups;   // the column groups, queued after the chain
+  std::vector<cudaEvent_t> ev;
+  u32 *cols_dev = nullptr;
 };
 
 static int mg_prove_trace_impl(stark_mgpu *const *ranks, int n_here, const uint64_t *host_cols, const stark_buf *const *my_cols,
@@ -1324,20 +1332,25 @@ static int mg_prove_trace_impl(stark_mgpu *const *ranks, int n_here, const uint6
     }
     if (rc == STARK_OK)
       rc = column_pipe_group(ctx, &t.cp, ev[0], cols_dev, t.lde, 0, 1, log_n, log_blowup, (u32)offset, true, tree0);
-    if (rc == STARK_OK) {
-      column_pipe_enter(ctx, &t.cp);
-      for (size_t gi = 0; gi < groups.size() && rc == STARK_OK; gi++)
-        rc = column_pipe_group(ctx, &t.cp, ev[1 + gi], cols_dev, t.lde, groups[gi].first, groups[gi].second, log_n, log_blowup,
-                               (u32)offset, true, true);
-      column_pipe_leave(ctx, &t.cp);
-    }
+    t.groups = groups, t.ev = ev, t.cols_dev = cols_dev;
     if (rc == STARK_OK)
       rc = P[k].begin(m, t.lde, N, N, (u32)offset, omega, 1u << log_blowup, nq, nullptr, 0, proof_cap, proof_len);
     else
       mg_begin_op(m);   // keep the operation count in step with the ranks that did begin
   }
-  // phase 2: the sharded Fri::prove on column 0
+  // phase 2: the sharded Fri::prove on column 0 -- queued BEFORE the column groups (see prove_trace_pipeline)
   if (rc == STARK_OK) rc = mg_prove_run(P.data(), n_here);
+  for (int k = 0; k < n_here && rc == STARK_OK; k++) {
+    stark_mgpu *m = ranks[k];
+    stark_ctx *ctx = m->ctx;
+    mg_use(m);
+    MgTraceRank &t = T[k];
+    column_pipe_enter(ctx, &t.cp);
+    for (size_t gi = 0; gi < t.groups.size() && rc == STARK_OK; gi++)
+      rc = column_pipe_group(ctx, &t.cp, t.ev[1 + gi], t.cols_dev, t.lde, t.groups[gi].first, t.groups[gi].second, log_n, log_blowup,
+                             (u32)offset, true, true);
+    column_pipe_leave(ctx, &t.cp);
+  }
   // phase 3: the column roots into every rank's table, then the barrier that ends the operation
   for (int k = 0; k < n_here && rc == STARK_OK; k++) {
     stark_mgpu *m = ranks[k];
