@@ -1272,6 +1272,8 @@ struct MgTraceRank {
   std::vector<std::pair<u32, u32>> groups;   // the column groups, queued after the chain
   std::vector<cudaEvent_t> ev;
   u32 *cols_dev = nullptr;
+  bool bcast0 = false;             // column 0 came through the window: its canonical flag travels with it
+  u32 bcast_flag = 0;
 };
 
 static int mg_prove_trace_impl(stark_mgpu *const *ranks, int n_here, const uint64_t *host_cols, const stark_buf *const *my_cols,
@@ -1323,15 +1325,34 @@ static int mg_prove_trace_impl(stark_mgpu *const *ranks, int n_here, const uint6
     if (rc == STARK_OK) rc = column_pipe_begin(ctx, &t.cp, tree0 ? t.n_my : t.n_my - 1, N);
     const auto groups = column_groups(t.n_my, host_cols != nullptr, (u32)ctx->colpipe_group);
     std::vector<cudaEvent_t> ev(1 + groups.size(), nullptr);
+    // Column 0 is needed by every rank.  From the host it is copied ONCE, by rank 0, and broadcast over NVLink
+    // (mg_bcast_column): with all ranks copying at the same time the host links are the scarce resource (8 ranks x 3
+    // columns took 2.5x as long per byte as one rank alone), and column 0 heads everybody's critical path.
+    const bool bcast0 = host_cols && m->world > 1 && n % 4 == 0 && n <= m->L.arena_elems / 2 && !ctx->no_bcast0;
     if (host_cols && rc == STARK_OK) {
-      rc = column_pipe_copy(ctx, &t.cp, host_cols, 0, n, true, &ev[0]);
+      if (!bcast0 || m->rank == 0) rc = column_pipe_copy(ctx, &t.cp, host_cols, 0, n, true, &ev[0]);
       for (size_t gi = 0; gi < groups.size() && rc == STARK_OK; gi++)
         for (u32 i = groups[gi].first; i < groups[gi].first + groups[gi].second && rc == STARK_OK; i++)
           rc = column_pipe_copy(ctx, &t.cp, host_cols + (size_t)t.owned[i - 1] * n, (size_t)i * n, n,
                                 i + 1 == groups[gi].first + groups[gi].second, &ev[1 + gi]);
     }
-    if (rc == STARK_OK)
+    if (rc == STARK_OK && bcast0) {
+      // rank 0: wait for its copy, narrow, store the column into every window, raise the flag; the others: wait for it.
+      // Every rank then runs the LDE of column 0 out of its own window.
+      if (m->rank == 0) {
+        if (ev[0] && cudaStreamWaitEvent(ctx->stream, ev[0], 0) != cudaSuccess) rc = stark_fail(ctx, STARK_ERR_CUDA, "stream wait failed");
+        if (rc == STARK_OK) rc = narrow_dev(ctx, t.cp.staging, n, cols_dev);
+      }
+      if (rc == STARK_OK) rc = mg_bcast_column(m, 0, cols_dev, n, mg_epoch(m, MG_MAX_ROUNDS + 2));
+      u64 *staging = t.cp.staging;
+      t.cp.staging = nullptr;     // column_pipe_group: no narrowing, the column is already u32
+      if (rc == STARK_OK)
+        rc = column_pipe_group(ctx, &t.cp, nullptr, mg_bcast_ptr(m, m->rank), t.lde, 0, 1, log_n, log_blowup, (u32)offset, true, tree0);
+      t.cp.staging = staging;
+      t.bcast0 = true;
+    } else if (rc == STARK_OK) {
       rc = column_pipe_group(ctx, &t.cp, ev[0], cols_dev, t.lde, 0, 1, log_n, log_blowup, (u32)offset, true, tree0);
+    }
     t.groups = groups, t.ev = ev, t.cols_dev = cols_dev;
     if (rc == STARK_OK)
       rc = P[k].begin(m, t.lde, N, N, (u32)offset, omega, 1u << log_blowup, nq, nullptr, 0, proof_cap, proof_len);
@@ -1369,6 +1390,9 @@ static int mg_prove_trace_impl(stark_mgpu *const *ranks, int n_here, const uint6
     stark_ctx *ctx = m->ctx;
     mg_use(m);
     if (rc == STARK_OK) rc = P[k].download(proofs[k], nullptr);
+    if (rc == STARK_OK && T[k].bcast0 &&
+        cudaMemcpyAsync(&T[k].bcast_flag, mg_bcast_ptr(m, m->rank) + n, 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+      rc = stark_fail(ctx, STARK_ERR_CUDA, "D2H copy failed");
     if (rc == STARK_OK && column_roots && column_roots[k] &&
         cudaMemcpyAsync(column_roots[k], mg_colroots(m, m->rank), 32 * (size_t)n_cols, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
       rc = stark_fail(ctx, STARK_ERR_CUDA, "D2H copy failed");
@@ -1381,6 +1405,8 @@ static int mg_prove_trace_impl(stark_mgpu *const *ranks, int n_here, const uint6
     if (rc == STARK_OK) rc = e;
     if (rc == STARK_OK && fri_rounds > 0 && column_roots && column_roots[k]) memcpy(column_roots[k], proofs[k] + 1, 32);  // root of column 0
     if (rc == STARK_OK && host_cols) rc = upload_u64_check(ctx);
+    if (rc == STARK_OK && T[k].bcast0 && T[k].bcast_flag)
+      rc = stark_fail(ctx, STARK_ERR_ARG, "non-canonical field element (value >= p) in input");
     P[k].release();
     column_pipe_free(ctx, &T[k].cp);
     dev_free(ctx, T[k].lde);

@@ -81,6 +81,48 @@ __global__ void k_mg_barrier(const __grid_constant__ BarrierArgs A) {
   if (A.mode != MG_X_SIGNAL) mg_wait_flag(A.flag_local + t, A.epoch, A.err_local);
 }
 
+// column broadcast (mg_bcast_column): 128-bit loads, one 128-bit store per peer; the word after the column carries the
+// root's canonical-input flag (api.cu k_narrow) so that every rank rejects a non-canonical column, as the root does
+struct BcastArgs {
+  int world, rank;
+  u32 *dst[MG_MAX_RANKS];
+  const u32 *src;
+  const u32 *flag_src;
+  size_t n;     // multiple of 4
+};
+__global__ void __launch_bounds__(256) k_mg_bcast(const __grid_constant__ BcastArgs A) {
+  pdl_entry();
+  const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
+  for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < A.n; i += stride) {
+    const uint4 v = *reinterpret_cast<const uint4 *>(A.src + i);
+#pragma unroll 1
+    for (int g = 0; g < A.world; g++) *reinterpret_cast<uint4 *>(A.dst[g] + i) = v;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const u32 f = A.flag_src ? *A.flag_src : 0u;
+    for (int g = 0; g < A.world; g++) A.dst[g][A.n] = f;
+  }
+  __threadfence_system();
+}
+// one rank raises flags[kind][rank] on every peer / every rank waits for ONE rank's flag
+struct SignalArgs {
+  int world, rank, from;
+  u32 epoch;
+  u32 *flag_peer[MG_MAX_RANKS];
+  const u32 *flag_local;
+  u32 *err_local;
+};
+__global__ void k_mg_signal_from(const __grid_constant__ SignalArgs A) {
+  pdl_entry();
+  const u32 t = threadIdx.x;
+  if (A.rank == A.from) {
+    __threadfence_system();
+    if (t < (u32)A.world) mg_st_release_sys(A.flag_peer[t] + A.rank, A.epoch);
+  } else if (t == 0) {
+    mg_wait_flag(A.flag_local + A.from, A.epoch, A.err_local);
+  }
+}
+
 // entries of `src` (32 bytes each) into slot idx[i] of every rank's column-root table
 struct PutRootsArgs {
   int world;
@@ -138,6 +180,25 @@ int mg_all_gather(stark_mgpu *m, const void *send_dev, void *recv_dev, size_t by
   m->bytes_sent += bytes * (size_t)(m->world - 1);
   return STARK_OK;
 }
+int mg_bcast_column(stark_mgpu *m, int root, const u32 *src, size_t n, u32 epoch) {
+  if (n % 4 || n > m->L.arena_elems / 2) return stark_fail(m->ctx, STARK_ERR_ARG, "column does not fit the group's window");
+  if (m->rank == root) {
+    BcastArgs A;
+    memset(&A, 0, sizeof A);
+    A.world = m->world, A.rank = m->rank, A.src = src, A.n = n, A.flag_src = m->ctx->flag + 2;
+    for (int g = 0; g < m->world; g++) A.dst[g] = mg_bcast_ptr(m, g);
+    size_t blocks = (n / 4 + 255) / 256, cap = (size_t)m->ctx->sm_count * 4;
+    LAUNCH_PDL(m->ctx, "mg_bcast", 4ull * n * m->world, k_mg_bcast, (u32)(blocks < cap ? blocks : cap), 256, A);
+    m->bytes_sent += 4ull * n * (size_t)(m->world - 1);
+  }
+  SignalArgs S;
+  memset(&S, 0, sizeof S);
+  S.world = m->world, S.rank = m->rank, S.from = root, S.epoch = epoch;
+  for (int g = 0; g < m->world; g++) S.flag_peer[g] = mg_flags(m, g, 2);
+  S.flag_local = mg_flags(m, m->rank, 2), S.err_local = reinterpret_cast<u32 *>(m->win + m->L.err);
+  LAUNCH_PDL(m->ctx, "mg_signal", 0, k_mg_signal_from, 1u, 32, S);
+  return STARK_OK;
+}
 int mg_put_roots(stark_mgpu *m, const u8 *src_dev, const u32 *idx, u32 n) {
   for (u32 i0 = 0; i0 < n; i0 += 64) {
     PutRootsArgs A;
@@ -169,6 +230,7 @@ static void layout(MgLayout *L, size_t max_codeword) {
   L->proof = off, off = up(off + L->proof_cap);
   L->arena_elems = max_codeword < 1024 ? 1024 : max_codeword;
   L->arena = off, off = up(off + 4 * L->arena_elems);
+  L->bcast = off, off = up(off + 4 * (L->arena_elems / 2) + 256);   // a trace column (<= max_codeword / 2 rows) + flag word
   L->total = off;
 }
 

@@ -31,6 +31,7 @@ struct MgLayout {
   size_t colroots;   // u8  [max_cols][32]: column / group roots of the current operation
   size_t proof;      // u8  [proof_cap]: ProofStream::serialize bytes, assembled by all ranks
   size_t arena;      // u32 [arena_elems]: replicas of the folded codewords
+  size_t bcast;      // u32 [arena_elems / 2] + one flag word: a column one rank uploaded for everybody (mg_bcast_column)
   size_t total;
   size_t max_cols, proof_cap, arena_elems;
 };
@@ -84,6 +85,11 @@ int mg_barrier(stark_mgpu *m, int kind, u32 epoch);          // signal + wait in
 int mg_check_err(stark_mgpu *m);
 // ncclAllGather of `bytes` per rank (device buffers) on the context's stream; MG_LOCAL groups copy peer to peer instead
 int mg_all_gather(stark_mgpu *m, const void *send_dev, void *recv_dev, size_t bytes);
+// Column broadcast: rank `root` stores n u32 values (src, on its device) and its canonical-input flag into every rank's
+// bcast region and raises flags[2]; the other ranks wait for that flag.  PCIe is the scarce link when every rank copies
+// from the host at once: a column all ranks need is uploaded by ONE of them and travels on over NVLink.
+int mg_bcast_column(stark_mgpu *m, int root, const u32 *src, size_t n, u32 epoch);
+static inline u32 *mg_bcast_ptr(const stark_mgpu *m, int g) { return reinterpret_cast<u32 *>(m->peer[g] + m->L.bcast); }
 // this rank's n roots (device, 32 bytes each) into entries idx[] of EVERY rank's column-root table (peer stores).  The
 // table is double-buffered by operation parity: a rank may be one operation ahead of a peer that is still copying the
 // previous table to its host.

@@ -243,3 +243,25 @@ def test_process_group_nccl_ipc(world):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count("MGPU_WORKER_OK") == world, out.stdout[-3000:]
+
+
+def test_virtual_prove_trace_rejects_non_canonical_column0(ctx, S, oracle):
+    """column 0 reaches the other ranks through rank 0's window (one host copy, NVLink broadcast): a value >= p in it must
+    fail on EVERY rank like it does on one GPU; without the broadcast (STARK_NO_BCAST0 path = world 1) the same text"""
+    cols = np.stack([oracle.splitmix64(5 + c, 1 << 10) for c in range(3)])
+    cols[0, 77] = S.P
+    with pytest.raises(S.StarkPanic, match="non-canonical field element"):
+        ctx.prove_trace(cols, 2, 3, 16)
+    g, ctxs = virtual_group(S, ctx, 2, 1 << 12)
+    try:
+        with pytest.raises(S.StarkPanic, match="non-canonical field element"):
+            g.prove_trace(cols, 2, 3, 16)
+        cols[0, 77] = 1
+        cols[2, 5] = S.P + 3                      # a column only rank 0 or rank 1 owns
+        with pytest.raises(S.StarkPanic, match="non-canonical field element"):
+            g.prove_trace(cols, 2, 3, 16)
+        cols[2, 5] = 3
+        ref = oracle.fri_prove(oracle.fast_lde(cols[0], 10, 2, 3), oracle.ff_prim_nth_root(1 << 12), 3, 4, 16)
+        assert all(p == ref["proof"] for _, p in g.prove_trace(cols, 2, 3, 16))     # and the group still works
+    finally:
+        close_group(g, ctxs)
