@@ -256,7 +256,9 @@ def run_ours(a):
         dev_cols = ctx.upload_ptr(stage.data_ptr(), len(mine) * n)
         step_dev = lambda cols=a.cols: group.prove_trace_dev([dev_cols], cols, a.log_n, a.log_blowup, 3, a.nq, [roots], [proof])
         step_e2e = lambda: group.prove_trace_ptr(host.data_ptr(), a.cols, a.log_n, a.log_blowup, 3, a.nq, [roots], [proof])
-        h2d_mine = len(mine) * n * 8
+        # column 0 is copied from the host by rank 0 only and broadcast over NVLink (stark_mgpu_prove_trace)
+        bcast0 = not os.environ.get("STARK_NO_BCAST0")
+        h2d_mine = (len(mine) - (1 if (rank and bcast0) else 0)) * n * 8
     else:
         mine = list(range(a.cols))
         dev_cols = ctx.upload_ptr(host.data_ptr(), a.cols * n)

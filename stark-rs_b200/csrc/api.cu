@@ -239,6 +239,7 @@ static int ctx_create(int device, cudaStream_t borrowed, bool borrow, stark_ctx 
   // shared memory): the tuning knob is clamped to the range the kernel supports
   ctx->colpipe_serial = getenv("STARK_COLPIPE_SERIAL") && atoi(getenv("STARK_COLPIPE_SERIAL")) != 0;
   ctx->keep_pdl = getenv("STARK_KEEP_PDL") && atoi(getenv("STARK_KEEP_PDL")) != 0;
+  ctx->trace_pipe = getenv("STARK_TRACE_PIPE") && atoi(getenv("STARK_TRACE_PIPE")) != 0;
   ctx->no_bcast0 = getenv("STARK_NO_BCAST0") && atoi(getenv("STARK_NO_BCAST0")) != 0;
   ctx->no_prio = getenv("STARK_NO_PRIO") && atoi(getenv("STARK_NO_PRIO")) != 0;
   ctx->colpipe_group = 8;

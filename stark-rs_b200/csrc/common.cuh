@@ -63,6 +63,7 @@ struct stark_ctx {
   int ntt_l2_persist;    // STARK_NTT_L2_PERSIST=1: mark each pass's destination as L2-persisting (experiment, default off)
   int l2_persist_ready;
   int keep_pdl;          // STARK_KEEP_PDL=1: programmatic dependent launch stays on inside multi-column pipelines (diagnosis)
+  int trace_pipe;        // STARK_TRACE_PIPE=1: print device timestamps of the config-3 pipeline's milestones (diagnosis)
   int no_bcast0;         // STARK_NO_BCAST0=1: every rank of a group copies column 0 from the host itself (comparison)
   int no_prio;           // STARK_NO_PRIO=1: keep the latency chain on the caller's stream (diagnosis)
   int colpipe_serial;    // STARK_COLPIPE_SERIAL=1: no column / copy stream (everything on the context's stream; diagnosis)

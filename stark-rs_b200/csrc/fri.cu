@@ -1220,30 +1220,55 @@ static int prove_trace_pipeline(stark_ctx *ctx, const uint64_t *host_cols, u32 *
       rc = column_pipe_copy(ctx, &cp, host_cols + (size_t)groups[gi].first * n, (size_t)groups[gi].first * n,
                             n * groups[gi].second, true, &ev[1 + gi]);
   }
+  // STARK_TRACE_PIPE=1: device timestamps of the pipeline's milestones (diagnosis; printed to stderr after the call)
+  std::vector<std::pair<const char *, cudaEvent_t>> marks;
+  auto mark = [&](const char *what, cudaStream_t st) {
+    if (!ctx->trace_pipe) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    marks.push_back({what, e});
+  };
+  mark("start", ctx->stream);
+  if (host_cols && cp.forked) mark("all copies done", ctx->side[COPY_STREAM]);
   // column 0 and the whole latency chain are QUEUED FIRST (no host synchronisation inside): the ~60 launches of the
   // chain are on the critical path, the ~25 launches per column group are not -- issued in the other order the chain
   // started half a millisecond of host launch time late (a constant 0.9 ms between the host-input and the
   // device-resident call at every group size, profiles/r2h_bench_g*.json)
   if (rc == STARK_OK) rc = column_pipe_group(ctx, &cp, ev[0], cols_dev, lde, 0, 1, log_n, log_blowup, offset, true, tree0);
   const u32 omega = ff::pow(ff::GEN, (ff::P - 1) >> (log_n + log_blowup));  // prim_nth_root(N), ff.rs:215-223
+  mark("column 0 LDE done", ctx->stream);
   if (rc == STARK_OK)
     rc = fri_prove_dev(ctx, lde, N, N, offset, omega, 1u << log_blowup, nq, nullptr, 0, proof, proof_cap, proof_len, nullptr, false);
+  mark("chain done", ctx->stream);
   // the other columns on the column stream
   if (rc == STARK_OK) {
     column_pipe_enter(ctx, &cp);
-    for (size_t gi = 0; gi < groups.size() && rc == STARK_OK; gi++)
+    for (size_t gi = 0; gi < groups.size() && rc == STARK_OK; gi++) {
       rc = column_pipe_group(ctx, &cp, ev[1 + gi], cols_dev, lde, groups[gi].first, groups[gi].second, log_n, log_blowup, offset, true, true);
+      mark("column group done", ctx->stream);
+    }
     column_pipe_leave(ctx, &cp);
   }
   column_pipe_join(ctx, &cp);
+  mark("joined", ctx->stream);
   // roots: d_roots holds [column 0 if tree0] followed by columns 1..
   const u32 first_col = tree0 ? 0u : 1u;
   if (rc == STARK_OK && column_roots && cp.n_roots &&
       cudaMemcpyAsync(column_roots + 32 * first_col, cp.d_roots, 32 * (size_t)cp.n_roots, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
     rc = stark_fail(ctx, STARK_ERR_CUDA, "D2H copy failed");
   if (rc == STARK_OK && host_cols) rc = upload_flag_fetch(ctx);
+  mark("end", ctx->stream);
   if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && rc == STARK_OK)
     rc = stark_fail(ctx, STARK_ERR_CUDA, "prove failed: %s", cudaGetErrorString(cudaGetLastError()));
+  for (size_t i = 0; i < marks.size(); i++) {
+    float ms = 0;
+    cudaEventSynchronize(marks[i].second);
+    cudaEventElapsedTime(&ms, marks[0].second, marks[i].second);
+    fprintf(stderr, "[pipe] %-22s %8.3f ms\n", marks[i].first, ms);
+    if (i) cudaEventDestroy(marks[i].second);
+  }
+  if (!marks.empty()) cudaEventDestroy(marks[0].second);
   if (rc == STARK_OK && column_roots && !tree0) memcpy(column_roots, proof + 1, 32);  // first object = root of column 0
   if (rc == STARK_OK && host_cols) rc = upload_u64_check(ctx);
   column_pipe_free(ctx, &cp);
@@ -1296,6 +1321,15 @@ static int mg_prove_trace_impl(stark_mgpu *const *ranks, int n_here, const uint6
   std::vector<MgProve> P(n_here);
   std::vector<PrioScope> prio(n_here);
   int rc = STARK_OK;
+  // STARK_TRACE_PIPE=1: device timestamps of the first driven rank's milestones (diagnosis)
+  std::vector<std::pair<const char *, cudaEvent_t>> marks;
+  auto mark = [&](int k, const char *what, cudaStream_t st) {
+    if (k != 0 || !ranks[0]->ctx->trace_pipe) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    marks.push_back({what, e});
+  };
   // phase 1 (no exchange): upload / LDE of column 0 and the owned columns, column trees on the side stream
   for (int k = 0; k < n_here && rc == STARK_OK; k++) {
     stark_mgpu *m = ranks[k];
@@ -1307,6 +1341,7 @@ static int mg_prove_trace_impl(stark_mgpu *const *ranks, int n_here, const uint6
     t.n_my = 1 + (u32)t.owned.size();
     // ranks that share a stream (virtual ranks in lock step) stay on it: their order IS the stream order
     if (!m->lockstep && n_cols > 1) prio[k].enter(ctx);
+    mark(k, "start", ctx->stream);
     u32 *cols_dev = nullptr;
     if (host_cols) {
       rc = stark_buf_alloc(ctx, n * t.n_my, &t.in);
@@ -1329,12 +1364,15 @@ static int mg_prove_trace_impl(stark_mgpu *const *ranks, int n_here, const uint6
     // (mg_bcast_column): with all ranks copying at the same time the host links are the scarce resource (8 ranks x 3
     // columns took 2.5x as long per byte as one rank alone), and column 0 heads everybody's critical path.
     const bool bcast0 = host_cols && m->world > 1 && n % 4 == 0 && n <= m->L.arena_elems / 2 && !ctx->no_bcast0;
-    if (host_cols && rc == STARK_OK) {
-      if (!bcast0 || m->rank == 0) rc = column_pipe_copy(ctx, &t.cp, host_cols, 0, n, true, &ev[0]);
+    auto copy_owned = [&]() {
       for (size_t gi = 0; gi < groups.size() && rc == STARK_OK; gi++)
         for (u32 i = groups[gi].first; i < groups[gi].first + groups[gi].second && rc == STARK_OK; i++)
           rc = column_pipe_copy(ctx, &t.cp, host_cols + (size_t)t.owned[i - 1] * n, (size_t)i * n, n,
                                 i + 1 == groups[gi].first + groups[gi].second, &ev[1 + gi]);
+    };
+    if (host_cols && rc == STARK_OK) {
+      if (!bcast0 || m->rank == 0) rc = column_pipe_copy(ctx, &t.cp, host_cols, 0, n, true, &ev[0]);
+      if (!bcast0) copy_owned();
     }
     if (rc == STARK_OK && bcast0) {
       // rank 0: wait for its copy, narrow, store the column into every window, raise the flag; the others: wait for it.
@@ -1343,7 +1381,20 @@ static int mg_prove_trace_impl(stark_mgpu *const *ranks, int n_here, const uint6
         if (ev[0] && cudaStreamWaitEvent(ctx->stream, ev[0], 0) != cudaSuccess) rc = stark_fail(ctx, STARK_ERR_CUDA, "stream wait failed");
         if (rc == STARK_OK) rc = narrow_dev(ctx, t.cp.staging, n, cols_dev);
       }
+      mark(k, "column 0 narrowed", ctx->stream);
       if (rc == STARK_OK) rc = mg_bcast_column(m, 0, cols_dev, n, mg_epoch(m, MG_MAX_ROUNDS + 2));
+      mark(k, "column 0 broadcast", ctx->stream);
+      // The host links are shared (8 ranks copying at once get 22-35 GB/s each instead of 53): the copies of the other
+      // columns start only once column 0 -- which heads every rank's critical path -- has arrived everywhere
+      if (rc == STARK_OK && t.cp.forked) {
+        cudaEvent_t arrived = nullptr;
+        if (cudaEventCreateWithFlags(&arrived, cudaEventDisableTiming) == cudaSuccess) {
+          t.cp.events.push_back(arrived);
+          cudaEventRecord(arrived, ctx->stream);
+          cudaStreamWaitEvent(ctx->side[COPY_STREAM], arrived, 0);
+        }
+      }
+      copy_owned();
       u64 *staging = t.cp.staging;
       t.cp.staging = nullptr;     // column_pipe_group: no narrowing, the column is already u32
       if (rc == STARK_OK)
@@ -1354,6 +1405,8 @@ static int mg_prove_trace_impl(stark_mgpu *const *ranks, int n_here, const uint6
       rc = column_pipe_group(ctx, &t.cp, ev[0], cols_dev, t.lde, 0, 1, log_n, log_blowup, (u32)offset, true, tree0);
     }
     t.groups = groups, t.ev = ev, t.cols_dev = cols_dev;
+    if (host_cols && t.cp.forked) mark(k, "all copies done", ctx->side[COPY_STREAM]);
+    mark(k, "column 0 LDE done", ctx->stream);
     if (rc == STARK_OK)
       rc = P[k].begin(m, t.lde, N, N, (u32)offset, omega, 1u << log_blowup, nq, nullptr, 0, proof_cap, proof_len);
     else
@@ -1361,15 +1414,18 @@ static int mg_prove_trace_impl(stark_mgpu *const *ranks, int n_here, const uint6
   }
   // phase 2: the sharded Fri::prove on column 0 -- queued BEFORE the column groups (see prove_trace_pipeline)
   if (rc == STARK_OK) rc = mg_prove_run(P.data(), n_here);
+  mark(0, "chain done", ranks[0]->ctx->stream);
   for (int k = 0; k < n_here && rc == STARK_OK; k++) {
     stark_mgpu *m = ranks[k];
     stark_ctx *ctx = m->ctx;
     mg_use(m);
     MgTraceRank &t = T[k];
     column_pipe_enter(ctx, &t.cp);
-    for (size_t gi = 0; gi < t.groups.size() && rc == STARK_OK; gi++)
+    for (size_t gi = 0; gi < t.groups.size() && rc == STARK_OK; gi++) {
       rc = column_pipe_group(ctx, &t.cp, t.ev[1 + gi], t.cols_dev, t.lde, t.groups[gi].first, t.groups[gi].second, log_n, log_blowup,
                              (u32)offset, true, true);
+      mark(k, "column group done", ctx->stream);
+    }
     column_pipe_leave(ctx, &t.cp);
   }
   // phase 3: the column roots into every rank's table, then the barrier that ends the operation
@@ -1385,6 +1441,7 @@ static int mg_prove_trace_impl(stark_mgpu *const *ranks, int n_here, const uint6
     if (rc == STARK_OK && host_cols) rc = upload_flag_fetch(m->ctx);
   }
   if (rc == STARK_OK) rc = mg_prove_finish(P.data(), n_here);
+  mark(0, "final barrier done", ranks[0]->ctx->stream);
   for (int k = 0; k < n_here; k++) {
     stark_mgpu *m = ranks[k];
     stark_ctx *ctx = m->ctx;
@@ -1403,6 +1460,16 @@ static int mg_prove_trace_impl(stark_mgpu *const *ranks, int n_here, const uint6
     mg_use(m);
     const int e = mg_check_err(m);   // synchronises the rank's stream
     if (rc == STARK_OK) rc = e;
+    if (k == 0 && !marks.empty()) {
+      for (size_t i = 0; i < marks.size(); i++) {
+        float ms = 0;
+        cudaEventSynchronize(marks[i].second);
+        cudaEventElapsedTime(&ms, marks[0].second, marks[i].second);
+        fprintf(stderr, "[pipe rank %d] %-22s %8.3f ms\n", m->rank, marks[i].first, ms);
+      }
+      for (auto &mk : marks) cudaEventDestroy(mk.second);
+      marks.clear();
+    }
     if (rc == STARK_OK && fri_rounds > 0 && column_roots && column_roots[k]) memcpy(column_roots[k], proofs[k] + 1, 32);  // root of column 0
     if (rc == STARK_OK && host_cols) rc = upload_u64_check(ctx);
     if (rc == STARK_OK && T[k].bcast0 && T[k].bcast_flag)
