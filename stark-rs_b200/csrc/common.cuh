@@ -43,14 +43,14 @@ struct stark_ctx {
   GeoCacheEntry geo[8];
   u64 geo_stamp;
   u32 *flag;       // device ints: [0], [2] validation flags; [4 .. 4 + 64): last-CTA tickets of the Merkle climb kernel for
-                   // launches on the context's stream, [68 .. 132): the same for work queued on a side stream
+                   // launches on the context's stream, [68 .. 132) / [132 .. 196): the same for the two column streams
   u32 *climb_counter;   // the tickets the next climb launch uses (one per tree of a batch): flag + 4, or flag + 68
   u32 *h_flag;     // pinned host mirror
   u64 launches;    // kernels launched through this context (bench.py "gpu_launches")
   // side streams for batched transforms larger than L2 (ntt.cu: column groups run all passes back to back, a few groups
   // in flight): created on first use
-  cudaStream_t side[4];
-  cudaEvent_t side_done[4], fork_ev;
+  cudaStream_t side[6];   // [0], [1]: NTT column groups; [2], [4]: the two column streams of the config-3 pipeline; [3]: copies
+  cudaEvent_t side_done[6], fork_ev;
   int n_side;            // streams created so far
   // the latency chain of a proof (column 0 -> LDE -> Fri::prove: ~50 short dependent kernels) runs on a stream of the
   // HIGHEST priority, so that its kernels are dispatched ahead of the pending CTAs of the throughput kernels the column
@@ -75,7 +75,7 @@ struct stark_ctx {
   struct ProfRec *prof;   // growing array
   size_t prof_n, prof_cap;
 };
-constexpr int FLAG_WORDS = 4 + 2 * 64, TICKET_MAIN = 4, TICKET_SIDE = 68;   // layout of stark_ctx::flag
+constexpr int FLAG_WORDS = 4 + 3 * 64, TICKET_MAIN = 4, TICKET_SIDE = 68, TICKET_SIDE2 = 132;   // layout of stark_ctx::flag
 struct ProfRec {
   const char *tag;
   u64 bytes;              // algorithmic HBM bytes of this launch, 0 if not meaningful
