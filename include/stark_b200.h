@@ -69,6 +69,7 @@ int stark_bench_mul_peak(stark_ctx *ctx, double *out4);
 /* dependent-hash latency (clock cycles per Hash::combine) of one warp alone on an SM, for the one-hash-per-thread,
  * two-per-thread and four-lanes-per-hash kernels forms (measurement only) */
 int stark_bench_hash_latency(stark_ctx *ctx, double *hs_cycles, double *hs2_cycles, double *hsq_cycles);
+int stark_bench_hash_latency_hso(stark_ctx *ctx, double *hso_cycles); /* eight lanes per hash (round 2) */
 const char *stark_last_error(void);
 const char *stark_version(void);
 

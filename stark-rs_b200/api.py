@@ -327,7 +327,9 @@ class Context:
     def hash_latency(self):
         a, b, c = C.c_double(), C.c_double(), C.c_double()
         _chk(lib().stark_bench_hash_latency(self.h, C.byref(a), C.byref(b), C.byref(c)))
-        return {"hs_cycles": a.value, "hs2_cycles": b.value, "hsq_cycles": c.value}
+        d = C.c_double()
+        _chk(lib().stark_bench_hash_latency_hso(self.h, C.byref(d)))
+        return {"hs_cycles": a.value, "hs2_cycles": b.value, "hsq_cycles": c.value, "hso_cycles": d.value}
 
     # ---- buffers
     def alloc(self, n):

@@ -515,3 +515,147 @@ __device__ __forceinline__ void combine(const uint8_t *left, const uint8_t *righ
 }
 }  // namespace hsq
 #endif
+
+// =====================================================================================================
+// hso -- ONE hash on EIGHT adjacent lanes (lane q holds state bytes 4q .. 4q+3), for the steps where the latency of one
+// hash is all that matters and most lanes of the CTA are idle anyway: the narrow levels of a Merkle climb (<= NT/8
+// parents), the Fiat-Shamir round.  Against hsq (four lanes, 2560 cycles per Hash::combine for a lone warp, which issues
+// its ~85 instructions per mix at ~2 cycles each -- dependency-bound, not issue-bound) it measures 2180 cycles
+// (stark_bench_hash_latency_hso): the ten mixes stay a chain of sbox -> linear layer -> byte totals -> one shuffle hop ->
+// prefix, ~140 cycles each however few bytes a lane holds; the gain is the absorb:
+//   * mix_state: half the bytes per lane.  sbox and the 4-byte linear group are lane-local; the neighbour add is the
+//     closed form of hsq (local prefix + 2 x the byte totals of the lower lanes - s[0] + s[4q]) with the seven lower
+//     totals fetched by independent shuffles, ONE hop.
+//   * absorb (hash.rs:15-20: byte i xors into byte i+7): hsq gathers the whole state into every lane and runs the 32
+//     serial steps redundantly (390 cycles).  The 32 steps are SEVEN independent chains (i mod 7) of at most five links:
+//     lane c takes chain c -- gather its five bytes (5 shuffles), five dependent links, the wrap-around of the last link
+//     into byte c+3 (1 shuffle), scatter back to the byte-block layout (8 shuffles).
+// The code is host+device inline over a lane-group interface W (W::q, W::shfl) so that tests/emul/hash_emul.cpp runs it
+// on eight host threads against the oracle; on the device W is hso::Dev (shuffles within the warp).
+namespace hso {
+using hs::u32;
+
+struct Oct {
+  u32 s[4];
+  u32 rc[4];      // round constants of this lane's bytes
+  u32 rc251[4];   // (rc * 251) & 0xff, folded into the next sbox multiply when the constants are still pending
+};
+HS_HD u32 pack4(u32 a, u32 b, u32 c, u32 d) {   // the four LOW bytes, little-endian
+  return hs2::prmt(hs2::prmt(a, b, 0x0040), hs2::prmt(c, d, 0x0040), 0x5410);
+}
+template <class W>
+HS_HD void init(const W &w, Oct &st) {
+  constexpr u32 pr[16] = HS_PRIMES;
+  constexpr u32 rc[32] = HS_RC;
+  const u32 q = w.q;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    // lane-dependent constants by selects (a lane-indexed constant load serialises per distinct address)
+    u32 p = 0, r = 0;
+#pragma unroll
+    for (int l = 0; l < 8; l++) {
+      if (q == (u32)l) p = pr[(4 * l + j) & 15], r = rc[4 * l + j];
+    }
+    st.s[j] = p, st.rc[j] = r, st.rc251[j] = (r * 251u) & 0xffu;
+  }
+}
+// mix_state (hash.rs:59-86) without its final round-constant add (left pending, as hs::mix_lazy)
+template <bool PENDING, class W>
+HS_HD void mix_lazy(const W &w, Oct &st) {
+  u32 *s = st.s;
+  const u32 q = w.q;
+#pragma unroll
+  for (int j = 0; j < 4; j++) s[j] = hs::rotl_lazy(s[j] * 251u + (PENDING ? st.rc251[j] : 0u), 1);
+  {
+    const u32 t0 = s[0], t1 = s[1], t2 = s[2], t3 = s[3];
+    const u32 x = t0 ^ t1 ^ t2 ^ t3;
+    s[0] = x ^ t2 ^ 0x63u, s[1] = x ^ t1 ^ 0x63u, s[2] = x ^ t3 ^ 0x63u, s[3] = x ^ t0 ^ 0x63u;
+  }
+  // neighbour add, closed form: with t[k] = s[k] + s[k+1], s'[i] = s[31] + sum_{k<=i} t[k] (i <= 30).  A lane's total of t
+  // telescopes to 2 T_q - s[4q] + s[4q+4] (T_q = its byte sum), so lane q's offset is
+  //   O_q = s[31] + 2 (T_0 + .. + T_{q-1}) - s[0] + s[4q]
+  const u32 e0 = s[0] + s[1];
+  const u32 T = e0 + (s[2] + s[3]);
+  const u32 s31 = w.shfl(s[3], 7u);          // old s[31]
+  const u32 z0 = w.shfl(s[0], 0u);           // s[0]
+  const u32 n0 = s31 + w.shfl(e0, 0u);       // s'[0] = s[31] + s[0] + s[1]
+  const u32 nxt0 = w.shfl(s[0], (q + 1u) & 7u);   // s[4q+4]
+  u32 a[7];
+#pragma unroll
+  for (int m = 0; m < 7; m++) {
+    const u32 tm = w.shfl(T, (u32)m);
+    a[m] = q > (u32)m ? tm : 0u;
+  }
+  const u32 lower = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + a[6]);   // a tree: three dependent adds, not seven
+  const u32 P0 = e0, P1 = P0 + (s[1] + s[2]), P2 = P1 + (s[2] + s[3]);
+  const u32 O = s31 + 2u * lower - z0 + s[0];
+  const u32 last = q == 7u ? s31 + n0 + (O + P2) : O + P2 + s[3] + nxt0;   // lane 7: s'[31] = s[31] + s'[0] + s'[30]
+  s[0] = O + P0, s[1] = O + P1, s[2] = O + P2, s[3] = last;
+}
+template <class W>
+HS_HD void settle(const W &, Oct &st) {
+#pragma unroll
+  for (int j = 0; j < 4; j++) st.s[j] += st.rc[j];
+}
+// absorb the 32-byte chunk at `msg` (hash.rs:14-21), then mix.  PENDING: round constants owed on entry.
+template <bool PENDING, class W>
+HS_HD void absorb_mix(const W &w, Oct &st, const uint8_t *msg) {
+  if (PENDING) settle(w, st);
+  u32 *s = st.s;
+  const u32 c = w.q;   // this lane's chain: positions c, c+7, .. (lane 7 computes an unused duplicate of a shifted chain)
+  const u32 word = pack4(s[0], s[1], s[2], s[3]);
+  u32 v[5];
+#pragma unroll
+  for (int j = 0; j < 5; j++) {
+    const u32 p = (c + 7u * (u32)j) & 31u;                 // positions past 31 (chains 4..6, j = 4) are computed and ignored
+    const u32 x = w.shfl(word, p >> 2) >> (8u * (p & 3u));   // state byte p (lazy: garbage above bit 7)
+    const u32 in = j ? x ^ v[j - 1] : x;                   // byte p was xored with v[p-7] by the link before
+    v[j] = hs::rotl_lazy(in + msg[p], 3);
+  }
+  // the links at positions 25..31 xor into positions 0..6 (after those were absorbed): position t receives v[t+25], the
+  // LAST element of chain (t+4) mod 7
+  const u32 lastv = c <= 3u ? v[4] : v[3];
+  const u32 src = c + 4u >= 7u ? c + 4u - 7u : c + 4u;
+  v[0] ^= w.shfl(lastv, c == 7u ? 0u : src);
+  // back to the byte-block layout: byte p = 4q + j is element p / 7 of chain p mod 7
+  const u32 A = pack4(v[0], v[1], v[2], v[3]), B = v[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const u32 p = 4u * w.q + (u32)j, idx = (p * 37u) >> 8, from = p - 7u * idx;
+    const u32 a = w.shfl(A, from), b = w.shfl(B, from);
+    s[j] = idx == 4u ? b : a >> (8u * idx);
+  }
+  mix_lazy<false>(w, st);
+}
+// Hash::combine (hash.rs:41-46) of the 32-byte hashes at `left` and `right`; lane q returns bytes 4q .. 4q+3 as one
+// little-endian word
+template <class W>
+HS_HD u32 combine(const W &w, const uint8_t *left, const uint8_t *right) {
+  Oct st;
+  init(w, st);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (int c = 0; c < 2; c++) {   // one copy of absorb + mix for both chunks (code size, see hs::combine)
+    if (c) settle(w, st);
+    absorb_mix<false>(w, st, c ? right : left);
+  }
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (int k = 0; k < 8; k++) mix_lazy<true>(w, st);
+  settle(w, st);
+  return pack4(st.s[0], st.s[1], st.s[2], st.s[3]);
+}
+#if defined(__CUDACC__)
+// the lane group on the device: eight adjacent lanes of a warp (ALL 32 lanes of the warp must execute the calls)
+struct Dev {
+  u32 q, base;
+  __device__ __forceinline__ Dev() {
+    const u32 lane = threadIdx.x & 31u;
+    q = lane & 7u, base = lane & ~7u;
+  }
+  __device__ __forceinline__ u32 shfl(u32 v, u32 src) const { return __shfl_sync(0xffffffffu, v, base + src); }
+};
+#endif
+}  // namespace hso

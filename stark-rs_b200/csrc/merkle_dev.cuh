@@ -21,6 +21,10 @@ __device__ __forceinline__ size_t level_off(size_t n, uint32_t l) { return 2 * n
 //   parents >  NT/4:   two parents per thread (hs2, ALU-pipe efficient)
 //   parents <= NT/4:   one parent per FOUR lanes (hsq): these steps are pure hash latency
 // sm: at least 16 cnt bytes.  Returns with the last computed level in sm (thread 0 can read the root there).
+// STARK_HSO=0 at compile time keeps the four-lane form everywhere (A/B measurement)
+#ifndef STARK_HSO
+#define STARK_HSO 1
+#endif
 #ifdef STARK_CLIMB_TIMING
 __device__ unsigned long long g_climb_clk[64];
 __device__ unsigned int g_climb_n;
@@ -41,7 +45,27 @@ __device__ __forceinline__ void cta_climb(uint8_t *nodes, size_t n, uint32_t lev
   for (uint32_t s = 0; s < levels && cur > 1; s++) {
     const uint32_t parents = cur >> 1;
     uint8_t *dst = nodes + 32 * (level_off(n, level_in + s + 1) + (first >> (s + 1)));
-    if (4 * parents <= (uint32_t)NT) {
+    if (parents <= 16 && 8 * parents <= (uint32_t)NT && STARK_HSO) {
+      // octet path (hso): parent p on lanes 8p .. 8p+7, four output bytes per lane; whole warps without a parent skip.
+      // Only while the live warps are at most one per scheduler (<= 128 lanes): a lone warp runs hso in 2180 cycles
+      // against 2560 for hsq, but two hso warps sharing a scheduler are no faster than one hsq warp (measured: the
+      // 64-parent step of the FRI tail got slower with it).
+      const uint32_t p = t >> 3, q = t & 7u;
+      const bool warp_on = (t & ~31u) < 8 * parents, act = p < parents;
+      uint32_t o = 0;
+      if (warp_on) {
+        const uint32_t pc = act ? p : 0;   // idle octets of a live warp hash parent 0 again (shuffles need all lanes)
+        const hso::Dev w;
+        o = hso::combine(w, src + 64 * pc, src + 64 * pc + 32);
+      }
+      CLIMB_TICK();
+      __syncthreads();
+      if (act) {
+        *reinterpret_cast<uint32_t *>(sm + 32 * p + 4 * q) = o;
+        *reinterpret_cast<uint32_t *>(dst + 32 * p + 4 * q) = o;
+      }
+      __syncthreads();
+    } else if (4 * parents <= (uint32_t)NT) {
       // quad path: parent p on lanes 4p .. 4p+3; whole warps without a parent skip (warp-uniform)
       const uint32_t p = t >> 2, q = t & 3u;
       const bool warp_on = (t & ~31u) < 4 * parents, act = p < parents;

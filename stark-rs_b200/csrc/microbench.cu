@@ -142,18 +142,41 @@ __global__ void k_hash_latency(int mode, int K, unsigned long long *cycles, u32 
       u32 oa[8], ob[8];
       hs2::combine2(x, x, y, y, oa, ob, blockDim.y);
       for (int i = 0; i < 8; i++) x[i] = oa[i], y[i] = ob[i];
-    } else {
+    } else if (mode == 2) {
       u32 o0, o1;
       hsq::combine(mine, mine, o0, o1);
       __syncwarp();
       *reinterpret_cast<uint2 *>(mine + 8 * q) = make_uint2(o0, o1);
       __syncwarp();
       x[0] = o0;
+    } else {
+      // eight lanes per hash (hso): octet o of the warp uses scratch hash o
+      const hso::Dev w;
+      u8 *mine8 = buf + 32 * (threadIdx.x >> 3);
+      const u32 o = hso::combine(w, mine8, mine8);
+      __syncwarp();
+      *reinterpret_cast<u32 *>(mine8 + 4 * w.q) = o;
+      __syncwarp();
+      x[0] = o;
     }
   }
   const unsigned long long t1 = clock64();
   if (threadIdx.x == 0) *cycles = (t1 - t0) / (unsigned long long)K;
   if (x[0] == 0x12345678u && y[0] == 1u) *sink = x[1];
+}
+// the same for the eight-lanes-per-hash form (hso), which the narrow steps of the Merkle climb and the transcript use
+extern "C" int stark_bench_hash_latency_hso(stark_ctx *ctx, double *hso_cycles) {
+  if (!ctx || !hso_cycles) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
+  unsigned long long *d = nullptr, h = 0;
+  ST_TRY(dev_alloc(ctx, (void **)&d, 64));
+  k_hash_latency<<<1, 32, 0, ctx->stream>>>(3, 4, d, (u32 *)(d + 4));    // warm-up (instruction cache)
+  k_hash_latency<<<1, 32, 0, ctx->stream>>>(3, 64, d, (u32 *)(d + 4));
+  ctx->launches += 2;
+  CU_TRY(ctx, cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  dev_free(ctx, d);
+  *hso_cycles = (double)h;
+  return STARK_OK;
 }
 extern "C" int stark_bench_hash_latency(stark_ctx *ctx, double *hs_cycles, double *hs2_cycles, double *hsq_cycles) {
   if (!ctx || !hs_cycles || !hs2_cycles || !hsq_cycles) return stark_fail(ctx, STARK_ERR_ARG, "null argument");

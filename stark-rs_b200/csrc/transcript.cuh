@@ -87,23 +87,26 @@ __device__ __forceinline__ void transcript_round_warp(const TranscriptArgs &A, c
     return;
   }
   if (lane < 8) reinterpret_cast<uint32_t *>(A.root_out)[lane] = m[lane];
-  hsq::Quad st;
-  hsq::init(st);
+  // one hash on eight lanes (hso); the four octets of the warp compute the same thing
+  const hso::Dev w;
+  hso::Oct st;
+  hso::init(w, st);
 #pragma unroll
-  for (int j = 0; j < 8; j++) st.s[j] = T->s[8 * st.q + j];
+  for (int j = 0; j < 4; j++) st.s[j] = T->s[4 * w.q + j];
   __syncwarp();             // every lane has read the sponge before lane group 0 overwrites it
-  hsq::absorb_mix<false>(st, m);          // round constants of this mix pending
-  if (lane < 4) {
+  hso::absorb_mix<false>(w, st, root_bytes);          // round constants of this mix pending
+  if (lane < 8) {
 #pragma unroll
-    for (int j = 0; j < 8; j++) T->s[8 * st.q + j] = (st.s[j] + st.rc[j]) & 0xffu;
+    for (int j = 0; j < 4; j++) T->s[4 * w.q + j] = (st.s[j] + st.rc[j]) & 0xffu;
   }
   if (!A.draw) return;
 #pragma unroll 1
-  for (int k = 0; k < 8; k++) hsq::mix_lazy<true>(st);
+  for (int k = 0; k < 8; k++) hso::mix_lazy<true>(w, st);
+  // FiatShamir::challenge: the first 8 bytes, little-endian (lanes 0 and 1 of an octet)
+  const uint32_t word = hso::pack4(st.s[0] + st.rc[0], st.s[1] + st.rc[1], st.s[2] + st.rc[2], st.s[3] + st.rc[3]);
+  const uint32_t lo = w.shfl(word, 0u), hi = w.shfl(word, 1u);
   if (lane == 0) {
-    uint64_t a = 0;
-#pragma unroll
-    for (int b = 0; b < 8; b++) a |= (uint64_t)((st.s[b] + st.rc[b]) & 0xffu) << (8 * b);
+    const uint64_t a = ((uint64_t)hi << 32) | lo;
     *A.alpha_raw = a;
     *A.alpha_m = ff::to_mont(ff::reduce64(a));
   }

@@ -69,6 +69,7 @@ extern "C" {
     pub fn stark_hash_from_u64(value: u64, out: *mut u8) -> i32;
     pub fn stark_bench_mul_peak(ctx: *mut StarkCtx, out4: *mut f64) -> i32;
     pub fn stark_bench_hash_latency(ctx: *mut StarkCtx, hs_cycles: *mut f64, hs2_cycles: *mut f64, hsq_cycles: *mut f64) -> i32;
+    pub fn stark_bench_hash_latency_hso(ctx: *mut StarkCtx, hso_cycles: *mut f64) -> i32;
     pub fn stark_fri_verify(ctx: *mut StarkCtx, proof: *const u8, proof_len: usize, domain_length: usize, offset: u64, omega: u64, expansion_factor: u32, num_colinearity_tests: u32, transcript: *const u8, transcript_len: usize, ok: *mut i32, reason: *mut u32, roots_out: *mut u8, top_indices: *mut u64, poly_indices: *mut u64, poly_values: *mut u64) -> i32;
     pub fn stark_fri_verify_reason(reason: u32) -> *const std::os::raw::c_char;
     pub fn stark_trace_to_columns(ctx: *mut StarkCtx, rows_i128: *const std::ffi::c_void, n_rows: usize, n_cols: u32, out: *mut *mut StarkBuf) -> i32;

@@ -56,3 +56,53 @@ static int check_hs2() {
   return fails;
 }
 static int dummy_hs2 = check_hs2();
+// ---- hso (one hash on eight lanes): the eight lanes run as eight host threads, a shuffle is a write to a shared slot,
+// a barrier, a read of the source lane's slot, a barrier
+#include <atomic>
+#include <thread>
+struct EmuBarrier {
+  std::atomic<int> count{0}, gen{0};
+  void wait() {
+    const int g = gen.load();
+    if (count.fetch_add(1) + 1 == 8) { count.store(0); gen.fetch_add(1); }
+    else while (gen.load() == g) std::this_thread::yield();
+  }
+};
+struct EmuOct {
+  uint32_t q;
+  uint32_t *slots;
+  EmuBarrier *bar;
+  uint32_t shfl(uint32_t v, uint32_t src) const {
+    slots[q] = v;
+    bar->wait();
+    const uint32_t r = slots[src & 7u];
+    bar->wait();
+    return r;
+  }
+};
+static int check_hso() {
+  int fails = 0;
+  uint64_t s = 31337;
+  auto rnd = [&]() { s = s * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)(s >> 32); };
+  for (int it = 0; it < 200; it++) {
+    uint32_t l[8], r[8]; uint8_t want[32], got[32];
+    for (int i = 0; i < 8; i++) l[i] = rnd(), r[i] = rnd();
+    if (it == 0) for (int i = 0; i < 8; i++) l[i] = r[i] = 0xffffffffu;
+    if (it == 1) for (int i = 0; i < 8; i++) l[i] = r[i] = 0;
+    oracle_hash_combine((uint8_t *)l, (uint8_t *)r, want);
+    uint32_t slots[8];
+    EmuBarrier bar;
+    std::thread th[8];
+    for (uint32_t q = 0; q < 8; q++)
+      th[q] = std::thread([&, q]() {
+        EmuOct w{q, slots, &bar};
+        const uint32_t o = hso::combine(w, (const uint8_t *)l, (const uint8_t *)r);
+        memcpy(got + 4 * q, &o, 4);
+      });
+    for (auto &t : th) t.join();
+    if (memcmp(got, want, 32)) { fails++; if (fails < 3) printf("hso combine mismatch it=%d\n", it); }
+  }
+  printf(fails ? "hso FAIL %d\n" : "hso OK\n", fails);
+  return fails;
+}
+static int dummy_hso = check_hso();
