@@ -50,7 +50,9 @@ def parse():
     ap.add_argument("--seed", type=lambda s: int(s, 0), default=0x5354524B)
     ap.add_argument("--ref-log-n", type=int, default=0, help="rows (log2) of the reference arm's sample; 0 = the largest "
                     "size whose steps + warmup fit --ref-budget-s")
-    ap.add_argument("--ref-budget-s", type=float, default=240.0)
+    ap.add_argument("--ref-budget-s", type=float, default=480.0,
+                    help="wall-clock budget of the reference arm's steps + warmup; the full 2^20-row config takes ~16.5 s per step "
+                         "on 16 host cores, i.e. ~7 min for 20 + 5 steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
     return ap.parse_args()
@@ -106,8 +108,9 @@ def run_reference(a):
     O.build()
     threads = os.cpu_count() or 1
     nq_of = lambda ln: min(a.nq, 1 << max(ln + a.log_blowup - 3, 0))
-    # size of the bounded sample: calibrate on a 2^14-row trace (per-element cost is flat in n: hashing dominates)
-    cal_ln = min(14, a.log_n)
+    # size of the bounded sample: calibrate on a 2^16-row trace (per-element cost is flat in n from there on: hashing
+    # dominates and the thread start-up cost of the oracle's loops is amortised)
+    cal_ln = min(16, a.log_n)
     t_cal, _, _ = cpu_config3(O, synth_cols(a, cal_ln), cal_ln, a.log_blowup, nq_of(cal_ln), threads)
     ln = a.ref_log_n or a.log_n
     if not a.ref_log_n:

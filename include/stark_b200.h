@@ -290,6 +290,8 @@ int stark_mgpu_set_shard_log(stark_mgpu *m, uint32_t log_n);
 int stark_mgpu_barrier(stark_mgpu *m); /* device-side barrier over the group + synchronisation of this rank's stream */
 /* the trace columns (indices > 0) this rank commits in stark_mgpu_prove_trace; returns their number */
 uint32_t stark_mgpu_owned_columns(const stark_mgpu *m, uint32_t n_cols, uint32_t *out);
+/* the same partition for any (rank, world) without a handle: host logic only, no device needed */
+uint32_t stark_mgpu_columns_of_rank(int rank, int world, uint32_t n_cols, uint32_t *out);
 
 /* BASELINE config 3 on a group = stark_prove_trace with the work sharded: column 0 is LDE'd by every rank (its codeword
  * is the FRI input), columns 1.. are LDE'd and committed round robin (column c by rank (c - 1) % world), Fri::prove runs

@@ -13,7 +13,7 @@ import numpy as np
 
 __all__ = ["P", "StarkError", "StarkPanic", "Context", "Buffer", "MerkleTree", "FriState", "lib", "lib_path",
            "build_library", "prim_nth_root", "fri_num_rounds", "fri_proof_size", "fri_sample_indices",
-           "fiat_shamir_challenge", "hash_from_u64", "Group", "mgpu_unique_id"]
+           "fiat_shamir_challenge", "hash_from_u64", "Group", "mgpu_unique_id", "mgpu_columns_of_rank"]
 
 P = 998244353
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -678,6 +678,13 @@ class Context:
 
 
 # ---------------------------------------------------------------------------------------------- groups of GPUs
+
+def mgpu_columns_of_rank(rank, world, n_cols):
+    """which trace columns (> 0) rank `rank` of a group of `world` commits in stark_mgpu_prove_trace (host logic only)"""
+    out = (C.c_uint32 * max(n_cols, 1))()
+    k = lib().stark_mgpu_columns_of_rank(C.c_int(rank), C.c_int(world), U32(n_cols), out)
+    return [int(out[i]) for i in range(k)]
+
 
 def mgpu_unique_id():
     """stark_mgpu_unique_id: 128 bytes rank 0 hands to the other ranks (any channel) before Group.init"""

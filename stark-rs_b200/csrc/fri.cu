@@ -2003,6 +2003,11 @@ extern "C" {
 uint32_t stark_mgpu_owned_columns(const stark_mgpu *m, uint32_t n_cols, uint32_t *out) {
   return m ? mg_owned_columns(m->rank, m->world, n_cols, out) : 0;
 }
+// the same partition without a group handle (pure host logic: usable, and tested, without a device)
+uint32_t stark_mgpu_columns_of_rank(int rank, int world, uint32_t n_cols, uint32_t *out) {
+  if (world < 1 || rank < 0 || rank >= world) return 0;
+  return mg_owned_columns(rank, world, n_cols, out);
+}
 
 static int mg_check_ranks(stark_mgpu *const *ranks, int n_here) {
   if (!ranks || n_here < 1 || n_here > MG_MAX_RANKS) return stark_fail(nullptr, STARK_ERR_ARG, "null argument");

@@ -102,6 +102,7 @@ extern "C" {
     pub fn stark_mgpu_set_shard_log(m: *mut StarkMgpu, log_n: u32) -> i32;
     pub fn stark_mgpu_barrier(m: *mut StarkMgpu) -> i32;
     pub fn stark_mgpu_owned_columns(m: *const StarkMgpu, n_cols: u32, out: *mut u32) -> u32;
+    pub fn stark_mgpu_columns_of_rank(rank: i32, world: i32, n_cols: u32, out: *mut u32) -> u32;
     pub fn stark_mgpu_prove_trace(ranks: *const *mut StarkMgpu, n_here: i32, cols: *const u64, n_cols: u32, log_n: u32, log_blowup: u32, offset: u64, num_colinearity_tests: u32, column_roots: *const *mut u8, proofs: *const *mut u8, proof_cap: usize, proof_len: *mut usize) -> i32;
     pub fn stark_mgpu_prove_trace_dev(ranks: *const *mut StarkMgpu, n_here: i32, my_cols: *const *const StarkBuf, n_cols: u32, log_n: u32, log_blowup: u32, offset: u64, num_colinearity_tests: u32, column_roots: *const *mut u8, proofs: *const *mut u8, proof_cap: usize, proof_len: *mut usize) -> i32;
     pub fn stark_mgpu_fri_prove_dev(ranks: *const *mut StarkMgpu, n_here: i32, codewords: *const *const StarkBuf, n: usize, domain_length: usize, offset: u64, omega: u64, expansion_factor: u32, num_colinearity_tests: u32, transcript: *const u8, transcript_len: usize, proofs: *const *mut u8, proof_cap: usize, proof_len: *mut usize, top_indices: *const *mut u64) -> i32;

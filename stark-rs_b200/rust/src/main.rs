@@ -6,6 +6,7 @@ mod fiat_shamir;
 mod fri;
 mod hash;
 mod merkle;
+mod mgpu;
 mod stream;
 mod trace;
 pub mod univariate;

@@ -107,3 +107,19 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".rs", ".cpp")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "import oracle" not in text and "liboracle" not in text and "stark_oracle" not in text, f
+
+
+def test_mgpu_column_partition_host_logic():
+    """stark_mgpu_prove_trace's column assignment (column 0 on every rank, columns 1.. round robin) is pure host logic:
+    for every group size the ranks' sets are disjoint, cover 1 .. n_cols - 1, are balanced within one column, and a group
+    of one owns everything"""
+    import stark_rs_b200 as S
+    for world in (1, 2, 4, 8):
+        for n_cols in (1, 2, 5, 16, 64):
+            sets = [S.mgpu_columns_of_rank(r, world, n_cols) for r in range(world)]
+            flat = sorted(c for s in sets for c in s)
+            assert flat == list(range(1, n_cols)), (world, n_cols)
+            assert max(len(s) for s in sets) - min(len(s) for s in sets) <= 1
+            assert all(s == sorted(s) for s in sets)
+    assert S.mgpu_columns_of_rank(0, 1, 16) == list(range(1, 16))
+    assert S.mgpu_columns_of_rank(3, 2, 16) == [] and S.mgpu_columns_of_rank(-1, 2, 16) == []
