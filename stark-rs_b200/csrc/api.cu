@@ -125,11 +125,11 @@ static int read_flag(stark_ctx *ctx, u32 *value) {
 int upload_u64(stark_ctx *ctx, const uint64_t *host, size_t n, u32 *dst) {
   if (n == 0) return STARK_OK;
   u64 *tmp = nullptr;
-  ST_TRY(dev_alloc(ctx, (void **)&tmp, n * 8));
+  Scratch sc(ctx);
+  ST_TRY(sc.get(&tmp, n * 8));
   CU_TRY(ctx, cudaMemsetAsync(ctx->flag, 0, 4, ctx->stream));
   CU_TRY(ctx, cudaMemcpyAsync(tmp, host, n * 8, cudaMemcpyHostToDevice, ctx->stream));
   LAUNCH(ctx, "narrow_u64", 12ull * n, k_narrow<<<(u32)((n + 255) / 256), 256, 0, ctx->stream>>>(tmp, dst, n, ctx->flag));
-  dev_free(ctx, tmp);
   u32 f = 0;
   ST_TRY(read_flag(ctx, &f));
   if (f) return stark_fail(ctx, STARK_ERR_ARG, "non-canonical field element (value >= p) in input");
@@ -147,10 +147,10 @@ int upload_flag_reset(stark_ctx *ctx) {   // once before a group of upload_u64_n
 int upload_u64_nosync(stark_ctx *ctx, const uint64_t *host, size_t n, u32 *dst) {
   if (n == 0) return STARK_OK;
   u64 *tmp = nullptr;
-  ST_TRY(dev_alloc(ctx, (void **)&tmp, n * 8));
+  Scratch sc(ctx);
+  ST_TRY(sc.get(&tmp, n * 8));
   CU_TRY(ctx, cudaMemcpyAsync(tmp, host, n * 8, cudaMemcpyHostToDevice, ctx->stream));
   LAUNCH(ctx, "narrow_u64", 12ull * n, k_narrow<<<(u32)((n + 255) / 256), 256, 0, ctx->stream>>>(tmp, dst, n, ctx->flag + 2));
-  dev_free(ctx, tmp);
   CU_TRY(ctx, cudaMemcpyAsync(ctx->h_flag + 2, ctx->flag + 2, 4, cudaMemcpyDeviceToHost, ctx->stream));
   return STARK_OK;
 }
@@ -173,10 +173,10 @@ int upload_u64_check(stark_ctx *ctx) {   // call after the stream has been synch
 int download_u64(stark_ctx *ctx, const u32 *src, size_t n, uint64_t *host) {
   if (n == 0) return STARK_OK;
   u64 *tmp = nullptr;
-  ST_TRY(dev_alloc(ctx, (void **)&tmp, n * 8));
+  Scratch sc(ctx);
+  ST_TRY(sc.get(&tmp, n * 8));
   LAUNCH(ctx, "widen_u64", 12ull * n, k_widen<<<(u32)((n + 255) / 256), 256, 0, ctx->stream>>>(src, tmp, n));
   CU_TRY(ctx, cudaMemcpyAsync(host, tmp, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  dev_free(ctx, tmp);
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return STARK_OK;
 }
@@ -186,11 +186,11 @@ int trace_to_columns_dev(stark_ctx *ctx, const void *rows_i128, size_t n_rows, u
   const size_t bytes = n_rows * (size_t)n_cols * 16;
   if (bytes == 0) return STARK_OK;
   uint4 *tmp = nullptr;
-  ST_TRY(dev_alloc(ctx, (void **)&tmp, bytes));
+  Scratch sc(ctx);
+  ST_TRY(sc.get(&tmp, bytes));
   CU_TRY(ctx, cudaMemcpyAsync(tmp, rows_i128, bytes, cudaMemcpyHostToDevice, ctx->stream));
   LAUNCH(ctx, "trace_ingest", bytes + 4 * n_rows * (size_t)n_cols,
          k_trace_ingest<<<dim3((u32)((n_rows + 31) / 32), (n_cols + 31) / 32), dim3(32, 8), 0, ctx->stream>>>(tmp, n_rows, n_cols, cols));
-  dev_free(ctx, tmp);
   return STARK_OK;
 }
 
@@ -393,11 +393,12 @@ static int ff_vec(stark_ctx *ctx, int op, const uint64_t *a, const uint64_t *b, 
   if (!ctx || (n && (!a || !out)) || (n && op <= OP_MUL && !b)) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
   if (n == 0) return STARK_OK;
   u32 *da = nullptr, *db = nullptr, *dout = nullptr;
-  ST_TRY(dev_alloc(ctx, (void **)&da, n * 4));
-  ST_TRY(dev_alloc(ctx, (void **)&dout, n * 4));
+  Scratch sc(ctx);
+  ST_TRY(sc.get(&da, n * 4));
+  ST_TRY(sc.get(&dout, n * 4));
   int rc = upload_u64(ctx, a, n, da);
   if (rc == STARK_OK && op <= OP_MUL) {
-    rc = dev_alloc(ctx, (void **)&db, n * 4);
+    rc = sc.get(&db, n * 4);
     if (rc == STARK_OK) rc = upload_u64(ctx, b, n, db);
   }
   if (rc == STARK_OK) {
@@ -417,7 +418,6 @@ static int ff_vec(stark_ctx *ctx, int op, const uint64_t *a, const uint64_t *b, 
     if (rc == STARK_OK && cudaGetLastError() != cudaSuccess) rc = stark_fail(ctx, STARK_ERR_CUDA, "kernel launch failed");
   }
   if (rc == STARK_OK) rc = download_u64(ctx, dout, n, out);
-  dev_free(ctx, da), dev_free(ctx, db), dev_free(ctx, dout);
   return rc;
 }
 int stark_ff_vec_add(stark_ctx *c, const uint64_t *a, const uint64_t *b, uint64_t *o, size_t n) { return ff_vec(c, OP_ADD, a, b, 0, o, n); }

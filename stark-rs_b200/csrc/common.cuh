@@ -169,6 +169,26 @@ static inline int dev_alloc(stark_ctx *ctx, void **p, size_t bytes) {
 static inline void dev_free(stark_ctx *ctx, void *p) {
   if (p) cudaFreeAsync(p, ctx->stream);
 }
+// Scratch blocks owned by ONE call: the TRY / LAUNCH macros return from the middle of a function, so the blocks are
+// handed back (stream-ordered, on the context's stream) by the destructor on every exit path.
+struct Scratch {
+  stark_ctx *ctx;
+  void *blk[8];
+  int n = 0;
+  explicit Scratch(stark_ctx *c) : ctx(c) {}
+  Scratch(const Scratch &) = delete;
+  Scratch &operator=(const Scratch &) = delete;
+  ~Scratch() {
+    for (int i = 0; i < n; i++) dev_free(ctx, blk[i]);
+  }
+  template <class T>
+  int get(T **out, size_t bytes) {
+    if (n == 8) return stark_fail(ctx, STARK_ERR_CUDA, "scratch holder full");
+    int rc = dev_alloc(ctx, (void **)out, bytes);
+    if (rc == STARK_OK) blk[n++] = *out;
+    return rc;
+  }
+};
 
 // ---- internal device-pointer entry points (implemented in ntt.cu / poly.cu / merkle.cu / fri.cu)
 struct ScaleSpec {

@@ -182,14 +182,14 @@ int lde_dev(stark_ctx *ctx, const u32 *cols, u32 n_cols, u32 log_n, u32 log_blow
   if (n_cols == 0) return STARK_OK;
   const u64 n = 1ull << log_n, N = n << log_blowup;
   u32 *coef = nullptr;
-  ST_TRY(dev_alloc(ctx, (void **)&coef, (size_t)n_cols * n * 4));
+  Scratch sc(ctx);
+  ST_TRY(sc.get(&coef, (size_t)n_cols * n * 4));
   // interpolate on the trace domain, and scale coefficient j by n^-1 * offset^j on the way out
   ScaleSpec none = {ntt::SCALE_NONE, 1, 1};
   ScaleSpec post = {ntt::SCALE_GEO, ff::inv((u32)(n % ff::P)), offset};
   int rc = ntt_transform(ctx, cols, coef, (int)log_n, true, n_cols, n, n, n, none, post);
   // evaluate on the big domain; the zero padding is never read
   if (rc == STARK_OK) rc = ntt_transform(ctx, coef, out, (int)(log_n + log_blowup), false, n_cols, n, N, n, none, none);
-  dev_free(ctx, coef);
   return rc;
 }
 
@@ -211,8 +211,9 @@ static int poly_mul_dev(stark_ctx *ctx, const u32 *a, size_t na, const u32 *b, s
   if (lg > ff::TWO_ADICITY) return stark_fail(ctx, STARK_ERR_ARG, "n > 2^23 not supported by this modulus");
   const size_t M = (size_t)1 << lg;
   u32 *fa = nullptr, *fb = nullptr;
-  ST_TRY(dev_alloc(ctx, (void **)&fa, M * 4));
-  ST_TRY(dev_alloc(ctx, (void **)&fb, M * 4));
+  Scratch sc(ctx);
+  ST_TRY(sc.get(&fa, M * 4));
+  ST_TRY(sc.get(&fb, M * 4));
   ScaleSpec none = {ntt::SCALE_NONE, 1, 1};
   int rc = ntt_transform(ctx, a, fa, lg, false, 1, M, M, na, none, none);
   if (rc == STARK_OK) rc = ntt_transform(ctx, b, fb, lg, false, 1, M, M, nb, none, none);
@@ -227,7 +228,6 @@ static int poly_mul_dev(stark_ctx *ctx, const u32 *a, size_t na, const u32 *b, s
     CU_TRY(ctx, cudaMemcpyAsync(out, fb, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     if (keep > m) CU_TRY(ctx, cudaMemsetAsync(out + m, 0, (keep - m) * 4, ctx->stream));
   }
-  dev_free(ctx, fa), dev_free(ctx, fb);
   return rc;
 }
 
@@ -238,11 +238,12 @@ static int poly_div_dev(stark_ctx *ctx, const u32 *a, size_t na, size_t da, cons
                         size_t r_len) {
   const size_t k = da - db + 1;
   u32 *ra = nullptr, *rb = nullptr, *g = nullptr, *t = nullptr, *qb = nullptr;
-  ST_TRY(dev_alloc(ctx, (void **)&ra, k * 4));
-  ST_TRY(dev_alloc(ctx, (void **)&rb, k * 4));
-  ST_TRY(dev_alloc(ctx, (void **)&g, k * 4));
-  ST_TRY(dev_alloc(ctx, (void **)&t, k * 4));
-  ST_TRY(dev_alloc(ctx, (void **)&qb, (k + db) * 4));
+  Scratch sc(ctx);
+  ST_TRY(sc.get(&ra, k * 4));
+  ST_TRY(sc.get(&rb, k * 4));
+  ST_TRY(sc.get(&g, k * 4));
+  ST_TRY(sc.get(&t, k * 4));
+  ST_TRY(sc.get(&qb, (k + db) * 4));
   k_reverse_copy<<<grid_for(ctx, k, 256), 256, 0, ctx->stream>>>(a, da, ra, k);
   k_reverse_copy<<<grid_for(ctx, k, 256), 256, 0, ctx->stream>>>(b, db, rb, k);
   ctx->launches += 2;
@@ -272,7 +273,6 @@ static int poly_div_dev(stark_ctx *ctx, const u32 *a, size_t na, size_t da, cons
     k_remainder<<<grid_for(ctx, r_len, 256), 256, 0, ctx->stream>>>(a, na, qb, k + db, db, r, r_len, ctx->flag);
     ctx->launches++;
   }
-  dev_free(ctx, ra), dev_free(ctx, rb), dev_free(ctx, g), dev_free(ctx, t), dev_free(ctx, qb);
   return rc;
 }
 
@@ -307,10 +307,11 @@ int stark_poly_div(stark_ctx *ctx, const uint64_t *a, size_t na, const uint64_t 
   const size_t rl = na > (size_t)da + 1 + tz ? na : (size_t)da + 1 + tz;
   if (!q || !r) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
   u32 *d_a = nullptr, *d_b = nullptr, *d_q = nullptr, *d_r = nullptr;
-  ST_TRY(dev_alloc(ctx, (void **)&d_a, na * 4));
-  ST_TRY(dev_alloc(ctx, (void **)&d_b, nb * 4));
-  ST_TRY(dev_alloc(ctx, (void **)&d_q, k * 4));
-  ST_TRY(dev_alloc(ctx, (void **)&d_r, rl * 4));
+  Scratch sc(ctx);
+  ST_TRY(sc.get(&d_a, na * 4));
+  ST_TRY(sc.get(&d_b, nb * 4));
+  ST_TRY(sc.get(&d_q, k * 4));
+  ST_TRY(sc.get(&d_r, rl * 4));
   int rc = upload_u64(ctx, a, na, d_a);
   if (rc == STARK_OK) rc = upload_u64(ctx, b, nb, d_b);
   if (rc == STARK_OK) rc = poly_div_dev(ctx, d_a, na, (size_t)da, d_b, (size_t)db, d_q, d_r, rl);
@@ -321,7 +322,6 @@ int stark_poly_div(stark_ctx *ctx, const uint64_t *a, size_t na, const uint64_t 
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     if (*ctx->h_flag & 4u) rc = stark_fail(ctx, STARK_ERR_CUDA, "internal error: quotient check failed");
   }
-  dev_free(ctx, d_a), dev_free(ctx, d_b), dev_free(ctx, d_q), dev_free(ctx, d_r);
   if (rc == STARK_OK) *q_len = k, *r_len = rl;
   return rc;
 }
@@ -340,10 +340,11 @@ int stark_poly_mul(stark_ctx *ctx, const uint64_t *a, size_t na, const uint64_t 
   if (lg > ff::TWO_ADICITY) return stark_fail(ctx, STARK_ERR_ARG, "n > 2^23 not supported by this modulus");
   const size_t M = (size_t)1 << lg;
   u32 *da = nullptr, *db = nullptr, *fa = nullptr, *fb = nullptr;
-  ST_TRY(dev_alloc(ctx, (void **)&da, na * 4));
-  ST_TRY(dev_alloc(ctx, (void **)&db, nb * 4));
-  ST_TRY(dev_alloc(ctx, (void **)&fa, M * 4));
-  ST_TRY(dev_alloc(ctx, (void **)&fb, M * 4));
+  Scratch sc(ctx);
+  ST_TRY(sc.get(&da, na * 4));
+  ST_TRY(sc.get(&db, nb * 4));
+  ST_TRY(sc.get(&fa, M * 4));
+  ST_TRY(sc.get(&fb, M * 4));
   // uploads without a host round trip; the canonical-input flag is inspected after the download's sync
   int rc = upload_flag_reset(ctx);
   if (rc == STARK_OK) rc = upload_u64_nosync(ctx, a, na, da);
@@ -359,7 +360,6 @@ int stark_poly_mul(stark_ctx *ctx, const uint64_t *a, size_t na, const uint64_t 
     rc = ntt_transform(ctx, fa, fb, lg, true, 1, M, M, M, none, post);
   }
   if (rc == STARK_OK) rc = download_u64(ctx, fb, m, out);
-  dev_free(ctx, da), dev_free(ctx, db), dev_free(ctx, fa), dev_free(ctx, fb);
   if (rc == STARK_OK) rc = upload_u64_check(ctx);
   if (rc == STARK_OK) *out_len = m;
   return rc;
@@ -373,15 +373,15 @@ int stark_poly_eval_coset(stark_ctx *ctx, const uint64_t *coeffs, size_t nc, uin
   if (nc > N) return stark_fail(ctx, STARK_ERR_ARG, "more coefficients than domain points");
   if (offset >= ff::P) return stark_fail(ctx, STARK_ERR_ARG, "non-canonical field element (value >= p) in input");
   u32 *dc = nullptr, *dv = nullptr;
-  ST_TRY(dev_alloc(ctx, (void **)&dc, (nc ? nc : 1) * 4));
-  ST_TRY(dev_alloc(ctx, (void **)&dv, N * 4));
+  Scratch sc(ctx);
+  ST_TRY(sc.get(&dc, (nc ? nc : 1) * 4));
+  ST_TRY(sc.get(&dv, N * 4));
   int rc = upload_flag_reset(ctx);
   if (rc == STARK_OK) rc = upload_u64_nosync(ctx, coeffs, nc, dc);
   ScaleSpec none = {ntt::SCALE_NONE, 1, 1};
   ScaleSpec pre = {ntt::SCALE_GEO, 1, (u32)offset};
   if (rc == STARK_OK) rc = ntt_transform(ctx, dc, dv, (int)log_n, false, 1, N, N, nc, pre, none);
   if (rc == STARK_OK) rc = download_u64(ctx, dv, N, out);
-  dev_free(ctx, dc), dev_free(ctx, dv);
   if (rc == STARK_OK) rc = upload_u64_check(ctx);
   return rc;
 }
@@ -394,15 +394,15 @@ int stark_poly_interpolate_coset(stark_ctx *ctx, const uint64_t *vals, uint64_t 
   if (offset >= ff::P) return stark_fail(ctx, STARK_ERR_ARG, "non-canonical field element (value >= p) in input");
   const size_t N = (size_t)1 << log_n;
   u32 *dv = nullptr, *dc = nullptr;
-  ST_TRY(dev_alloc(ctx, (void **)&dv, N * 4));
-  ST_TRY(dev_alloc(ctx, (void **)&dc, N * 4));
+  Scratch sc(ctx);
+  ST_TRY(sc.get(&dv, N * 4));
+  ST_TRY(sc.get(&dc, N * 4));
   int rc = upload_flag_reset(ctx);
   if (rc == STARK_OK) rc = upload_u64_nosync(ctx, vals, N, dv);
   ScaleSpec none = {ntt::SCALE_NONE, 1, 1};
   ScaleSpec post = {ntt::SCALE_GEO, ff::inv((u32)(N % ff::P)), ff::inv((u32)offset)};
   if (rc == STARK_OK) rc = ntt_transform(ctx, dv, dc, (int)log_n, true, 1, N, N, N, none, post);
   if (rc == STARK_OK) rc = download_u64(ctx, dc, N, coeffs);
-  dev_free(ctx, dv), dev_free(ctx, dc);
   if (rc == STARK_OK) rc = upload_u64_check(ctx);
   // shape rule (add.rs:7-12, mul.rs:7-12): all-zero values -> [] for N >= 2, [0] for N == 1
   if (rc == STARK_OK) *out_len = all_zero(vals, N) ? (N == 1 ? 1 : 0) : N;
@@ -414,9 +414,10 @@ int stark_poly_eval_domain(stark_ctx *ctx, const uint64_t *coeffs, size_t nc, co
   if (!ctx || (nc && !coeffs) || (m && (!domain || !out))) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
   if (m == 0) return STARK_OK;
   u32 *dc = nullptr, *dd = nullptr, *dout = nullptr;
-  ST_TRY(dev_alloc(ctx, (void **)&dc, (nc ? nc : 1) * 4));
-  ST_TRY(dev_alloc(ctx, (void **)&dd, m * 4));
-  ST_TRY(dev_alloc(ctx, (void **)&dout, m * 4));
+  Scratch sc(ctx);
+  ST_TRY(sc.get(&dc, (nc ? nc : 1) * 4));
+  ST_TRY(sc.get(&dd, m * 4));
+  ST_TRY(sc.get(&dout, m * 4));
   int rc = upload_u64(ctx, coeffs, nc, dc);
   if (rc == STARK_OK) rc = upload_u64(ctx, domain, m, dd);
   if (rc == STARK_OK) {
@@ -424,7 +425,6 @@ int stark_poly_eval_domain(stark_ctx *ctx, const uint64_t *coeffs, size_t nc, co
     ctx->launches++;
     rc = download_u64(ctx, dout, m, out);
   }
-  dev_free(ctx, dc), dev_free(ctx, dd), dev_free(ctx, dout);
   return rc;
 }
 
@@ -445,12 +445,12 @@ int stark_poly_zerofier_domain(stark_ctx *ctx, const uint64_t *domain, size_t n,
   if (!ctx || !out || (n && !domain)) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
   if (n == 0) return stark_fail(ctx, STARK_ERR_ARG, "empty domain");  // mod.rs:78 indexes domain[0]
   u32 *dx = nullptr, *dm = nullptr;
-  ST_TRY(dev_alloc(ctx, (void **)&dx, n * 4));
-  ST_TRY(dev_alloc(ctx, (void **)&dm, (n + 1) * 4));
+  Scratch sc(ctx);
+  ST_TRY(sc.get(&dx, n * 4));
+  ST_TRY(sc.get(&dm, (n + 1) * 4));
   int rc = upload_u64(ctx, domain, n, dx);
   if (rc == STARK_OK) rc = zerofier_dev(ctx, dx, n, dm);
   if (rc == STARK_OK) rc = download_u64(ctx, dm, n + 1, out);
-  dev_free(ctx, dx), dev_free(ctx, dm);
   return rc;
 }
 
@@ -460,12 +460,13 @@ int stark_poly_interpolate_domain(stark_ctx *ctx, const uint64_t *domain, const 
   if (n == 0) return stark_fail(ctx, STARK_ERR_ARG, "assertion failed: domain.len() > 0");  // interpolate.rs:11
   u32 *dx = nullptr, *dy = nullptr, *dc = nullptr, *dm = nullptr, *part = nullptr, *dout = nullptr;
   const u32 rows = (u32)((n + 255) / 256);
-  ST_TRY(dev_alloc(ctx, (void **)&dx, n * 4));
-  ST_TRY(dev_alloc(ctx, (void **)&dy, n * 4));
-  ST_TRY(dev_alloc(ctx, (void **)&dc, n * 4));
-  ST_TRY(dev_alloc(ctx, (void **)&dm, (n + 1) * 4));
-  ST_TRY(dev_alloc(ctx, (void **)&part, (size_t)rows * n * 4));
-  ST_TRY(dev_alloc(ctx, (void **)&dout, n * 4));
+  Scratch sc(ctx);
+  ST_TRY(sc.get(&dx, n * 4));
+  ST_TRY(sc.get(&dy, n * 4));
+  ST_TRY(sc.get(&dc, n * 4));
+  ST_TRY(sc.get(&dm, (n + 1) * 4));
+  ST_TRY(sc.get(&part, (size_t)rows * n * 4));
+  ST_TRY(sc.get(&dout, n * 4));
   int rc = upload_u64(ctx, domain, n, dx);
   if (rc == STARK_OK) rc = upload_u64(ctx, vals, n, dy);
   if (rc == STARK_OK) {
@@ -483,7 +484,6 @@ int stark_poly_interpolate_domain(stark_ctx *ctx, const uint64_t *domain, const 
     ctx->launches += 2;
     rc = download_u64(ctx, dout, n, coeffs);
   }
-  dev_free(ctx, dx), dev_free(ctx, dy), dev_free(ctx, dc), dev_free(ctx, dm), dev_free(ctx, part), dev_free(ctx, dout);
   if (rc == STARK_OK) *out_len = all_zero(vals, n) ? (n == 1 ? 1 : 0) : n;
   return rc;
 }
@@ -493,8 +493,9 @@ int stark_poly_scale(stark_ctx *ctx, const uint64_t *coeffs, size_t n, uint64_t 
   if (n == 0) return STARK_OK;
   if (factor >= ff::P) return stark_fail(ctx, STARK_ERR_ARG, "non-canonical field element (value >= p) in input");
   u32 *dc = nullptr, *dout = nullptr;
-  ST_TRY(dev_alloc(ctx, (void **)&dc, n * 4));
-  ST_TRY(dev_alloc(ctx, (void **)&dout, n * 4));
+  Scratch sc(ctx);
+  ST_TRY(sc.get(&dc, n * 4));
+  ST_TRY(sc.get(&dout, n * 4));
   int rc = upload_u64(ctx, coeffs, n, dc);
   GeoTables G;
   if (rc == STARK_OK) rc = geo_tables(ctx, (u32)factor, 1, n, &G);
@@ -503,7 +504,6 @@ int stark_poly_scale(stark_ctx *ctx, const uint64_t *coeffs, size_t n, uint64_t 
     ctx->launches++;
     rc = download_u64(ctx, dout, n, out);
   }
-  dev_free(ctx, dc), dev_free(ctx, dout);
   return rc;
 }
 
