@@ -306,13 +306,13 @@ int stark_hash_bytes(stark_ctx *ctx, const uint8_t *msgs, size_t n_msgs, size_t 
   if (!ctx || (!msgs && n_msgs && msg_len) || !out) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
   if (n_msgs == 0) return STARK_OK;
   u8 *d_in = nullptr, *d_out = nullptr;
-  ST_TRY(dev_alloc(ctx, (void **)&d_in, n_msgs * msg_len));
-  ST_TRY(dev_alloc(ctx, (void **)&d_out, n_msgs * 32));
+  Scratch sc(ctx);
+  ST_TRY(sc.get(&d_in, n_msgs * msg_len));
+  ST_TRY(sc.get(&d_out, n_msgs * 32));
   if (msg_len) CU_TRY(ctx, cudaMemcpyAsync(d_in, msgs, n_msgs * msg_len, cudaMemcpyHostToDevice, ctx->stream));
   LAUNCH(ctx, "hash_bytes", (msg_len + 32) * n_msgs,
          k_hash_bytes<<<(u32)((n_msgs + 127) / 128), 128, 0, ctx->stream>>>(d_in, n_msgs, msg_len, d_out));
   CU_TRY(ctx, cudaMemcpyAsync(out, d_out, n_msgs * 32, cudaMemcpyDeviceToHost, ctx->stream));
-  dev_free(ctx, d_in), dev_free(ctx, d_out);
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return STARK_OK;
 }
@@ -427,12 +427,12 @@ int stark_merkle_open_batch(stark_tree *t, const uint64_t *idx, size_t n_idx, ui
   if (depth == 0 || n_idx == 0) return STARK_OK;
   u64 *d_idx = nullptr;
   u8 *d_out = nullptr;
-  ST_TRY(dev_alloc(ctx, (void **)&d_idx, 8 * n_idx));
-  ST_TRY(dev_alloc(ctx, (void **)&d_out, 32 * (size_t)depth * n_idx));
+  Scratch sc(ctx);
+  ST_TRY(sc.get(&d_idx, 8 * n_idx));
+  ST_TRY(sc.get(&d_out, 32 * (size_t)depth * n_idx));
   CU_TRY(ctx, cudaMemcpyAsync(d_idx, idx, 8 * n_idx, cudaMemcpyHostToDevice, ctx->stream));
   ST_TRY(merkle_open_dev(ctx, t->nodes, t->n, d_idx, (u32)n_idx, d_out));
   CU_TRY(ctx, cudaMemcpyAsync(out, d_out, 32 * (size_t)depth * n_idx, cudaMemcpyDeviceToHost, ctx->stream));
-  dev_free(ctx, d_idx), dev_free(ctx, d_out);
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return STARK_OK;
 }
@@ -475,13 +475,13 @@ int stark_merkle_open(stark_tree *t, size_t index, uint8_t *out, size_t *n_hashe
   if (depth == 0) return STARK_OK;
   u64 *d_idx = nullptr;
   u8 *d_out = nullptr;
-  ST_TRY(dev_alloc(ctx, (void **)&d_idx, 8));
-  ST_TRY(dev_alloc(ctx, (void **)&d_out, 32 * depth));
+  Scratch sc(ctx);
+  ST_TRY(sc.get(&d_idx, 8));
+  ST_TRY(sc.get(&d_out, 32 * depth));
   u64 idx = index;
   CU_TRY(ctx, cudaMemcpyAsync(d_idx, &idx, 8, cudaMemcpyHostToDevice, ctx->stream));
   ST_TRY(merkle_open_dev(ctx, t->nodes, t->n, d_idx, 1, d_out));
   CU_TRY(ctx, cudaMemcpyAsync(out, d_out, 32 * depth, cudaMemcpyDeviceToHost, ctx->stream));
-  dev_free(ctx, d_idx), dev_free(ctx, d_out);
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return STARK_OK;
 }

@@ -97,12 +97,12 @@ static int run_mode(stark_ctx *ctx, u32 *d_out, double ops_per_inner, double *pe
 extern "C" int stark_bench_int_peak(stark_ctx *ctx, double *imad_per_s, double *alu_per_s, double *mixed_per_s) {
   if (!ctx || !imad_per_s || !alu_per_s || !mixed_per_s) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
   u32 *d_out = nullptr;
-  ST_TRY(dev_alloc(ctx, (void **)&d_out, 16));
+  Scratch sc(ctx);
+  ST_TRY(sc.get(&d_out, 16));
   // instructions per innermost statement (pinned with inline PTX): MODE 0: 1 IMAD; MODE 1: 1 LOP3; MODE 2: IMAD + LOP3
   int rc = run_mode<0>(ctx, d_out, 1.0, imad_per_s);
   if (rc == STARK_OK) rc = run_mode<1>(ctx, d_out, 1.0, alu_per_s);
   if (rc == STARK_OK) rc = run_mode<2>(ctx, d_out, 2.0, mixed_per_s);
-  dev_free(ctx, d_out);
   return rc;
 }
 
@@ -111,12 +111,12 @@ extern "C" int stark_bench_int_peak(stark_ctx *ctx, double *imad_per_s, double *
 extern "C" int stark_bench_mul_peak(stark_ctx *ctx, double *out) {
   if (!ctx || !out) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
   u32 *d_out = nullptr;
-  ST_TRY(dev_alloc(ctx, (void **)&d_out, 16));
+  Scratch sc(ctx);
+  ST_TRY(sc.get(&d_out, 16));
   int rc = run_mode<3>(ctx, d_out, 1.0, out + 0);
   if (rc == STARK_OK) rc = run_mode<4>(ctx, d_out, 1.0, out + 1);
   if (rc == STARK_OK) rc = run_mode<5>(ctx, d_out, 1.0, out + 2);
   if (rc == STARK_OK) rc = run_mode<6>(ctx, d_out, 1.0, out + 3);
-  dev_free(ctx, d_out);
   return rc;
 }
 
@@ -168,20 +168,21 @@ __global__ void k_hash_latency(int mode, int K, unsigned long long *cycles, u32 
 extern "C" int stark_bench_hash_latency_hso(stark_ctx *ctx, double *hso_cycles) {
   if (!ctx || !hso_cycles) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
   unsigned long long *d = nullptr, h = 0;
-  ST_TRY(dev_alloc(ctx, (void **)&d, 64));
+  Scratch sc(ctx);
+  ST_TRY(sc.get(&d, 64));
   k_hash_latency<<<1, 32, 0, ctx->stream>>>(3, 4, d, (u32 *)(d + 4));    // warm-up (instruction cache)
   k_hash_latency<<<1, 32, 0, ctx->stream>>>(3, 64, d, (u32 *)(d + 4));
   ctx->launches += 2;
   CU_TRY(ctx, cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, ctx->stream));
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  dev_free(ctx, d);
   *hso_cycles = (double)h;
   return STARK_OK;
 }
 extern "C" int stark_bench_hash_latency(stark_ctx *ctx, double *hs_cycles, double *hs2_cycles, double *hsq_cycles) {
   if (!ctx || !hs_cycles || !hs2_cycles || !hsq_cycles) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
   unsigned long long *d = nullptr, h[3];
-  ST_TRY(dev_alloc(ctx, (void **)&d, 64));
+  Scratch sc(ctx);
+  ST_TRY(sc.get(&d, 64));
   for (int mode = 0; mode < 3; mode++) {
     k_hash_latency<<<1, 32, 0, ctx->stream>>>(mode, 4, d + mode, (u32 *)(d + 4));    // warm-up (instruction cache)
     k_hash_latency<<<1, 32, 0, ctx->stream>>>(mode, 64, d + mode, (u32 *)(d + 4));
@@ -189,7 +190,6 @@ extern "C" int stark_bench_hash_latency(stark_ctx *ctx, double *hs_cycles, doubl
   }
   CU_TRY(ctx, cudaMemcpyAsync(h, d, 24, cudaMemcpyDeviceToHost, ctx->stream));
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  dev_free(ctx, d);
   *hs_cycles = (double)h[0], *hs2_cycles = (double)h[1], *hsq_cycles = (double)h[2];
   return STARK_OK;
 }
