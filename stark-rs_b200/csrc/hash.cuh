@@ -414,6 +414,11 @@ __device__ __forceinline__ void init(Quad &st) {
     }
   }
 }
+__device__ __forceinline__ u32 mad2(u32 x, u32 c) {   // 2 x + c, opaque to the re-association passes
+  u32 r;
+  asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(r) : "r"(x), "r"(c));
+  return r;
+}
 // mix_state without its final round-constant add (left pending, as hs::mix_lazy)
 template <bool PENDING>
 __device__ __forceinline__ void mix_lazy(Quad &st) {
@@ -433,26 +438,33 @@ __device__ __forceinline__ void mix_lazy(Quad &st) {
   // A lane's total telescopes: sum_{k=8q}^{8q+7} t[k] = 2 T_q - s[8q] + s[8q+8] with T_q the lane's byte sum, so the
   // offset of lane q is  O_q = s[31] + 2 (T_0 + .. + T_{q-1}) - s[0] + s[8q]  and needs only T of the lower lanes,
   // s[0] and s[31]: ONE hop of independent shuffles per mix (the local prefix runs underneath it).
+  // As in hso::mix_lazy the gather is arranged to leave as little as possible behind the last shuffle: lane q reads T from
+  // lanes q-1 .. q-3 and, where that runs off the quad, from ITSELF (no selects; the 3 - q surplus copies of T_q come out
+  // of the early constant), and s[31], s[0], the in-lane prefixes and the surplus are folded into C_j while the shuffles
+  // are in flight: s'[j] = C_j + 2 (a1 + a2 + a3).
+  const u32 q = st.q;
   const u32 e0 = s[0] + s[1];
-  const u32 T = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+  const u32 T = (s[0] + s[1] + s[2]) + (s[3] + s[4] + s[5]) + (s[6] + s[7]);
   const u32 s31 = shfl(s[7], st.base + 3u);                                       // old s[31]
   const u32 z0 = shfl(s[0], st.base);                                             // s[0]
   const u32 n0 = s31 + shfl(e0, st.base);                                         // s'[0] = s[31] + s[0] + s[1]
-  const u32 a = shfl(T, st.base), b = shfl(T, st.base + 1u), c = shfl(T, st.base + 2u);
-  const u32 nxt0 = shfl(s[0], st.base + ((st.q + 1u) & 3u));                      // s[8q+8] (lanes 0..2)
+  const u32 nxt0 = shfl(s[0], st.base + ((q + 1u) & 3u));                         // s[8q+8] (lanes 0..2)
+  const u32 a1 = shfl(T, st.base + (q >= 1u ? q - 1u : q));
+  const u32 a2 = shfl(T, st.base + (q >= 2u ? q - 2u : q));
+  const u32 a3 = shfl(T, st.base + (q >= 3u ? q - 3u : q));
   u32 P[7];
   P[0] = e0;
 #pragma unroll
   for (int j = 1; j < 7; j++) P[j] = P[j - 1] + (s[j] + s[j + 1]);
-  u32 lower = 0;
-  if (st.q > 0) lower += a;
-  if (st.q > 1) lower += b;
-  if (st.q > 2) lower += c;
-  const u32 O = s31 + 2u * lower - z0 + s[0];
-  const u32 last = (st.q == 3u) ? (s31 + n0 + (O + P[6])) : (O + P[6] + s[7] + nxt0);   // lane 3: s'[31]
+  const u32 c = s31 - z0 + s[0] - 2u * (3u - q) * T;
+  const u32 c6 = c + P[6];
+  const u32 clast = (q == 3u) ? (s31 + n0 + c6) : (c6 + s[7] + nxt0);   // lane 3: s'[31] = s[31] + s'[0] + s'[30]
+  // 2 x + C_j as ONE multiply-add behind the three-input add (plain C is re-associated into x + x, + c, + P_j: two adds
+  // deeper behind the last shuffle)
+  const u32 x = a1 + a2 + a3;
 #pragma unroll
-  for (int j = 0; j < 7; j++) s[j] = O + P[j];
-  s[7] = last;
+  for (int j = 0; j < 7; j++) s[j] = mad2(x, c + P[j]);
+  s[7] = mad2(x, clast);
 }
 __device__ __forceinline__ void settle(Quad &st) {
 #pragma unroll
@@ -574,23 +586,36 @@ HS_HD void mix_lazy(const W &w, Oct &st) {
   // neighbour add, closed form: with t[k] = s[k] + s[k+1], s'[i] = s[31] + sum_{k<=i} t[k] (i <= 30).  A lane's total of t
   // telescopes to 2 T_q - s[4q] + s[4q+4] (T_q = its byte sum), so lane q's offset is
   //   O_q = s[31] + 2 (T_0 + .. + T_{q-1}) - s[0] + s[4q]
+  // The gather of the D_m = 2 T_m is the critical path of the whole hash (a lone warp waits for seven shuffles and then
+  // for everything that depends on them), so it is arranged to leave ONE add behind the last shuffle:
+  //  * lane q reads D from lanes q-1 .. q-7 and, where that runs off the octet, from ITSELF -- no selects after the
+  //    shuffles; the (7 - q) surplus copies of D_q are taken out of the early constant instead;
+  //  * everything else (s[31], s[0], the in-lane prefixes P_j, the surplus) is folded into C_j while the shuffles are in
+  //    flight, and so are the first three arrivals; out_j = (C_j + a1 + a2 + a3) + (a4 + a5 + a6) + a7.
   const u32 e0 = s[0] + s[1];
-  const u32 T = e0 + (s[2] + s[3]);
+  // ONE three-input add, not a child of e0: the compiler re-associates plain C into the chain (s0 + s1) + s2, one add
+  // deeper on the critical path
+#if defined(__CUDA_ARCH__)
+  u32 g3;
+  asm("{\n\t.reg .u32 t;\n\tadd.u32 t, %1, %3;\n\tadd.u32 %0, t, %2;\n\t}" : "=r"(g3) : "r"(s[0]), "r"(s[1]), "r"(s[2]));
+#else
+  const u32 g3 = (s[0] + s[2]) + s[1];
+#endif
+  const u32 D = g3 + g3 + (s[3] + s[3]);     // 2 T_q, two adds deep like T itself
   const u32 s31 = w.shfl(s[3], 7u);          // old s[31]
   const u32 z0 = w.shfl(s[0], 0u);           // s[0]
   const u32 n0 = s31 + w.shfl(e0, 0u);       // s'[0] = s[31] + s[0] + s[1]
   const u32 nxt0 = w.shfl(s[0], (q + 1u) & 7u);   // s[4q+4]
   u32 a[7];
 #pragma unroll
-  for (int m = 0; m < 7; m++) {
-    const u32 tm = w.shfl(T, (u32)m);
-    a[m] = q > (u32)m ? tm : 0u;
-  }
-  const u32 lower = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + a[6]);   // a tree: three dependent adds, not seven
+  for (int d = 1; d <= 7; d++) a[d - 1] = w.shfl(D, q >= (u32)d ? q - (u32)d : q);
   const u32 P0 = e0, P1 = P0 + (s[1] + s[2]), P2 = P1 + (s[2] + s[3]);
-  const u32 O = s31 + 2u * lower - z0 + s[0];
-  const u32 last = q == 7u ? s31 + n0 + (O + P2) : O + P2 + s[3] + nxt0;   // lane 7: s'[31] = s[31] + s'[0] + s'[30]
-  s[0] = O + P0, s[1] = O + P1, s[2] = O + P2, s[3] = last;
+  const u32 base = s31 - z0 + s[0] - (7u - q) * D;
+  const u32 C0 = base + P0, C1 = base + P1, C2 = base + P2;
+  // lane 7: s'[31] = s[31] + s'[0] + s'[30]
+  const u32 C3 = q == 7u ? C2 + s31 + n0 : C2 + s[3] + nxt0;
+  const u32 x = a[0] + a[1] + a[2], y = a[3] + a[4] + a[5];
+  s[0] = (C0 + x) + y + a[6], s[1] = (C1 + x) + y + a[6], s[2] = (C2 + x) + y + a[6], s[3] = (C3 + x) + y + a[6];
 }
 template <class W>
 HS_HD void settle(const W &, Oct &st) {
