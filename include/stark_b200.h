@@ -261,7 +261,9 @@ int stark_prove_trace_rows(stark_ctx *ctx, const void *rows_i128, uint32_t n_col
  * (no exchange), Merkle trees split by leaf range (MerkleTree::new, merkle.rs:11-38: the ranks' subtree roots are
  * exchanged and the top levels replicated), fold_codeword split by output range (fri.rs:57-91: every rank stores its
  * slice into all replicas of the next codeword).  The library owns the NCCL communicator (loaded with dlopen) and the
- * peer-memory windows; a host in any language drives it through these calls.
+ * peer-memory windows; a host in any language drives it through these calls.  A stark_mgpu_* call makes the ranks' devices
+ * current while it runs and leaves the calling thread on the device it was on (single-context calls do NOT switch
+ * devices: a thread that uses contexts on different devices in turn calls stark_ctx_make_current, above).
  *
  * A stark_mgpu is ONE RANK's membership in a group of `world` (1, 2, 4 or 8) GPUs.  Two ways to make a group:
  *   stark_mgpu_init          one process or thread per GPU.  Rank 0 calls stark_mgpu_unique_id and hands the 128 bytes

@@ -2026,6 +2026,7 @@ static int mg_check_ranks(stark_mgpu *const *ranks, int n_here) {
 int stark_mgpu_prove_trace(stark_mgpu *const *ranks, int n_here, const uint64_t *cols, uint32_t n_cols, uint32_t log_n,
                            uint32_t log_blowup, uint64_t offset, uint32_t nq, uint8_t *const *column_roots,
                            uint8_t *const *proofs, size_t proof_cap, size_t *proof_len) {
+  MgDeviceScope restore_device;
   ST_TRY(mg_check_ranks(ranks, n_here));
   if (!cols) return stark_fail(ranks[0]->ctx, STARK_ERR_ARG, "null argument");
   return mg_prove_trace_impl(ranks, n_here, cols, nullptr, n_cols, log_n, log_blowup, offset, nq, column_roots, proofs, proof_cap, proof_len);
@@ -2033,6 +2034,7 @@ int stark_mgpu_prove_trace(stark_mgpu *const *ranks, int n_here, const uint64_t 
 int stark_mgpu_prove_trace_dev(stark_mgpu *const *ranks, int n_here, const stark_buf *const *my_cols, uint32_t n_cols,
                                uint32_t log_n, uint32_t log_blowup, uint64_t offset, uint32_t nq,
                                uint8_t *const *column_roots, uint8_t *const *proofs, size_t proof_cap, size_t *proof_len) {
+  MgDeviceScope restore_device;
   ST_TRY(mg_check_ranks(ranks, n_here));
   if (!my_cols) return stark_fail(ranks[0]->ctx, STARK_ERR_ARG, "null argument");
   return mg_prove_trace_impl(ranks, n_here, nullptr, my_cols, n_cols, log_n, log_blowup, offset, nq, column_roots, proofs, proof_cap, proof_len);
@@ -2042,6 +2044,7 @@ int stark_mgpu_fri_prove_dev(stark_mgpu *const *ranks, int n_here, const stark_b
                              size_t domain_length, uint64_t offset, uint64_t omega, uint32_t ef, uint32_t nq,
                              const uint8_t *transcript, size_t transcript_len, uint8_t *const *proofs, size_t proof_cap,
                              size_t *proof_len, uint64_t *const *top_indices) {
+  MgDeviceScope restore_device;
   ST_TRY(mg_check_ranks(ranks, n_here));
   if (!codewords || !proofs) return stark_fail(ranks[0]->ctx, STARK_ERR_ARG, "null argument");
   u32 off, om;
@@ -2076,6 +2079,7 @@ int stark_mgpu_fri_prove_dev(stark_mgpu *const *ranks, int n_here, const stark_b
 int stark_mgpu_fold_commit_round(stark_mgpu *const *ranks, int n_here, const stark_buf *const *codewords, size_t n,
                                  uint64_t offset, uint64_t omega, uint8_t *const *roots, uint64_t *alpha_raw,
                                  stark_buf **folded) {
+  MgDeviceScope restore_device;
   ST_TRY(mg_check_ranks(ranks, n_here));
   if (!codewords) return stark_fail(ranks[0]->ctx, STARK_ERR_ARG, "null argument");
   u32 off, om;
@@ -2086,6 +2090,7 @@ int stark_mgpu_fold_commit_round(stark_mgpu *const *ranks, int n_here, const sta
 int stark_mgpu_lde_commit(stark_mgpu *const *ranks, int n_here, const uint64_t *cols, uint32_t n_groups, uint32_t group_width,
                           uint32_t log_n, uint32_t log_blowup, uint64_t offset, uint8_t *const *group_roots,
                           uint8_t *const *commitments) {
+  MgDeviceScope restore_device;
   ST_TRY(mg_check_ranks(ranks, n_here));
   if (!cols) return stark_fail(ranks[0]->ctx, STARK_ERR_ARG, "null argument");
   return mg_lde_commit_impl(ranks, n_here, cols, nullptr, n_groups, group_width, log_n, log_blowup, offset, group_roots, commitments);
@@ -2093,6 +2098,7 @@ int stark_mgpu_lde_commit(stark_mgpu *const *ranks, int n_here, const uint64_t *
 int stark_mgpu_lde_commit_dev(stark_mgpu *const *ranks, int n_here, const stark_buf *const *owned_groups, uint32_t n_groups,
                               uint32_t group_width, uint32_t log_n, uint32_t log_blowup, uint64_t offset,
                               uint8_t *const *group_roots, uint8_t *const *commitments) {
+  MgDeviceScope restore_device;
   ST_TRY(mg_check_ranks(ranks, n_here));
   if (!owned_groups) return stark_fail(ranks[0]->ctx, STARK_ERR_ARG, "null argument");
   return mg_lde_commit_impl(ranks, n_here, nullptr, owned_groups, n_groups, group_width, log_n, log_blowup, offset, group_roots, commitments);

@@ -278,6 +278,7 @@ struct PeerRecord {
 
 int stark_mgpu_init(stark_ctx *ctx, const uint8_t id[STARK_MGPU_ID_BYTES], int rank, int world, size_t max_codeword,
                     stark_mgpu **out) {
+  MgDeviceScope restore_device;
   if (!ctx || !id || !out) return stark_fail(ctx, STARK_ERR_ARG, "null argument");
   if (!pow2_world(world) || rank < 0 || rank >= world)
     return stark_fail(ctx, STARK_ERR_ARG, "world size must be 1, 2, 4 or 8 and 0 <= rank < world");
@@ -351,6 +352,7 @@ int stark_mgpu_init(stark_ctx *ctx, const uint8_t id[STARK_MGPU_ID_BYTES], int r
 }
 
 int stark_mgpu_create_local(stark_ctx *const *ctxs, int world, size_t max_codeword, stark_mgpu **out) {
+  MgDeviceScope restore_device;
   if (!ctxs || !out) return stark_fail(nullptr, STARK_ERR_ARG, "null argument");
   if (!pow2_world(world)) return stark_fail(nullptr, STARK_ERR_ARG, "world size must be 1, 2, 4 or 8");
   stark_mgpu **group = new stark_mgpu *[world];
@@ -396,6 +398,7 @@ int stark_mgpu_create_local(stark_ctx *const *ctxs, int world, size_t max_codewo
 }
 
 void stark_mgpu_destroy(stark_mgpu *m) {
+  MgDeviceScope restore_device;
   if (!m) return;
   cudaSetDevice(m->ctx->device);
   cudaStreamSynchronize(m->ctx->stream);
@@ -436,6 +439,7 @@ int stark_mgpu_set_shard_log(stark_mgpu *m, uint32_t log_n) {
 
 // device-side barrier over the group followed by a host synchronisation of this rank's stream
 int stark_mgpu_barrier(stark_mgpu *m) {
+  MgDeviceScope restore_device;
   if (!m) return stark_fail(nullptr, STARK_ERR_ARG, "null argument");
   if (m->mode == MG_LOCAL) {
     stark_mgpu **G = m->group;

@@ -70,6 +70,16 @@ enum { MG_X_FUSED = 0, MG_X_SIGNAL = 1, MG_X_WAIT = 2 };
 // ---- host helpers (mgpu.cu)
 // one host thread may drive ranks on several devices: make the rank's device current before queueing its work
 static inline void mg_use(const stark_mgpu *m) { cudaSetDevice(m->ctx->device); }
+// Group calls walk over the ranks of a one-process group and make each rank's device current in turn: the device that was
+// current when the caller entered is current again when it gets its answer (a caller that goes on with a single-GPU
+// call on another context must not find itself on the last rank's device).
+struct MgDeviceScope {
+  int dev = -1;
+  MgDeviceScope() { if (cudaGetDevice(&dev) != cudaSuccess) dev = -1; }
+  MgDeviceScope(const MgDeviceScope &) = delete;
+  MgDeviceScope &operator=(const MgDeviceScope &) = delete;
+  ~MgDeviceScope() { if (dev >= 0) cudaSetDevice(dev); }
+};
 static inline u32 *mg_flags(const stark_mgpu *m, int g, int kind) {
   return reinterpret_cast<u32 *>(m->peer[g] + m->L.flags) + kind * MG_MAX_RANKS;
 }

@@ -226,7 +226,7 @@ def test_peer_group_one_process(S, par_oracle, world):
             b.free()
     finally:
         g.close()
-        for c in ctxs:
+        for c in reversed(ctxs):     # device 0 is current again when the test leaves (the module's `ctx` lives there)
             c.make_current()
             c.close()
 
