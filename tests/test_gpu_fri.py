@@ -34,6 +34,28 @@ def test_fold_large_vs_closed_form(ctx, oracle, log_n):
     assert np.array_equal(ctx.fri_fold(cw, alpha, 3, w), oracle.fast_fri_fold(cw, alpha, 3, w))
 
 
+def test_alignment_contract(ctx, oracle, S):
+    """include/stark_b200.h, ALIGNMENT: a wrapped device pointer must be 16-byte aligned (the kernels use 128-bit accesses)
+    and is rejected as an argument error, not left to raise a sticky misaligned-address fault; an output VIEW at an odd
+    element offset is legal and takes the scalar path of the fold"""
+    n = 1 << 12
+    w = oracle.ff_prim_nth_root(n)
+    cw = rf(77, n)
+    src = ctx.upload(cw)
+    with pytest.raises(S.StarkPanic, match="16-byte aligned"):
+        ctx.wrap(src.ptr + 4, n - 1)
+    view = ctx.wrap(src.ptr + 16, n - 4)                       # an aligned view is fine
+    assert np.array_equal(view.download(), cw[4:])
+    want = oracle.fri_fold(cw, 12345, 3, w)
+    for out_off, i0, cnt in ((1, 0, n // 2), (3, 4, 100), (2, 1, 7), (0, 0, n // 2)):
+        out = ctx.alloc(n // 2 + 8)
+        ctx.fri_fold_range_dev(src, n, 12345, 3, w, i0, cnt, out, out_off)
+        assert np.array_equal(out.download(out_off, cnt), want[i0:i0 + cnt]), (out_off, i0, cnt)
+        out.free()
+    assert np.array_equal(ctx.fri_fold(cw, 12345, 3, w), want)    # the context is still healthy
+    src.free()
+
+
 def test_fold_degenerate_domain(ctx, oracle, S):
     """Fri::new never checks omega's order (fri.rs:30-55): the fold is a pure function of its inputs"""
     cw = rf(1, 256)
