@@ -367,25 +367,23 @@ HS_HD void leaf2(u32 va, u32 vb, u32 *oa, u32 *ob, u32 one) {
 //   absorb (hash.rs:15-20): byte i xors into byte i+7, i.e. lane q's byte j depends on lane q-1's byte j+1 (and byte 7 on
 //   the lane's own byte 0), so the four lanes absorb in four phases; lane 3's bytes 1..7 wrap into lane 0's bytes 0..6.
 // Bytes are lazy as in hs (garbage above bit 7).  All 32 lanes of a warp must call these functions together.
-#if defined(__CUDACC__)
 namespace hsq {
 using hs::u32;
 
+// Like hso, written over a lane-group interface W { u32 q; u32 shfl(u32 v, u32 src_lane_of_the_quad); } so that
+// tests/emul/hash_emul.cpp can run the four lanes as four host threads against the oracle.
 struct Quad {
   u32 s[8];
   u32 rc[8];      // round constants of this lane's bytes
   u32 rc251[8];   // (rc * 251) & 0xff: the pending constants folded into the next sbox multiply (see hs::mix_lazy)
-  u32 q, base;    // lane within the quad, warp lane of the quad's lane 0
 };
-__device__ __forceinline__ u32 shfl(u32 v, u32 lane) { return __shfl_sync(0xffffffffu, v, lane); }
 
 // lane-dependent constants without lane-indexed constant-memory loads (those serialise per distinct address):
 // the four lanes' byte rows are packed into words and picked with selects
-__device__ __forceinline__ u32 pick4(u32 q, u32 a, u32 b, u32 c, u32 d) { return q < 2 ? (q == 0 ? a : b) : (q == 2 ? c : d); }
-__device__ __forceinline__ void init(Quad &st) {
-  const u32 lane = threadIdx.x & 31u;
-  const u32 q = lane & 3u;
-  st.q = q, st.base = lane & ~3u;
+HS_HD u32 pick4(u32 q, u32 a, u32 b, u32 c, u32 d) { return q < 2 ? (q == 0 ? a : b) : (q == 2 ? c : d); }
+template <class W>
+HS_HD void init(const W &w, Quad &st) {
+  const u32 q = w.q;
   constexpr u32 pr[16] = HS_PRIMES;
   constexpr u32 rc[32] = HS_RC;
 #pragma unroll
@@ -414,14 +412,18 @@ __device__ __forceinline__ void init(Quad &st) {
     }
   }
 }
-__device__ __forceinline__ u32 mad2(u32 x, u32 c) {   // 2 x + c, opaque to the re-association passes
+HS_HD u32 mad2(u32 x, u32 c) {   // 2 x + c, opaque to the re-association passes
+#if defined(__CUDA_ARCH__)
   u32 r;
   asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(r) : "r"(x), "r"(c));
   return r;
+#else
+  return 2u * x + c;
+#endif
 }
 // mix_state without its final round-constant add (left pending, as hs::mix_lazy)
-template <bool PENDING>
-__device__ __forceinline__ void mix_lazy(Quad &st) {
+template <bool PENDING, class W>
+HS_HD void mix_lazy(const W &w, Quad &st) {
   u32 *s = st.s;
 #pragma unroll
   for (int j = 0; j < 8; j++) s[j] = hs::rotl_lazy(s[j] * 251u + (PENDING ? st.rc251[j] : 0u), 1);
@@ -442,16 +444,16 @@ __device__ __forceinline__ void mix_lazy(Quad &st) {
   // lanes q-1 .. q-3 and, where that runs off the quad, from ITSELF (no selects; the 3 - q surplus copies of T_q come out
   // of the early constant), and s[31], s[0], the in-lane prefixes and the surplus are folded into C_j while the shuffles
   // are in flight: s'[j] = C_j + 2 (a1 + a2 + a3).
-  const u32 q = st.q;
+  const u32 q = w.q;
   const u32 e0 = s[0] + s[1];
   const u32 T = (s[0] + s[1] + s[2]) + (s[3] + s[4] + s[5]) + (s[6] + s[7]);
-  const u32 s31 = shfl(s[7], st.base + 3u);                                       // old s[31]
-  const u32 z0 = shfl(s[0], st.base);                                             // s[0]
-  const u32 n0 = s31 + shfl(e0, st.base);                                         // s'[0] = s[31] + s[0] + s[1]
-  const u32 nxt0 = shfl(s[0], st.base + ((q + 1u) & 3u));                         // s[8q+8] (lanes 0..2)
-  const u32 a1 = shfl(T, st.base + (q >= 1u ? q - 1u : q));
-  const u32 a2 = shfl(T, st.base + (q >= 2u ? q - 2u : q));
-  const u32 a3 = shfl(T, st.base + (q >= 3u ? q - 3u : q));
+  const u32 s31 = w.shfl(s[7], 3u);                                       // old s[31]
+  const u32 z0 = w.shfl(s[0], 0u);                                             // s[0]
+  const u32 n0 = s31 + w.shfl(e0, 0u);                                         // s'[0] = s[31] + s[0] + s[1]
+  const u32 nxt0 = w.shfl(s[0], (q + 1u) & 3u);                         // s[8q+8] (lanes 0..2)
+  const u32 a1 = w.shfl(T, q >= 1u ? q - 1u : q);
+  const u32 a2 = w.shfl(T, q >= 2u ? q - 2u : q);
+  const u32 a3 = w.shfl(T, q >= 3u ? q - 3u : q);
   u32 P[7];
   P[0] = e0;
 #pragma unroll
@@ -466,15 +468,17 @@ __device__ __forceinline__ void mix_lazy(Quad &st) {
   for (int j = 0; j < 7; j++) s[j] = mad2(x, c + P[j]);
   s[7] = mad2(x, clast);
 }
-__device__ __forceinline__ void settle(Quad &st) {
+HS_HD void settle(Quad &st) {
 #pragma unroll
   for (int j = 0; j < 8; j++) st.s[j] += st.rc[j];
 }
-template <bool PENDING>
-__device__ __forceinline__ void finalize(Quad &st) {
-  mix_lazy<PENDING>(st);
+template <bool PENDING, class W>
+HS_HD void finalize(const W &w, Quad &st) {
+  mix_lazy<PENDING>(w, st);
+#if defined(__CUDA_ARCH__)
 #pragma unroll 1
-  for (int k = 0; k < 7; k++) mix_lazy<true>(st);
+#endif
+  for (int k = 0; k < 7; k++) mix_lazy<true>(w, st);
   settle(st);
 }
 // absorb a full 32-byte chunk m[0..8) (little-endian words; EVERY lane holds the whole chunk), then mix.
@@ -483,16 +487,16 @@ __device__ __forceinline__ void finalize(Quad &st) {
 // measured 560-620 cycles per chunk for lane-phased and Jacobi-sweep variants).  So the quad all-gathers its state
 // (two packed words per lane, 8 shuffles), every lane runs the same serial absorb on the full state, and keeps its own
 // eight bytes.
-template <bool PENDING>
-__device__ __forceinline__ void absorb_mix(Quad &st, const u32 *m) {
+template <bool PENDING, class W>
+HS_HD void absorb_mix(const W &w, Quad &st, const u32 *m) {
   if (PENDING) settle(st);
   u32 *s = st.s;
-  const u32 w0 = __byte_perm(__byte_perm(s[0], s[1], 0x0040), __byte_perm(s[2], s[3], 0x0040), 0x5410);
-  const u32 w1 = __byte_perm(__byte_perm(s[4], s[5], 0x0040), __byte_perm(s[6], s[7], 0x0040), 0x5410);
+  const u32 w0 = hs2::prmt(hs2::prmt(s[0], s[1], 0x0040), hs2::prmt(s[2], s[3], 0x0040), 0x5410);
+  const u32 w1 = hs2::prmt(hs2::prmt(s[4], s[5], 0x0040), hs2::prmt(s[6], s[7], 0x0040), 0x5410);
   u32 S[32];
 #pragma unroll
   for (int l = 0; l < 4; l++) {
-    const u32 a = shfl(w0, st.base + l), b = shfl(w1, st.base + l);
+    const u32 a = w.shfl(w0, (u32)l), b = w.shfl(w1, (u32)l);
 #pragma unroll
     for (int j = 0; j < 4; j++) S[8 * l + j] = a >> (8 * j), S[8 * l + 4 + j] = b >> (8 * j);   // lazy bytes
   }
@@ -503,30 +507,57 @@ __device__ __forceinline__ void absorb_mix(Quad &st, const u32 *m) {
     S[(i + 7) & 31] ^= v;
   }
 #pragma unroll
-  for (int j = 0; j < 8; j++) s[j] = pick4(st.q, S[j], S[8 + j], S[16 + j], S[24 + j]);
-  mix_lazy<false>(st);
+  for (int j = 0; j < 8; j++) s[j] = pick4(w.q, S[j], S[8 + j], S[16 + j], S[24 + j]);
+  mix_lazy<false>(w, st);
 }
 // Hash::combine (hash.rs:41-46) of the 32-byte hashes at `left` and `right`; every lane of the quad returns its own
 // 8 output bytes as two little-endian words (lane q: bytes 8q .. 8q+7)
-__device__ __forceinline__ void combine(const uint8_t *left, const uint8_t *right, u32 &o0, u32 &o1) {
+template <class W>
+HS_HD void combine(const W &w, const uint8_t *left, const uint8_t *right, u32 &o0, u32 &o1) {
   Quad st;
-  init(st);
+  init(w, st);
+#if defined(__CUDA_ARCH__)
 #pragma unroll 1
+#endif
   for (int c = 0; c < 2; c++) {   // one copy of absorb + mix for both chunks (code size, see hs::combine)
     if (c) settle(st);
+#if defined(__CUDA_ARCH__)
     const uint4 x = reinterpret_cast<const uint4 *>(c ? right : left)[0], y = reinterpret_cast<const uint4 *>(c ? right : left)[1];
     const u32 m[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
-    absorb_mix<false>(st, m);
+#else
+    u32 m[8];
+    for (int i = 0; i < 8; i++) {
+      const uint8_t *b = (c ? right : left) + 4 * i;
+      m[i] = (u32)b[0] | ((u32)b[1] << 8) | ((u32)b[2] << 16) | ((u32)b[3] << 24);
+    }
+#endif
+    absorb_mix<false>(w, st, m);
   }
+#if defined(__CUDA_ARCH__)
 #pragma unroll 1
-  for (int k = 0; k < 8; k++) mix_lazy<true>(st);
+#endif
+  for (int k = 0; k < 8; k++) mix_lazy<true>(w, st);
   settle(st);
   const u32 *s = st.s;
-  o0 = __byte_perm(__byte_perm(s[0], s[1], 0x0040), __byte_perm(s[2], s[3], 0x0040), 0x5410);
-  o1 = __byte_perm(__byte_perm(s[4], s[5], 0x0040), __byte_perm(s[6], s[7], 0x0040), 0x5410);
+  o0 = hs2::prmt(hs2::prmt(s[0], s[1], 0x0040), hs2::prmt(s[2], s[3], 0x0040), 0x5410);
+  o1 = hs2::prmt(hs2::prmt(s[4], s[5], 0x0040), hs2::prmt(s[6], s[7], 0x0040), 0x5410);
 }
-}  // namespace hsq
+#if defined(__CUDACC__)
+// the lane group on the device: four adjacent lanes of a warp (ALL 32 lanes of the warp must execute the calls)
+struct Dev {
+  u32 q, base;
+  __device__ __forceinline__ Dev() {
+    const u32 lane = threadIdx.x & 31u;
+    q = lane & 3u, base = lane & ~3u;
+  }
+  __device__ __forceinline__ u32 shfl(u32 v, u32 src) const { return __shfl_sync(0xffffffffu, v, base + src); }
+};
+__device__ __forceinline__ void combine(const uint8_t *left, const uint8_t *right, u32 &o0, u32 &o1) {
+  const Dev w;
+  combine(w, left, right, o0, o1);
+}
 #endif
+}  // namespace hsq
 
 // =====================================================================================================
 // hso -- ONE hash on EIGHT adjacent lanes (lane q holds state bytes 4q .. 4q+3), for the steps where the latency of one

@@ -61,10 +61,11 @@ static int dummy_hs2 = check_hs2();
 #include <atomic>
 #include <thread>
 struct EmuBarrier {
+  int lanes = 8;
   std::atomic<int> count{0}, gen{0};
   void wait() {
     const int g = gen.load();
-    if (count.fetch_add(1) + 1 == 8) { count.store(0); gen.fetch_add(1); }
+    if (count.fetch_add(1) + 1 == lanes) { count.store(0); gen.fetch_add(1); }
     else while (gen.load() == g) std::this_thread::yield();
   }
 };
@@ -106,3 +107,46 @@ static int check_hso() {
   return fails;
 }
 static int dummy_hso = check_hso();
+// ---- hsq (one hash on four lanes, eight state bytes each): four host threads
+struct EmuQuad {
+  uint32_t q;
+  uint32_t *slots;
+  EmuBarrier *bar;
+  uint32_t shfl(uint32_t v, uint32_t src) const {
+    slots[q] = v;
+    bar->wait();
+    const uint32_t r = slots[src & 3u];
+    bar->wait();
+    return r;
+  }
+};
+static int check_hsq() {
+  int fails = 0;
+  uint64_t s = 424242;
+  auto rnd = [&]() { s = s * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)(s >> 32); };
+  for (int it = 0; it < 200; it++) {
+    alignas(16) uint32_t l[8], r[8];
+    uint8_t want[32], got[32];
+    for (int i = 0; i < 8; i++) l[i] = rnd(), r[i] = rnd();
+    if (it == 0) for (int i = 0; i < 8; i++) l[i] = r[i] = 0xffffffffu;
+    if (it == 1) for (int i = 0; i < 8; i++) l[i] = r[i] = 0;
+    oracle_hash_combine((uint8_t *)l, (uint8_t *)r, want);
+    uint32_t slots[4];
+    EmuBarrier bar;
+    bar.lanes = 4;
+    std::thread th[4];
+    for (uint32_t q = 0; q < 4; q++)
+      th[q] = std::thread([&, q]() {
+        EmuQuad w{q, slots, &bar};
+        uint32_t o0, o1;
+        hsq::combine(w, (const uint8_t *)l, (const uint8_t *)r, o0, o1);
+        memcpy(got + 8 * q, &o0, 4);
+        memcpy(got + 8 * q + 4, &o1, 4);
+      });
+    for (auto &t : th) t.join();
+    if (memcmp(got, want, 32)) { fails++; if (fails < 3) printf("hsq combine mismatch it=%d\n", it); }
+  }
+  printf(fails ? "hsq FAIL %d\n" : "hsq OK\n", fails);
+  return fails;
+}
+static int dummy_hsq = check_hsq();

@@ -32,12 +32,12 @@ def test_multi_pass_ntt_emulation(tmp_path):
 
 def test_hash_forms_on_host_vs_oracle(tmp_path, oracle):
     """hash.cuh is host+device inline: the one-hash (hs) and two-hashes-per-thread (hs2, lane 1 in bits 24-31) forms
-    are compared with the oracle on the CPU for random and all-ones inputs; so is the 8-lanes-per-hash form (hso), its eight
-    lanes running as eight host threads with shuffles emulated through a shared slot array (the 4-lane form hsq is
-    device-only and covered by the GPU tree tests)."""
+    are compared with the oracle on the CPU for random and all-ones inputs; so are the
+    8-lanes-per-hash form (hso) and the 4-lanes-per-hash form (hsq), their lanes running as eight / four host threads with
+    shuffles emulated through a shared slot array."""
     exe = str(tmp_path / "hash_emul")
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-I", os.path.join(ROOT, "stark-rs_b200", "csrc"),
                            os.path.join(ROOT, "tests", "emul", "hash_emul.cpp"), os.path.join(ROOT, "oracle", "liboracle.so"),
                            "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-o", exe])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0 and "hs2 OK" in out.stdout and "hso OK" in out.stdout and "\nOK" in out.stdout, out.stdout + out.stderr
+    assert out.returncode == 0 and "hs2 OK" in out.stdout and "hso OK" in out.stdout and "hsq OK" in out.stdout and "\nOK" in out.stdout, out.stdout + out.stderr
